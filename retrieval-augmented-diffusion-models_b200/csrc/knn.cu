@@ -1,0 +1,555 @@
+// Exact cosine top-k over an in-HBM CLIP database (K1/K11 of SURVEY.md section 2.1).
+//
+// Pipeline per query batch (all stream-ordered, no host sync):
+//   1. knn_scan_kernel   -- ONE pass over the database: coalesced 16-byte streaming loads, fp32 FMA dot
+//                           products against up to 16 queries held in shared memory, transposing
+//                           warp-shuffle reduction, threshold filter, per-CTA top-32 candidate lists.
+//                           HBM-bound: algorithmic bytes = n * d * sizeof(elem) (+4 B/row inverse norm).
+//   2. knn_select_kernel -- merges the per-CTA lists (warp bitonic networks), then RE-RANKS the 32 best
+//                           candidates of every query with the exact definition of oracle/knn_ref.c
+//                           (sequential fp64, separately rounded products) and emits the top-k by
+//                           (score desc, index asc).  The fp32 scan only has to put the true top-k among
+//                           its 32 candidates (margin >= 8 for k <= 24; fp32 dot error ~1e-7).
+// Replaces ScaNN behind `searcher.search_batched` (dsetbuilder.py:490, ddpm.py:906-908).
+#include "common.cuh"
+#include "../../include/rdm_b200.h"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int LIST = 32;          // candidates kept per query (one per lane)
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int MAX_QP = 16;        // queries per scan pass
+constexpr unsigned FULL = 0xffffffffu;
+typedef unsigned long long u64;
+
+__device__ __forceinline__ uint32_t order_f32(float f) {
+    uint32_t b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float unorder_f32(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+}
+// larger key = better candidate: higher score first, then LOWER row index
+__device__ __forceinline__ u64 make_key(float s, uint32_t idx) { return ((u64)order_f32(s) << 32) | (u64)(0xffffffffu - idx); }
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static constexpr int EPV = 4;
+    __device__ static __forceinline__ void unpack(const uint4& v, float* o) {
+        o[0] = __uint_as_float(v.x); o[1] = __uint_as_float(v.y); o[2] = __uint_as_float(v.z); o[3] = __uint_as_float(v.w);
+    }
+    __device__ static __forceinline__ float to_f32(float v) { return v; }
+};
+template <> struct Elem<__half> {
+    static constexpr int EPV = 8;
+    __device__ static __forceinline__ void unpack(const uint4& v, float* o) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            o[2 * i] = f.x; o[2 * i + 1] = f.y;
+        }
+    }
+    __device__ static __forceinline__ float to_f32(__half v) { return __half2float(v); }
+};
+
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m) {
+    uint32_t lo = __shfl_xor_sync(FULL, (uint32_t)v, m), hi = __shfl_xor_sync(FULL, (uint32_t)(v >> 32), m);
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u64 warp_min_u64(u64 v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { u64 o = shfl_xor_u64(v, m); v = o < v ? o : v; }
+    return v;
+}
+// ascending bitonic sort of one key per lane
+__device__ __forceinline__ u64 warp_sort_asc(u64 v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            u64 o = shfl_xor_u64(v, j);
+            bool asc = (lane & k) == 0, lower = (lane & j) == 0;
+            bool keep_min = (asc == lower);
+            v = keep_min ? (o < v ? o : v) : (o > v ? o : v);
+        }
+    }
+    return v;
+}
+// cur: descending-sorted (lane 0 best); batch: arbitrary.  Returns descending-sorted top-32 of the union.
+__device__ __forceinline__ u64 warp_merge_top32(u64 cur, u64 batch, int lane) {
+    u64 b = warp_sort_asc(batch, lane);
+    u64 v = cur > b ? cur : b;                 // half-cleaner of the bitonic sequence (batch asc | cur desc)
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {         // bitonic merge, descending
+        u64 o = shfl_xor_u64(v, j);
+        bool lower = (lane & j) == 0;
+        v = lower ? (o > v ? o : v) : (o < v ? o : v);
+    }
+    return v;
+}
+
+// Transposing reduction: R per-lane partial sums -> the complete sum of row `rsel(lane)` in lane groups.
+template <int R> __device__ __forceinline__ float reduce_rows(float (&acc)[R], int lane) {
+    int width = 16;
+#pragma unroll
+    for (int cnt = R; cnt > 1; cnt >>= 1, width >>= 1) {
+        const bool upper = (lane & width) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt / 2; i++) {
+            float send = upper ? acc[i] : acc[i + cnt / 2];
+            float keep = upper ? acc[i + cnt / 2] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(FULL, send, width);
+        }
+    }
+    float t = acc[0];
+    for (; width >= 1; width >>= 1) t += __shfl_xor_sync(FULL, t, width);
+    return t;
+}
+template <int R> __device__ __forceinline__ int row_of_lane(int lane) {
+    int r = 0, width = 16;
+#pragma unroll
+    for (int cnt = R; cnt > 1; cnt >>= 1, width >>= 1) if (lane & width) r += cnt / 2;
+    return r;
+}
+
+struct ScanShared {
+    u64 list[MAX_QP][LIST];
+    float thr[MAX_QP];
+    int lock[MAX_QP];
+};
+
+// Warp-uniform insertion of `key` into the CTA-wide list of query `q` (rare path: ~LIST*ln(rows/LIST) times per CTA).
+__device__ __noinline__ void list_insert(ScanShared* sh, int q, u64 key, int lane) {
+    if (lane == 0) { while (atomicCAS(&sh->lock[q], 0, 1) != 0) {} }
+    __syncwarp();
+    __threadfence_block();
+    volatile u64* lst = sh->list[q];
+    u64 mine = lst[lane];
+    u64 mn = warp_min_u64(mine);
+    if (key > mn) {
+        unsigned who = __ballot_sync(FULL, mine == mn);
+        if (lane == __ffs(who) - 1) { lst[lane] = key; mine = key; }
+        u64 mn2 = warp_min_u64(mine);
+        if (lane == 0) *(volatile float*)&sh->thr[q] = (mn2 == 0ull) ? -CUDART_INF_F : unorder_f32((uint32_t)(mn2 >> 32));
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicExch(&sh->lock[q], 0);
+    __syncwarp();
+}
+
+template <typename T, int D, int QP, int R>
+__global__ void __launch_bounds__(SCAN_THREADS)
+knn_scan_kernel(const T* __restrict__ db, const float* __restrict__ inv, long long n,
+                const float* __restrict__ q, int nq_valid, u64* __restrict__ lists_out) {
+    constexpr int EPL = D / 32;              // elements per lane per row
+    constexpr int EPV = Elem<T>::EPV;        // elements per 16-byte vector
+    constexpr int NV = EPL / EPV;            // vectors per lane per row
+    constexpr int NC = EPL / 4;              // float4 query chunks per lane
+    static_assert(EPL % EPV == 0 && EPL % 4 == 0, "row width");
+    extern __shared__ float4 smem_q[];       // [QP][NC][32], permuted so lane l reads consecutive float4s
+    __shared__ ScanShared sh;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < QP * NC * 32; i += SCAN_THREADS) {
+        int l = i & 31, c = (i >> 5) % NC, qi = i / (32 * NC);
+        float v[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            int j = 4 * c + t, vv = j / EPV, s = j % EPV;
+            int e = vv * 32 * EPV + l * EPV + s;
+            v[t] = qi < nq_valid ? q[(size_t)qi * D + e] : 0.f;
+        }
+        smem_q[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    for (int i = tid; i < MAX_QP * LIST; i += SCAN_THREADS) sh.list[i / LIST][i % LIST] = 0ull;
+    if (tid < MAX_QP) { sh.thr[tid] = -CUDART_INF_F; sh.lock[tid] = 0; }
+    __syncthreads();
+
+    const int rsel = row_of_lane<R>(lane);
+    const bool owner = (lane & (32 / R - 1)) == 0;
+    const long long ngroups = (n + R - 1) / R;
+    for (long long g = (long long)blockIdx.x * SCAN_WARPS + warp; g < ngroups; g += (long long)gridDim.x * SCAN_WARPS) {
+        const long long row0 = g * R;
+        uint4 raw[R][NV];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            long long row = row0 + r; row = row < n ? row : n - 1;
+            const uint4* p = reinterpret_cast<const uint4*>(db + (size_t)row * D);
+#pragma unroll
+            for (int v = 0; v < NV; v++) raw[r][v] = ldg_stream(p + v * 32 + lane);
+        }
+        const long long myrow = row0 + rsel;
+        const bool valid = owner && myrow < n;
+        const float myinv = valid ? __ldg(inv + myrow) : 0.f;
+        float x[R][EPL];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int v = 0; v < NV; v++) Elem<T>::unpack(raw[r][v], &x[r][v * EPV]);
+
+#pragma unroll
+        for (int qi = 0; qi < QP; qi++) {
+            float acc[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[r] = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const float4 qv = smem_q[(qi * NC + c) * 32 + lane];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    acc[r] = fmaf(x[r][4 * c + 0], qv.x, acc[r]);
+                    acc[r] = fmaf(x[r][4 * c + 1], qv.y, acc[r]);
+                    acc[r] = fmaf(x[r][4 * c + 2], qv.z, acc[r]);
+                    acc[r] = fmaf(x[r][4 * c + 3], qv.w, acc[r]);
+                }
+            }
+            float s = reduce_rows<R>(acc, lane) * myinv;
+            if (!(s == s)) s = -CUDART_INF_F;
+            const float thr = *(volatile float*)&sh.thr[qi];
+            unsigned m = __ballot_sync(FULL, valid && qi < nq_valid && s >= thr);
+            while (m) {
+                int src = __ffs(m) - 1; m &= m - 1;
+                float cs = __shfl_sync(FULL, s, src);
+                uint32_t ci = __shfl_sync(FULL, (uint32_t)myrow, src);
+                u64 key = make_key(cs, ci);
+                float tnow = __shfl_sync(FULL, *(volatile float*)&sh.thr[qi], 0);     // warp-uniform re-check
+                if (cs >= tnow) list_insert(&sh, qi, key, lane);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < QP * LIST; i += SCAN_THREADS)
+        lists_out[((size_t)blockIdx.x * QP + i / LIST) * LIST + (i % LIST)] = sh.list[i / LIST][i % LIST];
+}
+
+__device__ __forceinline__ bool better_pair(double sa, long long ia, double sb, long long ib) { return sa > sb || (sa == sb && ia < ib); }
+
+// grid = queries of this pass, block = 1024.  Merge per-CTA lists -> 32 candidates -> exact fp64 re-rank -> top-k.
+template <typename T, int D>
+__global__ void __launch_bounds__(1024)
+knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const T* __restrict__ db, const float* __restrict__ inv,
+                  long long n, const float* __restrict__ q, int k, long long idx_base,
+                  long long* __restrict__ idx_out, float* __restrict__ dist_out, double* __restrict__ score_out) {
+    __shared__ u64 s_keys[32][LIST];
+    __shared__ float s_q[D];
+    const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < D; i += blockDim.x) s_q[i] = q[(size_t)qi * D + i];
+    u64 cur = 0ull;
+    for (int b = warp; b < nblk; b += 32) {
+        u64 batch = lists[((size_t)b * QP + qi) * LIST + lane];
+        if (__any_sync(FULL, batch != 0ull)) cur = warp_merge_top32(cur, batch, lane);
+    }
+    s_keys[warp][lane] = cur;
+    __syncthreads();
+    if (warp != 0) return;
+    cur = s_keys[0][lane];
+    for (int w = 1; w < 32; w++) {
+        u64 batch = s_keys[w][lane];
+        if (__any_sync(FULL, batch != 0ull)) cur = warp_merge_top32(cur, batch, lane);
+    }
+    // exact re-rank (definition: oracle/knn_ref.c)
+    const bool have = cur != 0ull;
+    long long row = have ? (long long)(0xffffffffu - (uint32_t)cur) : 0x7fffffffffffffffLL;
+    double s = -CUDART_INF;
+    if (have && row < n) {
+        const T* r = db + (size_t)row * D;
+        double acc = 0.0;
+        for (int j = 0; j < D; j++) acc = __dadd_rn(acc, __dmul_rn((double)s_q[j], (double)Elem<T>::to_f32(r[j])));
+        acc = __dmul_rn(acc, (double)inv[row]);
+        s = (acc == acc) ? acc : -CUDART_INF;
+    }
+    // bitonic sort of (score, row) pairs, best first
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            double os = __shfl_xor_sync(FULL, s, j);
+            long long orow = __shfl_xor_sync(FULL, row, j);
+            bool desc = (lane & kk) == 0, lower = (lane & j) == 0;
+            bool keep_best = (desc == lower);
+            bool other_better = better_pair(os, orow, s, row);
+            if (keep_best == other_better) { s = os; row = orow; }
+        }
+    }
+    if (lane < k) {
+        bool ok = row != 0x7fffffffffffffffLL;
+        idx_out[(size_t)qi * k + lane] = ok ? row + idx_base : -1;
+        dist_out[(size_t)qi * k + lane] = ok ? (float)s : -CUDART_INF_F;
+        if (score_out) score_out[(size_t)qi * k + lane] = ok ? s : -CUDART_INF;
+    }
+}
+
+template <typename T, int D>
+__global__ void knn_inv_norm_kernel(const T* __restrict__ db, long long n, float* __restrict__ inv) {
+    long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    constexpr int EPV = Elem<T>::EPV;
+    const uint4* p = reinterpret_cast<const uint4*>(db + (size_t)row * D);
+    double s = 0.0;
+    for (int v = 0; v < D / EPV; v++) {
+        float f[EPV];
+        Elem<T>::unpack(__ldg(p + v), f);
+#pragma unroll
+        for (int j = 0; j < EPV; j++) { double e = (double)f[j]; s = __dadd_rn(s, __dmul_rn(e, e)); }
+    }
+    inv[row] = (float)(1.0 / sqrt(s));
+}
+
+template <typename T, int D>
+__global__ void knn_gather_kernel(const T* __restrict__ db, long long n, long long idx_base, const long long* __restrict__ idx,
+                                  long long count, float* __restrict__ out) {
+    constexpr int EPV = Elem<T>::EPV;
+    long long i = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (i >= count) return;
+    const int lane = threadIdx.x & 31;
+    long long row = idx[i] - idx_base;
+    const bool inside = row >= 0 && row < n;
+    float* o = out + (size_t)i * D;
+    for (int v = lane; v < D / EPV; v += 32) {
+        float f[EPV];
+        if (inside) Elem<T>::unpack(__ldg(reinterpret_cast<const uint4*>(db + (size_t)row * D) + v), f);
+        else {
+#pragma unroll
+            for (int j = 0; j < EPV; j++) f[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < EPV; j += 4) *reinterpret_cast<float4*>(o + v * EPV + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    }
+}
+
+// one warp per query: k rounds of arg-best over parts*k candidates
+__global__ void knn_merge_kernel(const long long* __restrict__ idx_in, const double* __restrict__ sc_in, int parts, int nq, int k,
+                                 long long* __restrict__ idx_out, float* __restrict__ dist_out, double* __restrict__ sc_out) {
+    const int qi = blockIdx.x, lane = threadIdx.x;
+    const int total = parts * k;
+    double last_s = CUDART_INF; long long last_i = -1;      // everything strictly worse than (last_s, last_i) is still available
+    for (int t = 0; t < k; t++) {
+        double bs = -CUDART_INF; long long bi = 0x7fffffffffffffffLL;
+        for (int c = lane; c < total; c += 32) {
+            int p = c / k, j = c % k;
+            long long ci = idx_in[((size_t)p * nq + qi) * k + j];
+            double cs = sc_in[((size_t)p * nq + qi) * k + j];
+            if (ci < 0) continue;
+            if (t > 0 && !better_pair(last_s, last_i, cs, ci)) continue;     // already emitted (or equal to it)
+            if (better_pair(cs, ci, bs, bi)) { bs = cs; bi = ci; }
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            double os = __shfl_xor_sync(FULL, bs, m); long long oi = __shfl_xor_sync(FULL, bi, m);
+            if (better_pair(os, oi, bs, bi)) { bs = os; bi = oi; }
+        }
+        bool ok = bi != 0x7fffffffffffffffLL;
+        if (lane == 0) {
+            idx_out[(size_t)qi * k + t] = ok ? bi : -1;
+            dist_out[(size_t)qi * k + t] = ok ? (float)bs : -CUDART_INF_F;
+            if (sc_out) sc_out[(size_t)qi * k + t] = ok ? bs : -CUDART_INF;
+        }
+        last_s = bs; last_i = bi;
+        if (!ok) { last_s = -CUDART_INF; last_i = 0x7fffffffffffffffLL; }
+    }
+}
+
+}  // namespace
+
+struct rdm_knn {
+    int device = 0;
+    long long n = 0;
+    int d = 0, dtype = 0;
+    long long idx_base = 0;
+    const void* db = nullptr;      // device
+    void* db_owned = nullptr;      // device allocation when copied from host
+    float* inv = nullptr;
+    u64* lists = nullptr;
+    int max_grid = 0;
+};
+
+namespace {
+
+template <typename T, int D, int QP, int R>
+int launch_scan(rdm_knn* h, const float* q, int nq_valid, cudaStream_t st, int* grid_out) {
+    auto kern = knn_scan_kernel<T, D, QP, R>;
+    size_t smem = (size_t)QP * D * sizeof(float);
+    static thread_local int cached_grid[8] = {0};   // per device
+    int& grid = cached_grid[h->device & 7];
+    if (grid == 0) {
+        RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        RDM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SCAN_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        grid = rdm_num_sms(h->device) * per_sm;
+        if (grid > h->max_grid) grid = h->max_grid;
+    }
+    long long ngroups = (h->n + R - 1) / R;
+    int g = grid;
+    long long need = (ngroups + SCAN_WARPS - 1) / SCAN_WARPS;
+    if (need < g) g = (int)(need < 1 ? 1 : need);
+    kern<<<g, SCAN_THREADS, smem, st>>>((const T*)h->db, h->inv, h->n, q, nq_valid, h->lists);
+    RDM_COUNT_LAUNCH();
+    RDM_CHECK_CUDA(cudaGetLastError());
+    *grid_out = g;
+    return RDM_OK;
+}
+
+template <typename T, int D>
+int search_typed(rdm_knn* h, const float* q, int nq, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st) {
+    constexpr int R = (128 / (D / 32)) >= 8 ? 8 : 4;     // keep R * D/32 <= 128 registers of row data per lane
+    for (int q0 = 0; q0 < nq; q0 += MAX_QP) {
+        int cnt = nq - q0 < MAX_QP ? nq - q0 : MAX_QP;
+        const float* qp = q + (size_t)q0 * D;
+        int grid = 0, QP;
+        if (cnt <= 1)      { QP = 1;  RDM_TRY((launch_scan<T, D, 1, R>(h, qp, cnt, st, &grid))); }
+        else if (cnt <= 2) { QP = 2;  RDM_TRY((launch_scan<T, D, 2, R>(h, qp, cnt, st, &grid))); }
+        else if (cnt <= 4) { QP = 4;  RDM_TRY((launch_scan<T, D, 4, R>(h, qp, cnt, st, &grid))); }
+        else if (cnt <= 8) { QP = 8;  RDM_TRY((launch_scan<T, D, 8, R>(h, qp, cnt, st, &grid))); }
+        else               { QP = 16; RDM_TRY((launch_scan<T, D, 16, R>(h, qp, cnt, st, &grid))); }
+        knn_select_kernel<T, D><<<cnt, 1024, 0, st>>>(h->lists, grid, QP, (const T*)h->db, h->inv, h->n, qp, k, h->idx_base,
+                                                      idx_out + (size_t)q0 * k, dist_out + (size_t)q0 * k,
+                                                      sc_out ? sc_out + (size_t)q0 * k : nullptr);
+        RDM_COUNT_LAUNCH();
+        RDM_CHECK_CUDA(cudaGetLastError());
+    }
+    return RDM_OK;
+}
+
+template <typename T, int D>
+int create_typed(rdm_knn* h) {
+    int blocks = (int)((h->n + 127) / 128);
+    knn_inv_norm_kernel<T, D><<<blocks, 128>>>((const T*)h->db, h->n, h->inv);
+    RDM_COUNT_LAUNCH();
+    RDM_CHECK_CUDA(cudaGetLastError());
+    RDM_CHECK_CUDA(cudaDeviceSynchronize());
+    return RDM_OK;
+}
+
+template <typename T, int D>
+int gather_typed(rdm_knn* h, const long long* idx, long long count, float* out, cudaStream_t st) {
+    if (count == 0) return RDM_OK;
+    int blocks = (int)((count + 7) / 8);
+    knn_gather_kernel<T, D><<<blocks, 256, 0, st>>>((const T*)h->db, h->n, h->idx_base, idx, count, out);
+    RDM_COUNT_LAUNCH();
+    RDM_CHECK_CUDA(cudaGetLastError());
+    return RDM_OK;
+}
+
+#define KNN_DISPATCH(h, FN, ...)                                                                    \
+    do {                                                                                            \
+        if ((h)->dtype == RDM_DTYPE_F16) {                                                          \
+            switch ((h)->d) {                                                                       \
+                case 256: return FN<__half, 256>(__VA_ARGS__);                                      \
+                case 512: return FN<__half, 512>(__VA_ARGS__);                                      \
+                case 768: return FN<__half, 768>(__VA_ARGS__);                                      \
+                case 1024: return FN<__half, 1024>(__VA_ARGS__);                                    \
+            }                                                                                       \
+        } else {                                                                                    \
+            switch ((h)->d) {                                                                       \
+                case 256: return FN<float, 256>(__VA_ARGS__);                                       \
+                case 512: return FN<float, 512>(__VA_ARGS__);                                       \
+                case 768: return FN<float, 768>(__VA_ARGS__);                                       \
+                case 1024: return FN<float, 1024>(__VA_ARGS__);                                     \
+            }                                                                                       \
+        }                                                                                           \
+        rdm_set_error("knn: unsupported d=%d", (h)->d);                                             \
+        return RDM_ERR_UNSUPPORTED;                                                                 \
+    } while (0)
+
+int do_create(rdm_knn* h) { KNN_DISPATCH(h, create_typed, h); }
+int do_search(rdm_knn* h, const float* q, int nq, int k, long long* i, float* d, double* s, cudaStream_t st) {
+    KNN_DISPATCH(h, search_typed, h, q, nq, k, i, d, s, st);
+}
+int do_gather(rdm_knn* h, const long long* idx, long long count, float* out, cudaStream_t st) {
+    KNN_DISPATCH(h, gather_typed, h, idx, count, out, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rdm_knn_create(rdm_knn_t** out, const void* db, int64_t n, int32_t d, int32_t dtype, int32_t db_on_device,
+                   int64_t idx_base, int32_t device) {
+    RDM_REQUIRE(out && db, RDM_ERR_ARG, "rdm_knn_create: null argument");
+    RDM_REQUIRE(n > 0 && n < 0xfffffff0LL, RDM_ERR_ARG, "rdm_knn_create: n=%lld out of range (1..2^32-16 rows per shard)", (long long)n);
+    RDM_REQUIRE(d == 256 || d == 512 || d == 768 || d == 1024, RDM_ERR_UNSUPPORTED, "rdm_knn_create: d=%d not in {256,512,768,1024}", d);
+    RDM_REQUIRE(dtype == RDM_DTYPE_F16 || dtype == RDM_DTYPE_F32, RDM_ERR_ARG, "rdm_knn_create: bad dtype %d", dtype);
+    DeviceGuard guard(device);
+    RDM_REQUIRE(guard.ok, RDM_ERR_CUDA, "rdm_knn_create: cannot select device %d", device);
+    rdm_knn* h = new rdm_knn();
+    h->device = device; h->n = n; h->d = d; h->dtype = dtype; h->idx_base = idx_base;
+    size_t bytes = (size_t)n * d * (dtype == RDM_DTYPE_F16 ? 2 : 4);
+    int rc = RDM_OK;
+    do {
+        if (db_on_device) {
+            if (((uintptr_t)db & 15) != 0) { rdm_set_error("rdm_knn_create: device db pointer must be 16-byte aligned"); rc = RDM_ERR_ARG; break; }
+            h->db = db;
+        } else {
+            if (cudaMalloc(&h->db_owned, bytes) != cudaSuccess) { rdm_set_error("rdm_knn_create: cudaMalloc(%zu) failed", bytes); rc = RDM_ERR_CUDA; break; }
+            if (cudaMemcpy(h->db_owned, db, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { rdm_set_error("rdm_knn_create: H2D copy failed"); rc = RDM_ERR_CUDA; break; }
+            h->db = h->db_owned;
+        }
+        h->max_grid = rdm_num_sms(device) * 8;
+        if (cudaMalloc(&h->inv, (size_t)n * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&h->lists, (size_t)h->max_grid * MAX_QP * LIST * sizeof(u64)) != cudaSuccess) {
+            rdm_set_error("rdm_knn_create: workspace cudaMalloc failed"); rc = RDM_ERR_CUDA; break;
+        }
+        rc = do_create(h);
+    } while (0);
+    if (rc != RDM_OK) { rdm_knn_destroy(h); return rc; }
+    *out = h;
+    return RDM_OK;
+}
+
+void rdm_knn_destroy(rdm_knn_t* h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    if (h->db_owned) cudaFree(h->db_owned);
+    if (h->inv) cudaFree(h->inv);
+    if (h->lists) cudaFree(h->lists);
+    delete h;
+}
+
+int64_t rdm_knn_size(const rdm_knn_t* h) { return h ? h->n : 0; }
+int rdm_knn_get_inv_norms(rdm_knn_t* h, float* out, void* stream) {
+    RDM_REQUIRE(h && out, RDM_ERR_ARG, "rdm_knn_get_inv_norms: null argument");
+    DeviceGuard guard(h->device);
+    RDM_CHECK_CUDA(cudaMemcpyAsync(out, h->inv, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return RDM_OK;
+}
+
+int rdm_knn_search(rdm_knn_t* h, const float* q, int32_t nq, int32_t k, int64_t* idx_out, float* dist_out, double* score_out, void* stream) {
+    RDM_REQUIRE(h && q && idx_out && dist_out, RDM_ERR_ARG, "rdm_knn_search: null argument");
+    RDM_REQUIRE(k >= 1 && k <= RDM_KNN_MAX_K, RDM_ERR_ARG, "rdm_knn_search: k=%d outside 1..%d", k, RDM_KNN_MAX_K);
+    RDM_REQUIRE(nq >= 0, RDM_ERR_ARG, "rdm_knn_search: nq=%d", nq);
+    if (nq == 0) return RDM_OK;
+    DeviceGuard guard(h->device);
+    return do_search(h, q, nq, k, (long long*)idx_out, dist_out, score_out, (cudaStream_t)stream);
+}
+
+int rdm_knn_merge(const int64_t* idx_in, const double* score_in, int32_t parts, int32_t nq, int32_t k,
+                  int64_t* idx_out, float* dist_out, double* score_out, int32_t device, void* stream) {
+    RDM_REQUIRE(idx_in && score_in && idx_out && dist_out, RDM_ERR_ARG, "rdm_knn_merge: null argument");
+    RDM_REQUIRE(parts >= 1 && k >= 1 && nq >= 0, RDM_ERR_ARG, "rdm_knn_merge: bad sizes");
+    if (nq == 0) return RDM_OK;
+    DeviceGuard guard(device);
+    knn_merge_kernel<<<nq, 32, 0, (cudaStream_t)stream>>>((const long long*)idx_in, score_in, parts, nq, k, (long long*)idx_out, dist_out, score_out);
+    RDM_COUNT_LAUNCH();
+    RDM_CHECK_CUDA(cudaGetLastError());
+    return RDM_OK;
+}
+
+int rdm_knn_gather(rdm_knn_t* h, const int64_t* idx, int64_t count, float* out, void* stream) {
+    RDM_REQUIRE(h && idx && out, RDM_ERR_ARG, "rdm_knn_gather: null argument");
+    RDM_REQUIRE(count >= 0, RDM_ERR_ARG, "rdm_knn_gather: count<0");
+    DeviceGuard guard(h->device);
+    return do_gather(h, (const long long*)idx, count, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+"""ctypes binding of librdm_b200.so (the C ABI declared in include/rdm_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+PyTorch is used only for device memory, streams and torch.distributed plumbing.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librdm_b200.so")
+CSRC_DIR = os.path.join(os.path.dirname(_HERE), "csrc")
+
+_lib = None
+
+c_void_p, c_int, c_int32, c_int64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64
+c_float, c_double, c_char_p, c_ulonglong = ctypes.c_float, ctypes.c_double, ctypes.c_char_p, ctypes.c_ulonglong
+
+# name -> (restype, argtypes); kept in sync with include/rdm_b200.h (tests/test_abi.py checks both ways)
+SIGNATURES = {
+    "rdm_last_error": (c_char_p, []),
+    "rdm_abi_version": (c_int, []),
+    "rdm_launch_count": (c_ulonglong, []),
+    "rdm_knn_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int64, c_int32, c_int32, c_int32, c_int64, c_int32]),
+    "rdm_knn_destroy": (None, [c_void_p]),
+    "rdm_knn_size": (c_int64, [c_void_p]),
+    "rdm_knn_get_inv_norms": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "rdm_knn_search": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rdm_knn_merge": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "rdm_knn_gather": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+}
+
+
+def build(verbose=False):
+    """Compile the CUDA sources in csrc/ for sm_100a into librdm_b200.so (in-tree)."""
+    import subprocess
+    out = subprocess.run(["make", "-C", CSRC_DIR, "-j8"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode != 0:
+        raise RuntimeError("building librdm_b200.so failed")
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the product has no CPU or PyTorch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().rdm_last_error()
+        raise RuntimeError(f"librdm_b200 {what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def stream_ptr(device=None):
+    import torch
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    """Device/host pointer of a contiguous tensor (or None)."""
+    if t is None:
+        return c_void_p(0)
+    assert t.is_contiguous(), "librdm_b200 needs contiguous tensors"
+    return c_void_p(t.data_ptr())
+
+
+def launch_count():
+    return int(lib().rdm_launch_count())

@@ -1,0 +1,86 @@
+"""GPU parity: librdm_b200 kNN (through the C ABI) vs the exact oracle.  Indices bit-exact, fp64 scores bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import knn as oknn
+
+pytestmark = pytest.mark.gpu
+
+
+def _db(n, d, dtype, seed, dup=True):
+    rng = np.random.default_rng(seed)
+    db = rng.standard_normal((n, d)).astype(np.float32)
+    db *= rng.uniform(0.5, 12.0, size=(n, 1)).astype(np.float32)        # raw CLIP rows are NOT unit norm (F7)
+    db = db.astype(dtype)
+    if dup and n > 5000:
+        db[1234] = db[7]; db[4321] = db[7]; db[n - 1] = db[7]            # exact duplicates -> score ties
+    return db
+
+
+@pytest.mark.parametrize("dtype", [np.float16, np.float32])
+@pytest.mark.parametrize("n,nq,k", [(50_000, 1, 4), (100_003, 16, 4), (30_001, 5, 8), (65_537, 37, 20), (999, 3, 24), (40, 2, 4)])
+def test_search_matches_oracle(cuda, dtype, n, nq, k):
+    from rdm_b200.knn import B200Searcher
+    db = _db(n, 512, dtype, seed=n)
+    rng = np.random.default_rng(n + 1)
+    rows = rng.integers(0, n, size=nq)
+    rows[0] = 7 if n > 5000 else rows[0]
+    q = db[rows].astype(np.float32)
+    q[nq // 2:] = rng.standard_normal((nq - nq // 2, 512)).astype(np.float32)   # half DB rows (ddpm.py:897), half free queries
+    qh = oknn.normalize_queries(q)
+    s = B200Searcher(db, device=cuda)
+    inv_ref = oknn.inv_norms(db)
+    assert np.array_equal(s.inv_norms().cpu().numpy().view(np.uint32), inv_ref.view(np.uint32)), "inverse norms must be bit-exact"
+    idx, dist, sc = s.search_device(torch.from_numpy(qh).to(cuda), k, return_scores=True)
+    ri, rd, rs = oknn.search(db, qh, k, inv=inv_ref, return_scores=True)
+    kk = min(k, n)
+    assert np.array_equal(idx.cpu().numpy()[:, :kk], ri[:, :kk]), "kNN indices must be bit-exact"
+    assert np.array_equal(sc.cpu().numpy()[:, :kk].view(np.uint64), rs[:, :kk].view(np.uint64)), "fp64 scores must be bit-exact"
+    assert np.array_equal(dist.cpu().numpy()[:, :kk], rd[:, :kk])
+    if n > 5000:
+        assert list(idx[0, :4].cpu().numpy()) == [7, 1234, 4321, n - 1]
+
+
+def test_scann_shaped_api_and_gather(cuda):
+    from rdm_b200.knn import B200Searcher
+    db = _db(20_000, 512, np.float16, seed=3)
+    s = B200Searcher(db, device=cuda)
+    q = oknn.normalize_queries(db[[11, 12, 13]].astype(np.float32))
+    nns, distances = s.search_batched(q, final_num_neighbors=4)
+    assert nns.shape == (3, 4) and distances.dtype == np.float32 and list(nns[:, 0]) == [11, 12, 13]
+    got = s.gather_device(torch.from_numpy(nns).to(cuda)).cpu().numpy()
+    assert got.dtype == np.float32 and np.array_equal(got, db[nns].astype(np.float32))      # raw rows, un-normalised (F7)
+
+
+def test_shards_merge_to_the_unsharded_result(cuda):
+    from rdm_b200.knn import B200Searcher, merge_device
+    db = _db(80_000, 512, np.float16, seed=5)
+    qh = oknn.normalize_queries(np.random.default_rng(6).standard_normal((9, 512)))
+    qd = torch.from_numpy(qh).to(cuda)
+    full = B200Searcher(db, device=cuda).search_device(qd, 8, return_scores=True)
+    parts_i, parts_s = [], []
+    for base in range(0, 80_000, 20_000):
+        sh = B200Searcher(db[base:base + 20_000], device=cuda, idx_base=base)
+        i, _, sc = sh.search_device(qd, 8, return_scores=True)
+        parts_i.append(i); parts_s.append(sc)
+    mi, md, ms = merge_device(torch.stack(parts_i), torch.stack(parts_s), 8)
+    assert torch.equal(mi, full[0]) and torch.equal(ms, full[2]) and torch.equal(md, full[1])
+
+
+def test_other_row_widths(cuda):
+    from rdm_b200.knn import B200Searcher
+    for d in (256, 768, 1024):
+        db = _db(9000, d, np.float16, seed=d)
+        qh = oknn.normalize_queries(np.random.default_rng(d).standard_normal((4, d)))
+        idx, _ = B200Searcher(db, device=cuda).search_device(torch.from_numpy(qh).to(cuda), 4)
+        assert np.array_equal(idx.cpu().numpy(), oknn.search(db, qh, 4)[0])
+
+
+def test_bad_arguments_fail_loudly(cuda):
+    from rdm_b200.knn import B200Searcher
+    s = B200Searcher(_db(100, 512, np.float32, seed=1, dup=False), device=cuda)
+    with pytest.raises(RuntimeError):
+        s.search_device(torch.zeros(1, 512, device=cuda), 25)          # k > RDM_KNN_MAX_K
+    with pytest.raises(RuntimeError):
+        B200Searcher(np.zeros((10, 100), np.float32), device=cuda)     # unsupported row width

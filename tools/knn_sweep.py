@@ -1,0 +1,52 @@
+"""cfg5 of BASELINE.json: kNN HBM sweep (GB/s vs the measured HBM peak).  Usage: python tools/knn_sweep.py [--n 1281167] [--out file.json]"""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "retrieval-augmented-diffusion-models_b200")]
+import numpy as np, torch
+from rdm_b200.knn import B200Searcher
+
+
+def time_search(s, q, k, iters=20, warm=3):
+    for _ in range(warm):
+        s.search_device(q, k)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(iters):
+        s.search_device(q, k)
+    ev[1].record(); torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, nargs="*", default=[1_281_167])
+    ap.add_argument("--q", type=int, nargs="*", default=[1, 2, 4, 8, 16, 64, 256])
+    ap.add_argument("--k", type=int, default=4)
+    ap.add_argument("--dtypes", nargs="*", default=["float16", "float32"])
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    peak = 6571.9
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    dev = torch.device("cuda:0"); rows = []
+    for n in a.n:
+        for dt in a.dtypes:
+            g = torch.Generator(device=dev).manual_seed(6)
+            db = torch.randn((n, 512), generator=g, device=dev, dtype=torch.float32).to(getattr(torch, dt))
+            s = B200Searcher(db, device=dev)
+            for nq in a.q:
+                q = torch.nn.functional.normalize(torch.randn((nq, 512), generator=g, device=dev), dim=1)
+                ms = time_search(s, q, a.k)
+                gbs = n * 512 * db.element_size() / ms / 1e6
+                rows.append(dict(n=n, dtype=dt, nq=nq, k=a.k, ms=round(ms, 4), qps=round(nq / ms * 1e3, 1), gbs=round(gbs, 1), frac_hbm=round(gbs / peak, 3)))
+                print(rows[-1], flush=True)
+            del s, db
+    if a.out:
+        json.dump(dict(hbm_peak_gbs=peak, rows=rows), open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
