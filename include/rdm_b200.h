@@ -77,6 +77,60 @@ RDM_API int rdm_knn_merge(const int64_t* idx_in_dev, const double* score_in_dev,
  * ([idx_base, idx_base+n)) are written as zeros so shards can be summed. out_dev float32 [count, d]. */
 RDM_API int rdm_knn_gather(rdm_knn_t* h, const int64_t* idx_dev, int64_t count, float* out_dev, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * U-Net eps-model: rdm/modules/diffusionmodules/openaimodel.py:66-317 (UNetModel.__init__),
+ * :335-371 (forward) with rdm/modules/attention.py:122-196 SpatialTransformers cross-attending the
+ * k retrieved CLIP vectors.  The struct mirrors the constructor arguments the shipped configs set
+ * (models/rdm/imagenet/config.yaml:36-59).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct rdm_unet rdm_unet_t;
+typedef struct rdm_unet_cfg {
+    int32_t in_channels, model_channels, out_channels, num_res_blocks;
+    int32_t n_attention_resolutions; int32_t attention_resolutions[8];   /* downsample rates with attention */
+    int32_t n_channel_mult; int32_t channel_mult[8];
+    int32_t num_head_channels;      /* d_head; must be 32 */
+    int32_t num_heads;              /* used only when num_head_channels <= 0 */
+    int32_t transformer_depth;      /* must be 1 */
+    int32_t context_dim;            /* 512 (CLIP) */
+} rdm_unet_cfg;
+
+#define RDM_UNET_MODE_FP32 0        /* every contraction in fp32 on CUDA cores (strict parity mode) */
+
+RDM_API int rdm_unet_create(rdm_unet_t** out, const rdm_unet_cfg* cfg, int32_t device);
+RDM_API void rdm_unet_destroy(rdm_unet_t* h);
+/* State-dict interface (`model.load_state_dict`, scripts/rdm_sample.py:170): parameter names are the
+ * reference's UNetModel keys, e.g. "input_blocks.4.1.transformer_blocks.0.attn2.to_k.weight". */
+RDM_API int64_t rdm_unet_num_params(const rdm_unet_t* h);
+RDM_API const char* rdm_unet_param_name(const rdm_unet_t* h, int64_t i);
+RDM_API int64_t rdm_unet_param_numel(const rdm_unet_t* h, const char* name);     /* -1 if unknown */
+/* host float32, PyTorch layout of that parameter (conv [Cout,Cin,kh,kw], linear [out,in]); re-packed on upload. */
+RDM_API int rdm_unet_load(rdm_unet_t* h, const char* name, const float* host, int64_t numel);
+RDM_API int64_t rdm_unet_missing(const rdm_unet_t* h);                           /* parameters not loaded yet */
+RDM_API int rdm_unet_set_mode(rdm_unet_t* h, int32_t mode);
+/* Debug aid: when on, every forward synchronises after each layer and records "<tag> <block> <layer> <mean> <absmean>"
+ * lines (blocks in execution order: input_blocks, middle_block, output_blocks) retrievable as text. */
+RDM_API int rdm_unet_set_debug(rdm_unet_t* h, int32_t on);
+RDM_API const char* rdm_unet_debug_log(const rdm_unet_t* h);
+/* context: float32 [B2, k, context_dim] (device).  Projects the step-invariant cross-attention K/V of all
+ * SpatialTransformers once (attention.py:47-48); must precede rdm_unet_forward and be repeated when the
+ * context, the batch or the weights change. */
+RDM_API int rdm_unet_set_context(rdm_unet_t* h, const float* ctx_dev, int32_t B2, int32_t k, void* stream);
+/* UNetModel.forward(x, timesteps, context): x float32 NCHW [Bx,C,H,W] with Bx == B2, or Bx == B2/2 to evaluate the
+ * classifier-free-guidance doubling cat([x]*2) of ddim.py:233 without materialising it; t int64 [B2];
+ * eps_out float32 NCHW [B2, out_channels, H, W]. */
+RDM_API int rdm_unet_forward(rdm_unet_t* h, const float* x_dev, int32_t Bx, const int64_t* t_dev, int32_t B2,
+                     int32_t H, int32_t W, float* eps_out_dev, void* stream);
+
+/* DDIMSampler.p_sample_ddim arithmetic after the model call (rdm/models/diffusion/ddim.py:236-238,253-267):
+ * e = cfg ? e_u + scale*(e_c - e_u) : eps;  pred_x0 = (x - c0*e)/c1;  x_prev = c2*pred_x0 + c3*e (+ c4*noise),
+ * coef_dev = {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma} as float32 (device).
+ * eps holds [cond | uncond] halves of n_per_half elements when cfg != 0.  Same rounding sequence as the
+ * reference's float32 tensor expressions.  pred_x0/noise may be NULL. */
+RDM_API int rdm_ddim_step(const float* x_dev, const float* eps_dev, int64_t n_per_half, int32_t cfg, float scale,
+                  const float* coef_dev, const float* noise_dev, float* x_prev_dev, float* pred_x0_dev,
+                  int32_t device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,273 @@
+// U-Net glue kernels: layout changes, timestep embedding, GroupNorm, LayerNorm, attention (d_head 32),
+// SiLU and the fused CFG + DDIM update.  All fp32 data, fp32 math with fp64 GroupNorm statistics.
+// Semantics: SURVEY.md Appendix A (ldm pieces), rdm/modules/attention.py:42-74,92-96,183-196,
+// rdm/models/diffusion/ddim.py:232-238,253-267.
+#include "kernels.cuh"
+#include <math_constants.h>
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int Bsrc, int Bout, int C, int HW, float* __restrict__ out, int ld) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over Bout*HW*C, c fastest
+    long long total = (long long)Bout * HW * C;
+    if (i >= total) return;
+    int c = (int)(i % C);
+    long long m = i / C;
+    int p = (int)(m % HW), b = (int)(m / HW) % Bsrc;
+    out[m * ld + c] = x[((long long)b * C + c) * HW + p];
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int ld, int B, int C, int HW, float* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over B*C*HW, p fastest
+    long long total = (long long)B * C * HW;
+    if (i >= total) return;
+    int p = (int)(i % HW);
+    long long r = i / HW;
+    int c = (int)(r % C), b = (int)(r / C);
+    out[i] = in[((long long)b * HW + p) * ld + c];
+}
+
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B, int dim, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int half = dim / 2;
+    if (i >= B * half) return;
+    int b = i / half, j = i % half;
+    // freqs = exp(-ln(10000) * j / half) in fp32, args = float(t) * freqs   (same op order as the torch statement)
+    float freq = expf(-9.210340371976184f * (float)j / (float)half);
+    float arg = (float)t[b] * freq;
+    out[(size_t)b * dim + j] = cosf(arg);
+    out[(size_t)b * dim + half + j] = sinf(arg);
+    if ((dim & 1) && j == 0) out[(size_t)b * dim + dim - 1] = 0.f;
+}
+
+// grid (row_chunks, B); each CTA streams whole rows (coalesced) and accumulates per-channel partial sums.
+// blockDim.x = 256; channels are covered by float4 lanes: thread handles float4 column v = tid % V, row slot tid / V.
+__global__ void gn_stats_kernel(const float* __restrict__ x, int ld, int C, int HW, int groups, int rows_per_cta, double* __restrict__ sums) {
+    extern __shared__ float s_acc[];           // [2][groups]
+    const int b = blockIdx.y, V = C / 4, cpg = C / groups;
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
+    const long long total = (long long)(r1 - r0) * V;
+    const float* base = x + ((long long)b * HW + r0) * ld;
+    // consecutive threads -> consecutive float4 columns of one row; a thread's column index changes per step, so
+    // accumulate per element into shared memory only after a per-thread run over the same group is exhausted.
+    int cur_g = -1; float s = 0.f, ss = 0.f;
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+        int v = (int)(i % V); long long r = i / V;
+        float4 q = *reinterpret_cast<const float4*>(base + r * ld + v * 4);
+        float e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            int g = (v * 4 + t) / cpg;
+            if (g != cur_g) {
+                if (cur_g >= 0) { atomicAdd(&s_acc[cur_g], s); atomicAdd(&s_acc[groups + cur_g], ss); }
+                cur_g = g; s = 0.f; ss = 0.f;
+            }
+            s += e[t]; ss += e[t] * e[t];
+        }
+    }
+    if (cur_g >= 0) { atomicAdd(&s_acc[cur_g], s); atomicAdd(&s_acc[groups + cur_g], ss); }
+    __syncthreads();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        atomicAdd(&sums[((size_t)b * groups + g) * 2 + 0], (double)s_acc[g]);
+        atomicAdd(&sums[((size_t)b * groups + g) * 2 + 1], (double)s_acc[groups + g]);
+    }
+}
+
+__global__ void gn_apply_kernel(const float* __restrict__ x, int ld, int C, int HW, int groups, const double* __restrict__ sums, float eps,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu, float* __restrict__ y, int ldy, long long total4) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over M * C/4
+    if (i >= total4) return;
+    const int V = C / 4, cpg = C / groups;
+    int v = (int)(i % V); long long m = i / V;
+    int b = (int)(m / HW);
+    float4 q = *reinterpret_cast<const float4*>(x + m * ld + v * 4);
+    float e[4] = {q.x, q.y, q.z, q.w}, o[4];
+    const double cnt = (double)HW * cpg;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        int c = v * 4 + t, g = c / cpg;
+        double s = sums[((size_t)b * groups + g) * 2], ss = sums[((size_t)b * groups + g) * 2 + 1];
+        double mean = s / cnt, var = ss / cnt - mean * mean;
+        float rstd = (float)(1.0 / sqrt((var > 0 ? var : 0.0) + (double)eps));
+        float val = (e[t] - (float)mean) * rstd * gamma[c] + beta[c];
+        o[t] = silu ? silu_f(val) : val;
+    }
+    *reinterpret_cast<float4*>(y + m * ldy + v * 4) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// one warp per row, two-pass (mean, then centred variance) in fp32 from registers/L1
+__global__ void layernorm_kernel(const float* __restrict__ x, int ld, int C, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float eps, float* __restrict__ y, int ldy) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* xr = x + (size_t)row * ld;
+    const int V = C / 4;
+    float s = 0.f;
+    for (int v = lane; v < V; v += 32) { float4 q = *reinterpret_cast<const float4*>(xr + v * 4); s += (q.x + q.y) + (q.z + q.w); }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(FULL, s, m);
+    const float mean = s / (float)C;
+    float ss = 0.f;
+    for (int v = lane; v < V; v += 32) {
+        float4 q = *reinterpret_cast<const float4*>(xr + v * 4);
+        float a = q.x - mean, b = q.y - mean, c = q.z - mean, d = q.w - mean;
+        ss += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(FULL, ss, m);
+    const float rstd = rsqrtf(ss / (float)C + eps);
+    float* yr = y + (size_t)row * ldy;
+    for (int v = lane; v < V; v += 32) {
+        float4 q = *reinterpret_cast<const float4*>(xr + v * 4);
+        float4 g = *reinterpret_cast<const float4*>(gamma + v * 4), bb = *reinterpret_cast<const float4*>(beta + v * 4);
+        float4 o = make_float4((q.x - mean) * rstd * g.x + bb.x, (q.y - mean) * rstd * g.y + bb.y,
+                               (q.z - mean) * rstd * g.z + bb.z, (q.w - mean) * rstd * g.w + bb.w);
+        *reinterpret_cast<float4*>(yr + v * 4) = o;
+    }
+}
+
+// Attention for d_head = 32: one thread per query row, keys/values of one (batch, head) staged through shared
+// memory in tiles of KT keys (broadcast reads), online softmax in fp32.  grid (ceil(Nq/blockDim), heads, B).
+constexpr int KT = 64;
+__global__ void attention_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
+                                     int Nq, int Nk, float scale_log2e, float* __restrict__ out, int ldo) {
+    __shared__ float4 sk[KT][8], sv[KT][8];
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = qi < Nq;
+    float qr[32], acc[32];
+    if (active) {
+        const float4* qp = reinterpret_cast<const float4*>(q + ((size_t)b * Nq + qi) * ldq + h * 32);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { float4 t = qp[i]; qr[4 * i] = t.x * scale_log2e; qr[4 * i + 1] = t.y * scale_log2e; qr[4 * i + 2] = t.z * scale_log2e; qr[4 * i + 3] = t.w * scale_log2e; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; i++) qr[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i++) acc[i] = 0.f;
+    float mx = -CUDART_INF_F, l = 0.f;
+    for (int k0 = 0; k0 < Nk; k0 += KT) {
+        const int kn = min(KT, Nk - k0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kn * 8; i += blockDim.x) {
+            int j = i >> 3, c = i & 7;
+            sk[j][c] = *reinterpret_cast<const float4*>(k + ((size_t)b * Nk + k0 + j) * ldk + h * 32 + c * 4);
+            sv[j][c] = *reinterpret_cast<const float4*>(v + ((size_t)b * Nk + k0 + j) * ldv + h * 32 + c * 4);
+        }
+        __syncthreads();
+        for (int j = 0; j < kn; j++) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                float4 kk = sk[j][c];
+                s = fmaf(qr[4 * c], kk.x, s); s = fmaf(qr[4 * c + 1], kk.y, s); s = fmaf(qr[4 * c + 2], kk.z, s); s = fmaf(qr[4 * c + 3], kk.w, s);
+            }
+            // s is the logit in log2 units
+            if (s > mx) {
+                float corr = exp2f(mx - s);
+                l *= corr;
+#pragma unroll
+                for (int i = 0; i < 32; i++) acc[i] *= corr;
+                mx = s;
+            }
+            float p = exp2f(s - mx);
+            l += p;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                float4 vv = sv[j][c];
+                acc[4 * c] = fmaf(p, vv.x, acc[4 * c]); acc[4 * c + 1] = fmaf(p, vv.y, acc[4 * c + 1]);
+                acc[4 * c + 2] = fmaf(p, vv.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(p, vv.w, acc[4 * c + 3]);
+            }
+        }
+    }
+    if (active) {
+        const float inv = 1.f / l;
+        float4* op = reinterpret_cast<float4*>(out + ((size_t)b * Nq + qi) * ldo + h * 32);
+#pragma unroll
+        for (int i = 0; i < 8; i++) op[i] = make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
+    }
+}
+
+__global__ void silu_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = silu_f(in[i]);
+}
+
+// Same operation order and rounding as the reference's float32 tensor expressions (no FMA contraction).
+__global__ void ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps, long long n, int cfg, float scale,
+                                   const float* __restrict__ coef, const float* __restrict__ noise, float* __restrict__ x_prev, float* __restrict__ pred_x0) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float s1m = coef[0], sqrt_at = coef[1], sqrt_aprev = coef[2], dirc = coef[3], sigma = coef[4];
+    float e = eps[i];
+    if (cfg) { float eu = eps[n + i]; e = __fadd_rn(eu, __fmul_rn(scale, __fsub_rn(e, eu))); }      // e_u + s*(e_c - e_u), ddim.py:238
+    float xv = x[i];
+    float p0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(s1m, e)), sqrt_at);                                 // ddim.py:259
+    float xp = __fadd_rn(__fmul_rn(sqrt_aprev, p0), __fmul_rn(dirc, e));                             // ddim.py:263,267
+    if (noise) xp = __fadd_rn(xp, __fmul_rn(sigma, noise[i]));
+    x_prev[i] = xp;
+    if (pred_x0) pred_x0[i] = p0;
+}
+
+inline int blocks_for(long long n, int t) { return (int)((n + t - 1) / t); }
+
+}  // namespace
+
+#define LAUNCH_CHECK() do { RDM_COUNT_LAUNCH(); RDM_CHECK_CUDA(cudaGetLastError()); } while (0)
+
+int k_nchw_to_nhwc(const float* x, int Bsrc, int Bout, int C, int H, int W, View out, cudaStream_t st) {
+    long long n = (long long)Bout * H * W * C;
+    nchw_to_nhwc_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, Bsrc, Bout, C, H * W, out.p, out.ld);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_nhwc_to_nchw(View in, int B, int C, int H, int W, float* out, cudaStream_t st) {
+    long long n = (long long)B * H * W * C;
+    nhwc_to_nchw_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in.p, in.ld, B, C, H * W, out);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_timestep_embedding(const long long* t, int B, int dim, float* out, cudaStream_t st) {
+    timestep_embedding_kernel<<<blocks_for((long long)B * (dim / 2), 128), 128, 0, st>>>(t, B, dim, out);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_gn_stats(View x, int B, int HW, int groups, double* sums, cudaStream_t st) {
+    RDM_REQUIRE(x.C % 4 == 0 && x.C % groups == 0 && x.ld % 4 == 0, RDM_ERR_ARG, "gn_stats: C=%d ld=%d groups=%d", x.C, x.ld, groups);
+    // ~8K float4 per CTA
+    int rows_per_cta = (8192 * 4) / x.C; if (rows_per_cta < 1) rows_per_cta = 1;
+    int chunks = (HW + rows_per_cta - 1) / rows_per_cta;
+    gn_stats_kernel<<<dim3(chunks, B), 256, 2 * groups * sizeof(float), st>>>(x.p, x.ld, x.C, HW, groups, rows_per_cta, sums);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps, const float* gamma, const float* beta, int silu, View y, cudaStream_t st) {
+    RDM_REQUIRE(x.C % 4 == 0 && y.ld % 4 == 0, RDM_ERR_ARG, "gn_apply: alignment");
+    long long total4 = (long long)B * HW * (x.C / 4);
+    gn_apply_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(x.p, x.ld, x.C, HW, groups, sums, eps, gamma, beta, silu, y.p, y.ld, total4);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_layernorm(View x, int M, const float* gamma, const float* beta, float eps, View y, cudaStream_t st) {
+    RDM_REQUIRE(x.C % 4 == 0, RDM_ERR_ARG, "layernorm: C %% 4");
+    layernorm_kernel<<<blocks_for(M, 8), 256, 0, st>>>(x.p, x.ld, x.C, M, gamma, beta, eps, y.p, y.ld);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_attention(View q, View k, View v, int B, int Nq, int Nk, int heads, float scale, View out, cudaStream_t st) {
+    RDM_REQUIRE(q.C == heads * 32, RDM_ERR_UNSUPPORTED, "attention: only d_head=32 is implemented (C=%d heads=%d)", q.C, heads);
+    int threads = Nq >= 128 ? 128 : ((Nq + 31) / 32) * 32;
+    dim3 grid((Nq + threads - 1) / threads, heads, B);
+    attention_d32_kernel<<<grid, threads, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, Nq, Nk, scale * 1.4426950408889634f, out.p, out.ld);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_silu(const float* in, float* out, long long n, cudaStream_t st) {
+    silu_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, out, n);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_ddim_update(const float* x, const float* eps, long long n, int cfg, float scale, const float* coef, const float* noise,
+                  float* x_prev, float* pred_x0, cudaStream_t st) {
+    ddim_update_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, eps, n, cfg, scale, coef, noise, x_prev, pred_x0);
+    LAUNCH_CHECK(); return RDM_OK;
+}

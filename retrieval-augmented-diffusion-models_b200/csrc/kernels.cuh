@@ -1,0 +1,56 @@
+// Launch wrappers of the U-Net glue kernels (definitions in kernels.cu) and the GEMM engines.
+// Activation layout everywhere: NHWC fp32, viewed as a row-major matrix [M = B*H*W, C] with a row
+// stride `ld` (in floats) so channel-concatenation is just two producers writing into one buffer.
+#pragma once
+#include "common.cuh"
+
+struct View {            // [M, C] fp32 matrix view
+    float* p = nullptr;
+    int ld = 0;          // row stride in floats (multiple of 4)
+    int C = 0;
+    View() {}
+    View(float* p_, int ld_, int C_) : p(p_), ld(ld_), C(C_) {}
+    View cols(int c0, int n) const { return View(p + c0, ld, n); }
+};
+
+// ---- implicit-GEMM description: out[M,N] = epi( A[M,K] * W[N,K]^T ) -----------------------------
+struct GemmA {
+    const float* x = nullptr; int ld = 0;   // source NHWC view [B*Hs*Ws, Cin]
+    int B = 1, Hs = 1, Ws = 1, Cin = 0;
+    int Ho = 1, Wo = 1;                     // output grid; M = B*Ho*Wo
+    int ksize = 1, stride = 1, ups = 0;     // 3x3 (pad 1) or 1x1; stride 1|2; ups=1: nearest-2x upsample before the conv
+    int M() const { return B * Ho * Wo; }
+    int K() const { return ksize * ksize * Cin; }
+};
+enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2 };
+struct GemmEpi {
+    const float* bias = nullptr;                                   // [N]
+    const float* rowvec = nullptr; int rowvec_ld = 0; int rows_per_batch = 1;   // + rowvec[(m / rows_per_batch)*rowvec_ld + n]
+    const float* res = nullptr; int res_ld = 0;                    // + res[m*res_ld + n]
+    int act = ACT_NONE;                                            // GEGLU: columns (2j,2j+1) = (a_j, gate_j) -> out col j
+    float* out = nullptr; int out_ld = 0;
+};
+// fp32 CUDA-core engine (strict mode / fallback).  W: [N, K] row-major, K ordered (tap, cin).
+int gemm_simt(const GemmA& a, const float* W, int N, const GemmEpi& e, cudaStream_t st);
+
+// ---- glue kernels -------------------------------------------------------------------------------
+// x NCHW [Bsrc,C,H,W] -> NHWC rows [Bout*H*W, C] with batch index taken modulo Bsrc (CFG doubling, ddim.py:233)
+int k_nchw_to_nhwc(const float* x, int Bsrc, int Bout, int C, int H, int W, View out, cudaStream_t st);
+int k_nhwc_to_nchw(View in, int B, int C, int H, int W, float* out, cudaStream_t st);
+// timestep_embedding (ldm util): t int64 [B] -> [B, dim] = [cos | sin]
+int k_timestep_embedding(const long long* t, int B, int dim, float* out, cudaStream_t st);
+// GroupNorm statistics: sums[b][g] = (sum, sumsq) in fp64 (buffer must be zeroed), over x [B*HW, C]
+int k_gn_stats(View x, int B, int HW, int groups, double* sums, cudaStream_t st);
+// y = (x-mean)*rstd*gamma+beta, optional SiLU; y is a contiguous-or-strided fp32 view
+int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps, const float* gamma, const float* beta,
+               int silu, View y, cudaStream_t st);
+// LayerNorm over the last dim of [M, C] (eps 1e-5), one warp per row
+int k_layernorm(View x, int M, const float* gamma, const float* beta, float eps, View y, cudaStream_t st);
+// softmax(q k^T * scale) v for heads of width 32.  q: [B*Nq, heads*32] view, k/v: [B*Nk, heads*32] views.
+int k_attention(View q, View k, View v, int B, int Nq, int Nk, int heads, float scale, View out, cudaStream_t st);
+// out[i] = silu(in[i])
+int k_silu(const float* in, float* out, long long n, cudaStream_t st);
+// DDIM update with classifier-free guidance (ddim.py:236-238,258-267).  x NHWC [B*HW, C]; eps [2B*HW, C] (cond first) or [B*HW,C] if !cfg.
+// coef (device, 8 floats per step): {sqrt_one_minus_at, 1/sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma, 0,0,0}
+int k_ddim_update(const float* x, const float* eps, long long n_per_half, int cfg, float scale, const float* coef_dev,
+                  const float* noise, float* x_prev, float* pred_x0, cudaStream_t st);

@@ -1,0 +1,564 @@
+// U-Net executor: builds the layer plan of rdm/modules/diffusionmodules/openaimodel.py:66-317 from a config
+// struct, owns the (re-packed) weights, the workspace arena and the per-context cross-attention K/V, and
+// runs UNetModel.forward (openaimodel.py:335-371) as a fixed sequence of kernels on one stream.
+//
+// Data layout: NHWC fp32 activations as [M, C] matrices (kernels.cuh).  Skip connections are written by their
+// producer straight into the concat buffer of the consuming output block (torch.cat at openaimodel.py:365 is free).
+// Hoisted out of the step loop: cross-attention K/V projections of the (step-invariant) retrieved context
+// (attention.py:47-48 -> rdm_unet_set_context), and all 25 ResBlock emb_layers as ONE GEMM per forward.
+#include "kernels.cuh"
+#include "../../include/rdm_b200.h"
+#include <functional>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <memory>
+#include <cstring>
+
+namespace {
+
+struct Arena {
+    char* base = nullptr; size_t cap = 0, off = 0, peak = 0; bool dry = true;
+    float* allocf(size_t n) { return (float*)alloc(n * sizeof(float)); }
+    void* alloc(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        size_t o = off; off += bytes; if (off > peak) peak = off;
+        return dry ? (void*)((char*)256 + o) : (void*)(base + o);
+    }
+    size_t mark() const { return off; }
+    void release(size_t m) { off = m; }
+};
+
+struct ParamSlot { size_t numel = 0; bool loaded = false; std::function<void(const float*, std::vector<float>&)> pack; float* dst = nullptr; size_t dst_numel = 0;
+                   // generic scatter: packed data is copied to dst (dst_numel floats) -- or rows scattered (see rows_*).
+                   int rows = 0, row_len = 0, dst_row0 = 0, dst_row_step = 1; };
+
+struct Norm { int C = 0; float* g = nullptr; float* b = nullptr; };
+struct Conv { int cin = 0, cout = 0, ks = 1; float* w = nullptr; float* b = nullptr; };     // w: [cout][ks*ks*cin] (tap-major K)
+struct Lin { int in = 0, out = 0; float* w = nullptr; float* b = nullptr; };                // w: [out][in]
+
+struct ResW { int cin, cout; Norm n1; Conv c1; int emb_off; Norm n2; Conv c2; bool has_skip; Conv skip; };
+struct STW { int C, heads, id; Norm norm; Conv proj_in; Norm ln1, ln2, ln3; Lin qkv, o1, q2, kv2, o2, ff1, ff2; Conv proj_out; };
+enum LayerKind { L_CONV_IN, L_RES, L_ST, L_DOWN, L_UP };
+struct Layer { LayerKind kind; int idx; };
+struct Block { std::vector<Layer> layers; int cout; int ds_after; };     // ds_after: spatial divisor after this block
+
+struct Act { View v; int B, H, W; int M() const { return B * H * W; } };
+
+}  // namespace
+
+struct rdm_unet {
+    int device = 0;
+    rdm_unet_cfg cfg{};
+    int mode = 0;
+    // weights
+    float* wbase = nullptr; size_t wfloats = 0, woff = 0;
+    std::unordered_map<std::string, ParamSlot> params;
+    std::vector<std::string> param_order;
+    std::vector<ResW> res; std::vector<STW> sts; std::vector<Conv> convs;   // convs: conv_in, downs, ups
+    std::vector<Block> in_blocks, out_blocks; Block mid;
+    Lin te0, te2, emb_all; Norm out_norm; Conv out_conv;
+    int emb_total = 0, ted = 0;
+    std::vector<int> skip_ch;          // channels of hs[i]
+    // runtime
+    Arena arena; double* stats = nullptr; size_t stats_cap = 0, stats_off = 0;
+    float* ctx_kv = nullptr; size_t ctx_kv_floats = 0; std::vector<size_t> ctx_off; int ctx_B = 0, ctx_k = 0;
+    long long* t_dev = nullptr; int t_cap = 0;
+    int plan_B = 0, plan_H = 0, plan_W = 0;
+    std::vector<float*> host_scratch;
+    int debug = 0, debug_block = 0; std::string debug_log;
+};
+
+namespace {
+
+typedef rdm_unet Net;
+
+float* walloc(Net* n, size_t floats) {
+    floats = (floats + 63) & ~(size_t)63;
+    float* p = n->wbase ? n->wbase + n->woff : (float*)nullptr + n->woff;   // pass 1 counts, pass 2 places
+    n->woff += floats;
+    return p;
+}
+
+// ---- parameter registration (names follow SURVEY.md Appendix C) ---------------------------------------
+void reg_plain(Net* n, const std::string& name, float* dst, size_t numel) {
+    ParamSlot s; s.numel = numel; s.dst = dst; s.dst_numel = numel;
+    s.pack = [](const float* src, std::vector<float>& out) { (void)src; (void)out; };
+    n->params[name] = s; n->param_order.push_back(name);
+}
+// conv weight [cout, cin, ks, ks] -> [cout][ks*ks][cin]
+void reg_conv_w(Net* n, const std::string& name, float* dst, int cout, int cin, int ks) {
+    ParamSlot s; s.numel = (size_t)cout * cin * ks * ks; s.dst = dst; s.dst_numel = s.numel;
+    s.pack = [=](const float* src, std::vector<float>& out) {
+        out.resize((size_t)cout * cin * ks * ks);
+        const int T = ks * ks;
+        for (int o = 0; o < cout; o++)
+            for (int c = 0; c < cin; c++)
+                for (int t = 0; t < T; t++) out[((size_t)o * T + t) * cin + c] = src[((size_t)o * cin + c) * T + t];
+    };
+    n->params[name] = s; n->param_order.push_back(name);
+}
+// rows of a [rows, row_len] matrix scattered to dst rows dst_row0 + r*step (QKV concat, GEGLU interleave, emb concat)
+void reg_rows(Net* n, const std::string& name, float* dst_base, int rows, int row_len, int dst_row0, int step) {
+    ParamSlot s; s.numel = (size_t)rows * row_len; s.dst = dst_base; s.rows = rows; s.row_len = row_len; s.dst_row0 = dst_row0; s.dst_row_step = step;
+    n->params[name] = s; n->param_order.push_back(name);
+}
+// GEGLU proj [8C, C]: value rows j -> 2j, gate rows 4C+j -> 2j+1
+void reg_geglu(Net* n, const std::string& name, float* dst, int half_rows, int row_len) {
+    ParamSlot s; s.numel = (size_t)2 * half_rows * row_len; s.dst = dst; s.dst_numel = s.numel;
+    s.pack = [=](const float* src, std::vector<float>& out) {
+        out.resize((size_t)2 * half_rows * row_len);
+        for (int j = 0; j < half_rows; j++) {
+            memcpy(&out[(size_t)(2 * j) * row_len], &src[(size_t)j * row_len], row_len * sizeof(float));
+            memcpy(&out[(size_t)(2 * j + 1) * row_len], &src[(size_t)(half_rows + j) * row_len], row_len * sizeof(float));
+        }
+    };
+    n->params[name] = s; n->param_order.push_back(name);
+}
+
+Norm make_norm(Net* n, const std::string& p, int C) {
+    Norm r; r.C = C; r.g = walloc(n, C); r.b = walloc(n, C);
+    reg_plain(n, p + ".weight", r.g, C); reg_plain(n, p + ".bias", r.b, C);
+    return r;
+}
+Conv make_conv(Net* n, const std::string& p, int cin, int cout, int ks) {
+    Conv c; c.cin = cin; c.cout = cout; c.ks = ks; c.w = walloc(n, (size_t)cout * cin * ks * ks); c.b = walloc(n, cout);
+    reg_conv_w(n, p + ".weight", c.w, cout, cin, ks); reg_plain(n, p + ".bias", c.b, cout);
+    return c;
+}
+Lin make_lin(Net* n, const std::string& p, int in, int out, bool bias) {
+    Lin l; l.in = in; l.out = out; l.w = walloc(n, (size_t)in * out); reg_plain(n, p + ".weight", l.w, (size_t)in * out);
+    if (bias) { l.b = walloc(n, out); reg_plain(n, p + ".bias", l.b, out); }
+    return l;
+}
+
+int add_res(Net* n, const std::string& p, int cin, int cout) {
+    ResW r{}; r.cin = cin; r.cout = cout;
+    r.n1 = make_norm(n, p + ".in_layers.0", cin);
+    r.c1 = make_conv(n, p + ".in_layers.2", cin, cout, 3);
+    r.emb_off = n->emb_total; n->emb_total += cout;          // emb_layers.1 registered after emb_all is allocated
+    r.n2 = make_norm(n, p + ".out_layers.0", cout);
+    r.c2 = make_conv(n, p + ".out_layers.3", cout, cout, 3);
+    r.has_skip = cin != cout;
+    if (r.has_skip) r.skip = make_conv(n, p + ".skip_connection", cin, cout, 1);
+    n->res.push_back(r);
+    n->host_scratch.push_back(nullptr);
+    return (int)n->res.size() - 1;
+}
+std::vector<std::string> g_res_prefix;   // parallel to net->res during construction (single-threaded build)
+
+int add_st(Net* n, const std::string& p, int C, int heads, int ctx_dim) {
+    STW s{}; s.C = C; s.heads = heads; s.id = (int)n->sts.size();
+    s.norm = make_norm(n, p + ".norm", C);
+    s.proj_in = make_conv(n, p + ".proj_in", C, C, 1);
+    const std::string t = p + ".transformer_blocks.0";
+    s.qkv.in = C; s.qkv.out = 3 * C; s.qkv.w = walloc(n, (size_t)3 * C * C);
+    reg_rows(n, t + ".attn1.to_q.weight", s.qkv.w, C, C, 0, 1);
+    reg_rows(n, t + ".attn1.to_k.weight", s.qkv.w, C, C, C, 1);
+    reg_rows(n, t + ".attn1.to_v.weight", s.qkv.w, C, C, 2 * C, 1);
+    s.o1 = make_lin(n, t + ".attn1.to_out.0", C, C, true);
+    s.q2 = make_lin(n, t + ".attn2.to_q", C, C, false);
+    s.kv2.in = ctx_dim; s.kv2.out = 2 * C; s.kv2.w = walloc(n, (size_t)2 * C * ctx_dim);
+    reg_rows(n, t + ".attn2.to_k.weight", s.kv2.w, C, ctx_dim, 0, 1);
+    reg_rows(n, t + ".attn2.to_v.weight", s.kv2.w, C, ctx_dim, C, 1);
+    s.o2 = make_lin(n, t + ".attn2.to_out.0", C, C, true);
+    s.ff1.in = C; s.ff1.out = 8 * C; s.ff1.w = walloc(n, (size_t)8 * C * C); s.ff1.b = walloc(n, 8 * C);
+    reg_geglu(n, t + ".ff.net.0.proj.weight", s.ff1.w, 4 * C, C);
+    reg_geglu(n, t + ".ff.net.0.proj.bias", s.ff1.b, 4 * C, 1);
+    s.ff2 = make_lin(n, t + ".ff.net.2", 4 * C, C, true);
+    s.ln1 = make_norm(n, t + ".norm1", C); s.ln2 = make_norm(n, t + ".norm2", C); s.ln3 = make_norm(n, t + ".norm3", C);
+    s.proj_out = make_conv(n, p + ".proj_out", C, C, 1);
+    n->sts.push_back(s);
+    return s.id;
+}
+
+bool in_list(const int* v, int n, int x) { for (int i = 0; i < n; i++) if (v[i] == x) return true; return false; }
+
+// Mirrors UNetModel.__init__ (openaimodel.py:137-311).  Called twice: counting pass (wbase == nullptr) and placing pass.
+void build_net(Net* n) {
+    const rdm_unet_cfg& c = n->cfg;
+    n->woff = 0; n->params.clear(); n->param_order.clear(); n->res.clear(); n->sts.clear(); n->convs.clear();
+    n->in_blocks.clear(); n->out_blocks.clear(); n->mid = Block(); n->emb_total = 0; n->skip_ch.clear(); g_res_prefix.clear();
+    const int mc = c.model_channels; n->ted = 4 * mc;
+    n->te0 = make_lin(n, "time_embed.0", mc, n->ted, true);
+    n->te2 = make_lin(n, "time_embed.2", n->ted, n->ted, true);
+    auto heads_of = [&](int ch) { return c.num_head_channels > 0 ? ch / c.num_head_channels : c.num_heads; };
+    auto push_res = [&](Block& b, const std::string& p, int cin, int cout) { b.layers.push_back({L_RES, add_res(n, p, cin, cout)}); g_res_prefix.push_back(p); };
+
+    int ch = mc, ds = 1;
+    { Block b; n->convs.push_back(make_conv(n, "input_blocks.0.0", c.in_channels, mc, 3)); b.layers.push_back({L_CONV_IN, 0}); b.cout = mc; b.ds_after = 1; n->in_blocks.push_back(b); n->skip_ch.push_back(mc); }
+    for (int level = 0; level < c.n_channel_mult; level++) {
+        int mult = c.channel_mult[level];
+        for (int r = 0; r < c.num_res_blocks; r++) {
+            Block b; std::string p = "input_blocks." + std::to_string(n->in_blocks.size());
+            push_res(b, p + ".0", ch, mult * mc); ch = mult * mc;
+            if (in_list(c.attention_resolutions, c.n_attention_resolutions, ds)) b.layers.push_back({L_ST, add_st(n, p + ".1", ch, heads_of(ch), c.context_dim)});
+            b.cout = ch; b.ds_after = ds; n->in_blocks.push_back(b); n->skip_ch.push_back(ch);
+        }
+        if (level != c.n_channel_mult - 1) {
+            Block b; std::string p = "input_blocks." + std::to_string(n->in_blocks.size());
+            n->convs.push_back(make_conv(n, p + ".0.op", ch, ch, 3)); b.layers.push_back({L_DOWN, (int)n->convs.size() - 1});
+            ds *= 2; b.cout = ch; b.ds_after = ds; n->in_blocks.push_back(b); n->skip_ch.push_back(ch);
+        }
+    }
+    { Block& b = n->mid; push_res(b, "middle_block.0", ch, ch); b.layers.push_back({L_ST, add_st(n, "middle_block.1", ch, heads_of(ch), c.context_dim)});
+      push_res(b, "middle_block.2", ch, ch); b.cout = ch; b.ds_after = ds; }
+    std::vector<int> chans = n->skip_ch;
+    for (int level = c.n_channel_mult - 1; level >= 0; level--) {
+        int mult = c.channel_mult[level];
+        for (int i = 0; i <= c.num_res_blocks; i++) {
+            int ich = chans.back(); chans.pop_back();
+            Block b; std::string p = "output_blocks." + std::to_string(n->out_blocks.size());
+            int li = 0;
+            push_res(b, p + "." + std::to_string(li++), ch + ich, mc * mult); ch = mc * mult;
+            if (in_list(c.attention_resolutions, c.n_attention_resolutions, ds)) b.layers.push_back({L_ST, add_st(n, p + "." + std::to_string(li++), ch, heads_of(ch), c.context_dim)});
+            if (level && i == c.num_res_blocks) {
+                n->convs.push_back(make_conv(n, p + "." + std::to_string(li++) + ".conv", ch, ch, 3)); b.layers.push_back({L_UP, (int)n->convs.size() - 1});
+                ds /= 2;
+            }
+            b.cout = ch; b.ds_after = ds; n->out_blocks.push_back(b);
+        }
+    }
+    n->out_norm = make_norm(n, "out.0", ch);
+    n->out_conv = make_conv(n, "out.2", mc, c.out_channels, 3);
+    // all ResBlock emb_layers.1 as one [sum(cout), ted] matrix
+    n->emb_all.in = n->ted; n->emb_all.out = n->emb_total;
+    n->emb_all.w = walloc(n, (size_t)n->emb_total * n->ted); n->emb_all.b = walloc(n, n->emb_total);
+    for (size_t i = 0; i < n->res.size(); i++) {
+        reg_rows(n, g_res_prefix[i] + ".emb_layers.1.weight", n->emb_all.w, n->res[i].cout, n->ted, n->res[i].emb_off, 1);
+        reg_rows(n, g_res_prefix[i] + ".emb_layers.1.bias", n->emb_all.b, n->res[i].cout, 1, n->res[i].emb_off, 1);
+    }
+}
+
+// ---- forward ------------------------------------------------------------------------------------------
+struct Ctx { Net* n; cudaStream_t st; bool dry; int rc = RDM_OK; };
+#define RUN(expr) do { if (!cx.dry && cx.rc == RDM_OK) cx.rc = (expr); } while (0)
+
+double* stats_alloc(Ctx& cx, int B, int groups) {
+    Net* n = cx.n; size_t need = (size_t)B * groups * 2;
+    size_t o = n->stats_off; n->stats_off += need;
+    return cx.dry ? (double*)nullptr + o : n->stats + o;
+}
+
+void conv_gemm(Ctx& cx, const Act& x, const Conv& c, int stride, int ups, GemmEpi e) {
+    GemmA a; a.x = x.v.p; a.ld = x.v.ld; a.B = x.B; a.Hs = x.H; a.Ws = x.W; a.Cin = c.cin; a.ksize = c.ks; a.stride = stride; a.ups = ups;
+    a.Ho = ups ? x.H * 2 : (stride == 2 ? (x.H + 1) / 2 : x.H); a.Wo = ups ? x.W * 2 : (stride == 2 ? (x.W + 1) / 2 : x.W);
+    if (!e.bias) e.bias = c.b;
+    RUN(gemm_simt(a, c.w, c.cout, e, cx.st));
+}
+void lin_gemm(Ctx& cx, View x, int M, const Lin& l, GemmEpi e) {
+    GemmA a; a.x = x.p; a.ld = x.ld; a.B = M; a.Hs = 1; a.Ws = 1; a.Cin = l.in; a.Ho = 1; a.Wo = 1;
+    if (!e.bias) e.bias = l.b;
+    RUN(gemm_simt(a, l.w, l.out, e, cx.st));
+}
+GemmEpi epi_to(View out) { GemmEpi e; e.out = out.p; e.out_ld = out.ld; return e; }
+
+View fresh(Ctx& cx, int M, int C) { return View(cx.n->arena.allocf((size_t)M * C), C, C); }
+
+void gn(Ctx& cx, const Act& x, const Norm& nm, float eps, int silu, View y) {
+    double* s = stats_alloc(cx, x.B, 32);
+    RUN(k_gn_stats(x.v, x.B, x.H * x.W, 32, s, cx.st));
+    RUN(k_gn_apply(x.v, x.B, x.H * x.W, 32, s, eps, nm.g, nm.b, silu, y, cx.st));
+}
+
+void run_res(Ctx& cx, const ResW& r, const Act& x, const float* emb_all, View out) {
+    Arena& A = cx.n->arena; size_t mk = A.mark();
+    const int M = x.M();
+    View a1 = fresh(cx, M, r.cin);
+    gn(cx, x, r.n1, 1e-5f, 1, a1);
+    View h1 = fresh(cx, M, r.cout);
+    { GemmEpi e = epi_to(h1); e.rowvec = emb_all + r.emb_off; e.rowvec_ld = cx.n->emb_total; e.rows_per_batch = x.H * x.W;
+      conv_gemm(cx, Act{a1, x.B, x.H, x.W}, r.c1, 1, 0, e); }
+    View a2 = fresh(cx, M, r.cout);
+    gn(cx, Act{h1, x.B, x.H, x.W}, r.n2, 1e-5f, 1, a2);
+    View resv = x.v;
+    if (r.has_skip) { resv = fresh(cx, M, r.cout); conv_gemm(cx, x, r.skip, 1, 0, epi_to(resv)); }
+    { GemmEpi e = epi_to(out); e.res = resv.p; e.res_ld = resv.ld; conv_gemm(cx, Act{a2, x.B, x.H, x.W}, r.c2, 1, 0, e); }
+    A.release(mk);
+}
+
+void run_st(Ctx& cx, const STW& s, const Act& x, View out) {
+    Net* n = cx.n; Arena& A = n->arena; size_t mk = A.mark();
+    const int M = x.M(), C = s.C, N = x.H * x.W;
+    View a = fresh(cx, M, C);
+    gn(cx, x, s.norm, 1e-6f, 0, a);
+    View t0 = fresh(cx, M, C);
+    conv_gemm(cx, Act{a, x.B, x.H, x.W}, s.proj_in, 1, 0, epi_to(t0));
+    View nrm = fresh(cx, M, C);
+    // self-attention (attention.py:93)
+    RUN(k_layernorm(t0, M, s.ln1.g, s.ln1.b, 1e-5f, nrm, cx.st));
+    View qkv = fresh(cx, M, 3 * C);
+    lin_gemm(cx, nrm, M, s.qkv, epi_to(qkv));
+    View att = fresh(cx, M, C);
+    RUN(k_attention(qkv.cols(0, C), qkv.cols(C, C), qkv.cols(2 * C, C), x.B, N, N, s.heads, 0.17677669529663687f, att, cx.st));
+    View t1 = fresh(cx, M, C);
+    { GemmEpi e = epi_to(t1); e.res = t0.p; e.res_ld = t0.ld; lin_gemm(cx, att, M, s.o1, e); }
+    // cross-attention to the retrieved neighbours (attention.py:94); K/V were projected once in set_context
+    RUN(k_layernorm(t1, M, s.ln2.g, s.ln2.b, 1e-5f, nrm, cx.st));
+    View q2 = qkv.cols(0, C);                                    // reuse the qkv buffer
+    lin_gemm(cx, nrm, M, s.q2, epi_to(q2));
+    View kv(cx.dry ? nullptr : n->ctx_kv + n->ctx_off[s.id], 2 * C, 2 * C);
+    RUN(k_attention(q2, kv.cols(0, C), kv.cols(C, C), x.B, N, n->ctx_k, s.heads, 0.17677669529663687f, att, cx.st));
+    View t2 = t0;                                                // t0 is dead after t1 was formed
+    { GemmEpi e = epi_to(t2); e.res = t1.p; e.res_ld = t1.ld; lin_gemm(cx, att, M, s.o2, e); }
+    // GEGLU feed-forward (attention.py:95)
+    RUN(k_layernorm(t2, M, s.ln3.g, s.ln3.b, 1e-5f, nrm, cx.st));
+    View g = fresh(cx, M, 4 * C);
+    { GemmEpi e = epi_to(g); e.act = ACT_GEGLU; lin_gemm(cx, nrm, M, s.ff1, e); }
+    View t3 = t1;
+    { GemmEpi e = epi_to(t3); e.res = t2.p; e.res_ld = t2.ld; lin_gemm(cx, g, M, s.ff2, e); }
+    { GemmEpi e = epi_to(out); e.res = x.v.p; e.res_ld = x.v.ld; conv_gemm(cx, Act{t3, x.B, x.H, x.W}, s.proj_out, 1, 0, e); }
+    A.release(mk);
+}
+
+// debug: "<tag> mean absmean" of an [M, C] view (synchronises; only when rdm_unet_set_debug(h, 1))
+void debug_view(Ctx& cx, const char* tag, int a, int b, View v, int M) {
+    if (cx.dry || !cx.n->debug || cx.rc != RDM_OK) return;
+    std::vector<float> host((size_t)M * v.C);
+    cudaStreamSynchronize(cx.st);
+    if (cudaMemcpy2D(host.data(), (size_t)v.C * 4, v.p, (size_t)v.ld * 4, (size_t)v.C * 4, M, cudaMemcpyDeviceToHost) != cudaSuccess) { cx.n->debug_log += "memcpy failed\n"; return; }
+    double s = 0, sa = 0; for (float f : host) { s += f; sa += f < 0 ? -f : f; }
+    char line[160]; snprintf(line, sizeof(line), "%s %d %d %.9g %.9g\n", tag, a, b, s / host.size(), sa / host.size());
+    cx.n->debug_log += line;
+}
+
+// Runs the layers of one block; the LAST layer writes into `dst`.
+Act run_block(Ctx& cx, const Block& b, Act x, const float* emb_all, View dst) {
+    Net* n = cx.n;
+    for (size_t i = 0; i < b.layers.size(); i++) {
+        const Layer& L = b.layers[i];
+        const bool last = i + 1 == b.layers.size();
+        int Ho = x.H, Wo = x.W, Co = 0;
+        switch (L.kind) {
+            case L_CONV_IN: Co = n->convs[L.idx].cout; break;
+            case L_RES: Co = n->res[L.idx].cout; break;
+            case L_ST: Co = n->sts[L.idx].C; break;
+            case L_DOWN: Co = n->convs[L.idx].cout; Ho = (x.H + 1) / 2; Wo = (x.W + 1) / 2; break;
+            case L_UP: Co = n->convs[L.idx].cout; Ho = x.H * 2; Wo = x.W * 2; break;
+        }
+        View o = last ? dst : fresh(cx, x.B * Ho * Wo, Co);
+        switch (L.kind) {
+            case L_CONV_IN: conv_gemm(cx, x, n->convs[L.idx], 1, 0, epi_to(o)); break;
+            case L_RES: run_res(cx, n->res[L.idx], x, emb_all, o); break;
+            case L_ST: run_st(cx, n->sts[L.idx], x, o); break;
+            case L_DOWN: conv_gemm(cx, x, n->convs[L.idx], 2, 0, epi_to(o)); break;
+            case L_UP: conv_gemm(cx, x, n->convs[L.idx], 1, 1, epi_to(o)); break;
+        }
+        x = Act{View(o.p, o.ld, Co), x.B, Ho, Wo};
+        debug_view(cx, "layer", cx.n->debug_block, (int)i, x.v, x.M());
+    }
+    cx.n->debug_block++;
+    return x;
+}
+
+// x_nchw: [Bx, C, H, W] with Bx == B2 or B2/2 (then duplicated, ddim.py:233); t: int64 [B2] device; out NCHW [B2,...]
+int forward_impl(Net* n, const float* x_nchw, int Bx, const long long* t, int B2, int H, int W, float* out_nchw, cudaStream_t st, bool dry) {
+    Ctx cx{n, st, dry};
+    n->debug_block = 0; if (!dry) n->debug_log.clear();
+    Arena& A = n->arena; A.off = 0; A.dry = dry; n->stats_off = 0;
+    const rdm_unet_cfg& c = n->cfg;
+    const int nin = (int)n->in_blocks.size(), nout = (int)n->out_blocks.size();
+    // spatial size per input block output
+    std::vector<int> hH(nin), hW(nin);
+    { int h = H, w = W; for (int i = 0; i < nin; i++) { if (n->in_blocks[i].layers[0].kind == L_DOWN) { h = (h + 1) / 2; w = (w + 1) / 2; } hH[i] = h; hW[i] = w; } }
+    // concat buffers: output block j reads cat([h (ch_j), hs[nin-1-j] (ich_j)])
+    std::vector<View> cat(nout); std::vector<int> cat_ch(nout);
+    {
+        int ch = n->mid.cout;
+        for (int j = 0; j < nout; j++) {
+            int i = nin - 1 - j, ich = n->skip_ch[i];
+            cat_ch[j] = ch;
+            cat[j] = View(A.allocf((size_t)B2 * hH[i] * hW[i] * (ch + ich)), ch + ich, ch + ich);
+            ch = n->out_blocks[j].cout;
+        }
+    }
+    if (!dry) RDM_CHECK_CUDA(cudaMemsetAsync(n->stats, 0, n->stats_cap * sizeof(double), st));
+    // time embedding (openaimodel.py:352-353); only SiLU(emb) is ever consumed (ResBlock emb_layers = [SiLU, Linear])
+    View temb = fresh(cx, B2, c.model_channels), e1 = fresh(cx, B2, n->ted), semb = fresh(cx, B2, n->ted), emb_all = fresh(cx, B2, n->emb_total);
+    RUN(k_timestep_embedding(t, B2, c.model_channels, temb.p, st));
+    { GemmEpi e = epi_to(e1); e.act = ACT_SILU; lin_gemm(cx, temb, B2, n->te0, e); }
+    { GemmEpi e = epi_to(semb); e.act = ACT_SILU; lin_gemm(cx, e1, B2, n->te2, e); }
+    lin_gemm(cx, semb, B2, n->emb_all, epi_to(emb_all));
+    debug_view(cx, "temb", 0, 0, temb, B2); debug_view(cx, "semb", 0, 0, semb, B2); debug_view(cx, "emb_all", 0, 0, emb_all, B2);
+    // input
+    View x0 = fresh(cx, B2 * H * W, c.in_channels < 4 ? 4 : c.in_channels); x0.C = c.in_channels;
+    RUN(k_nchw_to_nhwc(x_nchw, Bx, B2, c.in_channels, H, W, x0, st));
+    Act h{x0, B2, H, W};
+    for (int i = 0; i < nin; i++) {
+        int j = nout - 1 - i;
+        View dst = cat[j].cols(cat_ch[j], n->skip_ch[i]);
+        h = run_block(cx, n->in_blocks[i], h, emb_all.p, dst);
+    }
+    {   // middle block writes into the first concat buffer's leading columns
+        View dst = cat[0].cols(0, cat_ch[0]);
+        h = run_block(cx, n->mid, h, emb_all.p, dst);
+    }
+    View last;
+    for (int j = 0; j < nout; j++) {
+        int i = nin - 1 - j;
+        Act in{cat[j], B2, hH[i], hW[i]};
+        View dst;
+        if (j + 1 < nout) dst = cat[j + 1].cols(0, cat_ch[j + 1]);
+        else { last = fresh(cx, B2 * H * W, n->out_blocks[j].cout); dst = last; }
+        h = run_block(cx, n->out_blocks[j], in, emb_all.p, dst);
+    }
+    // out = conv3x3(SiLU(GN(h)))  (openaimodel.py:312-316,371)
+    View a = fresh(cx, h.M(), h.v.C);
+    gn(cx, h, n->out_norm, 1e-5f, 1, a);
+    View o = fresh(cx, h.M(), 4); o.C = c.out_channels;
+    conv_gemm(cx, Act{a, h.B, h.H, h.W}, n->out_conv, 1, 0, epi_to(o));
+    debug_view(cx, "out", 0, 0, o, h.M());
+    RUN(k_nhwc_to_nchw(o, B2, c.out_channels, H, W, out_nchw, st));
+    return cx.rc;
+}
+
+int ensure_plan(Net* n, int B2, int H, int W) {
+    if (n->plan_B == B2 && n->plan_H == H && n->plan_W == W && n->arena.base) return RDM_OK;
+    n->arena.dry = true; n->arena.off = 0; n->arena.peak = 0; n->stats_off = 0;
+    RDM_TRY(forward_impl(n, nullptr, B2, nullptr, B2, H, W, nullptr, 0, true));
+    size_t need = n->arena.peak, sneed = n->stats_off;
+    if (need > n->arena.cap) {
+        if (n->arena.base) cudaFree(n->arena.base);
+        n->arena.base = nullptr; n->arena.cap = 0;
+        RDM_CHECK_CUDA(cudaMalloc((void**)&n->arena.base, need));
+        n->arena.cap = need;
+    }
+    if (sneed > n->stats_cap) {
+        if (n->stats) cudaFree(n->stats);
+        n->stats = nullptr; n->stats_cap = 0;
+        RDM_CHECK_CUDA(cudaMalloc((void**)&n->stats, sneed * sizeof(double)));
+        n->stats_cap = sneed;
+    }
+    n->plan_B = B2; n->plan_H = H; n->plan_W = W;
+    return RDM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rdm_unet_create(rdm_unet_t** out, const rdm_unet_cfg* cfg, int32_t device) {
+    RDM_REQUIRE(out && cfg, RDM_ERR_ARG, "rdm_unet_create: null argument");
+    RDM_REQUIRE(cfg->n_channel_mult >= 1 && cfg->n_channel_mult <= 8 && cfg->n_attention_resolutions >= 0 && cfg->n_attention_resolutions <= 8,
+                RDM_ERR_ARG, "rdm_unet_create: bad list sizes");
+    RDM_REQUIRE(cfg->model_channels % 32 == 0, RDM_ERR_UNSUPPORTED, "rdm_unet_create: model_channels must be a multiple of 32 (GroupNorm32)");
+    RDM_REQUIRE(cfg->num_head_channels == 32, RDM_ERR_UNSUPPORTED, "rdm_unet_create: only num_head_channels=32 is implemented (got %d)", cfg->num_head_channels);
+    RDM_REQUIRE(cfg->transformer_depth == 1, RDM_ERR_UNSUPPORTED, "rdm_unet_create: transformer_depth must be 1");
+    RDM_REQUIRE(cfg->context_dim > 0 && cfg->context_dim % 16 == 0, RDM_ERR_UNSUPPORTED, "rdm_unet_create: context_dim %d", cfg->context_dim);
+    DeviceGuard guard(device);
+    RDM_REQUIRE(guard.ok, RDM_ERR_CUDA, "rdm_unet_create: cannot select device %d", device);
+    rdm_unet* n = new rdm_unet();
+    n->device = device; n->cfg = *cfg;
+    build_net(n);                                   // counting pass
+    n->wfloats = n->woff;
+    if (cudaMalloc((void**)&n->wbase, n->wfloats * sizeof(float)) != cudaSuccess) { delete n; rdm_set_error("rdm_unet_create: cudaMalloc(%zu) for weights failed", n->wfloats * 4); return RDM_ERR_CUDA; }
+    cudaMemset(n->wbase, 0, n->wfloats * sizeof(float));
+    build_net(n);                                   // placing pass
+    // context K/V offsets
+    size_t off = 0; n->ctx_off.resize(n->sts.size());
+    for (auto& s : n->sts) { n->ctx_off[s.id] = off; off += (size_t)2 * s.C; }      // per context row; scaled by rows in set_context
+    *out = n;
+    return RDM_OK;
+}
+
+void rdm_unet_destroy(rdm_unet_t* n) {
+    if (!n) return;
+    DeviceGuard guard(n->device);
+    if (n->wbase) cudaFree(n->wbase);
+    if (n->arena.base) cudaFree(n->arena.base);
+    if (n->stats) cudaFree(n->stats);
+    if (n->ctx_kv) cudaFree(n->ctx_kv);
+    if (n->t_dev) cudaFree(n->t_dev);
+    delete n;
+}
+
+int64_t rdm_unet_num_params(const rdm_unet_t* n) { return n ? (int64_t)n->param_order.size() : 0; }
+const char* rdm_unet_param_name(const rdm_unet_t* n, int64_t i) { return (n && i >= 0 && i < (int64_t)n->param_order.size()) ? n->param_order[i].c_str() : nullptr; }
+int64_t rdm_unet_param_numel(const rdm_unet_t* n, const char* name) {
+    if (!n || !name) return -1;
+    auto it = n->params.find(name);
+    return it == n->params.end() ? -1 : (int64_t)it->second.numel;
+}
+
+int rdm_unet_load(rdm_unet_t* n, const char* name, const float* host, int64_t numel) {
+    RDM_REQUIRE(n && name && host, RDM_ERR_ARG, "rdm_unet_load: null argument");
+    auto it = n->params.find(name);
+    RDM_REQUIRE(it != n->params.end(), RDM_ERR_ARG, "rdm_unet_load: unknown parameter '%s'", name);
+    ParamSlot& s = it->second;
+    RDM_REQUIRE((size_t)numel == s.numel, RDM_ERR_ARG, "rdm_unet_load: '%s' has %lld elements, expected %zu", name, (long long)numel, s.numel);
+    DeviceGuard guard(n->device);
+    if (s.rows > 0) {
+        RDM_CHECK_CUDA(cudaMemcpy2D(s.dst + (size_t)s.dst_row0 * s.row_len, (size_t)s.dst_row_step * s.row_len * sizeof(float), host,
+                                    (size_t)s.row_len * sizeof(float), (size_t)s.row_len * sizeof(float), s.rows, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> packed;
+        s.pack(host, packed);
+        const float* src = packed.empty() ? host : packed.data();
+        RDM_CHECK_CUDA(cudaMemcpy(s.dst, src, s.dst_numel * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    s.loaded = true;
+    n->ctx_B = 0;           // projections of a previously set context are stale
+    return RDM_OK;
+}
+
+int64_t rdm_unet_missing(const rdm_unet_t* n) {
+    if (!n) return -1;
+    int64_t m = 0; for (auto& kv : n->params) if (!kv.second.loaded) m++;
+    return m;
+}
+
+int rdm_unet_set_debug(rdm_unet_t* n, int32_t on) { RDM_REQUIRE(n, RDM_ERR_ARG, "rdm_unet_set_debug: null handle"); n->debug = on; return RDM_OK; }
+const char* rdm_unet_debug_log(const rdm_unet_t* n) { return n ? n->debug_log.c_str() : ""; }
+
+int rdm_unet_set_mode(rdm_unet_t* n, int32_t mode) {
+    RDM_REQUIRE(n, RDM_ERR_ARG, "rdm_unet_set_mode: null handle");
+    RDM_REQUIRE(mode == RDM_UNET_MODE_FP32, RDM_ERR_UNSUPPORTED, "rdm_unet_set_mode: mode %d not available", mode);
+    n->mode = mode; return RDM_OK;
+}
+
+int rdm_unet_set_context(rdm_unet_t* n, const float* ctx, int32_t B2, int32_t k, void* stream) {
+    RDM_REQUIRE(n && ctx, RDM_ERR_ARG, "rdm_unet_set_context: null argument");
+    RDM_REQUIRE(B2 >= 1 && k >= 1, RDM_ERR_ARG, "rdm_unet_set_context: B2=%d k=%d", B2, k);
+    RDM_REQUIRE(rdm_unet_missing(n) == 0, RDM_ERR_STATE, "rdm_unet_set_context: %lld parameters not loaded", (long long)rdm_unet_missing(n));
+    DeviceGuard guard(n->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rows = B2 * k;
+    size_t per_row = 0; for (auto& s : n->sts) per_row += (size_t)2 * s.C;
+    size_t need = per_row * rows;
+    if (need > n->ctx_kv_floats) {
+        if (n->ctx_kv) cudaFree(n->ctx_kv);
+        n->ctx_kv = nullptr; n->ctx_kv_floats = 0;
+        RDM_CHECK_CUDA(cudaMalloc((void**)&n->ctx_kv, need * sizeof(float)));
+        n->ctx_kv_floats = need;
+    }
+    size_t off = 0;
+    Ctx cx{n, st, false};
+    for (auto& s : n->sts) {
+        n->ctx_off[s.id] = off;
+        View dst(n->ctx_kv + off, 2 * s.C, 2 * s.C);
+        lin_gemm(cx, View(const_cast<float*>(ctx), n->cfg.context_dim, n->cfg.context_dim), rows, s.kv2, epi_to(dst));
+        off += (size_t)2 * s.C * rows;
+    }
+    n->ctx_B = B2; n->ctx_k = k;
+    return cx.rc;
+}
+
+int rdm_unet_forward(rdm_unet_t* n, const float* x, int32_t Bx, const int64_t* t, int32_t B2, int32_t H, int32_t W, float* eps_out, void* stream) {
+    RDM_REQUIRE(n && x && t && eps_out, RDM_ERR_ARG, "rdm_unet_forward: null argument");
+    RDM_REQUIRE(B2 >= 1 && (Bx == B2 || Bx * 2 == B2), RDM_ERR_ARG, "rdm_unet_forward: Bx=%d must equal B2=%d or B2/2", Bx, B2);
+    RDM_REQUIRE(n->ctx_B == B2, RDM_ERR_STATE, "rdm_unet_forward: context was set for batch %d, forward called with %d (call rdm_unet_set_context first)", n->ctx_B, B2);
+    int div = 1; for (int i = 1; i < n->cfg.n_channel_mult; i++) div *= 2;
+    RDM_REQUIRE(H % div == 0 && W % div == 0, RDM_ERR_ARG, "rdm_unet_forward: H=%d W=%d must be multiples of %d", H, W, div);
+    DeviceGuard guard(n->device);
+    RDM_TRY(ensure_plan(n, B2, H, W));
+    return forward_impl(n, x, Bx, (const long long*)t, B2, H, W, eps_out, (cudaStream_t)stream, false);
+}
+
+int rdm_ddim_step(const float* x, const float* eps, int64_t n_per_half, int32_t cfg, float scale, const float* coef_dev,
+                  const float* noise, float* x_prev, float* pred_x0, int32_t device, void* stream) {
+    RDM_REQUIRE(x && eps && coef_dev && x_prev, RDM_ERR_ARG, "rdm_ddim_step: null argument");
+    DeviceGuard guard(device);
+    return k_ddim_update(x, eps, n_per_half, cfg, scale, coef_dev, noise, x_prev, pred_x0, (cudaStream_t)stream);
+}
+
+}  // extern "C"

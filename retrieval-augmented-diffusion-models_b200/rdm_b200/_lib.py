@@ -27,6 +27,19 @@ SIGNATURES = {
     "rdm_knn_search": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdm_knn_merge": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "rdm_knn_gather": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "rdm_unet_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int32]),
+    "rdm_unet_destroy": (None, [c_void_p]),
+    "rdm_unet_num_params": (c_int64, [c_void_p]),
+    "rdm_unet_param_name": (c_char_p, [c_void_p, c_int64]),
+    "rdm_unet_param_numel": (c_int64, [c_void_p, c_char_p]),
+    "rdm_unet_load": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "rdm_unet_missing": (c_int64, [c_void_p]),
+    "rdm_unet_set_mode": (c_int, [c_void_p, c_int32]),
+    "rdm_unet_set_debug": (c_int, [c_void_p, c_int32]),
+    "rdm_unet_debug_log": (c_char_p, [c_void_p]),
+    "rdm_unet_set_context": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "rdm_unet_forward": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "rdm_ddim_step": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
 }
 
 

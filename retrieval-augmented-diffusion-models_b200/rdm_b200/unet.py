@@ -1,0 +1,196 @@
+"""Host wrapper of the U-Net executor in librdm_b200 (csrc/unet.cu).
+
+``unet_param_shapes`` restates the parameter inventory of the reference's ``UNetModel.__init__``
+(``rdm/modules/diffusionmodules/openaimodel.py:137-317``; key names per SURVEY.md Appendix C) so the
+Python mirror can own real ``nn.Parameter`` tensors with the checkpoint's names and shapes; the C++ side
+builds the same inventory independently and ``B200UNet.__init__`` asserts that both agree name by name.
+"""
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+
+MODE_FP32 = 0
+
+
+class UNetCfg(ctypes.Structure):
+    _fields_ = [("in_channels", ctypes.c_int32), ("model_channels", ctypes.c_int32), ("out_channels", ctypes.c_int32),
+                ("num_res_blocks", ctypes.c_int32), ("n_attention_resolutions", ctypes.c_int32),
+                ("attention_resolutions", ctypes.c_int32 * 8), ("n_channel_mult", ctypes.c_int32),
+                ("channel_mult", ctypes.c_int32 * 8), ("num_head_channels", ctypes.c_int32), ("num_heads", ctypes.c_int32),
+                ("transformer_depth", ctypes.c_int32), ("context_dim", ctypes.c_int32)]
+
+
+def make_cfg(in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, channel_mult,
+             num_head_channels=32, num_heads=-1, transformer_depth=1, context_dim=512):
+    c = UNetCfg()
+    c.in_channels, c.model_channels, c.out_channels, c.num_res_blocks = in_channels, model_channels, out_channels, num_res_blocks
+    ar, cm = [int(a) for a in attention_resolutions], [int(m) for m in channel_mult]
+    assert len(ar) <= 8 and len(cm) <= 8
+    c.n_attention_resolutions, c.n_channel_mult = len(ar), len(cm)
+    for i, a in enumerate(ar):
+        c.attention_resolutions[i] = a
+    for i, m in enumerate(cm):
+        c.channel_mult[i] = m
+    c.num_head_channels, c.num_heads, c.transformer_depth, c.context_dim = num_head_channels, num_heads, transformer_depth, int(context_dim)
+    return c
+
+
+def unet_param_shapes(in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, channel_mult,
+                      context_dim=512, **_):
+    """name -> shape, in the reference's registration order (openaimodel.py:137-317)."""
+    P = OrderedDict()
+    mc, ted = model_channels, 4 * model_channels
+
+    def lin(p, i, o, bias=True):
+        P[p + ".weight"] = (o, i)
+        if bias:
+            P[p + ".bias"] = (o,)
+
+    def conv(p, i, o, k):
+        P[p + ".weight"] = (o, i, k, k)
+        P[p + ".bias"] = (o,)
+
+    def norm(p, c):
+        P[p + ".weight"] = (c,)
+        P[p + ".bias"] = (c,)
+
+    def res(p, i, o):
+        norm(p + ".in_layers.0", i); conv(p + ".in_layers.2", i, o, 3)
+        lin(p + ".emb_layers.1", ted, o)
+        norm(p + ".out_layers.0", o); conv(p + ".out_layers.3", o, o, 3)
+        if i != o:
+            conv(p + ".skip_connection", i, o, 1)
+
+    def st(p, c):
+        norm(p + ".norm", c); conv(p + ".proj_in", c, c, 1)
+        t = p + ".transformer_blocks.0"
+        def attn(a, cd):
+            lin(t + a + ".to_q", c, c, False); lin(t + a + ".to_k", cd, c, False); lin(t + a + ".to_v", cd, c, False)
+            lin(t + a + ".to_out.0", c, c)
+        attn(".attn1", c)                                                   # registration order of attention.py:80-86
+        lin(t + ".ff.net.0.proj", c, 8 * c); lin(t + ".ff.net.2", 4 * c, c)
+        attn(".attn2", context_dim)
+        for i in (1, 2, 3):
+            norm(t + f".norm{i}", c)
+        conv(p + ".proj_out", c, c, 1)
+
+    lin("time_embed.0", mc, ted); lin("time_embed.2", ted, ted)
+    conv("input_blocks.0.0", in_channels, mc, 3)
+    chans, ch, ds, nb = [mc], mc, 1, 1
+    for level, mult in enumerate(channel_mult):
+        for _ in range(num_res_blocks):
+            res(f"input_blocks.{nb}.0", ch, mult * mc); ch = mult * mc
+            if ds in attention_resolutions:
+                st(f"input_blocks.{nb}.1", ch)
+            chans.append(ch); nb += 1
+        if level != len(channel_mult) - 1:
+            conv(f"input_blocks.{nb}.0.op", ch, ch, 3); chans.append(ch); nb += 1; ds *= 2
+    res("middle_block.0", ch, ch); st("middle_block.1", ch); res("middle_block.2", ch, ch)
+    nb = 0
+    for level, mult in list(enumerate(channel_mult))[::-1]:
+        for i in range(num_res_blocks + 1):
+            li = 0
+            res(f"output_blocks.{nb}.{li}", ch + chans.pop(), mc * mult); ch = mc * mult; li += 1
+            if ds in attention_resolutions:
+                st(f"output_blocks.{nb}.{li}", ch); li += 1
+            if level and i == num_res_blocks:
+                conv(f"output_blocks.{nb}.{li}.conv", ch, ch, 3); ds //= 2
+            nb += 1
+    norm("out.0", ch); conv("out.2", mc, out_channels, 3)
+    return P
+
+
+class B200UNet:
+    """Owns one ``rdm_unet_t`` handle.  ``forward`` == ``UNetModel.forward`` (openaimodel.py:335-371)."""
+
+    def __init__(self, device, **cfg):
+        L = _lib.lib()
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.cfg = dict(cfg)
+        self.shapes = unet_param_shapes(**cfg)
+        c = make_cfg(cfg["in_channels"], cfg["model_channels"], cfg["out_channels"], cfg["num_res_blocks"],
+                     cfg["attention_resolutions"], cfg["channel_mult"], cfg.get("num_head_channels", 32),
+                     cfg.get("num_heads", -1), cfg.get("transformer_depth", 1), cfg.get("context_dim", 512))
+        self._h = ctypes.c_void_p()
+        _lib.check(L.rdm_unet_create(ctypes.byref(self._h), ctypes.byref(c), self.device.index), "rdm_unet_create")
+        names = [L.rdm_unet_param_name(self._h, i).decode() for i in range(L.rdm_unet_num_params(self._h))]
+        assert sorted(names) == sorted(self.shapes), "parameter inventory of csrc/unet.cu and unet_param_shapes() differ"
+        for k, shp in self.shapes.items():
+            n = 1
+            for s in shp:
+                n *= s
+            assert L.rdm_unet_param_numel(self._h, k.encode()) == n, k
+        self._ctx_key = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().rdm_unet_destroy(h)
+            except Exception:
+                pass
+
+    def load_state_dict(self, sd, strict=True):
+        """sd: name -> tensor with the reference's names/shapes (any device/dtype; converted to host fp32)."""
+        L = _lib.lib()
+        missing = [k for k in self.shapes if k not in sd]
+        if strict and missing:
+            raise RuntimeError(f"missing U-Net parameters: {missing[:5]}{'...' if len(missing) > 5 else ''}")
+        for k, shp in self.shapes.items():
+            if k not in sd:
+                continue
+            t = sd[k].detach()
+            if tuple(t.shape) != tuple(shp):
+                raise RuntimeError(f"size mismatch for {k}: {tuple(t.shape)} vs {tuple(shp)}")
+            t = t.to("cpu", torch.float32).contiguous()
+            _lib.check(L.rdm_unet_load(self._h, k.encode(), ctypes.c_void_p(t.data_ptr()), t.numel()), f"rdm_unet_load({k})")
+        self._ctx_key = None
+        return missing
+
+    def missing(self):
+        return int(_lib.lib().rdm_unet_missing(self._h))
+
+    def set_mode(self, mode):
+        _lib.check(_lib.lib().rdm_unet_set_mode(self._h, int(mode)), "rdm_unet_set_mode")
+
+    def set_context(self, context):
+        """context: CUDA float32 [B2, k, context_dim]."""
+        if isinstance(context, (list, tuple)):
+            assert len(context) == 1
+            context = context[0]
+        context = context.to(self.device, torch.float32).contiguous()
+        B2, k, d = context.shape
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().rdm_unet_set_context(self._h, _lib.ptr(context), B2, k, _lib.stream_ptr(self.device)), "rdm_unet_set_context")
+        self._ctx_B2 = B2
+
+    def forward(self, x, t, out=None):
+        """x: CUDA float32 NCHW [Bx, C, H, W] (Bx == B2 or B2/2), t: int64 [B2] -> eps [B2, C_out, H, W]."""
+        x = x.to(self.device, torch.float32).contiguous()
+        t = t.to(self.device, torch.int64).contiguous()
+        B2, (Bx, _, H, W) = t.shape[0], x.shape
+        if out is None:
+            out = torch.empty((B2, self.cfg["out_channels"], H, W), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().rdm_unet_forward(self._h, _lib.ptr(x), Bx, _lib.ptr(t), B2, H, W, _lib.ptr(out), _lib.stream_ptr(self.device)),
+                       "rdm_unet_forward")
+        return out
+
+
+def ddim_step(x, eps, coef_row, cfg_scale=None, noise=None, want_pred_x0=True):
+    """One fused CFG + DDIM update (ddim.py:236-238,253-267).  x [B,...], eps [2B,...] if cfg_scale is not None else [B,...];
+    coef_row: CUDA float32 [>=5] = {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma}."""
+    x, eps = x.contiguous(), eps.contiguous()
+    xp = torch.empty_like(x)
+    p0 = torch.empty_like(x) if want_pred_x0 else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().rdm_ddim_step(_lib.ptr(x), _lib.ptr(eps), x.numel(), 1 if cfg_scale is not None else 0,
+                                            float(cfg_scale if cfg_scale is not None else 1.0), _lib.ptr(coef_row),
+                                            _lib.ptr(noise.contiguous() if noise is not None else None), _lib.ptr(xp), _lib.ptr(p0),
+                                            x.device.index, _lib.stream_ptr(x.device)), "rdm_ddim_step")
+    return xp, p0

@@ -38,8 +38,8 @@ def test_search_matches_oracle(cuda, dtype, n, nq, k):
     assert np.array_equal(idx.cpu().numpy()[:, :kk], ri[:, :kk]), "kNN indices must be bit-exact"
     assert np.array_equal(sc.cpu().numpy()[:, :kk].view(np.uint64), rs[:, :kk].view(np.uint64)), "fp64 scores must be bit-exact"
     assert np.array_equal(dist.cpu().numpy()[:, :kk], rd[:, :kk])
-    if n > 5000:
-        assert list(idx[0, :4].cpu().numpy()) == [7, 1234, 4321, n - 1]
+    if n > 5000 and nq >= 2:
+        assert list(idx[0, :4].cpu().numpy()) == [7, 1234, 4321, n - 1]     # query 0 is DB row 7; its exact duplicates tie -> index order
 
 
 def test_scann_shaped_api_and_gather(cuda):

@@ -1,0 +1,102 @@
+"""GPU parity: librdm_b200 U-Net forward / DDIM (through the C ABI) vs the torch-CPU fp32 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddim as oddim
+from oracle import unet as ounet
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def _pair(cfg, seed, cuda):
+    from rdm_b200.unet import B200UNet
+    ref = ounet.randomize_(ounet.UNetModel(**cfg), seed).eval()
+    net = B200UNet(cuda, **cfg)
+    net.load_state_dict(ref.state_dict())
+    assert net.missing() == 0
+    return ref, net
+
+
+@pytest.mark.parametrize("B2,H,k", [(2, 16, 4), (3, 8, 1), (4, 24, 8)])
+def test_tiny_unet_forward_strict(cuda, B2, H, k):
+    ref, net = _pair(ounet.TINY_UNET, 1, cuda)
+    g = torch.Generator().manual_seed(B2 * 100 + H)
+    x = torch.randn(B2, 4, H, H, generator=g)
+    t = torch.randint(0, 1000, (B2,), generator=g)
+    c = torch.randn(B2, k, 512, generator=g) * 3
+    with torch.no_grad():
+        want = ref(x, t, c)
+    net.set_context(c.to(cuda))
+    got = net.forward(x.to(cuda), t.to(cuda))
+    err = rel_l2(got, want)
+    assert err < 1e-4, f"strict fp32 forward rel-L2 {err:.2e} (tolerance 1e-4, SURVEY 8d)"
+
+
+def test_cfg_doubling_without_materialising_the_batch(cuda):
+    ref, net = _pair(ounet.TINY_UNET, 2, cuda)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 4, 16, 16, generator=g)
+    t = torch.full((4,), 501)
+    c = torch.cat([torch.randn(2, 4, 512, generator=g), torch.zeros(2, 4, 512)])      # [cond | uncond=0] (ddpm.py:673-680, label 0)
+    with torch.no_grad():
+        want = ref(torch.cat([x] * 2), t, c)
+    net.set_context(c.to(cuda))
+    got = net.forward(x.to(cuda), t.to(cuda))          # Bx = B2/2
+    assert rel_l2(got, want) < 1e-4
+
+
+def test_full_arch_forward_strict(cuda):
+    """BASELINE cfg2 architecture (mc 192, mult 1-2-3-5, 16 SpatialTransformers) on the 32x32x4 latent, B2 = 2."""
+    ref, net = _pair(ounet.BASELINE_UNET, 3, cuda)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 4, 32, 32, generator=g)
+    t = torch.tensor([991, 991])
+    c = torch.cat([torch.randn(1, 4, 512, generator=g) * 3, torch.zeros(1, 4, 512)])
+    with torch.no_grad():
+        want = ref(x, t, c)
+    net.set_context(c.to(cuda))
+    got = net.forward(x.to(cuda), t.to(cuda))
+    err = rel_l2(got, want)
+    assert err < 1e-4, f"rel-L2 {err:.2e}"
+
+
+def test_ddim_step_is_bit_exact(cuda):
+    from rdm_b200.unet import ddim_step
+    sch = oddim.Schedule(100)
+    g = torch.Generator().manual_seed(3)
+    x, e = torch.randn(3, 4, 8, 8, generator=g), torch.randn(6, 4, 8, 8, generator=g)
+    for index in (0, 50, 99):
+        a_t, a_prev, sigma, s1m = sch.coeffs(index)
+        e_t = e[3:] + 2.0 * (e[:3] - e[3:])
+        xp_ref, p0_ref = oddim.ddim_update(x, e_t, a_t, a_prev, sigma, s1m)
+        coef = torch.stack([s1m, a_t.sqrt(), a_prev.sqrt(), (1.0 - a_prev - sigma ** 2).sqrt(), sigma]).to(cuda)
+        xp, p0 = ddim_step(x.to(cuda), e.to(cuda), coef, cfg_scale=2.0)
+        assert torch.equal(xp.cpu(), xp_ref) and torch.equal(p0.cpu(), p0_ref)
+
+
+def test_ddim_trajectory_tiny(cuda):
+    """10 chained CFG steps with the tiny U-Net: final latents within 1e-3 rel of the fp32 oracle (north_star tolerance)."""
+    from rdm_b200.unet import ddim_step
+    ref, net = _pair(ounet.TINY_UNET, 5, cuda)
+    g = torch.Generator().manual_seed(21)
+    B, S, scale = 2, 10, 2.0
+    x_T = torch.randn(B, 4, 16, 16, generator=g)
+    cond, unc = torch.randn(B, 4, 512, generator=g) * 3, torch.zeros(B, 4, 512)
+    want = oddim.ddim_sample(ref, x_T, cond, unc, S=S, scale=scale)
+    sch = oddim.Schedule(S)
+    net.set_context(torch.cat([cond, unc]).to(cuda))
+    x = x_T.to(cuda)
+    for i, step in enumerate(np.flip(sch.timesteps)):
+        index = S - i - 1
+        a_t, a_prev, sigma, s1m = sch.coeffs(index)
+        coef = torch.stack([s1m, a_t.sqrt(), a_prev.sqrt(), (1.0 - a_prev - sigma ** 2).sqrt(), sigma]).to(cuda)
+        eps = net.forward(x, torch.full((2 * B,), int(step), device=cuda))
+        x, _ = ddim_step(x, eps, coef, cfg_scale=scale)
+    err = rel_l2(x, want)
+    assert err < 1e-3, f"DDIM-10 final latent rel-L2 {err:.2e}"
