@@ -1,0 +1,390 @@
+// tcgen05 tensor-core implicit GEMM for the U-Net contractions (sm_100a only).
+//
+//   out[M,N] = epi( A[M,K] * W[N,K]^T ),   A / W stored as bf16 "hi" (+ "lo") planes:
+//       x ~= hi + lo,  hi = bf16_rn(x), lo = bf16_rn(x - hi)            (2^-17 relative)
+//   NSPLIT = 3:  acc += A_hi*W_hi + A_lo*W_hi + A_hi*W_lo   (fp32-grade contraction on the bf16 tensor pipe)
+//   NSPLIT = 1:  acc += A_hi*W_hi                            (plain bf16)
+//
+// One 128 x BN output tile per CTA, K swept in 64-element blocks:
+//   warp 0   : TMA producer -- cp.async.bulk.tensor.4d into 128B-swizzled shared-memory stages; a 3x3 conv is
+//              9 shifted box loads of the NHWC plane (TMA out-of-bounds zero fill *is* the conv padding), so no
+//              im2col buffer exists; 1x1 convs / Linear layers use the same path with a degenerate box
+//   warp 1   : allocates TMEM, one elected lane issues tcgen05.mma (kind::f16, M=128, N=BN, K=16) with the
+//              fp32 accumulator in TMEM, tcgen05.commit releases stages / signals the epilogue
+//   warps 2-5: epilogue -- tcgen05.ld 32 lanes x 32 columns, bias / per-sample row vector (time embedding) /
+//              SiLU / GEGLU / residual, fp32 or bf16-plane stores
+// full/empty mbarrier ring between producer and MMA issuer; tmem_full mbarrier between issuer and epilogue.
+#include "kernels.cuh"
+#include "gemm_tc.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace {
+
+constexpr int BM = 128, BK = 64, TC_THREADS = 192;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) {        // ~2 s: a lost TMA/MMA completion must not hang the GPU
+            printf("gemm_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) { asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory"); }
+
+// K-major, 128-byte swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);        // start address  [0,14)
+    d |= (uint64_t)1 << 16;                              // leading byte offset (ignored for swizzled K-major) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                              // descriptor version [46,48)
+    d |= (uint64_t)2 << 61;                              // SWIZZLE_128B [61,64)
+    return d;
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M=128
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+
+struct TcKernelParams {
+    int M, N;                  // valid rows / columns of the output
+    int taps, kb_per_tap;      // K blocks: taps * kb_per_tap, each BK=64 wide
+    int ksize;                 // 1 or 3 (tap -> (dy,dx))
+    int plain;                 // 1: A is a plain [M, C] matrix encoded as (c, m, 1, 1): tile -> x0 = mt*128
+    int bw, bh, bb;            // box extents (x, y, batch): bw*bh*bb == 128
+    int H, W;                  // logical output grid per image (for tile -> (b,y,x))
+    // epilogue
+    const float* bias; const float* rowvec; int rowvec_ld; int rows_per_batch;
+    const float* res; int res_ld; int act;
+    float* out; int out_ld;                                // fp32 output (or null)
+    __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_bf_ld;   // bf16-plane output (or null)
+};
+
+template <int BN, int NSPLIT, int STAGES>
+struct TcSmem {
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int NSPLIT, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcKernelParams p) {
+    using S = TcSmem<BN, NSPLIT, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, mt = blockIdx.y;
+    const int nkb = p.taps * p.kb_per_tap;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA_hi); prefetch_tmap(&tmB_hi);
+        if (NSPLIT == 3) { prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_lo); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // tile origin in (x, y, b) of the NHWC plane
+            int x0 = 0, y0 = 0, b0 = 0;
+            if (p.plain) x0 = mt * BM;
+            else if (p.bb > 1 || p.bh * p.bw == p.H * p.W) b0 = mt * p.bb;
+            else { int tiles_per_img = (p.H * p.W) / BM; b0 = mt / tiles_per_img; y0 = (mt % tiles_per_img) * p.bh; }
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * S::STAGE_BYTES;
+                mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                const int tap = kb / p.kb_per_tap, kc = (kb - tap * p.kb_per_tap) * BK;
+                const int dy = p.ksize == 3 ? tap / 3 - 1 : 0, dx = p.ksize == 3 ? tap % 3 - 1 : 0;
+                tma_load_4d(st, &tmA_hi, &full[s], kc, x0 + dx, y0 + dy, b0);
+                tma_load_2d(st + S::A_BYTES, &tmB_hi, &full[s], kb * BK, n0);
+                if (NSPLIT == 3) {
+                    tma_load_4d(st + S::A_BYTES + S::B_BYTES, &tmA_lo, &full[s], kc, x0 + dx, y0 + dy, b0);
+                    tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmB_lo, &full[s], kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BN);
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES), b_hi = a_hi + S::A_BYTES;
+                const uint32_t a_lo = b_hi + S::B_BYTES, b_lo = a_lo + S::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / 16; k++) {
+                    const uint64_t da = umma_desc_sw128(a_hi + k * 32), db = umma_desc_sw128(b_hi + k * 32);
+                    umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+                    if (NSPLIT == 3) {
+                        umma_bf16(tmem_base, umma_desc_sw128(a_lo + k * 32), db, idesc, 1);
+                        umma_bf16(tmem_base, da, umma_desc_sw128(b_lo + k * 32), idesc, 1);
+                    }
+                }
+                umma_commit(&empty[s]);                // frees the stage once the MMAs above have read it
+            }
+            umma_commit(tmem_full);                    // accumulator complete
+        }
+    } else {
+        // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+        const int q = warp & 3;
+        const int row = q * 32 + lane, m = mt * BM + row;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const bool mvalid = m < p.M;
+        const int bidx = mvalid ? m / p.rows_per_batch : 0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c++) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+            const int nb = n0 + c * 32;
+            if (!mvalid || nb >= p.N) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                float t = __uint_as_float(r[j]);
+                const int n = nb + j;
+                if (n < p.N) {
+                    if (p.bias) t += __ldg(p.bias + n);
+                    if (p.rowvec) t += __ldg(p.rowvec + (size_t)bidx * p.rowvec_ld + n);
+                }
+                v[j] = t;
+            }
+            if (p.act == ACT_GEGLU) {
+                // (value, gate) column pairs -> 16 outputs at columns nb/2 ..
+                const int no = nb >> 1;
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
+                const int nvalid = min(16, (p.N - nb) >> 1);
+                if (p.out) {
+                    float* dst = p.out + (size_t)m * p.out_ld + no;
+                    for (int j = 0; j < nvalid; j++) dst[j] = o[j] + (p.res ? p.res[(size_t)m * p.res_ld + no + j] : 0.f);
+                } else {
+                    __nv_bfloat16* dh = p.out_hi + (size_t)m * p.out_bf_ld + no;
+                    __nv_bfloat16* dl = p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + no : nullptr;
+                    for (int j = 0; j < nvalid; j++) {
+                        __nv_bfloat16 h = __float2bfloat16_rn(o[j]);
+                        dh[j] = h;
+                        if (dl) dl[j] = __float2bfloat16_rn(o[j] - __bfloat162float(h));
+                    }
+                }
+            } else {
+                const int nvalid = min(32, p.N - nb);
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (p.act == ACT_SILU) v[j] = silu_f(v[j]);
+                if (p.res) {
+                    const float* rs = p.res + (size_t)m * p.res_ld + nb;
+                    if (nvalid == 32 && ((p.res_ld & 3) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) { float4 t = *reinterpret_cast<const float4*>(rs + j); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+                    } else {
+                        for (int j = 0; j < nvalid; j++) v[j] += rs[j];
+                    }
+                }
+                if (p.out) {
+                    float* dst = p.out + (size_t)m * p.out_ld + nb;
+                    if (nvalid == 32 && ((p.out_ld & 3) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+                        for (int j = 0; j < nvalid; j++) dst[j] = v[j];
+                    }
+                } else {
+                    __nv_bfloat16* dh = p.out_hi + (size_t)m * p.out_bf_ld + nb;
+                    __nv_bfloat16* dl = p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + nb : nullptr;
+                    for (int j = 0; j < nvalid; j++) {
+                        __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+                        dh[j] = h;
+                        if (dl) dl[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr; cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    }
+    return fn;
+}
+
+// 4D bf16 tensor (c, x, y, b) with row stride `ld` elements; box (64, bw, bh, bb); 128B swizzle, zero OOB fill
+int make_map_4d(CUtensorMap* tm, const void* base, int C, int W, int H, int B, int ld, int bw, int bh, int bb) {
+    auto enc = get_encode();
+    RDM_REQUIRE(enc, RDM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * W, (cuuint64_t)ld * 2 * W * H};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RDM_REQUIRE(r == CUDA_SUCCESS, RDM_ERR_CUDA, "cuTensorMapEncodeTiled(4d: C=%d W=%d H=%d B=%d ld=%d box %d,%d,%d) failed: %d", C, W, H, B, ld, bw, bh, bb, (int)r);
+    return RDM_OK;
+}
+int make_map_2d(CUtensorMap* tm, const void* base, int K, int rows, int ld, int box_rows) {
+    auto enc = get_encode();
+    RDM_REQUIRE(enc, RDM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RDM_REQUIRE(r == CUDA_SUCCESS, RDM_ERR_CUDA, "cuTensorMapEncodeTiled(2d: K=%d rows=%d ld=%d box %d) failed: %d", K, rows, ld, box_rows, (int)r);
+    return RDM_OK;
+}
+
+template <int BN, int NSPLIT, int STAGES>
+int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcKernelParams& p, cudaStream_t st) {
+    auto kern = gemm_tc_kernel<BN, NSPLIT, STAGES>;
+    constexpr int smem = TcSmem<BN, NSPLIT, STAGES>::TOTAL;
+    static bool configured[16] = {false};
+    int dev = 0; cudaGetDevice(&dev);
+    if (!configured[dev & 15]) {
+        RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured[dev & 15] = true;
+    }
+    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
+    kern<<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    RDM_COUNT_LAUNCH();
+    RDM_CHECK_CUDA(cudaGetLastError());
+    return RDM_OK;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const TcA& a) {
+    if (a.C % BK != 0 || a.ld % 8 != 0) return false;
+    if (a.ksize == 1) return true;
+    // 3x3: a 128-row tile must be an (x, y, b) box of the image
+    const int W = a.W, H = a.H;
+    if (W > BM || (BM % W) != 0) return false;
+    const int rows_y = BM / W;                        // image rows per tile if H is large enough
+    if (H >= rows_y) return H % rows_y == 0;
+    return (BM % (W * H)) == 0;
+}
+
+int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_bf_ld, int nsplit, cudaStream_t st) {
+    RDM_REQUIRE(gemm_tc_supported(a), RDM_ERR_UNSUPPORTED, "gemm_tc: shape not supported (C=%d W=%d H=%d ks=%d)", a.C, a.W, a.H, a.ksize);
+    RDM_REQUIRE(a.hi && w.hi && (nsplit == 1 || (a.lo && w.lo)), RDM_ERR_ARG, "gemm_tc: missing operand plane");
+    RDM_REQUIRE(w.K == a.ksize * a.ksize * a.C && w.ld % 8 == 0, RDM_ERR_ARG, "gemm_tc: weight K=%d vs %d", w.K, a.ksize * a.ksize * a.C);
+    TcKernelParams p{};
+    const int M = a.B * a.H * a.W;
+    p.M = M; p.N = w.N; p.taps = a.ksize * a.ksize; p.kb_per_tap = a.C / BK; p.ksize = a.ksize; p.H = a.H; p.W = a.W;
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    if (a.ksize == 1) {
+        // plain [M, C] matrix: box = 128 rows
+        p.plain = 1; p.bw = BM; p.bh = 1; p.bb = 1;
+        // encode as (c, m, 1, 1): x = m
+        RDM_TRY(make_map_4d(&ta_hi, a.hi, a.C, M, 1, 1, a.ld, BM, 1, 1));
+        if (nsplit == 3) RDM_TRY(make_map_4d(&ta_lo, a.lo, a.C, M, 1, 1, a.ld, BM, 1, 1)); else ta_lo = ta_hi;
+    } else {
+        const int W = a.W, H = a.H;
+        p.bw = W; p.bh = (BM / W) < H ? (BM / W) : H; p.bb = BM / (p.bw * p.bh);
+        RDM_TRY(make_map_4d(&ta_hi, a.hi, a.C, W, H, a.B, a.ld, p.bw, p.bh, p.bb));
+        if (nsplit == 3) RDM_TRY(make_map_4d(&ta_lo, a.lo, a.C, W, H, a.B, a.ld, p.bw, p.bh, p.bb)); else ta_lo = ta_hi;
+    }
+    p.bias = e.bias; p.rowvec = e.rowvec; p.rowvec_ld = e.rowvec_ld; p.rows_per_batch = e.rows_per_batch > 0 ? e.rows_per_batch : 1;
+    p.res = e.res; p.res_ld = e.res_ld; p.act = e.act; p.out = e.out; p.out_ld = e.out_ld;
+    p.out_hi = out_hi; p.out_lo = out_lo; p.out_bf_ld = out_bf_ld;
+    RDM_REQUIRE((p.out != nullptr) != (p.out_hi != nullptr), RDM_ERR_ARG, "gemm_tc: exactly one of fp32 / bf16 outputs");
+    // tile width: fill the machine
+    const int mtiles = (M + BM - 1) / BM;
+    int BN = 128;
+    if (w.N <= 32) BN = 32; else if (w.N <= 64 || mtiles * ((w.N + 127) / 128) < 120) BN = 64;
+    RDM_TRY(make_map_2d(&tb_hi, w.hi, w.K, w.N, w.ld, BN));
+    if (nsplit == 3) RDM_TRY(make_map_2d(&tb_lo, w.lo, w.K, w.N, w.ld, BN)); else tb_lo = tb_hi;
+    if (nsplit == 3) {
+        if (BN == 128) return launch_tc<128, 3, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        if (BN == 64) return launch_tc<64, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        return launch_tc<32, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+    }
+    if (BN == 128) return launch_tc<128, 1, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+    if (BN == 64) return launch_tc<64, 1, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+    return launch_tc<32, 1, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+}

@@ -1,0 +1,17 @@
+// tcgen05 GEMM engine interface (gemm_tc.cu).  Operands are bf16 hi/lo planes (x ~= hi + lo).
+#pragma once
+#include "kernels.cuh"
+
+struct TcA {                       // activation operand: NHWC plane [B*H*W, C] (row stride ld elements)
+    const __nv_bfloat16* hi = nullptr; const __nv_bfloat16* lo = nullptr; int ld = 0;
+    int B = 1, H = 1, W = 1, C = 0;
+    int ksize = 1;                 // 1: plain [M, C] matrix (B*H*W rows); 3: 3x3 / pad 1 / stride 1 conv over the (H, W) grid
+};
+struct TcW {                       // weights [N, K] K-major, K ordered (tap, cin)
+    const __nv_bfloat16* hi = nullptr; const __nv_bfloat16* lo = nullptr; int ld = 0;
+    int N = 0, K = 0;
+};
+bool gemm_tc_supported(const TcA& a);
+// nsplit 3: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-grade);  nsplit 1: A_hi*W_hi (bf16).
+// Output either fp32 (e.out) or bf16 planes (out_hi[/out_lo]); e.res / e.bias / e.rowvec / e.act as for gemm_simt.
+int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_bf_ld, int nsplit, cudaStream_t st);

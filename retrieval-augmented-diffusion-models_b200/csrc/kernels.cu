@@ -11,6 +11,23 @@ constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
 
+// 4 consecutive channels of row m starting at column c (c % 4 == 0)
+__device__ __forceinline__ void store4(const Out4& o, size_t m, int c, float a, float b, float cc, float d) {
+    if (o.f) *reinterpret_cast<float4*>(o.f + m * o.ldf + c) = make_float4(a, b, cc, d);
+    if (o.hi) {
+        __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b), h2 = __float2bfloat16_rn(cc), h3 = __float2bfloat16_rn(d);
+        __nv_bfloat162 p0 = __halves2bfloat162(h0, h1), p1 = __halves2bfloat162(h2, h3);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(o.hi + m * o.ldb + c) = pk;
+        if (o.lo) {
+            __nv_bfloat162 q0 = __halves2bfloat162(__float2bfloat16_rn(a - __bfloat162float(h0)), __float2bfloat16_rn(b - __bfloat162float(h1)));
+            __nv_bfloat162 q1 = __halves2bfloat162(__float2bfloat16_rn(cc - __bfloat162float(h2)), __float2bfloat16_rn(d - __bfloat162float(h3)));
+            uint2 pl; pl.x = *reinterpret_cast<uint32_t*>(&q0); pl.y = *reinterpret_cast<uint32_t*>(&q1);
+            *reinterpret_cast<uint2*>(o.lo + m * o.ldb + c) = pl;
+        }
+    }
+}
+
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int Bsrc, int Bout, int C, int HW, float* __restrict__ out, int ld) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over Bout*HW*C, c fastest
     long long total = (long long)Bout * HW * C;
@@ -80,7 +97,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int ld, int C, int 
 }
 
 __global__ void gn_apply_kernel(const float* __restrict__ x, int ld, int C, int HW, int groups, const double* __restrict__ sums, float eps,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu, float* __restrict__ y, int ldy, long long total4) {
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu, Out4 y, Out4 raw, long long total4) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over M * C/4
     if (i >= total4) return;
     const int V = C / 4, cpg = C / groups;
@@ -98,12 +115,13 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int ld, int C, int 
         float val = (e[t] - (float)mean) * rstd * gamma[c] + beta[c];
         o[t] = silu ? silu_f(val) : val;
     }
-    *reinterpret_cast<float4*>(y + m * ldy + v * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    store4(y, (size_t)m, v * 4, o[0], o[1], o[2], o[3]);
+    if (raw.any()) store4(raw, (size_t)m, v * 4, e[0], e[1], e[2], e[3]);
 }
 
 // one warp per row, two-pass (mean, then centred variance) in fp32 from registers/L1
 __global__ void layernorm_kernel(const float* __restrict__ x, int ld, int C, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 float eps, float* __restrict__ y, int ldy) {
+                                 float eps, Out4 y) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= M) return;
     const float* xr = x + (size_t)row * ld;
@@ -122,13 +140,11 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ld, int C, int
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(FULL, ss, m);
     const float rstd = rsqrtf(ss / (float)C + eps);
-    float* yr = y + (size_t)row * ldy;
     for (int v = lane; v < V; v += 32) {
         float4 q = *reinterpret_cast<const float4*>(xr + v * 4);
         float4 g = *reinterpret_cast<const float4*>(gamma + v * 4), bb = *reinterpret_cast<const float4*>(beta + v * 4);
-        float4 o = make_float4((q.x - mean) * rstd * g.x + bb.x, (q.y - mean) * rstd * g.y + bb.y,
-                               (q.z - mean) * rstd * g.z + bb.z, (q.w - mean) * rstd * g.w + bb.w);
-        *reinterpret_cast<float4*>(yr + v * 4) = o;
+        store4(y, (size_t)row, v * 4, (q.x - mean) * rstd * g.x + bb.x, (q.y - mean) * rstd * g.y + bb.y,
+               (q.z - mean) * rstd * g.z + bb.z, (q.w - mean) * rstd * g.w + bb.w);
     }
 }
 
@@ -136,7 +152,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ld, int C, int
 // memory in tiles of KT keys (broadcast reads), online softmax in fp32.  grid (ceil(Nq/blockDim), heads, B).
 constexpr int KT = 64;
 __global__ void attention_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
-                                     int Nq, int Nk, float scale_log2e, float* __restrict__ out, int ldo) {
+                                     int Nq, int Nk, float scale_log2e, Out4 out) {
     __shared__ float4 sk[KT][8], sv[KT][8];
     const int b = blockIdx.z, h = blockIdx.y;
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,10 +205,38 @@ __global__ void attention_d32_kernel(const float* __restrict__ q, int ldq, const
     }
     if (active) {
         const float inv = 1.f / l;
-        float4* op = reinterpret_cast<float4*>(out + ((size_t)b * Nq + qi) * ldo + h * 32);
 #pragma unroll
-        for (int i = 0; i < 8; i++) op[i] = make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
+        for (int i = 0; i < 8; i++) store4(out, (size_t)b * Nq + qi, h * 32 + 4 * i, acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
     }
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ x, int ld, int C, long long total4, Out4 y) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int V = C / 4; int v = (int)(i % V); long long m = i / V;
+    float4 q = *reinterpret_cast<const float4*>(x + m * ld + v * 4);
+    store4(y, (size_t)m, v * 4, q.x, q.y, q.z, q.w);
+}
+
+__global__ void im2col_s2_kernel(const float* __restrict__ x, int ld, int C, int B, int H, int W, int Ho, int Wo, long long total4, Out4 y) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over Mo * 9 * C/4
+    if (i >= total4) return;
+    const int V = C / 4; int v = (int)(i % V); long long r = i / V;
+    int tap = (int)(r % 9); long long mo = r / 9;
+    int ox = (int)(mo % Wo); long long t = mo / Wo; int oy = (int)(t % Ho), b = (int)(t / Ho);
+    int iy = oy * 2 + tap / 3 - 1, ix = ox * 2 + tap % 3 - 1;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) q = *reinterpret_cast<const float4*>(x + ((size_t)(b * H + iy) * W + ix) * ld + v * 4);
+    store4(y, (size_t)mo, tap * C + v * 4, q.x, q.y, q.z, q.w);
+}
+
+__global__ void upsample2x_kernel(const float* __restrict__ x, int ld, int C, int B, int H, int W, long long total4, Out4 y) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over B*2H*2W * C/4
+    if (i >= total4) return;
+    const int V = C / 4; int v = (int)(i % V); long long mo = i / V;
+    int ox = (int)(mo % (2 * W)); long long t = mo / (2 * W); int oy = (int)(t % (2 * H)), b = (int)(t / (2 * H));
+    float4 q = *reinterpret_cast<const float4*>(x + ((size_t)(b * H + (oy >> 1)) * W + (ox >> 1)) * ld + v * 4);
+    store4(y, (size_t)mo, v * 4, q.x, q.y, q.z, q.w);
 }
 
 __global__ void silu_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
@@ -244,22 +288,41 @@ int k_gn_stats(View x, int B, int HW, int groups, double* sums, cudaStream_t st)
     gn_stats_kernel<<<dim3(chunks, B), 256, 2 * groups * sizeof(float), st>>>(x.p, x.ld, x.C, HW, groups, rows_per_cta, sums);
     LAUNCH_CHECK(); return RDM_OK;
 }
-int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps, const float* gamma, const float* beta, int silu, View y, cudaStream_t st) {
-    RDM_REQUIRE(x.C % 4 == 0 && y.ld % 4 == 0, RDM_ERR_ARG, "gn_apply: alignment");
+int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps, const float* gamma, const float* beta, int silu, Out4 y, Out4 raw, cudaStream_t st) {
+    RDM_REQUIRE(x.C % 4 == 0 && y.ldf % 4 == 0 && y.ldb % 4 == 0, RDM_ERR_ARG, "gn_apply: alignment");
     long long total4 = (long long)B * HW * (x.C / 4);
-    gn_apply_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(x.p, x.ld, x.C, HW, groups, sums, eps, gamma, beta, silu, y.p, y.ld, total4);
+    gn_apply_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(x.p, x.ld, x.C, HW, groups, sums, eps, gamma, beta, silu, y, raw, total4);
     LAUNCH_CHECK(); return RDM_OK;
 }
-int k_layernorm(View x, int M, const float* gamma, const float* beta, float eps, View y, cudaStream_t st) {
+int k_layernorm(View x, int M, const float* gamma, const float* beta, float eps, Out4 y, cudaStream_t st) {
     RDM_REQUIRE(x.C % 4 == 0, RDM_ERR_ARG, "layernorm: C %% 4");
-    layernorm_kernel<<<blocks_for(M, 8), 256, 0, st>>>(x.p, x.ld, x.C, M, gamma, beta, eps, y.p, y.ld);
+    layernorm_kernel<<<blocks_for(M, 8), 256, 0, st>>>(x.p, x.ld, x.C, M, gamma, beta, eps, y);
     LAUNCH_CHECK(); return RDM_OK;
 }
-int k_attention(View q, View k, View v, int B, int Nq, int Nk, int heads, float scale, View out, cudaStream_t st) {
+int k_attention(View q, View k, View v, int B, int Nq, int Nk, int heads, float scale, Out4 out, cudaStream_t st) {
     RDM_REQUIRE(q.C == heads * 32, RDM_ERR_UNSUPPORTED, "attention: only d_head=32 is implemented (C=%d heads=%d)", q.C, heads);
     int threads = Nq >= 128 ? 128 : ((Nq + 31) / 32) * 32;
     dim3 grid((Nq + threads - 1) / threads, heads, B);
-    attention_d32_kernel<<<grid, threads, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, Nq, Nk, scale * 1.4426950408889634f, out.p, out.ld);
+    attention_d32_kernel<<<grid, threads, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, Nq, Nk, scale * 1.4426950408889634f, out);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_split_planes(View x, long long M, Out4 y, cudaStream_t st) {
+    RDM_REQUIRE(x.C % 4 == 0 && x.ld % 4 == 0, RDM_ERR_ARG, "split_planes: alignment");
+    long long total4 = M * (x.C / 4);
+    split_planes_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(x.p, x.ld, x.C, total4, y);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_im2col_s2(View x, int B, int H, int W, Out4 y, cudaStream_t st) {
+    RDM_REQUIRE(x.C % 4 == 0 && x.ld % 4 == 0, RDM_ERR_ARG, "im2col_s2: alignment");
+    int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    long long total4 = (long long)B * Ho * Wo * 9 * (x.C / 4);
+    im2col_s2_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(x.p, x.ld, x.C, B, H, W, Ho, Wo, total4, y);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_upsample2x(View x, int B, int H, int W, Out4 y, cudaStream_t st) {
+    RDM_REQUIRE(x.C % 4 == 0 && x.ld % 4 == 0, RDM_ERR_ARG, "upsample2x: alignment");
+    long long total4 = (long long)B * 4 * H * W * (x.C / 4);
+    upsample2x_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(x.p, x.ld, x.C, B, H, W, total4, y);
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_silu(const float* in, float* out, long long n, cudaStream_t st) {

@@ -13,6 +13,16 @@ struct View {            // [M, C] fp32 matrix view
     View cols(int c0, int n) const { return View(p + c0, ld, n); }
 };
 
+// Destination of an element-wise producer: fp32 view and/or bf16 hi(/lo) planes (x ~= hi + lo) for the tcgen05 engine.
+struct Out4 {
+    float* f = nullptr; int ldf = 0;
+    __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; int ldb = 0;
+    __host__ __device__ Out4() {}
+    Out4(View v) : f(v.p), ldf(v.ld) {}
+    Out4(__nv_bfloat16* h, __nv_bfloat16* l, int ld) : hi(h), lo(l), ldb(ld) {}
+    __host__ __device__ bool any() const { return f || hi; }
+};
+
 // ---- implicit-GEMM description: out[M,N] = epi( A[M,K] * W[N,K]^T ) -----------------------------
 struct GemmA {
     const float* x = nullptr; int ld = 0;   // source NHWC view [B*Hs*Ws, Cin]
@@ -43,11 +53,17 @@ int k_timestep_embedding(const long long* t, int B, int dim, float* out, cudaStr
 int k_gn_stats(View x, int B, int HW, int groups, double* sums, cudaStream_t st);
 // y = (x-mean)*rstd*gamma+beta, optional SiLU; y is a contiguous-or-strided fp32 view
 int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps, const float* gamma, const float* beta,
-               int silu, View y, cudaStream_t st);
+               int silu, Out4 y, Out4 raw, cudaStream_t st);      // raw (optional): the un-normalised x re-emitted (skip 1x1 conv operand)
 // LayerNorm over the last dim of [M, C] (eps 1e-5), one warp per row
-int k_layernorm(View x, int M, const float* gamma, const float* beta, float eps, View y, cudaStream_t st);
+int k_layernorm(View x, int M, const float* gamma, const float* beta, float eps, Out4 y, cudaStream_t st);
 // softmax(q k^T * scale) v for heads of width 32.  q: [B*Nq, heads*32] view, k/v: [B*Nk, heads*32] views.
-int k_attention(View q, View k, View v, int B, int Nq, int Nk, int heads, float scale, View out, cudaStream_t st);
+int k_attention(View q, View k, View v, int B, int Nq, int Nk, int heads, float scale, Out4 out, cudaStream_t st);
+// fp32 [M, C] -> bf16 planes
+int k_split_planes(View x, long long M, Out4 y, cudaStream_t st);
+// im2col of a 3x3 / stride 2 / pad 1 conv (ldm Downsample): x NHWC [B,H,W,C] -> [B*Ho*Wo, 9*C] (tap-major), Ho=(H+1)/2
+int k_im2col_s2(View x, int B, int H, int W, Out4 y, cudaStream_t st);
+// nearest-neighbour 2x upsample (ldm Upsample): x NHWC [B,H,W,C] -> [B,2H,2W,C]
+int k_upsample2x(View x, int B, int H, int W, Out4 y, cudaStream_t st);
 // out[i] = silu(in[i])
 int k_silu(const float* in, float* out, long long n, cudaStream_t st);
 // DDIM update with classifier-free guidance (ddim.py:236-238,258-267).  x NHWC [B*HW, C]; eps [2B*HW, C] (cond first) or [B*HW,C] if !cfg.

@@ -7,6 +7,7 @@
 // Hoisted out of the step loop: cross-attention K/V projections of the (step-invariant) retrieved context
 // (attention.py:47-48 -> rdm_unet_set_context), and all 25 ResBlock emb_layers as ONE GEMM per forward.
 #include "kernels.cuh"
+#include "gemm_tc.cuh"
 #include "../../include/rdm_b200.h"
 #include <functional>
 #include <string>
@@ -53,6 +54,7 @@ struct rdm_unet {
     int mode = 0;
     // weights
     float* wbase = nullptr; size_t wfloats = 0, woff = 0;
+    __nv_bfloat16* wb_hi = nullptr; __nv_bfloat16* wb_lo = nullptr; bool planes_dirty = true;   // bf16 planes of the weight arena (same offsets)
     std::unordered_map<std::string, ParamSlot> params;
     std::vector<std::string> param_order;
     std::vector<ResW> res; std::vector<STW> sts; std::vector<Conv> convs;   // convs: conv_in, downs, ups
@@ -234,80 +236,154 @@ void build_net(Net* n) {
 struct Ctx { Net* n; cudaStream_t st; bool dry; int rc = RDM_OK; };
 #define RUN(expr) do { if (!cx.dry && cx.rc == RDM_OK) cx.rc = (expr); } while (0)
 
+// GEMM operand / result: an fp32 view (CUDA-core engine) or bf16 hi/lo planes (tcgen05 engine)
+struct Opnd {
+    View f; __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; int ldb = 0;
+    bool tc() const { return hi != nullptr; }
+    Out4 out4() const { return tc() ? Out4(hi, lo, ldb) : Out4(f); }
+};
+Opnd from_view(View v) { Opnd o; o.f = v; return o; }
+
 double* stats_alloc(Ctx& cx, int B, int groups) {
     Net* n = cx.n; size_t need = (size_t)B * groups * 2;
     size_t o = n->stats_off; n->stats_off += need;
     return cx.dry ? (double*)nullptr + o : n->stats + o;
 }
-
-void conv_gemm(Ctx& cx, const Act& x, const Conv& c, int stride, int ups, GemmEpi e) {
-    GemmA a; a.x = x.v.p; a.ld = x.v.ld; a.B = x.B; a.Hs = x.H; a.Ws = x.W; a.Cin = c.cin; a.ksize = c.ks; a.stride = stride; a.ups = ups;
-    a.Ho = ups ? x.H * 2 : (stride == 2 ? (x.H + 1) / 2 : x.H); a.Wo = ups ? x.W * 2 : (stride == 2 ? (x.W + 1) / 2 : x.W);
-    if (!e.bias) e.bias = c.b;
-    RUN(gemm_simt(a, c.w, c.cout, e, cx.st));
-}
-void lin_gemm(Ctx& cx, View x, int M, const Lin& l, GemmEpi e) {
-    GemmA a; a.x = x.p; a.ld = x.ld; a.B = M; a.Hs = 1; a.Ws = 1; a.Cin = l.in; a.Ho = 1; a.Wo = 1;
-    if (!e.bias) e.bias = l.b;
-    RUN(gemm_simt(a, l.w, l.out, e, cx.st));
-}
-GemmEpi epi_to(View out) { GemmEpi e; e.out = out.p; e.out_ld = out.ld; return e; }
-
 View fresh(Ctx& cx, int M, int C) { return View(cx.n->arena.allocf((size_t)M * C), C, C); }
+Opnd fresh_opnd(Ctx& cx, int M, int C, bool tc) {
+    Opnd o;
+    if (!tc) { o.f = fresh(cx, M, C); return o; }
+    o.hi = (__nv_bfloat16*)cx.n->arena.alloc((size_t)M * C * 2);
+    if (cx.n->mode == RDM_UNET_MODE_TC_BF16X3) o.lo = (__nv_bfloat16*)cx.n->arena.alloc((size_t)M * C * 2);
+    o.ldb = C; o.f.C = C;
+    return o;
+}
+bool tc_ok(Ctx& cx, int B, int H, int W, int C, int ks) {
+    if (cx.n->mode == RDM_UNET_MODE_FP32) return false;
+    TcA a; a.B = B; a.H = H; a.W = W; a.C = C; a.ksize = ks; a.ld = C;
+    return gemm_tc_supported(a);
+}
+const __nv_bfloat16* w_hi(Net* n, const float* w) { return n->wb_hi + (w - n->wbase); }
+const __nv_bfloat16* w_lo(Net* n, const float* w) { return n->mode == RDM_UNET_MODE_TC_BF16X3 ? n->wb_lo + (w - n->wbase) : nullptr; }
 
-void gn(Ctx& cx, const Act& x, const Norm& nm, float eps, int silu, View y) {
+// out = epi(conv/linear(a)).  a: [B*H*W, C] operand; ks 1|3 (stride 1, pad ks/2) on the tensor-core engine;
+// stride / ups only exist on the CUDA-core engine (the TC path materialises im2col / upsampled planes instead).
+void gemm_any(Ctx& cx, const Opnd& a, int B, int H, int W, int C, int ks, int stride, int ups, const float* w, const float* bias, int N,
+              GemmEpi e, const Opnd& out) {
+    Net* n = cx.n;
+    if (!e.bias) e.bias = bias;
+    const int Ho = ups ? H * 2 : (stride == 2 ? (H + 1) / 2 : H), Wo = ups ? W * 2 : (stride == 2 ? (W + 1) / 2 : W);
+    const int M = B * Ho * Wo, Nout = e.act == ACT_GEGLU ? N / 2 : N;
+    if (a.tc()) {
+        TcA ta; ta.hi = a.hi; ta.lo = a.lo; ta.ld = a.ldb; ta.B = B; ta.H = H; ta.W = W; ta.C = C; ta.ksize = ks;
+        TcW tw; tw.hi = w_hi(n, w); tw.lo = w_lo(n, w); tw.N = N; tw.K = ks * ks * C; tw.ld = tw.K;
+        const int nsplit = n->mode == RDM_UNET_MODE_TC_BF16X3 ? 3 : 1;
+        if (out.tc()) { e.out = nullptr; RUN(gemm_tc(ta, tw, e, out.hi, out.lo, out.ldb, nsplit, cx.st)); }
+        else { e.out = out.f.p; e.out_ld = out.f.ld; RUN(gemm_tc(ta, tw, e, nullptr, nullptr, 0, nsplit, cx.st)); }
+        return;
+    }
+    GemmA ga; ga.x = a.f.p; ga.ld = a.f.ld; ga.B = B; ga.Hs = H; ga.Ws = W; ga.Cin = C; ga.ksize = ks; ga.stride = stride; ga.ups = ups; ga.Ho = Ho; ga.Wo = Wo;
+    if (out.tc()) {      // CUDA-core producer feeding a tensor-core consumer: fp32 temporary, then split
+        size_t mk = n->arena.mark();
+        View tmp = fresh(cx, M, Nout);
+        e.out = tmp.p; e.out_ld = tmp.ld;
+        RUN(gemm_simt(ga, w, N, e, cx.st));
+        RUN(k_split_planes(tmp, M, out.out4(), cx.st));
+        n->arena.release(mk);
+    } else {
+        e.out = out.f.p; e.out_ld = out.f.ld;
+        RUN(gemm_simt(ga, w, N, e, cx.st));
+    }
+}
+void conv_any(Ctx& cx, const Opnd& a, const Act& g, const Conv& c, GemmEpi e, const Opnd& out) {
+    gemm_any(cx, a, g.B, g.H, g.W, c.cin, c.ks, 1, 0, c.w, c.b, c.cout, e, out);
+}
+void lin_any(Ctx& cx, const Opnd& a, int M, const Lin& l, GemmEpi e, const Opnd& out) {
+    gemm_any(cx, a, M, 1, 1, l.in, 1, 1, 0, l.w, l.b, l.out, e, out);
+}
+
+void gn(Ctx& cx, const Act& x, const Norm& nm, float eps, int silu, const Opnd& y, const Opnd* raw = nullptr) {
     double* s = stats_alloc(cx, x.B, 32);
     RUN(k_gn_stats(x.v, x.B, x.H * x.W, 32, s, cx.st));
-    RUN(k_gn_apply(x.v, x.B, x.H * x.W, 32, s, eps, nm.g, nm.b, silu, y, cx.st));
+    RUN(k_gn_apply(x.v, x.B, x.H * x.W, 32, s, eps, nm.g, nm.b, silu, y.out4(), raw ? raw->out4() : Out4(), cx.st));
 }
 
 void run_res(Ctx& cx, const ResW& r, const Act& x, const float* emb_all, View out) {
     Arena& A = cx.n->arena; size_t mk = A.mark();
     const int M = x.M();
-    View a1 = fresh(cx, M, r.cin);
-    gn(cx, x, r.n1, 1e-5f, 1, a1);
+    const bool tc1 = tc_ok(cx, x.B, x.H, x.W, r.cin, 3), tc2 = tc_ok(cx, x.B, x.H, x.W, r.cout, 3);
+    const bool tcs = r.has_skip && tc_ok(cx, x.B, x.H, x.W, r.cin, 1);
+    Opnd a1 = fresh_opnd(cx, M, r.cin, tc1), xraw;
+    if (tcs) xraw = fresh_opnd(cx, M, r.cin, true);
+    gn(cx, x, r.n1, 1e-5f, 1, a1, tcs ? &xraw : nullptr);
     View h1 = fresh(cx, M, r.cout);
-    { GemmEpi e = epi_to(h1); e.rowvec = emb_all + r.emb_off; e.rowvec_ld = cx.n->emb_total; e.rows_per_batch = x.H * x.W;
-      conv_gemm(cx, Act{a1, x.B, x.H, x.W}, r.c1, 1, 0, e); }
-    View a2 = fresh(cx, M, r.cout);
+    { GemmEpi e; e.rowvec = emb_all + r.emb_off; e.rowvec_ld = cx.n->emb_total; e.rows_per_batch = x.H * x.W;
+      conv_any(cx, a1, x, r.c1, e, from_view(h1)); }
+    Opnd a2 = fresh_opnd(cx, M, r.cout, tc2);
     gn(cx, Act{h1, x.B, x.H, x.W}, r.n2, 1e-5f, 1, a2);
     View resv = x.v;
-    if (r.has_skip) { resv = fresh(cx, M, r.cout); conv_gemm(cx, x, r.skip, 1, 0, epi_to(resv)); }
-    { GemmEpi e = epi_to(out); e.res = resv.p; e.res_ld = resv.ld; conv_gemm(cx, Act{a2, x.B, x.H, x.W}, r.c2, 1, 0, e); }
+    if (r.has_skip) { resv = fresh(cx, M, r.cout); conv_any(cx, tcs ? xraw : from_view(x.v), x, r.skip, GemmEpi(), from_view(resv)); }
+    { GemmEpi e; e.res = resv.p; e.res_ld = resv.ld; conv_any(cx, a2, x, r.c2, e, from_view(out)); }
     A.release(mk);
 }
 
 void run_st(Ctx& cx, const STW& s, const Act& x, View out) {
     Net* n = cx.n; Arena& A = n->arena; size_t mk = A.mark();
     const int M = x.M(), C = s.C, N = x.H * x.W;
-    View a = fresh(cx, M, C);
+    const float scale = 0.17677669529663687f;                      // d_head ** -0.5 for d_head = 32 (attention.py:27)
+    const bool tcp = tc_ok(cx, M, 1, 1, C, 1), tcf = tc_ok(cx, M, 1, 1, 4 * C, 1);
+    Opnd a = fresh_opnd(cx, M, C, tcp);
     gn(cx, x, s.norm, 1e-6f, 0, a);
     View t0 = fresh(cx, M, C);
-    conv_gemm(cx, Act{a, x.B, x.H, x.W}, s.proj_in, 1, 0, epi_to(t0));
-    View nrm = fresh(cx, M, C);
+    conv_any(cx, a, x, s.proj_in, GemmEpi(), from_view(t0));
+    Opnd nrm = fresh_opnd(cx, M, C, tcp);
     // self-attention (attention.py:93)
-    RUN(k_layernorm(t0, M, s.ln1.g, s.ln1.b, 1e-5f, nrm, cx.st));
+    RUN(k_layernorm(t0, M, s.ln1.g, s.ln1.b, 1e-5f, nrm.out4(), cx.st));
     View qkv = fresh(cx, M, 3 * C);
-    lin_gemm(cx, nrm, M, s.qkv, epi_to(qkv));
-    View att = fresh(cx, M, C);
-    RUN(k_attention(qkv.cols(0, C), qkv.cols(C, C), qkv.cols(2 * C, C), x.B, N, N, s.heads, 0.17677669529663687f, att, cx.st));
+    lin_any(cx, nrm, M, s.qkv, GemmEpi(), from_view(qkv));
+    Opnd att = fresh_opnd(cx, M, C, tcp);
+    RUN(k_attention(qkv.cols(0, C), qkv.cols(C, C), qkv.cols(2 * C, C), x.B, N, N, s.heads, scale, att.out4(), cx.st));
     View t1 = fresh(cx, M, C);
-    { GemmEpi e = epi_to(t1); e.res = t0.p; e.res_ld = t0.ld; lin_gemm(cx, att, M, s.o1, e); }
+    { GemmEpi e; e.res = t0.p; e.res_ld = t0.ld; lin_any(cx, att, M, s.o1, e, from_view(t1)); }
     // cross-attention to the retrieved neighbours (attention.py:94); K/V were projected once in set_context
-    RUN(k_layernorm(t1, M, s.ln2.g, s.ln2.b, 1e-5f, nrm, cx.st));
+    RUN(k_layernorm(t1, M, s.ln2.g, s.ln2.b, 1e-5f, nrm.out4(), cx.st));
     View q2 = qkv.cols(0, C);                                    // reuse the qkv buffer
-    lin_gemm(cx, nrm, M, s.q2, epi_to(q2));
+    lin_any(cx, nrm, M, s.q2, GemmEpi(), from_view(q2));
     View kv(cx.dry ? nullptr : n->ctx_kv + n->ctx_off[s.id], 2 * C, 2 * C);
-    RUN(k_attention(q2, kv.cols(0, C), kv.cols(C, C), x.B, N, n->ctx_k, s.heads, 0.17677669529663687f, att, cx.st));
+    RUN(k_attention(q2, kv.cols(0, C), kv.cols(C, C), x.B, N, n->ctx_k, s.heads, scale, att.out4(), cx.st));
     View t2 = t0;                                                // t0 is dead after t1 was formed
-    { GemmEpi e = epi_to(t2); e.res = t1.p; e.res_ld = t1.ld; lin_gemm(cx, att, M, s.o2, e); }
+    { GemmEpi e; e.res = t1.p; e.res_ld = t1.ld; lin_any(cx, att, M, s.o2, e, from_view(t2)); }
     // GEGLU feed-forward (attention.py:95)
-    RUN(k_layernorm(t2, M, s.ln3.g, s.ln3.b, 1e-5f, nrm, cx.st));
-    View g = fresh(cx, M, 4 * C);
-    { GemmEpi e = epi_to(g); e.act = ACT_GEGLU; lin_gemm(cx, nrm, M, s.ff1, e); }
-    View t3 = t1;
-    { GemmEpi e = epi_to(t3); e.res = t2.p; e.res_ld = t2.ld; lin_gemm(cx, g, M, s.ff2, e); }
-    { GemmEpi e = epi_to(out); e.res = x.v.p; e.res_ld = x.v.ld; conv_gemm(cx, Act{t3, x.B, x.H, x.W}, s.proj_out, 1, 0, e); }
+    RUN(k_layernorm(t2, M, s.ln3.g, s.ln3.b, 1e-5f, nrm.out4(), cx.st));
+    Opnd g = fresh_opnd(cx, M, 4 * C, tcf);
+    { GemmEpi e; e.act = ACT_GEGLU; lin_any(cx, nrm, M, s.ff1, e, g); }
+    Opnd t3 = tcp ? fresh_opnd(cx, M, C, true) : from_view(t1);  // only proj_out consumes t3
+    { GemmEpi e; e.res = t2.p; e.res_ld = t2.ld; lin_any(cx, g, M, s.ff2, e, t3); }
+    { GemmEpi e; e.res = x.v.p; e.res_ld = x.v.ld; conv_any(cx, t3, x, s.proj_out, e, from_view(out)); }
+    A.release(mk);
+}
+
+void run_down(Ctx& cx, const Conv& c, const Act& x, View out) {
+    Arena& A = cx.n->arena; size_t mk = A.mark();
+    const int Ho = (x.H + 1) / 2, Wo = (x.W + 1) / 2, Mo = x.B * Ho * Wo;
+    if (tc_ok(cx, Mo, 1, 1, 9 * c.cin, 1)) {
+        Opnd col = fresh_opnd(cx, Mo, 9 * c.cin, true);
+        RUN(k_im2col_s2(x.v, x.B, x.H, x.W, col.out4(), cx.st));
+        gemm_any(cx, col, Mo, 1, 1, 9 * c.cin, 1, 1, 0, c.w, c.b, c.cout, GemmEpi(), from_view(out));
+    } else {
+        gemm_any(cx, from_view(x.v), x.B, x.H, x.W, c.cin, 3, 2, 0, c.w, c.b, c.cout, GemmEpi(), from_view(out));
+    }
+    A.release(mk);
+}
+void run_up(Ctx& cx, const Conv& c, const Act& x, View out) {
+    Arena& A = cx.n->arena; size_t mk = A.mark();
+    if (tc_ok(cx, x.B, 2 * x.H, 2 * x.W, c.cin, 3)) {
+        Opnd up = fresh_opnd(cx, x.B * 4 * x.H * x.W, c.cin, true);
+        RUN(k_upsample2x(x.v, x.B, x.H, x.W, up.out4(), cx.st));
+        gemm_any(cx, up, x.B, 2 * x.H, 2 * x.W, c.cin, 3, 1, 0, c.w, c.b, c.cout, GemmEpi(), from_view(out));
+    } else {
+        gemm_any(cx, from_view(x.v), x.B, x.H, x.W, c.cin, 3, 1, 1, c.w, c.b, c.cout, GemmEpi(), from_view(out));
+    }
     A.release(mk);
 }
 
@@ -315,7 +391,8 @@ void run_st(Ctx& cx, const STW& s, const Act& x, View out) {
 void debug_view(Ctx& cx, const char* tag, int a, int b, View v, int M) {
     if (cx.dry || !cx.n->debug || cx.rc != RDM_OK) return;
     std::vector<float> host((size_t)M * v.C);
-    cudaStreamSynchronize(cx.st);
+    cudaError_t err = cudaStreamSynchronize(cx.st);
+    if (err != cudaSuccess) { cx.n->debug_log += std::string("sync failed: ") + cudaGetErrorString(err) + "\n"; return; }
     if (cudaMemcpy2D(host.data(), (size_t)v.C * 4, v.p, (size_t)v.ld * 4, (size_t)v.C * 4, M, cudaMemcpyDeviceToHost) != cudaSuccess) { cx.n->debug_log += "memcpy failed\n"; return; }
     double s = 0, sa = 0; for (float f : host) { s += f; sa += f < 0 ? -f : f; }
     char line[160]; snprintf(line, sizeof(line), "%s %d %d %.9g %.9g\n", tag, a, b, s / host.size(), sa / host.size());
@@ -338,11 +415,11 @@ Act run_block(Ctx& cx, const Block& b, Act x, const float* emb_all, View dst) {
         }
         View o = last ? dst : fresh(cx, x.B * Ho * Wo, Co);
         switch (L.kind) {
-            case L_CONV_IN: conv_gemm(cx, x, n->convs[L.idx], 1, 0, epi_to(o)); break;
+            case L_CONV_IN: { const Conv& c = n->convs[L.idx]; gemm_any(cx, from_view(x.v), x.B, x.H, x.W, c.cin, 3, 1, 0, c.w, c.b, c.cout, GemmEpi(), from_view(o)); break; }
             case L_RES: run_res(cx, n->res[L.idx], x, emb_all, o); break;
             case L_ST: run_st(cx, n->sts[L.idx], x, o); break;
-            case L_DOWN: conv_gemm(cx, x, n->convs[L.idx], 2, 0, epi_to(o)); break;
-            case L_UP: conv_gemm(cx, x, n->convs[L.idx], 1, 1, epi_to(o)); break;
+            case L_DOWN: run_down(cx, n->convs[L.idx], x, o); break;
+            case L_UP: run_up(cx, n->convs[L.idx], x, o); break;
         }
         x = Act{View(o.p, o.ld, Co), x.B, Ho, Wo};
         debug_view(cx, "layer", cx.n->debug_block, (int)i, x.v, x.M());
@@ -358,7 +435,6 @@ int forward_impl(Net* n, const float* x_nchw, int Bx, const long long* t, int B2
     Arena& A = n->arena; A.off = 0; A.dry = dry; n->stats_off = 0;
     const rdm_unet_cfg& c = n->cfg;
     const int nin = (int)n->in_blocks.size(), nout = (int)n->out_blocks.size();
-    // spatial size per input block output
     std::vector<int> hH(nin), hW(nin);
     { int h = H, w = W; for (int i = 0; i < nin; i++) { if (n->in_blocks[i].layers[0].kind == L_DOWN) { h = (h + 1) / 2; w = (w + 1) / 2; } hH[i] = h; hW[i] = w; } }
     // concat buffers: output block j reads cat([h (ch_j), hs[nin-1-j] (ich_j)])
@@ -373,26 +449,22 @@ int forward_impl(Net* n, const float* x_nchw, int Bx, const long long* t, int B2
         }
     }
     if (!dry) RDM_CHECK_CUDA(cudaMemsetAsync(n->stats, 0, n->stats_cap * sizeof(double), st));
-    // time embedding (openaimodel.py:352-353); only SiLU(emb) is ever consumed (ResBlock emb_layers = [SiLU, Linear])
+    // time embedding (openaimodel.py:352-353); only SiLU(emb) is ever consumed (ResBlock emb_layers = [SiLU, Linear]).
+    // M = B2 rows: weight-bandwidth bound, stays on the CUDA-core engine in every mode.
     View temb = fresh(cx, B2, c.model_channels), e1 = fresh(cx, B2, n->ted), semb = fresh(cx, B2, n->ted), emb_all = fresh(cx, B2, n->emb_total);
     RUN(k_timestep_embedding(t, B2, c.model_channels, temb.p, st));
-    { GemmEpi e = epi_to(e1); e.act = ACT_SILU; lin_gemm(cx, temb, B2, n->te0, e); }
-    { GemmEpi e = epi_to(semb); e.act = ACT_SILU; lin_gemm(cx, e1, B2, n->te2, e); }
-    lin_gemm(cx, semb, B2, n->emb_all, epi_to(emb_all));
+    { GemmEpi e; e.act = ACT_SILU; lin_any(cx, from_view(temb), B2, n->te0, e, from_view(e1)); }
+    { GemmEpi e; e.act = ACT_SILU; lin_any(cx, from_view(e1), B2, n->te2, e, from_view(semb)); }
+    lin_any(cx, from_view(semb), B2, n->emb_all, GemmEpi(), from_view(emb_all));
     debug_view(cx, "temb", 0, 0, temb, B2); debug_view(cx, "semb", 0, 0, semb, B2); debug_view(cx, "emb_all", 0, 0, emb_all, B2);
-    // input
     View x0 = fresh(cx, B2 * H * W, c.in_channels < 4 ? 4 : c.in_channels); x0.C = c.in_channels;
     RUN(k_nchw_to_nhwc(x_nchw, Bx, B2, c.in_channels, H, W, x0, st));
     Act h{x0, B2, H, W};
     for (int i = 0; i < nin; i++) {
         int j = nout - 1 - i;
-        View dst = cat[j].cols(cat_ch[j], n->skip_ch[i]);
-        h = run_block(cx, n->in_blocks[i], h, emb_all.p, dst);
+        h = run_block(cx, n->in_blocks[i], h, emb_all.p, cat[j].cols(cat_ch[j], n->skip_ch[i]));
     }
-    {   // middle block writes into the first concat buffer's leading columns
-        View dst = cat[0].cols(0, cat_ch[0]);
-        h = run_block(cx, n->mid, h, emb_all.p, dst);
-    }
+    h = run_block(cx, n->mid, h, emb_all.p, cat[0].cols(0, cat_ch[0]));
     View last;
     for (int j = 0; j < nout; j++) {
         int i = nin - 1 - j;
@@ -403,13 +475,23 @@ int forward_impl(Net* n, const float* x_nchw, int Bx, const long long* t, int B2
         h = run_block(cx, n->out_blocks[j], in, emb_all.p, dst);
     }
     // out = conv3x3(SiLU(GN(h)))  (openaimodel.py:312-316,371)
-    View a = fresh(cx, h.M(), h.v.C);
+    Opnd a = fresh_opnd(cx, h.M(), h.v.C, tc_ok(cx, h.B, h.H, h.W, h.v.C, 3));
     gn(cx, h, n->out_norm, 1e-5f, 1, a);
     View o = fresh(cx, h.M(), 4); o.C = c.out_channels;
-    conv_gemm(cx, Act{a, h.B, h.H, h.W}, n->out_conv, 1, 0, epi_to(o));
+    conv_any(cx, a, h, n->out_conv, GemmEpi(), from_view(o));
     debug_view(cx, "out", 0, 0, o, h.M());
     RUN(k_nhwc_to_nchw(o, B2, c.out_channels, H, W, out_nchw, st));
     return cx.rc;
+}
+
+// (re)build the bf16 hi/lo planes of every packed weight matrix: one element-wise pass over the weight arena
+int ensure_weight_planes(Net* n, cudaStream_t st) {
+    if (n->mode == RDM_UNET_MODE_FP32 || !n->planes_dirty) return RDM_OK;
+    if (!n->wb_hi) RDM_CHECK_CUDA(cudaMalloc((void**)&n->wb_hi, n->wfloats * 2));
+    if (!n->wb_lo) RDM_CHECK_CUDA(cudaMalloc((void**)&n->wb_lo, n->wfloats * 2));
+    RDM_TRY(k_split_planes(View(n->wbase, 64, 64), (long long)(n->wfloats / 64), Out4(n->wb_hi, n->wb_lo, 64), st));
+    n->planes_dirty = false;
+    return RDM_OK;
 }
 
 int ensure_plan(Net* n, int B2, int H, int W) {
@@ -465,6 +547,8 @@ void rdm_unet_destroy(rdm_unet_t* n) {
     if (!n) return;
     DeviceGuard guard(n->device);
     if (n->wbase) cudaFree(n->wbase);
+    if (n->wb_hi) cudaFree(n->wb_hi);
+    if (n->wb_lo) cudaFree(n->wb_lo);
     if (n->arena.base) cudaFree(n->arena.base);
     if (n->stats) cudaFree(n->stats);
     if (n->ctx_kv) cudaFree(n->ctx_kv);
@@ -498,6 +582,7 @@ int rdm_unet_load(rdm_unet_t* n, const char* name, const float* host, int64_t nu
     }
     s.loaded = true;
     n->ctx_B = 0;           // projections of a previously set context are stale
+    n->planes_dirty = true;
     return RDM_OK;
 }
 
@@ -512,7 +597,9 @@ const char* rdm_unet_debug_log(const rdm_unet_t* n) { return n ? n->debug_log.c_
 
 int rdm_unet_set_mode(rdm_unet_t* n, int32_t mode) {
     RDM_REQUIRE(n, RDM_ERR_ARG, "rdm_unet_set_mode: null handle");
-    RDM_REQUIRE(mode == RDM_UNET_MODE_FP32, RDM_ERR_UNSUPPORTED, "rdm_unet_set_mode: mode %d not available", mode);
+    RDM_REQUIRE(mode == RDM_UNET_MODE_FP32 || mode == RDM_UNET_MODE_TC_BF16X3 || mode == RDM_UNET_MODE_TC_BF16, RDM_ERR_UNSUPPORTED,
+                "rdm_unet_set_mode: unknown mode %d", mode);
+    if (mode != n->mode) { n->plan_B = 0; n->planes_dirty = true; }      // workspace layout depends on the engine
     n->mode = mode; return RDM_OK;
 }
 
@@ -536,7 +623,8 @@ int rdm_unet_set_context(rdm_unet_t* n, const float* ctx, int32_t B2, int32_t k,
     for (auto& s : n->sts) {
         n->ctx_off[s.id] = off;
         View dst(n->ctx_kv + off, 2 * s.C, 2 * s.C);
-        lin_gemm(cx, View(const_cast<float*>(ctx), n->cfg.context_dim, n->cfg.context_dim), rows, s.kv2, epi_to(dst));
+        gemm_any(cx, from_view(View(const_cast<float*>(ctx), n->cfg.context_dim, n->cfg.context_dim)), rows, 1, 1, s.kv2.in, 1, 1, 0,
+                 s.kv2.w, nullptr, s.kv2.out, GemmEpi(), from_view(dst));
         off += (size_t)2 * s.C * rows;
     }
     n->ctx_B = B2; n->ctx_k = k;
@@ -551,6 +639,7 @@ int rdm_unet_forward(rdm_unet_t* n, const float* x, int32_t Bx, const int64_t* t
     RDM_REQUIRE(H % div == 0 && W % div == 0, RDM_ERR_ARG, "rdm_unet_forward: H=%d W=%d must be multiples of %d", H, W, div);
     DeviceGuard guard(n->device);
     RDM_TRY(ensure_plan(n, B2, H, W));
+    RDM_TRY(ensure_weight_planes(n, (cudaStream_t)stream));
     return forward_impl(n, x, Bx, (const long long*)t, B2, H, W, eps_out, (cudaStream_t)stream, false);
 }
 
