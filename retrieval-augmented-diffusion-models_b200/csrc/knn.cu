@@ -1,15 +1,21 @@
 // Exact cosine top-k over an in-HBM CLIP database (K1/K11 of SURVEY.md section 2.1).
 //
-// Pipeline per query batch (all stream-ordered, no host sync):
-//   1. knn_scan_kernel   -- ONE pass over the database: coalesced 16-byte streaming loads, fp32 FMA dot
-//                           products against up to 16 queries held in shared memory, transposing
-//                           warp-shuffle reduction, threshold filter, per-CTA top-32 candidate lists.
-//                           HBM-bound: algorithmic bytes = n * d * sizeof(elem) (+4 B/row inverse norm).
-//   2. knn_select_kernel -- merges the per-CTA lists (warp bitonic networks), then RE-RANKS the 32 best
-//                           candidates of every query with the exact definition of oracle/knn_ref.c
-//                           (sequential fp64, separately rounded products) and emits the top-k by
-//                           (score desc, index asc).  The fp32 scan only has to put the true top-k among
-//                           its 32 candidates (margin >= 8 for k <= 24; fp32 dot error ~1e-7).
+// Pipeline per query batch of <= 16 queries (all stream-ordered, no host sync):
+//   1. knn_scan_kernel<SAMPLE> -- a strided 1/16 sample of the row groups: every lane keeps the running maximum
+//                           (score, row) key of the rows it owns.  knn_threshold_kernel takes the 32nd largest of
+//                           those maxima per query: a VALID lower bound of the final 32nd-best key (they are 32
+//                           distinct real rows), i.e. a threshold only ~16*32 rows of the whole DB exceed.
+//   2. knn_scan_kernel<MAIN>   -- ONE pass over the database: coalesced 16-byte streaming loads, fp32 FMA dot
+//                           products against the queries held in shared memory, transposing warp-shuffle
+//                           reduction, ONE compare per (row, query) against the threshold; the rare survivors
+//                           are appended to a small global candidate buffer.  HBM-bound for few queries:
+//                           algorithmic bytes = n * d * sizeof(elem) (+4 B/row inverse norm).
+//   3. knn_select_kernel -- top-32 of the survivors (warp bitonic networks), then RE-RANK with the exact definition
+//                           of oracle/knn_ref.c (sequential fp64, separately rounded products) and emit the top-k
+//                           by (score desc, index asc).  The fp32 scan only has to put the true top-k among its 32
+//                           candidates (margin >= 8 for k <= 24; fp32 dot error ~1e-7).
+//   4. fallback (device-side conditional, normally two empty launches): if a candidate buffer overflowed (sample
+//      unrepresentative of the DB), knn_scan_kernel<LOCKED> redoes the pass with per-CTA top-32 lists under a lock.
 // Replaces ScaNN behind `searcher.search_batched` (dsetbuilder.py:490, ddpm.py:906-908).
 #include "common.cuh"
 #include "../../include/rdm_b200.h"
@@ -63,6 +69,10 @@ template <> struct Elem<__half> {
 
 __device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m) {
     uint32_t lo = __shfl_xor_sync(FULL, (uint32_t)v, m), hi = __shfl_xor_sync(FULL, (uint32_t)(v >> 32), m);
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
+    uint32_t lo = __shfl_sync(FULL, (uint32_t)v, src), hi = __shfl_sync(FULL, (uint32_t)(v >> 32), src);
     return ((u64)hi << 32) | lo;
 }
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
@@ -147,10 +157,25 @@ __device__ __noinline__ void list_insert(ScanShared* sh, int q, u64 key, int lan
     __syncwarp();
 }
 
-template <typename T, int D, int QP, int R>
+enum { SCAN_SAMPLE = 0, SCAN_MAIN = 1, SCAN_LOCKED = 2 };
+constexpr int CAND_CAP = 2048;     // survivors kept per query by the main scan
+constexpr int KSEL = 32;           // rank of the threshold among the sample maxima
+
+struct ScanArgs {
+    u64* lists_out;        // LOCKED: [grid][QP][LIST]
+    u64* maxima;           // SAMPLE: [QP][grid*SCAN_WARPS*32] per-lane maxima
+    const u64* thr_key;    // MAIN: [QP] threshold keys
+    u64* cand;             // MAIN: [QP][CAND_CAP]
+    unsigned* cand_cnt;    // MAIN: [QP]
+    const unsigned* overflow;   // LOCKED: run only if *overflow != 0
+    int group_stride;      // SAMPLE: take every group_stride-th row group
+};
+
+template <typename T, int D, int QP, int R, int MODE>
 __global__ void __launch_bounds__(SCAN_THREADS)
 knn_scan_kernel(const T* __restrict__ db, const float* __restrict__ inv, long long n,
-                const float* __restrict__ q, int nq_valid, u64* __restrict__ lists_out) {
+                const float* __restrict__ q, int nq_valid, ScanArgs args) {
+    if (MODE == SCAN_LOCKED) { if (*args.overflow == 0u) return; }
     constexpr int EPL = D / 32;              // elements per lane per row
     constexpr int EPV = Elem<T>::EPV;        // elements per 16-byte vector
     constexpr int NV = EPL / EPV;            // vectors per lane per row
@@ -172,14 +197,24 @@ knn_scan_kernel(const T* __restrict__ db, const float* __restrict__ inv, long lo
         smem_q[i] = make_float4(v[0], v[1], v[2], v[3]);
     }
     for (int i = tid; i < MAX_QP * LIST; i += SCAN_THREADS) sh.list[i / LIST][i % LIST] = 0ull;
-    if (tid < MAX_QP) { sh.thr[tid] = -CUDART_INF_F; sh.lock[tid] = 0; }
+    if (tid < MAX_QP) {
+        sh.lock[tid] = 0;
+        float t = -CUDART_INF_F;
+        if (MODE == SCAN_MAIN && tid < QP) { u64 k = args.thr_key[tid]; t = k == 0ull ? -CUDART_INF_F : unorder_f32((uint32_t)(k >> 32)); }
+        sh.thr[tid] = t;
+    }
     __syncthreads();
+    u64 best[QP];                                  // SAMPLE: running maximum key of the rows this lane owns
+#pragma unroll
+    for (int qi = 0; qi < QP; qi++) best[qi] = 0ull;
+    const int gstride = MODE == SCAN_SAMPLE ? args.group_stride : 1;
 
     const int rsel = row_of_lane<R>(lane);
     const bool owner = (lane & (32 / R - 1)) == 0;
     const long long ngroups = (n + R - 1) / R;
-    for (long long g = (long long)blockIdx.x * SCAN_WARPS + warp; g < ngroups; g += (long long)gridDim.x * SCAN_WARPS) {
-        const long long row0 = g * R;
+    const long long nsteps = (ngroups + gstride - 1) / gstride;
+    for (long long gs = (long long)blockIdx.x * SCAN_WARPS + warp; gs < nsteps; gs += (long long)gridDim.x * SCAN_WARPS) {
+        const long long row0 = gs * gstride * R;
         uint4 raw[R][NV];
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -215,39 +250,92 @@ knn_scan_kernel(const T* __restrict__ db, const float* __restrict__ inv, long lo
             }
             float s = reduce_rows<R>(acc, lane) * myinv;
             if (!(s == s)) s = -CUDART_INF_F;
-            const float thr = *(volatile float*)&sh.thr[qi];
-            unsigned m = __ballot_sync(FULL, valid && qi < nq_valid && s >= thr);
-            while (m) {
-                int src = __ffs(m) - 1; m &= m - 1;
-                float cs = __shfl_sync(FULL, s, src);
-                uint32_t ci = __shfl_sync(FULL, (uint32_t)myrow, src);
-                u64 key = make_key(cs, ci);
-                float tnow = __shfl_sync(FULL, *(volatile float*)&sh.thr[qi], 0);     // warp-uniform re-check
-                if (cs >= tnow) list_insert(&sh, qi, key, lane);
+            if (MODE == SCAN_SAMPLE) {
+                if (valid) { u64 key = make_key(s, (uint32_t)myrow); best[qi] = key > best[qi] ? key : best[qi]; }
+            } else if (MODE == SCAN_MAIN) {
+                if (valid && qi < nq_valid && s >= sh.thr[qi]) {                 // rare: ~16*KSEL rows of the whole DB per query
+                    const u64 key = make_key(s, (uint32_t)myrow);
+                    if (key >= args.thr_key[qi]) {
+                        unsigned pos = atomicAdd(&args.cand_cnt[qi], 1u);
+                        if (pos < (unsigned)CAND_CAP) args.cand[(size_t)qi * CAND_CAP + pos] = key;
+                    }
+                }
+            } else {
+                const float thr = *(volatile float*)&sh.thr[qi];
+                unsigned m = __ballot_sync(FULL, valid && qi < nq_valid && s >= thr);
+                while (m) {
+                    int src = __ffs(m) - 1; m &= m - 1;
+                    float cs = __shfl_sync(FULL, s, src);
+                    uint32_t ci = __shfl_sync(FULL, (uint32_t)myrow, src);
+                    u64 key = make_key(cs, ci);
+                    float tnow = __shfl_sync(FULL, *(volatile float*)&sh.thr[qi], 0);     // warp-uniform re-check
+                    if (cs >= tnow) list_insert(&sh, qi, key, lane);
+                }
             }
         }
     }
+    if (MODE == SCAN_SAMPLE) {
+        const size_t per_q = (size_t)gridDim.x * SCAN_THREADS;
+#pragma unroll
+        for (int qi = 0; qi < QP; qi++) args.maxima[qi * per_q + (size_t)blockIdx.x * SCAN_THREADS + tid] = best[qi];
+    }
+    if (MODE == SCAN_LOCKED) {
+        __syncthreads();
+        for (int i = tid; i < QP * LIST; i += SCAN_THREADS)
+            args.lists_out[((size_t)blockIdx.x * QP + i / LIST) * LIST + (i % LIST)] = sh.list[i / LIST][i % LIST];
+    }
+}
+
+// grid = QP, block = 1024: threshold key[q] = KSEL-th largest of the sample maxima (0 if fewer exist); resets the counters.
+__global__ void __launch_bounds__(1024)
+knn_threshold_kernel(const u64* __restrict__ maxima, size_t per_q, u64* __restrict__ thr_key, unsigned* __restrict__ cand_cnt, unsigned* __restrict__ overflow) {
+    __shared__ u64 s_keys[32][LIST];
+    const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64* src = maxima + (size_t)qi * per_q;
+    u64 cur = 0ull;
+    for (size_t b = (size_t)warp * 32; b < per_q; b += 32 * 32) {
+        u64 batch = b + lane < per_q ? src[b + lane] : 0ull;
+        const u64 cur_min = shfl_u64(cur, 31);                         // cur is sorted descending
+        if (__any_sync(FULL, batch > cur_min)) cur = warp_merge_top32(cur, batch, lane);
+    }
+    s_keys[warp][lane] = cur;
     __syncthreads();
-    for (int i = tid; i < QP * LIST; i += SCAN_THREADS)
-        lists_out[((size_t)blockIdx.x * QP + i / LIST) * LIST + (i % LIST)] = sh.list[i / LIST][i % LIST];
+    if (warp != 0) return;
+    cur = s_keys[0][lane];
+    for (int w = 1; w < 32; w++) cur = warp_merge_top32(cur, s_keys[w][lane], lane);
+    if (lane == KSEL - 1) thr_key[qi] = cur;           // descending: lane 31 holds the 32nd largest
+    if (lane == 0) { cand_cnt[qi] = 0u; if (qi == 0) *overflow = 0u; }
 }
 
 __device__ __forceinline__ bool better_pair(double sa, long long ia, double sb, long long ib) { return sa > sb || (sa == sb && ia < ib); }
 
 // grid = queries of this pass, block = 1024.  Merge per-CTA lists -> 32 candidates -> exact fp64 re-rank -> top-k.
-template <typename T, int D>
+// FROM_LISTS = false: candidates of query qi are cand[qi*CAND_CAP .. + min(cnt, CAP)); sets *overflow when cnt > CAP.
+// FROM_LISTS = true : fallback, per-CTA lists [nblk][QP][LIST]; runs only when *overflow != 0.
+template <typename T, int D, bool FROM_LISTS>
 __global__ void __launch_bounds__(1024)
-knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const T* __restrict__ db, const float* __restrict__ inv,
+knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const unsigned* __restrict__ cand_cnt, unsigned* __restrict__ overflow,
+                  const T* __restrict__ db, const float* __restrict__ inv,
                   long long n, const float* __restrict__ q, int k, long long idx_base,
                   long long* __restrict__ idx_out, float* __restrict__ dist_out, double* __restrict__ score_out) {
     __shared__ u64 s_keys[32][LIST];
     __shared__ float s_q[D];
     const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (FROM_LISTS) { if (*overflow == 0u) return; }
     for (int i = tid; i < D; i += blockDim.x) s_q[i] = q[(size_t)qi * D + i];
     u64 cur = 0ull;
-    for (int b = warp; b < nblk; b += 32) {
-        u64 batch = lists[((size_t)b * QP + qi) * LIST + lane];
-        if (__any_sync(FULL, batch != 0ull)) cur = warp_merge_top32(cur, batch, lane);
+    if (FROM_LISTS) {
+        for (int b = warp; b < nblk; b += 32) {
+            u64 batch = lists[((size_t)b * QP + qi) * LIST + lane];
+            if (__any_sync(FULL, batch != 0ull)) cur = warp_merge_top32(cur, batch, lane);
+        }
+    } else {
+        const unsigned cnt = cand_cnt[qi];
+        if (cnt > (unsigned)CAND_CAP) { if (tid == 0) atomicExch(overflow, 1u); return; }     // the fallback pass redoes this batch
+        for (unsigned b = warp * 32; b < cnt; b += 32 * 32) {
+            u64 batch = b + lane < cnt ? lists[(size_t)qi * CAND_CAP + b + lane] : 0ull;
+            cur = warp_merge_top32(cur, batch, lane);
+        }
     }
     s_keys[warp][lane] = cur;
     __syncthreads();
@@ -369,15 +457,19 @@ struct rdm_knn {
     const void* db = nullptr;      // device
     void* db_owned = nullptr;      // device allocation when copied from host
     float* inv = nullptr;
-    u64* lists = nullptr;
+    u64* lists = nullptr;      // fallback per-CTA lists
+    u64* maxima = nullptr;     // [MAX_QP][max_grid*SCAN_THREADS]
+    u64* cand = nullptr;       // [MAX_QP][CAND_CAP]
+    u64* thr_key = nullptr;    // [MAX_QP]
+    unsigned* cand_cnt = nullptr;   // [MAX_QP] + overflow flag at [MAX_QP]
     int max_grid = 0;
 };
 
 namespace {
 
-template <typename T, int D, int QP, int R>
-int launch_scan(rdm_knn* h, const float* q, int nq_valid, cudaStream_t st, int* grid_out) {
-    auto kern = knn_scan_kernel<T, D, QP, R>;
+template <typename T, int D, int QP, int R, int MODE>
+int launch_scan(rdm_knn* h, const float* q, int nq_valid, ScanArgs args, cudaStream_t st, int* grid_out) {
+    auto kern = knn_scan_kernel<T, D, QP, R, MODE>;
     size_t smem = (size_t)QP * D * sizeof(float);
     static thread_local int cached_grid[8] = {0};   // per device
     int& grid = cached_grid[h->device & 7];
@@ -389,14 +481,41 @@ int launch_scan(rdm_knn* h, const float* q, int nq_valid, cudaStream_t st, int* 
         grid = rdm_num_sms(h->device) * per_sm;
         if (grid > h->max_grid) grid = h->max_grid;
     }
-    long long ngroups = (h->n + R - 1) / R;
+    const long long ngroups = (h->n + R - 1) / R;
+    const long long nsteps = (ngroups + args.group_stride - 1) / args.group_stride;
     int g = grid;
-    long long need = (ngroups + SCAN_WARPS - 1) / SCAN_WARPS;
+    long long need = (nsteps + SCAN_WARPS - 1) / SCAN_WARPS;
     if (need < g) g = (int)(need < 1 ? 1 : need);
-    kern<<<g, SCAN_THREADS, smem, st>>>((const T*)h->db, h->inv, h->n, q, nq_valid, h->lists);
+    kern<<<g, SCAN_THREADS, smem, st>>>((const T*)h->db, h->inv, h->n, q, nq_valid, args);
     RDM_COUNT_LAUNCH();
     RDM_CHECK_CUDA(cudaGetLastError());
     *grid_out = g;
+    return RDM_OK;
+}
+
+template <typename T, int D, int QP, int R>
+int search_pass(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st) {
+    unsigned* overflow = h->cand_cnt + MAX_QP;
+    const long long ngroups = (h->n + R - 1) / R;
+    // sample ~1/16 of the row groups, but keep at least ~8K groups in the sample (small DBs are sampled densely)
+    int stride = (int)(ngroups / 8192); if (stride > 16) stride = 16; if (stride < 1) stride = 1;
+    int g0 = 0, g1 = 0, g2 = 0;
+    ScanArgs a{}; a.group_stride = stride; a.maxima = h->maxima;
+    RDM_TRY((launch_scan<T, D, QP, R, SCAN_SAMPLE>(h, qp, cnt, a, st, &g0)));
+    knn_threshold_kernel<<<QP, 1024, 0, st>>>(h->maxima, (size_t)g0 * SCAN_THREADS, h->thr_key, h->cand_cnt, overflow);
+    RDM_COUNT_LAUNCH();
+    ScanArgs m{}; m.group_stride = 1; m.thr_key = h->thr_key; m.cand = h->cand; m.cand_cnt = h->cand_cnt;
+    RDM_TRY((launch_scan<T, D, QP, R, SCAN_MAIN>(h, qp, cnt, m, st, &g1)));
+    knn_select_kernel<T, D, false><<<cnt, 1024, 0, st>>>(h->cand, 0, QP, h->cand_cnt, overflow, (const T*)h->db, h->inv, h->n, qp, k, h->idx_base,
+                                                         idx_out, dist_out, sc_out);
+    RDM_COUNT_LAUNCH();
+    // device-side conditional fallback (both kernels return immediately unless a candidate buffer overflowed)
+    ScanArgs f{}; f.group_stride = 1; f.lists_out = h->lists; f.overflow = overflow;
+    RDM_TRY((launch_scan<T, D, QP, R, SCAN_LOCKED>(h, qp, cnt, f, st, &g2)));
+    knn_select_kernel<T, D, true><<<cnt, 1024, 0, st>>>(h->lists, g2, QP, h->cand_cnt, overflow, (const T*)h->db, h->inv, h->n, qp, k, h->idx_base,
+                                                        idx_out, dist_out, sc_out);
+    RDM_COUNT_LAUNCH();
+    RDM_CHECK_CUDA(cudaGetLastError());
     return RDM_OK;
 }
 
@@ -406,17 +525,12 @@ int search_typed(rdm_knn* h, const float* q, int nq, int k, long long* idx_out, 
     for (int q0 = 0; q0 < nq; q0 += MAX_QP) {
         int cnt = nq - q0 < MAX_QP ? nq - q0 : MAX_QP;
         const float* qp = q + (size_t)q0 * D;
-        int grid = 0, QP;
-        if (cnt <= 1)      { QP = 1;  RDM_TRY((launch_scan<T, D, 1, R>(h, qp, cnt, st, &grid))); }
-        else if (cnt <= 2) { QP = 2;  RDM_TRY((launch_scan<T, D, 2, R>(h, qp, cnt, st, &grid))); }
-        else if (cnt <= 4) { QP = 4;  RDM_TRY((launch_scan<T, D, 4, R>(h, qp, cnt, st, &grid))); }
-        else if (cnt <= 8) { QP = 8;  RDM_TRY((launch_scan<T, D, 8, R>(h, qp, cnt, st, &grid))); }
-        else               { QP = 16; RDM_TRY((launch_scan<T, D, 16, R>(h, qp, cnt, st, &grid))); }
-        knn_select_kernel<T, D><<<cnt, 1024, 0, st>>>(h->lists, grid, QP, (const T*)h->db, h->inv, h->n, qp, k, h->idx_base,
-                                                      idx_out + (size_t)q0 * k, dist_out + (size_t)q0 * k,
-                                                      sc_out ? sc_out + (size_t)q0 * k : nullptr);
-        RDM_COUNT_LAUNCH();
-        RDM_CHECK_CUDA(cudaGetLastError());
+        long long* io = idx_out + (size_t)q0 * k; float* dist_o = dist_out + (size_t)q0 * k; double* so = sc_out ? sc_out + (size_t)q0 * k : nullptr;
+        if (cnt <= 1)      RDM_TRY((search_pass<T, D, 1, R>(h, qp, cnt, k, io, dist_o, so, st)));
+        else if (cnt <= 2) RDM_TRY((search_pass<T, D, 2, R>(h, qp, cnt, k, io, dist_o, so, st)));
+        else if (cnt <= 4) RDM_TRY((search_pass<T, D, 4, R>(h, qp, cnt, k, io, dist_o, so, st)));
+        else if (cnt <= 8) RDM_TRY((search_pass<T, D, 8, R>(h, qp, cnt, k, io, dist_o, so, st)));
+        else               RDM_TRY((search_pass<T, D, 16, R>(h, qp, cnt, k, io, dist_o, so, st)));
     }
     return RDM_OK;
 }
@@ -497,7 +611,11 @@ int rdm_knn_create(rdm_knn_t** out, const void* db, int64_t n, int32_t d, int32_
         }
         h->max_grid = rdm_num_sms(device) * 8;
         if (cudaMalloc(&h->inv, (size_t)n * sizeof(float)) != cudaSuccess ||
-            cudaMalloc(&h->lists, (size_t)h->max_grid * MAX_QP * LIST * sizeof(u64)) != cudaSuccess) {
+            cudaMalloc(&h->lists, (size_t)h->max_grid * MAX_QP * LIST * sizeof(u64)) != cudaSuccess ||
+            cudaMalloc(&h->maxima, (size_t)h->max_grid * SCAN_THREADS * MAX_QP * sizeof(u64)) != cudaSuccess ||
+            cudaMalloc(&h->cand, (size_t)MAX_QP * CAND_CAP * sizeof(u64)) != cudaSuccess ||
+            cudaMalloc(&h->thr_key, (size_t)MAX_QP * sizeof(u64)) != cudaSuccess ||
+            cudaMalloc(&h->cand_cnt, (size_t)(MAX_QP + 1) * sizeof(unsigned)) != cudaSuccess) {
             rdm_set_error("rdm_knn_create: workspace cudaMalloc failed"); rc = RDM_ERR_CUDA; break;
         }
         rc = do_create(h);
@@ -513,6 +631,10 @@ void rdm_knn_destroy(rdm_knn_t* h) {
     if (h->db_owned) cudaFree(h->db_owned);
     if (h->inv) cudaFree(h->inv);
     if (h->lists) cudaFree(h->lists);
+    if (h->maxima) cudaFree(h->maxima);
+    if (h->cand) cudaFree(h->cand);
+    if (h->thr_key) cudaFree(h->thr_key);
+    if (h->cand_cnt) cudaFree(h->cand_cnt);
     delete h;
 }
 

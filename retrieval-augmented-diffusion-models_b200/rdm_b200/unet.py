@@ -12,7 +12,9 @@ import torch
 
 from . import _lib
 
-MODE_FP32 = 0
+MODE_FP32 = 0          # every contraction fp32 on CUDA cores (strict)
+MODE_TC_BF16X3 = 1     # tcgen05, bf16 hi/lo split operands (fp32-grade)
+MODE_TC_BF16 = 2       # tcgen05, plain bf16 operands
 
 
 class UNetCfg(ctypes.Structure):

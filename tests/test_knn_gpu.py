@@ -68,6 +68,38 @@ def test_shards_merge_to_the_unsharded_result(cuda):
     assert torch.equal(mi, full[0]) and torch.equal(ms, full[2]) and torch.equal(md, full[1])
 
 
+def test_unrepresentative_sample_takes_the_fallback_path(cuda):
+    """The main scan's threshold comes from a strided sample of row groups.  Hide 5000 near-duplicates of the query in
+    rows the sample never visits: the candidate buffer (2048) overflows and the device-side fallback must still be exact."""
+    from rdm_b200.knn import B200Searcher
+    n = 300_000
+    rng = np.random.default_rng(9)
+    db = rng.standard_normal((n, 512)).astype(np.float32)
+    qv = rng.standard_normal(512).astype(np.float32)
+    stride = max(1, min(16, ((n + 7) // 8) // 8192))
+    assert stride >= 2
+    hidden = np.array([r for r in rng.permutation(n) if (r // 8) % stride != 0][:5000])
+    db[hidden] = qv[None] + 0.05 * rng.standard_normal((5000, 512)).astype(np.float32)
+    db = db.astype(np.float16)
+    qh = oknn.normalize_queries(np.stack([qv, rng.standard_normal(512).astype(np.float32)]))
+    idx, _, sc = B200Searcher(db, device=cuda).search_device(torch.from_numpy(qh).to(cuda), 8, return_scores=True)
+    ri, _, rs = oknn.search(db, qh, 8, return_scores=True)
+    assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(sc.cpu().numpy().view(np.uint64), rs.view(np.uint64))
+    assert set(ri[0]) <= set(hidden)
+
+
+def test_many_exact_duplicates_tie_break(cuda):
+    """4000 identical rows (e.g. placeholder images): ties must resolve to the lowest indices without overflowing anything."""
+    from rdm_b200.knn import B200Searcher
+    rng = np.random.default_rng(10)
+    db = rng.standard_normal((120_000, 512)).astype(np.float16)
+    dup = np.sort(rng.permutation(120_000)[:4000])
+    db[dup] = db[dup[0]]
+    qh = oknn.normalize_queries(db[dup[:1]].astype(np.float32))
+    idx, _ = B200Searcher(db, device=cuda).search_device(torch.from_numpy(qh).to(cuda), 20)
+    assert list(idx[0].cpu().numpy()) == list(dup[:20])
+
+
 def test_other_row_widths(cuda):
     from rdm_b200.knn import B200Searcher
     for d in (256, 768, 1024):

@@ -66,6 +66,40 @@ def test_full_arch_forward_strict(cuda):
     assert err < 1e-4, f"rel-L2 {err:.2e}"
 
 
+@pytest.mark.parametrize("mode,tol", [(1, 1e-4), (2, 3e-2)])
+@pytest.mark.parametrize("B2,H", [(2, 16), (4, 32), (3, 8)])
+def test_tiny_unet_forward_tensor_core(cuda, mode, tol, B2, H):
+    """tcgen05 engine: mode 1 = bf16 hi/lo split (3 MMAs per product, fp32-grade), mode 2 = plain bf16."""
+    ref, net = _pair(ounet.TINY_UNET, 1, cuda)
+    net.set_mode(mode)
+    g = torch.Generator().manual_seed(B2 * 100 + H)
+    x = torch.randn(B2, 4, H, H, generator=g)
+    t = torch.randint(0, 1000, (B2,), generator=g)
+    c = torch.randn(B2, 4, 512, generator=g) * 3
+    with torch.no_grad():
+        want = ref(x, t, c)
+    net.set_context(c.to(cuda))
+    got = net.forward(x.to(cuda), t.to(cuda))
+    err = rel_l2(got, want)
+    assert err < tol, f"mode {mode}: rel-L2 {err:.2e} (tolerance {tol})"
+
+
+@pytest.mark.parametrize("mode,tol", [(1, 1e-4), (2, 3e-2)])
+def test_full_arch_forward_tensor_core(cuda, mode, tol):
+    ref, net = _pair(ounet.BASELINE_UNET, 3, cuda)
+    net.set_mode(mode)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 4, 32, 32, generator=g)
+    t = torch.tensor([991, 991])
+    c = torch.cat([torch.randn(1, 4, 512, generator=g) * 3, torch.zeros(1, 4, 512)])
+    with torch.no_grad():
+        want = ref(x, t, c)
+    net.set_context(c.to(cuda))
+    got = net.forward(x.to(cuda), t.to(cuda))
+    err = rel_l2(got, want)
+    assert err < tol, f"mode {mode}: rel-L2 {err:.2e}"
+
+
 def test_ddim_step_is_bit_exact(cuda):
     from rdm_b200.unet import ddim_step
     sch = oddim.Schedule(100)

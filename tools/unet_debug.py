@@ -8,11 +8,12 @@ from rdm_b200 import _lib
 from rdm_b200.unet import B200UNet
 
 which = sys.argv[1] if len(sys.argv) > 1 else "tiny"
+mode = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 cfg = ounet.TINY_UNET if which == "tiny" else ounet.BASELINE_UNET
 H = 16 if which == "tiny" else 32
 dev = torch.device("cuda:0")
 ref = ounet.randomize_(ounet.UNetModel(**cfg), 1).eval()
-net = B200UNet(dev, **cfg); net.load_state_dict(ref.state_dict())
+net = B200UNet(dev, **cfg); net.load_state_dict(ref.state_dict()); net.set_mode(mode)
 g = torch.Generator().manual_seed(0)
 x = torch.randn(2, cfg["in_channels"], H, H, generator=g); t = torch.tensor([991, 17]); c = torch.randn(2, 4, 512, generator=g) * 3
 rows = []
