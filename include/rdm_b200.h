@@ -124,6 +124,25 @@ RDM_API int rdm_unet_set_context(rdm_unet_t* h, const float* ctx_dev, int32_t B2
 RDM_API int rdm_unet_forward(rdm_unet_t* h, const float* x_dev, int32_t Bx, const int64_t* t_dev, int32_t B2,
                      int32_t H, int32_t W, float* eps_out_dev, void* stream);
 
+/* CUDA-graph replay of the forward (default on).  Off: every kernel is launched eagerly. */
+RDM_API int rdm_unet_set_graph(rdm_unet_t* h, int32_t on);
+/* Same as rdm_unet_forward but eager, with CUDA events around every GEMM launch; synchronises.  out8 =
+ * {tcgen05 GEMM ms, tcgen05 GEMM algorithmic flop, CUDA-core GEMM ms, CUDA-core GEMM flop, whole forward ms,
+ *  #tcgen05 launches, #CUDA-core GEMM launches, 0}.  Used by bench.py for the live roofline numbers. */
+RDM_API int rdm_unet_profile_forward(rdm_unet_t* h, const float* x_dev, int32_t Bx, const int64_t* t_dev, int32_t B2,
+                             int32_t H, int32_t W, float* eps_out_dev, double* out8_host, void* stream);
+
+/* DDIMSampler.ddim_sampling (rdm/models/diffusion/ddim.py:143-215) for steps [first_step, first_step+num_steps) of a
+ * schedule given as device tables IN SAMPLING ORDER: timesteps int64 [S] (= np.flip(ddim_timesteps)), coef float32
+ * [S, 8] rows {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma, 0, 0, 0}, optional noise float32
+ * [S, B*C*H*W] (eta > 0).  x_dev float32 NCHW [B,C,H,W] is updated in place (x_T in, x_{t-1} of the last step out);
+ * pred_x0_dev (optional) receives the last step's x0 prediction.  cfg_scale > 1 evaluates classifier-free guidance by
+ * batch doubling (ddim.py:229-238): the context must have been set with B2 = 2B rows [cond | uncond]; otherwise B2 = B.
+ * One CUDA graph {timestep fill, U-Net, fused CFG+DDIM update, step++} is captured once and replayed per step. */
+RDM_API int rdm_ddim_sample(rdm_unet_t* h, float* x_dev, int32_t B, int32_t H, int32_t W, const int64_t* timesteps_dev,
+                    const float* coef_dev, int32_t first_step, int32_t num_steps, float cfg_scale, const float* noise_dev,
+                    float* pred_x0_dev, void* stream);
+
 /* DDIMSampler.p_sample_ddim arithmetic after the model call (rdm/models/diffusion/ddim.py:236-238,253-267):
  * e = cfg ? e_u + scale*(e_c - e_u) : eps;  pred_x0 = (x - c0*e)/c1;  x_prev = c2*pred_x0 + c3*e (+ c4*noise),
  * coef_dev = {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma} as float32 (device).

@@ -260,6 +260,29 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
     if (pred_x0) pred_x0[i] = p0;
 }
 
+__global__ void fill_timesteps_kernel(const long long* __restrict__ timesteps, const int* __restrict__ step, int B2, long long* __restrict__ t_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B2) t_out[i] = timesteps[*step];
+}
+__global__ void ddim_update_table_kernel(const float* __restrict__ x, const float* __restrict__ eps, long long n, int cfg, float scale,
+                                         const float* __restrict__ coef_table, const int* __restrict__ step, const float* __restrict__ noise_table,
+                                         float* __restrict__ x_prev, float* __restrict__ pred_x0) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = *step;
+    const float* coef = coef_table + 8 * s;
+    const float s1m = coef[0], sqrt_at = coef[1], sqrt_aprev = coef[2], dirc = coef[3], sigma = coef[4];
+    float e = eps[i];
+    if (cfg) { float eu = eps[n + i]; e = __fadd_rn(eu, __fmul_rn(scale, __fsub_rn(e, eu))); }
+    float xv = x[i];
+    float p0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(s1m, e)), sqrt_at);
+    float xp = __fadd_rn(__fmul_rn(sqrt_aprev, p0), __fmul_rn(dirc, e));
+    if (noise_table) xp = __fadd_rn(xp, __fmul_rn(sigma, noise_table[(size_t)s * n + i]));
+    x_prev[i] = xp;
+    if (pred_x0) pred_x0[i] = p0;
+}
+__global__ void step_advance_kernel(int* step) { *step += 1; }
+
 inline int blocks_for(long long n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace
@@ -332,5 +355,19 @@ int k_silu(const float* in, float* out, long long n, cudaStream_t st) {
 int k_ddim_update(const float* x, const float* eps, long long n, int cfg, float scale, const float* coef, const float* noise,
                   float* x_prev, float* pred_x0, cudaStream_t st) {
     ddim_update_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, eps, n, cfg, scale, coef, noise, x_prev, pred_x0);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+
+int k_fill_timesteps(const long long* timesteps, const int* step, int B2, long long* t_out, cudaStream_t st) {
+    fill_timesteps_kernel<<<blocks_for(B2, 128), 128, 0, st>>>(timesteps, step, B2, t_out);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_ddim_update_table(const float* x, const float* eps, long long n, int cfg, float scale, const float* coef_table, const int* step,
+                        const float* noise_table, float* x_prev, float* pred_x0, cudaStream_t st) {
+    ddim_update_table_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, eps, n, cfg, scale, coef_table, step, noise_table, x_prev, pred_x0);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_step_advance(int* step, cudaStream_t st) {
+    step_advance_kernel<<<1, 1, 0, st>>>(step);
     LAUNCH_CHECK(); return RDM_OK;
 }

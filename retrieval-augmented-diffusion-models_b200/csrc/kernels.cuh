@@ -70,3 +70,10 @@ int k_silu(const float* in, float* out, long long n, cudaStream_t st);
 // coef (device, 8 floats per step): {sqrt_one_minus_at, 1/sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma, 0,0,0}
 int k_ddim_update(const float* x, const float* eps, long long n_per_half, int cfg, float scale, const float* coef_dev,
                   const float* noise, float* x_prev, float* pred_x0, cudaStream_t st);
+// Table-driven variants for the graph-captured sampling loop: the step index lives in device memory so ONE captured
+// graph serves every step.  t_out[0..B2) = timesteps[*step]; coefficients = coef_table + 8*(*step); noise (optional)
+// = noise_table + (*step)*n_per_half; k_step_advance increments *step.
+int k_fill_timesteps(const long long* timesteps, const int* step, int B2, long long* t_out, cudaStream_t st);
+int k_ddim_update_table(const float* x, const float* eps, long long n_per_half, int cfg, float scale, const float* coef_table, const int* step,
+                        const float* noise_table, float* x_prev, float* pred_x0, cudaStream_t st);
+int k_step_advance(int* step, cudaStream_t st);

@@ -69,6 +69,16 @@ struct rdm_unet {
     int plan_B = 0, plan_H = 0, plan_W = 0;
     std::vector<float*> host_scratch;
     int debug = 0, debug_block = 0; std::string debug_log;
+    // CUDA-graph replay: fixed staging buffers + one captured graph per (Bx, B2, H, W, mode)
+    int use_graph = 1;
+    float* x_in = nullptr; long long* t_in = nullptr; float* eps_buf = nullptr; float* x_state = nullptr; float* p0_buf = nullptr; int* step_dev = nullptr;
+    size_t io_cap = 0;
+    cudaStream_t cap_stream = nullptr;
+    cudaGraphExec_t fwd_exec = nullptr; int fwd_key[5] = {0, 0, 0, 0, -1};
+    cudaGraphExec_t step_exec = nullptr; long long step_key[10] = {0};
+    unsigned long long fwd_kernels = 0, step_kernels = 0;      // kernels inside each captured graph (for rdm_launch_count)
+    // profiling (rdm_unet_profile_forward): event pairs around every GEMM launch
+    int profile = 0; std::vector<cudaEvent_t> prof_ev; std::vector<double> prof_flops; std::vector<int> prof_kind;
 };
 
 namespace {
@@ -274,6 +284,16 @@ void gemm_any(Ctx& cx, const Opnd& a, int B, int H, int W, int C, int ks, int st
     if (!e.bias) e.bias = bias;
     const int Ho = ups ? H * 2 : (stride == 2 ? (H + 1) / 2 : H), Wo = ups ? W * 2 : (stride == 2 ? (W + 1) / 2 : W);
     const int M = B * Ho * Wo, Nout = e.act == ACT_GEGLU ? N / 2 : N;
+    struct ProfScope {
+        Ctx& cx; bool on;
+        ProfScope(Ctx& c, double flops, int kind) : cx(c), on(!c.dry && c.n->profile) {
+            if (!on) return;
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            cx.n->prof_ev.push_back(e0); cx.n->prof_ev.push_back(e1); cx.n->prof_flops.push_back(flops); cx.n->prof_kind.push_back(kind);
+            cudaEventRecord(e0, cx.st);
+        }
+        ~ProfScope() { if (on) cudaEventRecord(cx.n->prof_ev.back(), cx.st); }
+    } prof(cx, 2.0 * M * (double)N * ks * ks * C, a.tc() ? 1 : 0);
     if (a.tc()) {
         TcA ta; ta.hi = a.hi; ta.lo = a.lo; ta.ld = a.ldb; ta.B = B; ta.H = H; ta.W = W; ta.C = C; ta.ksize = ks;
         TcW tw; tw.hi = w_hi(n, w); tw.lo = w_lo(n, w); tw.N = N; tw.K = ks * ks * C; tw.ld = tw.K;
@@ -512,6 +532,60 @@ int ensure_plan(Net* n, int B2, int H, int W) {
         n->stats_cap = sneed;
     }
     n->plan_B = B2; n->plan_H = H; n->plan_W = W;
+    if (n->fwd_exec) { cudaGraphExecDestroy(n->fwd_exec); n->fwd_exec = nullptr; }      // buffers moved: recapture
+    if (n->step_exec) { cudaGraphExecDestroy(n->step_exec); n->step_exec = nullptr; }
+    return RDM_OK;
+}
+
+
+int ensure_io(Net* n, int B2, int H, int W) {
+    const size_t C = (size_t)(n->cfg.in_channels > n->cfg.out_channels ? n->cfg.in_channels : n->cfg.out_channels);
+    const size_t need = (size_t)B2 * C * H * W;
+    if (!n->cap_stream) RDM_CHECK_CUDA(cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking));
+    if (!n->step_dev) RDM_CHECK_CUDA(cudaMalloc((void**)&n->step_dev, sizeof(int)));
+    if (need <= n->io_cap) return RDM_OK;
+    for (float** p : {&n->x_in, &n->eps_buf, &n->x_state, &n->p0_buf}) { if (*p) cudaFree(*p); *p = nullptr; }
+    if (n->t_in) cudaFree(n->t_in); n->t_in = nullptr;
+    n->io_cap = 0;
+    if (n->fwd_exec) { cudaGraphExecDestroy(n->fwd_exec); n->fwd_exec = nullptr; }
+    if (n->step_exec) { cudaGraphExecDestroy(n->step_exec); n->step_exec = nullptr; }
+    RDM_CHECK_CUDA(cudaMalloc((void**)&n->x_in, need * 4)); RDM_CHECK_CUDA(cudaMalloc((void**)&n->eps_buf, need * 4));
+    RDM_CHECK_CUDA(cudaMalloc((void**)&n->x_state, need * 4)); RDM_CHECK_CUDA(cudaMalloc((void**)&n->p0_buf, need * 4));
+    RDM_CHECK_CUDA(cudaMalloc((void**)&n->t_in, (size_t)B2 * 8));
+    n->io_cap = need;
+    return RDM_OK;
+}
+
+// Captures `body` (which must only enqueue work on n->cap_stream) into an executable graph.
+template <typename F> int capture_graph(Net* n, cudaGraphExec_t* exec, unsigned long long* nkernels, F body) {
+    if (*exec) { cudaGraphExecDestroy(*exec); *exec = nullptr; }
+    RDM_CHECK_CUDA(cudaStreamBeginCapture(n->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const unsigned long long before = g_rdm_launches;
+    int rc = body(n->cap_stream);
+    *nkernels = g_rdm_launches - before; g_rdm_launches = before;       // captured, not executed
+    cudaGraph_t g = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(n->cap_stream, &g);
+    if (rc != RDM_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    RDM_REQUIRE(ce == cudaSuccess && g, RDM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(exec, g, 0);
+    cudaGraphDestroy(g);
+    RDM_REQUIRE(ce == cudaSuccess, RDM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    return RDM_OK;
+}
+
+// eps_buf = UNet(x_in [Bx], t_in [B2]) by graph replay on `st` (first call per shape runs eagerly once, then captures).
+int forward_staged(Net* n, int Bx, int B2, int H, int W, cudaStream_t st) {
+    if (!n->use_graph || n->debug || n->profile) return forward_impl(n, n->x_in, Bx, n->t_in, B2, H, W, n->eps_buf, st, false);
+    const int key[5] = {Bx, B2, H, W, n->mode};
+    if (!n->fwd_exec || memcmp(key, n->fwd_key, sizeof(key)) != 0) {
+        RDM_TRY(forward_impl(n, n->x_in, Bx, n->t_in, B2, H, W, n->eps_buf, st, false));     // eager warm-up: sets kernel attributes
+        RDM_CHECK_CUDA(cudaStreamSynchronize(st));
+        RDM_TRY(capture_graph(n, &n->fwd_exec, &n->fwd_kernels, [&](cudaStream_t cs) { return forward_impl(n, n->x_in, Bx, n->t_in, B2, H, W, n->eps_buf, cs, false); }));
+        memcpy(n->fwd_key, key, sizeof(key));
+        return RDM_OK;                         // the warm-up already produced this call's result
+    }
+    RDM_CHECK_CUDA(cudaGraphLaunch(n->fwd_exec, st));
+    g_rdm_launches += n->fwd_kernels;
     return RDM_OK;
 }
 
@@ -553,6 +627,12 @@ void rdm_unet_destroy(rdm_unet_t* n) {
     if (n->stats) cudaFree(n->stats);
     if (n->ctx_kv) cudaFree(n->ctx_kv);
     if (n->t_dev) cudaFree(n->t_dev);
+    if (n->fwd_exec) cudaGraphExecDestroy(n->fwd_exec);
+    if (n->step_exec) cudaGraphExecDestroy(n->step_exec);
+    for (float* p : {n->x_in, n->eps_buf, n->x_state, n->p0_buf}) if (p) cudaFree(p);
+    if (n->t_in) cudaFree(n->t_in);
+    if (n->step_dev) cudaFree(n->step_dev);
+    if (n->cap_stream) cudaStreamDestroy(n->cap_stream);
     delete n;
 }
 
@@ -612,11 +692,16 @@ int rdm_unet_set_context(rdm_unet_t* n, const float* ctx, int32_t B2, int32_t k,
     const int rows = B2 * k;
     size_t per_row = 0; for (auto& s : n->sts) per_row += (size_t)2 * s.C;
     size_t need = per_row * rows;
+    bool relayout = (B2 != n->ctx_B || k != n->ctx_k);
     if (need > n->ctx_kv_floats) {
         if (n->ctx_kv) cudaFree(n->ctx_kv);
         n->ctx_kv = nullptr; n->ctx_kv_floats = 0;
         RDM_CHECK_CUDA(cudaMalloc((void**)&n->ctx_kv, need * sizeof(float)));
-        n->ctx_kv_floats = need;
+        n->ctx_kv_floats = need; relayout = true;
+    }
+    if (relayout) {       // captured graphs hold the K/V addresses and the neighbour count
+        if (n->fwd_exec) { cudaGraphExecDestroy(n->fwd_exec); n->fwd_exec = nullptr; }
+        if (n->step_exec) { cudaGraphExecDestroy(n->step_exec); n->step_exec = nullptr; }
     }
     size_t off = 0;
     Ctx cx{n, st, false};
@@ -638,9 +723,89 @@ int rdm_unet_forward(rdm_unet_t* n, const float* x, int32_t Bx, const int64_t* t
     int div = 1; for (int i = 1; i < n->cfg.n_channel_mult; i++) div *= 2;
     RDM_REQUIRE(H % div == 0 && W % div == 0, RDM_ERR_ARG, "rdm_unet_forward: H=%d W=%d must be multiples of %d", H, W, div);
     DeviceGuard guard(n->device);
+    cudaStream_t st = (cudaStream_t)stream;
     RDM_TRY(ensure_plan(n, B2, H, W));
-    RDM_TRY(ensure_weight_planes(n, (cudaStream_t)stream));
-    return forward_impl(n, x, Bx, (const long long*)t, B2, H, W, eps_out, (cudaStream_t)stream, false);
+    RDM_TRY(ensure_weight_planes(n, st));
+    RDM_TRY(ensure_io(n, B2, H, W));
+    const size_t per = (size_t)H * W;
+    RDM_CHECK_CUDA(cudaMemcpyAsync(n->x_in, x, (size_t)Bx * n->cfg.in_channels * per * 4, cudaMemcpyDeviceToDevice, st));
+    RDM_CHECK_CUDA(cudaMemcpyAsync(n->t_in, t, (size_t)B2 * 8, cudaMemcpyDeviceToDevice, st));
+    RDM_TRY(forward_staged(n, Bx, B2, H, W, st));
+    RDM_CHECK_CUDA(cudaMemcpyAsync(eps_out, n->eps_buf, (size_t)B2 * n->cfg.out_channels * per * 4, cudaMemcpyDeviceToDevice, st));
+    return RDM_OK;
+}
+
+int rdm_unet_set_graph(rdm_unet_t* n, int32_t on) { RDM_REQUIRE(n, RDM_ERR_ARG, "rdm_unet_set_graph: null handle"); n->use_graph = on; return RDM_OK; }
+
+int rdm_unet_profile_forward(rdm_unet_t* n, const float* x, int32_t Bx, const int64_t* t, int32_t B2, int32_t H, int32_t W, float* eps_out,
+                             double* out8, void* stream) {
+    RDM_REQUIRE(n && out8, RDM_ERR_ARG, "rdm_unet_profile_forward: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    n->profile = 1; n->prof_ev.clear(); n->prof_flops.clear(); n->prof_kind.clear();
+    cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
+    cudaEventRecord(t0, st);
+    int rc = rdm_unet_forward(n, x, Bx, t, B2, H, W, eps_out, stream);
+    cudaEventRecord(t1, st);
+    n->profile = 0;
+    cudaError_t ce = cudaStreamSynchronize(st);
+    for (int i = 0; i < 8; i++) out8[i] = 0.0;
+    if (rc == RDM_OK && ce == cudaSuccess) {
+        float ms = 0.f; cudaEventElapsedTime(&ms, t0, t1); out8[4] = ms;
+        for (size_t i = 0; i < n->prof_flops.size(); i++) {
+            float m = 0.f; cudaEventElapsedTime(&m, n->prof_ev[2 * i], n->prof_ev[2 * i + 1]);
+            const int kind = n->prof_kind[i];
+            out8[kind ? 0 : 2] += m; out8[kind ? 1 : 3] += n->prof_flops[i]; out8[kind ? 5 : 6] += 1.0;
+        }
+    }
+    for (cudaEvent_t e : n->prof_ev) cudaEventDestroy(e);
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    n->prof_ev.clear(); n->prof_flops.clear(); n->prof_kind.clear();
+    RDM_REQUIRE(ce == cudaSuccess, RDM_ERR_CUDA, "rdm_unet_profile_forward: %s", cudaGetErrorString(ce));
+    return rc;
+}
+
+int rdm_ddim_sample(rdm_unet_t* n, float* x_dev, int32_t B, int32_t H, int32_t W, const int64_t* timesteps_dev, const float* coef_dev,
+                    int32_t first_step, int32_t num_steps, float cfg_scale, const float* noise_dev, float* pred_x0_dev, void* stream) {
+    RDM_REQUIRE(n && x_dev && timesteps_dev && coef_dev, RDM_ERR_ARG, "rdm_ddim_sample: null argument");
+    RDM_REQUIRE(B >= 1 && num_steps >= 0 && first_step >= 0, RDM_ERR_ARG, "rdm_ddim_sample: bad sizes");
+    RDM_REQUIRE(n->cfg.in_channels == n->cfg.out_channels, RDM_ERR_UNSUPPORTED, "rdm_ddim_sample: eps-model needs in_channels == out_channels");
+    const int cfg = cfg_scale > 1.f ? 1 : 0, B2 = cfg ? 2 * B : B;
+    RDM_REQUIRE(n->ctx_B == B2, RDM_ERR_STATE, "rdm_ddim_sample: context was set for batch %d, need %d ([cond | uncond] when cfg_scale > 1)", n->ctx_B, B2);
+    if (num_steps == 0) return RDM_OK;
+    DeviceGuard guard(n->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    RDM_TRY(ensure_plan(n, B2, H, W));
+    RDM_TRY(ensure_weight_planes(n, st));
+    RDM_TRY(ensure_io(n, B2, H, W));
+    const long long nper = (long long)B * n->cfg.in_channels * H * W;
+    RDM_CHECK_CUDA(cudaMemcpyAsync(n->x_in, x_dev, (size_t)nper * 4, cudaMemcpyDeviceToDevice, st));
+    RDM_CHECK_CUDA(cudaMemcpyAsync(n->step_dev, &first_step, sizeof(int), cudaMemcpyHostToDevice, st));
+    // one step = {t_in <- timesteps[step]; eps = UNet(x_in); x_in <- ddim(x_in, eps, coef[step]); step++}; x_in doubles as the state
+    auto body = [&](cudaStream_t cs) -> int {
+        RDM_TRY(k_fill_timesteps((const long long*)timesteps_dev, n->step_dev, B2, n->t_in, cs));
+        RDM_TRY(forward_impl(n, n->x_in, B, n->t_in, B2, H, W, n->eps_buf, cs, false));
+        RDM_TRY(k_ddim_update_table(n->x_in, n->eps_buf, nper, cfg, cfg_scale, coef_dev, n->step_dev, noise_dev, n->x_in, n->p0_buf, cs));
+        RDM_TRY(k_step_advance(n->step_dev, cs));
+        return RDM_OK;
+    };
+    int done = 0;
+    if (n->use_graph && !n->debug) {
+        long long key[10] = {B, B2, H, W, n->mode, (long long)(uintptr_t)timesteps_dev, (long long)(uintptr_t)coef_dev, (long long)(uintptr_t)noise_dev, cfg,
+                             (long long)(cfg_scale * 1e6)};
+        if (!n->step_exec || memcmp(key, n->step_key, sizeof(key)) != 0) {
+            RDM_TRY(body(st));                                 // eager first step (also the warm-up)
+            RDM_CHECK_CUDA(cudaStreamSynchronize(st));
+            done = 1;
+            RDM_TRY(capture_graph(n, &n->step_exec, &n->step_kernels, body));
+            memcpy(n->step_key, key, sizeof(key));
+        }
+        for (int i = done; i < num_steps; i++) { RDM_CHECK_CUDA(cudaGraphLaunch(n->step_exec, st)); g_rdm_launches += n->step_kernels; }
+    } else {
+        for (int i = 0; i < num_steps; i++) RDM_TRY(body(st));
+    }
+    RDM_CHECK_CUDA(cudaMemcpyAsync(x_dev, n->x_in, (size_t)nper * 4, cudaMemcpyDeviceToDevice, st));
+    if (pred_x0_dev) RDM_CHECK_CUDA(cudaMemcpyAsync(pred_x0_dev, n->p0_buf, (size_t)nper * 4, cudaMemcpyDeviceToDevice, st));
+    return RDM_OK;
 }
 
 int rdm_ddim_step(const float* x, const float* eps, int64_t n_per_half, int32_t cfg, float scale, const float* coef_dev,

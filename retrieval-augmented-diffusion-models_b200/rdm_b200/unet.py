@@ -184,6 +184,34 @@ class B200UNet:
         return out
 
 
+    def set_graph(self, on):
+        _lib.check(_lib.lib().rdm_unet_set_graph(self._h, 1 if on else 0), "rdm_unet_set_graph")
+
+    def profile_forward(self, x, t):
+        """Eager forward with CUDA events around every GEMM -> dict(tc_ms, tc_flop, simt_ms, simt_flop, total_ms, n_tc, n_simt)."""
+        x = x.to(self.device, torch.float32).contiguous(); t = t.to(self.device, torch.int64).contiguous()
+        B2, (Bx, _, H, W) = t.shape[0], x.shape
+        out = torch.empty((B2, self.cfg["out_channels"], H, W), dtype=torch.float32, device=self.device)
+        o8 = (ctypes.c_double * 8)()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().rdm_unet_profile_forward(self._h, _lib.ptr(x), Bx, _lib.ptr(t), B2, H, W, _lib.ptr(out), o8, _lib.stream_ptr(self.device)),
+                       "rdm_unet_profile_forward")
+        return dict(tc_ms=o8[0], tc_flop=o8[1], simt_ms=o8[2], simt_flop=o8[3], total_ms=o8[4], n_tc=int(o8[5]), n_simt=int(o8[6]))
+
+    def ddim_sample(self, x, timesteps, coef, cfg_scale=1.0, first_step=0, num_steps=None, noise=None, want_pred_x0=False):
+        """Fused sampling loop (rdm_ddim_sample): x [B,C,H,W] CUDA float32 is consumed and the result returned.
+        timesteps int64 [S] / coef float32 [S,8] in sampling order (see sampler.make_ddim_tables)."""
+        x = x.to(self.device, torch.float32).contiguous().clone()
+        B, _, H, W = x.shape
+        S = timesteps.shape[0]
+        num_steps = S - first_step if num_steps is None else num_steps
+        p0 = torch.empty_like(x) if want_pred_x0 else None
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().rdm_ddim_sample(self._h, _lib.ptr(x), B, H, W, _lib.ptr(timesteps), _lib.ptr(coef), int(first_step), int(num_steps),
+                                                  float(cfg_scale), _lib.ptr(noise), _lib.ptr(p0), _lib.stream_ptr(self.device)), "rdm_ddim_sample")
+        return (x, p0) if want_pred_x0 else x
+
+
 def ddim_step(x, eps, coef_row, cfg_scale=None, noise=None, want_pred_x0=True):
     """One fused CFG + DDIM update (ddim.py:236-238,253-267).  x [B,...], eps [2B,...] if cfg_scale is not None else [B,...];
     coef_row: CUDA float32 [>=5] = {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma}."""

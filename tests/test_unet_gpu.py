@@ -134,3 +134,64 @@ def test_ddim_trajectory_tiny(cuda):
         x, _ = ddim_step(x, eps, coef, cfg_scale=scale)
     err = rel_l2(x, want)
     assert err < 1e-3, f"DDIM-10 final latent rel-L2 {err:.2e}"
+
+
+def _tables(S, cuda):
+    from rdm_b200 import sampler
+    return sampler.make_ddim_tables(sampler.alphas_cumprod_linear(), S, 0.0, device=cuda)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fused_ddim_loop_matches_oracle_tiny(cuda, mode):
+    """rdm_ddim_sample (one captured CUDA graph replayed per step) vs the oracle sampler: DDIM-10, CFG 2.0, zeros uncond."""
+    ref, net = _pair(ounet.TINY_UNET, 5, cuda)
+    net.set_mode(mode)
+    g = torch.Generator().manual_seed(21)
+    B, S = 3, 10
+    x_T = torch.randn(B, 4, 16, 16, generator=g)
+    cond, unc = torch.randn(B, 4, 512, generator=g) * 3, torch.zeros(B, 4, 512)
+    want = oddim.ddim_sample(ref, x_T, cond, unc, S=S, scale=2.0)
+    tb = _tables(S, cuda)
+    net.set_context(torch.cat([cond, unc]).to(cuda))
+    got, p0 = net.ddim_sample(x_T.to(cuda), tb["timesteps"], tb["coef"], cfg_scale=2.0, want_pred_x0=True)
+    assert rel_l2(got, want) < 1e-3
+    # a second call replays the captured graph with a new x_T and a new context of the same shape
+    x2 = torch.randn(B, 4, 16, 16, generator=g)
+    cond2 = torch.randn(B, 4, 512, generator=g)
+    want2 = oddim.ddim_sample(ref, x2, cond2, unc, S=S, scale=2.0)
+    net.set_context(torch.cat([cond2, unc]).to(cuda))
+    got2 = net.ddim_sample(x2.to(cuda), tb["timesteps"], tb["coef"], cfg_scale=2.0)
+    assert rel_l2(got2, want2) < 1e-3
+    # split ranges (what DDIMSampler does around intermediates) give the same trajectory
+    net.set_context(torch.cat([cond, unc]).to(cuda))
+    a = net.ddim_sample(x_T.to(cuda), tb["timesteps"], tb["coef"], cfg_scale=2.0, first_step=0, num_steps=4)
+    b = net.ddim_sample(a, tb["timesteps"], tb["coef"], cfg_scale=2.0, first_step=4, num_steps=6)
+    assert torch.equal(b, got)
+
+
+def test_no_cfg_path(cuda):
+    ref, net = _pair(ounet.TINY_UNET, 6, cuda)
+    g = torch.Generator().manual_seed(5)
+    x_T, cond = torch.randn(2, 4, 16, 16, generator=g), torch.randn(2, 2, 512, generator=g)
+    want = oddim.ddim_sample(ref, x_T, cond, None, S=5, scale=1.0)
+    tb = _tables(5, cuda)
+    net.set_context(cond.to(cuda))
+    got = net.ddim_sample(x_T.to(cuda), tb["timesteps"], tb["coef"], cfg_scale=1.0)
+    assert rel_l2(got, want) < 1e-3
+
+
+@pytest.mark.parametrize("mode,tol", [(1, 1e-3)])
+def test_full_arch_ddim20_tensor_core(cuda, mode, tol):
+    """BASELINE cfg2 architecture, 20 chained CFG steps, one image: denoised latents within 1e-3 rel of the fp32 oracle."""
+    ref, net = _pair(ounet.BASELINE_UNET, 3, cuda)
+    net.set_mode(mode)
+    g = torch.Generator().manual_seed(31)
+    x_T = torch.randn(1, 4, 32, 32, generator=g)
+    cond, unc = torch.randn(1, 4, 512, generator=g) * 3, torch.zeros(1, 4, 512)
+    want = oddim.ddim_sample(ref, x_T, cond, unc, S=20, scale=2.0)
+    tb = _tables(20, cuda)
+    net.set_context(torch.cat([cond, unc]).to(cuda))
+    got = net.ddim_sample(x_T.to(cuda), tb["timesteps"], tb["coef"], cfg_scale=2.0)
+    err = rel_l2(got, want)
+    print(f"full-arch DDIM-20 mode {mode}: rel-L2 {err:.3e}")
+    assert err < tol
