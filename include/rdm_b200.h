@@ -132,6 +132,9 @@ RDM_API int rdm_unet_set_graph(rdm_unet_t* h, int32_t on);
 RDM_API int rdm_unet_profile_forward(rdm_unet_t* h, const float* x_dev, int32_t Bx, const int64_t* t_dev, int32_t B2,
                              int32_t H, int32_t W, float* eps_out_dev, double* out8_host, void* stream);
 
+/* Per-GEMM lines ("<engine> M= N= K= ks= HxW= act= ms= tflops=") of the last rdm_unet_profile_forward. */
+RDM_API const char* rdm_unet_profile_text(const rdm_unet_t* h);
+
 /* DDIMSampler.ddim_sampling (rdm/models/diffusion/ddim.py:143-215) for steps [first_step, first_step+num_steps) of a
  * schedule given as device tables IN SAMPLING ORDER: timesteps int64 [S] (= np.flip(ddim_timesteps)), coef float32
  * [S, 8] rows {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma, 0, 0, 0}, optional noise float32

@@ -79,6 +79,7 @@ struct rdm_unet {
     unsigned long long fwd_kernels = 0, step_kernels = 0;      // kernels inside each captured graph (for rdm_launch_count)
     // profiling (rdm_unet_profile_forward): event pairs around every GEMM launch
     int profile = 0; std::vector<cudaEvent_t> prof_ev; std::vector<double> prof_flops; std::vector<int> prof_kind;
+    std::vector<std::string> prof_desc; std::string prof_text;
 };
 
 namespace {
@@ -294,6 +295,7 @@ void gemm_any(Ctx& cx, const Opnd& a, int B, int H, int W, int C, int ks, int st
         }
         ~ProfScope() { if (on) cudaEventRecord(cx.n->prof_ev.back(), cx.st); }
     } prof(cx, 2.0 * M * (double)N * ks * ks * C, a.tc() ? 1 : 0);
+    if (prof.on) { char d[128]; snprintf(d, sizeof(d), "%s M=%d N=%d K=%d ks=%d HxW=%dx%d act=%d", a.tc() ? "tc" : "simt", M, N, ks * ks * C, ks, H, W, e.act); n->prof_desc.push_back(d); }
     if (a.tc()) {
         TcA ta; ta.hi = a.hi; ta.lo = a.lo; ta.ld = a.ldb; ta.B = B; ta.H = H; ta.W = W; ta.C = C; ta.ksize = ks;
         TcW tw; tw.hi = w_hi(n, w); tw.lo = w_lo(n, w); tw.N = N; tw.K = ks * ks * C; tw.ld = tw.K;
@@ -741,7 +743,7 @@ int rdm_unet_profile_forward(rdm_unet_t* n, const float* x, int32_t Bx, const in
                              double* out8, void* stream) {
     RDM_REQUIRE(n && out8, RDM_ERR_ARG, "rdm_unet_profile_forward: null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    n->profile = 1; n->prof_ev.clear(); n->prof_flops.clear(); n->prof_kind.clear();
+    n->profile = 1; n->prof_ev.clear(); n->prof_flops.clear(); n->prof_kind.clear(); n->prof_desc.clear(); n->prof_text.clear();
     cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
     cudaEventRecord(t0, st);
     int rc = rdm_unet_forward(n, x, Bx, t, B2, H, W, eps_out, stream);
@@ -755,6 +757,8 @@ int rdm_unet_profile_forward(rdm_unet_t* n, const float* x, int32_t Bx, const in
             float m = 0.f; cudaEventElapsedTime(&m, n->prof_ev[2 * i], n->prof_ev[2 * i + 1]);
             const int kind = n->prof_kind[i];
             out8[kind ? 0 : 2] += m; out8[kind ? 1 : 3] += n->prof_flops[i]; out8[kind ? 5 : 6] += 1.0;
+            char line[256]; snprintf(line, sizeof(line), "%s ms=%.4f tflops=%.1f\n", n->prof_desc[i].c_str(), m, n->prof_flops[i] / (m * 1e-3) / 1e12);
+            n->prof_text += line;
         }
     }
     for (cudaEvent_t e : n->prof_ev) cudaEventDestroy(e);
@@ -763,6 +767,8 @@ int rdm_unet_profile_forward(rdm_unet_t* n, const float* x, int32_t Bx, const in
     RDM_REQUIRE(ce == cudaSuccess, RDM_ERR_CUDA, "rdm_unet_profile_forward: %s", cudaGetErrorString(ce));
     return rc;
 }
+
+const char* rdm_unet_profile_text(const rdm_unet_t* n) { return n ? n->prof_text.c_str() : ""; }
 
 int rdm_ddim_sample(rdm_unet_t* n, float* x_dev, int32_t B, int32_t H, int32_t W, const int64_t* timesteps_dev, const float* coef_dev,
                     int32_t first_step, int32_t num_steps, float cfg_scale, const float* noise_dev, float* pred_x0_dev, void* stream) {
