@@ -18,6 +18,7 @@
 #include "gemm_tc.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cstdlib>
 
 namespace {
 
@@ -119,8 +120,107 @@ struct TcSmem {
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+    static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
+    static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
+// ---- epilogue helpers: everything stays in registers (compile-time indices only) ----------------------
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        __nv_bfloat16 a = __float2bfloat16_rn(v[2 * j]), b = __float2bfloat16_rn(v[2 * j + 1]);
+        __nv_bfloat162 p = __halves2bfloat162(a, b);
+        h[j] = *reinterpret_cast<uint32_t*>(&p);
+        __nv_bfloat162 q = __halves2bfloat162(__float2bfloat16_rn(v[2 * j] - __bfloat162float(a)), __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(b)));
+        l[j] = *reinterpret_cast<uint32_t*>(&q);
+    }
+    *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// One 32-column chunk of one output row: r = accumulators (fp32 bits), row m, first column nb.
+__device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const uint32_t (&r)[32], int m, int bidx, int nb) {
+    const bool full = nb + 32 <= p.N;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+    if (full) {
+        if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+        }
+        if (p.rowvec) {
+            const float* rv = p.rowvec + (size_t)bidx * p.rowvec_ld + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) { float4 t = __ldg(reinterpret_cast<const float4*>(rv + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+        }
+        if (p.act == ACT_GEGLU) {
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
+            const int no = nb >> 1;
+            if (p.res) {
+                const float* rs = p.res + (size_t)m * p.res_ld + no;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) { float4 t = *reinterpret_cast<const float4*>(rs + j); o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w; }
+            }
+            if (p.out) {
+                float* dst = p.out + (size_t)m * p.out_ld + no;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            } else {
+                __nv_bfloat16* dh = p.out_hi + (size_t)m * p.out_bf_ld + no;
+                __nv_bfloat16* dl = p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + no : nullptr;
+#pragma unroll
+                for (int j = 0; j < 16; j += 8) store_bf16x8(dh + j, dl ? dl + j : nullptr, o + j);
+            }
+            return;
+        }
+        if (p.act == ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = silu_f(v[j]);
+        }
+        if (p.res) {
+            const float* rs = p.res + (size_t)m * p.res_ld + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) { float4 t = *reinterpret_cast<const float4*>(rs + j); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+        }
+        if (p.out) {
+            float* dst = p.out + (size_t)m * p.out_ld + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+            __nv_bfloat16* dh = p.out_hi + (size_t)m * p.out_bf_ld + nb;
+            __nv_bfloat16* dl = p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + nb : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) store_bf16x8(dh + j, dl ? dl + j : nullptr, v + j);
+        }
+        return;
+    }
+    // ragged last chunk (N not a multiple of 32; only the 4-channel output conv): predicated scalar path, still unrolled
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const int n = nb + j;
+        if (n < p.N) {
+            float t = v[j];
+            if (p.bias) t += __ldg(p.bias + n);
+            if (p.rowvec) t += __ldg(p.rowvec + (size_t)bidx * p.rowvec_ld + n);
+            if (p.act == ACT_SILU) t = silu_f(t);
+            if (p.res) t += p.res[(size_t)m * p.res_ld + n];
+            if (p.out) p.out[(size_t)m * p.out_ld + n] = t;
+            else {
+                __nv_bfloat16 h = __float2bfloat16_rn(t);
+                p.out_hi[(size_t)m * p.out_bf_ld + n] = h;
+                if (p.out_lo) p.out_lo[(size_t)m * p.out_bf_ld + n] = __float2bfloat16_rn(t - __bfloat162float(h));
+            }
+        }
+    }
+}
+
+// Persistent: grid = min(#tiles, #SMs); CTA c handles tiles c, c+grid, ...; tile -> (mt, nt) with nt fastest so
+// co-scheduled CTAs share the A tile in L2.  TMEM holds TWO accumulators: the epilogue of tile i overlaps the MMAs of i+1.
 template <int BN, int NSPLIT, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -130,22 +230,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
     uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty + STAGES;          // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, mt = blockIdx.y;
     const int nkb = p.taps * p.kb_per_tap;
+    const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + BM - 1) / BM, ntiles = ntn * ntm;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmB_hi);
         if (NSPLIT == 3) { prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_lo); }
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)S::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -155,130 +256,87 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            // tile origin in (x, y, b) of the NHWC plane
-            int x0 = 0, y0 = 0, b0 = 0;
-            if (p.plain) x0 = mt * BM;
-            else if (p.bb > 1 || p.bh * p.bw == p.H * p.W) b0 = mt * p.bb;
-            else { int tiles_per_img = (p.H * p.W) / BM; b0 = mt / tiles_per_img; y0 = (mt % tiles_per_img) * p.bh; }
-            for (int kb = 0; kb < nkb; kb++) {
-                const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                uint8_t* st = smem + s * S::STAGE_BYTES;
-                mbar_expect_tx(&full[s], S::STAGE_BYTES);
-                const int tap = kb / p.kb_per_tap, kc = (kb - tap * p.kb_per_tap) * BK;
-                const int dy = p.ksize == 3 ? tap / 3 - 1 : 0, dx = p.ksize == 3 ? tap % 3 - 1 : 0;
-                tma_load_4d(st, &tmA_hi, &full[s], kc, x0 + dx, y0 + dy, b0);
-                tma_load_2d(st + S::A_BYTES, &tmB_hi, &full[s], kb * BK, n0);
-                if (NSPLIT == 3) {
-                    tma_load_4d(st + S::A_BYTES + S::B_BYTES, &tmA_lo, &full[s], kc, x0 + dx, y0 + dy, b0);
-                    tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmB_lo, &full[s], kb * BK, n0);
+            int it = 0;                                                  // global k-block counter (ring position)
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int mt = tile / ntn, n0 = (tile % ntn) * BN;
+                int x0 = 0, y0 = 0, b0 = 0;                              // tile origin in (x, y, b) of the NHWC plane
+                if (p.plain) x0 = mt * BM;
+                else if (p.bb > 1 || p.bh * p.bw == p.H * p.W) b0 = mt * p.bb;
+                else { int tiles_per_img = (p.H * p.W) / BM; b0 = mt / tiles_per_img; y0 = (mt % tiles_per_img) * p.bh; }
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * S::STAGE_BYTES;
+                    mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                    const int tap = kb / p.kb_per_tap, kc = (kb - tap * p.kb_per_tap) * BK;
+                    const int dy = p.ksize == 3 ? tap / 3 - 1 : 0, dx = p.ksize == 3 ? tap % 3 - 1 : 0;
+                    tma_load_4d(st, &tmA_hi, &full[s], kc, x0 + dx, y0 + dy, b0);
+                    tma_load_2d(st + S::A_BYTES, &tmB_hi, &full[s], kb * BK, n0);
+                    if (NSPLIT == 3) {
+                        tma_load_4d(st + S::A_BYTES + S::B_BYTES, &tmA_lo, &full[s], kc, x0 + dx, y0 + dy, b0);
+                        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmB_lo, &full[s], kb * BK, n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BN);
-            for (int kb = 0; kb < nkb; kb++) {
-                const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full[s], ph);
+            int it = 0, lt = 0;                                          // ring position, local tile counter
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, lt++) {
+                const int buf = lt & 1;
+                mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES), b_hi = a_hi + S::A_BYTES;
-                const uint32_t a_lo = b_hi + S::B_BYTES, b_lo = a_lo + S::A_BYTES;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES), b_hi = a_hi + S::A_BYTES;
+                    const uint32_t a_lo = b_hi + S::B_BYTES, b_lo = a_lo + S::A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / 16; k++) {
-                    const uint64_t da = umma_desc_sw128(a_hi + k * 32), db = umma_desc_sw128(b_hi + k * 32);
-                    umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
-                    if (NSPLIT == 3) {
-                        umma_bf16(tmem_base, umma_desc_sw128(a_lo + k * 32), db, idesc, 1);
-                        umma_bf16(tmem_base, da, umma_desc_sw128(b_lo + k * 32), idesc, 1);
+                    for (int k = 0; k < BK / 16; k++) {
+                        const uint64_t da = umma_desc_sw128(a_hi + k * 32), db = umma_desc_sw128(b_hi + k * 32);
+                        umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+                        if (NSPLIT == 3) {
+                            umma_bf16(tmem_d, umma_desc_sw128(a_lo + k * 32), db, idesc, 1);
+                            umma_bf16(tmem_d, da, umma_desc_sw128(b_lo + k * 32), idesc, 1);
+                        }
                     }
+                    umma_commit(&empty[s]);                // frees the stage once the MMAs above have read it
                 }
-                umma_commit(&empty[s]);                // frees the stage once the MMAs above have read it
+                umma_commit(&tmem_full[buf]);              // accumulator complete
             }
-            umma_commit(tmem_full);                    // accumulator complete
         }
     } else {
         // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
         const int q = warp & 3;
-        const int row = q * 32 + lane, m = mt * BM + row;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const bool mvalid = m < p.M;
-        const int bidx = mvalid ? m / p.rows_per_batch : 0;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, lt++) {
+            const int buf = lt & 1;
+            const int mt = tile / ntn, n0 = (tile % ntn) * BN;
+            const int m = mt * BM + q * 32 + lane;
+            const bool mvalid = m < p.M;
+            const int bidx = mvalid ? m / p.rows_per_batch : 0;
+            mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; c++) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-            const int nb = n0 + c * 32;
-            if (!mvalid || nb >= p.N) continue;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                float t = __uint_as_float(r[j]);
-                const int n = nb + j;
-                if (n < p.N) {
-                    if (p.bias) t += __ldg(p.bias + n);
-                    if (p.rowvec) t += __ldg(p.rowvec + (size_t)bidx * p.rowvec_ld + n);
-                }
-                v[j] = t;
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
+                const int nb = n0 + c * 32;
+                if (mvalid && nb < p.N) epilogue_chunk(p, r, m, bidx, nb);
             }
-            if (p.act == ACT_GEGLU) {
-                // (value, gate) column pairs -> 16 outputs at columns nb/2 ..
-                const int no = nb >> 1;
-                float o[16];
-#pragma unroll
-                for (int j = 0; j < 16; j++) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
-                const int nvalid = min(16, (p.N - nb) >> 1);
-                if (p.out) {
-                    float* dst = p.out + (size_t)m * p.out_ld + no;
-                    for (int j = 0; j < nvalid; j++) dst[j] = o[j] + (p.res ? p.res[(size_t)m * p.res_ld + no + j] : 0.f);
-                } else {
-                    __nv_bfloat16* dh = p.out_hi + (size_t)m * p.out_bf_ld + no;
-                    __nv_bfloat16* dl = p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + no : nullptr;
-                    for (int j = 0; j < nvalid; j++) {
-                        __nv_bfloat16 h = __float2bfloat16_rn(o[j]);
-                        dh[j] = h;
-                        if (dl) dl[j] = __float2bfloat16_rn(o[j] - __bfloat162float(h));
-                    }
-                }
-            } else {
-                const int nvalid = min(32, p.N - nb);
-#pragma unroll
-                for (int j = 0; j < 32; j++) if (p.act == ACT_SILU) v[j] = silu_f(v[j]);
-                if (p.res) {
-                    const float* rs = p.res + (size_t)m * p.res_ld + nb;
-                    if (nvalid == 32 && ((p.res_ld & 3) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) { float4 t = *reinterpret_cast<const float4*>(rs + j); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
-                    } else {
-                        for (int j = 0; j < nvalid; j++) v[j] += rs[j];
-                    }
-                }
-                if (p.out) {
-                    float* dst = p.out + (size_t)m * p.out_ld + nb;
-                    if (nvalid == 32 && ((p.out_ld & 3) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-                        for (int j = 0; j < nvalid; j++) dst[j] = v[j];
-                    }
-                } else {
-                    __nv_bfloat16* dh = p.out_hi + (size_t)m * p.out_bf_ld + nb;
-                    __nv_bfloat16* dl = p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + nb : nullptr;
-                    for (int j = 0; j < nvalid; j++) {
-                        __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
-                        dh[j] = h;
-                        if (dl) dl[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
-                    }
-                }
-            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS) : "memory");
     }
 }
 
@@ -329,8 +387,9 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
         RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured[dev & 15] = true;
     }
-    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
-    kern<<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    const int ntiles = ((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM);
+    const int sms = rdm_num_sms(dev);
+    kern<<<ntiles < sms ? ntiles : sms, TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, p);
     RDM_COUNT_LAUNCH();
     RDM_CHECK_CUDA(cudaGetLastError());
     return RDM_OK;
@@ -373,18 +432,30 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     p.res = e.res; p.res_ld = e.res_ld; p.act = e.act; p.out = e.out; p.out_ld = e.out_ld;
     p.out_hi = out_hi; p.out_lo = out_lo; p.out_bf_ld = out_bf_ld;
     RDM_REQUIRE((p.out != nullptr) != (p.out_hi != nullptr), RDM_ERR_ARG, "gemm_tc: exactly one of fp32 / bf16 outputs");
-    // tile width: fill the machine
-    const int mtiles = (M + BM - 1) / BM;
-    int BN = 128;
-    if (w.N <= 32) BN = 32; else if (w.N <= 64 || mtiles * ((w.N + 127) / 128) < 120) BN = 64;
+    // tile width: the widest tile that still gives every SM work (persistent grid; U-Net widths are multiples of 192)
+    const int mtiles = (M + BM - 1) / BM, sms = 148;
+    static const int forced = getenv("RDM_TC_BN") ? atoi(getenv("RDM_TC_BN")) : 0;
+    int BN = 32;
+    const int cand[4] = {192, 128, 64, 32};
+    double best = -1.0;
+    for (int c : cand) {
+        if (c > 32 && w.N < c / 2) continue;
+        const int nt = (w.N + c - 1) / c, tiles = mtiles * nt, waves = (tiles + sms - 1) / sms;
+        // useful fraction of issued MMA columns x machine occupancy; slight preference for wider tiles (less A re-reading)
+        double eff = ((double)w.N / (nt * c)) * ((double)tiles / (waves * sms)) * (1.0 + 0.0005 * c);
+        if (eff > best) { best = eff; BN = c; }
+    }
+    if (forced == 192 || forced == 128 || forced == 64 || forced == 32) BN = forced;
     RDM_TRY(make_map_2d(&tb_hi, w.hi, w.K, w.N, w.ld, BN));
     if (nsplit == 3) RDM_TRY(make_map_2d(&tb_lo, w.lo, w.K, w.N, w.ld, BN)); else tb_lo = tb_hi;
     if (nsplit == 3) {
+        if (BN == 192) return launch_tc<192, 3, 2>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
         if (BN == 128) return launch_tc<128, 3, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
         if (BN == 64) return launch_tc<64, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        return launch_tc<32, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        return launch_tc<32, 3, 5>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
     }
+    if (BN == 192) return launch_tc<192, 1, 5>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
     if (BN == 128) return launch_tc<128, 1, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-    if (BN == 64) return launch_tc<64, 1, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-    return launch_tc<32, 1, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+    if (BN == 64) return launch_tc<64, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+    return launch_tc<32, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
 }
