@@ -1,0 +1,159 @@
+"""`rdm.data.retrieval_dataset.dsetbuilder.DatasetBuilder` -- the retrieval-database side of the reference
+(`rdm/data/retrieval_dataset/dsetbuilder.py:49-655`) reduced to what sampling uses:
+
+* `load_embeddings` (`:199-236`): `.npz` file or directory of parts with keys `embedding`, `img_id`, `patch_coords`;
+* `train_searcher` (`:534-619`): the ScaNN build/load is replaced by uploading the rows to HBM once
+  (`rdm_b200.knn.B200Searcher`: exact cosine top-k, per-row inverse norms computed on the device) -- no k-means,
+  no quantiser training, nothing to serialise; row-sharded across ranks when torch.distributed is initialised and
+  `shard=True`;
+* `search_k_nearest` (`:478-518`) with the same result dictionary;
+* `embed` (`:461-473`) through the retriever (CLIP).
+Database *construction* (`build_data_pool`, patch datasets, visualisation) is out of scope and raises.
+"""
+import datetime
+import os
+import time
+from glob import glob
+
+import numpy as np
+import torch
+
+from ldm.util import instantiate_from_config
+from rdm_b200.knn import B200Searcher, ShardedSearcher
+
+
+class DatasetBuilder(object):
+    def __init__(self, retriever_config, data=None, metric='dot_product', patch_size=128, n_patches=None, batch_size=10,
+                 patch_sampling='random', k=10, img_size=None, num_workers=None, max_pool_size=None, visualize=False, save=True,
+                 saved_embeddings=None, trainset_size_partitioning=None, chunk_size=None, gpu=True, load_patch_dataset=True,
+                 patch_dset_kwargs=None, searcher_savepath=None, timestamp_searcher_savepath=False, savepath_postfix=None,
+                 save_searcher=False, shard=False):
+        assert metric == 'dot_product', "the reference configs search by dot product on normalised vectors"
+        self.retriever_config = retriever_config
+        self.retriever_name = retriever_config["target"].split('.')[-1] if retriever_config else "none"
+        self.visualize, self.distance_metric, self.k, self.chunk_size = visualize, metric, k, chunk_size
+        self.timestamp = datetime.datetime.now().strftime("%Y-%m-%dT%H-%M-%S")
+        self.load_patch_dataset = bool(load_patch_dataset)
+        self.max_pool_size, self.patch_size, self.save_searcher = max_pool_size, patch_size, save_searcher
+        self.dset = self.patch_dset = None
+        if self.load_patch_dataset:
+            print(f'WARNING: {self.__class__.__name__} (B200 build) does not load image patch datasets; neighbour images are unavailable')
+            self.load_patch_dataset = False
+        self.retriever_bs = batch_size
+        self.gpu = gpu and torch.cuda.is_available()
+        self._retriever = None                        # CLIP is instantiated lazily: sampling from DB rows never needs it
+        self.data_pool = {'embedding': [], 'img_id': [], 'patch_coords': []}
+        self.saved_embeddings = saved_embeddings
+        self.shard = shard
+        if self.saved_embeddings:
+            self.load_embeddings()
+        self.searcher = None
+        self.searcher_savedir = searcher_savepath
+
+    # ---- retriever (CLIP) ------------------------------------------------------------------------------------
+    @property
+    def retriever(self):
+        if self._retriever is None and self.retriever_config:
+            self._retriever = self.load_retriever(gpu=self.gpu)
+        return self._retriever
+
+    def load_retriever(self, gpu=True, eval_mode=True):
+        model = instantiate_from_config(self.retriever_config)
+        if gpu and hasattr(model, "cuda"):
+            model.cuda()
+        if eval_mode and hasattr(model, "eval"):
+            model.eval()
+        return model
+
+    @torch.no_grad()
+    def embed(self, batch, is_caption=False):
+        if not is_caption:
+            if isinstance(batch, np.ndarray):
+                batch = torch.from_numpy(batch)
+            if batch.ndim == 5:
+                batch = batch.reshape(-1, *batch.shape[2:])
+            if batch.shape[-1] in (1, 3):
+                batch = batch.permute(0, 3, 1, 2)
+            batch = batch.contiguous().float()
+            bs = batch.shape[0]
+        else:
+            bs = len(batch)
+        return self.retriever(batch).reshape(bs, -1)
+
+    # ---- database ------------------------------------------------------------------------------------------------
+    def load_single_file(self, saved_embeddings):
+        assert saved_embeddings.endswith('.npz'), 'saved embeddings not stored as a .npz file'
+        compressed = np.load(saved_embeddings)
+        self.data_pool = {key: compressed[key] for key in compressed.files}
+        n = self.data_pool['embedding'].shape[0]
+        if self.max_pool_size is None or n >= self.max_pool_size:
+            self.max_pool_size = n
+        print('Finished loading of patch embeddings.')
+
+    def load_embeddings(self):
+        if len(self.data_pool['embedding']) > 0:
+            return
+        print(f'Load saved patch embedding from "{self.saved_embeddings}"')
+        if os.path.isfile(self.saved_embeddings):
+            self.load_single_file(self.saved_embeddings)
+        elif os.path.isdir(self.saved_embeddings):
+            files = sorted(glob(os.path.join(self.saved_embeddings, '*.npz')))
+            if len(files) == 1:
+                self.load_single_file(files[0])
+            else:
+                parts = [np.load(f) for f in files]
+                keys = parts[0].files
+                self.data_pool = {key: np.concatenate([p[key] for p in parts], axis=0) for key in keys}
+        else:
+            raise ValueError(f'Embeddings string "{self.saved_embeddings}" nor directory neither file --> check this.')
+        print(f'Finished loading of retrieval database of length {self.data_pool["embedding"].shape[0]}.')
+
+    # ---- searcher ------------------------------------------------------------------------------------------------
+    def train_searcher(self, k=None, metric=None, device=None, **ignored_scann_options):
+        """Uploads the RAW rows to HBM (fp16 stays fp16) and computes the inverse norms there.  Replaces
+        `scann.scann_ops_pybind.builder(emb / ||emb||, k, metric)...build()` (dsetbuilder.py:574-612)."""
+        if self.searcher is not None:
+            print('Using trained searcher')
+            return
+        emb = self.data_pool['embedding']
+        assert len(emb) > 0, "no embeddings loaded"
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        n, base = emb.shape[0], 0
+        dist_on = self.shard and torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        if dist_on:
+            r, w = torch.distributed.get_rank(), torch.distributed.get_world_size()
+            base, end = (n * r) // w, (n * (r + 1)) // w
+            emb = emb[base:end]
+        local = B200Searcher(emb, device=device, idx_base=base)
+        self.searcher = ShardedSearcher(local) if dist_on else local
+        print(f'Finish training searcher: {emb.shape[0]:,} rows resident on {device} (exact cosine top-k)')
+
+    def search_k_nearest(self, queries, k=None, is_caption=False, visualize=None, query_embedded=False):
+        assert self.searcher is not None, 'Cannot search with uninitialized searcher'
+        k = self.k if k is None else k
+        if not query_embedded:
+            q_emb_ = self.embed(queries, is_caption=is_caption)
+            q_emb_ = q_emb_.detach().cpu().numpy() if isinstance(q_emb_, torch.Tensor) else q_emb_
+        else:
+            q_emb_ = queries.detach().cpu().numpy() if isinstance(queries, torch.Tensor) else np.asarray(queries)
+        query_embeddings = q_emb_ / np.linalg.norm(q_emb_, axis=1)[:, np.newaxis]
+        start = time.time()
+        nns, distances = self.searcher.search_batched(query_embeddings, final_num_neighbors=k)
+        end = time.time()
+        out = {'embeddings': self.data_pool['embedding'][nns], 'queries': queries, 'exec_time': end - start, 'nns': nns,
+               'distances': distances, 'q_embeddings': q_emb_}
+        for key_out, key in (('img_ids', 'img_id'), ('patch_coords', 'patch_coords')):
+            if key in self.data_pool and len(self.data_pool[key]) > 0:
+                out[key_out] = self.data_pool[key][nns]
+        if visualize if visualize is not None else self.visualize:
+            raise NotImplementedError("neighbour image patches need the patch dataset, which is outside the sampling hot path")
+        return out
+
+    def get_nn_patches(self, batched_nns):
+        raise NotImplementedError("neighbour image patches need the patch dataset, which is outside the sampling hot path")
+
+    def build_data_pool(self, *a, **k):
+        raise NotImplementedError("database construction is outside the sampling hot path (SURVEY.md section 2)")
+
+    save_datapool = build_data_pool

@@ -30,15 +30,15 @@ class DDIMSampler(object):
         alphas_cumprod = self.model.alphas_cumprod
         assert alphas_cumprod.shape[0] == self.ddpm_num_timesteps, 'alphas have to be defined for each timestep'
         to_torch = lambda x: x.clone().detach().to(torch.float32).to(self.model.device)
-        ac = alphas_cumprod.detach().cpu()
+        ac = alphas_cumprod.detach().cpu().to(torch.float32)
         self.register_buffer('betas', to_torch(self.model.betas))
         self.register_buffer('alphas_cumprod', to_torch(alphas_cumprod))
         self.register_buffer('alphas_cumprod_prev', to_torch(self.model.alphas_cumprod_prev))
-        self.register_buffer('sqrt_alphas_cumprod', to_torch(np.sqrt(ac)))
-        self.register_buffer('sqrt_one_minus_alphas_cumprod', to_torch(np.sqrt(1. - ac)))
-        self.register_buffer('log_one_minus_alphas_cumprod', to_torch(np.log(1. - ac)))
-        self.register_buffer('sqrt_recip_alphas_cumprod', to_torch(np.sqrt(1. / ac)))
-        self.register_buffer('sqrt_recipm1_alphas_cumprod', to_torch(np.sqrt(1. / ac - 1)))
+        self.register_buffer('sqrt_alphas_cumprod', to_torch(ac.sqrt()))
+        self.register_buffer('sqrt_one_minus_alphas_cumprod', to_torch((1. - ac).sqrt()))
+        self.register_buffer('log_one_minus_alphas_cumprod', to_torch((1. - ac).log()))
+        self.register_buffer('sqrt_recip_alphas_cumprod', to_torch((1. / ac).sqrt()))
+        self.register_buffer('sqrt_recipm1_alphas_cumprod', to_torch((1. / ac - 1).sqrt()))
         t = _tables.make_ddim_tables(ac, ddim_num_steps, ddim_eta, device=self.model.device)
         self.ddim_timesteps = t["ddim_timesteps"]
         self.register_buffer('ddim_sigmas', t["sigmas"])

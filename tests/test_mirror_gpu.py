@@ -1,0 +1,91 @@
+"""GPU: the reference-facing API end to end -- YAML-style config -> MinimalRETRODiffusion -> sample_from_rdata /
+sample_with_query -> DDIMSampler -> librdm_b200, checked against the oracle pipeline on identical inputs and RNG."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddim as oddim
+from oracle import knn as oknn
+from oracle import unet as ounet
+from test_mirror_host import TINY_CFG
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(tmp_path, cuda, seed=4):
+    import copy
+    import rdm  # noqa: F401
+    from ldm.util import instantiate_from_config
+    from omegaconf import OmegaConf
+    rng = np.random.default_rng(seed)
+    db = (rng.standard_normal((30_000, 512)) * rng.uniform(0.5, 8, (30_000, 1))).astype(np.float16)
+    np.savez(tmp_path / "db.npz", embedding=db, img_id=np.arange(30_000), patch_coords=np.zeros((30_000, 4), np.int32))
+    cfg = copy.deepcopy(TINY_CFG)
+    cfg["params"]["retrieval_cfg"]["params"]["saved_embeddings"] = str(tmp_path / "db.npz")
+    model = instantiate_from_config(OmegaConf.create(cfg))
+    ref = ounet.randomize_(ounet.UNetModel(**ounet.TINY_UNET), seed).eval()
+    ema = ounet.randomize_(ounet.UNetModel(**ounet.TINY_UNET), seed + 1).eval()          # sampling must use THESE (ddpm.py:977)
+    ck = {"model.diffusion_model." + k: v for k, v in ref.state_dict().items()}
+    ck.update({"model_ema." + ("diffusion_model." + k).replace(".", ""): v for k, v in ema.state_dict().items()})
+    missing, unexpected = model.load_state_dict(ck, strict=False)
+    assert not unexpected and set(missing) <= {"unconditional_guidance_vex", "model_ema.decay", "model_ema.num_updates"}
+    model = model.eval().to(cuda)
+    return model, db, ema
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def test_sample_from_rdata_matches_the_oracle_pipeline(tmp_path, cuda):
+    model, db, ema = _setup(tmp_path, cuda)
+    qids = np.array([5, 777, 12345])
+    x_T = torch.randn(3, 4, 16, 16, generator=torch.Generator().manual_seed(0))
+    logs = model.sample_from_rdata(3, qids=qids, k_nn=4, use_weights=False, memsize=100, unconditional_guidance_scale=2.0, ddim_steps=10,
+                                   ddim=True, unconditional_retro_guidance_label=0., x_T=x_T.to(cuda))             # scripts/rdm_sample.py:241-252
+    # oracle: exact kNN on normalised DB-row queries, raw neighbour rows as context, zeros uncond, EMA weights
+    qh = oknn.normalize_queries(db[qids].astype(np.float32))
+    nns, _ = oknn.search(db, qh, 4)
+    assert np.array_equal(logs["nns"].cpu().numpy(), nns) and list(nns[:, 0]) == list(qids)
+    cond = torch.from_numpy(db[nns].astype(np.float32))
+    want = oddim.ddim_sample(ema, x_T, cond, torch.zeros_like(cond), S=10, scale=2.0)
+    assert logs["samples_with_sampled_nns"].shape == (3, 4, 16, 16)
+    assert rel_l2(logs["samples_with_sampled_nns"], want) < 1e-3
+
+
+def test_sample_with_query_embedded_prepends_the_query(tmp_path, cuda):
+    model, db, ema = _setup(tmp_path, cuda, seed=6)
+    g = torch.Generator().manual_seed(1)
+    q = torch.randn(2, 512, generator=g) * 4
+    x_T = torch.randn(2, 4, 16, 16, generator=g)
+    logs = model.sample_with_query(query=q, query_embedded=True, k_nn=4, visualize_nns=False, use_weights=False, unconditional_guidance_scale=3.0,
+                                   ddim_steps=5, ddim=True, unconditional_retro_guidance_label=0., omit_query=False, x_T=x_T.to(cuda))   # rdm_sample.py:287-299
+    qh = oknn.normalize_queries(q.numpy())
+    nns, _ = oknn.search(db, qh, 4)
+    cond = torch.cat([q[:, None], torch.from_numpy(db[nns].astype(np.float32))[:, :3]], dim=1)                         # ddpm.py:775
+    want = oddim.ddim_sample(ema, x_T, cond, torch.zeros_like(cond), S=5, scale=3.0)
+    assert rel_l2(logs["query_samples"], want) < 1e-3
+
+
+def test_ddim_sampler_generic_path_with_callbacks_and_intermediates(tmp_path, cuda):
+    from rdm.models.diffusion.ddim import DDIMSampler
+    model, db, ema = _setup(tmp_path, cuda, seed=8)
+    g = torch.Generator().manual_seed(2)
+    cond = torch.randn(2, 4, 512, generator=g)
+    x_T = torch.randn(2, 4, 16, 16, generator=g)
+    seen = []
+    with model.ema_scope():
+        s1, inter1 = DDIMSampler(model).sample(S=10, batch_size=2, shape=(4, 16, 16), conditioning=cond.to(cuda), x_T=x_T.to(cuda), verbose=False,
+                                               unconditional_guidance_scale=2.0, unconditional_conditioning=torch.zeros_like(cond).to(cuda), log_every_t=5)
+        s2, inter2 = DDIMSampler(model).sample(S=10, batch_size=2, shape=(4, 16, 16), conditioning=cond.to(cuda), x_T=x_T.to(cuda), verbose=False,
+                                               unconditional_guidance_scale=2.0, unconditional_conditioning=torch.zeros_like(cond).to(cuda), log_every_t=5,
+                                               callback=lambda i: seen.append(i))
+    want, traj = oddim.ddim_sample(ema, x_T, cond, torch.zeros_like(cond), S=10, scale=2.0, return_all=True)
+    assert seen == list(range(10))
+    assert rel_l2(s1, want) < 1e-3 and rel_l2(s2, want) < 1e-3
+    # intermediates logged at index % 5 == 0 or index == 9  ->  loop positions i = 0, 4, 9 (ddim.py:207-213), after the initial x_T entry
+    assert len(inter1["x_inter"]) == 4 and len(inter2["x_inter"]) == 4
+    for k, i in enumerate((0, 4, 9)):
+        assert rel_l2(inter1["x_inter"][k + 1], traj[i][0]) < 1e-3 and rel_l2(inter1["pred_x0"][k + 1], traj[i][1]) < 1e-3
+        assert rel_l2(inter2["x_inter"][k + 1], traj[i][0]) < 1e-3
