@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from ldm.util import instantiate_from_config
-from rdm_b200.knn import B200Searcher, ShardedSearcher
+from rdm_b200.knn import B200Searcher, ShardedSearcher, shard_range
 
 
 class DatasetBuilder(object):
@@ -123,7 +123,7 @@ class DatasetBuilder(object):
         dist_on = self.shard and torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
         if dist_on:
             r, w = torch.distributed.get_rank(), torch.distributed.get_world_size()
-            base, end = (n * r) // w, (n * (r + 1)) // w
+            base, end = shard_range(n, r, w)
             emb = emb[base:end]
         local = B200Searcher(emb, device=device, idx_base=base)
         self.searcher = ShardedSearcher(local) if dist_on else local

@@ -109,26 +109,32 @@ def merge_device(idx_parts, score_parts, k):
     return idx, dist, sc
 
 
+def shard_range(n, rank, world):
+    """Rows [lo, hi) owned by `rank` of `world` for an n-row database (contiguous, balanced; DatasetBuilder.train_searcher)."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
 class ShardedSearcher:
     """Row-sharded database: rank r owns rows [base_r, base_r + n_r).  Every rank passes the SAME queries;
     one all_gather of the per-shard exact (index, fp64 score) lists, then an on-device merge by
     (score desc, index asc) -- identical results on every rank, independent of the number of shards
     (SURVEY.md section 8e).  Works with any initialised torch.distributed backend (NCCL on the box, gloo in CI)."""
 
-    def __init__(self, local: B200Searcher, group=None):
+    def __init__(self, local, group=None, merge_fn=None):
         import torch.distributed as dist
         self.local, self.group, self.dist = local, group, dist
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.merge = merge_fn or merge_device          # injectable so the exchange logic is testable on CPU/gloo
 
     def search_device(self, q_hat, k):
         idx, _, sc = self.local.search_device(q_hat, k, return_scores=True)
         if self.world == 1:
-            return merge_device(idx[None], sc[None], k)[:2]
+            return self.merge(idx[None], sc[None], k)[:2]
         idx_all = [torch.empty_like(idx) for _ in range(self.world)]
         sc_all = [torch.empty_like(sc) for _ in range(self.world)]
         self.dist.all_gather(idx_all, idx, group=self.group)
         self.dist.all_gather(sc_all, sc, group=self.group)
-        return merge_device(torch.stack(idx_all), torch.stack(sc_all), k)[:2]
+        return self.merge(torch.stack(idx_all), torch.stack(sc_all), k)[:2]
 
     def gather_device(self, idx):
         out = self.local.gather_device(idx)          # rows outside the local shard come back as zeros

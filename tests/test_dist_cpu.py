@@ -1,0 +1,86 @@
+"""CPU, world_size 2, gloo: the row-sharded database exchange -- shard ranges, idx_base, one all_gather
+of (idx, fp64 score), merge by (score desc, idx asc).  The local scan is played by the oracle so no GPU is needed; the
+CUDA kernels behind the same interfaces are covered by tests/test_knn_gpu.py::test_shards_merge_to_the_unsharded_result."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.multiprocessing as mp
+
+from conftest import PKG, ROOT
+
+
+class OracleLocalSearcher:
+    """CPU stand-in with the B200Searcher device-level interface."""
+
+    def __init__(self, db, idx_base):
+        from oracle import knn as oknn
+        self.db, self.base, self.oknn, self.device, self.d = db, idx_base, oknn, torch.device("cpu"), db.shape[1]
+        self.inv = oknn.inv_norms(db)
+
+    def search_device(self, q_hat, k, return_scores=False):
+        i, d, s = self.oknn.search(self.db, q_hat.numpy(), k, inv=self.inv, idx_base=self.base, return_scores=True)
+        out = (torch.from_numpy(i), torch.from_numpy(d), torch.from_numpy(s))
+        return out if return_scores else out[:2]
+
+    def gather_device(self, idx):
+        rows = idx.numpy() - self.base
+        ok = (rows >= 0) & (rows < self.db.shape[0])
+        out = np.zeros(idx.shape + (self.d,), np.float32)
+        out[ok] = self.db[rows[ok]].astype(np.float32)
+        return torch.from_numpy(out)
+
+
+def cpu_merge(idx_parts, score_parts, k):
+    from oracle import knn as oknn
+    parts = [(idx_parts[p].numpy(), score_parts[p].numpy()) for p in range(idx_parts.shape[0])]
+    i, s = oknn.merge_shards(parts, k)
+    return torch.from_numpy(i), torch.from_numpy(s.astype(np.float32)), torch.from_numpy(s)
+
+
+def _worker(rank, world, port, q):
+    import sys
+    sys.path[:0] = [ROOT, PKG]
+    import torch.distributed as dist
+    from oracle import knn as oknn
+    from rdm_b200.knn import ShardedSearcher, shard_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)                              # same DB / queries on every rank
+    db = rng.standard_normal((5001, 512)).astype(np.float16)
+    db[4000] = db[3]                                            # a duplicate that lives in the OTHER shard: tie -> lowest global index
+    qh = oknn.normalize_queries(np.concatenate([db[[3, 4990]].astype(np.float32), rng.standard_normal((3, 512)).astype(np.float32)]))
+    lo, hi = shard_range(len(db), rank, world)
+    s = ShardedSearcher(OracleLocalSearcher(db[lo:hi], lo), merge_fn=cpu_merge)
+    idx, dist_ = s.search_device(torch.from_numpy(qh), 6)
+    ctx = s.gather_device(idx)
+    full_i, full_d = oknn.search(db, qh, 6)
+    ok = np.array_equal(idx.numpy(), full_i) and np.array_equal(dist_.numpy(), full_d) and np.array_equal(ctx.numpy(), db[full_i].astype(np.float32))
+    ok = ok and list(full_i[0, :2]) == [3, 4000]
+    q.put((rank, bool(ok), (lo, hi)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_search_world2_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [True, True]
+    assert res[0][2] == (0, 2500) and res[1][2] == (2500, 5001)
+
+
+def test_shard_ranges_cover_the_database():
+    from rdm_b200.knn import shard_range
+    for n in (1, 7, 1_281_167, 20_927_907):
+        for w in (1, 2, 4, 8):
+            r = [shard_range(n, i, w) for i in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
