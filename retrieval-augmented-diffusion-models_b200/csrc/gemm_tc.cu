@@ -203,13 +203,22 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
     __syncwarp();
     const int lpr = wout >> 2;                     // lanes per row: 8 (128 B) or 4 (64 B)
     const int rstep = 32 / lpr, r0 = lane / lpr, cg = (lane % lpr) * 4;
-    for (int rr = r0; rr < 32; rr += rstep) {
-        const int mo = m_warp0 + rr;
-        if (mo >= p.M) break;
-        float4 t = *reinterpret_cast<const float4*>(stage + rr * EPI_LD + cg);
-        if (p.res) { float4 q = *reinterpret_cast<const float4*>(p.res + (size_t)mo * p.res_ld + no + cg); t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
-        if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)mo * p.out_ld + no + cg) = t;
-        else store_bf16x4(p.out_hi + (size_t)mo * p.out_bf_ld + no + cg, p.out_lo ? p.out_lo + (size_t)mo * p.out_bf_ld + no + cg : nullptr, t.x, t.y, t.z, t.w);
+    float4 t[8], q[8];
+#pragma unroll
+    for (int it = 0; it < 8; it++) {               // all residual loads in flight before the first store
+        const int rr = r0 + it * rstep, mo = m_warp0 + rr;
+        const bool ok = rr < 32 && mo < p.M;
+        t[it] = ok ? *reinterpret_cast<const float4*>(stage + rr * EPI_LD + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+        q[it] = (ok && p.res) ? __ldcs(reinterpret_cast<const float4*>(p.res + (size_t)mo * p.res_ld + no + cg)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int rr = r0 + it * rstep, mo = m_warp0 + rr;
+        if (rr < 32 && mo < p.M) {
+            float4 o = make_float4(t[it].x + q[it].x, t[it].y + q[it].y, t[it].z + q[it].z, t[it].w + q[it].w);
+            if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)mo * p.out_ld + no + cg) = o;
+            else store_bf16x4(p.out_hi + (size_t)mo * p.out_bf_ld + no + cg, p.out_lo ? p.out_lo + (size_t)mo * p.out_bf_ld + no + cg : nullptr, o.x, o.y, o.z, o.w);
+        }
     }
 }
 
@@ -425,18 +434,18 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     p.res = e.res; p.res_ld = e.res_ld; p.act = e.act; p.out = e.out; p.out_ld = e.out_ld;
     p.out_hi = out_hi; p.out_lo = out_lo; p.out_bf_ld = out_bf_ld;
     RDM_REQUIRE((p.out != nullptr) != (p.out_hi != nullptr), RDM_ERR_ARG, "gemm_tc: exactly one of fp32 / bf16 outputs");
-    // tile width: the widest tile that still gives every SM work (persistent grid; U-Net widths are multiples of 192)
+    // tile width.  The mainloop is operand-feed bound (TMA/L2 -> smem), so the time of one tile grows like (128 + BN) per k-block:
+    // the A tile (128 rows) is re-loaded for every N tile.  Persistent grid: cost = ceil(tiles / SMs) * (128 + BN), ties -> wider.
     const int mtiles = (M + BM - 1) / BM, sms = 148;
     static const int forced = getenv("RDM_TC_BN") ? atoi(getenv("RDM_TC_BN")) : 0;
     int BN = 32;
     const int cand[4] = {192, 128, 64, 32};
-    double best = -1.0;
+    long best = -1;
     for (int c : cand) {
-        if (c > 32 && w.N < c / 2) continue;
-        const int nt = (w.N + c - 1) / c, tiles = mtiles * nt, waves = (tiles + sms - 1) / sms;
-        // useful fraction of issued MMA columns x machine occupancy; slight preference for wider tiles (less A re-reading)
-        double eff = ((double)w.N / (nt * c)) * ((double)tiles / (waves * sms)) * (1.0 + 0.0005 * c);
-        if (eff > best) { best = eff; BN = c; }
+        if (c > 32 && w.N <= c / 2) continue;
+        const int nt = (w.N + c - 1) / c;
+        const long tiles = (long)mtiles * nt, waves = (tiles + sms - 1) / sms, cost = waves * (128 + c);
+        if (best < 0 || cost < best) { best = cost; BN = c; }
     }
     if (forced == 192 || forced == 128 || forced == 64 || forced == 32) BN = forced;
     RDM_TRY(make_map_2d(&tb_hi, w.hi, w.K, w.N, w.ld, BN));

@@ -61,34 +61,34 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B
     if ((dim & 1) && j == 0) out[(size_t)b * dim + dim - 1] = 0.f;
 }
 
-// grid (row_chunks, B); each CTA streams whole rows (coalesced) and accumulates per-channel partial sums.
-// blockDim.x = 256; channels are covered by float4 lanes: thread handles float4 column v = tid % V, row slot tid / V.
+// grid (row_chunks, B).  Thread t owns the float4 column v = t % V for the whole kernel and walks rows slot, slot+nslots, ...
+// (consecutive threads -> consecutive 16-byte pieces of a row: coalesced), keeping its 4 channel sums in registers; one
+// shared-memory atomic per touched group per thread at the end, then fp64 atomics to the global accumulators.
 __global__ void gn_stats_kernel(const float* __restrict__ x, int ld, int C, int HW, int groups, int rows_per_cta, double* __restrict__ sums) {
     extern __shared__ float s_acc[];           // [2][groups]
     const int b = blockIdx.y, V = C / 4, cpg = C / groups;
     for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
+    const int nslots = blockDim.x / V;          // blockDim.x is a multiple of V or smaller threads idle
+    const int v = threadIdx.x % V, slot = threadIdx.x / V;
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
-    const long long total = (long long)(r1 - r0) * V;
-    const float* base = x + ((long long)b * HW + r0) * ld;
-    // consecutive threads -> consecutive float4 columns of one row; a thread's column index changes per step, so
-    // accumulate per element into shared memory only after a per-thread run over the same group is exhausted.
-    int cur_g = -1; float s = 0.f, ss = 0.f;
-    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-        int v = (int)(i % V); long long r = i / V;
-        float4 q = *reinterpret_cast<const float4*>(base + r * ld + v * 4);
-        float e[4] = {q.x, q.y, q.z, q.w};
+    if (slot < nslots) {
+        const float* base = x + ((long long)b * HW) * ld + v * 4;
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int r = r0 + slot; r < r1; r += nslots) {
+            float4 q = *reinterpret_cast<const float4*>(base + (long long)r * ld);
+            s[0] += q.x; ss[0] += q.x * q.x; s[1] += q.y; ss[1] += q.y * q.y;
+            s[2] += q.z; ss[2] += q.z * q.z; s[3] += q.w; ss[3] += q.w * q.w;
+        }
+        int g = (v * 4) / cpg; float gs = 0.f, gss = 0.f;
 #pragma unroll
         for (int t = 0; t < 4; t++) {
-            int g = (v * 4 + t) / cpg;
-            if (g != cur_g) {
-                if (cur_g >= 0) { atomicAdd(&s_acc[cur_g], s); atomicAdd(&s_acc[groups + cur_g], ss); }
-                cur_g = g; s = 0.f; ss = 0.f;
-            }
-            s += e[t]; ss += e[t] * e[t];
+            int gt = (v * 4 + t) / cpg;
+            if (gt != g) { atomicAdd(&s_acc[g], gs); atomicAdd(&s_acc[groups + g], gss); g = gt; gs = 0.f; gss = 0.f; }
+            gs += s[t]; gss += ss[t];
         }
+        atomicAdd(&s_acc[g], gs); atomicAdd(&s_acc[groups + g], gss);
     }
-    if (cur_g >= 0) { atomicAdd(&s_acc[cur_g], s); atomicAdd(&s_acc[groups + cur_g], ss); }
     __syncthreads();
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
         atomicAdd(&sums[((size_t)b * groups + g) * 2 + 0], (double)s_acc[g]);
@@ -96,23 +96,43 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int ld, int C, int 
     }
 }
 
+// grid covers M * C/4 float4s; the (mean, rstd) of the <= 2 samples a CTA can touch are finalised once into shared memory
 __global__ void gn_apply_kernel(const float* __restrict__ x, int ld, int C, int HW, int groups, const double* __restrict__ sums, float eps,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu, Out4 y, Out4 raw, long long total4) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over M * C/4
-    if (i >= total4) return;
+    constexpr int NB = 4;                                      // samples cached per CTA; rarer layouts take the direct path below
+    __shared__ float s_mean[NB][64], s_rstd[NB][64];           // groups <= 64
     const int V = C / 4, cpg = C / groups;
+    const long long i0 = (long long)blockIdx.x * blockDim.x;
+    const int b_first = (int)((i0 / V) / HW);
+    if (threadIdx.x < NB * groups) {
+        const int which = threadIdx.x / groups, g = threadIdx.x % groups, bb = b_first + which;
+        const long long last = i0 + blockDim.x - 1 < total4 ? i0 + blockDim.x - 1 : total4 - 1;
+        if (bb <= (int)((last / V) / HW)) {
+            const double cnt = (double)HW * cpg;
+            double s = sums[((size_t)bb * groups + g) * 2], ss = sums[((size_t)bb * groups + g) * 2 + 1];
+            double mean = s / cnt, var = ss / cnt - mean * mean;
+            s_mean[which][g] = (float)mean;
+            s_rstd[which][g] = (float)(1.0 / sqrt((var > 0 ? var : 0.0) + (double)eps));
+        }
+    }
+    __syncthreads();
+    long long i = i0 + threadIdx.x;       // over M * C/4
+    if (i >= total4) return;
     int v = (int)(i % V); long long m = i / V;
-    int b = (int)(m / HW);
+    const int which = (int)(m / HW) - b_first;
     float4 q = *reinterpret_cast<const float4*>(x + m * ld + v * 4);
     float e[4] = {q.x, q.y, q.z, q.w}, o[4];
-    const double cnt = (double)HW * cpg;
 #pragma unroll
     for (int t = 0; t < 4; t++) {
         int c = v * 4 + t, g = c / cpg;
-        double s = sums[((size_t)b * groups + g) * 2], ss = sums[((size_t)b * groups + g) * 2 + 1];
-        double mean = s / cnt, var = ss / cnt - mean * mean;
-        float rstd = (float)(1.0 / sqrt((var > 0 ? var : 0.0) + (double)eps));
-        float val = (e[t] - (float)mean) * rstd * gamma[c] + beta[c];
+        float mean, rstd;
+        if (which < NB) { mean = s_mean[which][g]; rstd = s_rstd[which][g]; }
+        else {
+            const double cnt = (double)HW * cpg; const size_t bb = (size_t)(b_first + which);
+            double s = sums[(bb * groups + g) * 2], ss = sums[(bb * groups + g) * 2 + 1], mu = s / cnt, var = ss / cnt - mu * mu;
+            mean = (float)mu; rstd = (float)(1.0 / sqrt((var > 0 ? var : 0.0) + (double)eps));
+        }
+        float val = (e[t] - mean) * rstd * gamma[c] + beta[c];
         o[t] = silu ? silu_f(val) : val;
     }
     store4(y, (size_t)m, v * 4, o[0], o[1], o[2], o[3]);
@@ -305,14 +325,22 @@ int k_timestep_embedding(const long long* t, int B, int dim, float* out, cudaStr
 }
 int k_gn_stats(View x, int B, int HW, int groups, double* sums, cudaStream_t st) {
     RDM_REQUIRE(x.C % 4 == 0 && x.C % groups == 0 && x.ld % 4 == 0, RDM_ERR_ARG, "gn_stats: C=%d ld=%d groups=%d", x.C, x.ld, groups);
-    // ~8K float4 per CTA
-    int rows_per_cta = (8192 * 4) / x.C; if (rows_per_cta < 1) rows_per_cta = 1;
+    RDM_REQUIRE(groups <= 64, RDM_ERR_UNSUPPORTED, "gn_stats: groups > 64");
+    const int V = x.C / 4;
+    int threads = V >= 256 ? ((V + 31) / 32) * 32 : (256 / V) * V;             // whole rows of float4 columns per pass
+    if (threads > 1024) threads = 1024;
+    RDM_REQUIRE(V <= 1024, RDM_ERR_UNSUPPORTED, "gn_stats: C=%d too wide", x.C);
+    // enough CTAs to fill the machine, at least ~8 rows per thread slot
+    int nslots = threads / V; if (nslots < 1) nslots = 1;
+    int rows_per_cta = nslots * 8;
     int chunks = (HW + rows_per_cta - 1) / rows_per_cta;
-    gn_stats_kernel<<<dim3(chunks, B), 256, 2 * groups * sizeof(float), st>>>(x.p, x.ld, x.C, HW, groups, rows_per_cta, sums);
+    while (chunks * B > 148 * 8 && rows_per_cta < HW) { rows_per_cta *= 2; chunks = (HW + rows_per_cta - 1) / rows_per_cta; }
+    gn_stats_kernel<<<dim3(chunks, B), threads, 2 * groups * sizeof(float), st>>>(x.p, x.ld, x.C, HW, groups, rows_per_cta, sums);
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps, const float* gamma, const float* beta, int silu, Out4 y, Out4 raw, cudaStream_t st) {
     RDM_REQUIRE(x.C % 4 == 0 && y.ldf % 4 == 0 && y.ldb % 4 == 0, RDM_ERR_ARG, "gn_apply: alignment");
+    RDM_REQUIRE(groups <= 64, RDM_ERR_UNSUPPORTED, "gn_apply: groups > 64");
     long long total4 = (long long)B * HW * (x.C / 4);
     gn_apply_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(x.p, x.ld, x.C, HW, groups, sums, eps, gamma, beta, silu, y, raw, total4);
     LAUNCH_CHECK(); return RDM_OK;
