@@ -108,6 +108,8 @@ struct TcKernelParams {
     int plain;                 // 1: A is a plain [M, C] matrix encoded as (c, m, 1, 1): tile -> x0 = mt*128
     int bw, bh, bb;            // box extents (x, y, batch): bw*bh*bb == 128
     int H, W;                  // logical output grid per image (for tile -> (b,y,x))
+    int splits, kb_per_split;  // split-K: work item = (tile, split); partial fp32 accumulators go to `part` [splits][M][N]
+    float* part;
     // epilogue
     const float* bias; const float* rowvec; int rowvec_ld; int rows_per_batch;
     const float* res; int res_ld; int act;
@@ -240,7 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.taps * p.kb_per_tap;
-    const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + BM - 1) / BM, ntiles = ntn * ntm;
+    const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + BM - 1) / BM, nitems = ntn * ntm * p.splits;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmB_hi);
@@ -261,13 +263,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;                                                  // global k-block counter (ring position)
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int tile = item / p.splits, sp = item - tile * p.splits;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
                 const int mt = tile / ntn, n0 = (tile % ntn) * BN;
                 int x0 = 0, y0 = 0, b0 = 0;                              // tile origin in (x, y, b) of the NHWC plane
                 if (p.plain) x0 = mt * BM;
                 else if (p.bb > 1 || p.bh * p.bw == p.H * p.W) b0 = mt * p.bb;
                 else { int tiles_per_img = (p.H * p.W) / BM; b0 = mt / tiles_per_img; y0 = (mt % tiles_per_img) * p.bh; }
-                for (int kb = 0; kb < nkb; kb++, it++) {
+                for (int kb = kb0; kb < kb1; kb++, it++) {
                     const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * S::STAGE_BYTES;
@@ -287,12 +291,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BN);
             int it = 0, lt = 0;                                          // ring position, local tile counter
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, lt++) {
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x, lt++) {
+                const int sp = item % p.splits;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
                 const int buf = lt & 1;
                 mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-                for (int kb = 0; kb < nkb; kb++, it++) {
+                for (int kb = kb0; kb < kb1; kb++, it++) {
                     const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
@@ -301,7 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < BK / 16; k++) {
                         const uint64_t da = umma_desc_sw128(a_hi + k * 32), db = umma_desc_sw128(b_hi + k * 32);
-                        umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+                        umma_bf16(tmem_d, da, db, idesc, ((kb - kb0) | k) != 0);
                         if (NSPLIT == 3) {
                             umma_bf16(tmem_d, umma_desc_sw128(a_lo + k * 32), db, idesc, 1);
                             umma_bf16(tmem_d, da, umma_desc_sw128(b_lo + k * 32), idesc, 1);
@@ -316,7 +322,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
         const int q = warp & 3;
         int lt = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, lt++) {
+        TcKernelParams pp = p;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, lt++) {
+            const int tile = item / p.splits, sp = item - tile * p.splits;
+            if (p.splits > 1) {                                   // raw partial sums; the reduce kernel applies the epilogue
+                pp.bias = nullptr; pp.rowvec = nullptr; pp.res = nullptr; pp.act = ACT_NONE; pp.out_hi = nullptr; pp.out_lo = nullptr;
+                pp.out = p.part + (size_t)sp * p.M * p.N; pp.out_ld = p.N;
+            }
             const int buf = lt & 1;
             const int mt = tile / ntn, n0 = (tile % ntn) * BN;
             const int m_warp0 = mt * BM + q * 32;
@@ -327,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
                 const int nb = n0 + c * 32;
-                if (m_warp0 < p.M && nb < p.N) epilogue_chunk(p, r, epi_stage + q * EPI_WARP_FLOATS, lane, m_warp0, nb);
+                if (m_warp0 < p.M && nb < p.N) epilogue_chunk(pp, r, epi_stage + q * EPI_WARP_FLOATS, lane, m_warp0, nb);
             }
             tc_fence_before();
             __syncwarp();
@@ -340,6 +352,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS) : "memory");
     }
+}
+
+// out = epi( sum_s part[s] ): 4 consecutive columns of one row per thread
+__global__ void splitk_reduce_kernel(const TcKernelParams p) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int N4 = p.N >> 2;
+    if (i >= (long long)p.M * N4) return;
+    const int m = (int)(i / N4), n = (int)(i % N4) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < p.splits; s++) {
+        float4 t = __ldcs(reinterpret_cast<const float4*>(p.part + ((size_t)s * p.M + m) * p.N + n));
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    float v[4] = {a.x, a.y, a.z, a.w};
+    if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+    if (p.rowvec) { float4 t = __ldg(reinterpret_cast<const float4*>(p.rowvec + (size_t)(m / p.rows_per_batch) * p.rowvec_ld + n)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+    if (p.act == ACT_GEGLU) {
+        float o0 = v[0] * gelu_erf(v[1]), o1 = v[2] * gelu_erf(v[3]);
+        const int no = n >> 1;
+        if (p.res) { o0 += p.res[(size_t)m * p.res_ld + no]; o1 += p.res[(size_t)m * p.res_ld + no + 1]; }
+        if (p.out) *reinterpret_cast<float2*>(p.out + (size_t)m * p.out_ld + no) = make_float2(o0, o1);
+        else {
+            __nv_bfloat16 h0 = __float2bfloat16_rn(o0), h1 = __float2bfloat16_rn(o1);
+            *reinterpret_cast<__nv_bfloat162*>(p.out_hi + (size_t)m * p.out_bf_ld + no) = __halves2bfloat162(h0, h1);
+            if (p.out_lo) *reinterpret_cast<__nv_bfloat162*>(p.out_lo + (size_t)m * p.out_bf_ld + no) =
+                __halves2bfloat162(__float2bfloat16_rn(o0 - __bfloat162float(h0)), __float2bfloat16_rn(o1 - __bfloat162float(h1)));
+        }
+        return;
+    }
+    if (p.act == ACT_SILU) { v[0] = silu_f(v[0]); v[1] = silu_f(v[1]); v[2] = silu_f(v[2]); v[3] = silu_f(v[3]); }
+    if (p.res) { float4 t = *reinterpret_cast<const float4*>(p.res + (size_t)m * p.res_ld + n); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+    if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)m * p.out_ld + n) = make_float4(v[0], v[1], v[2], v[3]);
+    else store_bf16x4(p.out_hi + (size_t)m * p.out_bf_ld + n, p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + n : nullptr, v[0], v[1], v[2], v[3]);
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -389,9 +434,9 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
         RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured[dev & 15] = true;
     }
-    const int ntiles = ((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM);
+    const int nitems = ((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * p.splits;
     const int sms = rdm_num_sms(dev);
-    kern<<<ntiles < sms ? ntiles : sms, TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    kern<<<nitems < sms ? nitems : sms, TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, p);
     RDM_COUNT_LAUNCH();
     RDM_CHECK_CUDA(cudaGetLastError());
     return RDM_OK;
@@ -434,30 +479,62 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     p.res = e.res; p.res_ld = e.res_ld; p.act = e.act; p.out = e.out; p.out_ld = e.out_ld;
     p.out_hi = out_hi; p.out_lo = out_lo; p.out_bf_ld = out_bf_ld;
     RDM_REQUIRE((p.out != nullptr) != (p.out_hi != nullptr), RDM_ERR_ARG, "gemm_tc: exactly one of fp32 / bf16 outputs");
-    // tile width.  The mainloop is operand-feed bound (TMA/L2 -> smem), so the time of one tile grows like (128 + BN) per k-block:
-    // the A tile (128 rows) is re-loaded for every N tile.  Persistent grid: cost = ceil(tiles / SMs) * (128 + BN), ties -> wider.
-    const int mtiles = (M + BM - 1) / BM, sms = 148;
+    // Tile width and split-K.  The mainloop is operand-feed bound (TMA/L2 -> smem): one k-block of a work item costs ~(128 + BN)
+    // (the 128-row A tile is re-loaded for every N tile); every item pays a fixed prologue/epilogue worth ~6 k-blocks.  Small-M layers
+    // (4x4 / 8x8 latents) split K so that all SMs stream a slice of the weights.  cost = waves * (kb_per_item + 6) * (128 + BN).
+    const int mtiles = (M + BM - 1) / BM, sms = 148, nkb_total = p.taps * p.kb_per_tap;
     static const int forced = getenv("RDM_TC_BN") ? atoi(getenv("RDM_TC_BN")) : 0;
-    int BN = 32;
+    static const int no_split = getenv("RDM_TC_NOSPLIT") ? 1 : 0;
+    int BN = 32, splits = 1;
     const int cand[4] = {192, 128, 64, 32};
     long best = -1;
     for (int c : cand) {
         if (c > 32 && w.N <= c / 2) continue;
+        if (forced && c != forced) continue;
         const int nt = (w.N + c - 1) / c;
-        const long tiles = (long)mtiles * nt, waves = (tiles + sms - 1) / sms, cost = waves * (128 + c);
-        if (best < 0 || cost < best) { best = cost; BN = c; }
+        for (int sp = 1; sp <= 16; sp++) {
+            if (sp > 1 && (no_split || nkb_total / sp < 4 || (w.N & 3) || (size_t)sp * M * w.N * 4 > ((size_t)48 << 20))) break;
+            const int kbps = (nkb_total + sp - 1) / sp;
+            if ((sp - 1) * kbps >= nkb_total) continue;                  // an empty split
+            const long items = (long)mtiles * nt * sp, waves = (items + sms - 1) / sms;
+            const long cost = waves * (kbps + 6) * (128 + c) + (sp > 1 ? 2 * (128 + c) : 0);
+            if (best < 0 || cost < best) { best = cost; BN = c; splits = sp; }
+        }
     }
-    if (forced == 192 || forced == 128 || forced == 64 || forced == 32) BN = forced;
+    p.splits = splits; p.kb_per_split = (nkb_total + splits - 1) / splits; p.part = nullptr;
+    if (splits > 1) {
+        static float* ws[16] = {nullptr}; static size_t ws_cap[16] = {0};
+        int dev = 0; cudaGetDevice(&dev);
+        const size_t need = (size_t)splits * M * w.N * sizeof(float);
+        if (need > ws_cap[dev & 15]) {                                   // grown during the eager warm-up pass, never inside a graph capture
+            if (ws[dev & 15]) cudaFree(ws[dev & 15]);
+            ws[dev & 15] = nullptr; ws_cap[dev & 15] = 0;
+            size_t cap = (size_t)48 << 20;
+            RDM_CHECK_CUDA(cudaMalloc((void**)&ws[dev & 15], cap));
+            ws_cap[dev & 15] = cap;
+        }
+        p.part = ws[dev & 15];
+    }
     RDM_TRY(make_map_2d(&tb_hi, w.hi, w.K, w.N, w.ld, BN));
     if (nsplit == 3) RDM_TRY(make_map_2d(&tb_lo, w.lo, w.K, w.N, w.ld, BN)); else tb_lo = tb_hi;
+    int rc;
     if (nsplit == 3) {
-        if (BN == 192) return launch_tc<192, 3, 2>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        if (BN == 128) return launch_tc<128, 3, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        if (BN == 64) return launch_tc<64, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        return launch_tc<32, 3, 5>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        if (BN == 192) rc = launch_tc<192, 3, 2>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        else if (BN == 128) rc = launch_tc<128, 3, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        else if (BN == 64) rc = launch_tc<64, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        else rc = launch_tc<32, 3, 5>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+    } else {
+        if (BN == 192) rc = launch_tc<192, 1, 5>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        else if (BN == 128) rc = launch_tc<128, 1, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        else if (BN == 64) rc = launch_tc<64, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        else rc = launch_tc<32, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
     }
-    if (BN == 192) return launch_tc<192, 1, 5>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-    if (BN == 128) return launch_tc<128, 1, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-    if (BN == 64) return launch_tc<64, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-    return launch_tc<32, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+    RDM_TRY(rc);
+    if (splits > 1) {
+        const long long n4 = (long long)M * (w.N >> 2);
+        splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(p);
+        RDM_COUNT_LAUNCH();
+        RDM_CHECK_CUDA(cudaGetLastError());
+    }
+    return RDM_OK;
 }

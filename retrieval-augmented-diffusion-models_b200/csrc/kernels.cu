@@ -96,47 +96,39 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int ld, int C, int 
     }
 }
 
-// grid covers M * C/4 float4s; the (mean, rstd) of the <= 2 samples a CTA can touch are finalised once into shared memory
+// grid (row_chunks, B), same thread->column mapping as gn_stats: a thread owns float4 column v for the whole kernel (group ids, gamma,
+// beta and the finalised mean/rstd are loaded once) and walks rows slot, slot+nslots, ...; no per-element integer division.
 __global__ void gn_apply_kernel(const float* __restrict__ x, int ld, int C, int HW, int groups, const double* __restrict__ sums, float eps,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu, Out4 y, Out4 raw, long long total4) {
-    constexpr int NB = 4;                                      // samples cached per CTA; rarer layouts take the direct path below
-    __shared__ float s_mean[NB][64], s_rstd[NB][64];           // groups <= 64
-    const int V = C / 4, cpg = C / groups;
-    const long long i0 = (long long)blockIdx.x * blockDim.x;
-    const int b_first = (int)((i0 / V) / HW);
-    if (threadIdx.x < NB * groups) {
-        const int which = threadIdx.x / groups, g = threadIdx.x % groups, bb = b_first + which;
-        const long long last = i0 + blockDim.x - 1 < total4 ? i0 + blockDim.x - 1 : total4 - 1;
-        if (bb <= (int)((last / V) / HW)) {
-            const double cnt = (double)HW * cpg;
-            double s = sums[((size_t)bb * groups + g) * 2], ss = sums[((size_t)bb * groups + g) * 2 + 1];
-            double mean = s / cnt, var = ss / cnt - mean * mean;
-            s_mean[which][g] = (float)mean;
-            s_rstd[which][g] = (float)(1.0 / sqrt((var > 0 ? var : 0.0) + (double)eps));
-        }
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu, Out4 y, Out4 raw, int rows_per_cta) {
+    __shared__ float s_mean[64], s_rstd[64];
+    const int b = blockIdx.y, V = C / 4, cpg = C / groups;
+    if (threadIdx.x < groups) {
+        const double cnt = (double)HW * cpg;
+        double s = sums[((size_t)b * groups + threadIdx.x) * 2], ss = sums[((size_t)b * groups + threadIdx.x) * 2 + 1];
+        double mean = s / cnt, var = ss / cnt - mean * mean;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt((var > 0 ? var : 0.0) + (double)eps));
     }
     __syncthreads();
-    long long i = i0 + threadIdx.x;       // over M * C/4
-    if (i >= total4) return;
-    int v = (int)(i % V); long long m = i / V;
-    const int which = (int)(m / HW) - b_first;
-    float4 q = *reinterpret_cast<const float4*>(x + m * ld + v * 4);
-    float e[4] = {q.x, q.y, q.z, q.w}, o[4];
+    const int nslots = blockDim.x / V, v = threadIdx.x % V, slot = threadIdx.x / V;
+    if (slot >= nslots) return;
+    float sc[4], sh[4];
 #pragma unroll
     for (int t = 0; t < 4; t++) {
-        int c = v * 4 + t, g = c / cpg;
-        float mean, rstd;
-        if (which < NB) { mean = s_mean[which][g]; rstd = s_rstd[which][g]; }
-        else {
-            const double cnt = (double)HW * cpg; const size_t bb = (size_t)(b_first + which);
-            double s = sums[(bb * groups + g) * 2], ss = sums[(bb * groups + g) * 2 + 1], mu = s / cnt, var = ss / cnt - mu * mu;
-            mean = (float)mu; rstd = (float)(1.0 / sqrt((var > 0 ? var : 0.0) + (double)eps));
-        }
-        float val = (e[t] - mean) * rstd * gamma[c] + beta[c];
-        o[t] = silu ? silu_f(val) : val;
+        const int c = v * 4 + t, g = c / cpg;
+        sc[t] = s_rstd[g] * gamma[c];
+        sh[t] = beta[c] - s_mean[g] * sc[t];
     }
-    store4(y, (size_t)m, v * 4, o[0], o[1], o[2], o[3]);
-    if (raw.any()) store4(raw, (size_t)m, v * 4, e[0], e[1], e[2], e[3]);
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
+    const size_t m0 = (size_t)b * HW;
+    const bool want_raw = raw.any();
+    for (int r = r0 + slot; r < r1; r += nslots) {
+        const float4 q = *reinterpret_cast<const float4*>(x + (m0 + r) * ld + v * 4);
+        float o0 = fmaf(q.x, sc[0], sh[0]), o1 = fmaf(q.y, sc[1], sh[1]), o2 = fmaf(q.z, sc[2], sh[2]), o3 = fmaf(q.w, sc[3], sh[3]);
+        if (silu) { o0 = silu_f(o0); o1 = silu_f(o1); o2 = silu_f(o2); o3 = silu_f(o3); }
+        store4(y, m0 + r, v * 4, o0, o1, o2, o3);
+        if (want_raw) store4(raw, m0 + r, v * 4, q.x, q.y, q.z, q.w);
+    }
 }
 
 // one warp per row, two-pass (mean, then centred variance) in fp32 from registers/L1
@@ -340,9 +332,15 @@ int k_gn_stats(View x, int B, int HW, int groups, double* sums, cudaStream_t st)
 }
 int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps, const float* gamma, const float* beta, int silu, Out4 y, Out4 raw, cudaStream_t st) {
     RDM_REQUIRE(x.C % 4 == 0 && y.ldf % 4 == 0 && y.ldb % 4 == 0, RDM_ERR_ARG, "gn_apply: alignment");
-    RDM_REQUIRE(groups <= 64, RDM_ERR_UNSUPPORTED, "gn_apply: groups > 64");
-    long long total4 = (long long)B * HW * (x.C / 4);
-    gn_apply_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(x.p, x.ld, x.C, HW, groups, sums, eps, gamma, beta, silu, y, raw, total4);
+    RDM_REQUIRE(groups <= 64 && x.C / 4 <= 1024, RDM_ERR_UNSUPPORTED, "gn_apply: groups > 64 or C too wide");
+    const int V = x.C / 4;
+    int threads = V >= 256 ? ((V + 31) / 32) * 32 : (256 / V) * V;
+    if (threads < groups) threads = ((groups + 31) / 32) * 32;
+    int nslots = threads / V; if (nslots < 1) nslots = 1;
+    int rows_per_cta = nslots * 4;
+    int chunks = (HW + rows_per_cta - 1) / rows_per_cta;
+    while (chunks * B > 148 * 16 && rows_per_cta < HW) { rows_per_cta *= 2; chunks = (HW + rows_per_cta - 1) / rows_per_cta; }
+    gn_apply_kernel<<<dim3(chunks, B), threads, 0, st>>>(x.p, x.ld, x.C, HW, groups, sums, eps, gamma, beta, silu, y, raw, rows_per_cta);
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_layernorm(View x, int M, const float* gamma, const float* beta, float eps, Out4 y, cudaStream_t st) {

@@ -28,7 +28,9 @@ def _setup(tmp_path, cuda, seed=4):
     ck = {"model.diffusion_model." + k: v for k, v in ref.state_dict().items()}
     ck.update({"model_ema." + ("diffusion_model." + k).replace(".", ""): v for k, v in ema.state_dict().items()})
     missing, unexpected = model.load_state_dict(ck, strict=False)
-    assert not unexpected and set(missing) <= {"unconditional_guidance_vex", "model_ema.decay", "model_ema.num_updates"}
+    sched = {"betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "log_one_minus_alphas_cumprod",
+             "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod"}            # present in real checkpoints, not in this synthetic one
+    assert not unexpected and set(missing) <= {"unconditional_guidance_vex", "model_ema.decay", "model_ema.num_updates"} | sched
     model = model.eval().to(cuda)
     return model, db, ema
 
