@@ -155,6 +155,36 @@ RDM_API int rdm_ddim_step(const float* x_dev, const float* eps_dev, int64_t n_pe
                   const float* coef_dev, const float* noise_dev, float* x_prev_dev, float* pred_x0_dev,
                   int32_t device, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * CLIP encoders (retrieval queries): rdm/modules/custom_clip/model.py:201-235 (VisualTransformer), :166-198 (Transformer),
+ * :304 (encode_image), :307-320 (encode_text); call sites rdm/modules/retrievers.py:83-95 (ClipImageRetriever),
+ * scripts/rdm_sample.py:275-277 and scripts/rarm_sample.py:232-236 (clip.encode_text), dsetbuilder.py:461-473 (embed).
+ * The struct mirrors the CLIP constructor (model.py:240-252); parameter names are the reference state-dict keys
+ * ("visual.transformer.resblocks.0.attn.in_proj_weight", "text_projection", ...).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct rdm_clip rdm_clip_t;
+typedef struct rdm_clip_cfg {
+    int32_t embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size;
+    int32_t context_length, vocab_size, transformer_width, transformer_heads, transformer_layers;
+} rdm_clip_cfg;
+RDM_API int rdm_clip_create(rdm_clip_t** out, const rdm_clip_cfg* cfg, int32_t device);
+RDM_API void rdm_clip_destroy(rdm_clip_t* h);
+RDM_API int64_t rdm_clip_num_params(const rdm_clip_t* h);
+RDM_API const char* rdm_clip_param_name(const rdm_clip_t* h, int64_t i);
+RDM_API int64_t rdm_clip_param_numel(const rdm_clip_t* h, const char* name);
+RDM_API int rdm_clip_load(rdm_clip_t* h, const char* name, const float* host, int64_t numel);   /* host float32, reference layout */
+RDM_API int64_t rdm_clip_missing(const rdm_clip_t* h);
+RDM_API int rdm_clip_set_mode(rdm_clip_t* h, int32_t mode);                                       /* RDM_UNET_MODE_* (default bf16x3) */
+/* CLIP.encode_text: tokens int64 [B, context_length] (device) -> float32 [B, embed_dim] */
+RDM_API int rdm_clip_encode_text(rdm_clip_t* h, const int64_t* tokens_dev, int32_t B, float* out_dev, void* stream);
+/* CLIP.encode_image: float32 NCHW [B, 3, R, R], already preprocessed -> float32 [B, embed_dim] */
+RDM_API int rdm_clip_encode_image(rdm_clip_t* h, const float* image_dev, int32_t B, float* out_dev, void* stream);
+/* ClipImageRetriever.preprocess (retrievers.py:83-95): x in [-1,1] NCHW [B,3,H,W] -> bicubic (align_corners=True) resize to
+ * size x size, (x+1)/2, CLIP mean/std normalisation.  out float32 [B,3,size,size]. */
+RDM_API int rdm_clip_preprocess(const float* image_dev, int32_t B, int32_t H, int32_t W, int32_t size, float* out_dev,
+                        int32_t device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

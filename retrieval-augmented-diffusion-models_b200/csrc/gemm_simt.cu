@@ -166,6 +166,7 @@ gemm_simt_kernel(AParams a, const float* __restrict__ W, int N, EParams e) {
                     if (n < N) {
                         float t = v[j];
                         if (e.act == ACT_SILU) t = silu_f(t);
+                        else if (e.act == ACT_QUICKGELU) t = t / (1.f + expf(-1.702f * t));
                         if (e.res) t += e.res[(size_t)m * e.res_ld + n];
                         e.out[(size_t)m * e.out_ld + n] = t;
                     }

@@ -166,6 +166,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
                     if (p.bias) t += __ldg(p.bias + n);
                     if (p.rowvec) t += __ldg(p.rowvec + (size_t)bidx * p.rowvec_ld + n);
                     if (p.act == ACT_SILU) t = silu_f(t);
+                    else if (p.act == ACT_QUICKGELU) t = t / (1.f + expf(-1.702f * t));
                     if (p.res) t += p.res[(size_t)m * p.res_ld + n];
                     if (p.out) p.out[(size_t)m * p.out_ld + n] = t;
                     else {
@@ -196,6 +197,9 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
     } else if (p.act == ACT_SILU) {
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = silu_f(v[j]);
+    } else if (p.act == ACT_QUICKGELU) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = v[j] / (1.f + expf(-1.702f * v[j]));
     }
     // transpose through shared memory
     float* row = stage + lane * EPI_LD;
@@ -382,6 +386,10 @@ __global__ void splitk_reduce_kernel(const TcKernelParams p) {
         return;
     }
     if (p.act == ACT_SILU) { v[0] = silu_f(v[0]); v[1] = silu_f(v[1]); v[2] = silu_f(v[2]); v[3] = silu_f(v[3]); }
+    else if (p.act == ACT_QUICKGELU) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = v[j] / (1.f + expf(-1.702f * v[j]));
+    }
     if (p.res) { float4 t = *reinterpret_cast<const float4*>(p.res + (size_t)m * p.res_ld + n); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
     if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)m * p.out_ld + n) = make_float4(v[0], v[1], v[2], v[3]);
     else store_bf16x4(p.out_hi + (size_t)m * p.out_bf_ld + n, p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + n : nullptr, v[0], v[1], v[2], v[3]);

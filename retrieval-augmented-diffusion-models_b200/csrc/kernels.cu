@@ -160,55 +160,58 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ld, int C, int
     }
 }
 
-// Attention for d_head = 32: one thread per query row, keys/values of one (batch, head) staged through shared
-// memory in tiles of KT keys (broadcast reads), online softmax in fp32.  grid (ceil(Nq/blockDim), heads, B).
+// Attention for d_head = DH (32: U-Net, 64: CLIP): one thread per query row, keys/values of one (batch, head) staged through
+// shared memory in tiles of KT keys (broadcast reads), online softmax in fp32.  grid (ceil(Nq/blockDim), heads, B).
+// causal: key j contributes to query i only if j <= i.
 constexpr int KT = 64;
-__global__ void attention_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
-                                     int Nq, int Nk, float scale_log2e, Out4 out) {
-    __shared__ float4 sk[KT][8], sv[KT][8];
+template <int DH>
+__global__ void attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
+                                 int Nq, int Nk, float scale_log2e, int causal, Out4 out) {
+    constexpr int V4 = DH / 4;
+    __shared__ float4 sk[KT][V4], sv[KT][V4];
     const int b = blockIdx.z, h = blockIdx.y;
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = qi < Nq;
-    float qr[32], acc[32];
+    float qr[DH], acc[DH];
     if (active) {
-        const float4* qp = reinterpret_cast<const float4*>(q + ((size_t)b * Nq + qi) * ldq + h * 32);
+        const float4* qp = reinterpret_cast<const float4*>(q + ((size_t)b * Nq + qi) * ldq + h * DH);
 #pragma unroll
-        for (int i = 0; i < 8; i++) { float4 t = qp[i]; qr[4 * i] = t.x * scale_log2e; qr[4 * i + 1] = t.y * scale_log2e; qr[4 * i + 2] = t.z * scale_log2e; qr[4 * i + 3] = t.w * scale_log2e; }
+        for (int i = 0; i < V4; i++) { float4 t = qp[i]; qr[4 * i] = t.x * scale_log2e; qr[4 * i + 1] = t.y * scale_log2e; qr[4 * i + 2] = t.z * scale_log2e; qr[4 * i + 3] = t.w * scale_log2e; }
     } else {
 #pragma unroll
-        for (int i = 0; i < 32; i++) qr[i] = 0.f;
+        for (int i = 0; i < DH; i++) qr[i] = 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 32; i++) acc[i] = 0.f;
+    for (int i = 0; i < DH; i++) acc[i] = 0.f;
     float mx = -CUDART_INF_F, l = 0.f;
     for (int k0 = 0; k0 < Nk; k0 += KT) {
         const int kn = min(KT, Nk - k0);
         __syncthreads();
-        for (int i = threadIdx.x; i < kn * 8; i += blockDim.x) {
-            int j = i >> 3, c = i & 7;
-            sk[j][c] = *reinterpret_cast<const float4*>(k + ((size_t)b * Nk + k0 + j) * ldk + h * 32 + c * 4);
-            sv[j][c] = *reinterpret_cast<const float4*>(v + ((size_t)b * Nk + k0 + j) * ldv + h * 32 + c * 4);
+        for (int i = threadIdx.x; i < kn * V4; i += blockDim.x) {
+            int j = i / V4, c = i % V4;
+            sk[j][c] = *reinterpret_cast<const float4*>(k + ((size_t)b * Nk + k0 + j) * ldk + h * DH + c * 4);
+            sv[j][c] = *reinterpret_cast<const float4*>(v + ((size_t)b * Nk + k0 + j) * ldv + h * DH + c * 4);
         }
         __syncthreads();
-        for (int j = 0; j < kn; j++) {
+        const int jend = causal ? min(kn, qi - k0 + 1) : kn;
+        for (int j = 0; j < jend; j++) {
             float s = 0.f;
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
+            for (int c = 0; c < V4; c++) {
                 float4 kk = sk[j][c];
                 s = fmaf(qr[4 * c], kk.x, s); s = fmaf(qr[4 * c + 1], kk.y, s); s = fmaf(qr[4 * c + 2], kk.z, s); s = fmaf(qr[4 * c + 3], kk.w, s);
             }
-            // s is the logit in log2 units
-            if (s > mx) {
+            if (s > mx) {                      // s is the logit in log2 units
                 float corr = exp2f(mx - s);
                 l *= corr;
 #pragma unroll
-                for (int i = 0; i < 32; i++) acc[i] *= corr;
+                for (int i = 0; i < DH; i++) acc[i] *= corr;
                 mx = s;
             }
             float p = exp2f(s - mx);
             l += p;
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
+            for (int c = 0; c < V4; c++) {
                 float4 vv = sv[j][c];
                 acc[4 * c] = fmaf(p, vv.x, acc[4 * c]); acc[4 * c + 1] = fmaf(p, vv.y, acc[4 * c + 1]);
                 acc[4 * c + 2] = fmaf(p, vv.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(p, vv.w, acc[4 * c + 3]);
@@ -218,7 +221,7 @@ __global__ void attention_d32_kernel(const float* __restrict__ q, int ldq, const
     if (active) {
         const float inv = 1.f / l;
 #pragma unroll
-        for (int i = 0; i < 8; i++) store4(out, (size_t)b * Nq + qi, h * 32 + 4 * i, acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
+        for (int i = 0; i < V4; i++) store4(out, (size_t)b * Nq + qi, h * DH + 4 * i, acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
     }
 }
 
@@ -352,7 +355,14 @@ int k_attention(View q, View k, View v, int B, int Nq, int Nk, int heads, float 
     RDM_REQUIRE(q.C == heads * 32, RDM_ERR_UNSUPPORTED, "attention: only d_head=32 is implemented (C=%d heads=%d)", q.C, heads);
     int threads = Nq >= 128 ? 128 : ((Nq + 31) / 32) * 32;
     dim3 grid((Nq + threads - 1) / threads, heads, B);
-    attention_d32_kernel<<<grid, threads, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, Nq, Nk, scale * 1.4426950408889634f, out);
+    attention_kernel<32><<<grid, threads, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, Nq, Nk, scale * 1.4426950408889634f, 0, out);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_attention_d64(View q, View k, View v, int B, int N, int heads, float scale, int causal, Out4 out, cudaStream_t st) {
+    RDM_REQUIRE(q.C == heads * 64, RDM_ERR_UNSUPPORTED, "attention_d64: C=%d heads=%d", q.C, heads);
+    int threads = N >= 128 ? 128 : ((N + 31) / 32) * 32;
+    dim3 grid((N + threads - 1) / threads, heads, B);
+    attention_kernel<64><<<grid, threads, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, N, N, scale * 1.4426950408889634f, causal, out);
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_split_planes(View x, long long M, Out4 y, cudaStream_t st) {

@@ -32,7 +32,7 @@ struct GemmA {
     int M() const { return B * Ho * Wo; }
     int K() const { return ksize * ksize * Cin; }
 };
-enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2 };
+enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2, ACT_QUICKGELU = 3 };      // QuickGELU: x * sigmoid(1.702 x) (custom_clip/model.py:159-161)
 struct GemmEpi {
     const float* bias = nullptr;                                   // [N]
     const float* rowvec = nullptr; int rowvec_ld = 0; int rows_per_batch = 1;   // + rowvec[(m / rows_per_batch)*rowvec_ld + n]
@@ -58,6 +58,8 @@ int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps,
 int k_layernorm(View x, int M, const float* gamma, const float* beta, float eps, Out4 y, cudaStream_t st);
 // softmax(q k^T * scale) v for heads of width 32.  q: [B*Nq, heads*32] view, k/v: [B*Nk, heads*32] views.
 int k_attention(View q, View k, View v, int B, int Nq, int Nk, int heads, float scale, Out4 out, cudaStream_t st);
+// same for heads of width 64 (CLIP), optional causal mask (key j visible to query i iff j <= i; custom_clip/model.py:287-292)
+int k_attention_d64(View q, View k, View v, int B, int N, int heads, float scale, int causal, Out4 out, cudaStream_t st);
 // fp32 [M, C] -> bf16 planes
 int k_split_planes(View x, long long M, Out4 y, cudaStream_t st);
 // im2col of a 3x3 / stride 2 / pad 1 conv (ldm Downsample): x NHWC [B,H,W,C] -> [B*Ho*Wo, 9*C] (tap-major), Ho=(H+1)/2

@@ -43,6 +43,17 @@ SIGNATURES = {
     "rdm_unet_profile_forward": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "rdm_unet_profile_text": (c_char_p, [c_void_p]),
     "rdm_ddim_sample": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
+    "rdm_clip_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int32]),
+    "rdm_clip_destroy": (None, [c_void_p]),
+    "rdm_clip_num_params": (c_int64, [c_void_p]),
+    "rdm_clip_param_name": (c_char_p, [c_void_p, c_int64]),
+    "rdm_clip_param_numel": (c_int64, [c_void_p, c_char_p]),
+    "rdm_clip_load": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "rdm_clip_missing": (c_int64, [c_void_p]),
+    "rdm_clip_set_mode": (c_int, [c_void_p, c_int32]),
+    "rdm_clip_encode_text": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "rdm_clip_encode_image": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "rdm_clip_preprocess": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "rdm_ddim_step": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
 }
 
