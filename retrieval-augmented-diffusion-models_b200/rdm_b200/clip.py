@@ -22,7 +22,7 @@ def cfg_from_state_dict(sd):
     P = sd["visual.conv1.weight"].shape[-1]
     G = round((sd["visual.positional_embedding"].shape[0] - 1) ** 0.5)
     tw = sd["ln_final.weight"].shape[0]
-    nl = lambda p: len({k.split(".")[len(p.split("."))] for k in sd if k.startswith(p + ".resblocks.")})
+    nl = lambda p: len({k.split(".")[len(p.split(".")) + 1] for k in sd if k.startswith(p + ".resblocks.")})
     return dict(embed_dim=sd["text_projection"].shape[1], image_resolution=P * G, vision_layers=nl("visual.transformer"), vision_width=vw,
                 vision_patch_size=P, context_length=sd["positional_embedding"].shape[0], vocab_size=sd["token_embedding.weight"].shape[0],
                 transformer_width=tw, transformer_heads=tw // 64, transformer_layers=nl("transformer"))

@@ -32,3 +32,11 @@ def test_random_state_dict_has_the_reference_vit_b32_inventory():
     n = sum(v.numel() for k, v in sd.items() if k != "token_embedding.weight")
     # custom_clip ViT-B/32 = 151,277,313 parameters (151.28 M) of which 49408*512 are the token embedding
     assert n == 151_277_313 - 49408 * 512
+
+
+def test_cfg_inference_from_state_dict_matches_build_model():
+    from rdm_b200.clip import VIT_B32, cfg_from_state_dict
+    d, sd, cfg = _golden()
+    assert cfg_from_state_dict(sd) == cfg
+    big = oclip.random_state_dict(**dict(VIT_B32, vocab_size=1000))
+    assert cfg_from_state_dict(big) == dict(VIT_B32, vocab_size=1000)

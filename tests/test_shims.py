@@ -39,3 +39,22 @@ def test_seed_everything_seeds_numpy_and_torch():
     from pytorch_lightning import seed_everything
     seed_everything(7); a, b = np.random.rand(), torch.rand(1)
     seed_everything(7); assert a == np.random.rand() and torch.equal(b, torch.rand(1))
+
+
+def test_tokenizer_matches_reference_golden_ids():
+    """Golden ids come from the reference's own tokenizer (tests/golden/make_golden_tokens.py).  Needs the CLIP merge table, a data
+    file that is not shipped in this repo: skipped where it is absent (e.g. on the GPU box)."""
+    import json
+    import pytest
+    _shims()
+    import clip
+    try:
+        clip._find_vocab()
+    except FileNotFoundError:
+        pytest.skip("bpe_simple_vocab_16e6.txt.gz not available")
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clip_tokens.json")))
+    toks = clip.tokenize(list(g["prompts"].keys()))
+    assert toks.shape == (len(g["prompts"]), 77) and toks.dtype.is_floating_point is False
+    for row, (prompt, ids) in zip(toks, g["prompts"].items()):
+        assert row[:len(ids)].tolist() == ids and int(row[len(ids):].abs().sum()) == 0, prompt
+        assert int(row.argmax()) == len(ids) - 1                      # EOT is the largest id: encode_text gathers it (model.py:318)
