@@ -18,6 +18,7 @@
 //      unrepresentative of the DB), knn_scan_kernel<LOCKED> redoes the pass with per-CTA top-32 lists under a lock.
 // Replaces ScaNN behind `searcher.search_batched` (dsetbuilder.py:490, ddpm.py:906-908).
 #include "common.cuh"
+#include "ptx.cuh"
 #include "../../include/rdm_b200.h"
 #include <math_constants.h>
 
@@ -131,10 +132,12 @@ template <int R> __device__ __forceinline__ int row_of_lane(int lane) {
     return r;
 }
 
+constexpr int SCAN_MAX_STAGES = 3;
 struct ScanShared {
     u64 list[MAX_QP][LIST];
     float thr[MAX_QP];
     int lock[MAX_QP];
+    uint64_t full[SCAN_WARPS][SCAN_MAX_STAGES];     // per-warp TMA ring barriers
 };
 
 // Warp-uniform insertion of `key` into the CTA-wide list of query `q` (rare path: ~LIST*ln(rows/LIST) times per CTA).
@@ -171,18 +174,22 @@ struct ScanArgs {
     int group_stride;      // SAMPLE: take every group_stride-th row group
 };
 
-template <typename T, int D, int QP, int R, int MODE>
+// Rows reach the SM through per-warp shared-memory rings filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier): one elected
+// lane keeps NST groups of R rows (8 KB each) in flight per warp, decoupled from the registers that do the arithmetic.
+template <typename T, int D, int QP, int R, int MODE, int NST>
 __global__ void __launch_bounds__(SCAN_THREADS)
 knn_scan_kernel(const T* __restrict__ db, const float* __restrict__ inv, long long n,
                 const float* __restrict__ q, int nq_valid, ScanArgs args) {
     if (MODE == SCAN_LOCKED) { if (*args.overflow == 0u) return; }
+    constexpr int STAGE_BYTES = R * D * (int)sizeof(T);
     constexpr int EPL = D / 32;              // elements per lane per row
     constexpr int EPV = Elem<T>::EPV;        // elements per 16-byte vector
     constexpr int NV = EPL / EPV;            // vectors per lane per row
     constexpr int NC = EPL / 4;              // float4 query chunks per lane
     static_assert(EPL % EPV == 0 && EPL % 4 == 0, "row width");
-    extern __shared__ float4 smem_q[];       // [QP][NC][32], permuted so lane l reads consecutive float4s
+    extern __shared__ float4 smem_q[];       // [QP][NC][32], permuted so lane l reads consecutive float4s; then the row rings
     __shared__ ScanShared sh;
+    uint8_t* ring = reinterpret_cast<uint8_t*>(smem_q + QP * NC * 32) + (size_t)(threadIdx.x >> 5) * NST * STAGE_BYTES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < QP * NC * 32; i += SCAN_THREADS) {
@@ -203,6 +210,10 @@ knn_scan_kernel(const T* __restrict__ db, const float* __restrict__ inv, long lo
         if (MODE == SCAN_MAIN && tid < QP) { u64 k = args.thr_key[tid]; t = k == 0ull ? -CUDART_INF_F : unorder_f32((uint32_t)(k >> 32)); }
         sh.thr[tid] = t;
     }
+    if ((tid & 31) == 0) {
+        for (int s = 0; s < NST; s++) mbar_init(&sh.full[tid >> 5][s], 1);
+        fence_barrier_init();
+    }
     __syncthreads();
     u64 best[QP];                                  // SAMPLE: running maximum key of the rows this lane owns
 #pragma unroll
@@ -213,16 +224,31 @@ knn_scan_kernel(const T* __restrict__ db, const float* __restrict__ inv, long lo
     const bool owner = (lane & (32 / R - 1)) == 0;
     const long long ngroups = (n + R - 1) / R;
     const long long nsteps = (ngroups + gstride - 1) / gstride;
-    for (long long gs = (long long)blockIdx.x * SCAN_WARPS + warp; gs < nsteps; gs += (long long)gridDim.x * SCAN_WARPS) {
-        const long long row0 = gs * gstride * R;
+    const long long gs0 = (long long)blockIdx.x * SCAN_WARPS + warp, gstep = (long long)gridDim.x * SCAN_WARPS;
+    const long long nit = gs0 < nsteps ? (nsteps - gs0 + gstep - 1) / gstep : 0;
+    uint64_t* bars = sh.full[warp];
+    auto issue = [&](long long i) {                 // lane 0: one bulk copy of the (valid part of the) i-th row group of this warp
+        const long long row0 = (gs0 + i * gstep) * gstride * R;
+        const long long nrows = n - row0 < R ? n - row0 : R;
+        const uint32_t bytes = (uint32_t)(nrows * D * (long long)sizeof(T));
+        const int s = (int)(i % NST);
+        mbar_expect_tx(&bars[s], bytes);
+        bulk_load(ring + s * STAGE_BYTES, db + (size_t)row0 * D, bytes, &bars[s]);
+    };
+    if (lane == 0) for (long long i = 0; i < NST && i < nit; i++) issue(i);
+    for (long long it = 0; it < nit; it++) {
+        const long long row0 = (gs0 + it * gstep) * gstride * R;
+        const int s = (int)(it % NST);
+        mbar_wait(&bars[s], (uint32_t)((it / NST) & 1));
         uint4 raw[R][NV];
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            long long row = row0 + r; row = row < n ? row : n - 1;
-            const uint4* p = reinterpret_cast<const uint4*>(db + (size_t)row * D);
+            const uint4* p = reinterpret_cast<const uint4*>(ring + s * STAGE_BYTES + r * D * (int)sizeof(T));
 #pragma unroll
-            for (int v = 0; v < NV; v++) raw[r][v] = ldg_stream(p + v * 32 + lane);
+            for (int v = 0; v < NV; v++) raw[r][v] = p[v * 32 + lane];
         }
+        __syncwarp();                                // every lane has its rows in registers: the stage can be refilled
+        if (lane == 0 && it + NST < nit) { fence_proxy_async(); issue(it + NST); }
         const long long myrow = row0 + rsel;
         const bool valid = owner && myrow < n;
         const float myinv = valid ? __ldg(inv + myrow) : 0.f;
@@ -469,8 +495,12 @@ namespace {
 
 template <typename T, int D, int QP, int R, int MODE>
 int launch_scan(rdm_knn* h, const float* q, int nq_valid, ScanArgs args, cudaStream_t st, int* grid_out) {
-    auto kern = knn_scan_kernel<T, D, QP, R, MODE>;
-    size_t smem = (size_t)QP * D * sizeof(float);
+    constexpr int STAGE = R * D * (int)sizeof(T);
+    constexpr int QBYTES = QP * D * (int)sizeof(float);
+    constexpr int NST = (QBYTES + 3 * SCAN_WARPS * STAGE + 8192 <= 232448) ? 3 : 2;      // 227 KB of shared memory per CTA
+    static_assert(QBYTES + NST * SCAN_WARPS * STAGE + 8192 <= 232448, "scan shared-memory budget");
+    auto kern = knn_scan_kernel<T, D, QP, R, MODE, NST>;
+    size_t smem = (size_t)QBYTES + (size_t)NST * SCAN_WARPS * STAGE;
     static thread_local int cached_grid[8] = {0};   // per device
     int& grid = cached_grid[h->device & 7];
     if (grid == 0) {
@@ -521,7 +551,9 @@ int search_pass(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_out,
 
 template <typename T, int D>
 int search_typed(rdm_knn* h, const float* q, int nq, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st) {
-    constexpr int R = (128 / (D / 32)) >= 8 ? 8 : 4;     // keep R * D/32 <= 128 registers of row data per lane
+    // rows per group: <= 8 KB per ring stage and <= 128 registers of row data per lane
+    constexpr int RB = 8192 / (D * (int)sizeof(T)), RR = 128 / (D / 32);
+    constexpr int R = (RB >= 8 && RR >= 8) ? 8 : (RB >= 4 && RR >= 4) ? 4 : 2;
     for (int q0 = 0; q0 < nq; q0 += MAX_QP) {
         int cnt = nq - q0 < MAX_QP ? nq - q0 : MAX_QP;
         const float* qp = q + (size_t)q0 * D;
