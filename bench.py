@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--mode", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--mode", default="bf16x3", choices=["bf16x3", "bf16", "fp32", "fp16x2", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -170,7 +170,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    mode = {"fp32": 0, "bf16x3": 1, "bf16": 2}[args.mode]
+    mode = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp16x2": 3, "fp16": 4}[args.mode]
 
     # ---- resident state: DB (replicated per GPU: 1.31 GB fp16), weights, schedule tables
     g = torch.Generator(device=dev).manual_seed(1)
@@ -263,7 +263,9 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16x3": "bf16x3 (hi/lo-split bf16 operands on tcgen05, fp32 accumulate; fp32 norms/softmax)", "bf16": "bf16", "fp32": "f32"}[args.mode],
+        "dtype": {"bf16x3": "bf16x3 (hi/lo-split bf16 operands on tcgen05, fp32 accumulate; fp32 norms/softmax)", "bf16": "bf16", "fp32": "f32",
+                  "fp16x2": "fp16x2 (fp16 activations x hi/lo-split fp16 weights on tcgen05, fp32 accumulate; fp32 norms/softmax)",
+                  "fp16": "fp16 (fp16 operands on tcgen05, fp32 accumulate; fp32 norms/softmax)"}[args.mode],
         "data": "synthetic",
         "config": {"workload": "cfg2: RDM ImageNet-arch U-Net (400.9M params) on 32x32x4 latent, DDIM-100, CFG 2.0, k=4 exact kNN over 1,281,167x512 fp16 DB",
                    "batch_per_gpu": BATCH, "global_batch": BATCH * world, "ddim_steps": S_DDIM, "k_nn": K_NN, "parallelism": f"dp{world} (images sharded by batch, DB replicated)",

@@ -97,7 +97,9 @@ typedef struct rdm_unet_cfg {
 
 #define RDM_UNET_MODE_FP32 0        /* every contraction in fp32 on CUDA cores (strict parity mode) */
 #define RDM_UNET_MODE_TC_BF16X3 1   /* tcgen05: operands split into bf16 hi+lo, 3 MMAs per product (fp32-grade, default for parity) */
-#define RDM_UNET_MODE_TC_BF16 2     /* tcgen05: plain bf16 operands, fp32 accumulation (fastest, ~1e-2 relative) */
+#define RDM_UNET_MODE_TC_BF16 2     /* tcgen05: plain bf16 operands, fp32 accumulation (~6e-3 on DDIM-100 latents: outside the tolerance) */
+#define RDM_UNET_MODE_TC_FP16X2 3   /* tcgen05: fp16 activations x (fp16 hi + lo) weights, 2 MMAs per product */
+#define RDM_UNET_MODE_TC_FP16 4     /* tcgen05: plain fp16 operands (11-bit significand), 1 MMA per product */
 
 RDM_API int rdm_unet_create(rdm_unet_t** out, const rdm_unet_cfg* cfg, int32_t device);
 RDM_API void rdm_unet_destroy(rdm_unet_t* h);

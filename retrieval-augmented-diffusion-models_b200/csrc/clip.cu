@@ -48,14 +48,7 @@ __global__ void patchify_kernel(const float* __restrict__ img, int R, int P, int
     int k = v * 4, c = k / (P * P), ky = (k / P) % P, kx = k % P;           // P % 4 == 0: the 4 elements share (c, ky)
     const float4 q = *reinterpret_cast<const float4*>(img + (((size_t)b * 3 + c) * R + gy * P + ky) * R + gx * P + kx);
     if (y.f) *reinterpret_cast<float4*>(y.f + m * y.ldf + k) = q;
-    if (y.hi) {
-        const float e[4] = {q.x, q.y, q.z, q.w};
-        __nv_bfloat16 h[4], l[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) { h[t] = __float2bfloat16_rn(e[t]); l[t] = __float2bfloat16_rn(e[t] - __bfloat162float(h[t])); }
-        *reinterpret_cast<uint2*>(y.hi + m * y.ldb + k) = *reinterpret_cast<uint2*>(h);
-        if (y.lo) *reinterpret_cast<uint2*>(y.lo + m * y.ldb + k) = *reinterpret_cast<uint2*>(l);
-    }
+    if (y.hi) store_planes4(y.hi + m * y.ldb + k, y.lo ? y.lo + m * y.ldb + k : nullptr, y.f16, q.x, q.y, q.z, q.w);
 }
 // x[b,0,:] = class + pos[0];  x[b,1+g,:] = patch[b*G2+g,:] + pos[1+g]
 __global__ void assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos, int T, int W,
@@ -107,10 +100,14 @@ struct LayerW { float *ln1g, *ln1b, *inw, *inb, *ow, *ob, *ln2g, *ln2b, *fcw, *f
 struct Tower { int W = 0, heads = 0, L = 0, T = 0; std::vector<LayerW> layers; };
 
 struct Opnd {
-    View f; __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; int ldb = 0;
+    View f; __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; int ldb = 0; int f16 = 0;
     bool tc() const { return hi != nullptr; }
-    Out4 out4() const { return tc() ? Out4(hi, lo, ldb) : Out4(f); }
+    Out4 out4() const { return tc() ? Out4(hi, lo, ldb, f16) : Out4(f); }
 };
+inline int mode_nsplit(int m) { return m == RDM_UNET_MODE_TC_BF16X3 ? 3 : m == RDM_UNET_MODE_TC_FP16X2 ? 2 : 1; }
+inline bool mode_a_split(int m) { return m == RDM_UNET_MODE_TC_BF16X3; }
+inline bool mode_w_split(int m) { return m == RDM_UNET_MODE_TC_BF16X3 || m == RDM_UNET_MODE_TC_FP16X2; }
+inline int mode_f16(int m) { return (m == RDM_UNET_MODE_TC_FP16X2 || m == RDM_UNET_MODE_TC_FP16) ? 1 : 0; }
 
 }  // namespace
 
@@ -175,8 +172,8 @@ View fresh(Clip* n, int M, int C) { return View((float*)wsalloc(n, (size_t)M * C
 Opnd fresh_opnd(Clip* n, int M, int C, bool tc) {
     Opnd o; if (!tc) { o.f = fresh(n, M, C); return o; }
     o.hi = (__nv_bfloat16*)wsalloc(n, (size_t)M * C * 2);
-    if (n->mode == RDM_UNET_MODE_TC_BF16X3) o.lo = (__nv_bfloat16*)wsalloc(n, (size_t)M * C * 2);
-    o.ldb = C; o.f.C = C; return o;
+    if (mode_a_split(n->mode)) o.lo = (__nv_bfloat16*)wsalloc(n, (size_t)M * C * 2);
+    o.ldb = C; o.f.C = C; o.f16 = mode_f16(n->mode); return o;
 }
 Opnd from_view(View v) { Opnd o; o.f = v; return o; }
 bool tc_ok(Clip* n, int K) { return n->mode != RDM_UNET_MODE_FP32 && K % 64 == 0; }
@@ -187,10 +184,10 @@ void gemm(Run& r, const Opnd& a, int M, int K, const float* w, const float* bias
     e.bias = bias;
     if (a.tc()) {
         TcA ta; ta.hi = a.hi; ta.lo = a.lo; ta.ld = a.ldb; ta.B = M; ta.H = 1; ta.W = 1; ta.C = K; ta.ksize = 1;
-        TcW tw; tw.hi = n->wb_hi + (w - n->wbase); tw.lo = n->mode == RDM_UNET_MODE_TC_BF16X3 ? n->wb_lo + (w - n->wbase) : nullptr; tw.N = N; tw.K = K; tw.ld = K;
-        const int ns = n->mode == RDM_UNET_MODE_TC_BF16X3 ? 3 : 1;
-        if (out.tc()) { e.out = nullptr; RUN(gemm_tc(ta, tw, e, out.hi, out.lo, out.ldb, ns, r.st)); }
-        else { e.out = out.f.p; e.out_ld = out.f.ld; RUN(gemm_tc(ta, tw, e, nullptr, nullptr, 0, ns, r.st)); }
+        TcW tw; tw.hi = n->wb_hi + (w - n->wbase); tw.lo = mode_w_split(n->mode) ? n->wb_lo + (w - n->wbase) : nullptr; tw.N = N; tw.K = K; tw.ld = K;
+        const int ns = mode_nsplit(n->mode), f16 = mode_f16(n->mode);
+        if (out.tc()) { e.out = nullptr; RUN(gemm_tc(ta, tw, e, out.hi, out.lo, out.ldb, ns, f16, r.st)); }
+        else { e.out = out.f.p; e.out_ld = out.f.ld; RUN(gemm_tc(ta, tw, e, nullptr, nullptr, 0, ns, f16, r.st)); }
         return;
     }
     GemmA ga; ga.x = a.f.p; ga.ld = a.f.ld; ga.B = M; ga.Cin = K;
@@ -242,7 +239,7 @@ int ensure_planes(Clip* n, cudaStream_t st) {
     if (n->mode == RDM_UNET_MODE_FP32 || !n->planes_dirty) return RDM_OK;
     if (!n->wb_hi) RDM_CHECK_CUDA(cudaMalloc((void**)&n->wb_hi, n->wfloats * 2));
     if (!n->wb_lo) RDM_CHECK_CUDA(cudaMalloc((void**)&n->wb_lo, n->wfloats * 2));
-    RDM_TRY(k_split_planes(View(n->wbase, 64, 64), (long long)(n->wfloats / 64), Out4(n->wb_hi, n->wb_lo, 64), st));
+    RDM_TRY(k_split_planes(View(n->wbase, 64, 64), (long long)(n->wfloats / 64), Out4(n->wb_hi, n->wb_lo, 64, mode_f16(n->mode)), st));
     n->planes_dirty = false;
     return RDM_OK;
 }
@@ -279,7 +276,7 @@ const char* rdm_clip_param_name(const rdm_clip_t* n, int64_t i) { return (n && i
 int64_t rdm_clip_param_numel(const rdm_clip_t* n, const char* name) { if (!n || !name) return -1; auto it = n->params.find(name); return it == n->params.end() ? -1 : (int64_t)it->second.numel; }
 int64_t rdm_clip_missing(const rdm_clip_t* n) { return n ? missing(n) : -1; }
 int rdm_clip_set_mode(rdm_clip_t* n, int32_t mode) {
-    RDM_REQUIRE(n && mode >= 0 && mode <= 2, RDM_ERR_ARG, "rdm_clip_set_mode: bad argument");
+    RDM_REQUIRE(n && mode >= 0 && mode <= RDM_UNET_MODE_TC_FP16, RDM_ERR_ARG, "rdm_clip_set_mode: bad argument");
     if (mode != n->mode) n->planes_dirty = true;
     n->mode = mode; return RDM_OK;
 }

@@ -40,8 +40,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 // instruction descriptor: D fp32, A/B bf16, both K-major, M=128
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// a/b format field: 0 = F16, 1 = BF16
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int N, int f16 = 0) {
+    return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -82,13 +83,14 @@ struct TcKernelParams {
     const float* bias; const float* rowvec; int rowvec_ld; int rows_per_batch;
     const float* res; int res_ld; int act;
     float* out; int out_ld;                                // fp32 output (or null)
-    __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_bf_ld;   // bf16-plane output (or null)
+    __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_bf_ld;   // 16-bit-plane output (or null)
+    int f16;                                                       // planes are IEEE fp16 instead of bf16
 };
 
 template <int BN, int NSPLIT, int STAGES>
 struct TcSmem {
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
+    static constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * A_BYTES + (NSPLIT >= 2 ? 2 : 1) * B_BYTES;   // [A_hi][B_hi][B_lo?][A_lo?]
     static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;      // per-epilogue-warp transpose tiles
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
     static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
@@ -103,17 +105,6 @@ struct TcSmem {
 // result written as [4 or 8 rows] x [128 B | 64 B] per instruction instead of 32 rows x 16 B.
 constexpr int EPI_LD = 36;                         // floats per staged row (32 + 4 pad: conflict-free float4 rows)
 constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
-
-__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* hi, __nv_bfloat16* lo, float a, float b, float c, float d) {
-    __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b), h2 = __float2bfloat16_rn(c), h3 = __float2bfloat16_rn(d);
-    __nv_bfloat162 p0 = __halves2bfloat162(h0, h1), p1 = __halves2bfloat162(h2, h3);
-    *reinterpret_cast<uint2*>(hi) = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
-    if (lo) {
-        __nv_bfloat162 q0 = __halves2bfloat162(__float2bfloat16_rn(a - __bfloat162float(h0)), __float2bfloat16_rn(b - __bfloat162float(h1)));
-        __nv_bfloat162 q1 = __halves2bfloat162(__float2bfloat16_rn(c - __bfloat162float(h2)), __float2bfloat16_rn(d - __bfloat162float(h3)));
-        *reinterpret_cast<uint2*>(lo) = make_uint2(*reinterpret_cast<uint32_t*>(&q0), *reinterpret_cast<uint32_t*>(&q1));
-    }
-}
 
 // r: this lane's 32 accumulators (row m_warp0 + lane, columns nb..nb+31); stage: this warp's smem tile.
 __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const uint32_t (&r)[32], float* stage, int lane, int m_warp0, int nb) {
@@ -138,9 +129,9 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
                     if (p.res) t += p.res[(size_t)m * p.res_ld + n];
                     if (p.out) p.out[(size_t)m * p.out_ld + n] = t;
                     else {
-                        __nv_bfloat16 h = __float2bfloat16_rn(t);
-                        p.out_hi[(size_t)m * p.out_bf_ld + n] = h;
-                        if (p.out_lo) p.out_lo[(size_t)m * p.out_bf_ld + n] = __float2bfloat16_rn(t - __bfloat162float(h));
+                        unsigned short h, l; split16(t, p.f16, h, l);
+                        reinterpret_cast<unsigned short*>(p.out_hi)[(size_t)m * p.out_bf_ld + n] = h;
+                        if (p.out_lo) reinterpret_cast<unsigned short*>(p.out_lo)[(size_t)m * p.out_bf_ld + n] = l;
                     }
                 }
             }
@@ -191,7 +182,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
         if (rr < 32 && mo < p.M) {
             float4 o = make_float4(t[it].x + q[it].x, t[it].y + q[it].y, t[it].z + q[it].z, t[it].w + q[it].w);
             if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)mo * p.out_ld + no + cg) = o;
-            else store_bf16x4(p.out_hi + (size_t)mo * p.out_bf_ld + no + cg, p.out_lo ? p.out_lo + (size_t)mo * p.out_bf_ld + no + cg : nullptr, o.x, o.y, o.z, o.w);
+            else store_planes4(p.out_hi + (size_t)mo * p.out_bf_ld + no + cg, p.out_lo ? p.out_lo + (size_t)mo * p.out_bf_ld + no + cg : nullptr, p.f16, o.x, o.y, o.z, o.w);
         }
     }
 }
@@ -218,7 +209,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmB_hi);
-        if (NSPLIT == 3) { prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_lo); }
+        if (NSPLIT >= 2) prefetch_tmap(&tmB_lo);
+        if (NSPLIT == 3) prefetch_tmap(&tmA_lo);
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         fence_barrier_init();
@@ -252,16 +244,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const int dy = p.ksize == 3 ? tap / 3 - 1 : 0, dx = p.ksize == 3 ? tap % 3 - 1 : 0;
                     tma_load_4d(st, &tmA_hi, &full[s], kc, x0 + dx, y0 + dy, b0);
                     tma_load_2d(st + S::A_BYTES, &tmB_hi, &full[s], kb * BK, n0);
-                    if (NSPLIT == 3) {
-                        tma_load_4d(st + S::A_BYTES + S::B_BYTES, &tmA_lo, &full[s], kc, x0 + dx, y0 + dy, b0);
-                        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmB_lo, &full[s], kb * BK, n0);
-                    }
+                    if (NSPLIT >= 2) tma_load_2d(st + S::A_BYTES + S::B_BYTES, &tmB_lo, &full[s], kb * BK, n0);
+                    if (NSPLIT == 3) tma_load_4d(st + S::A_BYTES + 2 * S::B_BYTES, &tmA_lo, &full[s], kc, x0 + dx, y0 + dy, b0);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BN);
+            const uint32_t idesc = umma_idesc_bf16(BN, p.f16);
             int it = 0, lt = 0;                                          // ring position, local tile counter
             for (int item = blockIdx.x; item < nitems; item += gridDim.x, lt++) {
                 const int sp = item % p.splits;
@@ -275,15 +265,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES), b_hi = a_hi + S::A_BYTES;
-                    const uint32_t a_lo = b_hi + S::B_BYTES, b_lo = a_lo + S::A_BYTES;
+                    const uint32_t b_lo = b_hi + S::B_BYTES, a_lo = b_lo + S::B_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / 16; k++) {
                         const uint64_t da = umma_desc_sw128(a_hi + k * 32), db = umma_desc_sw128(b_hi + k * 32);
                         umma_bf16(tmem_d, da, db, idesc, ((kb - kb0) | k) != 0);
-                        if (NSPLIT == 3) {
-                            umma_bf16(tmem_d, umma_desc_sw128(a_lo + k * 32), db, idesc, 1);
-                            umma_bf16(tmem_d, da, umma_desc_sw128(b_lo + k * 32), idesc, 1);
-                        }
+                        if (NSPLIT >= 2) umma_bf16(tmem_d, da, umma_desc_sw128(b_lo + k * 32), idesc, 1);
+                        if (NSPLIT == 3) umma_bf16(tmem_d, umma_desc_sw128(a_lo + k * 32), db, idesc, 1);
                     }
                     umma_commit(&empty[s]);                // frees the stage once the MMAs above have read it
                 }
@@ -346,10 +334,9 @@ __global__ void splitk_reduce_kernel(const TcKernelParams p) {
         if (p.res) { o0 += p.res[(size_t)m * p.res_ld + no]; o1 += p.res[(size_t)m * p.res_ld + no + 1]; }
         if (p.out) *reinterpret_cast<float2*>(p.out + (size_t)m * p.out_ld + no) = make_float2(o0, o1);
         else {
-            __nv_bfloat16 h0 = __float2bfloat16_rn(o0), h1 = __float2bfloat16_rn(o1);
-            *reinterpret_cast<__nv_bfloat162*>(p.out_hi + (size_t)m * p.out_bf_ld + no) = __halves2bfloat162(h0, h1);
-            if (p.out_lo) *reinterpret_cast<__nv_bfloat162*>(p.out_lo + (size_t)m * p.out_bf_ld + no) =
-                __halves2bfloat162(__float2bfloat16_rn(o0 - __bfloat162float(h0)), __float2bfloat16_rn(o1 - __bfloat162float(h1)));
+            unsigned short h0, l0, h1, l1; split16(o0, p.f16, h0, l0); split16(o1, p.f16, h1, l1);
+            *reinterpret_cast<uint32_t*>(p.out_hi + (size_t)m * p.out_bf_ld + no) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            if (p.out_lo) *reinterpret_cast<uint32_t*>(p.out_lo + (size_t)m * p.out_bf_ld + no) = (uint32_t)l0 | ((uint32_t)l1 << 16);
         }
         return;
     }
@@ -360,7 +347,7 @@ __global__ void splitk_reduce_kernel(const TcKernelParams p) {
     }
     if (p.res) { float4 t = *reinterpret_cast<const float4*>(p.res + (size_t)m * p.res_ld + n); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
     if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)m * p.out_ld + n) = make_float4(v[0], v[1], v[2], v[3]);
-    else store_bf16x4(p.out_hi + (size_t)m * p.out_bf_ld + n, p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + n : nullptr, v[0], v[1], v[2], v[3]);
+    else store_planes4(p.out_hi + (size_t)m * p.out_bf_ld + n, p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + n : nullptr, p.f16, v[0], v[1], v[2], v[3]);
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -431,9 +418,9 @@ bool gemm_tc_supported(const TcA& a) {
     return (BM % (W * H)) == 0;
 }
 
-int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_bf_ld, int nsplit, cudaStream_t st) {
+int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_bf_ld, int nsplit, int f16, cudaStream_t st) {
     RDM_REQUIRE(gemm_tc_supported(a), RDM_ERR_UNSUPPORTED, "gemm_tc: shape not supported (C=%d W=%d H=%d ks=%d)", a.C, a.W, a.H, a.ksize);
-    RDM_REQUIRE(a.hi && w.hi && (nsplit == 1 || (a.lo && w.lo)), RDM_ERR_ARG, "gemm_tc: missing operand plane");
+    RDM_REQUIRE(nsplit >= 1 && nsplit <= 3 && a.hi && w.hi && (nsplit < 2 || w.lo) && (nsplit < 3 || a.lo), RDM_ERR_ARG, "gemm_tc: missing operand plane (nsplit %d)", nsplit);
     RDM_REQUIRE(w.K == a.ksize * a.ksize * a.C && w.ld % 8 == 0, RDM_ERR_ARG, "gemm_tc: weight K=%d vs %d", w.K, a.ksize * a.ksize * a.C);
     TcKernelParams p{};
     const int M = a.B * a.H * a.W;
@@ -453,7 +440,7 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     }
     p.bias = e.bias; p.rowvec = e.rowvec; p.rowvec_ld = e.rowvec_ld; p.rows_per_batch = e.rows_per_batch > 0 ? e.rows_per_batch : 1;
     p.res = e.res; p.res_ld = e.res_ld; p.act = e.act; p.out = e.out; p.out_ld = e.out_ld;
-    p.out_hi = out_hi; p.out_lo = out_lo; p.out_bf_ld = out_bf_ld;
+    p.out_hi = out_hi; p.out_lo = out_lo; p.out_bf_ld = out_bf_ld; p.f16 = f16;
     RDM_REQUIRE((p.out != nullptr) != (p.out_hi != nullptr), RDM_ERR_ARG, "gemm_tc: exactly one of fp32 / bf16 outputs");
     // Tile width and split-K.  The mainloop is operand-feed bound (TMA/L2 -> smem): one k-block of a work item costs ~(128 + BN)
     // (the 128-row A tile is re-loaded for every N tile); every item pays a fixed prologue/epilogue worth ~6 k-blocks.  Small-M layers
@@ -492,9 +479,14 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
         p.part = ws[dev & 15];
     }
     RDM_TRY(make_map_2d(&tb_hi, w.hi, w.K, w.N, w.ld, BN));
-    if (nsplit == 3) RDM_TRY(make_map_2d(&tb_lo, w.lo, w.K, w.N, w.ld, BN)); else tb_lo = tb_hi;
+    if (nsplit >= 2) RDM_TRY(make_map_2d(&tb_lo, w.lo, w.K, w.N, w.ld, BN)); else tb_lo = tb_hi;
     int rc;
-    if (nsplit == 3) {
+    if (nsplit == 2) {
+        if (BN == 192) rc = launch_tc<192, 2, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        else if (BN == 128) rc = launch_tc<128, 2, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        else if (BN == 64) rc = launch_tc<64, 2, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        else rc = launch_tc<32, 2, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+    } else if (nsplit == 3) {
         if (BN == 192) rc = launch_tc<192, 3, 2>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
         else if (BN == 128) rc = launch_tc<128, 3, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
         else if (BN == 64) rc = launch_tc<64, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);

@@ -12,6 +12,7 @@ struct TcW {                       // weights [N, K] K-major, K ordered (tap, ci
     int N = 0, K = 0;
 };
 bool gemm_tc_supported(const TcA& a);
-// nsplit 3: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-grade);  nsplit 1: A_hi*W_hi (bf16).
-// Output either fp32 (e.out) or bf16 planes (out_hi[/out_lo]); e.res / e.bias / e.rowvec / e.act as for gemm_simt.
-int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_bf_ld, int nsplit, cudaStream_t st);
+// nsplit 3: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-grade);  nsplit 2: A*W_hi + A*W_lo (single-plane A, split W);  nsplit 1: A*W.
+// f16: the 16-bit planes hold IEEE fp16 (11-bit significand) instead of bf16 (8-bit); kind::f16 MMA either way.
+// Output either fp32 (e.out) or 16-bit planes (out_hi[/out_lo], same format flag); e.res / e.bias / e.rowvec / e.act as for gemm_simt.
+int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_bf_ld, int nsplit, int f16, cudaStream_t st);

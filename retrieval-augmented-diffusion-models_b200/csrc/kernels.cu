@@ -14,18 +14,7 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); 
 // 4 consecutive channels of row m starting at column c (c % 4 == 0)
 __device__ __forceinline__ void store4(const Out4& o, size_t m, int c, float a, float b, float cc, float d) {
     if (o.f) *reinterpret_cast<float4*>(o.f + m * o.ldf + c) = make_float4(a, b, cc, d);
-    if (o.hi) {
-        __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b), h2 = __float2bfloat16_rn(cc), h3 = __float2bfloat16_rn(d);
-        __nv_bfloat162 p0 = __halves2bfloat162(h0, h1), p1 = __halves2bfloat162(h2, h3);
-        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-        *reinterpret_cast<uint2*>(o.hi + m * o.ldb + c) = pk;
-        if (o.lo) {
-            __nv_bfloat162 q0 = __halves2bfloat162(__float2bfloat16_rn(a - __bfloat162float(h0)), __float2bfloat16_rn(b - __bfloat162float(h1)));
-            __nv_bfloat162 q1 = __halves2bfloat162(__float2bfloat16_rn(cc - __bfloat162float(h2)), __float2bfloat16_rn(d - __bfloat162float(h3)));
-            uint2 pl; pl.x = *reinterpret_cast<uint32_t*>(&q0); pl.y = *reinterpret_cast<uint32_t*>(&q1);
-            *reinterpret_cast<uint2*>(o.lo + m * o.ldb + c) = pl;
-        }
-    }
+    if (o.hi) store_planes4(o.hi + m * o.ldb + c, o.lo ? o.lo + m * o.ldb + c : nullptr, o.f16, a, b, cc, d);
 }
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int Bsrc, int Bout, int C, int HW, float* __restrict__ out, int ld) {

@@ -16,12 +16,30 @@ struct View {            // [M, C] fp32 matrix view
 // Destination of an element-wise producer: fp32 view and/or bf16 hi(/lo) planes (x ~= hi + lo) for the tcgen05 engine.
 struct Out4 {
     float* f = nullptr; int ldf = 0;
-    __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; int ldb = 0;
+    __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; int ldb = 0;      // 16-bit planes: bf16, or IEEE fp16 bits when f16 != 0
+    int f16 = 0;
     __host__ __device__ Out4() {}
     Out4(View v) : f(v.p), ldf(v.ld) {}
-    Out4(__nv_bfloat16* h, __nv_bfloat16* l, int ld) : hi(h), lo(l), ldb(ld) {}
+    Out4(__nv_bfloat16* h, __nv_bfloat16* l, int ld, int f16_ = 0) : hi(h), lo(l), ldb(ld), f16(f16_) {}
     __host__ __device__ bool any() const { return f || hi; }
 };
+
+// 16-bit split of an fp32 value: hi = rn16(x), lo = rn16(x - hi); bf16 or fp16 (clamped to the finite fp16 range)
+__device__ __forceinline__ void split16(float x, int f16, unsigned short& hi, unsigned short& lo) {
+    if (f16) {
+        x = fminf(fmaxf(x, -65504.f), 65504.f);
+        __half h = __float2half_rn(x); hi = __half_as_ushort(h); lo = __half_as_ushort(__float2half_rn(x - __half2float(h)));
+    } else {
+        __nv_bfloat16 h = __float2bfloat16_rn(x); hi = __bfloat16_as_ushort(h); lo = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(h)));
+    }
+}
+// 4 consecutive values -> packed hi (and lo) 8-byte stores
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, int f16, float a, float b, float c, float d) {
+    unsigned short h[4], l[4];
+    split16(a, f16, h[0], l[0]); split16(b, f16, h[1], l[1]); split16(c, f16, h[2], l[2]); split16(d, f16, h[3], l[3]);
+    *reinterpret_cast<uint2*>(hi) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    if (lo) *reinterpret_cast<uint2*>(lo) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+}
 
 // ---- implicit-GEMM description: out[M,N] = epi( A[M,K] * W[N,K]^T ) -----------------------------
 struct GemmA {

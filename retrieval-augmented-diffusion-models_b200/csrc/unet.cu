@@ -251,9 +251,15 @@ struct Ctx { Net* n; cudaStream_t st; bool dry; int rc = RDM_OK; };
 struct Opnd {
     View f; __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; int ldb = 0;
     bool tc() const { return hi != nullptr; }
-    Out4 out4() const { return tc() ? Out4(hi, lo, ldb) : Out4(f); }
+    int f16 = 0;
+    Out4 out4() const { return tc() ? Out4(hi, lo, ldb, f16) : Out4(f); }
 };
 Opnd from_view(View v) { Opnd o; o.f = v; return o; }
+// engine configuration of a mode: MMAs per product, whether activations / weights carry a lo plane, fp16 vs bf16 planes
+inline int mode_nsplit(int m) { return m == RDM_UNET_MODE_TC_BF16X3 ? 3 : m == RDM_UNET_MODE_TC_FP16X2 ? 2 : 1; }
+inline bool mode_a_split(int m) { return m == RDM_UNET_MODE_TC_BF16X3; }
+inline bool mode_w_split(int m) { return m == RDM_UNET_MODE_TC_BF16X3 || m == RDM_UNET_MODE_TC_FP16X2; }
+inline int mode_f16(int m) { return (m == RDM_UNET_MODE_TC_FP16X2 || m == RDM_UNET_MODE_TC_FP16) ? 1 : 0; }
 
 double* stats_alloc(Ctx& cx, int B, int groups) {
     Net* n = cx.n; size_t need = (size_t)B * groups * 2;
@@ -265,8 +271,8 @@ Opnd fresh_opnd(Ctx& cx, int M, int C, bool tc) {
     Opnd o;
     if (!tc) { o.f = fresh(cx, M, C); return o; }
     o.hi = (__nv_bfloat16*)cx.n->arena.alloc((size_t)M * C * 2);
-    if (cx.n->mode == RDM_UNET_MODE_TC_BF16X3) o.lo = (__nv_bfloat16*)cx.n->arena.alloc((size_t)M * C * 2);
-    o.ldb = C; o.f.C = C;
+    if (mode_a_split(cx.n->mode)) o.lo = (__nv_bfloat16*)cx.n->arena.alloc((size_t)M * C * 2);
+    o.ldb = C; o.f.C = C; o.f16 = mode_f16(cx.n->mode);
     return o;
 }
 bool tc_ok(Ctx& cx, int B, int H, int W, int C, int ks) {
@@ -275,7 +281,7 @@ bool tc_ok(Ctx& cx, int B, int H, int W, int C, int ks) {
     return gemm_tc_supported(a);
 }
 const __nv_bfloat16* w_hi(Net* n, const float* w) { return n->wb_hi + (w - n->wbase); }
-const __nv_bfloat16* w_lo(Net* n, const float* w) { return n->mode == RDM_UNET_MODE_TC_BF16X3 ? n->wb_lo + (w - n->wbase) : nullptr; }
+const __nv_bfloat16* w_lo(Net* n, const float* w) { return mode_w_split(n->mode) ? n->wb_lo + (w - n->wbase) : nullptr; }
 
 // out = epi(conv/linear(a)).  a: [B*H*W, C] operand; ks 1|3 (stride 1, pad ks/2) on the tensor-core engine;
 // stride / ups only exist on the CUDA-core engine (the TC path materialises im2col / upsampled planes instead).
@@ -299,9 +305,9 @@ void gemm_any(Ctx& cx, const Opnd& a, int B, int H, int W, int C, int ks, int st
     if (a.tc()) {
         TcA ta; ta.hi = a.hi; ta.lo = a.lo; ta.ld = a.ldb; ta.B = B; ta.H = H; ta.W = W; ta.C = C; ta.ksize = ks;
         TcW tw; tw.hi = w_hi(n, w); tw.lo = w_lo(n, w); tw.N = N; tw.K = ks * ks * C; tw.ld = tw.K;
-        const int nsplit = n->mode == RDM_UNET_MODE_TC_BF16X3 ? 3 : 1;
-        if (out.tc()) { e.out = nullptr; RUN(gemm_tc(ta, tw, e, out.hi, out.lo, out.ldb, nsplit, cx.st)); }
-        else { e.out = out.f.p; e.out_ld = out.f.ld; RUN(gemm_tc(ta, tw, e, nullptr, nullptr, 0, nsplit, cx.st)); }
+        const int nsplit = mode_nsplit(n->mode), f16 = mode_f16(n->mode);
+        if (out.tc()) { e.out = nullptr; RUN(gemm_tc(ta, tw, e, out.hi, out.lo, out.ldb, nsplit, f16, cx.st)); }
+        else { e.out = out.f.p; e.out_ld = out.f.ld; RUN(gemm_tc(ta, tw, e, nullptr, nullptr, 0, nsplit, f16, cx.st)); }
         return;
     }
     GemmA ga; ga.x = a.f.p; ga.ld = a.f.ld; ga.B = B; ga.Hs = H; ga.Ws = W; ga.Cin = C; ga.ksize = ks; ga.stride = stride; ga.ups = ups; ga.Ho = Ho; ga.Wo = Wo;
@@ -511,7 +517,7 @@ int ensure_weight_planes(Net* n, cudaStream_t st) {
     if (n->mode == RDM_UNET_MODE_FP32 || !n->planes_dirty) return RDM_OK;
     if (!n->wb_hi) RDM_CHECK_CUDA(cudaMalloc((void**)&n->wb_hi, n->wfloats * 2));
     if (!n->wb_lo) RDM_CHECK_CUDA(cudaMalloc((void**)&n->wb_lo, n->wfloats * 2));
-    RDM_TRY(k_split_planes(View(n->wbase, 64, 64), (long long)(n->wfloats / 64), Out4(n->wb_hi, n->wb_lo, 64), st));
+    RDM_TRY(k_split_planes(View(n->wbase, 64, 64), (long long)(n->wfloats / 64), Out4(n->wb_hi, n->wb_lo, 64, mode_f16(n->mode)), st));
     n->planes_dirty = false;
     return RDM_OK;
 }
@@ -679,8 +685,7 @@ const char* rdm_unet_debug_log(const rdm_unet_t* n) { return n ? n->debug_log.c_
 
 int rdm_unet_set_mode(rdm_unet_t* n, int32_t mode) {
     RDM_REQUIRE(n, RDM_ERR_ARG, "rdm_unet_set_mode: null handle");
-    RDM_REQUIRE(mode == RDM_UNET_MODE_FP32 || mode == RDM_UNET_MODE_TC_BF16X3 || mode == RDM_UNET_MODE_TC_BF16, RDM_ERR_UNSUPPORTED,
-                "rdm_unet_set_mode: unknown mode %d", mode);
+    RDM_REQUIRE(mode >= RDM_UNET_MODE_FP32 && mode <= RDM_UNET_MODE_TC_FP16, RDM_ERR_UNSUPPORTED, "rdm_unet_set_mode: unknown mode %d", mode);
     if (mode != n->mode) { n->plan_B = 0; n->planes_dirty = true; }      // workspace layout depends on the engine
     n->mode = mode; return RDM_OK;
 }

@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from rdm_b200.unet import B200UNet, unet_param_shapes
 
-_MODES = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+_MODES = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp16x2": 3, "fp16": 4}
 
 
 def _set_param(root, dotted, tensor):

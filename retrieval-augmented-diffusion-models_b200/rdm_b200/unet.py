@@ -15,6 +15,9 @@ from . import _lib
 MODE_FP32 = 0          # every contraction fp32 on CUDA cores (strict)
 MODE_TC_BF16X3 = 1     # tcgen05, bf16 hi/lo split operands (fp32-grade)
 MODE_TC_BF16 = 2       # tcgen05, plain bf16 operands
+MODE_TC_FP16X2 = 3     # tcgen05, fp16 activations x (fp16 hi + lo) weights, 2 MMAs per product
+MODE_TC_FP16 = 4       # tcgen05, plain fp16 operands
+MODES = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp16x2": 3, "fp16": 4}
 
 
 class UNetCfg(ctypes.Structure):
