@@ -62,7 +62,7 @@ class UNetModel(nn.Module):
             else:
                 t = torch.zeros(shp)
             _set_param(self, name, t)
-        self.engine_mode = os.environ.get("RDM_B200_MODE", "bf16x3")
+        self.engine_mode = os.environ.get("RDM_B200_MODE", "fp16x2")   # 2.4e-4 on DDIM-100 latents (tools/ddim_error.py); "bf16x3" = strict
         self._engine, self._loaded_key, self._ctx_key, self._weight_override = None, None, None, None
 
     # ---- engine management -------------------------------------------------------------------------------

@@ -180,7 +180,7 @@ def test_no_cfg_path(cuda):
     assert rel_l2(got, want) < 1e-3
 
 
-@pytest.mark.parametrize("mode,tol", [(1, 1e-3)])
+@pytest.mark.parametrize("mode,tol", [(1, 1e-4), (3, 1e-3)])
 def test_full_arch_ddim20_tensor_core(cuda, mode, tol):
     """BASELINE cfg2 architecture, 20 chained CFG steps, one image: denoised latents within 1e-3 rel of the fp32 oracle."""
     ref, net = _pair(ounet.BASELINE_UNET, 3, cuda)
