@@ -130,6 +130,8 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count()
+    os.environ["OMP_NUM_THREADS"] = str(cores)          # torchrun pins it to 1; the reference arm may use every host thread
+    torch.set_num_threads(cores)
     vals = []
     for _ in range(args.warmup):
         cpu_reference_images_per_sec(1)
@@ -286,6 +288,7 @@ def main():
         "knn": {"ms": knn_ms, "qps": BATCH / knn_ms * 1e3, "gbs": knn_gbs, "frac_hbm": knn_gbs / pk["hbm_gbs"], "peak_gbs": pk["hbm_gbs"]},
     }
     if not args.no_cpu_baseline and world == 1:
+        torch.set_num_threads(os.cpu_count())
         v, info = cpu_reference_images_per_sec(4)
         line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": "4 DDIM steps (CFG, B2=2) of 1 image on the torch-CPU fp32 oracle + C kNN oracle over 100K rows, extrapolated to DDIM-100 / 1.28M rows",

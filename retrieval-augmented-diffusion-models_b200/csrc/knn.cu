@@ -19,6 +19,9 @@
 // Replaces ScaNN behind `searcher.search_batched` (dsetbuilder.py:490, ddpm.py:906-908).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "knn_tc.cuh"
+#include <type_traits>
+#include <cstdlib>
 #include "../../include/rdm_b200.h"
 #include <math_constants.h>
 
@@ -176,6 +179,7 @@ struct ScanArgs {
 
 // Rows reach the SM through per-warp shared-memory rings filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier): one elected
 // lane keeps NST groups of R rows (8 KB each) in flight per warp, decoupled from the registers that do the arithmetic.
+// NST == 0: rows are loaded straight into registers with 16-byte streaming loads (fp32 rows: a ring stage would be 16 KB per warp).
 template <typename T, int D, int QP, int R, int MODE, int NST>
 __global__ void __launch_bounds__(SCAN_THREADS)
 knn_scan_kernel(const T* __restrict__ db, const float* __restrict__ inv, long long n,
@@ -189,7 +193,7 @@ knn_scan_kernel(const T* __restrict__ db, const float* __restrict__ inv, long lo
     static_assert(EPL % EPV == 0 && EPL % 4 == 0, "row width");
     extern __shared__ float4 smem_q[];       // [QP][NC][32], permuted so lane l reads consecutive float4s; then the row rings
     __shared__ ScanShared sh;
-    uint8_t* ring = reinterpret_cast<uint8_t*>(smem_q + QP * NC * 32) + (size_t)(threadIdx.x >> 5) * NST * STAGE_BYTES;
+    uint8_t* ring = reinterpret_cast<uint8_t*>(smem_q + QP * NC * 32) + (size_t)(threadIdx.x >> 5) * (NST > 0 ? NST : 1) * STAGE_BYTES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < QP * NC * 32; i += SCAN_THREADS) {
@@ -210,7 +214,7 @@ knn_scan_kernel(const T* __restrict__ db, const float* __restrict__ inv, long lo
         if (MODE == SCAN_MAIN && tid < QP) { u64 k = args.thr_key[tid]; t = k == 0ull ? -CUDART_INF_F : unorder_f32((uint32_t)(k >> 32)); }
         sh.thr[tid] = t;
     }
-    if ((tid & 31) == 0) {
+    if (NST > 0 && (tid & 31) == 0) {
         for (int s = 0; s < NST; s++) mbar_init(&sh.full[tid >> 5][s], 1);
         fence_barrier_init();
     }
@@ -231,24 +235,34 @@ knn_scan_kernel(const T* __restrict__ db, const float* __restrict__ inv, long lo
         const long long row0 = (gs0 + i * gstep) * gstride * R;
         const long long nrows = n - row0 < R ? n - row0 : R;
         const uint32_t bytes = (uint32_t)(nrows * D * (long long)sizeof(T));
-        const int s = (int)(i % NST);
+        const int s = (int)(i % (NST > 0 ? NST : 1));
         mbar_expect_tx(&bars[s], bytes);
         bulk_load(ring + s * STAGE_BYTES, db + (size_t)row0 * D, bytes, &bars[s]);
     };
-    if (lane == 0) for (long long i = 0; i < NST && i < nit; i++) issue(i);
+    if (NST > 0 && lane == 0) for (long long i = 0; i < NST && i < nit; i++) issue(i);
     for (long long it = 0; it < nit; it++) {
         const long long row0 = (gs0 + it * gstep) * gstride * R;
-        const int s = (int)(it % NST);
-        mbar_wait(&bars[s], (uint32_t)((it / NST) & 1));
         uint4 raw[R][NV];
+        if (NST > 0) {
+            const int s = (int)(it % (NST > 0 ? NST : 1));
+            mbar_wait(&bars[s], (uint32_t)((it / (NST > 0 ? NST : 1)) & 1));
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const uint4* p = reinterpret_cast<const uint4*>(ring + s * STAGE_BYTES + r * D * (int)sizeof(T));
+            for (int r = 0; r < R; r++) {
+                const uint4* p = reinterpret_cast<const uint4*>(ring + s * STAGE_BYTES + r * D * (int)sizeof(T));
 #pragma unroll
-            for (int v = 0; v < NV; v++) raw[r][v] = p[v * 32 + lane];
+                for (int v = 0; v < NV; v++) raw[r][v] = p[v * 32 + lane];
+            }
+            __syncwarp();                            // every lane has its rows in registers: the stage can be refilled
+            if (lane == 0 && it + NST < nit) { fence_proxy_async(); issue(it + NST); }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                long long row = row0 + r; row = row < n ? row : n - 1;
+                const uint4* p = reinterpret_cast<const uint4*>(db + (size_t)row * D);
+#pragma unroll
+                for (int v = 0; v < NV; v++) raw[r][v] = ldg_stream(p + v * 32 + lane);
+            }
         }
-        __syncwarp();                                // every lane has its rows in registers: the stage can be refilled
-        if (lane == 0 && it + NST < nit) { fence_proxy_async(); issue(it + NST); }
         const long long myrow = row0 + rsel;
         const bool valid = owner && myrow < n;
         const float myinv = valid ? __ldg(inv + myrow) : 0.f;
@@ -488,6 +502,7 @@ struct rdm_knn {
     u64* cand = nullptr;       // [MAX_QP][CAND_CAP]
     u64* thr_key = nullptr;    // [MAX_QP]
     unsigned* cand_cnt = nullptr;   // [MAX_QP] + overflow flag at [MAX_QP]
+    void* qsplit = nullptr;         // fp16 hi/lo query rows for the tensor-core scan
     int max_grid = 0;
 };
 
@@ -497,7 +512,8 @@ template <typename T, int D, int QP, int R, int MODE>
 int launch_scan(rdm_knn* h, const float* q, int nq_valid, ScanArgs args, cudaStream_t st, int* grid_out) {
     constexpr int STAGE = R * D * (int)sizeof(T);
     constexpr int QBYTES = QP * D * (int)sizeof(float);
-    constexpr int NST = (QBYTES + 3 * SCAN_WARPS * STAGE + 8192 <= 232448) ? 3 : 2;      // 227 KB of shared memory per CTA
+    // 2-byte rows: TMA rings (3 stages if they fit next to the queries in 227 KB, else 2); 4-byte rows: direct loads
+    constexpr int NST = sizeof(T) == 4 ? 0 : ((QBYTES + 3 * SCAN_WARPS * STAGE + 8192 <= 232448) ? 3 : 2);
     static_assert(QBYTES + NST * SCAN_WARPS * STAGE + 8192 <= 232448, "scan shared-memory budget");
     auto kern = knn_scan_kernel<T, D, QP, R, MODE, NST>;
     size_t smem = (size_t)QBYTES + (size_t)NST * SCAN_WARPS * STAGE;
@@ -534,8 +550,18 @@ int search_pass(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_out,
     RDM_TRY((launch_scan<T, D, QP, R, SCAN_SAMPLE>(h, qp, cnt, a, st, &g0)));
     knn_threshold_kernel<<<QP, 1024, 0, st>>>(h->maxima, (size_t)g0 * SCAN_THREADS, h->thr_key, h->cand_cnt, overflow);
     RDM_COUNT_LAUNCH();
-    ScanArgs m{}; m.group_stride = 1; m.thr_key = h->thr_key; m.cand = h->cand; m.cand_cnt = h->cand_cnt;
-    RDM_TRY((launch_scan<T, D, QP, R, SCAN_MAIN>(h, qp, cnt, m, st, &g1)));
+    static const bool no_tc = getenv("RDM_KNN_NO_TC") != nullptr;
+    bool used_tc = false;
+    if constexpr (std::is_same<T, __half>::value && D == 512 && QP >= 8) {
+        if (!no_tc) {        // >= 5 queries: the FMA-bound CUDA-core scan is replaced by the tcgen05 scan (HBM-bound again)
+            RDM_TRY(knn_scan_tc(h->db, h->inv, h->n, h->device, qp, cnt, h->qsplit, h->thr_key, h->cand, h->cand_cnt, st));
+            used_tc = true;
+        }
+    }
+    if (!used_tc) {
+        ScanArgs m{}; m.group_stride = 1; m.thr_key = h->thr_key; m.cand = h->cand; m.cand_cnt = h->cand_cnt;
+        RDM_TRY((launch_scan<T, D, QP, R, SCAN_MAIN>(h, qp, cnt, m, st, &g1)));
+    }
     knn_select_kernel<T, D, false><<<cnt, 1024, 0, st>>>(h->cand, 0, QP, h->cand_cnt, overflow, (const T*)h->db, h->inv, h->n, qp, k, h->idx_base,
                                                          idx_out, dist_out, sc_out);
     RDM_COUNT_LAUNCH();
@@ -552,7 +578,7 @@ int search_pass(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_out,
 template <typename T, int D>
 int search_typed(rdm_knn* h, const float* q, int nq, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st) {
     // rows per group: <= 8 KB per ring stage and <= 128 registers of row data per lane
-    constexpr int RB = 8192 / (D * (int)sizeof(T)), RR = 128 / (D / 32);
+    constexpr int RB = sizeof(T) == 4 ? 8 : 8192 / (D * (int)sizeof(T)), RR = 128 / (D / 32);
     constexpr int R = (RB >= 8 && RR >= 8) ? 8 : (RB >= 4 && RR >= 4) ? 4 : 2;
     for (int q0 = 0; q0 < nq; q0 += MAX_QP) {
         int cnt = nq - q0 < MAX_QP ? nq - q0 : MAX_QP;
@@ -647,7 +673,8 @@ int rdm_knn_create(rdm_knn_t** out, const void* db, int64_t n, int32_t d, int32_
             cudaMalloc(&h->maxima, (size_t)h->max_grid * SCAN_THREADS * MAX_QP * sizeof(u64)) != cudaSuccess ||
             cudaMalloc(&h->cand, (size_t)MAX_QP * CAND_CAP * sizeof(u64)) != cudaSuccess ||
             cudaMalloc(&h->thr_key, (size_t)MAX_QP * sizeof(u64)) != cudaSuccess ||
-            cudaMalloc(&h->cand_cnt, (size_t)(MAX_QP + 1) * sizeof(unsigned)) != cudaSuccess) {
+            cudaMalloc(&h->cand_cnt, (size_t)(MAX_QP + 1) * sizeof(unsigned)) != cudaSuccess ||
+            cudaMalloc(&h->qsplit, (size_t)knn_tc_queries_bytes()) != cudaSuccess) {
             rdm_set_error("rdm_knn_create: workspace cudaMalloc failed"); rc = RDM_ERR_CUDA; break;
         }
         rc = do_create(h);
@@ -667,6 +694,7 @@ void rdm_knn_destroy(rdm_knn_t* h) {
     if (h->cand) cudaFree(h->cand);
     if (h->thr_key) cudaFree(h->thr_key);
     if (h->cand_cnt) cudaFree(h->cand_cnt);
+    if (h->qsplit) cudaFree(h->qsplit);
     delete h;
 }
 
