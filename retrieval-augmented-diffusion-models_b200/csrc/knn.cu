@@ -22,6 +22,7 @@
 #include "knn_tc.cuh"
 #include <type_traits>
 #include <cstdlib>
+#include <algorithm>
 #include "../../include/rdm_b200.h"
 #include <math_constants.h>
 
@@ -30,7 +31,8 @@ namespace {
 constexpr int LIST = 32;          // candidates kept per query (one per lane)
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
-constexpr int MAX_QP = 16;        // queries per scan pass
+constexpr int MAX_QP = 16;        // queries per CUDA-core scan pass
+constexpr int MAX_TCQ = 64;       // queries per tensor-core pass (fp16 databases)
 constexpr unsigned FULL = 0xffffffffu;
 typedef unsigned long long u64;
 
@@ -498,7 +500,8 @@ struct rdm_knn {
     void* db_owned = nullptr;      // device allocation when copied from host
     float* inv = nullptr;
     u64* lists = nullptr;      // fallback per-CTA lists
-    u64* maxima = nullptr;     // [MAX_QP][max_grid*SCAN_THREADS]
+    u64* maxima = nullptr;     // sample keys: [queries][per_q]
+    size_t maxima_keys = 0;
     u64* cand = nullptr;       // [MAX_QP][CAND_CAP]
     u64* thr_key = nullptr;    // [MAX_QP]
     unsigned* cand_cnt = nullptr;   // [MAX_QP] + overflow flag at [MAX_QP]
@@ -541,7 +544,7 @@ int launch_scan(rdm_knn* h, const float* q, int nq_valid, ScanArgs args, cudaStr
 
 template <typename T, int D, int QP, int R>
 int search_pass(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st) {
-    unsigned* overflow = h->cand_cnt + MAX_QP;
+    unsigned* overflow = h->cand_cnt + MAX_TCQ;
     const long long ngroups = (h->n + R - 1) / R;
     // sample ~1/16 of the row groups, but keep at least ~8K groups in the sample (small DBs are sampled densely)
     int stride = (int)(ngroups / 8192); if (stride > 16) stride = 16; if (stride < 1) stride = 1;
@@ -550,18 +553,8 @@ int search_pass(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_out,
     RDM_TRY((launch_scan<T, D, QP, R, SCAN_SAMPLE>(h, qp, cnt, a, st, &g0)));
     knn_threshold_kernel<<<QP, 1024, 0, st>>>(h->maxima, (size_t)g0 * SCAN_THREADS, h->thr_key, h->cand_cnt, overflow);
     RDM_COUNT_LAUNCH();
-    static const bool no_tc = getenv("RDM_KNN_NO_TC") != nullptr;
-    bool used_tc = false;
-    if constexpr (std::is_same<T, __half>::value && D == 512 && QP >= 8) {
-        if (!no_tc) {        // >= 5 queries: the FMA-bound CUDA-core scan is replaced by the tcgen05 scan (HBM-bound again)
-            RDM_TRY(knn_scan_tc(h->db, h->inv, h->n, h->device, qp, cnt, h->qsplit, h->thr_key, h->cand, h->cand_cnt, st));
-            used_tc = true;
-        }
-    }
-    if (!used_tc) {
-        ScanArgs m{}; m.group_stride = 1; m.thr_key = h->thr_key; m.cand = h->cand; m.cand_cnt = h->cand_cnt;
-        RDM_TRY((launch_scan<T, D, QP, R, SCAN_MAIN>(h, qp, cnt, m, st, &g1)));
-    }
+    ScanArgs m{}; m.group_stride = 1; m.thr_key = h->thr_key; m.cand = h->cand; m.cand_cnt = h->cand_cnt;
+    RDM_TRY((launch_scan<T, D, QP, R, SCAN_MAIN>(h, qp, cnt, m, st, &g1)));
     knn_select_kernel<T, D, false><<<cnt, 1024, 0, st>>>(h->cand, 0, QP, h->cand_cnt, overflow, (const T*)h->db, h->inv, h->n, qp, k, h->idx_base,
                                                          idx_out, dist_out, sc_out);
     RDM_COUNT_LAUNCH();
@@ -575,8 +568,46 @@ int search_pass(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_out,
     return RDM_OK;
 }
 
+// fp16 / d=512, >= 8 queries: sample + main scans on the tensor cores, up to 64 queries per pass.
+template <typename T, int D>
+int search_pass_tc(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st) {
+    constexpr int R = 8;
+    unsigned* overflow = h->cand_cnt + MAX_TCQ;
+    const long long ntiles = (h->n + 127) / 128;
+    int stride = (int)(ntiles / 512); if (stride > 16) stride = 16; if (stride < 1) stride = 1;       // >= ~64K sampled rows
+    const long long per_q = knn_tc_sample_rows(h->n, stride);
+    RDM_REQUIRE((size_t)per_q * cnt <= h->maxima_keys, RDM_ERR_STATE, "knn: sample buffer too small");
+    RDM_TRY(knn_scan_tc(h->db, h->inv, h->n, h->device, qp, cnt, h->qsplit, 1, stride, h->maxima, per_q, nullptr, nullptr, nullptr, st));
+    knn_threshold_kernel<<<cnt, 1024, 0, st>>>(h->maxima, (size_t)per_q, h->thr_key, h->cand_cnt, overflow);
+    RDM_COUNT_LAUNCH();
+    RDM_TRY(knn_scan_tc(h->db, h->inv, h->n, h->device, qp, cnt, h->qsplit, 0, 1, nullptr, 0, h->thr_key, h->cand, h->cand_cnt, st));
+    knn_select_kernel<T, D, false><<<cnt, 1024, 0, st>>>(h->cand, 0, 0, h->cand_cnt, overflow, (const T*)h->db, h->inv, h->n, qp, k, h->idx_base,
+                                                         idx_out, dist_out, sc_out);
+    RDM_COUNT_LAUNCH();
+    for (int g0 = 0; g0 < cnt; g0 += MAX_QP) {         // device-side conditional fallback, 16 queries per group (normally empty launches)
+        const int gc = cnt - g0 < MAX_QP ? cnt - g0 : MAX_QP; int g2 = 0;
+        ScanArgs f{}; f.group_stride = 1; f.lists_out = h->lists; f.overflow = overflow;
+        RDM_TRY((launch_scan<T, D, MAX_QP, R, SCAN_LOCKED>(h, qp + (size_t)g0 * D, gc, f, st, &g2)));
+        knn_select_kernel<T, D, true><<<gc, 1024, 0, st>>>(h->lists, g2, MAX_QP, h->cand_cnt, overflow, (const T*)h->db, h->inv, h->n, qp + (size_t)g0 * D, k,
+                                                           h->idx_base, idx_out + (size_t)g0 * k, dist_out + (size_t)g0 * k, sc_out ? sc_out + (size_t)g0 * k : nullptr);
+        RDM_COUNT_LAUNCH();
+    }
+    RDM_CHECK_CUDA(cudaGetLastError());
+    return RDM_OK;
+}
+
 template <typename T, int D>
 int search_typed(rdm_knn* h, const float* q, int nq, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st) {
+    if constexpr (std::is_same<T, __half>::value && D == 512) {
+        static const bool no_tc = getenv("RDM_KNN_NO_TC") != nullptr;
+        if (!no_tc && nq >= 8) {
+            for (int q0 = 0; q0 < nq; q0 += MAX_TCQ) {
+                int cnt = nq - q0 < MAX_TCQ ? nq - q0 : MAX_TCQ;
+                RDM_TRY((search_pass_tc<T, D>(h, q + (size_t)q0 * D, cnt, k, idx_out + (size_t)q0 * k, dist_out + (size_t)q0 * k, sc_out ? sc_out + (size_t)q0 * k : nullptr, st)));
+            }
+            return RDM_OK;
+        }
+    }
     // rows per group: <= 8 KB per ring stage and <= 128 registers of row data per lane
     constexpr int RB = sizeof(T) == 4 ? 8 : 8192 / (D * (int)sizeof(T)), RR = 128 / (D / 32);
     constexpr int R = (RB >= 8 && RR >= 8) ? 8 : (RB >= 4 && RR >= 4) ? 4 : 2;
@@ -668,12 +699,15 @@ int rdm_knn_create(rdm_knn_t** out, const void* db, int64_t n, int32_t d, int32_
             h->db = h->db_owned;
         }
         h->max_grid = rdm_num_sms(device) * 8;
+        const long long tc_tiles = (n + 127) / 128;
+        int tc_stride = (int)(tc_tiles / 512); if (tc_stride > 16) tc_stride = 16; if (tc_stride < 1) tc_stride = 1;
+        const long long tc_per_q = (dtype == RDM_DTYPE_F16 && d == 512) ? knn_tc_sample_rows(n, tc_stride) : 0;
         if (cudaMalloc(&h->inv, (size_t)n * sizeof(float)) != cudaSuccess ||
             cudaMalloc(&h->lists, (size_t)h->max_grid * MAX_QP * LIST * sizeof(u64)) != cudaSuccess ||
-            cudaMalloc(&h->maxima, (size_t)h->max_grid * SCAN_THREADS * MAX_QP * sizeof(u64)) != cudaSuccess ||
-            cudaMalloc(&h->cand, (size_t)MAX_QP * CAND_CAP * sizeof(u64)) != cudaSuccess ||
-            cudaMalloc(&h->thr_key, (size_t)MAX_QP * sizeof(u64)) != cudaSuccess ||
-            cudaMalloc(&h->cand_cnt, (size_t)(MAX_QP + 1) * sizeof(unsigned)) != cudaSuccess ||
+            cudaMalloc(&h->maxima, (h->maxima_keys = std::max((size_t)h->max_grid * SCAN_THREADS * MAX_QP, (size_t)tc_per_q * MAX_TCQ)) * sizeof(u64)) != cudaSuccess ||
+            cudaMalloc(&h->cand, (size_t)MAX_TCQ * CAND_CAP * sizeof(u64)) != cudaSuccess ||
+            cudaMalloc(&h->thr_key, (size_t)MAX_TCQ * sizeof(u64)) != cudaSuccess ||
+            cudaMalloc(&h->cand_cnt, (size_t)(MAX_TCQ + 1) * sizeof(unsigned)) != cudaSuccess ||
             cudaMalloc(&h->qsplit, (size_t)knn_tc_queries_bytes()) != cudaSuccess) {
             rdm_set_error("rdm_knn_create: workspace cudaMalloc failed"); rc = RDM_ERR_CUDA; break;
         }

@@ -1,4 +1,4 @@
-// Tensor-core main scan of the exact kNN for fp16 databases (d = 512) and 8..16 queries per pass.
+// Tensor-core scans (sample + main) of the exact kNN for fp16 databases (d = 512), 16 / 32 / 64 query columns per pass.
 //
 // With >= 8 queries the CUDA-core scan (knn.cu) is FMA-bound; here the 128-row database tile is the A operand of tcgen05.mma
 // straight from TMA (the stored fp16 rows are used as they are -- no conversion pass), the queries are the B operand, resident in
@@ -18,17 +18,22 @@
 namespace {
 
 typedef unsigned long long u64;
-constexpr int TM = 128, TK = 64, D = 512, KB = D / TK, NQ = 16, NCOL = 2 * NQ, STAGES = 8, THREADS = 192;
-constexpr int A_BYTES = TM * TK * 2, B_KB_BYTES = NCOL * TK * 2, B_BYTES = KB * B_KB_BYTES;
-constexpr int SMEM_TOTAL = STAGES * A_BYTES + B_BYTES + 1024 + 512;
+constexpr int TM = 128, TK = 64, D = 512, KB = D / TK, THREADS = 192;
+constexpr int A_BYTES = TM * TK * 2;
 constexpr int CAND_CAP = 2048;
+template <int NQ> struct Cfg {
+    static constexpr int NCOL = 2 * NQ, B_KB_BYTES = NCOL * TK * 2, B_BYTES = KB * B_KB_BYTES;
+    static constexpr int STAGES = NQ <= 16 ? 8 : NQ <= 32 ? 6 : 4;
+    static constexpr int SMEM_TOTAL = STAGES * A_BYTES + B_BYTES + 1024 + 1024;
+    static constexpr int TMEM_COLS = 2 * NCOL <= 64 ? 64 : 2 * NCOL <= 128 ? 128 : 256;
+};
 
 __device__ __forceinline__ uint32_t order_f32(float f) { uint32_t b = __float_as_uint(f); return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
 __device__ __forceinline__ float unorder_f32(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u); }
 __device__ __forceinline__ u64 make_key(float s, uint32_t idx) { return ((u64)order_f32(s) << 32) | (u64)(0xffffffffu - idx); }
 
 // q fp32 [nq, 512] -> fp16 rows [0, NQ) = hi, [NQ, 2 NQ) = lo (zero rows beyond nq)
-__global__ void split_queries_kernel(const float* __restrict__ q, int nq, __half* __restrict__ out) {
+__global__ void split_queries_kernel(const float* __restrict__ q, int nq, int NQ, __half* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NQ * D) return;
     int qi = i / D, c = i % D;
@@ -38,9 +43,14 @@ __global__ void split_queries_kernel(const float* __restrict__ q, int nq, __half
     out[(size_t)(NQ + qi) * D + c] = __float2half_rn(v - __half2float(h));
 }
 
+// SAMPLE: visits every `tile_stride`-th row tile and writes the key of EVERY (row, query) to maxima[q][sample_row] (per_q keys per
+// query; the threshold kernel takes the 32nd largest).  MAIN: all tiles, survivors of the threshold go to the candidate buffer.
+template <int NQ, bool SAMPLE>
 __global__ void __launch_bounds__(THREADS, 1)
 knn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ inv, long long n,
-                   int nq_valid, const u64* __restrict__ thr_key, u64* __restrict__ cand, unsigned* __restrict__ cand_cnt) {
+                   int nq_valid, const u64* __restrict__ thr_key, u64* __restrict__ cand, unsigned* __restrict__ cand_cnt,
+                   int tile_stride, u64* __restrict__ maxima, long long per_q) {
+    constexpr int NCOL = Cfg<NQ>::NCOL, B_KB_BYTES = Cfg<NQ>::B_KB_BYTES, B_BYTES = Cfg<NQ>::B_BYTES, STAGES = Cfg<NQ>::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sB = smem + STAGES * A_BYTES;
@@ -53,7 +63,9 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     float* s_thr = reinterpret_cast<float*>(tmem_slot + 1);           // [NQ]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long ntiles = (n + TM - 1) / TM;
+    const long long ntiles_all = (n + TM - 1) / TM;
+    const long long ntiles = SAMPLE ? (ntiles_all + tile_stride - 1) / tile_stride : ntiles_all;       // work items of this launch
+    const long long tmul = SAMPLE ? tile_stride : 1;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmB);
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -61,9 +73,9 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_init(b_full, 1);
         fence_barrier_init();
     }
-    if (threadIdx.x < NQ) { u64 k = thr_key[threadIdx.x]; s_thr[threadIdx.x] = k == 0ull ? -CUDART_INF_F : unorder_f32((uint32_t)(k >> 32)); }
+    if (!SAMPLE && threadIdx.x < NQ) { u64 k = thr_key[threadIdx.x]; s_thr[threadIdx.x] = k == 0ull ? -CUDART_INF_F : unorder_f32((uint32_t)(k >> 32)); }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg<NQ>::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -81,7 +93,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const int s = (int)(it % STAGES); const uint32_t ph = (uint32_t)((it / STAGES) & 1);
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], A_BYTES);
-                    tma_load_2d(smem + s * A_BYTES, &tmA, &full[s], kb * TK, (int)(tile * TM));
+                    tma_load_2d(smem + s * A_BYTES, &tmA, &full[s], kb * TK, (int)(tile * tmul * TM));
                 }
             }
         }
@@ -112,27 +124,54 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         int lt = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, lt++) {
             const int buf = lt & 1;
-            const long long row = tile * TM + q4 * 32 + lane;
+            const long long row = tile * tmul * TM + q4 * 32 + lane;
+            const long long srow = tile * TM + q4 * 32 + lane;                  // position in the sample (SAMPLE mode)
             mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
             tc_fence_after();
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NCOL), r);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
-            if (row < n) {
-                const float iv = __ldg(inv + row);
+            const float iv = row < n ? __ldg(inv + row) : 0.f;
+            // columns [0, NQ) = hi products, [NQ, 2 NQ) = lo products; processed 16 queries at a time (two 32-bit x16 halves)
+#pragma unroll 1
+            for (int q0 = 0; q0 < NQ; q0 += 16) {
+                uint32_t r[32];
+                {
+                    uint32_t rh[32];
+                    // hi block: columns q0..q0+15 ; lo block: NQ+q0 .. NQ+q0+15 (two x16 loads packed into one x32 array)
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(rh[0]), "=r"(rh[1]), "=r"(rh[2]), "=r"(rh[3]), "=r"(rh[4]), "=r"(rh[5]), "=r"(rh[6]), "=r"(rh[7]),
+                                   "=r"(rh[8]), "=r"(rh[9]), "=r"(rh[10]), "=r"(rh[11]), "=r"(rh[12]), "=r"(rh[13]), "=r"(rh[14]), "=r"(rh[15])
+                                 : "r"(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NCOL + q0)));
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(rh[16]), "=r"(rh[17]), "=r"(rh[18]), "=r"(rh[19]), "=r"(rh[20]), "=r"(rh[21]), "=r"(rh[22]), "=r"(rh[23]),
+                                   "=r"(rh[24]), "=r"(rh[25]), "=r"(rh[26]), "=r"(rh[27]), "=r"(rh[28]), "=r"(rh[29]), "=r"(rh[30]), "=r"(rh[31])
+                                 : "r"(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NCOL + NQ + q0)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int qi = 0; qi < NQ; qi++) {
-                    float s = (__uint_as_float(r[qi]) + __uint_as_float(r[NQ + qi])) * iv;
-                    if (!(s == s)) s = -CUDART_INF_F;
-                    if (qi < nq_valid && s >= s_thr[qi]) {
-                        const u64 key = make_key(s, (uint32_t)row);
-                        if (key >= thr_key[qi]) {
-                            unsigned pos = atomicAdd(&cand_cnt[qi], 1u);
-                            if (pos < (unsigned)CAND_CAP) cand[(size_t)qi * CAND_CAP + pos] = key;
+                    for (int j = 0; j < 32; j++) r[j] = rh[j];
+                }
+                if (q0 + 16 >= NQ) {                                            // last read of this accumulator: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+                }
+                if (row < n) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int qi = q0 + j;
+                        float s = (__uint_as_float(r[j]) + __uint_as_float(r[16 + j])) * iv;
+                        if (!(s == s)) s = -CUDART_INF_F;
+                        if (SAMPLE) {
+                            if (qi < nq_valid) maxima[(size_t)qi * per_q + srow] = make_key(s, (uint32_t)row);
+                        } else if (qi < nq_valid && s >= s_thr[qi]) {
+                            const u64 key = make_key(s, (uint32_t)row);
+                            if (key >= thr_key[qi]) {
+                                unsigned pos = atomicAdd(&cand_cnt[qi], 1u);
+                                if (pos < (unsigned)CAND_CAP) cand[(size_t)qi * CAND_CAP + pos] = key;
+                            }
                         }
                     }
+                } else if (SAMPLE && srow < per_q) {
+#pragma unroll 1
+                    for (int j = 0; j < 16; j++) if (q0 + j < nq_valid) maxima[(size_t)(q0 + j) * per_q + srow] = 0ull;
                 }
             }
         }
@@ -141,7 +180,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg<NQ>::TMEM_COLS) : "memory");
     }
 }
 
@@ -166,27 +205,45 @@ int make_map(CUtensorMap* tm, const void* base, long long rows, int box_rows) {
     return RDM_OK;
 }
 
-}  // namespace
 
-int knn_tc_queries_bytes() { return 2 * NQ * D * (int)sizeof(__half); }
-
-int knn_scan_tc(const void* db_f16, const float* inv, long long n, int device, const float* q, int nq_valid, void* qsplit_ws,
-                const unsigned long long* thr_key, unsigned long long* cand, unsigned* cand_cnt, cudaStream_t st) {
-    RDM_REQUIRE(nq_valid >= 1 && nq_valid <= NQ, RDM_ERR_ARG, "knn_scan_tc: %d queries", nq_valid);
-    split_queries_kernel<<<(NQ * D + 255) / 256, 256, 0, st>>>(q, nq_valid, (__half*)qsplit_ws);
-    RDM_COUNT_LAUNCH();
-    CUtensorMap ta, tb;
-    RDM_TRY(make_map(&ta, db_f16, n, TM));
-    RDM_TRY(make_map(&tb, qsplit_ws, NCOL, NCOL));
+template <int NQ, bool SAMPLE>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const float* inv, long long n, int device, int nq_valid, const u64* thr_key, u64* cand,
+           unsigned* cand_cnt, int tile_stride, u64* maxima, long long per_q, cudaStream_t st) {
+    auto kern = knn_scan_tc_kernel<NQ, SAMPLE>;
     static bool configured[16] = {false};
     if (!configured[device & 15]) {
-        RDM_CHECK_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NQ>::SMEM_TOTAL));
         configured[device & 15] = true;
     }
-    const long long ntiles = (n + TM - 1) / TM;
+    const long long ntiles_all = (n + TM - 1) / TM, items = SAMPLE ? (ntiles_all + tile_stride - 1) / tile_stride : ntiles_all;
     const int sms = rdm_num_sms(device);
-    knn_scan_tc_kernel<<<(int)(ntiles < sms ? ntiles : sms), THREADS, SMEM_TOTAL, st>>>(ta, tb, inv, n, nq_valid, thr_key, cand, cand_cnt);
+    kern<<<(int)(items < sms ? items : sms), THREADS, Cfg<NQ>::SMEM_TOTAL, st>>>(ta, tb, inv, n, nq_valid, thr_key, cand, cand_cnt, tile_stride, maxima, per_q);
     RDM_COUNT_LAUNCH();
     RDM_CHECK_CUDA(cudaGetLastError());
     return RDM_OK;
+}
+
+}  // namespace
+
+int knn_tc_queries_bytes() { return 2 * 64 * D * (int)sizeof(__half); }
+int knn_tc_pass_queries(int nq) { return nq <= 16 ? 16 : nq <= 32 ? 32 : 64; }
+long long knn_tc_sample_rows(long long n, int tile_stride) { long long t = (n + TM - 1) / TM; return ((t + tile_stride - 1) / tile_stride) * TM; }
+
+int knn_scan_tc(const void* db_f16, const float* inv, long long n, int device, const float* q, int nq_valid, void* qsplit_ws, int sample, int tile_stride,
+                unsigned long long* maxima, long long per_q, const unsigned long long* thr_key, unsigned long long* cand, unsigned* cand_cnt, cudaStream_t st) {
+    RDM_REQUIRE(nq_valid >= 1 && nq_valid <= 64, RDM_ERR_ARG, "knn_scan_tc: %d queries", nq_valid);
+    const int NQ = knn_tc_pass_queries(nq_valid);
+    if (sample) {                                     // the sample pass runs first: it also prepares the fp16 hi/lo query rows
+        split_queries_kernel<<<(NQ * D + 255) / 256, 256, 0, st>>>(q, nq_valid, NQ, (__half*)qsplit_ws);
+        RDM_COUNT_LAUNCH();
+    }
+    CUtensorMap ta, tb;
+    RDM_TRY(make_map(&ta, db_f16, n, TM));
+    RDM_TRY(make_map(&tb, qsplit_ws, 2 * NQ, 2 * NQ));
+#define KNN_TC_GO(NQV) (sample ? launch<NQV, true>(ta, tb, inv, n, device, nq_valid, thr_key, cand, cand_cnt, tile_stride, maxima, per_q, st) \
+                               : launch<NQV, false>(ta, tb, inv, n, device, nq_valid, thr_key, cand, cand_cnt, tile_stride, maxima, per_q, st))
+    if (NQ == 16) return KNN_TC_GO(16);
+    if (NQ == 32) return KNN_TC_GO(32);
+    return KNN_TC_GO(64);
+#undef KNN_TC_GO
 }

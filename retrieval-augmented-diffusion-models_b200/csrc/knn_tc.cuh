@@ -1,7 +1,10 @@
-// Tensor-core main scan for fp16 / d=512 databases (knn_tc.cu); same survivor-buffer contract as knn_scan_kernel<MAIN>.
+// Tensor-core scans for fp16 / d=512 databases (knn_tc.cu); same survivor-buffer contract as knn_scan_kernel<MAIN>.
 #pragma once
 #include <cuda_runtime.h>
 int knn_tc_queries_bytes();
-// q: fp32 [nq_valid, 512] normalised queries (device); qsplit_ws: knn_tc_queries_bytes() of device scratch.
-int knn_scan_tc(const void* db_f16, const float* inv, long long n, int device, const float* q, int nq_valid, void* qsplit_ws,
-                const unsigned long long* thr_key, unsigned long long* cand, unsigned* cand_cnt, cudaStream_t st);
+int knn_tc_pass_queries(int nq);                                  // 16, 32 or 64 query columns for a pass of nq <= 64 queries
+long long knn_tc_sample_rows(long long n, int tile_stride);       // keys per query written by the sample pass
+// sample != 0: every tile_stride-th 128-row tile, writes maxima[q][per_q] (and prepares qsplit_ws from q).
+// sample == 0: the main scan; survivors of thr_key go to cand / cand_cnt.  q: fp32 [nq_valid, 512] normalised queries (device).
+int knn_scan_tc(const void* db_f16, const float* inv, long long n, int device, const float* q, int nq_valid, void* qsplit_ws, int sample, int tile_stride,
+                unsigned long long* maxima, long long per_q, const unsigned long long* thr_key, unsigned long long* cand, unsigned* cand_cnt, cudaStream_t st);
