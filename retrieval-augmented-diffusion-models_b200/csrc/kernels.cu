@@ -149,30 +149,37 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ld, int C, int
     }
 }
 
-// Attention for d_head = DH (32: U-Net, 64: CLIP): one thread per query row, keys/values of one (batch, head) staged through
-// shared memory in tiles of KT keys (broadcast reads), online softmax in fp32.  grid (ceil(Nq/blockDim), heads, B).
-// causal: key j contributes to query i only if j <= i.
+// Attention for d_head = DH (32: U-Net, 64: CLIP): a thread owns RQ query rows, keys/values of one (batch, head) are staged through
+// shared memory in tiles of KT keys and read as broadcasts (RQ rows per thread divide the shared-memory traffic per FMA by RQ);
+// online softmax in fp32.  grid (ceil(Nq / (blockDim*RQ)), heads, B).  causal: key j contributes to query i only if j <= i.
 constexpr int KT = 64;
-template <int DH>
+template <int DH, int RQ>
 __global__ void attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
                                  int Nq, int Nk, float scale_log2e, int causal, Out4 out) {
     constexpr int V4 = DH / 4;
     __shared__ float4 sk[KT][V4], sv[KT][V4];
     const int b = blockIdx.z, h = blockIdx.y;
-    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = qi < Nq;
-    float qr[DH], acc[DH];
-    if (active) {
-        const float4* qp = reinterpret_cast<const float4*>(q + ((size_t)b * Nq + qi) * ldq + h * DH);
+    int qi[RQ]; bool active[RQ];
+    float qr[RQ][DH], acc[RQ][DH], mx[RQ], l[RQ];
 #pragma unroll
-        for (int i = 0; i < V4; i++) { float4 t = qp[i]; qr[4 * i] = t.x * scale_log2e; qr[4 * i + 1] = t.y * scale_log2e; qr[4 * i + 2] = t.z * scale_log2e; qr[4 * i + 3] = t.w * scale_log2e; }
-    } else {
+    for (int u = 0; u < RQ; u++) {
+        qi[u] = (blockIdx.x * RQ + u) * blockDim.x + threadIdx.x;          // rows of one thread are blockDim apart: coalescing as before
+        active[u] = qi[u] < Nq;
+        mx[u] = -CUDART_INF_F; l[u] = 0.f;
+        if (active[u]) {
+            const float4* qp = reinterpret_cast<const float4*>(q + ((size_t)b * Nq + qi[u]) * ldq + h * DH);
 #pragma unroll
-        for (int i = 0; i < DH; i++) qr[i] = 0.f;
+            for (int i = 0; i < V4; i++) { float4 t = qp[i]; qr[u][4 * i] = t.x * scale_log2e; qr[u][4 * i + 1] = t.y * scale_log2e; qr[u][4 * i + 2] = t.z * scale_log2e; qr[u][4 * i + 3] = t.w * scale_log2e; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < DH; i++) qr[u][i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < DH; i++) acc[u][i] = 0.f;
     }
+    int qmax = 0;
 #pragma unroll
-    for (int i = 0; i < DH; i++) acc[i] = 0.f;
-    float mx = -CUDART_INF_F, l = 0.f;
+    for (int u = 0; u < RQ; u++) qmax = max(qmax, qi[u]);
     for (int k0 = 0; k0 < Nk; k0 += KT) {
         const int kn = min(KT, Nk - k0);
         __syncthreads();
@@ -182,35 +189,52 @@ __global__ void attention_kernel(const float* __restrict__ q, int ldq, const flo
             sv[j][c] = *reinterpret_cast<const float4*>(v + ((size_t)b * Nk + k0 + j) * ldv + h * DH + c * 4);
         }
         __syncthreads();
-        const int jend = causal ? min(kn, qi - k0 + 1) : kn;
+        const int jend = causal ? min(kn, qmax - k0 + 1) : kn;
         for (int j = 0; j < jend; j++) {
-            float s = 0.f;
+            float s[RQ];
+#pragma unroll
+            for (int u = 0; u < RQ; u++) s[u] = 0.f;
 #pragma unroll
             for (int c = 0; c < V4; c++) {
-                float4 kk = sk[j][c];
-                s = fmaf(qr[4 * c], kk.x, s); s = fmaf(qr[4 * c + 1], kk.y, s); s = fmaf(qr[4 * c + 2], kk.z, s); s = fmaf(qr[4 * c + 3], kk.w, s);
-            }
-            if (s > mx) {                      // s is the logit in log2 units
-                float corr = exp2f(mx - s);
-                l *= corr;
+                const float4 kk = sk[j][c];
 #pragma unroll
-                for (int i = 0; i < DH; i++) acc[i] *= corr;
-                mx = s;
+                for (int u = 0; u < RQ; u++) {
+                    s[u] = fmaf(qr[u][4 * c], kk.x, s[u]); s[u] = fmaf(qr[u][4 * c + 1], kk.y, s[u]);
+                    s[u] = fmaf(qr[u][4 * c + 2], kk.z, s[u]); s[u] = fmaf(qr[u][4 * c + 3], kk.w, s[u]);
+                }
             }
-            float p = exp2f(s - mx);
-            l += p;
+            float p[RQ];
+#pragma unroll
+            for (int u = 0; u < RQ; u++) {                 // s is the logit in log2 units
+                const bool vis = !causal || (k0 + j <= qi[u]);
+                if (vis && s[u] > mx[u]) {
+                    float corr = exp2f(mx[u] - s[u]);
+                    l[u] *= corr;
+#pragma unroll
+                    for (int i = 0; i < DH; i++) acc[u][i] *= corr;
+                    mx[u] = s[u];
+                }
+                p[u] = vis ? exp2f(s[u] - mx[u]) : 0.f;
+                l[u] += p[u];
+            }
 #pragma unroll
             for (int c = 0; c < V4; c++) {
-                float4 vv = sv[j][c];
-                acc[4 * c] = fmaf(p, vv.x, acc[4 * c]); acc[4 * c + 1] = fmaf(p, vv.y, acc[4 * c + 1]);
-                acc[4 * c + 2] = fmaf(p, vv.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(p, vv.w, acc[4 * c + 3]);
+                const float4 vv = sv[j][c];
+#pragma unroll
+                for (int u = 0; u < RQ; u++) {
+                    acc[u][4 * c] = fmaf(p[u], vv.x, acc[u][4 * c]); acc[u][4 * c + 1] = fmaf(p[u], vv.y, acc[u][4 * c + 1]);
+                    acc[u][4 * c + 2] = fmaf(p[u], vv.z, acc[u][4 * c + 2]); acc[u][4 * c + 3] = fmaf(p[u], vv.w, acc[u][4 * c + 3]);
+                }
             }
         }
     }
-    if (active) {
-        const float inv = 1.f / l;
 #pragma unroll
-        for (int i = 0; i < V4; i++) store4(out, (size_t)b * Nq + qi, h * DH + 4 * i, acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
+    for (int u = 0; u < RQ; u++) {
+        if (active[u]) {
+            const float inv = 1.f / l[u];
+#pragma unroll
+            for (int i = 0; i < V4; i++) store4(out, (size_t)b * Nq + qi[u], h * DH + 4 * i, acc[u][4 * i] * inv, acc[u][4 * i + 1] * inv, acc[u][4 * i + 2] * inv, acc[u][4 * i + 3] * inv);
+        }
     }
 }
 
@@ -342,16 +366,21 @@ int k_layernorm(View x, int M, const float* gamma, const float* beta, float eps,
 }
 int k_attention(View q, View k, View v, int B, int Nq, int Nk, int heads, float scale, Out4 out, cudaStream_t st) {
     RDM_REQUIRE(q.C == heads * 32, RDM_ERR_UNSUPPORTED, "attention: only d_head=32 is implemented (C=%d heads=%d)", q.C, heads);
-    int threads = Nq >= 128 ? 128 : ((Nq + 31) / 32) * 32;
-    dim3 grid((Nq + threads - 1) / threads, heads, B);
-    attention_kernel<32><<<grid, threads, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, Nq, Nk, scale * 1.4426950408889634f, 0, out);
+    if (Nq >= 256 && Nk >= 64) {                     // self-attention at the large levels: 2 query rows per thread
+        dim3 grid((Nq + 255) / 256, heads, B);
+        attention_kernel<32, 2><<<grid, 128, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, Nq, Nk, scale * 1.4426950408889634f, 0, out);
+    } else {
+        int threads = Nq >= 128 ? 128 : ((Nq + 31) / 32) * 32;
+        dim3 grid((Nq + threads - 1) / threads, heads, B);
+        attention_kernel<32, 1><<<grid, threads, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, Nq, Nk, scale * 1.4426950408889634f, 0, out);
+    }
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_attention_d64(View q, View k, View v, int B, int N, int heads, float scale, int causal, Out4 out, cudaStream_t st) {
     RDM_REQUIRE(q.C == heads * 64, RDM_ERR_UNSUPPORTED, "attention_d64: C=%d heads=%d", q.C, heads);
     int threads = N >= 128 ? 128 : ((N + 31) / 32) * 32;
     dim3 grid((N + threads - 1) / threads, heads, B);
-    attention_kernel<64><<<grid, threads, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, N, N, scale * 1.4426950408889634f, causal, out);
+    attention_kernel<64, 1><<<grid, threads, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, N, N, scale * 1.4426950408889634f, causal, out);
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_split_planes(View x, long long M, Out4 y, cudaStream_t st) {
