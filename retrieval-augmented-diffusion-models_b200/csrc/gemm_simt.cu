@@ -176,50 +176,6 @@ gemm_simt_kernel(AParams a, const float* __restrict__ W, int N, EParams e) {
     }
 }
 
-// Small-M linear layer (time-embedding MLP, per-ResBlock embedding projections: M = 2B rows): weight-bandwidth bound.
-// A tile [<=32, K] sits in shared memory (broadcast reads); every lane owns ONE output column and streams its weight row
-// (16-byte loads, each 128-byte line is consumed by the same lane over 8 consecutive steps), 32 fp32 accumulators per lane.
-constexpr int SM_ROWS = 32;
-__global__ void __launch_bounds__(256)
-gemm_small_m_kernel(const float* __restrict__ A, int lda, int M, int K, const float* __restrict__ W, int N, EParams e) {
-    extern __shared__ float sA[];                 // [rows][K]
-    const int m0 = blockIdx.y * SM_ROWS, rows = min(SM_ROWS, M - m0);
-    for (int i = threadIdx.x; i < rows * (K / 4); i += blockDim.x) {
-        int r = i / (K / 4), c = i % (K / 4);
-        reinterpret_cast<float4*>(sA)[r * (K / 4) + c] = *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + c * 4);
-    }
-    __syncthreads();
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    float acc[SM_ROWS];
-#pragma unroll
-    for (int r = 0; r < SM_ROWS; r++) acc[r] = 0.f;
-    const float4* w = reinterpret_cast<const float4*>(W + (size_t)n * K);
-    for (int k4 = 0; k4 < K / 4; k4++) {
-        const float4 wv = __ldg(w + k4);
-#pragma unroll
-        for (int r = 0; r < SM_ROWS; r++) {
-            if (r < rows) {
-                const float4 av = reinterpret_cast<const float4*>(sA)[r * (K / 4) + k4];
-                acc[r] = fmaf(av.x, wv.x, acc[r]); acc[r] = fmaf(av.y, wv.y, acc[r]); acc[r] = fmaf(av.z, wv.z, acc[r]); acc[r] = fmaf(av.w, wv.w, acc[r]);
-            }
-        }
-    }
-    const float b = e.bias ? e.bias[n] : 0.f;
-#pragma unroll
-    for (int r = 0; r < SM_ROWS; r++) {
-        if (r < rows) {
-            const int m = m0 + r;
-            float t = acc[r] + b;
-            if (e.rowvec) t += e.rowvec[(size_t)(m / e.rows_per_batch) * e.rowvec_ld + n];
-            if (e.act == ACT_SILU) t = silu_f(t);
-            else if (e.act == ACT_QUICKGELU) t = t / (1.f + expf(-1.702f * t));
-            if (e.res) t += e.res[(size_t)m * e.res_ld + n];
-            e.out[(size_t)m * e.out_ld + n] = t;
-        }
-    }
-}
-
 }  // namespace
 
 int gemm_simt(const GemmA& a, const float* W, int N, const GemmEpi& e, cudaStream_t st) {
@@ -227,19 +183,6 @@ int gemm_simt(const GemmA& a, const float* W, int N, const GemmEpi& e, cudaStrea
     RDM_REQUIRE(a.ksize == 1 || a.ksize == 3, RDM_ERR_UNSUPPORTED, "gemm_simt: ksize %d", a.ksize);
     AParams ap{a.x, a.ld, a.B, a.Hs, a.Ws, a.Cin, a.Ho, a.Wo, a.ksize, a.stride, a.ups, a.M(), a.K()};
     EParams ep{e.bias, e.rowvec, e.rowvec_ld, e.rows_per_batch > 0 ? e.rows_per_batch : 1, e.res, e.res_ld, e.act, e.out, e.out_ld};
-    // small-M linear layers: dedicated weight-streaming kernel
-    if (a.ksize == 1 && ap.M <= 64 && a.Cin % 4 == 0 && a.ld % 4 == 0 && e.act != ACT_GEGLU && (size_t)SM_ROWS * a.Cin * 4 <= 200 * 1024 &&
-        (((uintptr_t)a.x | (uintptr_t)W) & 15) == 0) {
-        const size_t smem = (size_t)SM_ROWS * a.Cin * sizeof(float);
-        static bool configured[16] = {false};
-        int dev = 0; cudaGetDevice(&dev);
-        if (!configured[dev & 15]) { RDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_small_m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured[dev & 15] = true; }
-        dim3 g((N + 127) / 128, (ap.M + SM_ROWS - 1) / SM_ROWS);
-        gemm_small_m_kernel<<<g, 128, smem, st>>>(a.x, a.ld, ap.M, a.Cin, W, N, ep);
-        RDM_COUNT_LAUNCH();
-        RDM_CHECK_CUDA(cudaGetLastError());
-        return RDM_OK;
-    }
     dim3 grid((N + BN - 1) / BN, (ap.M + BM - 1) / BM);
     bool vec = (a.Cin % BK == 0) && (a.ld % 4 == 0) && (((uintptr_t)a.x & 15) == 0) && (((uintptr_t)W & 15) == 0);
     if (vec) gemm_simt_kernel<true><<<grid, THREADS, 0, st>>>(ap, W, N, ep);

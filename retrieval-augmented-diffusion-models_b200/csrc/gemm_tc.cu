@@ -38,6 +38,7 @@ struct TcKernelParams {
     int H, W;                  // logical output grid per image (for tile -> (b,y,x))
     int splits, kb_per_split;  // split-K: work item = (tile, split); partial fp32 accumulators go to `part` [splits][M][N]
     float* part;
+    int pdl;                   // launched with programmatic stream serialization: prefetch weights before griddepcontrol.wait
     // epilogue
     const float* bias; const float* rowvec; int rowvec_ld; int rows_per_batch;
     const float* res; int res_ld; int act;
@@ -165,6 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.taps * p.kb_per_tap;
     const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + BM - 1) / BM, nitems = ntn * ntm * p.splits;
+    pdl_launch_dependents();                       // the next kernel may start its own prologue as soon as every CTA of this grid runs
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmB_hi);
@@ -185,6 +187,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
+            // PDL prologue: the WEIGHT tiles of the first stages do not depend on the previous kernel -> request them before waiting
+            int pre = 0;
+            {
+                const int item = blockIdx.x;
+                if (p.pdl && item < nitems) {
+                    const int tile = item / p.splits, sp = item - tile * p.splits;
+                    const int kb0 = sp * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split), n0 = (tile % ntn) * BN;
+                    for (int kb = kb0; kb < kb1 && pre < STAGES; kb++, pre++) {
+                        uint8_t* st = smem + pre * S::STAGE_BYTES;
+                        mbar_expect_tx(&full[pre], S::STAGE_BYTES);
+                        tma_load_2d(st + S::A_BYTES, &tmB_hi, &full[pre], kb * BK, n0);
+                        if (NSPLIT >= 2) tma_load_2d(st + S::A_BYTES + S::B_BYTES, &tmB_lo, &full[pre], kb * BK, n0);
+                    }
+                }
+            }
+            pdl_wait();                                                  // activations / residuals of the previous kernels are now visible
             int it = 0;                                                  // global k-block counter (ring position)
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int tile = item / p.splits, sp = item - tile * p.splits;
@@ -196,14 +214,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 else { int tiles_per_img = (p.H * p.W) / BM; b0 = mt / tiles_per_img; y0 = (mt % tiles_per_img) * p.bh; }
                 for (int kb = kb0; kb < kb1; kb++, it++) {
                     const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * S::STAGE_BYTES;
-                    mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                    const bool prefetched = it < pre;                    // weights already requested (and the barrier armed) before pdl_wait
+                    if (!prefetched) { mbar_wait(&empty[s], ph ^ 1); mbar_expect_tx(&full[s], S::STAGE_BYTES); }
                     const int tap = kb / p.kb_per_tap, kc = (kb - tap * p.kb_per_tap) * BK;
                     const int dy = p.ksize == 3 ? tap / 3 - 1 : 0, dx = p.ksize == 3 ? tap % 3 - 1 : 0;
                     tma_load_4d(st, &tmA_hi, &full[s], kc, x0 + dx, y0 + dy, b0);
-                    tma_load_2d(st + S::A_BYTES, &tmB_hi, &full[s], kb * BK, n0);
-                    if (NSPLIT >= 2) tma_load_2d(st + S::A_BYTES + S::B_BYTES, &tmB_lo, &full[s], kb * BK, n0);
+                    if (!prefetched) {
+                        tma_load_2d(st + S::A_BYTES, &tmB_hi, &full[s], kb * BK, n0);
+                        if (NSPLIT >= 2) tma_load_2d(st + S::A_BYTES + S::B_BYTES, &tmB_lo, &full[s], kb * BK, n0);
+                    }
                     if (NSPLIT == 3) tma_load_4d(st + S::A_BYTES + 2 * S::B_BYTES, &tmA_lo, &full[s], kc, x0 + dx, y0 + dy, b0);
                 }
             }
@@ -239,6 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
     } else {
         // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+        pdl_wait();                                   // residual / row-vector operands come from previous kernels
         const int q = warp & 3;
         int lt = 0;
         TcKernelParams pp = p;
@@ -275,6 +296,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
 // out = epi( sum_s part[s] ): 4 consecutive columns of one row per thread
 __global__ void splitk_reduce_kernel(const TcKernelParams p) {
+    pdl_launch_dependents();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int N4 = p.N >> 2;
     if (i >= (long long)p.M * N4) return;
@@ -358,7 +380,14 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     }
     const int nitems = ((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * p.splits;
     const int sms = rdm_num_sms(dev);
-    kern<<<nitems < sms ? nitems : sms, TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    static const int use_pdl = getenv("RDM_TC_PDL") ? atoi(getenv("RDM_TC_PDL")) : 1;
+    TcKernelParams pl = p; pl.pdl = use_pdl;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nitems < sms ? nitems : sms); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    RDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, b_hi, b_lo, pl));
     RDM_COUNT_LAUNCH();
     RDM_CHECK_CUDA(cudaGetLastError());
     return RDM_OK;

@@ -3,6 +3,7 @@
 // Semantics: SURVEY.md Appendix A (ldm pieces), rdm/modules/attention.py:42-74,92-96,183-196,
 // rdm/models/diffusion/ddim.py:232-238,253-267.
 #include "kernels.cuh"
+#include "ptx.cuh"
 #include <math_constants.h>
 
 namespace {
@@ -54,6 +55,7 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B
 // (consecutive threads -> consecutive 16-byte pieces of a row: coalesced), keeping its 4 channel sums in registers; one
 // shared-memory atomic per touched group per thread at the end, then fp64 atomics to the global accumulators.
 __global__ void gn_stats_kernel(const float* __restrict__ x, int ld, int C, int HW, int groups, int rows_per_cta, double* __restrict__ sums) {
+    pdl_launch_dependents();
     extern __shared__ float s_acc[];           // [2][groups]
     const int b = blockIdx.y, V = C / 4, cpg = C / groups;
     for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) s_acc[i] = 0.f;
@@ -89,6 +91,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int ld, int C, int 
 // beta and the finalised mean/rstd are loaded once) and walks rows slot, slot+nslots, ...; no per-element integer division.
 __global__ void gn_apply_kernel(const float* __restrict__ x, int ld, int C, int HW, int groups, const double* __restrict__ sums, float eps,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu, Out4 y, Out4 raw, int rows_per_cta) {
+    pdl_launch_dependents();
     __shared__ float s_mean[64], s_rstd[64];
     const int b = blockIdx.y, V = C / 4, cpg = C / groups;
     if (threadIdx.x < groups) {
@@ -123,6 +126,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int ld, int C, int 
 // one warp per row, two-pass (mean, then centred variance) in fp32 from registers/L1
 __global__ void layernorm_kernel(const float* __restrict__ x, int ld, int C, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float eps, Out4 y) {
+    pdl_launch_dependents();
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= M) return;
     const float* xr = x + (size_t)row * ld;
@@ -156,6 +160,7 @@ constexpr int KT = 64;
 template <int DH, int RQ>
 __global__ void attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
                                  int Nq, int Nk, float scale_log2e, int causal, Out4 out) {
+    pdl_launch_dependents();
     constexpr int V4 = DH / 4;
     __shared__ float4 sk[KT][V4], sv[KT][V4];
     const int b = blockIdx.z, h = blockIdx.y;
@@ -239,6 +244,7 @@ __global__ void attention_kernel(const float* __restrict__ q, int ldq, const flo
 }
 
 __global__ void split_planes_kernel(const float* __restrict__ x, int ld, int C, long long total4, Out4 y) {
+    pdl_launch_dependents();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int V = C / 4; int v = (int)(i % V); long long m = i / V;
@@ -247,6 +253,7 @@ __global__ void split_planes_kernel(const float* __restrict__ x, int ld, int C, 
 }
 
 __global__ void im2col_s2_kernel(const float* __restrict__ x, int ld, int C, int B, int H, int W, int Ho, int Wo, long long total4, Out4 y) {
+    pdl_launch_dependents();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over Mo * 9 * C/4
     if (i >= total4) return;
     const int V = C / 4; int v = (int)(i % V); long long r = i / V;
@@ -259,6 +266,7 @@ __global__ void im2col_s2_kernel(const float* __restrict__ x, int ld, int C, int
 }
 
 __global__ void upsample2x_kernel(const float* __restrict__ x, int ld, int C, int B, int H, int W, long long total4, Out4 y) {
+    pdl_launch_dependents();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over B*2H*2W * C/4
     if (i >= total4) return;
     const int V = C / 4; int v = (int)(i % V); long long mo = i / V;

@@ -478,13 +478,21 @@ int forward_impl(Net* n, const float* x_nchw, int Bx, const long long* t, int B2
     }
     if (!dry) RDM_CHECK_CUDA(cudaMemsetAsync(n->stats, 0, n->stats_cap * sizeof(double), st));
     // time embedding (openaimodel.py:352-353); only SiLU(emb) is ever consumed (ResBlock emb_layers = [SiLU, Linear]).
-    // M = B2 rows: weight-bandwidth bound, stays on the CUDA-core engine in every mode.
-    View temb = fresh(cx, B2, c.model_channels), e1 = fresh(cx, B2, n->ted), semb = fresh(cx, B2, n->ted), emb_all = fresh(cx, B2, n->emb_total);
+    // M = B2 rows: pure weight streaming (38 MB for the 25 concatenated emb_layers) -- on the tensor-core engine the weights arrive by
+    // TMA and split-K spreads them over all SMs; in fp32 mode the CUDA-core engine is used.
+    View temb = fresh(cx, B2, c.model_channels), semb = fresh(cx, B2, n->ted), emb_all = fresh(cx, B2, n->emb_total);
     RUN(k_timestep_embedding(t, B2, c.model_channels, temb.p, st));
-    { GemmEpi e; e.act = ACT_SILU; lin_any(cx, from_view(temb), B2, n->te0, e, from_view(e1)); }
-    { GemmEpi e; e.act = ACT_SILU; lin_any(cx, from_view(e1), B2, n->te2, e, from_view(semb)); }
-    lin_any(cx, from_view(semb), B2, n->emb_all, GemmEpi(), from_view(emb_all));
-    debug_view(cx, "temb", 0, 0, temb, B2); debug_view(cx, "semb", 0, 0, semb, B2); debug_view(cx, "emb_all", 0, 0, emb_all, B2);
+    {
+        const bool tc0 = tc_ok(cx, B2, 1, 1, c.model_channels, 1), tc1 = tc_ok(cx, B2, 1, 1, n->ted, 1);
+        Opnd t0 = from_view(temb);
+        if (tc0) { t0 = fresh_opnd(cx, B2, c.model_channels, true); RUN(k_split_planes(temb, B2, t0.out4(), st)); }
+        Opnd e1 = fresh_opnd(cx, B2, n->ted, tc1), se = fresh_opnd(cx, B2, n->ted, tc1);
+        { GemmEpi e; e.act = ACT_SILU; lin_any(cx, t0, B2, n->te0, e, e1); }
+        { GemmEpi e; e.act = ACT_SILU; lin_any(cx, e1, B2, n->te2, e, se); }
+        lin_any(cx, se, B2, n->emb_all, GemmEpi(), from_view(emb_all));
+        if (cx.n->debug && !dry) { if (se.tc()) { /* planes only: no fp32 copy to show */ } else semb = se.f; }
+    }
+    debug_view(cx, "temb", 0, 0, temb, B2); debug_view(cx, "emb_all", 0, 0, emb_all, B2);
     View x0 = fresh(cx, B2 * H * W, c.in_channels < 4 ? 4 : c.in_channels); x0.C = c.in_channels;
     RUN(k_nchw_to_nhwc(x_nchw, Bx, B2, c.in_channels, H, W, x0, st));
     Act h{x0, B2, H, W};
