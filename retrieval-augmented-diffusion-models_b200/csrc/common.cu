@@ -1,9 +1,11 @@
 // Error reporting, launch counter and misc. exports of librdm_b200.
 #include "common.cuh"
+#include <cstdlib>
 #include "../../include/rdm_b200.h"
 
 static thread_local char t_err[1024] = "";
 unsigned long long g_rdm_launches = 0;
+int g_rdm_use_pdl = getenv("RDM_PDL") ? atoi(getenv("RDM_PDL")) : 1;
 
 void rdm_set_error(const char* fmt, ...) {
     va_list ap;

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <string>
+#include <utility>
 
 #define RDM_OK 0
 #define RDM_ERR_ARG -1
@@ -46,6 +47,19 @@ extern unsigned long long g_rdm_launches;
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Launch with the programmatic-stream-serialization attribute (PDL).  A kernel launched this way MUST execute griddepcontrol.wait
+// (pdl_wait) in every CTA before touching data of earlier kernels; RDM_PDL=0 disables the attribute globally.
+extern int g_rdm_use_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_rdm_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 struct DeviceGuard {
     int prev = -1;

@@ -296,6 +296,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
 // out = epi( sum_s part[s] ): 4 consecutive columns of one row per thread
 __global__ void splitk_reduce_kernel(const TcKernelParams p) {
+    pdl_wait();
     pdl_launch_dependents();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int N4 = p.N >> 2;
@@ -380,7 +381,7 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     }
     const int nitems = ((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * p.splits;
     const int sms = rdm_num_sms(dev);
-    static const int use_pdl = getenv("RDM_TC_PDL") ? atoi(getenv("RDM_TC_PDL")) : 1;
+    const int use_pdl = g_rdm_use_pdl;
     TcKernelParams pl = p; pl.pdl = use_pdl;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nitems < sms ? nitems : sms); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -488,7 +489,7 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     RDM_TRY(rc);
     if (splits > 1) {
         const long long n4 = (long long)M * (w.N >> 2);
-        splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(p);
+        RDM_CHECK_CUDA(launch_pdl(splitk_reduce_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, p));
         RDM_COUNT_LAUNCH();
         RDM_CHECK_CUDA(cudaGetLastError());
     }

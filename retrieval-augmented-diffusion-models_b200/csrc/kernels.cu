@@ -55,6 +55,7 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B
 // (consecutive threads -> consecutive 16-byte pieces of a row: coalesced), keeping its 4 channel sums in registers; one
 // shared-memory atomic per touched group per thread at the end, then fp64 atomics to the global accumulators.
 __global__ void gn_stats_kernel(const float* __restrict__ x, int ld, int C, int HW, int groups, int rows_per_cta, double* __restrict__ sums) {
+    pdl_wait();
     pdl_launch_dependents();
     extern __shared__ float s_acc[];           // [2][groups]
     const int b = blockIdx.y, V = C / 4, cpg = C / groups;
@@ -91,6 +92,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int ld, int C, int 
 // beta and the finalised mean/rstd are loaded once) and walks rows slot, slot+nslots, ...; no per-element integer division.
 __global__ void gn_apply_kernel(const float* __restrict__ x, int ld, int C, int HW, int groups, const double* __restrict__ sums, float eps,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu, Out4 y, Out4 raw, int rows_per_cta) {
+    pdl_wait();
     pdl_launch_dependents();
     __shared__ float s_mean[64], s_rstd[64];
     const int b = blockIdx.y, V = C / 4, cpg = C / groups;
@@ -126,6 +128,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int ld, int C, int 
 // one warp per row, two-pass (mean, then centred variance) in fp32 from registers/L1
 __global__ void layernorm_kernel(const float* __restrict__ x, int ld, int C, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float eps, Out4 y) {
+    pdl_wait();
     pdl_launch_dependents();
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -160,6 +163,7 @@ constexpr int KT = 64;
 template <int DH, int RQ>
 __global__ void attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
                                  int Nq, int Nk, float scale_log2e, int causal, Out4 out) {
+    pdl_wait();
     pdl_launch_dependents();
     constexpr int V4 = DH / 4;
     __shared__ float4 sk[KT][V4], sv[KT][V4];
@@ -244,6 +248,7 @@ __global__ void attention_kernel(const float* __restrict__ q, int ldq, const flo
 }
 
 __global__ void split_planes_kernel(const float* __restrict__ x, int ld, int C, long long total4, Out4 y) {
+    pdl_wait();
     pdl_launch_dependents();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
@@ -253,6 +258,7 @@ __global__ void split_planes_kernel(const float* __restrict__ x, int ld, int C, 
 }
 
 __global__ void im2col_s2_kernel(const float* __restrict__ x, int ld, int C, int B, int H, int W, int Ho, int Wo, long long total4, Out4 y) {
+    pdl_wait();
     pdl_launch_dependents();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over Mo * 9 * C/4
     if (i >= total4) return;
@@ -266,6 +272,7 @@ __global__ void im2col_s2_kernel(const float* __restrict__ x, int ld, int C, int
 }
 
 __global__ void upsample2x_kernel(const float* __restrict__ x, int ld, int C, int B, int H, int W, long long total4, Out4 y) {
+    pdl_wait();
     pdl_launch_dependents();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // over B*2H*2W * C/4
     if (i >= total4) return;
@@ -351,7 +358,7 @@ int k_gn_stats(View x, int B, int HW, int groups, double* sums, cudaStream_t st)
     int rows_per_cta = nslots * 8;
     int chunks = (HW + rows_per_cta - 1) / rows_per_cta;
     while (chunks * B > 148 * 8 && rows_per_cta < HW) { rows_per_cta *= 2; chunks = (HW + rows_per_cta - 1) / rows_per_cta; }
-    gn_stats_kernel<<<dim3(chunks, B), threads, 2 * groups * sizeof(float), st>>>(x.p, x.ld, x.C, HW, groups, rows_per_cta, sums);
+    RDM_CHECK_CUDA(launch_pdl(gn_stats_kernel, dim3(chunks, B), dim3(threads), 2 * groups * sizeof(float), st, (const float*)x.p, x.ld, x.C, HW, groups, rows_per_cta, sums));
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps, const float* gamma, const float* beta, int silu, Out4 y, Out4 raw, cudaStream_t st) {
@@ -364,23 +371,23 @@ int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps,
     int rows_per_cta = nslots * 4;
     int chunks = (HW + rows_per_cta - 1) / rows_per_cta;
     while (chunks * B > 148 * 16 && rows_per_cta < HW) { rows_per_cta *= 2; chunks = (HW + rows_per_cta - 1) / rows_per_cta; }
-    gn_apply_kernel<<<dim3(chunks, B), threads, 0, st>>>(x.p, x.ld, x.C, HW, groups, sums, eps, gamma, beta, silu, y, raw, rows_per_cta);
+    RDM_CHECK_CUDA(launch_pdl(gn_apply_kernel, dim3(chunks, B), dim3(threads), 0, st, (const float*)x.p, x.ld, x.C, HW, groups, sums, eps, gamma, beta, silu, y, raw, rows_per_cta));
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_layernorm(View x, int M, const float* gamma, const float* beta, float eps, Out4 y, cudaStream_t st) {
     RDM_REQUIRE(x.C % 4 == 0, RDM_ERR_ARG, "layernorm: C %% 4");
-    layernorm_kernel<<<blocks_for(M, 8), 256, 0, st>>>(x.p, x.ld, x.C, M, gamma, beta, eps, y);
+    RDM_CHECK_CUDA(launch_pdl(layernorm_kernel, dim3(blocks_for(M, 8)), dim3(256), 0, st, (const float*)x.p, x.ld, x.C, M, gamma, beta, eps, y));
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_attention(View q, View k, View v, int B, int Nq, int Nk, int heads, float scale, Out4 out, cudaStream_t st) {
     RDM_REQUIRE(q.C == heads * 32, RDM_ERR_UNSUPPORTED, "attention: only d_head=32 is implemented (C=%d heads=%d)", q.C, heads);
     if (Nq >= 256 && Nk >= 64) {                     // self-attention at the large levels: 2 query rows per thread
         dim3 grid((Nq + 255) / 256, heads, B);
-        attention_kernel<32, 2><<<grid, 128, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, Nq, Nk, scale * 1.4426950408889634f, 0, out);
+        RDM_CHECK_CUDA(launch_pdl(attention_kernel<32, 2>, grid, dim3(128), 0, st, (const float*)q.p, q.ld, (const float*)k.p, k.ld, (const float*)v.p, v.ld, Nq, Nk, scale * 1.4426950408889634f, 0, out));
     } else {
         int threads = Nq >= 128 ? 128 : ((Nq + 31) / 32) * 32;
         dim3 grid((Nq + threads - 1) / threads, heads, B);
-        attention_kernel<32, 1><<<grid, threads, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, Nq, Nk, scale * 1.4426950408889634f, 0, out);
+        RDM_CHECK_CUDA(launch_pdl(attention_kernel<32, 1>, grid, dim3(threads), 0, st, (const float*)q.p, q.ld, (const float*)k.p, k.ld, (const float*)v.p, v.ld, Nq, Nk, scale * 1.4426950408889634f, 0, out));
     }
     LAUNCH_CHECK(); return RDM_OK;
 }
@@ -388,26 +395,26 @@ int k_attention_d64(View q, View k, View v, int B, int N, int heads, float scale
     RDM_REQUIRE(q.C == heads * 64, RDM_ERR_UNSUPPORTED, "attention_d64: C=%d heads=%d", q.C, heads);
     int threads = N >= 128 ? 128 : ((N + 31) / 32) * 32;
     dim3 grid((N + threads - 1) / threads, heads, B);
-    attention_kernel<64, 1><<<grid, threads, 0, st>>>(q.p, q.ld, k.p, k.ld, v.p, v.ld, N, N, scale * 1.4426950408889634f, causal, out);
+    RDM_CHECK_CUDA(launch_pdl(attention_kernel<64, 1>, grid, dim3(threads), 0, st, (const float*)q.p, q.ld, (const float*)k.p, k.ld, (const float*)v.p, v.ld, N, N, scale * 1.4426950408889634f, causal, out));
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_split_planes(View x, long long M, Out4 y, cudaStream_t st) {
     RDM_REQUIRE(x.C % 4 == 0 && x.ld % 4 == 0, RDM_ERR_ARG, "split_planes: alignment");
     long long total4 = M * (x.C / 4);
-    split_planes_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(x.p, x.ld, x.C, total4, y);
+    RDM_CHECK_CUDA(launch_pdl(split_planes_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, st, (const float*)x.p, x.ld, x.C, total4, y));
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_im2col_s2(View x, int B, int H, int W, Out4 y, cudaStream_t st) {
     RDM_REQUIRE(x.C % 4 == 0 && x.ld % 4 == 0, RDM_ERR_ARG, "im2col_s2: alignment");
     int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     long long total4 = (long long)B * Ho * Wo * 9 * (x.C / 4);
-    im2col_s2_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(x.p, x.ld, x.C, B, H, W, Ho, Wo, total4, y);
+    RDM_CHECK_CUDA(launch_pdl(im2col_s2_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, st, (const float*)x.p, x.ld, x.C, B, H, W, Ho, Wo, total4, y));
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_upsample2x(View x, int B, int H, int W, Out4 y, cudaStream_t st) {
     RDM_REQUIRE(x.C % 4 == 0 && x.ld % 4 == 0, RDM_ERR_ARG, "upsample2x: alignment");
     long long total4 = (long long)B * 4 * H * W * (x.C / 4);
-    upsample2x_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(x.p, x.ld, x.C, B, H, W, total4, y);
+    RDM_CHECK_CUDA(launch_pdl(upsample2x_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, st, (const float*)x.p, x.ld, x.C, B, H, W, total4, y));
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_silu(const float* in, float* out, long long n, cudaStream_t st) {
