@@ -6,6 +6,7 @@
 static thread_local char t_err[1024] = "";
 unsigned long long g_rdm_launches = 0;
 int g_rdm_use_pdl = getenv("RDM_PDL") ? atoi(getenv("RDM_PDL")) : 1;
+int g_rdm_use_pdl_glue = getenv("RDM_PDL_GLUE") ? atoi(getenv("RDM_PDL_GLUE")) : 0;
 
 void rdm_set_error(const char* fmt, ...) {
     va_list ap;

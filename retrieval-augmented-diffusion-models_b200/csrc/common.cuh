@@ -50,14 +50,14 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 
 // Launch with the programmatic-stream-serialization attribute (PDL).  A kernel launched this way MUST execute griddepcontrol.wait
 // (pdl_wait) in every CTA before touching data of earlier kernels; RDM_PDL=0 disables the attribute globally.
-extern int g_rdm_use_pdl;
+extern int g_rdm_use_pdl, g_rdm_use_pdl_glue;       // glue kernels: measured slightly slower with PDL -> opt-in (RDM_PDL_GLUE=1)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = g_rdm_use_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = (g_rdm_use_pdl && g_rdm_use_pdl_glue) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

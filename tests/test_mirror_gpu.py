@@ -32,6 +32,9 @@ def _setup(tmp_path, cuda, seed=4):
              "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod"}            # present in real checkpoints, not in this synthetic one
     assert not unexpected and set(missing) <= {"unconditional_guidance_vex", "model_ema.decay", "model_ema.num_updates"} | sched
     model = model.eval().to(cuda)
+    # strict split mode for the oracle comparison: this tiny random net has activations ~100 and amplifies operand rounding; the
+    # default fp16x2 mode is validated at full architecture size (tests/test_unet_gpu.py::test_full_arch_ddim20_tensor_core, tools/ddim_error.py)
+    model.model.diffusion_model.engine_mode = "bf16x3"
     return model, db, ema
 
 
@@ -91,3 +94,14 @@ def test_ddim_sampler_generic_path_with_callbacks_and_intermediates(tmp_path, cu
     for k, i in enumerate((0, 4, 9)):
         assert rel_l2(inter1["x_inter"][k + 1], traj[i][0]) < 1e-3 and rel_l2(inter1["pred_x0"][k + 1], traj[i][1]) < 1e-3
         assert rel_l2(inter2["x_inter"][k + 1], traj[i][0]) < 1e-3
+
+
+def test_default_engine_mode_runs_end_to_end(tmp_path, cuda):
+    model, db, ema = _setup(tmp_path, cuda, seed=9)
+    model.model.diffusion_model.engine_mode = "fp16x2"
+    x_T = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(3))
+    logs = model.sample_from_rdata(2, qids=np.array([1, 2]), k_nn=4, unconditional_guidance_scale=2.0, ddim_steps=5, ddim=True,
+                                   unconditional_retro_guidance_label=0., x_T=x_T.to(cuda))
+    cond = torch.from_numpy(db[logs["nns"].cpu().numpy()].astype(np.float32))
+    want = oddim.ddim_sample(ema, x_T, cond, torch.zeros_like(cond), S=5, scale=2.0)
+    assert torch.isfinite(logs["latents"]).all() and rel_l2(logs["latents"], want) < 2e-2
