@@ -23,7 +23,7 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 64, TC_THREADS = 192;
+constexpr int BM = 128, BK = 64, EPI_WARPS = 8, TC_THREADS = 64 + EPI_WARPS * 32;     // warp 0 TMA, warp 1 MMA, 8 epilogue warps
 
 // ---- PTX wrappers (mbarrier / TMA helpers live in ptx.cuh) -----------------------------------------------
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
@@ -51,7 +51,7 @@ template <int BN, int NSPLIT, int STAGES>
 struct TcSmem {
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * A_BYTES + (NSPLIT >= 2 ? 2 : 1) * B_BYTES;   // [A_hi][B_hi][B_lo?][A_lo?]
-    static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;      // per-epilogue-warp transpose tiles
+    static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;      // per-epilogue-warp transpose tiles
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
     static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
     static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
@@ -63,8 +63,8 @@ struct TcSmem {
 // activation are applied in registers; the 32x32 (or 32x16 after GEGLU) block is then transposed through a padded per-warp
 // shared-memory tile so that every global access of the warp covers whole 128-byte lines: the residual is read and the
 // result written as [4 or 8 rows] x [128 B | 64 B] per instruction instead of 32 rows x 16 B.
-constexpr int EPI_LD = 36;                         // floats per staged row (32 + 4 pad: conflict-free float4 rows)
-constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
+constexpr int EPI_WARP_FLOATS = 32 * 32;            // per-warp staging tile, float4 column groups XOR-swizzled by (row & 7): conflict-free
+__device__ __forceinline__ float* epi_at(float* stage, int row, int col4) { return stage + row * 32 + (((col4 >> 2) ^ (row & 7)) << 2); }
 
 // r: this lane's 32 accumulators (row m_warp0 + lane, columns nb..nb+31); stage: this warp's smem tile.
 __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const uint32_t (&r)[32], float* stage, int lane, int m_warp0, int nb) {
@@ -121,10 +121,9 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
         for (int j = 0; j < 32; j++) v[j] = v[j] / (1.f + expf(-1.702f * v[j]));
     }
     // transpose through shared memory
-    float* row = stage + lane * EPI_LD;
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) if (j < wout) *reinterpret_cast<float4*>(row + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    for (int j = 0; j < 32; j += 4) if (j < wout) *reinterpret_cast<float4*>(epi_at(stage, lane, j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     __syncwarp();
     const int lpr = wout >> 2;                     // lanes per row: 8 (128 B) or 4 (64 B)
     const int rstep = 32 / lpr, r0 = lane / lpr, cg = (lane % lpr) * 4;
@@ -133,7 +132,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
     for (int it = 0; it < 8; it++) {               // all residual loads in flight before the first store
         const int rr = r0 + it * rstep, mo = m_warp0 + rr;
         const bool ok = rr < 32 && mo < p.M;
-        t[it] = ok ? *reinterpret_cast<const float4*>(stage + rr * EPI_LD + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+        t[it] = ok ? *reinterpret_cast<const float4*>(epi_at(stage, rr, cg)) : make_float4(0.f, 0.f, 0.f, 0.f);
         q[it] = (ok && p.res) ? __ldcs(reinterpret_cast<const float4*>(p.res + (size_t)mo * p.res_ld + no + cg)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
@@ -173,7 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (NSPLIT >= 2) prefetch_tmap(&tmB_lo);
         if (NSPLIT == 3) prefetch_tmap(&tmA_lo);
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -258,9 +257,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
         }
     } else {
-        // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+        // epilogue: warp w may touch TMEM lanes [32*(w%4), +32); each lane quarter is served by TWO warps that alternate column chunks
         pdl_wait();                                   // residual / row-vector operands come from previous kernels
-        const int q = warp & 3;
+        const int q = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
         int lt = 0;
         TcKernelParams pp = p;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, lt++) {
@@ -275,11 +274,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
+            for (int c = half; c < BN / 32; c += 2) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
                 const int nb = n0 + c * 32;
-                if (m_warp0 < p.M && nb < p.N) epilogue_chunk(pp, r, epi_stage + q * EPI_WARP_FLOATS, lane, m_warp0, nb);
+                if (m_warp0 < p.M && nb < p.N) epilogue_chunk(pp, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb);
             }
             tc_fence_before();
             __syncwarp();
@@ -479,9 +478,9 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
         if (BN == 192) rc = launch_tc<192, 3, 2>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
         else if (BN == 128) rc = launch_tc<128, 3, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
         else if (BN == 64) rc = launch_tc<64, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        else rc = launch_tc<32, 3, 5>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        else rc = launch_tc<32, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
     } else {
-        if (BN == 192) rc = launch_tc<192, 1, 5>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
+        if (BN == 192) rc = launch_tc<192, 1, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
         else if (BN == 128) rc = launch_tc<128, 1, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
         else if (BN == 64) rc = launch_tc<64, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
         else rc = launch_tc<32, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
