@@ -76,6 +76,10 @@ int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps,
 int k_layernorm(View x, int M, const float* gamma, const float* beta, float eps, Out4 y, cudaStream_t st);
 // softmax(q k^T * scale) v for heads of width 32.  q: [B*Nq, heads*32] view, k/v: [B*Nk, heads*32] views.
 int k_attention(View q, View k, View v, int B, int Nq, int Nk, int heads, float scale, Out4 out, cudaStream_t st);
+// Tensor-core variant for the f16 engine modes (attention_mma.cu): q/k/v are column blocks of an fp16 plane with row stride ld
+// (the QKV GEMM writes that plane directly); warp-level m16n8k16 MMAs, fp32 online softmax.  Nq, Nk multiples of 64.
+bool k_attention_mma_supported(int Nq, int Nk);
+int k_attention_mma(const __half* q, const __half* k, const __half* v, int ld, int B, int Nq, int Nk, int heads, float scale, Out4 out, cudaStream_t st);
 // same for heads of width 64 (CLIP), optional causal mask (key j visible to query i iff j <= i; custom_clip/model.py:287-292)
 int k_attention_d64(View q, View k, View v, int B, int N, int heads, float scale, int causal, Out4 out, cudaStream_t st);
 // fp32 [M, C] -> bf16 planes

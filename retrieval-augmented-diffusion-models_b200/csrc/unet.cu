@@ -368,9 +368,19 @@ void run_st(Ctx& cx, const STW& s, const Act& x, View out) {
     // self-attention (attention.py:93)
     RUN(k_layernorm(t0, M, s.ln1.g, s.ln1.b, 1e-5f, nrm.out4(), cx.st));
     View qkv = fresh(cx, M, 3 * C);
-    lin_any(cx, nrm, M, s.qkv, GemmEpi(), from_view(qkv));
     Opnd att = fresh_opnd(cx, M, C, tcp);
-    RUN(k_attention(qkv.cols(0, C), qkv.cols(C, C), qkv.cols(2 * C, C), x.B, N, N, s.heads, scale, att.out4(), cx.st));
+    if (tcp && mode_f16(n->mode) && k_attention_mma_supported(N, N)) {
+        // f16 engine modes: the QKV GEMM writes ONE fp16 plane that the warp-MMA attention kernel consumes directly
+        size_t mk2 = A.mark();
+        Opnd qh; qh.hi = (__nv_bfloat16*)A.alloc((size_t)M * 3 * C * 2); qh.ldb = 3 * C; qh.f.C = 3 * C; qh.f16 = 1;
+        lin_any(cx, nrm, M, s.qkv, GemmEpi(), qh);
+        const __half* qp = reinterpret_cast<const __half*>(qh.hi);
+        RUN(k_attention_mma(qp, qp + C, qp + 2 * C, 3 * C, x.B, N, N, s.heads, scale, att.out4(), cx.st));
+        A.release(mk2);
+    } else {
+        lin_any(cx, nrm, M, s.qkv, GemmEpi(), from_view(qkv));
+        RUN(k_attention(qkv.cols(0, C), qkv.cols(C, C), qkv.cols(2 * C, C), x.B, N, N, s.heads, scale, att.out4(), cx.st));
+    }
     View t1 = fresh(cx, M, C);
     { GemmEpi e; e.res = t0.p; e.res_ld = t0.ld; lin_any(cx, att, M, s.o1, e, from_view(t1)); }
     // cross-attention to the retrieved neighbours (attention.py:94); K/V were projected once in set_context
