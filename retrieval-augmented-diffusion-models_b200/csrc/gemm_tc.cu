@@ -38,10 +38,12 @@ struct TcKernelParams {
     int H, W;                  // logical output grid per image (for tile -> (b,y,x))
     int splits, kb_per_split;  // split-K: work item = (tile, split); partial fp32 accumulators go to `part` [splits][M][N]
     float* part;
+    int cluster;               // split-K inside a thread-block cluster: CTA rank = split, partial tiles reduced through distributed shared memory
     int pdl;                   // launched with programmatic stream serialization: prefetch weights before griddepcontrol.wait
     // epilogue
     const float* bias; const float* rowvec; int rowvec_ld; int rows_per_batch;
     const float* res; int res_ld; int act;
+    const float* xkv; int xkv_ld, xv_off, xk; float xscale_log2e;  // ACT_XATTN (see GemmEpi)
     float* out; int out_ld;                                // fp32 output (or null)
     __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_bf_ld;   // 16-bit-plane output (or null)
     int f16;                                                       // planes are IEEE fp16 instead of bf16
@@ -77,7 +79,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
         // ragged last chunk (N not a multiple of 32; only the 4-channel output conv): predicated scalar path
         if (m < p.M) {
             const int bidx = m / p.rows_per_batch;
+#ifdef RDM_AB_RAGGED_UNROLL4
+#pragma unroll 4
+#else
 #pragma unroll
+#endif
             for (int j = 0; j < 32; j++) {
                 const int n = nb + j;
                 if (n < p.N) {
@@ -109,7 +115,50 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
         for (int j = 0; j < 32; j += 4) { float4 t = __ldg(reinterpret_cast<const float4*>(rv + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
     }
     int wout = 32, no = nb;                       // output width of this chunk and its first output column
-    if (p.act == ACT_GEGLU) {
+    if (p.act == ACT_XATTN) {
+        // v[0..31] is the query of head nb/32 for token m: attend to the (<= 8) retrieved-context keys of this sample.  With ~200 KB of the
+        // SM's unified array carved out as shared memory there is next to no L1, so the K/V rows of this head (1-2 images per warp) are
+        // staged once per chunk in the warp's transpose tile and read back as shared-memory broadcasts.
+        const int mm = m < p.M ? m : p.M - 1, hw = p.rows_per_batch;
+        const int b0 = (m_warp0 < p.M ? m_warp0 : p.M - 1) / hw, b1 = (m_warp0 + 31 < p.M ? m_warp0 + 31 : p.M - 1) / hw;
+        const int per_img = 2 * p.xk * 8;                              // float4 pieces per image: [K | V][xk][32 floats]
+        __syncwarp();
+        for (int i = lane; i < (b1 - b0 + 1) * per_img; i += 32) {
+            const int img = i / per_img, r = i - img * per_img, kvsel = r / (p.xk * 8), r2 = r - kvsel * p.xk * 8;
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.xkv + ((size_t)(b0 + img) * p.xk + (r2 >> 3)) * p.xkv_ld + nb + kvsel * p.xv_off) + (r2 & 7));
+            *reinterpret_cast<float4*>(stage + (size_t)i * 4) = t;
+        }
+        __syncwarp();
+        const float* kb = stage + (size_t)(mm / hw - b0) * per_img * 4;
+        // online softmax over the keys; deliberately a rolled loop: a chunk executes this once, and straight-line code of that size would be
+        // fetched from L2 every time (instruction-cache misses cost more than the arithmetic)
+        float o[32], mx = -3.0e38f, l = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i++) o[i] = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < p.xk; j++) {
+            const float4* kr = reinterpret_cast<const float4*>(kb + j * 32);
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                const float4 t = kr[i], u = kr[i + 1];
+                s0 = fmaf(v[4 * i], t.x, s0); s0 = fmaf(v[4 * i + 1], t.y, s0); s0 = fmaf(v[4 * i + 2], t.z, s0); s0 = fmaf(v[4 * i + 3], t.w, s0);
+                s1 = fmaf(v[4 * i + 4], u.x, s1); s1 = fmaf(v[4 * i + 5], u.y, s1); s1 = fmaf(v[4 * i + 6], u.z, s1); s1 = fmaf(v[4 * i + 7], u.w, s1);
+            }
+            const float sj = (s0 + s1) * p.xscale_log2e, mn = fmaxf(mx, sj), corr = exp2f(mx - mn), pj = exp2f(sj - mn);
+            mx = mn; l = fmaf(l, corr, pj);
+            const float4* vr = reinterpret_cast<const float4*>(kb + (p.xk + j) * 32);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float4 t = vr[i];
+                o[4 * i] = fmaf(pj, t.x, o[4 * i] * corr); o[4 * i + 1] = fmaf(pj, t.y, o[4 * i + 1] * corr);
+                o[4 * i + 2] = fmaf(pj, t.z, o[4 * i + 2] * corr); o[4 * i + 3] = fmaf(pj, t.w, o[4 * i + 3] * corr);
+            }
+        }
+        const float il = 1.f / l;
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = o[i] * il;
+    } else if (p.act == ACT_GEGLU) {
 #pragma unroll
         for (int j = 0; j < 16; j++) v[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
         wout = 16; no = nb >> 1;
@@ -146,6 +195,49 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
     }
 }
 
+// epilogue of 4 consecutive accumulator columns n..n+3 of row m (bias, time-embedding row vector, activation, residual, store)
+__device__ __forceinline__ void epi_store4(const TcKernelParams& p, int m, int n, float (&v)[4]) {
+    if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+    if (p.rowvec) { float4 t = __ldg(reinterpret_cast<const float4*>(p.rowvec + (size_t)(m / p.rows_per_batch) * p.rowvec_ld + n)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+    if (p.act == ACT_GEGLU) {
+        float o0 = v[0] * gelu_erf(v[1]), o1 = v[2] * gelu_erf(v[3]);
+        const int no = n >> 1;
+        if (p.res) { o0 += p.res[(size_t)m * p.res_ld + no]; o1 += p.res[(size_t)m * p.res_ld + no + 1]; }
+        if (p.out) *reinterpret_cast<float2*>(p.out + (size_t)m * p.out_ld + no) = make_float2(o0, o1);
+        else {
+            unsigned short h0, l0, h1, l1; split16(o0, p.f16, h0, l0); split16(o1, p.f16, h1, l1);
+            *reinterpret_cast<uint32_t*>(p.out_hi + (size_t)m * p.out_bf_ld + no) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            if (p.out_lo) *reinterpret_cast<uint32_t*>(p.out_lo + (size_t)m * p.out_bf_ld + no) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        }
+        return;
+    }
+    if (p.act == ACT_SILU) { v[0] = silu_f(v[0]); v[1] = silu_f(v[1]); v[2] = silu_f(v[2]); v[3] = silu_f(v[3]); }
+    else if (p.act == ACT_QUICKGELU) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = v[j] / (1.f + expf(-1.702f * v[j]));
+    }
+    if (p.res) { float4 t = *reinterpret_cast<const float4*>(p.res + (size_t)m * p.res_ld + n); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+    if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)m * p.out_ld + n) = make_float4(v[0], v[1], v[2], v[3]);
+    else store_planes4(p.out_hi + (size_t)m * p.out_bf_ld + n, p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + n : nullptr, p.f16, v[0], v[1], v[2], v[3]);
+}
+
+// Fallback (RDM_TC_CLUSTER=0): out = epi( sum_s part[s] ), 4 consecutive columns of one row per thread
+__global__ void splitk_reduce_kernel(const TcKernelParams p) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int N4 = p.N >> 2;
+    if (i >= (long long)p.M * N4) return;
+    const int m = (int)(i / N4), n = (int)(i % N4) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < p.splits; s++) {
+        float4 t = __ldcs(reinterpret_cast<const float4*>(p.part + ((size_t)s * p.M + m) * p.N + n));
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    float v[4] = {a.x, a.y, a.z, a.w};
+    epi_store4(p, m, n, v);
+}
+
 // Persistent: grid = min(#tiles, #SMs); CTA c handles tiles c, c+grid, ...; tile -> (mt, nt) with nt fastest so
 // co-scheduled CTAs share the A tile in L2.  TMEM holds TWO accumulators: the epilogue of tile i overlaps the MMAs of i+1.
 template <int BN, int NSPLIT, int STAGES>
@@ -153,8 +245,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcKernelParams p) {
     using S = TcSmem<BN, NSPLIT, STAGES>;
+    constexpr int RED_LD = BN + 4;                 // row stride (floats) of the split-K staging tile: conflict-free float4 rows
+    static_assert(BM * RED_LD * 4 <= STAGES * S::STAGE_BYTES, "split-K staging tile must fit the pipeline stages");
     extern __shared__ uint8_t smem_raw[];
+#ifdef RDM_AB_GENERIC_SMEM
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+#else
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // 1 KB aligned; pointer arithmetic keeps the shared address space
+#endif
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;          // [2]
@@ -262,6 +360,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int q = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
         int lt = 0;
         TcKernelParams pp = p;
+        if (p.cluster) {
+            // cluster split-K: park this CTA's fp32 partial tile in (now idle) pipeline shared memory; the cluster-wide reduction follows below
+            mbar_wait(&tmem_full[0], 0);
+            tc_fence_after();
+            float* red = reinterpret_cast<float*>(smem) + (size_t)(q * 32 + lane) * RED_LD;
+#pragma unroll 1
+            for (int c = half; c < BN / 32; c += 2) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(red + c * 32 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+        } else
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, lt++) {
             const int tile = item / p.splits, sp = item - tile * p.splits;
             if (p.splits > 1) {                                   // raw partial sums; the reduce kernel applies the epilogue
@@ -287,48 +399,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cluster) {
+        // Every CTA of the cluster (rank = split) now holds a 128 x BN fp32 partial in its shared memory.  CTA r reduces the r-th slice of
+        // the tile over all ranks through distributed shared memory (fixed summation order: deterministic) and applies the real epilogue.
+        cluster_sync_all();
+        if (warp >= 2) {
+            const int tile = blockIdx.x / p.splits, rank = blockIdx.x - tile * p.splits;
+            const int mt = tile / ntn, n0 = (tile % ntn) * BN;
+            constexpr int C4 = BN / 4, TOTAL4 = BM * C4;
+            const int i0 = (int)((long long)TOTAL4 * rank / p.splits), i1 = (int)((long long)TOTAL4 * (rank + 1) / p.splits);
+            const uint32_t red_base = smem_u32(smem);
+            for (int i = i0 + (int)threadIdx.x - 64; i < i1; i += EPI_WARPS * 32) {
+                const int row = i / C4, c4 = i - row * C4;
+                const int m = mt * BM + row, n = n0 + c4 * 4;
+                if (m >= p.M || n >= p.N) continue;
+                const uint32_t off = red_base + (uint32_t)(row * RED_LD + c4 * 4) * 4u;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int s = 0; s < p.splits; s++) {
+                    float4 t = ld_dsmem_f4(off, (uint32_t)s);
+                    v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                }
+                epi_store4(p, m, n, v);
+            }
+        }
+        cluster_sync_all();                          // no CTA may exit (and free its shared memory) while a peer still reads it
+    }
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS) : "memory");
     }
-}
-
-// out = epi( sum_s part[s] ): 4 consecutive columns of one row per thread
-__global__ void splitk_reduce_kernel(const TcKernelParams p) {
-    pdl_wait();
-    pdl_launch_dependents();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int N4 = p.N >> 2;
-    if (i >= (long long)p.M * N4) return;
-    const int m = (int)(i / N4), n = (int)(i % N4) * 4;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < p.splits; s++) {
-        float4 t = __ldcs(reinterpret_cast<const float4*>(p.part + ((size_t)s * p.M + m) * p.N + n));
-        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-    }
-    float v[4] = {a.x, a.y, a.z, a.w};
-    if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
-    if (p.rowvec) { float4 t = __ldg(reinterpret_cast<const float4*>(p.rowvec + (size_t)(m / p.rows_per_batch) * p.rowvec_ld + n)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
-    if (p.act == ACT_GEGLU) {
-        float o0 = v[0] * gelu_erf(v[1]), o1 = v[2] * gelu_erf(v[3]);
-        const int no = n >> 1;
-        if (p.res) { o0 += p.res[(size_t)m * p.res_ld + no]; o1 += p.res[(size_t)m * p.res_ld + no + 1]; }
-        if (p.out) *reinterpret_cast<float2*>(p.out + (size_t)m * p.out_ld + no) = make_float2(o0, o1);
-        else {
-            unsigned short h0, l0, h1, l1; split16(o0, p.f16, h0, l0); split16(o1, p.f16, h1, l1);
-            *reinterpret_cast<uint32_t*>(p.out_hi + (size_t)m * p.out_bf_ld + no) = (uint32_t)h0 | ((uint32_t)h1 << 16);
-            if (p.out_lo) *reinterpret_cast<uint32_t*>(p.out_lo + (size_t)m * p.out_bf_ld + no) = (uint32_t)l0 | ((uint32_t)l1 << 16);
-        }
-        return;
-    }
-    if (p.act == ACT_SILU) { v[0] = silu_f(v[0]); v[1] = silu_f(v[1]); v[2] = silu_f(v[2]); v[3] = silu_f(v[3]); }
-    else if (p.act == ACT_QUICKGELU) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = v[j] / (1.f + expf(-1.702f * v[j]));
-    }
-    if (p.res) { float4 t = *reinterpret_cast<const float4*>(p.res + (size_t)m * p.res_ld + n); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
-    if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)m * p.out_ld + n) = make_float4(v[0], v[1], v[2], v[3]);
-    else store_planes4(p.out_hi + (size_t)m * p.out_bf_ld + n, p.out_lo ? p.out_lo + (size_t)m * p.out_bf_ld + n : nullptr, p.f16, v[0], v[1], v[2], v[3]);
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -369,7 +468,7 @@ int make_map_2d(CUtensorMap* tm, const void* base, int K, int rows, int ld, int 
 }
 
 template <int BN, int NSPLIT, int STAGES>
-int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcKernelParams& p, cudaStream_t st) {
+int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcKernelParams& p, cudaStream_t st, int* cluster_cap) {
     auto kern = gemm_tc_kernel<BN, NSPLIT, STAGES>;
     constexpr int smem = TcSmem<BN, NSPLIT, STAGES>::TOTAL;
     static bool configured[16] = {false};
@@ -378,19 +477,57 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
         RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured[dev & 15] = true;
     }
+    if (cluster_cap) {                               // query only: how many clusters of p.splits CTAs can be co-resident
+        static int cap[16][9];
+        int& c = cap[dev & 15][p.splits];
+        if (c == 0) {
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(p.splits * 64); q.blockDim = dim3(TC_THREADS); q.dynamicSmemBytes = smem;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = p.splits; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.attrs = qa; q.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess) { cudaGetLastError(); n = 0; }
+            c = n > 0 ? n : -1;
+        }
+        *cluster_cap = c > 0 ? c : 0;
+        return RDM_OK;
+    }
     const int nitems = ((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * p.splits;
     const int sms = rdm_num_sms(dev);
     const int use_pdl = g_rdm_use_pdl;
     TcKernelParams pl = p; pl.pdl = use_pdl;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(nitems < sms ? nitems : sms); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    cfg.gridDim = dim3(p.cluster ? nitems : (nitems < sms ? nitems : sms)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+    if (p.cluster) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = p.splits; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; na++; }
+    cfg.attrs = attr; cfg.numAttrs = na;
     RDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, b_hi, b_lo, pl));
     RDM_COUNT_LAUNCH();
     RDM_CHECK_CUDA(cudaGetLastError());
     return RDM_OK;
+}
+
+// dispatch on (tile width, MMAs per product); cluster_cap != nullptr: capacity query only (see launch_tc)
+int dispatch_tc(int BN, int nsplit, const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
+                const TcKernelParams& p, cudaStream_t st, int* cluster_cap) {
+    if (nsplit == 2) {
+        if (BN == 192) return launch_tc<192, 2, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+        if (BN == 128) return launch_tc<128, 2, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+        if (BN == 64) return launch_tc<64, 2, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+        return launch_tc<32, 2, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    } else if (nsplit == 3) {
+        if (BN == 192) return launch_tc<192, 3, 2>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+        if (BN == 128) return launch_tc<128, 3, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+        if (BN == 64) return launch_tc<64, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+        return launch_tc<32, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    }
+    if (BN == 192) return launch_tc<192, 1, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    if (BN == 128) return launch_tc<128, 1, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    if (BN == 64) return launch_tc<64, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    return launch_tc<32, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
 }
 
 }  // namespace
@@ -428,6 +565,9 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     }
     p.bias = e.bias; p.rowvec = e.rowvec; p.rowvec_ld = e.rowvec_ld; p.rows_per_batch = e.rows_per_batch > 0 ? e.rows_per_batch : 1;
     p.res = e.res; p.res_ld = e.res_ld; p.act = e.act; p.out = e.out; p.out_ld = e.out_ld;
+    p.xkv = e.xkv; p.xkv_ld = e.xkv_ld; p.xv_off = e.xv_off; p.xk = e.xk; p.xscale_log2e = e.xscale * 1.4426950408889634f;
+    RDM_REQUIRE(e.act != ACT_XATTN || (e.xkv && e.xk >= 1 && e.xk <= 8 && p.rows_per_batch >= 16 && w.N % 32 == 0 && e.xkv_ld % 4 == 0 && !e.bias && !e.res && !e.rowvec), RDM_ERR_ARG,
+                "gemm_tc: fused cross-attention needs 1..8 context rows, N %% 32 == 0 and no bias/residual (xk=%d N=%d)", e.xk, w.N);
     p.out_hi = out_hi; p.out_lo = out_lo; p.out_bf_ld = out_bf_ld; p.f16 = f16;
     RDM_REQUIRE((p.out != nullptr) != (p.out_hi != nullptr), RDM_ERR_ARG, "gemm_tc: exactly one of fp32 / bf16 outputs");
     // Tile width and split-K.  The mainloop is operand-feed bound (TMA/L2 -> smem): one k-block of a work item costs ~(128 + BN)
@@ -436,24 +576,42 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     const int mtiles = (M + BM - 1) / BM, sms = 148, nkb_total = p.taps * p.kb_per_tap;
     static const int forced = getenv("RDM_TC_BN") ? atoi(getenv("RDM_TC_BN")) : 0;
     static const int no_split = getenv("RDM_TC_NOSPLIT") ? 1 : 0;
-    int BN = 32, splits = 1;
+    static const int use_cluster = getenv("RDM_TC_CLUSTER") ? atoi(getenv("RDM_TC_CLUSTER")) : 1;
+    // Split-K has two implementations: (a) persistent CTAs write fp32 partials, a dependent kernel reduces them; (b) the splits of a tile
+    // form a thread-block cluster (CTA rank = split) and reduce through distributed shared memory -- no partials in HBM/L2 and no second
+    // kernel, but splits <= 8 (portable cluster size), one CTA per item, and only `cap` clusters are co-resident (GPC granularity).
+    // Both are candidates of the cost model below; RDM_TC_CLUSTER=0 / 2 forces the reduce-kernel / the cluster variant.
+    CUtensorMap tdummy = ta_hi;
+    int BN = 32, splits = 1, clustered = 0;
     const int cand[4] = {192, 128, 64, 32};
     long best = -1;
     for (int c : cand) {
         if (c > 32 && w.N <= c / 2) continue;
         if (forced && c != forced) continue;
         const int nt = (w.N + c - 1) / c;
-        for (int sp = 1; sp <= 16; sp++) {
-            if (sp > 1 && (no_split || nkb_total / sp < 4 || (w.N & 3) || (size_t)sp * M * w.N * 4 > ((size_t)48 << 20))) break;
-            const int kbps = (nkb_total + sp - 1) / sp;
-            if ((sp - 1) * kbps >= nkb_total) continue;                  // an empty split
-            const long items = (long)mtiles * nt * sp, waves = (items + sms - 1) / sms;
-            const long cost = waves * (kbps + 6) * (128 + c) + (sp > 1 ? 2 * (128 + c) : 0);
-            if (best < 0 || cost < best) { best = cost; BN = c; splits = sp; }
+        for (int cl = 0; cl <= 1; cl++) {
+            if (cl == 1 && use_cluster == 0) continue;
+            for (int sp = cl ? 2 : 1; sp <= (cl ? 8 : 16); sp++) {
+                if (sp > 1 && (no_split || e.act == ACT_XATTN || nkb_total / sp < 4 || (w.N & 3) || (!cl && (size_t)sp * M * w.N * 4 > ((size_t)48 << 20)))) break;
+                if (sp > 1 && !cl && use_cluster == 2) break;
+                const int kbps = (nkb_total + sp - 1) / sp;
+                if ((sp - 1) * kbps >= nkb_total) continue;                  // an empty split
+                long items = (long)mtiles * nt * sp, waves = (items + sms - 1) / sms;
+                if (cl) {
+                    TcKernelParams q = p; q.splits = sp; int cap = 0;
+                    RDM_TRY(dispatch_tc(c, nsplit, tdummy, tdummy, tdummy, tdummy, q, st, &cap));
+                    if (cap <= 0) continue;
+                    waves = ((long)mtiles * nt + cap - 1) / cap;
+                }
+                // fixed cost of the reduction in k-block units: a dependent reduce kernel over partials in L2 vs an in-kernel DSMEM pass
+                const long cost = waves * (kbps + 6) * (128 + c) + (sp > 1 ? (cl ? 2 : 5) * (128 + c) : 0);
+                if (best < 0 || cost < best) { best = cost; BN = c; splits = sp; clustered = cl; }
+            }
         }
     }
-    p.splits = splits; p.kb_per_split = (nkb_total + splits - 1) / splits; p.part = nullptr;
-    if (splits > 1) {
+    p.splits = splits; p.kb_per_split = (nkb_total + splits - 1) / splits; p.part = nullptr; p.cluster = clustered;
+    if (getenv("RDM_TC_TRACE")) fprintf(stderr, "gemm_tc M=%d N=%d K=%d -> BN=%d splits=%d cluster=%d\n", M, w.N, w.K, BN, splits, clustered);
+    if (splits > 1 && !p.cluster) {
         static float* ws[16] = {nullptr}; static size_t ws_cap[16] = {0};
         int dev = 0; cudaGetDevice(&dev);
         const size_t need = (size_t)splits * M * w.N * sizeof(float);
@@ -468,25 +626,8 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     }
     RDM_TRY(make_map_2d(&tb_hi, w.hi, w.K, w.N, w.ld, BN));
     if (nsplit >= 2) RDM_TRY(make_map_2d(&tb_lo, w.lo, w.K, w.N, w.ld, BN)); else tb_lo = tb_hi;
-    int rc;
-    if (nsplit == 2) {
-        if (BN == 192) rc = launch_tc<192, 2, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        else if (BN == 128) rc = launch_tc<128, 2, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        else if (BN == 64) rc = launch_tc<64, 2, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        else rc = launch_tc<32, 2, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-    } else if (nsplit == 3) {
-        if (BN == 192) rc = launch_tc<192, 3, 2>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        else if (BN == 128) rc = launch_tc<128, 3, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        else if (BN == 64) rc = launch_tc<64, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        else rc = launch_tc<32, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-    } else {
-        if (BN == 192) rc = launch_tc<192, 1, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        else if (BN == 128) rc = launch_tc<128, 1, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        else if (BN == 64) rc = launch_tc<64, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-        else rc = launch_tc<32, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st);
-    }
-    RDM_TRY(rc);
-    if (splits > 1) {
+    RDM_TRY(dispatch_tc(BN, nsplit, ta_hi, ta_lo, tb_hi, tb_lo, p, st, nullptr));
+    if (splits > 1 && !p.cluster) {
         const long long n4 = (long long)M * (w.N >> 2);
         RDM_CHECK_CUDA(launch_pdl(splitk_reduce_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, p));
         RDM_COUNT_LAUNCH();

@@ -50,12 +50,16 @@ struct GemmA {
     int M() const { return B * Ho * Wo; }
     int K() const { return ksize * ksize * Cin; }
 };
-enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2, ACT_QUICKGELU = 3 };      // QuickGELU: x * sigmoid(1.702 x) (custom_clip/model.py:159-161)
+enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2, ACT_QUICKGELU = 3,        // QuickGELU: x * sigmoid(1.702 x) (custom_clip/model.py:159-161)
+       ACT_XATTN = 4 };   // tensor-core engine only: the 32-column chunk of a row IS one head's query -> attend to the xk cached context keys/values
 struct GemmEpi {
     const float* bias = nullptr;                                   // [N]
     const float* rowvec = nullptr; int rowvec_ld = 0; int rows_per_batch = 1;   // + rowvec[(m / rows_per_batch)*rowvec_ld + n]
     const float* res = nullptr; int res_ld = 0;                    // + res[m*res_ld + n]
     int act = ACT_NONE;                                            // GEGLU: columns (2j,2j+1) = (a_j, gate_j) -> out col j
+    // ACT_XATTN (cross-attention fused into the to_q projection, attention.py:46-74 with d_head 32): keys at xkv[(b*xk + j)*xkv_ld + n],
+    // values at + xv_off, b = m / rows_per_batch; out[m, head*32 + i] = sum_j softmax_j(q . k_j * xscale) v_j[i]
+    const float* xkv = nullptr; int xkv_ld = 0, xv_off = 0, xk = 0; float xscale = 1.f;
     float* out = nullptr; int out_ld = 0;
 };
 // fp32 CUDA-core engine (strict mode / fallback).  W: [N, K] row-major, K ordered (tap, cin).

@@ -46,6 +46,19 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- thread-block clusters: barrier over all threads of all CTAs, distributed-shared-memory loads --------------------------
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// float4 at the shared-memory offset `cta_addr` (a shared::cta address of THIS CTA's window) in the CTA of rank `rank`
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cta_addr, uint32_t rank) {
+    uint32_t ra; float4 v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(cta_addr), "r"(rank));
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+    return v;
+}
+
 // ---- tcgen05 (UMMA) helpers: fences, shared-memory / instruction descriptors, MMA issue, commit, TMEM load ----------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

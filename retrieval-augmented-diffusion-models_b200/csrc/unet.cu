@@ -15,6 +15,7 @@
 #include <vector>
 #include <memory>
 #include <cstring>
+#include <cstdlib>
 
 namespace {
 
@@ -246,6 +247,10 @@ void build_net(Net* n) {
 // ---- forward ------------------------------------------------------------------------------------------
 struct Ctx { Net* n; cudaStream_t st; bool dry; int rc = RDM_OK; };
 #define RUN(expr) do { if (!cx.dry && cx.rc == RDM_OK) cx.rc = (expr); } while (0)
+// Timing ablation (tools/ablate_forward.py): RDM_SKIP is a bit mask of kernel classes that are NOT launched (results are garbage; only the
+// change of the graph-replayed forward time is meaningful).  1 gn_stats, 2 gn_apply, 4 layernorm, 8 attention, 16 GEMM M>=8192, 32 GEMM M<8192.
+static const int g_skip = getenv("RDM_SKIP") ? atoi(getenv("RDM_SKIP")) : 0;
+#define RUN_UNLESS(bit, expr) do { if (!(g_skip & (bit))) RUN(expr); } while (0)
 
 // GEMM operand / result: an fp32 view (CUDA-core engine) or bf16 hi/lo planes (tcgen05 engine)
 struct Opnd {
@@ -306,8 +311,9 @@ void gemm_any(Ctx& cx, const Opnd& a, int B, int H, int W, int C, int ks, int st
         TcA ta; ta.hi = a.hi; ta.lo = a.lo; ta.ld = a.ldb; ta.B = B; ta.H = H; ta.W = W; ta.C = C; ta.ksize = ks;
         TcW tw; tw.hi = w_hi(n, w); tw.lo = w_lo(n, w); tw.N = N; tw.K = ks * ks * C; tw.ld = tw.K;
         const int nsplit = mode_nsplit(n->mode), f16 = mode_f16(n->mode);
-        if (out.tc()) { e.out = nullptr; RUN(gemm_tc(ta, tw, e, out.hi, out.lo, out.ldb, nsplit, f16, cx.st)); }
-        else { e.out = out.f.p; e.out_ld = out.f.ld; RUN(gemm_tc(ta, tw, e, nullptr, nullptr, 0, nsplit, f16, cx.st)); }
+        const int skip_bit = M >= 8192 ? 16 : 32;
+        if (out.tc()) { e.out = nullptr; RUN_UNLESS(skip_bit, gemm_tc(ta, tw, e, out.hi, out.lo, out.ldb, nsplit, f16, cx.st)); }
+        else { e.out = out.f.p; e.out_ld = out.f.ld; RUN_UNLESS(skip_bit, gemm_tc(ta, tw, e, nullptr, nullptr, 0, nsplit, f16, cx.st)); }
         return;
     }
     GemmA ga; ga.x = a.f.p; ga.ld = a.f.ld; ga.B = B; ga.Hs = H; ga.Ws = W; ga.Cin = C; ga.ksize = ks; ga.stride = stride; ga.ups = ups; ga.Ho = Ho; ga.Wo = Wo;
@@ -332,8 +338,8 @@ void lin_any(Ctx& cx, const Opnd& a, int M, const Lin& l, GemmEpi e, const Opnd&
 
 void gn(Ctx& cx, const Act& x, const Norm& nm, float eps, int silu, const Opnd& y, const Opnd* raw = nullptr) {
     double* s = stats_alloc(cx, x.B, 32);
-    RUN(k_gn_stats(x.v, x.B, x.H * x.W, 32, s, cx.st));
-    RUN(k_gn_apply(x.v, x.B, x.H * x.W, 32, s, eps, nm.g, nm.b, silu, y.out4(), raw ? raw->out4() : Out4(), cx.st));
+    RUN_UNLESS(1, k_gn_stats(x.v, x.B, x.H * x.W, 32, s, cx.st));
+    RUN_UNLESS(2, k_gn_apply(x.v, x.B, x.H * x.W, 32, s, eps, nm.g, nm.b, silu, y.out4(), raw ? raw->out4() : Out4(), cx.st));
 }
 
 void run_res(Ctx& cx, const ResW& r, const Act& x, const float* emb_all, View out) {
@@ -366,7 +372,7 @@ void run_st(Ctx& cx, const STW& s, const Act& x, View out) {
     conv_any(cx, a, x, s.proj_in, GemmEpi(), from_view(t0));
     Opnd nrm = fresh_opnd(cx, M, C, tcp);
     // self-attention (attention.py:93)
-    RUN(k_layernorm(t0, M, s.ln1.g, s.ln1.b, 1e-5f, nrm.out4(), cx.st));
+    RUN_UNLESS(4, k_layernorm(t0, M, s.ln1.g, s.ln1.b, 1e-5f, nrm.out4(), cx.st));
     View qkv = fresh(cx, M, 3 * C);
     Opnd att = fresh_opnd(cx, M, C, tcp);
     if (tcp && mode_f16(n->mode) && k_attention_mma_supported(N, N)) {
@@ -375,24 +381,31 @@ void run_st(Ctx& cx, const STW& s, const Act& x, View out) {
         Opnd qh; qh.hi = (__nv_bfloat16*)A.alloc((size_t)M * 3 * C * 2); qh.ldb = 3 * C; qh.f.C = 3 * C; qh.f16 = 1;
         lin_any(cx, nrm, M, s.qkv, GemmEpi(), qh);
         const __half* qp = reinterpret_cast<const __half*>(qh.hi);
-        RUN(k_attention_mma(qp, qp + C, qp + 2 * C, 3 * C, x.B, N, N, s.heads, scale, att.out4(), cx.st));
+        RUN_UNLESS(8, k_attention_mma(qp, qp + C, qp + 2 * C, 3 * C, x.B, N, N, s.heads, scale, att.out4(), cx.st));
         A.release(mk2);
     } else {
         lin_any(cx, nrm, M, s.qkv, GemmEpi(), from_view(qkv));
-        RUN(k_attention(qkv.cols(0, C), qkv.cols(C, C), qkv.cols(2 * C, C), x.B, N, N, s.heads, scale, att.out4(), cx.st));
+        RUN_UNLESS(8, k_attention(qkv.cols(0, C), qkv.cols(C, C), qkv.cols(2 * C, C), x.B, N, N, s.heads, scale, att.out4(), cx.st));
     }
     View t1 = fresh(cx, M, C);
     { GemmEpi e; e.res = t0.p; e.res_ld = t0.ld; lin_any(cx, att, M, s.o1, e, from_view(t1)); }
     // cross-attention to the retrieved neighbours (attention.py:94); K/V were projected once in set_context
-    RUN(k_layernorm(t1, M, s.ln2.g, s.ln2.b, 1e-5f, nrm.out4(), cx.st));
-    View q2 = qkv.cols(0, C);                                    // reuse the qkv buffer
-    lin_any(cx, nrm, M, s.q2, GemmEpi(), from_view(q2));
+    RUN_UNLESS(4, k_layernorm(t1, M, s.ln2.g, s.ln2.b, 1e-5f, nrm.out4(), cx.st));
     View kv(cx.dry ? nullptr : n->ctx_kv + n->ctx_off[s.id], 2 * C, 2 * C);
-    RUN(k_attention(q2, kv.cols(0, C), kv.cols(C, C), x.B, N, n->ctx_k, s.heads, scale, att.out4(), cx.st));
+    if (tcp && n->ctx_k <= 8 && N >= 16 && !(g_skip & 64)) {
+        // tensor-core engine: softmax(q k^T) v over the k retrieved neighbours runs in the epilogue of the to_q GEMM (one 32-column
+        // accumulator chunk = one head's query), so neither q nor a separate attention launch exists
+        GemmEpi e; e.act = ACT_XATTN; e.xkv = kv.p; e.xkv_ld = kv.ld; e.xv_off = C; e.xk = n->ctx_k; e.xscale = scale; e.rows_per_batch = N;
+        gemm_any(cx, nrm, M, 1, 1, s.q2.in, 1, 1, 0, s.q2.w, nullptr, s.q2.out, e, att);
+    } else {
+        View q2 = qkv.cols(0, C);                                    // reuse the qkv buffer
+        lin_any(cx, nrm, M, s.q2, GemmEpi(), from_view(q2));
+        RUN_UNLESS(8, k_attention(q2, kv.cols(0, C), kv.cols(C, C), x.B, N, n->ctx_k, s.heads, scale, att.out4(), cx.st));
+    }
     View t2 = t0;                                                // t0 is dead after t1 was formed
     { GemmEpi e; e.res = t1.p; e.res_ld = t1.ld; lin_any(cx, att, M, s.o2, e, from_view(t2)); }
     // GEGLU feed-forward (attention.py:95)
-    RUN(k_layernorm(t2, M, s.ln3.g, s.ln3.b, 1e-5f, nrm.out4(), cx.st));
+    RUN_UNLESS(4, k_layernorm(t2, M, s.ln3.g, s.ln3.b, 1e-5f, nrm.out4(), cx.st));
     Opnd g = fresh_opnd(cx, M, 4 * C, tcf);
     { GemmEpi e; e.act = ACT_GEGLU; lin_any(cx, nrm, M, s.ff1, e, g); }
     Opnd t3 = tcp ? fresh_opnd(cx, M, C, true) : from_view(t1);  // only proj_out consumes t3

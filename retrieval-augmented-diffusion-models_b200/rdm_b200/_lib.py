@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librdm_b200.so")
+LIB_PATH = os.environ.get("RDM_B200_LIB") or os.path.join(_HERE, "librdm_b200.so")     # RDM_B200_LIB: developer A/B builds (tools/ab_build.sh)
 CSRC_DIR = os.path.join(os.path.dirname(_HERE), "csrc")
 
 _lib = None
