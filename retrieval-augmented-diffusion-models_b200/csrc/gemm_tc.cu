@@ -23,7 +23,14 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 64, EPI_WARPS = 8, TC_THREADS = 64 + EPI_WARPS * 32;     // warp 0 TMA, warp 1 MMA, 8 epilogue warps
+// Developer build (tools/ab_build.sh ... -DRDM_AB_TIMING): CTA 0 prints SM-clock offsets of its pipeline milestones.
+#ifdef RDM_AB_TIMING
+#define TSTAMP(i) do { if (blockIdx.x == 0) g_ts[i] = clock64(); } while (0)
+#else
+#define TSTAMP(i) do { } while (0)
+#endif
+
+constexpr int BM = 128, BK = 64, EPI_WARPS = 8, EPI_WARP0 = 4, TC_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // warpgroup 0: warp 0 TMA, warp 1 MMA, warps 2-3 idle; warpgroups 1-2: epilogue
 
 // ---- PTX wrappers (mbarrier / TMA helpers live in ptx.cuh) -----------------------------------------------
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
@@ -61,138 +68,195 @@ struct TcSmem {
 };
 
 // ---- epilogue ------------------------------------------------------------------------------------------
-// A thread owns one accumulator ROW (TMEM lane) and 32 consecutive columns per tcgen05.ld.  Bias / time-embedding row vector /
-// activation are applied in registers; the 32x32 (or 32x16 after GEGLU) block is then transposed through a padded per-warp
-// shared-memory tile so that every global access of the warp covers whole 128-byte lines: the residual is read and the
-// result written as [4 or 8 rows] x [128 B | 64 B] per instruction instead of 32 rows x 16 B.
+// Phase 1: a thread owns one accumulator ROW (TMEM lane) and 32 consecutive columns per tcgen05.ld (the fused cross-attention works on
+// that view: 32 columns = one head).  The raw 32x32 block is transposed through a per-warp shared-memory tile.
+// Phase 2: lane (r0 = lane / 8, cg = 4 * (lane % 8)) owns columns cg..cg+3 of rows r0, r0+4, ..., r0+28, so every global access of the
+// warp covers whole 128-byte lines (64-byte after GEGLU), and bias / time-embedding row vector / residual are ONE float4 per lane (per
+// row).  These operands do not depend on the accumulator: they are prefetched into registers (EpiPre) before the accumulator is
+// waited for / while the previous chunk is stored -- with ~200 KB of the SM carved out as shared memory there is next to no L1, every
+// such load is an L2 round trip, and the epilogue of a short GEMM is latency-, not bandwidth-bound.
 constexpr int EPI_WARP_FLOATS = 32 * 32;            // per-warp staging tile, float4 column groups XOR-swizzled by (row & 7): conflict-free
 __device__ __forceinline__ float* epi_at(float* stage, int row, int col4) { return stage + row * 32 + (((col4 >> 2) ^ (row & 7)) << 2); }
 
-// r: this lane's 32 accumulators (row m_warp0 + lane, columns nb..nb+31); stage: this warp's smem tile.
-__device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const uint32_t (&r)[32], float* stage, int lane, int m_warp0, int nb) {
-    const int m = m_warp0 + lane;
-    const bool full = nb + 32 <= p.N;
+struct EpiPre { float4 b[2]; float4 r[8]; };        // bias (+ row vector) for rows 0..15 / 16..31 of the warp; residual per row
+
+__device__ __forceinline__ void epi_prefetch(const TcKernelParams& p, int lane, int m_warp0, int nb, EpiPre& pre) {
+    const int cg = (lane & 7) * 4, r0 = lane >> 3, n = nb + cg;
+    float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bz = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    pre.b[0] = bz; pre.b[1] = bz;
+    if (p.rowvec && p.rows_per_batch >= 16) {       // 16 | rows_per_batch (power-of-two grids): rows 0..15 and 16..31 each lie in one image
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            int row = m_warp0 + 16 * s; row = row < p.M ? row : p.M - 1;
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.rowvec + (size_t)(row / p.rows_per_batch) * p.rowvec_ld + n));
+            pre.b[s].x += t.x; pre.b[s].y += t.y; pre.b[s].z += t.z; pre.b[s].w += t.w;
+        }
+    }
+    const bool geglu = p.act == ACT_GEGLU;
+    const int no = geglu ? (n >> 1) : n;
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int mo = m_warp0 + r0 + 4 * it;
+        pre.r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.res && mo < p.M) {
+            if (geglu) { const float2 t = __ldcs(reinterpret_cast<const float2*>(p.res + (size_t)mo * p.res_ld + no)); pre.r[it].x = t.x; pre.r[it].y = t.y; }
+            else pre.r[it] = __ldcs(reinterpret_cast<const float4*>(p.res + (size_t)mo * p.res_ld + no));
+        }
+    }
+}
+
+// ragged last chunk (N not a multiple of 32; only the 4-channel output conv): the row goes through the warp's staging tile so that a
+// ROLLED scalar loop can index it (a rolled loop over registers would put them in local memory; an unrolled one is 32x the code)
+__device__ __forceinline__ void epilogue_ragged(const TcKernelParams& p, const uint32_t (&r)[32], float* stage, int lane, int m, int nb) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(epi_at(stage, lane, j)) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+    __syncwarp();
+    if (m >= p.M) return;
+    const int bidx = m / p.rows_per_batch, nv = p.N - nb < 32 ? p.N - nb : 32;
+#pragma unroll 1
+    for (int j = 0; j < nv; j++) {
+        const int n = nb + j;
+        float t = epi_at(stage, lane, j & ~3)[j & 3];
+        if (p.bias) t += __ldg(p.bias + n);
+        if (p.rowvec) t += __ldg(p.rowvec + (size_t)bidx * p.rowvec_ld + n);
+        if (p.act == ACT_SILU) t = silu_f(t);
+        else if (p.act == ACT_QUICKGELU) t = t / (1.f + expf(-1.702f * t));
+        if (p.res) t += p.res[(size_t)m * p.res_ld + n];
+        if (p.out) p.out[(size_t)m * p.out_ld + n] = t;
+        else {
+            unsigned short h, l; split16(t, p.f16, h, l);
+            reinterpret_cast<unsigned short*>(p.out_hi)[(size_t)m * p.out_bf_ld + n] = h;
+            if (p.out_lo) reinterpret_cast<unsigned short*>(p.out_lo)[(size_t)m * p.out_bf_ld + n] = l;
+        }
+    }
+}
+
+// fused cross-attention on one row's 32-column chunk (= the query of head nb/32 for token m): attend to the (<= 8) retrieved-context keys
+// of this sample.  The K/V rows of this head (1-2 images per warp) are staged once per chunk in the warp's transpose tile and read back as
+// shared-memory broadcasts.  Online softmax in a deliberately ROLLED key loop: a chunk executes this once, and straight-line code of that
+// size would be fetched from L2 every time (instruction-cache misses cost more than the arithmetic).
+__device__ __forceinline__ void epilogue_xattn(const TcKernelParams& p, float (&v)[32], float* stage, int lane, int m_warp0, int nb) {
+    const int m = m_warp0 + lane, mm = m < p.M ? m : p.M - 1, hw = p.rows_per_batch;
+    const int b0 = (m_warp0 < p.M ? m_warp0 : p.M - 1) / hw, b1 = (m_warp0 + 31 < p.M ? m_warp0 + 31 : p.M - 1) / hw;
+    const int per_img = 2 * p.xk * 8;                              // float4 pieces per image: [K | V][xk][32 floats]
+    __syncwarp();
+    for (int i = lane; i < (b1 - b0 + 1) * per_img; i += 32) {
+        const int img = i / per_img, r = i - img * per_img, kvsel = r / (p.xk * 8), r2 = r - kvsel * p.xk * 8;
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.xkv + ((size_t)(b0 + img) * p.xk + (r2 >> 3)) * p.xkv_ld + nb + kvsel * p.xv_off) + (r2 & 7));
+        *reinterpret_cast<float4*>(stage + (size_t)i * 4) = t;
+    }
+    __syncwarp();
+    const float* kb = stage + (size_t)(mm / hw - b0) * per_img * 4;
+    float o[32], mx = -3.0e38f, l = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i++) o[i] = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < p.xk; j++) {
+        const float4* kr = reinterpret_cast<const float4*>(kb + j * 32);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            const float4 t = kr[i], u = kr[i + 1];
+            s0 = fmaf(v[4 * i], t.x, s0); s0 = fmaf(v[4 * i + 1], t.y, s0); s0 = fmaf(v[4 * i + 2], t.z, s0); s0 = fmaf(v[4 * i + 3], t.w, s0);
+            s1 = fmaf(v[4 * i + 4], u.x, s1); s1 = fmaf(v[4 * i + 5], u.y, s1); s1 = fmaf(v[4 * i + 6], u.z, s1); s1 = fmaf(v[4 * i + 7], u.w, s1);
+        }
+        const float sj = (s0 + s1) * p.xscale_log2e, mn = fmaxf(mx, sj), corr = exp2f(mx - mn), pj = exp2f(sj - mn);
+        mx = mn; l = fmaf(l, corr, pj);
+        const float4* vr = reinterpret_cast<const float4*>(kb + (p.xk + j) * 32);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 t = vr[i];
+            o[4 * i] = fmaf(pj, t.x, o[4 * i] * corr); o[4 * i + 1] = fmaf(pj, t.y, o[4 * i + 1] * corr);
+            o[4 * i + 2] = fmaf(pj, t.z, o[4 * i + 2] * corr); o[4 * i + 3] = fmaf(pj, t.w, o[4 * i + 3] * corr);
+        }
+    }
+    const float il = 1.f / l;
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = o[i] * il;
+}
+
+// r: this lane's 32 accumulators (row m_warp0 + lane, columns nb..nb+31, nb + 32 <= N); stage: this warp's smem tile; pre: operands of THIS
+// chunk (epi_prefetch).  nb_next >= 0: prefetch the operands of that chunk (same rows) into `pre` once this chunk has consumed them.
+__device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const uint32_t (&r)[32], float* stage, int lane, int m_warp0, int nb, EpiPre& pre, int nb_next, float* part) {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
-    if (!full) {
-        // ragged last chunk (N not a multiple of 32; only the 4-channel output conv): predicated scalar path
-        if (m < p.M) {
-            const int bidx = m / p.rows_per_batch;
-#ifdef RDM_AB_RAGGED_UNROLL4
-#pragma unroll 4
-#else
+    const int cg = (lane & 7) * 4, r0 = lane >> 3, n = nb + cg;
+    if (p.act == ACT_XATTN && !part) {             // no bias / residual operands on this path (checked on the host): `pre` is dead here
+        epilogue_xattn(p, v, stage, lane, m_warp0, nb);
+        __syncwarp();
 #pragma unroll
-#endif
-            for (int j = 0; j < 32; j++) {
-                const int n = nb + j;
-                if (n < p.N) {
-                    float t = v[j];
-                    if (p.bias) t += __ldg(p.bias + n);
-                    if (p.rowvec) t += __ldg(p.rowvec + (size_t)bidx * p.rowvec_ld + n);
-                    if (p.act == ACT_SILU) t = silu_f(t);
-                    else if (p.act == ACT_QUICKGELU) t = t / (1.f + expf(-1.702f * t));
-                    if (p.res) t += p.res[(size_t)m * p.res_ld + n];
-                    if (p.out) p.out[(size_t)m * p.out_ld + n] = t;
-                    else {
-                        unsigned short h, l; split16(t, p.f16, h, l);
-                        reinterpret_cast<unsigned short*>(p.out_hi)[(size_t)m * p.out_bf_ld + n] = h;
-                        if (p.out_lo) reinterpret_cast<unsigned short*>(p.out_lo)[(size_t)m * p.out_bf_ld + n] = l;
-                    }
-                }
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(epi_at(stage, lane, j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int mo = m_warp0 + r0 + 4 * it;
+            const float4 o = *reinterpret_cast<const float4*>(epi_at(stage, r0 + 4 * it, cg));
+            if (mo < p.M) {
+                if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)mo * p.out_ld + n) = o;
+                else store_planes4(p.out_hi + (size_t)mo * p.out_bf_ld + n, p.out_lo ? p.out_lo + (size_t)mo * p.out_bf_ld + n : nullptr, p.f16, o.x, o.y, o.z, o.w);
             }
         }
         return;
     }
-    if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
-    }
-    if (p.rowvec) {
-        const int mm = m < p.M ? m : p.M - 1;
-        const float* rv = p.rowvec + (size_t)(mm / p.rows_per_batch) * p.rowvec_ld + nb;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) { float4 t = __ldg(reinterpret_cast<const float4*>(rv + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
-    }
-    int wout = 32, no = nb;                       // output width of this chunk and its first output column
-    if (p.act == ACT_XATTN) {
-        // v[0..31] is the query of head nb/32 for token m: attend to the (<= 8) retrieved-context keys of this sample.  With ~200 KB of the
-        // SM's unified array carved out as shared memory there is next to no L1, so the K/V rows of this head (1-2 images per warp) are
-        // staged once per chunk in the warp's transpose tile and read back as shared-memory broadcasts.
-        const int mm = m < p.M ? m : p.M - 1, hw = p.rows_per_batch;
-        const int b0 = (m_warp0 < p.M ? m_warp0 : p.M - 1) / hw, b1 = (m_warp0 + 31 < p.M ? m_warp0 + 31 : p.M - 1) / hw;
-        const int per_img = 2 * p.xk * 8;                              // float4 pieces per image: [K | V][xk][32 floats]
-        __syncwarp();
-        for (int i = lane; i < (b1 - b0 + 1) * per_img; i += 32) {
-            const int img = i / per_img, r = i - img * per_img, kvsel = r / (p.xk * 8), r2 = r - kvsel * p.xk * 8;
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.xkv + ((size_t)(b0 + img) * p.xk + (r2 >> 3)) * p.xkv_ld + nb + kvsel * p.xv_off) + (r2 & 7));
-            *reinterpret_cast<float4*>(stage + (size_t)i * 4) = t;
-        }
-        __syncwarp();
-        const float* kb = stage + (size_t)(mm / hw - b0) * per_img * 4;
-        // online softmax over the keys; deliberately a rolled loop: a chunk executes this once, and straight-line code of that size would be
-        // fetched from L2 every time (instruction-cache misses cost more than the arithmetic)
-        float o[32], mx = -3.0e38f, l = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; i++) o[i] = 0.f;
-#pragma unroll 1
-        for (int j = 0; j < p.xk; j++) {
-            const float4* kr = reinterpret_cast<const float4*>(kb + j * 32);
-            float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-                const float4 t = kr[i], u = kr[i + 1];
-                s0 = fmaf(v[4 * i], t.x, s0); s0 = fmaf(v[4 * i + 1], t.y, s0); s0 = fmaf(v[4 * i + 2], t.z, s0); s0 = fmaf(v[4 * i + 3], t.w, s0);
-                s1 = fmaf(v[4 * i + 4], u.x, s1); s1 = fmaf(v[4 * i + 5], u.y, s1); s1 = fmaf(v[4 * i + 6], u.z, s1); s1 = fmaf(v[4 * i + 7], u.w, s1);
-            }
-            const float sj = (s0 + s1) * p.xscale_log2e, mn = fmaxf(mx, sj), corr = exp2f(mx - mn), pj = exp2f(sj - mn);
-            mx = mn; l = fmaf(l, corr, pj);
-            const float4* vr = reinterpret_cast<const float4*>(kb + (p.xk + j) * 32);
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float4 t = vr[i];
-                o[4 * i] = fmaf(pj, t.x, o[4 * i] * corr); o[4 * i + 1] = fmaf(pj, t.y, o[4 * i + 1] * corr);
-                o[4 * i + 2] = fmaf(pj, t.z, o[4 * i + 2] * corr); o[4 * i + 3] = fmaf(pj, t.w, o[4 * i + 3] * corr);
-            }
-        }
-        const float il = 1.f / l;
-#pragma unroll
-        for (int i = 0; i < 32; i++) v[i] = o[i] * il;
-    } else if (p.act == ACT_GEGLU) {
-#pragma unroll
-        for (int j = 0; j < 16; j++) v[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
-        wout = 16; no = nb >> 1;
-    } else if (p.act == ACT_SILU) {
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = silu_f(v[j]);
-    } else if (p.act == ACT_QUICKGELU) {
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = v[j] / (1.f + expf(-1.702f * v[j]));
-    }
     // transpose through shared memory
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) if (j < wout) *reinterpret_cast<float4*>(epi_at(stage, lane, j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(epi_at(stage, lane, j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     __syncwarp();
-    const int lpr = wout >> 2;                     // lanes per row: 8 (128 B) or 4 (64 B)
-    const int rstep = 32 / lpr, r0 = lane / lpr, cg = (lane % lpr) * 4;
-    float4 t[8], q[8];
+    if (part) {                                    // split-K partial tile [M, N] fp32: raw accumulators
 #pragma unroll
-    for (int it = 0; it < 8; it++) {               // all residual loads in flight before the first store
-        const int rr = r0 + it * rstep, mo = m_warp0 + rr;
-        const bool ok = rr < 32 && mo < p.M;
-        t[it] = ok ? *reinterpret_cast<const float4*>(epi_at(stage, rr, cg)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        q[it] = (ok && p.res) ? __ldcs(reinterpret_cast<const float4*>(p.res + (size_t)mo * p.res_ld + no + cg)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int it = 0; it < 8; it++) {
+            const int mo = m_warp0 + r0 + 4 * it;
+            if (mo < p.M) *reinterpret_cast<float4*>(part + (size_t)mo * p.N + n) = *reinterpret_cast<const float4*>(epi_at(stage, r0 + 4 * it, cg));
+        }
+        return;
     }
+    const bool slow_rv = p.rowvec && p.rows_per_batch < 16;
+    float4 t[8];
 #pragma unroll
-    for (int it = 0; it < 8; it++) {
-        const int rr = r0 + it * rstep, mo = m_warp0 + rr;
-        if (rr < 32 && mo < p.M) {
-            float4 o = make_float4(t[it].x + q[it].x, t[it].y + q[it].y, t[it].z + q[it].z, t[it].w + q[it].w);
-            if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)mo * p.out_ld + no + cg) = o;
-            else store_planes4(p.out_hi + (size_t)mo * p.out_bf_ld + no + cg, p.out_lo ? p.out_lo + (size_t)mo * p.out_bf_ld + no + cg : nullptr, p.f16, o.x, o.y, o.z, o.w);
+    for (int it = 0; it < 8; it++) t[it] = *reinterpret_cast<const float4*>(epi_at(stage, r0 + 4 * it, cg));
+    if (p.act == ACT_GEGLU) {
+        const int no = n >> 1;
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int mo = m_warp0 + r0 + 4 * it;
+            if (mo < p.M) {
+                const float4 bb = pre.b[it >> 2];
+                const float o0 = (t[it].x + bb.x) * gelu_erf(t[it].y + bb.y) + pre.r[it].x, o1 = (t[it].z + bb.z) * gelu_erf(t[it].w + bb.w) + pre.r[it].y;
+                if (p.out) *reinterpret_cast<float2*>(p.out + (size_t)mo * p.out_ld + no) = make_float2(o0, o1);
+                else {
+                    unsigned short h0, l0, h1, l1; split16(o0, p.f16, h0, l0); split16(o1, p.f16, h1, l1);
+                    *reinterpret_cast<uint32_t*>(p.out_hi + (size_t)mo * p.out_bf_ld + no) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                    if (p.out_lo) *reinterpret_cast<uint32_t*>(p.out_lo + (size_t)mo * p.out_bf_ld + no) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int mo = m_warp0 + r0 + 4 * it;
+            if (mo < p.M) {
+                const float4 bb = pre.b[it >> 2];
+                float4 o = make_float4(t[it].x + bb.x, t[it].y + bb.y, t[it].z + bb.z, t[it].w + bb.w);
+                if (slow_rv) {
+                    const float4 rv = __ldg(reinterpret_cast<const float4*>(p.rowvec + (size_t)(mo / p.rows_per_batch) * p.rowvec_ld + n));
+                    o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                }
+                if (p.act == ACT_SILU) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+                else if (p.act == ACT_QUICKGELU) {
+                    o.x = o.x / (1.f + expf(-1.702f * o.x)); o.y = o.y / (1.f + expf(-1.702f * o.y));
+                    o.z = o.z / (1.f + expf(-1.702f * o.z)); o.w = o.w / (1.f + expf(-1.702f * o.w));
+                }
+                o.x += pre.r[it].x; o.y += pre.r[it].y; o.z += pre.r[it].z; o.w += pre.r[it].w;
+                if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)mo * p.out_ld + n) = o;
+                else store_planes4(p.out_hi + (size_t)mo * p.out_bf_ld + n, p.out_lo ? p.out_lo + (size_t)mo * p.out_bf_ld + n : nullptr, p.f16, o.x, o.y, o.z, o.w);
+            }
         }
     }
+    if (nb_next >= 0) epi_prefetch(p, lane, m_warp0, nb_next, pre);
 }
 
 // epilogue of 4 consecutive accumulator columns n..n+3 of row m (bias, time-embedding row vector, activation, residual, store)
@@ -263,6 +327,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.taps * p.kb_per_tap;
     const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + BM - 1) / BM, nitems = ntn * ntm * p.splits;
+#ifdef RDM_AB_TIMING
+    __shared__ long long g_ts[8];
+    unsigned long long gt0 = 0;
+    if (threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0)); for (int i = 0; i < 8; i++) g_ts[i] = 0; TSTAMP(0); }
+#endif
     pdl_launch_dependents();                       // the next kernel may start its own prologue as soon as every CTA of this grid runs
 
     if (warp == 0 && lane == 0) {
@@ -281,7 +350,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TSTAMP(1);
 
+    // Register re-allocation between the warp roles (setmaxnreg acts on whole WARPGROUPS, hence the 4-warp issuer group): 12 warps start
+    // with 168 registers/thread; warpgroup 0 (TMA issuer, MMA issuer, two idle warps) gives registers back, the two epilogue warpgroups
+    // (operand prefetch + 32 accumulators + transpose tiles) take them: 4 x 32 x 56 + 8 x 32 x 224 = 64512 = 384 x 168.
+    if (warp < EPI_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         if (lane == 0) {
             // PDL prologue: the WEIGHT tiles of the first stages do not depend on the previous kernel -> request them before waiting
@@ -300,6 +375,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 }
             }
             pdl_wait();                                                  // activations / residuals of the previous kernels are now visible
+            TSTAMP(2);
             int it = 0;                                                  // global k-block counter (ring position)
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int tile = item / p.splits, sp = item - tile * p.splits;
@@ -340,6 +416,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
+#ifdef RDM_AB_TIMING
+                    if (it == 0) TSTAMP(3);
+#endif
                     const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES), b_hi = a_hi + S::A_BYTES;
                     const uint32_t b_lo = b_hi + S::B_BYTES, a_lo = b_lo + S::B_BYTES;
 #pragma unroll
@@ -352,14 +431,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     umma_commit(&empty[s]);                // frees the stage once the MMAs above have read it
                 }
                 umma_commit(&tmem_full[buf]);              // accumulator complete
+                TSTAMP(4);
             }
         }
+    }
     } else {
         // epilogue: warp w may touch TMEM lanes [32*(w%4), +32); each lane quarter is served by TWO warps that alternate column chunks
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         pdl_wait();                                   // residual / row-vector operands come from previous kernels
-        const int q = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
+        const int q = warp & 3, half = (warp - EPI_WARP0) >> 2, ew = warp - EPI_WARP0;
         int lt = 0;
-        TcKernelParams pp = p;
         if (p.cluster) {
             // cluster split-K: park this CTA's fp32 partial tile in (now idle) pipeline shared memory; the cluster-wide reduction follows below
             mbar_wait(&tmem_full[0], 0);
@@ -376,25 +457,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         } else
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, lt++) {
             const int tile = item / p.splits, sp = item - tile * p.splits;
-            if (p.splits > 1) {                                   // raw partial sums; the reduce kernel applies the epilogue
-                pp.bias = nullptr; pp.rowvec = nullptr; pp.res = nullptr; pp.act = ACT_NONE; pp.out_hi = nullptr; pp.out_lo = nullptr;
-                pp.out = p.part + (size_t)sp * p.M * p.N; pp.out_ld = p.N;
-            }
+            float* part = p.splits > 1 ? p.part + (size_t)sp * p.M * p.N : nullptr;    // raw partial sums; the reduce kernel applies the epilogue
             const int buf = lt & 1;
             const int mt = tile / ntn, n0 = (tile % ntn) * BN;
             const int m_warp0 = mt * BM + q * 32;
+            EpiPre pre;
+            if (!part && m_warp0 < p.M && n0 + half * 32 + 32 <= p.N) epi_prefetch(p, lane, m_warp0, n0 + half * 32, pre);      // overlaps the mainloop
             mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
             tc_fence_after();
+#ifdef RDM_AB_TIMING
+            if (warp == EPI_WARP0 && lane == 0 && lt == 0) TSTAMP(5);
+#endif
 #pragma unroll 1
             for (int c = half; c < BN / 32; c += 2) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
                 const int nb = n0 + c * 32;
-                if (m_warp0 < p.M && nb < p.N) epilogue_chunk(pp, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32);
+                if (m_warp0 >= p.M || nb >= p.N) continue;
+                uint32_t r[32];
+                tmem_ld32(taddr, r);
+                if (nb + 32 <= p.N) {
+                    const int nbn = nb + 64;                       // this warp's next chunk of the tile
+                    epilogue_chunk(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb, pre, (c + 2 < BN / 32 && nbn + 32 <= p.N) ? nbn : -1, part);
+                } else epilogue_ragged(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0 + lane, nb);     // (split-K needs N % 4 == 0 ... never a partial tile here)
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+#ifdef RDM_AB_TIMING
+            if (warp == EPI_WARP0 && lane == 0) TSTAMP(6);
+#endif
         }
     }
     tc_fence_before();
@@ -403,13 +494,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // Every CTA of the cluster (rank = split) now holds a 128 x BN fp32 partial in its shared memory.  CTA r reduces the r-th slice of
         // the tile over all ranks through distributed shared memory (fixed summation order: deterministic) and applies the real epilogue.
         cluster_sync_all();
-        if (warp >= 2) {
+        if (warp >= EPI_WARP0) {
             const int tile = blockIdx.x / p.splits, rank = blockIdx.x - tile * p.splits;
             const int mt = tile / ntn, n0 = (tile % ntn) * BN;
             constexpr int C4 = BN / 4, TOTAL4 = BM * C4;
             const int i0 = (int)((long long)TOTAL4 * rank / p.splits), i1 = (int)((long long)TOTAL4 * (rank + 1) / p.splits);
             const uint32_t red_base = smem_u32(smem);
-            for (int i = i0 + (int)threadIdx.x - 64; i < i1; i += EPI_WARPS * 32) {
+            for (int i = i0 + (int)threadIdx.x - EPI_WARP0 * 32; i < i1; i += EPI_WARPS * 32) {
                 const int row = i / C4, c4 = i - row * C4;
                 const int m = mt * BM + row, n = n0 + c4 * 4;
                 if (m >= p.M || n >= p.N) continue;
@@ -424,6 +515,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         cluster_sync_all();                          // no CTA may exit (and free its shared memory) while a peer still reads it
     }
+#ifdef RDM_AB_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const long long t7 = clock64();
+        printf("TCT M=%d N=%d K=%d BN=%d sp=%d cl=%d act=%d grid=%d gt0=%llu | setup %lld pdlwait %lld firstfull %lld lastmma %lld epi0 %lld epiend %lld end %lld\n", p.M, p.N, nkb * BK, BN, p.splits, p.cluster, p.act,
+               (int)gridDim.x, gt0, g_ts[1] - g_ts[0], g_ts[2] - g_ts[0], g_ts[3] - g_ts[0], g_ts[4] - g_ts[0], g_ts[5] - g_ts[0], g_ts[6] - g_ts[0], t7 - g_ts[0]);
+    }
+#endif
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS) : "memory");
@@ -592,7 +690,7 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
         for (int cl = 0; cl <= 1; cl++) {
             if (cl == 1 && use_cluster == 0) continue;
             for (int sp = cl ? 2 : 1; sp <= (cl ? 8 : 16); sp++) {
-                if (sp > 1 && (no_split || e.act == ACT_XATTN || nkb_total / sp < 4 || (w.N & 3) || (!cl && (size_t)sp * M * w.N * 4 > ((size_t)48 << 20)))) break;
+                if (sp > 1 && (no_split || e.act == ACT_XATTN || nkb_total / sp < 4 || (w.N & 31) || (!cl && (size_t)sp * M * w.N * 4 > ((size_t)48 << 20)))) break;
                 if (sp > 1 && !cl && use_cluster == 2) break;
                 const int kbps = (nkb_total + sp - 1) / sp;
                 if ((sp - 1) * kbps >= nkb_total) continue;                  // an empty split
