@@ -25,14 +25,18 @@ namespace {
 
 // Developer build (tools/ab_build.sh ... -DRDM_AB_TIMING): CTA 0 prints SM-clock offsets of its pipeline milestones.
 #ifdef RDM_AB_TIMING
+__shared__ long long g_ts[24];
 #define TSTAMP(i) do { if (blockIdx.x == 0) g_ts[i] = clock64(); } while (0)
+#define TSTAMP_EPI(i) do { if (blockIdx.x == 0 && threadIdx.x == 128 && g_ts[i] == 0) g_ts[i] = clock64(); } while (0)     /* first epilogue warp, first time */
 #else
 #define TSTAMP(i) do { } while (0)
+#define TSTAMP_EPI(i) do { } while (0)
 #endif
 
 constexpr int BM = 128, BK = 64, EPI_WARPS = 8, EPI_WARP0 = 4, TC_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // warpgroup 0: warp 0 TMA, warp 1 MMA, warps 2-3 idle; warpgroups 1-2: epilogue
 
 // ---- PTX wrappers (mbarrier / TMA helpers live in ptx.cuh) -----------------------------------------------
+// exact-erf GELU (F.gelu default, ldm FeedForward GEGLU).  (A two-MUFU Abramowitz-Stegun erf was measured SLOWER than erff's FMA-only polynomial here.)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
 
@@ -183,6 +187,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+    TSTAMP_EPI(8);
     const int cg = (lane & 7) * 4, r0 = lane >> 3, n = nb + cg;
     if (p.act == ACT_XATTN && !part) {             // no bias / residual operands on this path (checked on the host): `pre` is dead here
         epilogue_xattn(p, v, stage, lane, m_warp0, nb);
@@ -218,6 +223,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
     float4 t[8];
 #pragma unroll
     for (int it = 0; it < 8; it++) t[it] = *reinterpret_cast<const float4*>(epi_at(stage, r0 + 4 * it, cg));
+    TSTAMP_EPI(9);
     if (p.act == ACT_GEGLU) {
         const int no = n >> 1;
 #pragma unroll
@@ -256,7 +262,9 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
             }
         }
     }
+    TSTAMP_EPI(10);
     if (nb_next >= 0) epi_prefetch(p, lane, m_warp0, nb_next, pre);
+    TSTAMP_EPI(11);
 }
 
 // epilogue of 4 consecutive accumulator columns n..n+3 of row m (bias, time-embedding row vector, activation, residual, store)
@@ -328,9 +336,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int nkb = p.taps * p.kb_per_tap;
     const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + BM - 1) / BM, nitems = ntn * ntm * p.splits;
 #ifdef RDM_AB_TIMING
-    __shared__ long long g_ts[8];
     unsigned long long gt0 = 0;
-    if (threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0)); for (int i = 0; i < 8; i++) g_ts[i] = 0; TSTAMP(0); }
+    if (threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0)); for (int i = 0; i < 24; i++) g_ts[i] = 0; TSTAMP(0); }
+    __syncthreads();
 #endif
     pdl_launch_dependents();                       // the next kernel may start its own prologue as soon as every CTA of this grid runs
 
@@ -520,6 +528,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const long long t7 = clock64();
         printf("TCT M=%d N=%d K=%d BN=%d sp=%d cl=%d act=%d grid=%d gt0=%llu | setup %lld pdlwait %lld firstfull %lld lastmma %lld epi0 %lld epiend %lld end %lld\n", p.M, p.N, nkb * BK, BN, p.splits, p.cluster, p.act,
                (int)gridDim.x, gt0, g_ts[1] - g_ts[0], g_ts[2] - g_ts[0], g_ts[3] - g_ts[0], g_ts[4] - g_ts[0], g_ts[5] - g_ts[0], g_ts[6] - g_ts[0], t7 - g_ts[0]);
+        printf("TCE chunk0: tmemld %lld transposed %lld stored %lld prefetched %lld (cycles after epi0)\n", g_ts[8] - g_ts[5], g_ts[9] - g_ts[5], g_ts[10] - g_ts[5], g_ts[11] - g_ts[5]);
     }
 #endif
     if (warp == 1) {
