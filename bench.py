@@ -29,6 +29,9 @@ UNET = dict(image_size=32, in_channels=4, out_channels=4, model_channels=192, at
             channel_mult=[1, 2, 3, 5], num_head_channels=32, transformer_depth=1, context_dim=512)
 N_DB, D, K_NN, BATCH, S_DDIM, CFG_SCALE = 1_281_167, 512, 4, 16, 100, 2.0
 FLOP_PER_FWD_SAMPLE = 50.56e9          # SURVEY.md section 6 (32x32x4 latent, k=4)
+# dram__bytes_read.sum + dram__bytes_write.sum over the 197 gemm_tc launches of one forward (fp16x2, B2 = 32), from the ncu pass committed as
+# profiles/gemm_tc_dram_r1f.csv (1.79 GB read = two fp16 weight planes + activations, 1.28 GB written)
+TRAFFIC_BYTES, TRAFFIC_SRC = 3.07e9, "profiles/gemm_tc_dram_r1f.csv (ncu, per forward = 197 launches, fp16x2)"
 
 
 def peaks():
@@ -245,8 +248,26 @@ def main():
     pk = peaks()
     unet.set_context(torch.cat([searcher.gather_device(searcher.search_device(torch.nn.functional.normalize(searcher.gather_device(d_q[0]), dim=1), K_NN)[0]), uncond]))
     prof = [unet.profile_forward(d_x[0], torch.full((2 * BATCH,), int(t), device=dev)) for t in (991, 501, 11)]
-    tc_ms = float(np.mean([p["tc_ms"] for p in prof])); tc_flop = float(np.mean([p["tc_flop"] for p in prof]))
+    tc_flop = float(np.mean([p["tc_flop"] for p in prof])); tc_ms_events = float(np.mean([p["tc_ms"] for p in prof]))
     n_tc = prof[0]["n_tc"]
+    # In-graph duration of the tcgen05 launches: graph-replayed forward with every kernel vs. the same graph without the GEMM launches
+    # (rdm_unet_set_ablation), CUDA events on the launching stream.  Per-launch event brackets cannot resolve ~10 us kernels (an event
+    # record costs microseconds on the device timeline), so they are reported separately as tc_ms_event_brackets.
+    t_probe = torch.full((2 * BATCH,), 501, device=dev)
+
+    def fwd_ms(mask, reps=20):
+        unet.set_ablation(mask)
+        for _ in range(3):
+            unet.forward(d_x[0], t_probe)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); a.record()
+        for _ in range(reps):
+            unet.forward(d_x[0], t_probe)
+        b.record(); torch.cuda.synchronize()
+        unet.set_ablation(0)
+        return a.elapsed_time(b) / reps
+    fwd_full, fwd_nogemm = fwd_ms(0), fwd_ms(48)
+    tc_ms = fwd_full - fwd_nogemm
     achieved = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     # kNN scan alone (the HBM-bound sink)
     qh = torch.nn.functional.normalize(searcher.gather_device(d_q[0]), dim=1)
@@ -280,11 +301,13 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM; all conv / linear layers of one U-Net forward)", "achieved": achieved,
                      "peak": pk["bf16_tflops_sustained"], "peak_src": pk["src"] + " bf16 sustained (kernel timed inside a long step)", "unit": "TFLOP/s",
-                     "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+                     "frac": achieved / pk["bf16_tflops_sustained"], "traffic": TRAFFIC_BYTES,
                      "algorithmic_flop_per_forward": tc_flop, "tc_launches_per_forward": n_tc, "tc_ms_per_forward": tc_ms,
-                     "forward_ms_eager_profiled": float(np.mean([p["total_ms"] for p in prof])),
+                     "forward_ms_graph": fwd_full, "forward_ms_graph_without_gemms": fwd_nogemm, "tc_ms_event_brackets": tc_ms_events,
+                     "traffic_src": TRAFFIC_SRC,
                      "mma_per_product": {"bf16x3": 3, "fp16x2": 2, "fp16": 1, "bf16": 1, "fp32": 0}[args.mode],
-                     "note": "algorithmic FLOPs over the CUDA-event time of the tcgen05 launches; split-operand modes issue 2-3 MMAs per product, so frac <= 1/2 (fp16x2) or 1/3 (bf16x3)"},
+                     "note": "algorithmic FLOPs of all tcgen05 launches of one U-Net forward over their in-graph duration (forward minus GEMM-less forward, "
+                             "CUDA events); split-operand modes issue 2-3 MMAs per product, so frac <= 1/2 (fp16x2) or 1/3 (bf16x3)"},
         "knn": {"ms": knn_ms, "qps": BATCH / knn_ms * 1e3, "gbs": knn_gbs, "frac_hbm": knn_gbs / pk["hbm_gbs"], "peak_gbs": pk["hbm_gbs"]},
     }
     if not args.no_cpu_baseline and world == 1:

@@ -126,9 +126,14 @@ RDM_API int rdm_unet_set_context(rdm_unet_t* h, const float* ctx_dev, int32_t B2
 RDM_API int rdm_unet_forward(rdm_unet_t* h, const float* x_dev, int32_t Bx, const int64_t* t_dev, int32_t B2,
                      int32_t H, int32_t W, float* eps_out_dev, void* stream);
 
+/* Measurement aid: bit mask of kernel classes that are NOT launched by the following forwards (1 GroupNorm statistics, 2 GroupNorm apply,
+ * 4 LayerNorm, 8 attention, 16 GEMMs with M >= 8192, 32 GEMMs with M < 8192, 64 un-fuse the cross-attention).  Outputs are garbage while a
+ * mask is set; bench.py uses full-forward time minus GEMM-less forward time as the in-graph duration of the tcgen05 launches. */
+RDM_API int rdm_unet_set_ablation(rdm_unet_t* h, int32_t mask);
 /* CUDA-graph replay of the forward (default on).  Off: every kernel is launched eagerly. */
 RDM_API int rdm_unet_set_graph(rdm_unet_t* h, int32_t on);
-/* Same as rdm_unet_forward but eager, with CUDA events around every GEMM launch; synchronises.  out8 =
+/* rdm_unet_forward, then the same forward replayed from a CUDA graph captured with external event-record nodes around every
+ * GEMM launch (so the brackets hold the graph-replayed kernel only, no host launch gaps); synchronises.  out8 =
  * {tcgen05 GEMM ms, tcgen05 GEMM algorithmic flop, CUDA-core GEMM ms, CUDA-core GEMM flop, whole forward ms,
  *  #tcgen05 launches, #CUDA-core GEMM launches, 0}.  Used by bench.py for the live roofline numbers. */
 RDM_API int rdm_unet_profile_forward(rdm_unet_t* h, const float* x_dev, int32_t Bx, const int64_t* t_dev, int32_t B2,

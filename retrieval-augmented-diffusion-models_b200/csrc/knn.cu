@@ -328,25 +328,54 @@ knn_scan_kernel(const T* __restrict__ db, const float* __restrict__ inv, long lo
     }
 }
 
-// grid = QP, block = 1024: threshold key[q] = KSEL-th largest of the sample maxima (0 if fewer exist); resets the counters.
-__global__ void __launch_bounds__(1024)
-knn_threshold_kernel(const u64* __restrict__ maxima, size_t per_q, u64* __restrict__ thr_key, unsigned* __restrict__ cand_cnt, unsigned* __restrict__ overflow) {
-    __shared__ u64 s_keys[32][LIST];
-    const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u64* src = maxima + (size_t)qi * per_q;
-    u64 cur = 0ull;
-    for (size_t b = (size_t)warp * 32; b < per_q; b += 32 * 32) {
-        u64 batch = b + lane < per_q ? src[b + lane] : 0ull;
-        const u64 cur_min = shfl_u64(cur, 31);                         // cur is sorted descending
-        if (__any_sync(FULL, batch > cur_min)) cur = warp_merge_top32(cur, batch, lane);
-    }
+// Tree merge of the 32 per-warp descending top-32 lists of a 1024-thread CTA (5 rounds instead of 31 serial merges); the result is
+// warp 0's `cur`.  nlists: number of leading warps that hold a list (power of two).
+__device__ __forceinline__ u64 cta_tree_merge(u64 cur, u64 (*s_keys)[LIST], int warp, int lane, int nlists) {
     s_keys[warp][lane] = cur;
     __syncthreads();
-    if (warp != 0) return;
-    cur = s_keys[0][lane];
-    for (int w = 1; w < 32; w++) cur = warp_merge_top32(cur, s_keys[w][lane], lane);
-    if (lane == KSEL - 1) thr_key[qi] = cur;           // descending: lane 31 holds the 32nd largest
-    if (lane == 0) { cand_cnt[qi] = 0u; if (qi == 0) *overflow = 0u; }
+    for (int s = 1; s < nlists; s <<= 1) {
+        if ((warp & (2 * s - 1)) == 0 && warp + s < nlists) {
+            const u64 other = s_keys[warp + s][lane];
+            if (__any_sync(FULL, other != 0ull)) cur = warp_merge_top32(cur, other, lane);
+            s_keys[warp][lane] = cur;
+        }
+        __syncthreads();
+    }
+    return cur;
+}
+
+// threshold key[q] = (at least) the KSEL-th largest key of KSEL distinct sampled rows (0 if fewer exist); resets the counters.
+// grid (queries, THR_P), block 1024.  Every thread first folds its strided share of the sample into ONE running maximum (a maximum
+// over a group of rows is still the key of a real row, so the bound stays valid and is almost as tight: the top-32 sample rows fall into
+// distinct groups with probability ~ 1 - 32^2 / (2 * 1024 * THR_P)); the CTA then takes the exact top-32 of its 1024 maxima (one bitonic
+// sort per warp + a 5-round tree merge), and the last CTA of a query to finish merges the THR_P partial lists.
+constexpr int THR_P = 8;
+__global__ void __launch_bounds__(1024)
+knn_threshold_kernel(const u64* __restrict__ maxima, size_t per_q, u64* __restrict__ thr_key, unsigned* __restrict__ cand_cnt, unsigned* __restrict__ overflow,
+                     u64* __restrict__ part, unsigned* __restrict__ done) {
+    __shared__ u64 s_keys[32][LIST];
+    __shared__ unsigned s_last;
+    const int qi = blockIdx.x, p = blockIdx.y, P = gridDim.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64* src = maxima + (size_t)qi * per_q;
+    u64 best = 0ull;
+    for (size_t i = (size_t)p * 1024 + tid; i < per_q; i += (size_t)P * 1024) { const u64 v = __ldcs(src + i); best = v > best ? v : best; }
+    u64 cur = warp_merge_top32(0ull, best, lane);                      // sort this warp's 32 maxima, best first
+    cur = cta_tree_merge(cur, s_keys, warp, lane, 32);
+    if (warp == 0) {
+        part[((size_t)qi * P + p) * LIST + lane] = cur;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) s_last = atomicAdd(&done[qi], 1u) == (unsigned)(P - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    cur = warp < P ? __ldcg(part + ((size_t)qi * P + warp) * LIST + lane) : 0ull;
+    cur = cta_tree_merge(cur, s_keys, warp, lane, P);
+    if (warp == 0) {
+        if (lane == KSEL - 1) thr_key[qi] = cur;       // descending: lane 31 holds the 32nd largest
+        if (lane == 0) { cand_cnt[qi] = 0u; done[qi] = 0u; if (qi == 0) *overflow = 0u; }
+    }
 }
 
 __device__ __forceinline__ bool better_pair(double sa, long long ia, double sb, long long ib) { return sa > sb || (sa == sb && ia < ib); }
@@ -379,22 +408,23 @@ knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const unsigne
             cur = warp_merge_top32(cur, batch, lane);
         }
     }
-    s_keys[warp][lane] = cur;
-    __syncthreads();
+    cur = cta_tree_merge(cur, s_keys, warp, lane, 32);
     if (warp != 0) return;
-    cur = s_keys[0][lane];
-    for (int w = 1; w < 32; w++) {
-        u64 batch = s_keys[w][lane];
-        if (__any_sync(FULL, batch != 0ull)) cur = warp_merge_top32(cur, batch, lane);
-    }
     // exact re-rank (definition: oracle/knn_ref.c)
     const bool have = cur != 0ull;
     long long row = have ? (long long)(0xffffffffu - (uint32_t)cur) : 0x7fffffffffffffffLL;
     double s = -CUDART_INF;
     if (have && row < n) {
-        const T* r = db + (size_t)row * D;
+        const uint4* r = reinterpret_cast<const uint4*>(db + (size_t)row * D);      // 16-byte pieces: the loads run ahead of the fp64 chain
+        constexpr int EPV = Elem<T>::EPV;
         double acc = 0.0;
-        for (int j = 0; j < D; j++) acc = __dadd_rn(acc, __dmul_rn((double)s_q[j], (double)Elem<T>::to_f32(r[j])));
+#pragma unroll 4
+        for (int j = 0; j < D / EPV; j++) {
+            float f[EPV];
+            Elem<T>::unpack(ldg_stream(r + j), f);
+#pragma unroll
+            for (int e = 0; e < EPV; e++) acc = __dadd_rn(acc, __dmul_rn((double)s_q[j * EPV + e], (double)f[e]));      // same order as the oracle
+        }
         acc = __dmul_rn(acc, (double)inv[row]);
         s = (acc == acc) ? acc : -CUDART_INF;
     }
@@ -505,6 +535,8 @@ struct rdm_knn {
     u64* cand = nullptr;       // [MAX_QP][CAND_CAP]
     u64* thr_key = nullptr;    // [MAX_QP]
     unsigned* cand_cnt = nullptr;   // [MAX_QP] + overflow flag at [MAX_QP]
+    u64* thr_part = nullptr;        // threshold kernel: [MAX_TCQ][THR_P][LIST] partial top-32 lists
+    unsigned* thr_done = nullptr;   // [MAX_TCQ] arrival counters (zero between searches)
     void* qsplit = nullptr;         // fp16 hi/lo query rows for the tensor-core scan
     int max_grid = 0;
 };
@@ -551,7 +583,7 @@ int search_pass(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_out,
     int g0 = 0, g1 = 0, g2 = 0;
     ScanArgs a{}; a.group_stride = stride; a.maxima = h->maxima;
     RDM_TRY((launch_scan<T, D, QP, R, SCAN_SAMPLE>(h, qp, cnt, a, st, &g0)));
-    knn_threshold_kernel<<<QP, 1024, 0, st>>>(h->maxima, (size_t)g0 * SCAN_THREADS, h->thr_key, h->cand_cnt, overflow);
+    knn_threshold_kernel<<<dim3(QP, THR_P), 1024, 0, st>>>(h->maxima, (size_t)g0 * SCAN_THREADS, h->thr_key, h->cand_cnt, overflow, h->thr_part, h->thr_done);
     RDM_COUNT_LAUNCH();
     ScanArgs m{}; m.group_stride = 1; m.thr_key = h->thr_key; m.cand = h->cand; m.cand_cnt = h->cand_cnt;
     RDM_TRY((launch_scan<T, D, QP, R, SCAN_MAIN>(h, qp, cnt, m, st, &g1)));
@@ -578,7 +610,7 @@ int search_pass_tc(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_o
     const long long per_q = knn_tc_sample_rows(h->n, stride);
     RDM_REQUIRE((size_t)per_q * cnt <= h->maxima_keys, RDM_ERR_STATE, "knn: sample buffer too small");
     RDM_TRY(knn_scan_tc(h->db, h->inv, h->n, h->device, qp, cnt, h->qsplit, 1, stride, h->maxima, per_q, nullptr, nullptr, nullptr, st));
-    knn_threshold_kernel<<<cnt, 1024, 0, st>>>(h->maxima, (size_t)per_q, h->thr_key, h->cand_cnt, overflow);
+    knn_threshold_kernel<<<dim3(cnt, THR_P), 1024, 0, st>>>(h->maxima, (size_t)per_q, h->thr_key, h->cand_cnt, overflow, h->thr_part, h->thr_done);
     RDM_COUNT_LAUNCH();
     RDM_TRY(knn_scan_tc(h->db, h->inv, h->n, h->device, qp, cnt, h->qsplit, 0, 1, nullptr, 0, h->thr_key, h->cand, h->cand_cnt, st));
     knn_select_kernel<T, D, false><<<cnt, 1024, 0, st>>>(h->cand, 0, 0, h->cand_cnt, overflow, (const T*)h->db, h->inv, h->n, qp, k, h->idx_base,
@@ -600,7 +632,7 @@ template <typename T, int D>
 int search_typed(rdm_knn* h, const float* q, int nq, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st) {
     if constexpr (std::is_same<T, __half>::value && D == 512) {
         static const bool no_tc = getenv("RDM_KNN_NO_TC") != nullptr;
-        if (!no_tc && nq >= 8) {
+        if (!no_tc && nq >= 3) {          // measured: from 3 queries on, the (padded) tensor-core pass beats the FMA scan (0.28 vs 0.35 ms at 4 queries, 1.28 M rows)
             for (int q0 = 0; q0 < nq; q0 += MAX_TCQ) {
                 int cnt = nq - q0 < MAX_TCQ ? nq - q0 : MAX_TCQ;
                 RDM_TRY((search_pass_tc<T, D>(h, q + (size_t)q0 * D, cnt, k, idx_out + (size_t)q0 * k, dist_out + (size_t)q0 * k, sc_out ? sc_out + (size_t)q0 * k : nullptr, st)));
@@ -708,6 +740,9 @@ int rdm_knn_create(rdm_knn_t** out, const void* db, int64_t n, int32_t d, int32_
             cudaMalloc(&h->cand, (size_t)MAX_TCQ * CAND_CAP * sizeof(u64)) != cudaSuccess ||
             cudaMalloc(&h->thr_key, (size_t)MAX_TCQ * sizeof(u64)) != cudaSuccess ||
             cudaMalloc(&h->cand_cnt, (size_t)(MAX_TCQ + 1) * sizeof(unsigned)) != cudaSuccess ||
+            cudaMalloc(&h->thr_part, (size_t)MAX_TCQ * THR_P * LIST * sizeof(u64)) != cudaSuccess ||
+            cudaMalloc(&h->thr_done, (size_t)MAX_TCQ * sizeof(unsigned)) != cudaSuccess ||
+            cudaMemset(h->thr_done, 0, (size_t)MAX_TCQ * sizeof(unsigned)) != cudaSuccess ||
             cudaMalloc(&h->qsplit, (size_t)knn_tc_queries_bytes()) != cudaSuccess) {
             rdm_set_error("rdm_knn_create: workspace cudaMalloc failed"); rc = RDM_ERR_CUDA; break;
         }
@@ -729,6 +764,8 @@ void rdm_knn_destroy(rdm_knn_t* h) {
     if (h->thr_key) cudaFree(h->thr_key);
     if (h->cand_cnt) cudaFree(h->cand_cnt);
     if (h->qsplit) cudaFree(h->qsplit);
+    if (h->thr_part) cudaFree(h->thr_part);
+    if (h->thr_done) cudaFree(h->thr_done);
     delete h;
 }
 

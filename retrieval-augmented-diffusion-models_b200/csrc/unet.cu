@@ -75,7 +75,8 @@ struct rdm_unet {
     float* x_in = nullptr; long long* t_in = nullptr; float* eps_buf = nullptr; float* x_state = nullptr; float* p0_buf = nullptr; int* step_dev = nullptr;
     size_t io_cap = 0;
     cudaStream_t cap_stream = nullptr;
-    cudaGraphExec_t fwd_exec = nullptr; int fwd_key[5] = {0, 0, 0, 0, -1};
+    cudaGraphExec_t fwd_exec = nullptr; int fwd_key[6] = {0, 0, 0, 0, -1, 0};
+    int skip = getenv("RDM_SKIP") ? atoi(getenv("RDM_SKIP")) : 0;      // ablation mask (see RUN_UNLESS)
     cudaGraphExec_t step_exec = nullptr; long long step_key[10] = {0};
     unsigned long long fwd_kernels = 0, step_kernels = 0;      // kernels inside each captured graph (for rdm_launch_count)
     // profiling (rdm_unet_profile_forward): event pairs around every GEMM launch
@@ -247,10 +248,9 @@ void build_net(Net* n) {
 // ---- forward ------------------------------------------------------------------------------------------
 struct Ctx { Net* n; cudaStream_t st; bool dry; int rc = RDM_OK; };
 #define RUN(expr) do { if (!cx.dry && cx.rc == RDM_OK) cx.rc = (expr); } while (0)
-// Timing ablation (tools/ablate_forward.py): RDM_SKIP is a bit mask of kernel classes that are NOT launched (results are garbage; only the
+// Timing ablation (rdm_unet_set_ablation, tools/ablate_forward.py; env RDM_SKIP sets the initial value): a bit mask of kernel classes that are NOT launched (results are garbage; only the
 // change of the graph-replayed forward time is meaningful).  1 gn_stats, 2 gn_apply, 4 layernorm, 8 attention, 16 GEMM M>=8192, 32 GEMM M<8192.
-static const int g_skip = getenv("RDM_SKIP") ? atoi(getenv("RDM_SKIP")) : 0;
-#define RUN_UNLESS(bit, expr) do { if (!(g_skip & (bit))) RUN(expr); } while (0)
+#define RUN_UNLESS(bit, expr) do { if (!(cx.n->skip & (bit))) RUN(expr); } while (0)
 
 // GEMM operand / result: an fp32 view (CUDA-core engine) or bf16 hi/lo planes (tcgen05 engine)
 struct Opnd {
@@ -302,9 +302,11 @@ void gemm_any(Ctx& cx, const Opnd& a, int B, int H, int W, int C, int ks, int st
             if (!on) return;
             cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
             cx.n->prof_ev.push_back(e0); cx.n->prof_ev.push_back(e1); cx.n->prof_flops.push_back(flops); cx.n->prof_kind.push_back(kind);
-            cudaEventRecord(e0, cx.st);
+            rec(e0);
         }
-        ~ProfScope() { if (on) cudaEventRecord(cx.n->prof_ev.back(), cx.st); }
+        // profile == 2: the forward is being captured into a CUDA graph; external event-record nodes time the kernels inside the replay
+        void rec(cudaEvent_t e) { if (cx.n->profile == 2) cudaEventRecordWithFlags(e, cx.st, cudaEventRecordExternal); else cudaEventRecord(e, cx.st); }
+        ~ProfScope() { if (on) rec(cx.n->prof_ev.back()); }
     } prof(cx, 2.0 * M * (double)N * ks * ks * C, a.tc() ? 1 : 0);
     if (prof.on) { char d[128]; snprintf(d, sizeof(d), "%s M=%d N=%d K=%d ks=%d HxW=%dx%d act=%d", a.tc() ? "tc" : "simt", M, N, ks * ks * C, ks, H, W, e.act); n->prof_desc.push_back(d); }
     if (a.tc()) {
@@ -392,7 +394,7 @@ void run_st(Ctx& cx, const STW& s, const Act& x, View out) {
     // cross-attention to the retrieved neighbours (attention.py:94); K/V were projected once in set_context
     RUN_UNLESS(4, k_layernorm(t1, M, s.ln2.g, s.ln2.b, 1e-5f, nrm.out4(), cx.st));
     View kv(cx.dry ? nullptr : n->ctx_kv + n->ctx_off[s.id], 2 * C, 2 * C);
-    if (tcp && n->ctx_k <= 8 && N >= 16 && !(g_skip & 64)) {
+    if (tcp && n->ctx_k <= 8 && N >= 16 && !(n->skip & 64)) {
         // tensor-core engine: softmax(q k^T) v over the k retrieved neighbours runs in the epilogue of the to_q GEMM (one 32-column
         // accumulator chunk = one head's query), so neither q nor a separate attention launch exists
         GemmEpi e; e.act = ACT_XATTN; e.xkv = kv.p; e.xkv_ld = kv.ld; e.xv_off = C; e.xk = n->ctx_k; e.xscale = scale; e.rows_per_batch = N;
@@ -615,7 +617,7 @@ template <typename F> int capture_graph(Net* n, cudaGraphExec_t* exec, unsigned 
 // eps_buf = UNet(x_in [Bx], t_in [B2]) by graph replay on `st` (first call per shape runs eagerly once, then captures).
 int forward_staged(Net* n, int Bx, int B2, int H, int W, cudaStream_t st) {
     if (!n->use_graph || n->debug || n->profile) return forward_impl(n, n->x_in, Bx, n->t_in, B2, H, W, n->eps_buf, st, false);
-    const int key[5] = {Bx, B2, H, W, n->mode};
+    const int key[6] = {Bx, B2, H, W, n->mode, n->skip};
     if (!n->fwd_exec || memcmp(key, n->fwd_key, sizeof(key)) != 0) {
         RDM_TRY(forward_impl(n, n->x_in, Bx, n->t_in, B2, H, W, n->eps_buf, st, false));     // eager warm-up: sets kernel attributes
         RDM_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -773,18 +775,35 @@ int rdm_unet_forward(rdm_unet_t* n, const float* x, int32_t Bx, const int64_t* t
     return RDM_OK;
 }
 
+int rdm_unet_set_ablation(rdm_unet_t* n, int32_t mask) { RDM_REQUIRE(n, RDM_ERR_ARG, "rdm_unet_set_ablation: null handle"); n->skip = mask; return RDM_OK; }
 int rdm_unet_set_graph(rdm_unet_t* n, int32_t on) { RDM_REQUIRE(n, RDM_ERR_ARG, "rdm_unet_set_graph: null handle"); n->use_graph = on; return RDM_OK; }
 
 int rdm_unet_profile_forward(rdm_unet_t* n, const float* x, int32_t Bx, const int64_t* t, int32_t B2, int32_t H, int32_t W, float* eps_out,
                              double* out8, void* stream) {
     RDM_REQUIRE(n && out8, RDM_ERR_ARG, "rdm_unet_profile_forward: null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    n->profile = 1; n->prof_ev.clear(); n->prof_flops.clear(); n->prof_kind.clear(); n->prof_desc.clear(); n->prof_text.clear();
+    // 1. a plain forward: validates arguments, stages the inputs, sets kernel attributes, produces eps_out
+    RDM_TRY(rdm_unet_forward(n, x, Bx, t, B2, H, W, eps_out, stream));
+    RDM_CHECK_CUDA(cudaStreamSynchronize(st));
+    DeviceGuard guard(n->device);
+    // 2. the same forward captured into a graph with external event-record nodes around every GEMM: durations are those of the
+    //    graph-replayed kernels (no host launch gaps inside the brackets).  Replayed twice; the second replay is the one measured.
+    n->profile = 2; n->prof_ev.clear(); n->prof_flops.clear(); n->prof_kind.clear(); n->prof_desc.clear(); n->prof_text.clear();
     cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
-    cudaEventRecord(t0, st);
-    int rc = rdm_unet_forward(n, x, Bx, t, B2, H, W, eps_out, stream);
-    cudaEventRecord(t1, st);
+    cudaGraphExec_t pexec = nullptr; unsigned long long nk = 0;
+    int rc = capture_graph(n, &pexec, &nk, [&](cudaStream_t cs) {
+        cudaEventRecordWithFlags(t0, cs, cudaEventRecordExternal);
+        int r = forward_impl(n, n->x_in, Bx, n->t_in, B2, H, W, n->eps_buf, cs, false);
+        cudaEventRecordWithFlags(t1, cs, cudaEventRecordExternal);
+        return r;
+    });
     n->profile = 0;
+    if (rc == RDM_OK) {
+        for (int rep = 0; rep < 2 && rc == RDM_OK; rep++) {
+            if (cudaGraphLaunch(pexec, st) != cudaSuccess) { rdm_set_error("rdm_unet_profile_forward: graph launch failed"); rc = RDM_ERR_CUDA; }
+            g_rdm_launches += nk;
+        }
+    }
     cudaError_t ce = cudaStreamSynchronize(st);
     for (int i = 0; i < 8; i++) out8[i] = 0.0;
     if (rc == RDM_OK && ce == cudaSuccess) {
@@ -799,6 +818,7 @@ int rdm_unet_profile_forward(rdm_unet_t* n, const float* x, int32_t Bx, const in
     }
     for (cudaEvent_t e : n->prof_ev) cudaEventDestroy(e);
     cudaEventDestroy(t0); cudaEventDestroy(t1);
+    if (pexec) cudaGraphExecDestroy(pexec);
     n->prof_ev.clear(); n->prof_flops.clear(); n->prof_kind.clear();
     RDM_REQUIRE(ce == cudaSuccess, RDM_ERR_CUDA, "rdm_unet_profile_forward: %s", cudaGetErrorString(ce));
     return rc;

@@ -190,8 +190,13 @@ class B200UNet:
     def set_graph(self, on):
         _lib.check(_lib.lib().rdm_unet_set_graph(self._h, 1 if on else 0), "rdm_unet_set_graph")
 
+    def set_ablation(self, mask):
+        """Measurement aid (rdm_unet_set_ablation): bit mask of kernel classes that the following forwards do NOT launch."""
+        _lib.check(_lib.lib().rdm_unet_set_ablation(self._h, int(mask)), "rdm_unet_set_ablation")
+
     def profile_forward(self, x, t):
-        """Eager forward with CUDA events around every GEMM -> dict(tc_ms, tc_flop, simt_ms, simt_flop, total_ms, n_tc, n_simt)."""
+        """Graph-replayed forward with event-record nodes around every GEMM -> dict(tc_ms, tc_flop, simt_ms, simt_flop, total_ms, n_tc, n_simt).
+        (Event nodes cost a few microseconds each: use the per-layer lines for SHARES; bench.py takes the in-graph GEMM time by ablation.)"""
         x = x.to(self.device, torch.float32).contiguous(); t = t.to(self.device, torch.int64).contiguous()
         B2, (Bx, _, H, W) = t.shape[0], x.shape
         out = torch.empty((B2, self.cfg["out_channels"], H, W), dtype=torch.float32, device=self.device)
