@@ -1,0 +1,24 @@
+"""Every scheduling variant of the tcgen05 engine must give the same answer: split-K through the reduce kernel vs through a thread-block
+cluster (DSMEM reduction), fused vs un-fused cross-attention, with / without programmatic dependent launch.  The variants are chosen by
+environment variables that librdm_b200 reads once at load time, hence one sub-process each (tools/variant_check.py)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = {"0": 1e-4, "1": 1e-4, "3": 3e-3, "4": 4e-3}          # same per-forward tolerances as tests/test_unet_gpu.py
+
+
+@pytest.mark.parametrize("env", [{"RDM_TC_CLUSTER": "0"}, {"RDM_TC_CLUSTER": "2"}, {"RDM_SKIP": "64"}, {"RDM_PDL": "0"}, {"RDM_TC_NOSPLIT": "1"}],
+                         ids=["splitk-reduce-kernel", "splitk-cluster-dsmem", "unfused-cross-attention", "no-pdl", "no-splitk"])
+def test_engine_variant_matches_oracle(cuda, env):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "variant_check.py"), "1,3"], env=dict(os.environ, **env),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    errs = json.loads(r.stdout.strip().splitlines()[-1])
+    for mode, err in errs.items():
+        assert err < TOL[mode], f"{env} mode {mode}: rel-L2 {err:.2e} (tolerance {TOL[mode]})"
