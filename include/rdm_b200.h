@@ -164,6 +164,27 @@ RDM_API int rdm_ddim_step(const float* x_dev, const float* eps_dev, int64_t n_pe
 
 
 /* ------------------------------------------------------------------------------------------------
+ * First-stage decode: `decode_first_stage` at rdm/models/diffusion/ddpm.py:840,981 ->
+ * ldm VQModelInterface.decode = VectorQuantizer lookup -> post_quant_conv -> Decoder (conv_in, mid ResnetBlock / AttnBlock /
+ * ResnetBlock, up levels with nearest-2x Upsample, GroupNorm-SiLU-conv_out); configuration = first_stage_config.params of
+ * models/rdm/imagenet/config.yaml:60-80.  The decoder shares the executor of the U-Net: the handle is an rdm_unet_t and the
+ * rdm_unet_num_params / param_name / param_numel / load / missing / set_mode / set_graph / destroy calls accept it.
+ * Parameter names: latent-diffusion checkpoint keys below `first_stage_model.` ("decoder.mid.attn_1.q.weight",
+ * "quantize.embedding.weight", "post_quant_conv.weight", ...).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct rdm_vqdec_cfg {
+    int32_t embed_dim, n_embed;            /* codebook [n_embed, embed_dim], embed_dim <= 4 */
+    int32_t z_channels, resolution, out_ch, ch, num_res_blocks;
+    int32_t n_ch_mult; int32_t ch_mult[8];
+    int32_t n_attn_resolutions; int32_t attn_resolutions[8];
+} rdm_vqdec_cfg;
+RDM_API int rdm_vqdec_create(rdm_unet_t** out, const rdm_vqdec_cfg* cfg, int32_t device);
+/* z float32 NCHW [B, embed_dim, h, w] (device) -> images float32 NCHW [B, out_ch, h * 2^(n_ch_mult-1), w * 2^(n_ch_mult-1)];
+ * quantize == 0 is `force_not_quantize=True`.  fp16 tensor-core modes only (default fp16x2). */
+RDM_API int rdm_vqdec_decode(rdm_unet_t* h, const float* z_dev, int32_t B, int32_t hh, int32_t ww, int32_t quantize, float* out_dev, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
  * CLIP encoders (retrieval queries): rdm/modules/custom_clip/model.py:201-235 (VisualTransformer), :166-198 (Transformer),
  * :304 (encode_image), :307-320 (encode_text); call sites rdm/modules/retrievers.py:83-95 (ClipImageRetriever),
  * scripts/rdm_sample.py:275-277 and scripts/rarm_sample.py:232-236 (clip.encode_text), dsetbuilder.py:461-473 (embed).

@@ -1,8 +1,10 @@
-"""`ldm.models.autoencoder.VQModelInterface` stand-in: the DECODE side only (quantise -> post_quant_conv -> Decoder), as
-described in SURVEY.md Appendix A, so `decode_first_stage` (ddpm.py:840,981) returns images for the unchanged sampling scripts.
-The nn.Modules below are the parameter containers (checkpoint key layout); on a CUDA tensor `decode` runs the hand-written
-decoder of librdm_b200 (`rdm_b200.vqdecoder.B200VQDecoder`) -- the eager PyTorch forward only serves CPU tensors.  Module names follow the latent-diffusion checkpoint layout (`first_stage_model.decoder.*`,
-`first_stage_model.quantize.embedding.weight`, `first_stage_model.post_quant_conv.*`)."""
+"""ORACLE (test infrastructure; imported only by tests/, __graft_entry__.smoke() and bench.py's CPU legs).
+
+torch-CPU fp32 restatement of the first-stage decode path `VQModelInterface.decode` = VectorQuantizer lookup -> post_quant_conv ->
+Decoder.  The source of these modules is NOT in /root/reference (un-vendored dependency `latent-diffusion@main`,
+`ldm/modules/diffusionmodules/model.py` + `taming/modules/vqvae/quantize.py`); the call sites this
+follows are rdm/models/diffusion/ddpm.py:840,981 (`decode_first_stage`) and the configuration models/rdm/imagenet/config.yaml:60-80.
+Parity unpinned by the reference (no fixtures); module / key names follow the latent-diffusion checkpoint layout."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -103,23 +105,30 @@ class VQModelInterface(nn.Module):
         self.quantize = VectorQuantizer(n_embed, embed_dim)
         self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
         self.embed_dim = embed_dim
-        self._ddconfig = dict(ddconfig)
-
-    def encode(self, x):
-        raise NotImplementedError("the first-stage ENCODER is outside the sampling hot path (SURVEY.md section 2)")
-
-    def _b200(self, device):
-        """Decoder handle on `device`, re-synchronised whenever a parameter tensor was written (load_state_dict, .to, ...)."""
-        from rdm_b200.vqdecoder import B200VQDecoder
-        stamp = (str(device), tuple((p.data_ptr(), p._version) for p in self.parameters()))
-        if getattr(self, "_b200_stamp", None) != stamp:
-            dec = B200VQDecoder(device, self.embed_dim, self.quantize.embedding.num_embeddings, self._ddconfig)
-            dec.load_state_dict(self.state_dict())
-            self._b200_dec, self._b200_stamp = dec, stamp
-        return self._b200_dec
 
     def decode(self, h, force_not_quantize=False):
-        if h.is_cuda:
-            return self._b200(h.device).decode(h, force_not_quantize)
         quant = h if force_not_quantize else self.quantize(h)[0]
         return self.decoder(self.post_quant_conv(quant))
+
+
+TINY_VQ = dict(embed_dim=3, n_embed=512, ddconfig=dict(double_z=False, z_channels=3, resolution=64, in_channels=3, out_ch=3, ch=64,
+                                                         ch_mult=[1, 2], num_res_blocks=1, attn_resolutions=[], dropout=0.0))
+RDM_VQ_F4 = dict(embed_dim=3, n_embed=8192, ddconfig=dict(double_z=False, z_channels=3, resolution=256, in_channels=3, out_ch=3, ch=128,
+                                                          ch_mult=[1, 2, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0))
+"""models/rdm/imagenet/config.yaml:60-80 (VQ-f4: 64x64x3 latent -> 256x256x3 image)."""
+
+
+def randomize_(m, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if p.dim() >= 2 and "embedding" not in name:
+                fan_in = p[0].numel()
+                p.copy_(torch.randn(p.shape, generator=g) / fan_in ** 0.5)
+            elif "embedding" in name:
+                p.copy_(torch.randn(p.shape, generator=g))
+            elif name.endswith("weight"):
+                p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+    return m

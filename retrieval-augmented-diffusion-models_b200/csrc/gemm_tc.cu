@@ -50,6 +50,7 @@ struct TcKernelParams {
     int splits, kb_per_split;  // split-K: work item = (tile, split); partial fp32 accumulators go to `part` [splits][M][N]
     float* part;
     int cluster;               // split-K inside a thread-block cluster: CTA rank = split, partial tiles reduced through distributed shared memory
+    int pdl_off;               // the B operand is an activation of a preceding kernel: no prefetch ahead of griddepcontrol.wait
     int pdl;                   // launched with programmatic stream serialization: prefetch weights before griddepcontrol.wait
     // epilogue
     const float* bias; const float* rowvec; int rowvec_ld; int rows_per_batch;
@@ -391,6 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const int mt = tile / ntn, n0 = (tile % ntn) * BN;
                 int x0 = 0, y0 = 0, b0 = 0;                              // tile origin in (x, y, b) of the NHWC plane
                 if (p.plain) x0 = mt * BM;
+                else if (p.W > BM) { const int tpr = p.W / BM; x0 = (mt % tpr) * BM; y0 = (mt / tpr) % p.H; b0 = mt / (tpr * p.H); }   // wide images: a tile is a 128-pixel piece of one row
                 else if (p.bb > 1 || p.bh * p.bw == p.H * p.W) b0 = mt * p.bb;
                 else { int tiles_per_img = (p.H * p.W) / BM; b0 = mt / tiles_per_img; y0 = (mt % tiles_per_img) * p.bh; }
                 for (int kb = kb0; kb < kb1; kb++, it++) {
@@ -603,7 +605,7 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     const int nitems = ((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * p.splits;
     const int sms = rdm_num_sms(dev);
     const int use_pdl = g_rdm_use_pdl;
-    TcKernelParams pl = p; pl.pdl = use_pdl;
+    TcKernelParams pl = p; pl.pdl = use_pdl && !p.pdl_off;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(p.cluster ? nitems : (nitems < sms ? nitems : sms)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -644,7 +646,8 @@ bool gemm_tc_supported(const TcA& a) {
     if (a.ksize == 1) return true;
     // 3x3: a 128-row tile must be an (x, y, b) box of the image
     const int W = a.W, H = a.H;
-    if (W > BM || (BM % W) != 0) return false;
+    if (W > BM) return W % BM == 0;                    // first-stage decoder (128 / 256 pixel rows): tiles are row pieces
+    if ((BM % W) != 0) return false;
     const int rows_y = BM / W;                        // image rows per tile if H is large enough
     if (H >= rows_y) return H % rows_y == 0;
     return (BM % (W * H)) == 0;
@@ -666,7 +669,8 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
         if (nsplit == 3) RDM_TRY(make_map_4d(&ta_lo, a.lo, a.C, M, 1, 1, a.ld, BM, 1, 1)); else ta_lo = ta_hi;
     } else {
         const int W = a.W, H = a.H;
-        p.bw = W; p.bh = (BM / W) < H ? (BM / W) : H; p.bb = BM / (p.bw * p.bh);
+        if (W > BM) { p.bw = BM; p.bh = 1; p.bb = 1; }
+        else { p.bw = W; p.bh = (BM / W) < H ? (BM / W) : H; p.bb = BM / (p.bw * p.bh); }
         RDM_TRY(make_map_4d(&ta_hi, a.hi, a.C, W, H, a.B, a.ld, p.bw, p.bh, p.bb));
         if (nsplit == 3) RDM_TRY(make_map_4d(&ta_lo, a.lo, a.C, W, H, a.B, a.ld, p.bw, p.bh, p.bb)); else ta_lo = ta_hi;
     }
@@ -675,7 +679,7 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     p.xkv = e.xkv; p.xkv_ld = e.xkv_ld; p.xv_off = e.xv_off; p.xk = e.xk; p.xscale_log2e = e.xscale * 1.4426950408889634f;
     RDM_REQUIRE(e.act != ACT_XATTN || (e.xkv && e.xk >= 1 && e.xk <= 8 && p.rows_per_batch >= 16 && w.N % 32 == 0 && e.xkv_ld % 4 == 0 && !e.bias && !e.res && !e.rowvec), RDM_ERR_ARG,
                 "gemm_tc: fused cross-attention needs 1..8 context rows, N %% 32 == 0 and no bias/residual (xk=%d N=%d)", e.xk, w.N);
-    p.out_hi = out_hi; p.out_lo = out_lo; p.out_bf_ld = out_bf_ld; p.f16 = f16;
+    p.out_hi = out_hi; p.out_lo = out_lo; p.out_bf_ld = out_bf_ld; p.f16 = f16; p.pdl_off = w.dynamic;
     RDM_REQUIRE((p.out != nullptr) != (p.out_hi != nullptr), RDM_ERR_ARG, "gemm_tc: exactly one of fp32 / bf16 outputs");
     // Tile width and split-K.  The mainloop is operand-feed bound (TMA/L2 -> smem): one k-block of a work item costs ~(128 + BN)
     // (the 128-row A tile is re-loaded for every N tile); every item pays a fixed prologue/epilogue worth ~6 k-blocks.  Small-M layers

@@ -10,6 +10,7 @@ struct TcA {                       // activation operand: NHWC plane [B*H*W, C] 
 struct TcW {                       // weights [N, K] K-major, K ordered (tap, cin)
     const __nv_bfloat16* hi = nullptr; const __nv_bfloat16* lo = nullptr; int ld = 0;
     int N = 0, K = 0;
+    int dynamic = 0;               // 1: this operand is an ACTIVATION written by preceding kernels (attention K / V^T): it must not be prefetched before griddepcontrol.wait
 };
 bool gemm_tc_supported(const TcA& a);
 // nsplit 3: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-grade);  nsplit 2: A*W_hi + A*W_lo (single-plane A, split W);  nsplit 1: A*W.

@@ -53,39 +53,43 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B
 }
 
 // grid (row_chunks, B).  Thread t owns the float4 column v = t % V for the whole kernel and walks rows slot, slot+nslots, ...
-// (consecutive threads -> consecutive 16-byte pieces of a row: coalesced), keeping its 4 channel sums in registers; one
+// (consecutive threads -> consecutive 16-byte pieces of a row: coalesced), keeping its 4 channel sums in fp64 registers; one
 // shared-memory atomic per touched group per thread at the end, then fp64 atomics to the global accumulators.
 __global__ void gn_stats_kernel(const float* __restrict__ x, int ld, int C, int HW, int groups, int rows_per_cta, double* __restrict__ sums) {
     pdl_wait();
     pdl_launch_dependents();
-    extern __shared__ float s_acc[];           // [2][groups]
+    // All accumulation in fp64: the variance is E[x^2] - mean^2, and with fp32 partial sums (whose atomics also commit in a varying order)
+    // a group whose |mean| is several times its spread lost ~1e-4 of rstd -- run-to-run noise as large as the fp16 operand rounding itself
+    // (seen on the first-stage decoder).  The kernel is L2/HBM-bound; 8 DFMA per 16 bytes are free on B200.
+    extern __shared__ double s_acc[];          // [2][groups]
     const int b = blockIdx.y, V = C / 4, cpg = C / groups;
-    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) s_acc[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) s_acc[i] = 0.0;
     __syncthreads();
     const int nslots = blockDim.x / V;          // blockDim.x is a multiple of V or smaller threads idle
     const int v = threadIdx.x % V, slot = threadIdx.x / V;
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
     if (slot < nslots) {
         const float* base = x + ((long long)b * HW) * ld + v * 4;
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+        double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
         for (int r = r0 + slot; r < r1; r += nslots) {
-            float4 q = *reinterpret_cast<const float4*>(base + (long long)r * ld);
-            s[0] += q.x; ss[0] += q.x * q.x; s[1] += q.y; ss[1] += q.y * q.y;
-            s[2] += q.z; ss[2] += q.z * q.z; s[3] += q.w; ss[3] += q.w * q.w;
+            const float4 q = *reinterpret_cast<const float4*>(base + (long long)r * ld);
+            const double q0 = q.x, q1 = q.y, q2 = q.z, q3 = q.w;
+            s[0] += q0; ss[0] = fma(q0, q0, ss[0]); s[1] += q1; ss[1] = fma(q1, q1, ss[1]);
+            s[2] += q2; ss[2] = fma(q2, q2, ss[2]); s[3] += q3; ss[3] = fma(q3, q3, ss[3]);
         }
-        int g = (v * 4) / cpg; float gs = 0.f, gss = 0.f;
+        int g = (v * 4) / cpg; double gs = 0.0, gss = 0.0;
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             int gt = (v * 4 + t) / cpg;
-            if (gt != g) { atomicAdd(&s_acc[g], gs); atomicAdd(&s_acc[groups + g], gss); g = gt; gs = 0.f; gss = 0.f; }
+            if (gt != g) { atomicAdd(&s_acc[g], gs); atomicAdd(&s_acc[groups + g], gss); g = gt; gs = 0.0; gss = 0.0; }
             gs += s[t]; gss += ss[t];
         }
         atomicAdd(&s_acc[g], gs); atomicAdd(&s_acc[groups + g], gss);
     }
     __syncthreads();
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        atomicAdd(&sums[((size_t)b * groups + g) * 2 + 0], (double)s_acc[g]);
-        atomicAdd(&sums[((size_t)b * groups + g) * 2 + 1], (double)s_acc[groups + g]);
+        atomicAdd(&sums[((size_t)b * groups + g) * 2 + 0], s_acc[g]);
+        atomicAdd(&sums[((size_t)b * groups + g) * 2 + 1], s_acc[groups + g]);
     }
 }
 
@@ -370,6 +374,115 @@ inline int blocks_for(long long n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace
 
+
+// ---- first-stage (VQ) decoder glue: single-head attention over all pixels runs as two tensor-core GEMMs with these in between ------------
+// P[r, :] = softmax(scale * S[r, :]) as an fp16 plane; one CTA per row, the row lives in registers (N <= 256 threads * 16 values)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, int ld_s, int N, float scale_log2e, __half* __restrict__ out, int ld_o) {
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ float red[8];
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float4* src = reinterpret_cast<const float4*>(s + (size_t)row * ld_s);
+    const int V = N >> 2;
+    float4 q[4];
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int v = tid + 256 * i;
+        q[i] = v < V ? src[v] : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+        mx = fmaxf(mx, fmaxf(fmaxf(q[i].x, q[i].y), fmaxf(q[i].z, q[i].w)));
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, m));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        q[i].x = exp2f((q[i].x - mx) * scale_log2e); q[i].y = exp2f((q[i].y - mx) * scale_log2e);
+        q[i].z = exp2f((q[i].z - mx) * scale_log2e); q[i].w = exp2f((q[i].w - mx) * scale_log2e);
+        sum += (q[i].x + q[i].y) + (q[i].z + q[i].w);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) sum += __shfl_xor_sync(FULL, sum, m);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) sum += red[w];
+    const float inv = 1.f / sum;
+    __half* dst = out + (size_t)row * ld_o;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int v = tid + 256 * i;
+        if (v < V) {
+            const __half2 a = __floats2half2_rn(q[i].x * inv, q[i].y * inv), b = __floats2half2_rn(q[i].z * inv, q[i].w * inv);
+            *reinterpret_cast<uint2*>(dst + v * 4) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+        }
+    }
+}
+
+// out[c][r] = in[r][c] for a 16-bit plane (V -> V^T: the B operand of the P V product must be K-major); 32 x 32 tiles through shared memory
+__global__ void transpose_plane_kernel(const unsigned short* __restrict__ in, int ld_in, int rows, int cols, unsigned short* __restrict__ out, int ld_out) {
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ unsigned short tile[32][34];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 256 threads: 8 rows per pass
+    for (int j = ty; j < 32; j += 8) if (r0 + j < rows && c0 + tx < cols) tile[j][tx] = in[(size_t)(r0 + j) * ld_in + c0 + tx];
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) if (c0 + j < cols && r0 + tx < rows) out[(size_t)(c0 + j) * ld_out + r0 + tx] = tile[tx][j];
+}
+
+// VectorQuantizer lookup + post_quant_conv (taming VectorQuantizer2 / ldm VQModelInterface.decode): for every pixel
+// of z NCHW [B, E, H, W] (E <= 4) the nearest codebook row by d = |z|^2 + |e|^2 - 2 z.e (first minimum wins), then the 1x1 post_quant_conv
+// [Z, E] (+bias) -> NHWC rows [B*H*W, ld] (ld >= Z).  quantize == 0 skips the lookup (force_not_quantize).  The codebook is streamed through
+// shared memory in chunks that every thread of the CTA scans.
+__global__ void __launch_bounds__(256) vq_quantize_kernel(const float* __restrict__ z, int B, int E, int HW, const float* __restrict__ codebook, int n_e,
+                                                          const float* __restrict__ pq_w, const float* __restrict__ pq_b, int Z, int quantize,
+                                                          float* __restrict__ out, int ld) {
+    __shared__ float4 s_code[1024];
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x, total = (long long)B * HW;
+    const bool ok = pix < total;
+    float zv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ok) { const long long b = pix / HW, p = pix % HW; for (int e = 0; e < E; e++) zv[e] = z[(b * E + e) * HW + p]; }
+    float zq[4] = {zv[0], zv[1], zv[2], zv[3]};
+    if (quantize) {
+        const float zz = ((zv[0] * zv[0] + zv[1] * zv[1]) + zv[2] * zv[2]) + zv[3] * zv[3];
+        float best = CUDART_INF_F; int bi = 0;
+        for (int c0 = 0; c0 < n_e; c0 += 1024) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < 1024 && c0 + i < n_e; i += blockDim.x) {
+                float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* cr = codebook + (size_t)(c0 + i) * E;
+                e4.x = cr[0]; if (E > 1) e4.y = cr[1]; if (E > 2) e4.z = cr[2]; if (E > 3) e4.w = cr[3];
+                s_code[i] = e4;
+            }
+            __syncthreads();
+            const int cn = n_e - c0 < 1024 ? n_e - c0 : 1024;
+            for (int i = 0; i < cn; i++) {
+                const float4 e4 = s_code[i];
+                const float ee = ((e4.x * e4.x + e4.y * e4.y) + e4.z * e4.z) + e4.w * e4.w;
+                const float dot = ((zv[0] * e4.x + zv[1] * e4.y) + zv[2] * e4.z) + zv[3] * e4.w;
+                const float d = (zz + ee) - 2.f * dot;
+                if (d < best) { best = d; bi = c0 + i; }
+            }
+        }
+        const float* cr = codebook + (size_t)bi * E;
+        for (int e = 0; e < E; e++) zq[e] = cr[e];
+    }
+    if (!ok) return;
+    for (int o = 0; o < Z; o++) {
+        float acc = pq_b ? pq_b[o] : 0.f;
+        for (int e = 0; e < E; e++) acc = fmaf(pq_w[o * E + e], zq[e], acc);
+        out[pix * ld + o] = acc;
+    }
+    for (int o = Z; o < ld; o++) out[pix * ld + o] = 0.f;
+}
+
 #define LAUNCH_CHECK() do { RDM_COUNT_LAUNCH(); RDM_CHECK_CUDA(cudaGetLastError()); } while (0)
 
 int k_nchw_to_nhwc(const float* x, int Bsrc, int Bout, int C, int H, int W, View out, cudaStream_t st) {
@@ -398,7 +511,7 @@ int k_gn_stats(View x, int B, int HW, int groups, double* sums, cudaStream_t st)
     int rows_per_cta = nslots * 8;
     int chunks = (HW + rows_per_cta - 1) / rows_per_cta;
     while (chunks * B > 148 * 8 && rows_per_cta < HW) { rows_per_cta *= 2; chunks = (HW + rows_per_cta - 1) / rows_per_cta; }
-    RDM_CHECK_CUDA(launch_pdl(gn_stats_kernel, dim3(chunks, B), dim3(threads), 2 * groups * sizeof(float), st, (const float*)x.p, x.ld, x.C, HW, groups, rows_per_cta, sums));
+    RDM_CHECK_CUDA(launch_pdl(gn_stats_kernel, dim3(chunks, B), dim3(threads), 2 * groups * sizeof(double), st, (const float*)x.p, x.ld, x.C, HW, groups, rows_per_cta, sums));
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps, const float* gamma, const float* beta, int silu, Out4 y, Out4 raw, cudaStream_t st) {
@@ -436,6 +549,23 @@ int k_attention_d64(View q, View k, View v, int B, int N, int heads, float scale
     int threads = N >= 128 ? 128 : ((N + 31) / 32) * 32;
     dim3 grid((N + threads - 1) / threads, heads, B);
     RDM_CHECK_CUDA(launch_pdl(attention_kernel<64, 1>, grid, dim3(threads), 0, st, (const float*)q.p, q.ld, (const float*)k.p, k.ld, (const float*)v.p, v.ld, N, N, scale * 1.4426950408889634f, causal, out));
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_softmax_rows(const float* s, int ld_s, int M, int N, float scale, __half* out, int ld_o, cudaStream_t st) {
+    RDM_REQUIRE(N % 4 == 0 && N <= 4096 && ld_s % 4 == 0 && ld_o % 4 == 0, RDM_ERR_UNSUPPORTED, "softmax_rows: N=%d (multiple of 4, <= 4096)", N);
+    RDM_CHECK_CUDA(launch_pdl(softmax_rows_kernel, dim3(M), dim3(256), 0, st, s, ld_s, N, scale * 1.4426950408889634f, out, ld_o));
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_transpose_plane(const __half* in, int ld_in, int rows, int cols, __half* out, int ld_out, cudaStream_t st) {
+    RDM_CHECK_CUDA(launch_pdl(transpose_plane_kernel, dim3((cols + 31) / 32, (rows + 31) / 32), dim3(256), 0, st,
+                              reinterpret_cast<const unsigned short*>(in), ld_in, rows, cols, reinterpret_cast<unsigned short*>(out), ld_out));
+    LAUNCH_CHECK(); return RDM_OK;
+}
+int k_vq_quantize(const float* z, int B, int E, int HW, const float* codebook, int n_e, const float* pq_w, const float* pq_b, int Z, int quantize,
+                  View out, cudaStream_t st) {
+    RDM_REQUIRE(E >= 1 && E <= 4 && Z >= 1 && Z <= out.ld, RDM_ERR_UNSUPPORTED, "vq_quantize: embed_dim=%d z_channels=%d", E, Z);
+    const long long total = (long long)B * HW;
+    vq_quantize_kernel<<<blocks_for(total, 256), 256, 0, st>>>(z, B, E, HW, codebook, n_e, pq_w, pq_b, Z, quantize, out.p, out.ld);
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_split_planes(View x, long long M, Out4 y, cudaStream_t st) {

@@ -86,6 +86,11 @@ bool k_attention_mma_supported(int Nq, int Nk);
 int k_attention_mma(const __half* q, const __half* k, const __half* v, int ld, int B, int Nq, int Nk, int heads, float scale, Out4 out, cudaStream_t st);
 // same for heads of width 64 (CLIP), optional causal mask (key j visible to query i iff j <= i; custom_clip/model.py:287-292)
 int k_attention_d64(View q, View k, View v, int B, int N, int heads, float scale, int causal, Out4 out, cudaStream_t st);
+// first-stage decoder glue: P = softmax(scale * S) rows as an fp16 plane; 16-bit plane transpose (V -> V^T); VQ lookup + post_quant_conv
+int k_softmax_rows(const float* s, int ld_s, int M, int N, float scale, __half* out, int ld_o, cudaStream_t st);
+int k_transpose_plane(const __half* in, int ld_in, int rows, int cols, __half* out, int ld_out, cudaStream_t st);
+int k_vq_quantize(const float* z, int B, int E, int HW, const float* codebook, int n_e, const float* pq_w, const float* pq_b, int Z, int quantize,
+                  View out, cudaStream_t st);
 // fp32 [M, C] -> bf16 planes
 int k_split_planes(View x, long long M, Out4 y, cudaStream_t st);
 // im2col of a 3x3 / stride 2 / pad 1 conv (ldm Downsample): x NHWC [B,H,W,C] -> [B*Ho*Wo, 9*C] (tap-major), Ho=(H+1)/2

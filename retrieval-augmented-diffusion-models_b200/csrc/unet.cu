@@ -15,6 +15,8 @@
 #include <vector>
 #include <memory>
 #include <cstring>
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 namespace {
@@ -39,7 +41,10 @@ struct Norm { int C = 0; float* g = nullptr; float* b = nullptr; };
 struct Conv { int cin = 0, cout = 0, ks = 1; float* w = nullptr; float* b = nullptr; };     // w: [cout][ks*ks*cin] (tap-major K)
 struct Lin { int in = 0, out = 0; float* w = nullptr; float* b = nullptr; };                // w: [out][in]
 
-struct ResW { int cin, cout; Norm n1; Conv c1; int emb_off; Norm n2; Conv c2; bool has_skip; Conv skip; };
+struct ResW { int cin, cout; Norm n1; Conv c1; int emb_off; Norm n2; Conv c2; bool has_skip; Conv skip; float eps = 1e-5f; };   // emb_off < 0: no time embedding (VQ decoder ResnetBlock)
+struct AttnW { int C; Norm norm; Lin qkv; Conv proj_out; };     // taming/ldm AttnBlock: single head over all pixels, q/k/v 1x1 convs concatenated [3C, C]
+enum DecKind { D_RES, D_ATTN, D_UP };
+struct DecLayer { DecKind kind; int idx; };
 struct STW { int C, heads, id; Norm norm; Conv proj_in; Norm ln1, ln2, ln3; Lin qkv, o1, q2, kv2, o2, ff1, ff2; Conv proj_out; };
 enum LayerKind { L_CONV_IN, L_RES, L_ST, L_DOWN, L_UP };
 struct Layer { LayerKind kind; int idx; };
@@ -63,6 +68,11 @@ struct rdm_unet {
     Lin te0, te2, emb_all; Norm out_norm; Conv out_conv;
     int emb_total = 0, ted = 0;
     std::vector<int> skip_ch;          // channels of hs[i]
+    // first-stage VQ decoder (kind == 1): ldm.modules.diffusionmodules.model.Decoder behind VQModelInterface.decode
+    int kind = 0; rdm_vqdec_cfg dcfg{};
+    std::vector<AttnW> attns; std::vector<DecLayer> dec_layers; Conv dec_conv_in, dec_conv_out; Norm dec_norm_out;
+    float* codebook = nullptr; float* pq_w = nullptr; float* pq_b = nullptr;
+    cudaGraphExec_t dec_exec = nullptr; int dec_key[5] = {0, 0, 0, 0, -1}; unsigned long long dec_kernels = 0; float* dec_in = nullptr; float* dec_out = nullptr; size_t dec_io_cap = 0;
     // runtime
     Arena arena; double* stats = nullptr; size_t stats_cap = 0, stats_off = 0;
     float* ctx_kv = nullptr; size_t ctx_kv_floats = 0; std::vector<size_t> ctx_off; int ctx_B = 0, ctx_k = 0;
@@ -351,12 +361,12 @@ void run_res(Ctx& cx, const ResW& r, const Act& x, const float* emb_all, View ou
     const bool tcs = r.has_skip && tc_ok(cx, x.B, x.H, x.W, r.cin, 1);
     Opnd a1 = fresh_opnd(cx, M, r.cin, tc1), xraw;
     if (tcs) xraw = fresh_opnd(cx, M, r.cin, true);
-    gn(cx, x, r.n1, 1e-5f, 1, a1, tcs ? &xraw : nullptr);
+    gn(cx, x, r.n1, r.eps, 1, a1, tcs ? &xraw : nullptr);
     View h1 = fresh(cx, M, r.cout);
-    { GemmEpi e; e.rowvec = emb_all + r.emb_off; e.rowvec_ld = cx.n->emb_total; e.rows_per_batch = x.H * x.W;
+    { GemmEpi e; if (r.emb_off >= 0) { e.rowvec = emb_all + r.emb_off; e.rowvec_ld = cx.n->emb_total; e.rows_per_batch = x.H * x.W; }
       conv_any(cx, a1, x, r.c1, e, from_view(h1)); }
     Opnd a2 = fresh_opnd(cx, M, r.cout, tc2);
-    gn(cx, Act{h1, x.B, x.H, x.W}, r.n2, 1e-5f, 1, a2);
+    gn(cx, Act{h1, x.B, x.H, x.W}, r.n2, r.eps, 1, a2);
     View resv = x.v;
     if (r.has_skip) { resv = fresh(cx, M, r.cout); conv_any(cx, tcs ? xraw : from_view(x.v), x, r.skip, GemmEpi(), from_view(resv)); }
     { GemmEpi e; e.res = resv.p; e.res_ld = resv.ld; conv_any(cx, a2, x, r.c2, e, from_view(out)); }
@@ -545,6 +555,141 @@ int forward_impl(Net* n, const float* x_nchw, int Bx, const long long* t, int B2
     return cx.rc;
 }
 
+// ---- first-stage VQ decoder -----------------------------------------------------------------------------------
+// Mirrors ldm/taming `Decoder.__init__` (conv_in, mid.block_1 / attn_1 / block_2, up levels from the coarsest, norm_out, conv_out) with the
+// latent-diffusion checkpoint key layout (`decoder.*`, `quantize.embedding.weight`, `post_quant_conv.*`).  Called twice like build_net.
+int add_dec_res(Net* n, const std::string& p, int cin, int cout) {
+    ResW r{}; r.cin = cin; r.cout = cout; r.eps = 1e-6f; r.emb_off = -1;
+    r.n1 = make_norm(n, p + ".norm1", cin); r.c1 = make_conv(n, p + ".conv1", cin, cout, 3);
+    r.n2 = make_norm(n, p + ".norm2", cout); r.c2 = make_conv(n, p + ".conv2", cout, cout, 3);
+    r.has_skip = cin != cout;
+    if (r.has_skip) r.skip = make_conv(n, p + ".nin_shortcut", cin, cout, 1);
+    n->res.push_back(r);
+    return (int)n->res.size() - 1;
+}
+int add_dec_attn(Net* n, const std::string& p, int C) {
+    AttnW a{}; a.C = C;
+    a.norm = make_norm(n, p + ".norm", C);
+    a.qkv.in = C; a.qkv.out = 3 * C; a.qkv.w = walloc(n, (size_t)3 * C * C); a.qkv.b = walloc(n, 3 * C);
+    const char* nm[3] = {".q", ".k", ".v"};
+    for (int i = 0; i < 3; i++) {
+        reg_rows(n, p + nm[i] + ".weight", a.qkv.w, C, C, i * C, 1);          // 1x1 conv weight [C, C, 1, 1] == [C][C]
+        reg_rows(n, p + nm[i] + ".bias", a.qkv.b, C, 1, i * C, 1);
+    }
+    a.proj_out = make_conv(n, p + ".proj_out", C, C, 1);
+    n->attns.push_back(a);
+    return (int)n->attns.size() - 1;
+}
+void build_decoder(Net* n) {
+    const rdm_vqdec_cfg& c = n->dcfg;
+    n->woff = 0; n->params.clear(); n->param_order.clear(); n->res.clear(); n->attns.clear(); n->convs.clear(); n->dec_layers.clear();
+    const int L = c.n_ch_mult;
+    int block_in = c.ch * c.ch_mult[L - 1], curr_res = c.resolution >> (L - 1);
+    n->dec_conv_in = make_conv(n, "decoder.conv_in", c.z_channels, block_in, 3);
+    n->dec_layers.push_back({D_RES, add_dec_res(n, "decoder.mid.block_1", block_in, block_in)});
+    n->dec_layers.push_back({D_ATTN, add_dec_attn(n, "decoder.mid.attn_1", block_in)});
+    n->dec_layers.push_back({D_RES, add_dec_res(n, "decoder.mid.block_2", block_in, block_in)});
+    for (int lvl = L - 1; lvl >= 0; lvl--) {
+        const int block_out = c.ch * c.ch_mult[lvl];
+        const std::string up = "decoder.up." + std::to_string(lvl);
+        for (int i = 0; i <= c.num_res_blocks; i++) {
+            n->dec_layers.push_back({D_RES, add_dec_res(n, up + ".block." + std::to_string(i), block_in, block_out)});
+            block_in = block_out;
+            if (in_list(c.attn_resolutions, c.n_attn_resolutions, curr_res))
+                n->dec_layers.push_back({D_ATTN, add_dec_attn(n, up + ".attn." + std::to_string(i), block_in)});
+        }
+        if (lvl != 0) {
+            n->convs.push_back(make_conv(n, up + ".upsample.conv", block_in, block_in, 3));
+            n->dec_layers.push_back({D_UP, (int)n->convs.size() - 1});
+            curr_res *= 2;
+        }
+    }
+    n->dec_norm_out = make_norm(n, "decoder.norm_out", block_in);
+    n->dec_conv_out = make_conv(n, "decoder.conv_out", block_in, c.out_ch, 3);
+    n->codebook = walloc(n, (size_t)c.n_embed * c.embed_dim); reg_plain(n, "quantize.embedding.weight", n->codebook, (size_t)c.n_embed * c.embed_dim);
+    n->pq_w = walloc(n, (size_t)c.z_channels * c.embed_dim); reg_plain(n, "post_quant_conv.weight", n->pq_w, (size_t)c.z_channels * c.embed_dim);
+    n->pq_b = walloc(n, c.z_channels); reg_plain(n, "post_quant_conv.bias", n->pq_b, c.z_channels);
+}
+
+// AttnBlock.forward: h = GN(x); q,k,v = 1x1 convs; w = softmax(q k^T * C^-0.5) over ALL pixels of the image; out = x + proj_out(w v).
+// One head of width C (512): both contractions are real GEMMs (4096 x 4096 x 512 per image at 64 x 64), so they run on the tcgen05 engine
+// per image with the K / V^T planes of that image as the "weight" operand; softmax and the V transpose are row / tile kernels in between.
+void run_dec_attn(Ctx& cx, const AttnW& a, const Act& x, View out) {
+    Net* n = cx.n; Arena& A = n->arena; size_t mk = A.mark();
+    const int M = x.M(), C = a.C, HW = x.H * x.W;
+    Opnd g = fresh_opnd(cx, M, C, true);
+    gn(cx, x, a.norm, 1e-6f, 0, g);
+    Opnd qkv; qkv.hi = (__nv_bfloat16*)A.alloc((size_t)M * 3 * C * 2); qkv.ldb = 3 * C; qkv.f.C = 3 * C; qkv.f16 = 1;
+    lin_any(cx, g, M, a.qkv, GemmEpi(), qkv);
+    Opnd o; o.hi = (__nv_bfloat16*)A.alloc((size_t)M * C * 2); o.ldb = C; o.f.C = C; o.f16 = 1;
+    float* S = A.allocf((size_t)HW * HW);
+    __half* P = (__half*)A.alloc((size_t)HW * HW * 2);
+    __half* Vt = (__half*)A.alloc((size_t)C * HW * 2);
+    const float scale = 1.f / sqrtf((float)C);
+    for (int b = 0; b < x.B; b++) {
+        const __nv_bfloat16* base = qkv.hi + (size_t)b * HW * 3 * C;
+        TcA qa; qa.hi = base; qa.ld = 3 * C; qa.B = 1; qa.H = 1; qa.W = HW; qa.C = C; qa.ksize = 1;
+        TcW kw; kw.hi = base + C; kw.ld = 3 * C; kw.N = HW; kw.K = C; kw.dynamic = 1;
+        { GemmEpi e; e.out = S; e.out_ld = HW; RUN(gemm_tc(qa, kw, e, nullptr, nullptr, 0, 1, 1, cx.st)); }
+        RUN(k_softmax_rows(S, HW, HW, HW, scale, P, HW, cx.st));
+        RUN(k_transpose_plane(reinterpret_cast<const __half*>(base + 2 * C), 3 * C, HW, C, Vt, HW, cx.st));
+        TcA pa; pa.hi = reinterpret_cast<const __nv_bfloat16*>(P); pa.ld = HW; pa.B = 1; pa.H = 1; pa.W = HW; pa.C = HW; pa.ksize = 1;
+        TcW vw; vw.hi = reinterpret_cast<const __nv_bfloat16*>(Vt); vw.ld = HW; vw.N = C; vw.K = HW; vw.dynamic = 1;
+        RUN(gemm_tc(pa, vw, GemmEpi(), o.hi + (size_t)b * HW * C, nullptr, C, 1, 1, cx.st));
+    }
+    { GemmEpi e; e.res = x.v.p; e.res_ld = x.v.ld; conv_any(cx, o, x, a.proj_out, e, from_view(out)); }
+    A.release(mk);
+}
+
+// images NCHW [B, out_ch, 2^(L-1) h, 2^(L-1) w] = Decoder(post_quant_conv(quantize(z)))  for z NCHW [B, embed_dim, h, w]
+int dec_forward_impl(Net* n, const float* z_nchw, int B, int h, int w, int quantize, float* out_nchw, cudaStream_t st, bool dry) {
+    Ctx cx{n, st, dry};
+    Arena& A = n->arena; A.off = 0; A.dry = dry; n->stats_off = 0;
+    const rdm_vqdec_cfg& c = n->dcfg;
+    if (!dry) RDM_CHECK_CUDA(cudaMemsetAsync(n->stats, 0, n->stats_cap * sizeof(double), st));
+    // two ping-pong activation buffers sized for the largest layer output
+    size_t big = 0;
+    { int H = h, W = w, ch = c.ch * c.ch_mult[c.n_ch_mult - 1];
+      big = (size_t)B * H * W * ch;
+      for (const DecLayer& L : n->dec_layers) {
+          if (L.kind == D_RES) ch = n->res[L.idx].cout;
+          if (L.kind == D_UP) { H *= 2; W *= 2; }
+          big = std::max(big, (size_t)B * H * W * ch);
+      } }
+    float* buf[2] = {A.allocf(big), A.allocf(big)};
+    int H = h, W = w, cur = 0;
+    View z0 = fresh(cx, B * H * W, 4); z0.C = c.z_channels;
+    RUN(k_vq_quantize(z_nchw, B, c.embed_dim, H * W, n->codebook, c.n_embed, n->pq_w, n->pq_b, c.z_channels, quantize, z0, st));
+    Act x{View(buf[cur], n->dec_conv_in.cout, n->dec_conv_in.cout), B, H, W};
+    gemm_any(cx, from_view(z0), B, H, W, c.z_channels, 3, 1, 0, n->dec_conv_in.w, n->dec_conv_in.b, n->dec_conv_in.cout, GemmEpi(), from_view(x.v));
+    for (const DecLayer& L : n->dec_layers) {
+        const int nxt = cur ^ 1;
+        if (L.kind == D_RES) {
+            const ResW& r = n->res[L.idx];
+            View o(buf[nxt], r.cout, r.cout);
+            run_res(cx, r, x, nullptr, o);
+            x = Act{o, B, H, W};
+        } else if (L.kind == D_ATTN) {
+            View o(buf[nxt], x.v.C, x.v.C);
+            run_dec_attn(cx, n->attns[L.idx], x, o);
+            x = Act{o, B, H, W};
+        } else {
+            const Conv& cv = n->convs[L.idx];
+            View o(buf[nxt], cv.cout, cv.cout);
+            run_up(cx, cv, x, o);
+            H *= 2; W *= 2;
+            x = Act{o, B, H, W};
+        }
+        cur = nxt;
+    }
+    Opnd a = fresh_opnd(cx, x.M(), x.v.C, tc_ok(cx, B, H, W, x.v.C, 3));
+    gn(cx, x, n->dec_norm_out, 1e-6f, 1, a);
+    View o = fresh(cx, x.M(), 4); o.C = c.out_ch;
+    conv_any(cx, a, x, n->dec_conv_out, GemmEpi(), from_view(o));
+    RUN(k_nhwc_to_nchw(o, B, c.out_ch, H, W, out_nchw, st));
+    return cx.rc;
+}
+
 // (re)build the bf16 hi/lo planes of every packed weight matrix: one element-wise pass over the weight arena
 int ensure_weight_planes(Net* n, cudaStream_t st) {
     if (n->mode == RDM_UNET_MODE_FP32 || !n->planes_dirty) return RDM_OK;
@@ -674,6 +819,9 @@ void rdm_unet_destroy(rdm_unet_t* n) {
     if (n->t_in) cudaFree(n->t_in);
     if (n->step_dev) cudaFree(n->step_dev);
     if (n->cap_stream) cudaStreamDestroy(n->cap_stream);
+    if (n->dec_exec) cudaGraphExecDestroy(n->dec_exec);
+    if (n->dec_in) cudaFree(n->dec_in);
+    if (n->dec_out) cudaFree(n->dec_out);
     delete n;
 }
 
@@ -758,6 +906,7 @@ int rdm_unet_set_context(rdm_unet_t* n, const float* ctx, int32_t B2, int32_t k,
 
 int rdm_unet_forward(rdm_unet_t* n, const float* x, int32_t Bx, const int64_t* t, int32_t B2, int32_t H, int32_t W, float* eps_out, void* stream) {
     RDM_REQUIRE(n && x && t && eps_out, RDM_ERR_ARG, "rdm_unet_forward: null argument");
+    RDM_REQUIRE(n->kind == 0, RDM_ERR_ARG, "rdm_unet_forward: this handle is a VQ decoder (use rdm_vqdec_decode)");
     RDM_REQUIRE(B2 >= 1 && (Bx == B2 || Bx * 2 == B2), RDM_ERR_ARG, "rdm_unet_forward: Bx=%d must equal B2=%d or B2/2", Bx, B2);
     RDM_REQUIRE(n->ctx_B == B2, RDM_ERR_STATE, "rdm_unet_forward: context was set for batch %d, forward called with %d (call rdm_unet_set_context first)", n->ctx_B, B2);
     int div = 1; for (int i = 1; i < n->cfg.n_channel_mult; i++) div *= 2;
@@ -822,6 +971,84 @@ int rdm_unet_profile_forward(rdm_unet_t* n, const float* x, int32_t Bx, const in
     n->prof_ev.clear(); n->prof_flops.clear(); n->prof_kind.clear();
     RDM_REQUIRE(ce == cudaSuccess, RDM_ERR_CUDA, "rdm_unet_profile_forward: %s", cudaGetErrorString(ce));
     return rc;
+}
+
+
+// ---- first-stage VQ decoder entry points ------------------------------------------------------------------------------------------------
+int rdm_vqdec_create(rdm_unet_t** out, const rdm_vqdec_cfg* cfg, int32_t device) {
+    RDM_REQUIRE(out && cfg, RDM_ERR_ARG, "rdm_vqdec_create: null argument");
+    RDM_REQUIRE(cfg->n_ch_mult >= 1 && cfg->n_ch_mult <= 8 && cfg->n_attn_resolutions >= 0 && cfg->n_attn_resolutions <= 8, RDM_ERR_ARG, "rdm_vqdec_create: bad list sizes");
+    RDM_REQUIRE(cfg->ch % 64 == 0, RDM_ERR_UNSUPPORTED, "rdm_vqdec_create: ch must be a multiple of 64 (GroupNorm32 + 64-wide K blocks), got %d", cfg->ch);
+    RDM_REQUIRE(cfg->embed_dim >= 1 && cfg->embed_dim <= 4 && cfg->z_channels >= 1 && cfg->z_channels <= 4 && cfg->out_ch >= 1 && cfg->out_ch <= 4,
+                RDM_ERR_UNSUPPORTED, "rdm_vqdec_create: embed_dim / z_channels / out_ch must be 1..4");
+    RDM_REQUIRE(cfg->n_embed >= 1 && cfg->num_res_blocks >= 1, RDM_ERR_ARG, "rdm_vqdec_create: n_embed / num_res_blocks");
+    DeviceGuard guard(device);
+    RDM_REQUIRE(guard.ok, RDM_ERR_CUDA, "rdm_vqdec_create: cannot select device %d", device);
+    rdm_unet* n = new rdm_unet();
+    n->device = device; n->kind = 1; n->dcfg = *cfg; n->mode = RDM_UNET_MODE_TC_FP16X2;
+    build_decoder(n);                               // counting pass
+    n->wfloats = n->woff;
+    if (cudaMalloc((void**)&n->wbase, n->wfloats * sizeof(float)) != cudaSuccess) { delete n; rdm_set_error("rdm_vqdec_create: cudaMalloc for weights failed"); return RDM_ERR_CUDA; }
+    cudaMemset(n->wbase, 0, n->wfloats * sizeof(float));
+    build_decoder(n);                               // placing pass
+    *out = n;
+    return RDM_OK;
+}
+
+int rdm_vqdec_decode(rdm_unet_t* n, const float* z, int32_t B, int32_t h, int32_t w, int32_t quantize, float* out, void* stream) {
+    RDM_REQUIRE(n && z && out, RDM_ERR_ARG, "rdm_vqdec_decode: null argument");
+    RDM_REQUIRE(n->kind == 1, RDM_ERR_ARG, "rdm_vqdec_decode: this handle is not a VQ decoder");
+    RDM_REQUIRE(mode_f16(n->mode), RDM_ERR_UNSUPPORTED, "rdm_vqdec_decode: the decoder runs in the fp16 tensor-core modes only (fp16x2 / fp16), mode is %d", n->mode);
+    RDM_REQUIRE(B >= 1 && h >= 1 && w >= 1, RDM_ERR_ARG, "rdm_vqdec_decode: B=%d h=%d w=%d", B, h, w);
+    for (auto& kv : n->params) RDM_REQUIRE(kv.second.loaded, RDM_ERR_STATE, "rdm_vqdec_decode: parameter '%s' was never loaded", kv.first.c_str());
+    DeviceGuard guard(n->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int up = 1 << (n->dcfg.n_ch_mult - 1);
+    const size_t zin = (size_t)B * n->dcfg.embed_dim * h * w, zout = (size_t)B * n->dcfg.out_ch * h * w * up * up;
+    if (n->plan_B != B || n->plan_H != h || n->plan_W != w || !n->arena.base) {
+        n->arena.dry = true; n->arena.off = 0; n->arena.peak = 0; n->stats_off = 0;
+        RDM_TRY(dec_forward_impl(n, nullptr, B, h, w, quantize, nullptr, 0, true));
+        const size_t need = n->arena.peak, sneed = n->stats_off;
+        if (need > n->arena.cap) {
+            if (n->arena.base) cudaFree(n->arena.base);
+            n->arena.base = nullptr; n->arena.cap = 0;
+            RDM_CHECK_CUDA(cudaMalloc((void**)&n->arena.base, need));
+            n->arena.cap = need;
+        }
+        if (sneed > n->stats_cap) {
+            if (n->stats) cudaFree(n->stats);
+            n->stats = nullptr; n->stats_cap = 0;
+            RDM_CHECK_CUDA(cudaMalloc((void**)&n->stats, sneed * sizeof(double)));
+            n->stats_cap = sneed;
+        }
+        n->plan_B = B; n->plan_H = h; n->plan_W = w;
+        if (n->dec_exec) { cudaGraphExecDestroy(n->dec_exec); n->dec_exec = nullptr; }
+    }
+    RDM_TRY(ensure_weight_planes(n, st));
+    if (!n->cap_stream) RDM_CHECK_CUDA(cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking));
+    if (zin + zout > n->dec_io_cap) {
+        if (n->dec_in) cudaFree(n->dec_in);
+        if (n->dec_out) cudaFree(n->dec_out);
+        n->dec_in = n->dec_out = nullptr; n->dec_io_cap = 0;
+        if (n->dec_exec) { cudaGraphExecDestroy(n->dec_exec); n->dec_exec = nullptr; }
+        RDM_CHECK_CUDA(cudaMalloc((void**)&n->dec_in, zin * 4)); RDM_CHECK_CUDA(cudaMalloc((void**)&n->dec_out, zout * 4));
+        n->dec_io_cap = zin + zout;
+    }
+    RDM_CHECK_CUDA(cudaMemcpyAsync(n->dec_in, z, zin * 4, cudaMemcpyDeviceToDevice, st));
+    const int key[5] = {B, h, w, quantize, n->mode};
+    if (!n->use_graph) {
+        RDM_TRY(dec_forward_impl(n, n->dec_in, B, h, w, quantize, n->dec_out, st, false));
+    } else if (!n->dec_exec || memcmp(key, n->dec_key, sizeof(key)) != 0) {
+        RDM_TRY(dec_forward_impl(n, n->dec_in, B, h, w, quantize, n->dec_out, st, false));       // eager warm-up: sets kernel attributes, produces this call's result
+        RDM_CHECK_CUDA(cudaStreamSynchronize(st));
+        RDM_TRY(capture_graph(n, &n->dec_exec, &n->dec_kernels, [&](cudaStream_t cs) { return dec_forward_impl(n, n->dec_in, B, h, w, quantize, n->dec_out, cs, false); }));
+        memcpy(n->dec_key, key, sizeof(key));
+    } else {
+        RDM_CHECK_CUDA(cudaGraphLaunch(n->dec_exec, st));
+        g_rdm_launches += n->dec_kernels;
+    }
+    RDM_CHECK_CUDA(cudaMemcpyAsync(out, n->dec_out, zout * 4, cudaMemcpyDeviceToDevice, st));
+    return RDM_OK;
 }
 
 const char* rdm_unet_profile_text(const rdm_unet_t* n) { return n ? n->prof_text.c_str() : ""; }

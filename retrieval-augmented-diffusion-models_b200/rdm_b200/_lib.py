@@ -44,6 +44,8 @@ SIGNATURES = {
     "rdm_unet_profile_forward": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "rdm_unet_profile_text": (c_char_p, [c_void_p]),
     "rdm_ddim_sample": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
+    "rdm_vqdec_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int32]),
+    "rdm_vqdec_decode": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "rdm_clip_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int32]),
     "rdm_clip_destroy": (None, [c_void_p]),
     "rdm_clip_num_params": (c_int64, [c_void_p]),
