@@ -202,7 +202,7 @@ class MinimalRETRODiffusion(nn.Module):
     def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
         if self.first_stage_model is None:
             return z
-        return self.first_stage_model.decode(1. / self.scale_factor * z)
+        return self.first_stage_model.decode(1. / self.scale_factor * z, force_not_quantize=predict_cids or force_not_quantize)
 
     def get_unconditional_guiding_vex(self, vector_shape):
         print('Initializing unconditional guidance vector')

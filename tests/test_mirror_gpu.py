@@ -105,3 +105,37 @@ def test_default_engine_mode_runs_end_to_end(tmp_path, cuda):
     cond = torch.from_numpy(db[logs["nns"].cpu().numpy()].astype(np.float32))
     want = oddim.ddim_sample(ema, x_T, cond, torch.zeros_like(cond), S=5, scale=2.0)
     assert torch.isfinite(logs["latents"]).all() and rel_l2(logs["latents"], want) < 2e-2
+
+
+def test_first_stage_decode_runs_on_the_device(tmp_path, cuda):
+    """`decode_first_stage` (ddpm.py:840,981): with a first_stage_config the sampler returns IMAGES decoded by the CUDA VQ decoder
+    (librdm_b200 rdm_vqdec_decode behind ldm.models.autoencoder.VQModelInterface); checked against the oracle decoder on the returned latents."""
+    import copy
+    import rdm  # noqa: F401
+    from ldm.util import instantiate_from_config
+    from omegaconf import OmegaConf
+    from oracle import vqdecoder as ovq
+    rng = np.random.default_rng(3)
+    db = rng.standard_normal((20_000, 512)).astype(np.float16)
+    np.savez(tmp_path / "db.npz", embedding=db, img_id=np.arange(20_000), patch_coords=np.zeros((20_000, 4), np.int32))
+    vq = dict(embed_dim=4, n_embed=256, ddconfig=dict(ovq.TINY_VQ["ddconfig"], z_channels=4, resolution=32))
+    cfg = copy.deepcopy(TINY_CFG)
+    cfg["params"]["retrieval_cfg"]["params"]["saved_embeddings"] = str(tmp_path / "db.npz")
+    cfg["params"]["first_stage_config"] = {"target": "ldm.models.autoencoder.VQModelInterface", "params": dict(vq, lossconfig={"target": "torch.nn.Identity"})}
+    model = instantiate_from_config(OmegaConf.create(cfg))
+    unet = ounet.randomize_(ounet.UNetModel(**ounet.TINY_UNET), 5).eval()
+    fs = ovq.randomize_(ovq.VQModelInterface(**vq), 6).eval()
+    ck = {"model.diffusion_model." + k: v for k, v in unet.state_dict().items()}
+    ck.update({"model_ema." + ("diffusion_model." + k).replace(".", ""): v for k, v in unet.state_dict().items()})
+    ck.update({"first_stage_model." + k: v for k, v in fs.state_dict().items()})
+    missing, unexpected = model.load_state_dict(ck, strict=False)
+    assert not unexpected and not [m for m in missing if m.startswith("first_stage_model.")]
+    model = model.eval().to(cuda)
+    x_T = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(1))
+    logs = model.sample_from_rdata(2, qids=np.array([10, 20]), k_nn=4, unconditional_guidance_scale=2.0, ddim_steps=5, ddim=True,
+                                   unconditional_retro_guidance_label=0., x_T=x_T.to(cuda))
+    imgs = logs["samples_with_sampled_nns"]
+    assert imgs.is_cuda and imgs.shape == (2, 3, 32, 32)
+    with torch.no_grad():
+        want = fs.decode(logs["latents"].float().cpu() / float(model.scale_factor))
+    assert rel_l2(imgs, want) < 5e-3
