@@ -205,3 +205,91 @@ class DDIMSampler(object):
         if noise_dropout > 0.:
             noise = torch.nn.functional.dropout(noise, p=noise_dropout)
         return a_prev.sqrt() * pred_x0 + dir_xt + noise, pred_x0
+
+
+class DDIMRetroSampler(DDIMSampler):
+    """Per-step re-retrieval sampler (`rdm/models/diffusion/ddim.py:270-415`, BASELINE cfg4): after every DDIM step the x0 prediction is
+    decoded by the first stage, its patches are embedded by the CLIP image retriever, the k nearest database rows are looked up again and
+    become the conditioning of the NEXT step.  Every stage runs on the device (U-Net, VQ decoder, CLIP tower, exact kNN, gather); the loop
+    itself is host-driven because the context changes each step (cross-attention K/V are re-projected by `rdm_unet_set_context`).
+
+    The reference class asserts a `PreNoiserRetroDiffusion` model that is not part of the repository (dead upstream), so the
+    model hooks it reads are optional here: `pre_noise` (default False), `conditional_retrieval_encoder` (False), `adjust_support` (identity)."""
+
+    def __init__(self, model, *args, **kwargs):
+        super().__init__(model, *args, **kwargs)
+        assert hasattr(model, "get_nn_and_encoding"), "the model must provide get_nn_and_encoding (MinimalRETRODiffusion)"
+
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, retro_cond=None, r_shape=None, eta=0., x_T=None, log_every_t=100, verbose=True,
+               unconditional_guidance_scale=1., unconditional_conditioning=None, return_neighbors=False, k_nn=None, ignore_noising=False,
+               callback=None, img_callback=None, mask=None, x0=None, **kwargs):
+        self.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=verbose)
+        size = (batch_size,) + tuple(shape)
+        samples, inter = self.ddim_sampling(conditioning, retro_cond, size, r_shape=r_shape, x_T=x_T, callback=callback, img_callback=img_callback,
+                                            mask=mask, x0=x0, log_every_t=log_every_t, unconditional_guidance_scale=unconditional_guidance_scale,
+                                            unconditional_conditioning=unconditional_conditioning, return_neighbors=return_neighbors, k_nn=k_nn,
+                                            ignore_noising=ignore_noising)
+        return samples.detach(), inter
+
+    @torch.no_grad()
+    def ddim_sampling(self, cond, retro_cond, shape, r_shape=None, x_T=None, ddim_use_original_steps=False, callback=None, timesteps=None,
+                      quantize_denoised=False, mask=None, x0=None, img_callback=None, log_every_t=100, temperature=1., noise_dropout=0.,
+                      score_corrector=None, corrector_kwargs=None, unconditional_guidance_scale=1., unconditional_conditioning=None,
+                      return_neighbors=False, k_nn=None, ignore_noising=False):
+        model, device = self.model, self.model.betas.device
+        if return_neighbors:
+            raise NotImplementedError("neighbour image patches need the patch dataset, which is outside the sampling hot path")
+        if cond is not None:
+            raise NotImplementedError("extra conditionings next to the retrieved neighbours are not implemented")
+        pre_noise = bool(getattr(model, "pre_noise", False))
+        assert not pre_noise and not getattr(model, "conditional_retrieval_encoder", False), "pre-noised / query-conditioned retrieval encoders are not part of the shipped models"
+        adjust_support = getattr(model, "adjust_support", lambda t: t)
+        b = shape[0]
+        k_nn = model.k_nn if k_nn is None else k_nn
+        img = torch.randn(shape, device=device) if x_T is None else x_T.to(device)
+        if retro_cond is None:                                      # ddim.py:296-316: noise as the first conditioning, its shape from r_shape
+            assert r_shape is not None, "r_shape = (b, n*k, d) is needed when no initial retrieval conditioning is given"
+            r_enc = torch.randn(r_shape, device=device)
+        else:
+            r_enc = model.retrieval_encoder(retro_cond.to(device, torch.float32))
+        if timesteps is None:
+            timesteps = self.ddpm_num_timesteps if ddim_use_original_steps else self.ddim_timesteps
+        elif not ddim_use_original_steps:
+            subset_end = int(min(timesteps / self.ddim_timesteps.shape[0], 1) * self.ddim_timesteps.shape[0]) - 1
+            timesteps = self.ddim_timesteps[:subset_end]
+        intermediates = {'x_inter': [], 'pred_x0': [], 'nns': []}
+        time_range = reversed(range(0, timesteps)) if ddim_use_original_steps else np.flip(timesteps)
+        total_steps = timesteps if ddim_use_original_steps else timesteps.shape[0]
+        print(f"Running DDIM Sampling with {total_steps} timesteps")
+        for i, step in enumerate(tqdm(time_range, desc='DDIM Sampler', total=total_steps)):
+            index = total_steps - i - 1
+            ts = torch.full((b,), int(step), device=device, dtype=torch.long)
+            if mask is not None:
+                assert x0 is not None
+                img = model.q_sample(x0, ts) * mask + (1. - mask) * img
+            noise = torch.randn(shape, device=device)                                       # ddim.py:340
+            img, pred_x0 = self.p_sample_ddim(img, [r_enc], ts, index=index, use_original_steps=ddim_use_original_steps,
+                                              quantize_denoised=quantize_denoised, temperature=temperature, noise_dropout=noise_dropout,
+                                              score_corrector=score_corrector, corrector_kwargs=corrector_kwargs,
+                                              unconditional_guidance_scale=unconditional_guidance_scale,
+                                              unconditional_conditioning=unconditional_conditioning, noise=noise)
+            if retro_cond is None:
+                px0 = model.decode_first_stage(pred_x0)                                     # ddim.py:357
+                found = model.get_nn_and_encoding(px0, k_nn=k_nn)                           # ddim.py:358-361
+                rc = found[model.nn_key]
+                intermediates['nns'].append(found['nns'])
+                if rc.ndim == 4:
+                    rc = rc.reshape(rc.shape[0], rc.shape[1] * rc.shape[2], rc.shape[3])    # 'b n k d -> b (n k) d'   ddim.py:374
+            else:
+                rc = retro_cond.to(device, torch.float32)
+            r_enc = model.retrieval_encoder(rc)                                             # ddim.py:396
+            r_enc = adjust_support(r_enc)                                                   # ddim.py:398-400
+            if not ignore_noising:
+                r_enc = model.q_sample(r_enc, ts)                                           # ddim.py:401-402
+            if callback: callback(i)
+            if img_callback: img_callback(pred_x0, i)
+            if index % log_every_t == 0 or index == total_steps - 1:
+                intermediates['x_inter'].append(img)
+                intermediates['pred_x0'].append(pred_x0)
+        return img, intermediates

@@ -229,6 +229,33 @@ class MinimalRETRODiffusion(nn.Module):
             self.train_searcher()
         return self.retriever.searcher
 
+    @torch.no_grad()
+    def get_nn_and_encoding(self, query, return_patches=False, k_nn=None, n_patches_per_side=None, return_query_patches=False):
+        """`ddpm.py:263-316`, device resident: image batch in [-1, 1] -> n x n patches -> retriever (CLIP image tower) -> q / ||q|| ->
+        exact kNN -> raw neighbour rows.  Returns {nn_key: float32 [b, n*n, k, d]} (+ 'query_patches').  Used by the per-step
+        re-retrieval sampler (`ddim.py:355-380`, BASELINE cfg4)."""
+        searcher = self._searcher()
+        n_ptch = self.n_patches_per_side if n_patches_per_side is None else n_patches_per_side
+        k_nn = self.k_nn if k_nn is None else k_nn
+        query = query.to(self.device)
+        if not isimage(query):
+            query = query.permute(0, 3, 1, 2)                                              # 'b h w c -> b c h w'    ddpm.py:275
+        side = query.shape[-1] // n_ptch
+        queries = torch.stack([query[..., i * side:(i + 1) * side, j * side:(j + 1) * side] for i in range(n_ptch) for j in range(n_ptch)], dim=1)
+        output = {}
+        if return_query_patches:
+            output['query_patches'] = queries[:, :, None]                                   # [b, n, 1, c, h, w] (not resized: no first-stage encoder here)
+        queries = queries.reshape(-1, *queries.shape[2:]).contiguous().float()               # '(b n) c h w'           ddpm.py:292
+        q_emb = self.retriever.retriever(queries).float()                                    # CLIP image encode       ddpm.py:294
+        qh = q_emb / q_emb.norm(dim=1, keepdim=True)                                         # ddpm.py:297
+        nns, _ = searcher.search_device(qh.contiguous(), k_nn)                               # ddpm.py:298
+        out = searcher.gather_device(nns)                                                    # data_pool['embedding'][nns]   ddpm.py:301
+        output[self.nn_key] = out.reshape(query.shape[0], n_ptch ** 2, k_nn, out.shape[-1])  # '(b n) k d -> b n k d'
+        output['nns'] = nns
+        if return_patches or self.nn_encoder is not None:
+            raise NotImplementedError("neighbour image patches need the patch dataset, which is outside the sampling hot path")
+        return output
+
     def get_qids(self, memsize, N, qids=None, use_weights=False, verbose=False):
         if isinstance(memsize, float) and hasattr(self, 'nn_memory'):
             assert 0 < memsize <= 1., 'Require memsize in (0,1]'

@@ -139,3 +139,86 @@ def test_first_stage_decode_runs_on_the_device(tmp_path, cuda):
     with torch.no_grad():
         want = fs.decode(logs["latents"].float().cpu() / float(model.scale_factor))
     assert rel_l2(imgs, want) < 5e-3
+
+
+def _retro_model(tmp_path, cuda):
+    """Tiny RDM with a first stage and a (random-weight, one-layer, full-width) CLIP image retriever: everything cfg4's re-retrieval needs."""
+    import copy
+    import rdm  # noqa: F401
+    from ldm.util import instantiate_from_config
+    from omegaconf import OmegaConf
+    from oracle import clip as oclip
+    from oracle import vqdecoder as ovq
+    from rdm_b200.clip import VIT_B32
+    rng = np.random.default_rng(11)
+    db = rng.standard_normal((20_000, 512)).astype(np.float16)
+    np.savez(tmp_path / "db.npz", embedding=db, img_id=np.arange(20_000), patch_coords=np.zeros((20_000, 4), np.int32))
+    vq = dict(embed_dim=4, n_embed=256, ddconfig=dict(ovq.TINY_VQ["ddconfig"], z_channels=4, resolution=32))
+    cfg = copy.deepcopy(TINY_CFG)
+    cfg["params"]["retrieval_cfg"]["params"]["saved_embeddings"] = str(tmp_path / "db.npz")
+    cfg["params"]["first_stage_config"] = {"target": "ldm.models.autoencoder.VQModelInterface", "params": dict(vq, lossconfig={"target": "torch.nn.Identity"})}
+    model = instantiate_from_config(OmegaConf.create(cfg))
+    unet = ounet.randomize_(ounet.UNetModel(**ounet.TINY_UNET), 5).eval()
+    fs = ovq.randomize_(ovq.VQModelInterface(**vq), 6).eval()
+    ck = {"model.diffusion_model." + k: v for k, v in unet.state_dict().items()}
+    ck.update({"model_ema." + ("diffusion_model." + k).replace(".", ""): v for k, v in unet.state_dict().items()})
+    ck.update({"first_stage_model." + k: v for k, v in fs.state_dict().items()})
+    model.load_state_dict(ck, strict=False)
+    model = model.eval().to(cuda)
+    model.model.diffusion_model.engine_mode = "bf16x3"
+    clip_sd = oclip.random_state_dict(**dict(VIT_B32, vocab_size=64, vision_layers=1, transformer_layers=1), seed=7)
+    model.retriever.retriever.model.load_state_dict(clip_sd)
+    model.retriever.retriever.to(cuda)                                                          # scripts/rdm_sample.py:185
+    return model, db, unet
+
+
+def _oracle_nns(model, images, db, k):
+    emb = model.retriever.retriever(images.float()).float().cpu().numpy()
+    qh = emb / np.linalg.norm(emb, axis=1)[:, np.newaxis]                                       # ddpm.py:297 (numpy, as the reference)
+    return oknn.search(db, qh.astype(np.float32), k)[0]
+
+
+def test_get_nn_and_encoding_on_device(tmp_path, cuda):
+    model, db, _ = _retro_model(tmp_path, cuda)
+    imgs = (torch.rand(3, 3, 32, 32, generator=torch.Generator().manual_seed(2)) * 2 - 1).to(cuda)
+    out = model.get_nn_and_encoding(imgs, k_nn=4)
+    enc = out[model.nn_key]
+    assert enc.shape == (3, 1, 4, 512) and enc.is_cuda
+    nns = _oracle_nns(model, imgs, db, 4)
+    assert np.array_equal(out["nns"].cpu().numpy(), nns)
+    assert np.array_equal(enc.cpu().numpy()[:, 0], db[nns].astype(np.float32))
+    four = model.get_nn_and_encoding(imgs, k_nn=2, n_patches_per_side=2)                        # 2 x 2 patches of 16 x 16
+    assert four[model.nn_key].shape == (3, 4, 2, 512)
+    patches = torch.stack([imgs[..., i * 16:(i + 1) * 16, j * 16:(j + 1) * 16] for i in range(2) for j in range(2)], dim=1).reshape(12, 3, 16, 16)
+    assert np.array_equal(four["nns"].cpu().numpy(), _oracle_nns(model, patches, db, 2))
+
+
+def test_per_step_re_retrieval_sampler(tmp_path, cuda):
+    """DDIMRetroSampler (ddim.py:270-415, BASELINE cfg4): step i is conditioned on the neighbours retrieved from the decoded x0 prediction of
+    step i-1.  Checked (a) step by step: the recorded neighbours are the exact kNN of the CLIP embedding of decode(pred_x0); (b) end to end:
+    the oracle U-Net replaying the trajectory with the recorded contexts reproduces the final latent."""
+    from rdm.models.diffusion.ddim import DDIMRetroSampler
+    model, db, unet = _retro_model(tmp_path, cuda)
+    S, k, scale = 5, 4, 2.0
+    x_T = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(3))
+    torch.manual_seed(77)
+    r0 = torch.randn((2, k, 512), device=cuda)                                                  # the sampler's first draw (ddim.py:299)
+    uc = torch.zeros(2, k, 512, device=cuda)
+    torch.manual_seed(77)
+    with model.ema_scope():
+        img, inter = DDIMRetroSampler(model).sample(S, 2, (4, 16, 16), r_shape=(2, k, 512), x_T=x_T.to(cuda), log_every_t=1, k_nn=k,
+                                                    unconditional_guidance_scale=scale, unconditional_conditioning=[uc], ignore_noising=True, verbose=False)
+    assert len(inter["nns"]) == S and len(inter["pred_x0"]) == S
+    sch = oddim.Schedule(S)
+    x, ctx = x_T, r0.cpu()
+    for i in range(S):
+        step = int(np.flip(sch.timesteps)[i])
+        with torch.no_grad():
+            e = unet(torch.cat([x] * 2), torch.full((4,), step), torch.cat([ctx, torch.zeros_like(ctx)]))
+        x, p0 = oddim.ddim_update(x, e[2:] + scale * (e[:2] - e[2:]), *sch.coeffs(S - i - 1))
+        assert rel_l2(inter["pred_x0"][i], p0) < 2e-3, f"step {i}"
+        px0 = model.decode_first_stage(inter["pred_x0"][i])                                      # deterministic device decode of the device's own prediction
+        nns = _oracle_nns(model, px0, db, k)
+        assert np.array_equal(inter["nns"][i].cpu().numpy(), nns), f"step {i}"
+        ctx = torch.from_numpy(db[nns].astype(np.float32))                                       # conditioning of the NEXT step
+    assert rel_l2(img, x) < 2e-3
