@@ -222,3 +222,31 @@ def test_per_step_re_retrieval_sampler(tmp_path, cuda):
         assert np.array_equal(inter["nns"][i].cpu().numpy(), nns), f"step {i}"
         ctx = torch.from_numpy(db[nns].astype(np.float32))                                       # conditioning of the NEXT step
     assert rel_l2(img, x) < 2e-3
+
+
+def test_offline_neighbour_precompute_writes_the_reference_file_format(tmp_path, cuda):
+    """scripts/search_neighbors.py:381-450 over the device searcher: per-example pickles in the layout QueryDataset.load_nns reads
+    (rdm/data/base.py:925-939), and the neighbour histogram behind nn_memory."""
+    import pickle
+    from rdm_b200.search_neighbors import build_nn_memory, search_nns
+    model, db, _ = _retro_model(tmp_path, cuda)
+    builder = model.retriever
+    builder.train_searcher()
+
+    class Loader(list):
+        batch_size = 3
+    g = torch.Generator().manual_seed(4)
+    batches = Loader({'patches': torch.rand(3, 4, 16, 16, 3, generator=g) * 2 - 1} for _ in range(2))      # 2 x 2 patch grid per example, channel-last
+    (tmp_path / "embeddings").mkdir()
+    paths = search_nns(builder, batches, device=cuda, save=True, npatches_perside=2, base_savedir=str(tmp_path), start_id=100)
+    assert sorted(paths) == list(range(100, 106)) and paths[104] == f"embeddings/{builder.k}_nns-img000000104.p"
+    with open(tmp_path / paths[104], "rb") as f:
+        entry = pickle.load(f)[2]
+    assert entry['nn_ids'].shape == (4, builder.k) and entry['embeddings'].shape == (4, builder.k, 512) and entry['img_ids'].shape == (4, builder.k)
+    q = batches[1]['patches'][1].permute(0, 3, 1, 2).to(cuda)                                          # example 104 = batch 1, item 1
+    assert np.array_equal(entry['nn_ids'], _oracle_nns(model, q, db, builder.k))
+    assert np.array_equal(entry['embeddings'], db[entry['nn_ids']])
+    hist = search_nns(builder, batches, device=cuda, save=False)
+    assert sum(hist.values()) == 2 * 3 * 4 * builder.k
+    mem = build_nn_memory(hist)
+    assert mem['nn_memory'].shape[0] == len(hist) and hist[int(mem['nn_memory'][0])] == max(hist.values())
