@@ -228,7 +228,7 @@ def test_offline_neighbour_precompute_writes_the_reference_file_format(tmp_path,
     """scripts/search_neighbors.py:381-450 over the device searcher: per-example pickles in the layout QueryDataset.load_nns reads
     (rdm/data/base.py:925-939), and the neighbour histogram behind nn_memory."""
     import pickle
-    from rdm_b200.search_neighbors import build_nn_memory, search_nns
+    from rdm_b200.nn_precompute import build_nn_memory, search_nns
     model, db, _ = _retro_model(tmp_path, cuda)
     builder = model.retriever
     builder.train_searcher()
