@@ -221,11 +221,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
         return;
     }
     const bool slow_rv = p.rowvec && p.rows_per_batch < 16;
-    float4 t[8];
-#pragma unroll
-    for (int it = 0; it < 8; it++) t[it] = *reinterpret_cast<const float4*>(epi_at(stage, r0 + 4 * it, cg));
-    TSTAMP_EPI(9);
     if (p.act == ACT_GEGLU) {
+        float4 t[8];
+#pragma unroll
+        for (int it = 0; it < 8; it++) t[it] = *reinterpret_cast<const float4*>(epi_at(stage, r0 + 4 * it, cg));
+        TSTAMP_EPI(9);
         const int no = n >> 1;
 #pragma unroll
         for (int it = 0; it < 8; it++) {
@@ -241,23 +241,42 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
                 }
             }
         }
+    } else if (p.act != ACT_NONE || slow_rv) {
+        // Rare variants (SiLU of the time-embedding MLP, CLIP's QuickGELU, images smaller than 16 pixels): a ROLLED row loop that reads its
+        // operands straight from shared / global memory.  Keeping these ~2000 instructions out of the unrolled loop below shrinks the code the
+        // common layers have to fetch (the kernel starts with a cold instruction cache every launch; ncu: `no_instruction` stalls).
+#pragma unroll 1
+        for (int it = 0; it < 8; it++) {
+            const int mo = m_warp0 + r0 + 4 * it;
+            if (mo >= p.M) continue;
+            float4 o = *reinterpret_cast<const float4*>(epi_at(stage, r0 + 4 * it, cg));
+            const float4 bb = it < 4 ? pre.b[0] : pre.b[1];
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            if (slow_rv) {
+                const float4 rv = __ldg(reinterpret_cast<const float4*>(p.rowvec + (size_t)(mo / p.rows_per_batch) * p.rowvec_ld + n));
+                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+            }
+            if (p.act == ACT_SILU) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+            else if (p.act == ACT_QUICKGELU) {
+                o.x = o.x / (1.f + expf(-1.702f * o.x)); o.y = o.y / (1.f + expf(-1.702f * o.y));
+                o.z = o.z / (1.f + expf(-1.702f * o.z)); o.w = o.w / (1.f + expf(-1.702f * o.w));
+            }
+            if (p.res) { const float4 q = *reinterpret_cast<const float4*>(p.res + (size_t)mo * p.res_ld + n); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+            if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)mo * p.out_ld + n) = o;
+            else store_planes4(p.out_hi + (size_t)mo * p.out_bf_ld + n, p.out_lo ? p.out_lo + (size_t)mo * p.out_bf_ld + n : nullptr, p.f16, o.x, o.y, o.z, o.w);
+        }
     } else {
+        // the common layers: bias (+ time-embedding row) and residual from the prefetched registers, fp32 or 16-bit-plane store
+        float4 t[8];
+#pragma unroll
+        for (int it = 0; it < 8; it++) t[it] = *reinterpret_cast<const float4*>(epi_at(stage, r0 + 4 * it, cg));
+        TSTAMP_EPI(9);
 #pragma unroll
         for (int it = 0; it < 8; it++) {
             const int mo = m_warp0 + r0 + 4 * it;
             if (mo < p.M) {
                 const float4 bb = pre.b[it >> 2];
-                float4 o = make_float4(t[it].x + bb.x, t[it].y + bb.y, t[it].z + bb.z, t[it].w + bb.w);
-                if (slow_rv) {
-                    const float4 rv = __ldg(reinterpret_cast<const float4*>(p.rowvec + (size_t)(mo / p.rows_per_batch) * p.rowvec_ld + n));
-                    o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-                }
-                if (p.act == ACT_SILU) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
-                else if (p.act == ACT_QUICKGELU) {
-                    o.x = o.x / (1.f + expf(-1.702f * o.x)); o.y = o.y / (1.f + expf(-1.702f * o.y));
-                    o.z = o.z / (1.f + expf(-1.702f * o.z)); o.w = o.w / (1.f + expf(-1.702f * o.w));
-                }
-                o.x += pre.r[it].x; o.y += pre.r[it].y; o.z += pre.r[it].z; o.w += pre.r[it].w;
+                const float4 o = make_float4(t[it].x + bb.x + pre.r[it].x, t[it].y + bb.y + pre.r[it].y, t[it].z + bb.z + pre.r[it].z, t[it].w + bb.w + pre.r[it].w);
                 if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)mo * p.out_ld + n) = o;
                 else store_planes4(p.out_hi + (size_t)mo * p.out_bf_ld + n, p.out_lo ? p.out_lo + (size_t)mo * p.out_bf_ld + n : nullptr, p.f16, o.x, o.y, o.z, o.w);
             }
