@@ -98,15 +98,23 @@ __device__ __forceinline__ void epi_prefetch(const TcKernelParams& p, int lane, 
             pre.b[s].x += t.x; pre.b[s].y += t.y; pre.b[s].z += t.z; pre.b[s].w += t.w;
         }
     }
-    const bool geglu = p.act == ACT_GEGLU;
-    const int no = geglu ? (n >> 1) : n;
+    // (branches hoisted out of the unrolled row loops: a skipped block inside an unrolled loop breaks the sequential instruction fetch 8 times)
+    if (!p.res) {
 #pragma unroll
-    for (int it = 0; it < 8; it++) {
-        const int mo = m_warp0 + r0 + 4 * it;
-        pre.r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.res && mo < p.M) {
-            if (geglu) { const float2 t = __ldcs(reinterpret_cast<const float2*>(p.res + (size_t)mo * p.res_ld + no)); pre.r[it].x = t.x; pre.r[it].y = t.y; }
-            else pre.r[it] = __ldcs(reinterpret_cast<const float4*>(p.res + (size_t)mo * p.res_ld + no));
+        for (int it = 0; it < 8; it++) pre.r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (p.act == ACT_GEGLU) {
+        const int no = n >> 1;
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int mo = m_warp0 + r0 + 4 * it;
+            pre.r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mo < p.M) { const float2 t = __ldcs(reinterpret_cast<const float2*>(p.res + (size_t)mo * p.res_ld + no)); pre.r[it].x = t.x; pre.r[it].y = t.y; }
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int mo = m_warp0 + r0 + 4 * it;
+            pre.r[it] = mo < p.M ? __ldcs(reinterpret_cast<const float4*>(p.res + (size_t)mo * p.res_ld + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 }
@@ -273,12 +281,20 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
         TSTAMP_EPI(9);
 #pragma unroll
         for (int it = 0; it < 8; it++) {
-            const int mo = m_warp0 + r0 + 4 * it;
-            if (mo < p.M) {
-                const float4 bb = pre.b[it >> 2];
-                const float4 o = make_float4(t[it].x + bb.x + pre.r[it].x, t[it].y + bb.y + pre.r[it].y, t[it].z + bb.z + pre.r[it].z, t[it].w + bb.w + pre.r[it].w);
-                if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)mo * p.out_ld + n) = o;
-                else store_planes4(p.out_hi + (size_t)mo * p.out_bf_ld + n, p.out_lo ? p.out_lo + (size_t)mo * p.out_bf_ld + n : nullptr, p.f16, o.x, o.y, o.z, o.w);
+            const float4 bb = pre.b[it >> 2];
+            t[it] = make_float4(t[it].x + bb.x + pre.r[it].x, t[it].y + bb.y + pre.r[it].y, t[it].z + bb.z + pre.r[it].z, t[it].w + bb.w + pre.r[it].w);
+        }
+        if (p.out) {
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int mo = m_warp0 + r0 + 4 * it;
+                if (mo < p.M) *reinterpret_cast<float4*>(p.out + (size_t)mo * p.out_ld + n) = t[it];
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int mo = m_warp0 + r0 + 4 * it;
+                if (mo < p.M) store_planes4(p.out_hi + (size_t)mo * p.out_bf_ld + n, p.out_lo ? p.out_lo + (size_t)mo * p.out_bf_ld + n : nullptr, p.f16, t[it].x, t[it].y, t[it].z, t[it].w);
             }
         }
     }
