@@ -1,0 +1,55 @@
+"""CPU: row-range loading of a multi-part .npz database (rdm_b200/db_loader.py; dsetbuilder.py:181-236 layout) -- every range must equal
+the slice of the reference-style full concatenation, shard ranges must tile the database, and only overlapping parts may be opened."""
+import numpy as np
+import pytest
+
+from rdm_b200 import db_loader
+from rdm_b200.knn import shard_range
+
+
+def _make_db(tmp_path, sizes=(5, 1, 7, 3), dtype=np.float16):
+    rng = np.random.default_rng(0)
+    full = {"embedding": [], "img_id": [], "patch_coords": []}
+    start = 0
+    for i, n in enumerate(sizes):
+        part = {"embedding": rng.standard_normal((n, 8)).astype(dtype), "img_id": np.arange(start, start + n), "patch_coords": rng.integers(0, 9, (n, 4)).astype(np.int32)}
+        np.savez(tmp_path / f"part_{i:03d}.npz", **part)
+        for k in full:
+            full[k].append(part[k])
+        start += n
+    return {k: np.concatenate(v) for k, v in full.items()}
+
+
+def test_headers_give_the_row_counts_without_reading_data(tmp_path):
+    _make_db(tmp_path)
+    parts = db_loader.list_parts(str(tmp_path))
+    assert [p.split("/")[-1] for p in parts] == [f"part_{i:03d}.npz" for i in range(4)]
+    assert db_loader.part_row_counts(parts) == [5, 1, 7, 3]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 16])
+def test_shard_ranges_tile_the_database(tmp_path, world):
+    full = _make_db(tmp_path)
+    n = full["embedding"].shape[0]
+    got = []
+    for r in range(world):
+        lo, hi = shard_range(n, r, world)
+        if lo == hi:
+            continue
+        rows = db_loader.load_rows(str(tmp_path), lo, hi)
+        assert rows["n_total"] == n and rows["embedding"].dtype == np.float16
+        for k in ("embedding", "img_id", "patch_coords"):
+            assert np.array_equal(rows[k], full[k][lo:hi]), (k, lo, hi)
+        got.append(rows["img_id"])
+    assert np.array_equal(np.concatenate(got), np.arange(n))
+
+
+def test_only_overlapping_parts_are_opened(tmp_path, monkeypatch):
+    full = _make_db(tmp_path)
+    opened = []
+    real = np.load
+    monkeypatch.setattr(np, "load", lambda p, *a, **k: (opened.append(str(p).split("/")[-1]), real(p, *a, **k))[1])
+    rows = db_loader.load_rows(str(tmp_path), 6, 9)                      # rows 6..8 live in part 2 only (parts hold 0-4, 5, 6-12, 13-15)
+    assert opened == ["part_002.npz"] and np.array_equal(rows["embedding"], full["embedding"][6:9])
+    with pytest.raises(ValueError):
+        db_loader.load_rows(str(tmp_path), 16, 20)
