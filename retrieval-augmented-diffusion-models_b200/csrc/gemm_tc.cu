@@ -83,8 +83,17 @@ struct TcSmem {
 constexpr int EPI_WARP_FLOATS = 32 * 32;            // per-warp staging tile, float4 column groups XOR-swizzled by (row & 7): conflict-free
 __device__ __forceinline__ float* epi_at(float* stage, int row, int col4) { return stage + row * 32 + (((col4 >> 2) ^ (row & 7)) << 2); }
 
+// Epilogue families: the kernel is instantiated once per family so that a launch only carries (and fetches) the epilogue code it can run.
+//   EPI_PLAIN  no activation, bias / time-embedding row (images >= 16 pixels) / residual, full 32-column chunks   -- most layers
+//   EPI_GEGLU  ff.net.0 of the SpatialTransformers        EPI_XATTN  to_q with the fused cross-attention
+//   EPI_ANY    everything (SiLU, QuickGELU, ragged N, tiny images); also the reference point for the other three
+enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_XATTN = 2, EPI_ANY = 3 };
+template <int EPI> __device__ __forceinline__ bool epi_is_geglu(const TcKernelParams& p) { return EPI == EPI_ANY ? p.act == ACT_GEGLU : EPI == EPI_GEGLU; }
+template <int EPI> __device__ __forceinline__ bool epi_is_xattn(const TcKernelParams& p) { return EPI == EPI_ANY ? p.act == ACT_XATTN : EPI == EPI_XATTN; }
+
 struct EpiPre { float4 b[2]; float4 r[8]; };        // bias (+ row vector) for rows 0..15 / 16..31 of the warp; residual per row
 
+template <int EPI>
 __device__ __forceinline__ void epi_prefetch(const TcKernelParams& p, int lane, int m_warp0, int nb, EpiPre& pre) {
     const int cg = (lane & 7) * 4, r0 = lane >> 3, n = nb + cg;
     float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -102,7 +111,7 @@ __device__ __forceinline__ void epi_prefetch(const TcKernelParams& p, int lane, 
     if (!p.res) {
 #pragma unroll
         for (int it = 0; it < 8; it++) pre.r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else if (p.act == ACT_GEGLU) {
+    } else if (epi_is_geglu<EPI>(p)) {
         const int no = n >> 1;
 #pragma unroll
         for (int it = 0; it < 8; it++) {
@@ -192,13 +201,14 @@ __device__ __forceinline__ void epilogue_xattn(const TcKernelParams& p, float (&
 
 // r: this lane's 32 accumulators (row m_warp0 + lane, columns nb..nb+31, nb + 32 <= N); stage: this warp's smem tile; pre: operands of THIS
 // chunk (epi_prefetch).  nb_next >= 0: prefetch the operands of that chunk (same rows) into `pre` once this chunk has consumed them.
+template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const uint32_t (&r)[32], float* stage, int lane, int m_warp0, int nb, EpiPre& pre, int nb_next, float* part) {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
     TSTAMP_EPI(8);
     const int cg = (lane & 7) * 4, r0 = lane >> 3, n = nb + cg;
-    if (p.act == ACT_XATTN && !part) {             // no bias / residual operands on this path (checked on the host): `pre` is dead here
+    if (epi_is_xattn<EPI>(p) && !part) {           // no bias / residual operands on this path (checked on the host): `pre` is dead here
         epilogue_xattn(p, v, stage, lane, m_warp0, nb);
         __syncwarp();
 #pragma unroll
@@ -228,8 +238,8 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
         }
         return;
     }
-    const bool slow_rv = p.rowvec && p.rows_per_batch < 16;
-    if (p.act == ACT_GEGLU) {
+    const bool slow_rv = EPI == EPI_ANY && p.rowvec && p.rows_per_batch < 16;
+    if (epi_is_geglu<EPI>(p)) {
         float4 t[8];
 #pragma unroll
         for (int it = 0; it < 8; it++) t[it] = *reinterpret_cast<const float4*>(epi_at(stage, r0 + 4 * it, cg));
@@ -249,7 +259,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
                 }
             }
         }
-    } else if (p.act != ACT_NONE || slow_rv) {
+    } else if (EPI == EPI_ANY && (p.act != ACT_NONE || slow_rv)) {
         // Rare variants (SiLU of the time-embedding MLP, CLIP's QuickGELU, images smaller than 16 pixels): a ROLLED row loop that reads its
         // operands straight from shared / global memory.  Keeping these ~2000 instructions out of the unrolled loop below shrinks the code the
         // common layers have to fetch (the kernel starts with a cold instruction cache every launch; ncu: `no_instruction` stalls).
@@ -299,7 +309,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
         }
     }
     TSTAMP_EPI(10);
-    if (nb_next >= 0) epi_prefetch(p, lane, m_warp0, nb_next, pre);
+    if (nb_next >= 0) epi_prefetch<EPI>(p, lane, m_warp0, nb_next, pre);
     TSTAMP_EPI(11);
 }
 
@@ -348,7 +358,7 @@ __global__ void splitk_reduce_kernel(const TcKernelParams p) {
 
 // Persistent: grid = min(#tiles, #SMs); CTA c handles tiles c, c+grid, ...; tile -> (mt, nt) with nt fastest so
 // co-scheduled CTAs share the A tile in L2.  TMEM holds TWO accumulators: the epilogue of tile i overlaps the MMAs of i+1.
-template <int BN, int NSPLIT, int STAGES>
+template <int BN, int NSPLIT, int STAGES, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcKernelParams p) {
@@ -507,7 +517,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const int mt = tile / ntn, n0 = (tile % ntn) * BN;
             const int m_warp0 = mt * BM + q * 32;
             EpiPre pre;
-            if (!part && m_warp0 < p.M && n0 + half * 32 + 32 <= p.N) epi_prefetch(p, lane, m_warp0, n0 + half * 32, pre);      // overlaps the mainloop
+            if (!part && m_warp0 < p.M && n0 + half * 32 + 32 <= p.N) epi_prefetch<EPI>(p, lane, m_warp0, n0 + half * 32, pre);      // overlaps the mainloop
             mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
             tc_fence_after();
 #ifdef RDM_AB_TIMING
@@ -522,8 +532,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 tmem_ld32(taddr, r);
                 if (nb + 32 <= p.N) {
                     const int nbn = nb + 64;                       // this warp's next chunk of the tile
-                    epilogue_chunk(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb, pre, (c + 2 < BN / 32 && nbn + 32 <= p.N) ? nbn : -1, part);
-                } else epilogue_ragged(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0 + lane, nb);     // (split-K needs N % 4 == 0 ... never a partial tile here)
+                    epilogue_chunk<EPI>(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb, pre, (c + 2 < BN / 32 && nbn + 32 <= p.N) ? nbn : -1, part);
+                } else if (EPI == EPI_ANY) epilogue_ragged(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0 + lane, nb);     // (split-K needs N % 4 == 0 ... never a partial tile here)
             }
             tc_fence_before();
             __syncwarp();
@@ -611,9 +621,9 @@ int make_map_2d(CUtensorMap* tm, const void* base, int K, int rows, int ld, int 
     return RDM_OK;
 }
 
-template <int BN, int NSPLIT, int STAGES>
+template <int BN, int NSPLIT, int STAGES, int EPI>
 int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcKernelParams& p, cudaStream_t st, int* cluster_cap) {
-    auto kern = gemm_tc_kernel<BN, NSPLIT, STAGES>;
+    auto kern = gemm_tc_kernel<BN, NSPLIT, STAGES, EPI>;
     constexpr int smem = TcSmem<BN, NSPLIT, STAGES>::TOTAL;
     static bool configured[16] = {false};
     int dev = 0; cudaGetDevice(&dev);
@@ -654,24 +664,39 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     return RDM_OK;
 }
 
-// dispatch on (tile width, MMAs per product); cluster_cap != nullptr: capacity query only (see launch_tc)
+// dispatch on (tile width, MMAs per product, epilogue family); cluster_cap != nullptr: capacity query only (see launch_tc)
+template <int EPI>
+int dispatch_tc_epi(int BN, int nsplit, const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
+                    const TcKernelParams& p, cudaStream_t st, int* cluster_cap) {
+    if (nsplit == 2) {
+        if (BN == 192) return launch_tc<192, 2, 3, EPI>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+        if (BN == 128) return launch_tc<128, 2, 4, EPI>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+        if (BN == 64) return launch_tc<64, 2, 6, EPI>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+        return launch_tc<32, 2, 8, EPI>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    } else if (nsplit == 3) {
+        if (BN == 192) return launch_tc<192, 3, 2, EPI>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+        if (BN == 128) return launch_tc<128, 3, 3, EPI>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+        if (BN == 64) return launch_tc<64, 3, 4, EPI>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+        return launch_tc<32, 3, 4, EPI>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    }
+    if (BN == 192) return launch_tc<192, 1, 4, EPI>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    if (BN == 128) return launch_tc<128, 1, 6, EPI>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    if (BN == 64) return launch_tc<64, 1, 8, EPI>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    return launch_tc<32, 1, 8, EPI>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+}
 int dispatch_tc(int BN, int nsplit, const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
                 const TcKernelParams& p, cudaStream_t st, int* cluster_cap) {
-    if (nsplit == 2) {
-        if (BN == 192) return launch_tc<192, 2, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
-        if (BN == 128) return launch_tc<128, 2, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
-        if (BN == 64) return launch_tc<64, 2, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
-        return launch_tc<32, 2, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
-    } else if (nsplit == 3) {
-        if (BN == 192) return launch_tc<192, 3, 2>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
-        if (BN == 128) return launch_tc<128, 3, 3>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
-        if (BN == 64) return launch_tc<64, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
-        return launch_tc<32, 3, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    static const int one_family = getenv("RDM_TC_ONE_EPI") ? 1 : 0;              // A/B: always the all-in-one kernel
+    int epi = EPI_ANY;
+    if (!one_family) {
+        if (p.act == ACT_XATTN) epi = EPI_XATTN;
+        else if (p.act == ACT_GEGLU && (p.N & 31) == 0) epi = EPI_GEGLU;
+        else if (p.act == ACT_NONE && (p.N & 31) == 0 && !(p.rowvec && p.rows_per_batch < 16)) epi = EPI_PLAIN;
     }
-    if (BN == 192) return launch_tc<192, 1, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
-    if (BN == 128) return launch_tc<128, 1, 6>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
-    if (BN == 64) return launch_tc<64, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
-    return launch_tc<32, 1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    if (epi == EPI_PLAIN) return dispatch_tc_epi<EPI_PLAIN>(BN, nsplit, ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    if (epi == EPI_GEGLU) return dispatch_tc_epi<EPI_GEGLU>(BN, nsplit, ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    if (epi == EPI_XATTN) return dispatch_tc_epi<EPI_XATTN>(BN, nsplit, ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
+    return dispatch_tc_epi<EPI_ANY>(BN, nsplit, ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
 }
 
 }  // namespace
