@@ -67,23 +67,24 @@ def ddim_update(x, e_t, a_t, a_prev, sigma, s1m, noise=None, temperature=1.0):
 
 
 @torch.no_grad()
-def ddim_sample(unet, x_T, cond, uncond=None, S=100, scale=1.0, eta=0.0, schedule=None, return_all=False):
+def ddim_sample(unet, x_T, cond, uncond=None, S=100, scale=1.0, eta=0.0, schedule=None, return_all=False, draw_noise_always=False):
     """ddim.py:143-215 + :218-268: eps-model = ``unet(x, t, context)``; CFG by batch doubling
-    with the *conditional half first* (``cat([c, uc])``, ddim.py:232-238)."""
+    with the *conditional half first* (``cat([c, uc])``, ddim.py:232-238).  ``draw_noise_always`` consumes the global torch RNG
+    like the reference does -- one ``randn(x.shape)`` per step BEFORE the model call, even when sigma = 0 (ddim.py:226-227)."""
     sch = schedule or Schedule(S, eta)
     x, b = x_T.clone(), x_T.shape[0]
     traj = []
     for i, step in enumerate(np.flip(sch.timesteps)):
         index = len(sch.timesteps) - i - 1
         ts = torch.full((b,), int(step), dtype=torch.long)
+        noise = torch.randn(x.shape) if (eta > 0 or draw_noise_always) else None
         if scale > 1.0:
             out = unet(torch.cat([x] * 2), torch.cat([ts] * 2), torch.cat([cond, uncond]))
             e_c, e_u = out[:b], out[b:]
             e_t = e_u + scale * (e_c - e_u)
         else:
             e_t = unet(x, ts, cond)
-        noise = torch.randn(x.shape) if eta > 0 else None
-        x, pred_x0 = ddim_update(x, e_t, *sch.coeffs(index), noise=noise)
+        x, pred_x0 = ddim_update(x, e_t, *sch.coeffs(index), noise=noise if eta > 0 else None)
         if return_all:
             traj.append((x.clone(), pred_x0.clone()))
     return (x, traj) if return_all else x

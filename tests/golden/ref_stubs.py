@@ -1,0 +1,228 @@
+"""Stand-ins for the packages the REFERENCE imports but does not vendor, so that its own hot-path modules can be imported and
+run on CPU in the build container (used ONLY by tests/golden/make_golden_ref.py; never on the GPU box, never by the product).
+
+The reference's `rdm/modules/attention.py`, `rdm/modules/diffusionmodules/openaimodel.py` and `rdm/models/diffusion/ddim.py`
+import `ldm` (latent-diffusion@main, un-pinned git dependency, `environment.yaml:38`), `kornia` and `main`.  What they need from
+there is restated below from the published latent-diffusion sources with ldm's signatures: these few
+functions are third-party arithmetic, everything else executed by the generator is the reference's own code, unmodified, from
+/root/reference.  Kept independent of `oracle/` on purpose, so the fixtures check the oracle rather than echo it.
+"""
+import importlib
+import inspect
+import math
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+# ---- ldm.util ----------------------------------------------------------------------------------------------
+def exists(x):
+    return x is not None
+
+
+def default(val, d):
+    if exists(val):
+        return val
+    return d() if inspect.isfunction(d) else d
+
+
+def instantiate_from_config(config):
+    module, cls = config["target"].rsplit(".", 1)
+    return getattr(importlib.import_module(module), cls)(**config.get("params", dict()))
+
+
+# ---- ldm.modules.diffusionmodules.util ---------------------------------------------------------------------
+def checkpoint(func, inputs, params, flag):
+    return func(*inputs)            # gradient checkpointing is a training-memory device; the forward value is func(*inputs)
+
+
+def conv_nd(dims, *args, **kwargs):
+    return {1: nn.Conv1d, 2: nn.Conv2d, 3: nn.Conv3d}[dims](*args, **kwargs)
+
+
+def linear(*args, **kwargs):
+    return nn.Linear(*args, **kwargs)
+
+
+def avg_pool_nd(dims, *args, **kwargs):
+    return {1: nn.AvgPool1d, 2: nn.AvgPool2d, 3: nn.AvgPool3d}[dims](*args, **kwargs)
+
+
+def zero_module(module):
+    for p in module.parameters():
+        p.detach().zero_()
+    return module
+
+
+class GroupNorm32(nn.GroupNorm):
+    def forward(self, x):
+        return super().forward(x.float()).type(x.dtype)
+
+
+def normalization(channels):
+    return GroupNorm32(32, channels)
+
+
+def timestep_embedding(timesteps, dim, max_period=10000, repeat_only=False):
+    assert not repeat_only
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(device=timesteps.device)
+    args = timesteps[:, None].float() * freqs[None]
+    embedding = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        embedding = torch.cat([embedding, torch.zeros_like(embedding[:, :1])], dim=-1)
+    return embedding
+
+
+def make_ddim_timesteps(ddim_discr_method, num_ddim_timesteps, num_ddpm_timesteps, verbose=True):
+    assert ddim_discr_method == "uniform"
+    c = num_ddpm_timesteps // num_ddim_timesteps
+    ddim_timesteps = np.asarray(list(range(0, num_ddpm_timesteps, c)))
+    return ddim_timesteps + 1        # "add one to get the final alpha values right (the ones from first scale to data during sampling)"
+
+
+def make_ddim_sampling_parameters(alphacums, ddim_timesteps, eta, verbose=True):
+    alphas = alphacums[ddim_timesteps]
+    alphas_prev = np.asarray([alphacums[0]] + alphacums[ddim_timesteps[:-1]].tolist())
+    sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
+    return sigmas, alphas, alphas_prev
+
+
+def noise_like(shape, device, repeat=False):
+    assert not repeat
+    return torch.randn(shape, device=device)
+
+
+def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):
+    assert schedule == "linear"
+    betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64) ** 2
+    return betas.numpy()
+
+
+# ---- ldm.modules.attention ---------------------------------------------------------------------------------
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        x, gate = self.proj(x).chunk(2, dim=-1)
+        return x * F.gelu(gate)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, dim_out=None, mult=4, glu=False, dropout=0.):
+        super().__init__()
+        inner_dim = int(dim * mult)
+        dim_out = default(dim_out, dim)
+        project_in = nn.Sequential(nn.Linear(dim, inner_dim), nn.GELU()) if not glu else GEGLU(dim, inner_dim)
+        self.net = nn.Sequential(project_in, nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+# ---- ldm.modules.diffusionmodules.openaimodel --------------------------------------------------------------
+class TimestepBlock(nn.Module):
+    def forward(self, x, emb):
+        raise NotImplementedError
+
+
+class Upsample(nn.Module):
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        self.channels, self.out_channels, self.use_conv, self.dims = channels, out_channels or channels, use_conv, dims
+        if use_conv:
+            self.conv = conv_nd(dims, self.channels, self.out_channels, 3, padding=padding)
+
+    def forward(self, x):
+        assert x.shape[1] == self.channels
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        if self.use_conv:
+            x = self.conv(x)
+        return x
+
+
+class Downsample(nn.Module):
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        self.channels, self.out_channels, self.use_conv, self.dims = channels, out_channels or channels, use_conv, dims
+        stride = 2 if dims != 3 else (1, 2, 2)
+        if use_conv:
+            self.op = conv_nd(dims, self.channels, self.out_channels, 3, stride=stride, padding=padding)
+        else:
+            assert self.channels == self.out_channels
+            self.op = avg_pool_nd(dims, kernel_size=stride, stride=stride)
+
+    def forward(self, x):
+        assert x.shape[1] == self.channels
+        return self.op(x)
+
+
+class ResBlock(TimestepBlock):
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False, use_scale_shift_norm=False, dims=2,
+                 use_checkpoint=False, up=False, down=False):
+        super().__init__()
+        assert not (use_scale_shift_norm or up or down), "the shipped configs use plain ResBlocks"
+        self.channels, self.emb_channels, self.dropout = channels, emb_channels, dropout
+        self.out_channels = out_channels or channels
+        self.in_layers = nn.Sequential(normalization(channels), nn.SiLU(), conv_nd(dims, channels, self.out_channels, 3, padding=1))
+        self.emb_layers = nn.Sequential(nn.SiLU(), linear(emb_channels, self.out_channels))
+        self.out_layers = nn.Sequential(normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        zero_module(conv_nd(dims, self.out_channels, self.out_channels, 3, padding=1)))
+        if self.out_channels == channels:
+            self.skip_connection = nn.Identity()
+        elif use_conv:
+            self.skip_connection = conv_nd(dims, channels, self.out_channels, 3, padding=1)
+        else:
+            self.skip_connection = conv_nd(dims, channels, self.out_channels, 1)
+
+    def forward(self, x, emb):
+        h = self.in_layers(x)
+        emb_out = self.emb_layers(emb).type(h.dtype)
+        while len(emb_out.shape) < len(h.shape):
+            emb_out = emb_out[..., None]
+        h = h + emb_out
+        h = self.out_layers(h)
+        return self.skip_connection(x) + h
+
+
+class AttentionBlock(nn.Module):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("the shipped configs set use_spatial_transformer=True")
+
+
+def install(reference_root="/root/reference"):
+    """Registers the stand-ins in sys.modules and puts the reference checkout first on sys.path."""
+    me = sys.modules[__name__]
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        m.__path__ = []
+        sys.modules[name] = m
+        return m
+
+    pick = lambda *names: {n: getattr(me, n) for n in names}
+    mod("ldm")
+    mod("ldm.util", **pick("exists", "default", "instantiate_from_config"), log_txt_as_img=None, isimage=None, ismap=None)
+    mod("ldm.modules")
+    mod("ldm.modules.attention", **pick("FeedForward", "GEGLU", "zero_module"))
+    mod("ldm.modules.diffusionmodules")
+    mod("ldm.modules.diffusionmodules.util", **pick("checkpoint", "conv_nd", "linear", "avg_pool_nd", "zero_module", "normalization",
+                                                    "timestep_embedding", "make_ddim_timesteps", "make_ddim_sampling_parameters",
+                                                    "noise_like", "make_beta_schedule"))
+    mod("ldm.modules.diffusionmodules.openaimodel", **pick("TimestepBlock", "ResBlock", "Downsample", "Upsample", "AttentionBlock"))
+    mod("main", **pick("instantiate_from_config"))
+    mod("kornia")
+    mod("omegaconf")
+    mod("omegaconf.listconfig", ListConfig=type("ListConfig", (list,), {}))      # openaimodel.py:102 only type-checks against it
+    for k in [k for k in sys.modules if k == "rdm" or k.startswith("rdm.")]:       # never mix with the repo's own mirror package
+        del sys.modules[k]
+    if reference_root in sys.path:
+        sys.path.remove(reference_root)
+    sys.path.insert(0, reference_root)
