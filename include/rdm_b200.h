@@ -213,6 +213,52 @@ RDM_API int rdm_clip_encode_image(rdm_clip_t* h, const float* image_dev, int32_t
 RDM_API int rdm_clip_preprocess(const float* image_dev, int32_t B, int32_t H, int32_t W, int32_t size, float* out_dev,
                         int32_t device, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * RARM decoder: rdm/modules/attention.py:199-272 (RetrievalPatchTransformer with `continuous: false`,
+ * positional encodings, causal self-attention + cross-attention to the retrieved CLIP vectors, GEGLU feed-forward, Conv1d head;
+ * models/rarm/imagenet/dogs/config.yaml:14-27) evaluated with per-layer key/value caches, and the sampling loop
+ * rdm/models/autoregression/transformer.py:224-270 (LatentImageRETRO.sample; call sites :279-294, scripts/rarm_sample.py:253-266).
+ * The struct mirrors `transformer_config.params`; parameter names are the reference state-dict keys below `transformer.`
+ * ("proj_in.weight", "positional_encoding", "transformer_blocks.3.attn2.to_k.weight", "proj_out.weight" [out, C, 1], ...).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct rdm_rarm rdm_rarm_t;
+typedef struct rdm_rarm_cfg {
+    int32_t in_channels;        /* input vocabulary (16386 = codebook + mask + sos) */
+    int32_t n_heads, d_head;    /* d_head must be 64 */
+    int32_t depth, context_dim, sequence_length;
+    int32_t out_channels;       /* output vocabulary (16384) */
+} rdm_rarm_cfg;
+RDM_API int rdm_rarm_create(rdm_rarm_t** out, const rdm_rarm_cfg* cfg, int32_t device);
+RDM_API void rdm_rarm_destroy(rdm_rarm_t* h);
+RDM_API int64_t rdm_rarm_num_params(const rdm_rarm_t* h);
+RDM_API const char* rdm_rarm_param_name(const rdm_rarm_t* h, int64_t i);
+RDM_API int64_t rdm_rarm_param_numel(const rdm_rarm_t* h, const char* name);
+RDM_API int rdm_rarm_load(rdm_rarm_t* h, const char* name, const float* host, int64_t numel);   /* host float32, reference layout */
+RDM_API int64_t rdm_rarm_missing(const rdm_rarm_t* h);
+/* RDM_UNET_MODE_FP32: fp32 weights (strict parity);  RDM_UNET_MODE_TC_FP16 (default): fp16 weights, fp32 accumulation. */
+RDM_API int rdm_rarm_set_mode(rdm_rarm_t* h, int32_t mode);
+RDM_API int rdm_rarm_set_graph(rdm_rarm_t* h, int32_t on);
+/* Retrieval context r: float32 [B2, k, context_dim] (device); under guidance B2 = 2B rows [r | zeros] (transformer.py:233-236).
+ * Projects the step-invariant cross-attention keys/values of every layer once and restarts the sequences (empty caches). */
+RDM_API int rdm_rarm_set_context(rdm_rarm_t* h, const float* ctx_dev, int32_t B2, int32_t k, void* stream);
+/* `transformer(x, context=r)[:, pos]` for the token at position `pos` of every sequence, given that positions 0..pos-1 were fed
+ * before (in order, since the last rdm_rarm_set_context): tokens_dev int64 [B] with B == B2 or B == B2/2 (guidance doubling:
+ * row b + B reuses token b) -> logits_out_dev float32 [B2, out_channels]. */
+RDM_API int rdm_rarm_forward_token(rdm_rarm_t* h, const int64_t* tokens_dev, int32_t B, int32_t pos, float* logits_out_dev, void* stream);
+/* transformer.py:249-266 on given last-position logits [B or 2B, V] ([cond | uncond] when guided != 0; V <= 40960):
+ * logits = (l_u + scale*(l_c - l_u)) / temperature -> top-k filter (top_k <= 0: none) -> softmax -> one token per sequence.
+ * uniforms_dev float32 [B] in [0,1): token = first index whose cumulative probability exceeds u (the device-side definition of
+ * torch.multinomial(probs, 1)); NULL: argmax (`sample=False`).  probs_out_dev (optional) float32 [B, V]. */
+RDM_API int rdm_rarm_sample_step(rdm_rarm_t* h, const float* logits_dev, int32_t B, int32_t V, int32_t guided, float guidance_scale, float temperature,
+                         int32_t top_k, const float* uniforms_dev, int64_t* token_out_dev, float* probs_out_dev, void* stream);
+/* LatentImageRETRO.sample: tokens_dev int64 [B, n_prefix + steps]; columns [0, n_prefix) hold cat(c, x) (the sos token and any
+ * start tokens, transformer.py:232), columns [n_prefix, n_prefix + steps) receive the sampled ids.  uniforms_dev float32
+ * [steps, B] (NULL: greedy).  The context must have been set with B2 = B (guidance_scale <= 1) or 2B rows.  One CUDA graph
+ * {embed, layers, head, guided top-k draw, position++} is captured once and replayed per position; no host synchronisation. */
+RDM_API int rdm_rarm_sample(rdm_rarm_t* h, int64_t* tokens_dev, int32_t B, int32_t n_prefix, int32_t steps, float temperature, int32_t top_k,
+                    float guidance_scale, const float* uniforms_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,6 @@ int rdm_num_sms(int device) {
 
 extern "C" {
 const char* rdm_last_error(void) { return t_err; }
-int rdm_abi_version(void) { return 1; }
+int rdm_abi_version(void) { return 2; }
 unsigned long long rdm_launch_count(void) { return g_rdm_launches; }
 }

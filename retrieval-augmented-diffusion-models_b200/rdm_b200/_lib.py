@@ -57,6 +57,19 @@ SIGNATURES = {
     "rdm_clip_encode_text": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "rdm_clip_encode_image": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "rdm_clip_preprocess": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "rdm_rarm_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int32]),
+    "rdm_rarm_destroy": (None, [c_void_p]),
+    "rdm_rarm_num_params": (c_int64, [c_void_p]),
+    "rdm_rarm_param_name": (c_char_p, [c_void_p, c_int64]),
+    "rdm_rarm_param_numel": (c_int64, [c_void_p, c_char_p]),
+    "rdm_rarm_load": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "rdm_rarm_missing": (c_int64, [c_void_p]),
+    "rdm_rarm_set_mode": (c_int, [c_void_p, c_int32]),
+    "rdm_rarm_set_graph": (c_int, [c_void_p, c_int32]),
+    "rdm_rarm_set_context": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "rdm_rarm_forward_token": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "rdm_rarm_sample_step": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rdm_rarm_sample": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_int32, c_float, c_void_p, c_void_p]),
     "rdm_ddim_step": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
 }
 

@@ -32,7 +32,7 @@ import ref_weights  # noqa: E402
 UNET_CFG = dict(image_size=16, in_channels=4, out_channels=4, model_channels=64, attention_resolutions=[2, 4], num_res_blocks=1,
                 channel_mult=[1, 2, 3], num_head_channels=32, use_spatial_transformer=True, transformer_depth=1, context_dim=512)
 # = oracle.unet.TINY_UNET (every layer kind, non-aligned concat GroupNorm groups) + the reference's use_spatial_transformer switch
-RARM_CFG = dict(in_channels=50, n_heads=2, d_head=64, depth=2, context_dim=32, positional_encodings=True, sequence_length=12,
+RARM_CFG = dict(in_channels=50, n_heads=2, d_head=64, depth=2, context_dim=128, positional_encodings=True, sequence_length=12,
                 out_channels=48, cross_attend=True, causal=True, continuous=False)
 
 
@@ -107,7 +107,7 @@ def rarm():
     g = torch.Generator().manual_seed(22)
     tok = torch.randint(0, 50, (3, 12), generator=g)
     tok[:, 0] = 49                                                             # sos id = last vocabulary entry (config.yaml: sos_token 16385 of 16386)
-    ctx = torch.randn(3, 4, 32, generator=g)
+    ctx = torch.randn(3, 4, 128, generator=g)
     with torch.no_grad():
         logits = net(tok, context=ctx)
         logits_short = net(tok[:, :5], context=ctx)                            # a prefix: what step 4 of the sampling loop evaluates

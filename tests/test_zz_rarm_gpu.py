@@ -1,0 +1,141 @@
+"""GPU parity of the RARM decoder (csrc/rarm.cu) through the C ABI: key/value-cached logits vs logits of the REFERENCE's own
+RetrievalPatchTransformer (tests/golden/ref_rarm_small.npz) and vs the pinned oracle at the ImageNet model size; the fused
+guidance / top-k / draw kernel vs the oracle's restatement of transformer.py:249-266; the graph-replayed sampling loop token by token.
+Tolerances: 1e-4 rel-L2 on logits with fp32 weights, 5e-3 with fp16 weights; a drawn token must be the inverse-CDF pick of its
+uniform up to 1e-4 of probability mass (index-exact away from CDF boundaries).  (File name: runs after the U-Net / kNN suites.)"""
+import ast
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import rarm as orarm
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, GOLD)
+import ref_weights  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), torch.as_tensor(b).double()
+    return float((a - b).norm() / b.norm())
+
+
+def small(cuda, mode):
+    from rdm_b200.rarm import B200Rarm
+    d = np.load(os.path.join(GOLD, "ref_rarm_small.npz"))
+    cfg = ast.literal_eval(str(d["cfg_json"]))
+    net = B200Rarm(cuda, **cfg)
+    assert list(net.shapes) == [str(k) for k in d["sd_keys"]]
+    sd = ref_weights.state_dict_for(net.shapes.items(), int(d["weight_seed"]))
+    net.load_state_dict(sd)
+    assert net.missing() == 0
+    net.set_mode(mode)
+    return d, cfg, sd, net
+
+
+def consistent_with_uniform(probs, token, u, tol=1e-4):
+    """token is the inverse-CDF pick for u under `probs` (float64 CDF), allowing `tol` of probability mass at the boundaries."""
+    cdf = probs.double().cumsum(-1)
+    cdf = cdf / cdf[-1]
+    lo = float(cdf[token - 1]) if token > 0 else 0.0
+    return float(probs[token]) > 0 and lo - tol <= u <= float(cdf[token]) + tol
+
+
+@pytest.mark.parametrize("mode,tol", [(0, 1e-4), (4, 5e-3)])
+def test_cached_logits_match_reference_code(cuda, mode, tol):
+    d, cfg, sd, net = small(cuda, mode)
+    tok, ctx = torch.from_numpy(d["tokens"]), torch.from_numpy(d["context"])
+    got = net.forward(tok, ctx)
+    assert rel(got, d["logits"]) < tol
+    assert rel(got[:, :5], d["logits_prefix5"]) < tol                       # causality: the cache never leaks later positions
+    # guidance doubling (transformer.py:233-248): B tokens against 2B context rows [r | zeros]
+    net.set_context(torch.cat([ctx, torch.zeros_like(ctx)]))
+    both = torch.stack([net.forward_token(tok[:, t], t) for t in range(tok.shape[1])], 1)
+    assert rel(both[:3], d["logits"]) < tol and rel(both[3:], d["logits_uncond"]) < tol
+
+
+@pytest.mark.parametrize("V,top_k,guided", [(16384, 256, True), (16384, 256, False), (48, 5, True), (1000, None, False), (16384, 1, True)])
+def test_guided_topk_draw_kernel_matches_oracle(cuda, V, top_k, guided):
+    _, _, _, net = small(cuda, 0)
+    g = torch.Generator().manual_seed(V + (top_k or 0))
+    B = 4
+    lc, lu = torch.randn(B, V, generator=g) * 3, torch.randn(B, V, generator=g) * 3
+    lc[0, 7] = lc[0, 9]                                                       # a tie inside the candidates
+    scale, temp = (2.5, 0.8) if guided else (1.0, 1.3)
+    u = torch.rand(B, generator=g)
+    logits = torch.cat([lc, lu]) if guided else lc
+    tok, probs = net.sample_step(logits, guidance_scale=scale, temperature=temp, top_k=top_k, uniforms=u, want_probs=True)
+    want = orarm.step_probs(lc, lu if guided else None, scale, temp, top_k)
+    assert torch.equal(probs.cpu() > 0, want > 0)                             # the same candidate set (ties at the k-th value kept)
+    assert float((probs.cpu() - want).abs().max()) < 1e-6
+    for b in range(B):
+        assert consistent_with_uniform(want[b], int(tok[b]), float(u[b]), 1e-5)
+    greedy, _ = net.sample_step(logits, guidance_scale=scale, temperature=temp, top_k=top_k, uniforms=None)
+    assert torch.equal(greedy.cpu(), want.argmax(-1))
+
+
+@pytest.mark.parametrize("mode", [0, 4])
+@pytest.mark.parametrize("scale", [1.0, 2.0])
+def test_sampling_loop_token_by_token(cuda, mode, scale):
+    d, cfg, sd, net = small(cuda, mode)
+    ctx = torch.from_numpy(d["context"])
+    B, steps, top_k, temp = 3, 11, 6, 0.9
+    c = torch.full((B, 1), cfg["in_channels"] - 1)
+    g = torch.Generator().manual_seed(5)
+    u = torch.rand(steps, B, generator=g)
+    r = torch.cat([ctx, torch.zeros_like(ctx)]) if scale > 1.0 else ctx
+    net.set_context(r)
+    toks = net.sample(c, steps, temperature=temp, top_k=top_k, guidance_scale=scale, uniforms=u).cpu()
+    assert toks.shape == (B, 1 + steps) and torch.equal(toks[:, :1], c) and int(toks[:, 1:].max()) < cfg["out_channels"]
+    net.set_graph(False)                                                      # eager launches give the same tokens as the graph replay
+    net.set_context(r)
+    assert torch.equal(net.sample(c, steps, temperature=temp, top_k=top_k, guidance_scale=scale, uniforms=u).cpu(), toks)
+    net.set_graph(True)
+    # teacher-forced check against the oracle: every drawn token is the inverse-CDF pick of its uniform under the ORACLE's probabilities
+    lc = orarm.forward(sd, toks[:, :-1], ctx, cfg["n_heads"])
+    lu = orarm.forward(sd, toks[:, :-1], torch.zeros_like(ctx), cfg["n_heads"]) if scale > 1.0 else None
+    tol = 1e-4 if mode == 0 else 2e-2
+    for t in range(steps):
+        p = orarm.step_probs(lc[:, t], None if lu is None else lu[:, t], scale, temp, top_k)
+        for b in range(B):
+            assert consistent_with_uniform(p[b], int(toks[b, t + 1]), float(u[t, b]), tol), (t, b)
+    # a start prefix (half-sampling, transformer.py:452-457): given tokens are kept, the rest continues from them
+    net.set_context(r)
+    cont = net.sample(toks[:, :5], steps - 4, temperature=temp, top_k=top_k, guidance_scale=scale, uniforms=u[4:]).cpu()
+    assert torch.equal(cont, toks)
+    # greedy decoding == argmax of the oracle's probabilities at every position (fp32 weights)
+    if mode == 0:
+        net.set_context(r)
+        gr = net.sample(c, 6, temperature=1.0, top_k=None, guidance_scale=scale, uniforms=None).cpu()
+        want, _ = orarm.sample(sd, cfg["n_heads"], c, torch.zeros((B, 0), dtype=torch.long), ctx, 6, guidance_scale=scale)
+        assert torch.equal(gr[:, 1:], want)
+
+
+def test_imagenet_size_decoder_against_oracle(cuda):
+    """models/rarm/imagenet/*/config.yaml: 18 x (12 x 64), vocabulary 16386 -> 16384, k = 4 CLIP neighbours; 230.9 M parameters."""
+    from rdm_b200.rarm import RARM_IMAGENET, B200Rarm
+    net = B200Rarm(cuda, **RARM_IMAGENET)
+    sd = ref_weights.state_dict_for(net.shapes.items(), 31)
+    net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(6)
+    tok = torch.randint(0, 16384, (2, 4), generator=g)
+    tok[:, 0] = 16385
+    ctx = torch.randn(2, 4, 512, generator=g)
+    want = orarm.forward(sd, tok, ctx, 12)
+    for mode, tol in ((0, 1e-4), (4, 5e-3)):
+        net.set_mode(mode)
+        assert rel(net.forward(tok, ctx), want) < tol, mode
+    # the full 256-step loop of scripts/rarm_sample.py (guided, batch 2 -> 4 rows): runs, stays in range, is reproducible
+    u = torch.rand(256, 2, generator=g)
+    r = torch.cat([ctx, torch.zeros_like(ctx)])
+    net.set_context(r)
+    a = net.sample(tok[:, :1], 256, temperature=1.0, top_k=256, guidance_scale=2.0, uniforms=u)
+    net.set_context(r)
+    b = net.sample(tok[:, :1], 256, temperature=1.0, top_k=256, guidance_scale=2.0, uniforms=u)
+    assert a.shape == (2, 257) and torch.equal(a, b) and 0 <= int(a[:, 1:].min()) and int(a[:, 1:].max()) < 16384
