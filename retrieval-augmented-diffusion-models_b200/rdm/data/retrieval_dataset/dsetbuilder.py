@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from ldm.util import instantiate_from_config
+from rdm_b200 import db_loader
 from rdm_b200.knn import B200Searcher, ShardedSearcher, shard_range
 
 
@@ -45,6 +46,7 @@ class DatasetBuilder(object):
         self.data_pool = {'embedding': [], 'img_id': [], 'patch_coords': []}
         self.saved_embeddings = saved_embeddings
         self.shard = shard
+        self._row_base, self._n_total = None, None   # set when only this rank's rows of a sharded database were read
         if self.saved_embeddings:
             self.load_embeddings()
         self.searcher = None
@@ -94,6 +96,20 @@ class DatasetBuilder(object):
         if len(self.data_pool['embedding']) > 0:
             return
         print(f'Load saved patch embedding from "{self.saved_embeddings}"')
+        if self._dist_world() > 1 and (os.path.isfile(self.saved_embeddings) or os.path.isdir(self.saved_embeddings)):
+            # row-sharded database: this rank reads only the parts that overlap the rows it will own; the small
+            # id / coordinate arrays stay complete on every rank because search results index them globally (dsetbuilder.py:494-495)
+            r, w = torch.distributed.get_rank(), torch.distributed.get_world_size()
+            n_total = sum(db_loader.part_row_counts(db_loader.list_parts(self.saved_embeddings)))
+            lo, hi = shard_range(n_total, r, w)
+            self.data_pool = {'embedding': db_loader.load_rows(self.saved_embeddings, lo, hi, keys=('embedding',))['embedding']}
+            meta = db_loader.load_rows(self.saved_embeddings, 0, n_total, keys=('img_id', 'patch_coords'))
+            self.data_pool.update({k: meta[k] for k in ('img_id', 'patch_coords') if k in meta})
+            self._row_base, self._n_total = lo, n_total
+            if self.max_pool_size is None or n_total >= self.max_pool_size:
+                self.max_pool_size = n_total
+            print(f'Rank {r}/{w}: rows [{lo}, {hi}) of the {n_total}-row retrieval database.')
+            return
         if os.path.isfile(self.saved_embeddings):
             self.load_single_file(self.saved_embeddings)
         elif os.path.isdir(self.saved_embeddings):
@@ -108,6 +124,11 @@ class DatasetBuilder(object):
             raise ValueError(f'Embeddings string "{self.saved_embeddings}" nor directory neither file --> check this.')
         print(f'Finished loading of retrieval database of length {self.data_pool["embedding"].shape[0]}.')
 
+    def _dist_world(self):
+        """World size when the database is to be row-sharded (`shard=True` under an initialised torch.distributed), else 1."""
+        d = torch.distributed
+        return d.get_world_size() if (self.shard and d.is_available() and d.is_initialized()) else 1
+
     # ---- searcher ------------------------------------------------------------------------------------------------
     def train_searcher(self, k=None, metric=None, device=None, **ignored_scann_options):
         """Uploads the RAW rows to HBM (fp16 stays fp16) and computes the inverse norms there.  Replaces
@@ -120,8 +141,10 @@ class DatasetBuilder(object):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         n, base = emb.shape[0], 0
-        dist_on = self.shard and torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
-        if dist_on:
+        dist_on = self._dist_world() > 1
+        if dist_on and self._row_base is not None:
+            base = self._row_base                                        # load_embeddings already read just this rank's rows
+        elif dist_on:
             r, w = torch.distributed.get_rank(), torch.distributed.get_world_size()
             base, end = shard_range(n, r, w)
             emb = emb[base:end]
@@ -141,7 +164,11 @@ class DatasetBuilder(object):
         start = time.time()
         nns, distances = self.searcher.search_batched(query_embeddings, final_num_neighbors=k)
         end = time.time()
-        out = {'embeddings': self.data_pool['embedding'][nns], 'queries': queries, 'exec_time': end - start, 'nns': nns,
+        if self._row_base is not None:                                   # local rows only: gather across the shards on the device
+            nn_emb = self.searcher.gather_device(torch.as_tensor(np.asarray(nns), dtype=torch.int64, device=self.searcher.local.device)).cpu().numpy()
+        else:
+            nn_emb = self.data_pool['embedding'][nns]
+        out = {'embeddings': nn_emb, 'queries': queries, 'exec_time': end - start, 'nns': nns,
                'distances': distances, 'q_embeddings': q_emb_}
         for key_out, key in (('img_ids', 'img_id'), ('patch_coords', 'patch_coords')):
             if key in self.data_pool and len(self.data_pool[key]) > 0:

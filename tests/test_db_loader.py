@@ -53,3 +53,25 @@ def test_only_overlapping_parts_are_opened(tmp_path, monkeypatch):
     assert opened == ["part_002.npz"] and np.array_equal(rows["embedding"], full["embedding"][6:9])
     with pytest.raises(ValueError):
         db_loader.load_rows(str(tmp_path), 16, 20)
+
+
+@pytest.mark.parametrize("rank", [0, 1, 2])
+def test_dataset_builder_reads_only_its_shard(tmp_path, monkeypatch, rank):
+    """DatasetBuilder(shard=True) under an initialised process group: rank r holds rows shard_range(n, r, world) of the embeddings
+    (what `train_searcher` uploads with idx_base = lo), the id / coordinate arrays stay complete (results index them globally)."""
+    import torch
+    import rdm  # noqa: F401  (installs the shims)
+    from rdm.data.retrieval_dataset.dsetbuilder import DatasetBuilder
+    full = _make_db(tmp_path)
+    n, world = full["embedding"].shape[0], 3
+    monkeypatch.setattr(torch.distributed, "is_initialized", lambda: True)
+    monkeypatch.setattr(torch.distributed, "get_rank", lambda *a: rank)
+    monkeypatch.setattr(torch.distributed, "get_world_size", lambda *a: world)
+    b = DatasetBuilder(retriever_config=None, saved_embeddings=str(tmp_path), load_patch_dataset=False, gpu=False, shard=True)
+    lo, hi = shard_range(n, rank, world)
+    assert (b._row_base, b._n_total) == (lo, n) and b.max_pool_size == n
+    assert np.array_equal(b.data_pool["embedding"], full["embedding"][lo:hi]) and b.data_pool["embedding"].dtype == np.float16
+    assert np.array_equal(b.data_pool["img_id"], full["img_id"]) and np.array_equal(b.data_pool["patch_coords"], full["patch_coords"])
+    # without shard=True every rank keeps the reference behaviour: the whole database
+    b = DatasetBuilder(retriever_config=None, saved_embeddings=str(tmp_path), load_patch_dataset=False, gpu=False, shard=False)
+    assert b._row_base is None and np.array_equal(b.data_pool["embedding"], full["embedding"])
