@@ -10,6 +10,9 @@ stand-ins of tests/golden/ref_stubs.py (see its header for what that covers).  W
                       BasicTransformerBlock (:77-96), CrossAttention (:20-74)                          -> oracle/unet.py
   ref_ddim_tiny.npz   rdm/models/diffusion/ddim.py DDIMSampler.make_schedule/sample/ddim_sampling/p_sample_ddim (:27-268) with
                       classifier-free guidance, eta = 0 and eta = 0.5, over the same U-Net                -> oracle/ddim.py
+  ref_pipeline_tiny.npz  rdm/models/diffusion/ddpm.py MinimalRETRODiffusion.sample_from_rdata / sample_with_query / get_qids /
+                      get_unconditional_conditioning / apply_model / sample_log (:445-458, :647-686, :689-844, :847-875, :878-1011) with
+                      EMA weights, over an exact brute-force searcher (what the reference builds for pools < 2e4 rows)   -> the mirror
   ref_rarm_small.npz  rdm/modules/attention.py RetrievalPatchTransformer (:199-272; discrete tokens, positional encodings, causal
                       self-attention, cross-attention to the retrieved vectors) and the sampling arithmetic of
                       rdm/models/autoregression/transformer.py LatentImageRETRO.sample (:224-270)         -> oracle/rarm.py
@@ -118,7 +121,106 @@ def rarm():
     save("ref_rarm_small.npz", out)
 
 
+N_DB, K_NN = 600, 4
+
+
+class ExactSearcher:
+    """What `scann.scann_ops_pybind.builder(db / |db|, k, "dot_product").score_brute_force().build()` computes for pools < 2e4
+    (dsetbuilder.py:574,590-592): exact top-k by dot product on unit rows, best first."""
+
+    def __init__(self, emb):
+        e = emb.astype(np.float64)
+        self.unit = e / np.linalg.norm(e, axis=1)[:, None]
+
+    def search_batched(self, q, final_num_neighbors=None):
+        s = q.astype(np.float64) @ self.unit.T
+        idx = np.argsort(-s, axis=1, kind="stable")[:, :final_num_neighbors]
+        return idx.astype(np.uint32), np.take_along_axis(s, idx, 1).astype(np.float32)
+
+
+class Retriever:
+    """The DatasetBuilder surface `sample_from_rdata` / `sample_with_query` touch; `search_k_nearest` follows dsetbuilder.py:478-518
+    for already-embedded queries (the reference's own dsetbuilder.py cannot be imported: scann, streamlit, the image datasets)."""
+    load_patch_dataset = False
+
+    def __init__(self, emb):
+        self.data_pool = {"embedding": emb, "img_id": np.arange(len(emb)), "patch_coords": np.zeros((len(emb), 4), np.int32)}
+        self.searcher = None
+        self.retriever = torch.nn.Identity()
+
+    def train_searcher(self):
+        self.searcher = ExactSearcher(self.data_pool["embedding"])
+
+    def search_k_nearest(self, queries, k=None, is_caption=False, visualize=None, query_embedded=False):
+        assert query_embedded
+        q_emb_ = queries
+        query_embeddings = q_emb_ / np.linalg.norm(q_emb_, axis=1)[:, np.newaxis]
+        nns, distances = self.searcher.search_batched(query_embeddings, final_num_neighbors=k)
+        return {"embeddings": self.data_pool["embedding"][nns], "img_ids": self.data_pool["img_id"][nns], "patch_coords": self.data_pool["patch_coords"][nns],
+                "queries": queries, "exec_time": 0.0, "nns": nns, "q_embeddings": q_emb_}
+
+
+def pipeline():
+    """MinimalRETRODiffusion.sample_from_rdata / sample_with_query / get_qids / get_unconditional_conditioning / apply_model / sample_log
+    (ddpm.py:445-458,647-686,689-844,847-875,878-1011) run end to end on CPU."""
+    import pickle
+    import tempfile
+    import rdm.models.diffusion.ddpm as ref_ddpm                              # the reference's
+    from rdm.models.diffusion.ddim import DDIMSampler
+
+    class CpuDDIMSampler(DDIMSampler):
+        def register_buffer(self, name, attr):
+            setattr(self, name, attr)
+    ref_ddpm.DDIMSampler = CpuDDIMSampler                                      # sample_log constructs DDIMSampler(self) (ddpm.py:993)
+
+    db, mem, id_count = ref_weights.make_db(N_DB)
+    with tempfile.TemporaryDirectory() as td:
+        mem_path = os.path.join(td, "nn_memory.p")
+        with open(mem_path, "wb") as f:
+            pickle.dump({"nn_memory": mem, "id_count": id_count}, f)
+        A = ref_stubs.AttrDict
+        unet = dict(UNET_CFG)
+        model = ref_ddpm.MinimalRETRODiffusion(
+            k_nn=K_NN, query_key="clip_img_emb", retrieval_encoder_cfg=A(target="torch.nn.Identity"), nn_memory=mem_path, retrieval_cfg=None,
+            unet_config=A(target="rdm.modules.diffusionmodules.openaimodel.UNetModel", params=unet), first_stage_config=None,
+            cond_stage_config="__is_unconditional__", timesteps=1000, linear_start=0.0015, linear_end=0.0195, image_size=16, channels=4,
+            conditioning_key="crossattn", log_every_t=100).eval()
+    model.retriever = Retriever(db)
+    # checkpoint layout: live weights under model.diffusion_model.*, EMA shadows under model_ema.<name without dots> (ddpm.py:162-164)
+    live = ref_weights.state_dict_for(((k, v.shape) for k, v in model.model.diffusion_model.state_dict().items()), 11)
+    ema = ref_weights.state_dict_for(((k, v.shape) for k, v in model.model.diffusion_model.state_dict().items()), 12)
+    sd = {"model.diffusion_model." + k: v for k, v in live.items()}
+    sd.update({"model_ema." + ("diffusion_model." + k).replace(".", ""): v for k, v in ema.items()})
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    out = {"n_db": np.int64(N_DB), "k_nn": np.int64(K_NN), "live_seed": np.int64(11), "ema_seed": np.int64(12), "missing_keys": np.array(sorted(missing)),
+           "nn_memory": mem, "id_count_keys": np.array(list(id_count.keys())), "id_count_vals": np.array(list(id_count.values()))}
+    g = torch.Generator().manual_seed(43)
+    xT = torch.randn(3, 4, 16, 16, generator=g)
+    common = dict(unconditional_guidance_scale=2.0, ddim_steps=4, ddim=True, unconditional_retro_guidance_label=0.)
+    # (1) scripts/rdm_sample.py:226-262: top-m pseudo-queries from the NumPy global RNG, then sample_from_rdata
+    np.random.seed(44)
+    qids = model.get_qids(50, 3, use_weights=False)
+    np.random.seed(44)
+    logs = model.sample_from_rdata(3, qids=None, k_nn=K_NN, use_weights=False, memsize=50, x_T=xT.clone(), **common)
+    out["rdata:qids"], out["rdata:x_T"], out["rdata:samples"] = qids, xT.numpy(), logs["samples_with_sampled_nns"].numpy()
+    np.random.seed(45)
+    out["qids_weighted"] = model.get_qids(0.4, 5, use_weights=True)
+    # (2) scripts/rdm_sample.py:272-299: an embedded (text) query, prepended as neighbour 0; and omit_query
+    q = torch.from_numpy(ref_weights.tensor_for("query", (2, 512), 46) * 22.0)
+    for tag, omit in (("query", False), ("query_omit", True)):
+        logs = model.sample_with_query(query=q, query_embedded=True, k_nn=K_NN, visualize_nns=False, omit_query=omit, x_T=xT[:2].clone(), **common)
+        out[f"{tag}:samples"] = logs["query_samples"].numpy()
+    out["query:q"] = q.numpy()
+    # (3) unconditional conditioning for a non-zero label (ddpm.py:663-686): vex / |vex| * label, stacked [bs, k, d]
+    model.unconditional_guidance_vex.copy_(torch.from_numpy(ref_weights.tensor_for("vex", (512,), 47)))
+    out["uncond_label_1.5"] = model.get_unconditional_conditioning((2, K_NN, 512), unconditional_guidance_label=1.5, k_nn=K_NN).numpy()
+    out["vex"] = model.unconditional_guidance_vex.numpy().copy()
+    save("ref_pipeline_tiny.npz", out)
+
+
 if __name__ == "__main__":
     ref_stubs.install()
     unet_and_ddim()
     rarm()
+    pipeline()

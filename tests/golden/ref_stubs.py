@@ -196,6 +196,101 @@ class AttentionBlock(nn.Module):
         raise NotImplementedError("the shipped configs set use_spatial_transformer=True")
 
 
+# ---- ldm.modules.ema / ldm.models.diffusion.ddpm (what MinimalRETRODiffusion's sampling methods use of its base class) ----------
+class LitEma(nn.Module):
+    def __init__(self, model, decay=0.9999, use_num_upates=True):
+        super().__init__()
+        self.m_name2s_name = {}
+        self.register_buffer("decay", torch.tensor(decay, dtype=torch.float32))
+        self.register_buffer("num_updates", torch.tensor(0, dtype=torch.int) if use_num_upates else torch.tensor(-1, dtype=torch.int))
+        for name, p in model.named_parameters():
+            if p.requires_grad:
+                s_name = name.replace(".", "")                    # "remove as '.'-character is not allowed in buffers"
+                self.m_name2s_name.update({name: s_name})
+                self.register_buffer(s_name, p.clone().detach().data)
+        self.collected_params = []
+
+    def copy_to(self, model):
+        m_param, shadow_params = dict(model.named_parameters()), dict(self.named_buffers())
+        for key in m_param:
+            if m_param[key].requires_grad:
+                m_param[key].data.copy_(shadow_params[self.m_name2s_name[key]].data)
+
+    def store(self, parameters):
+        self.collected_params = [param.clone() for param in parameters]
+
+    def restore(self, parameters):
+        for c_param, param in zip(self.collected_params, parameters):
+            param.data.copy_(c_param.data)
+
+
+class LdmDiffusionWrapper(nn.Module):
+    def __init__(self, diff_model_config, conditioning_key):
+        super().__init__()
+        self.diffusion_model = instantiate_from_config(diff_model_config)
+        self.conditioning_key = conditioning_key
+
+
+class IdentityFirstStage(nn.Module):
+    def decode(self, x, *args, **kwargs):
+        return x
+
+
+class LatentDiffusion(nn.Module):
+    """The slice of ldm's DDPM / LatentDiffusion that sampling touches: the eps-model wrapper, the float32 schedule buffers
+    (register_schedule), `device`, `ema_scope` (store -> copy_to -> restore) and `decode_first_stage` over an identity first stage."""
+
+    def __init__(self, unet_config, first_stage_config=None, cond_stage_config=None, timesteps=1000, beta_schedule="linear", linear_start=1e-4,
+                 linear_end=2e-2, image_size=256, channels=3, conditioning_key=None, scale_factor=1.0, log_every_t=100, parameterization="eps",
+                 first_stage_key="image", cond_stage_key="image", **unused):
+        super().__init__()
+        if cond_stage_config == "__is_unconditional__":
+            conditioning_key = None
+        self.parameterization, self.log_every_t, self.image_size, self.channels = parameterization, log_every_t, image_size, channels
+        self.model = LdmDiffusionWrapper(unet_config, conditioning_key)
+        betas = make_beta_schedule(beta_schedule, timesteps, linear_start=linear_start, linear_end=linear_end)
+        alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
+        self.num_timesteps = int(timesteps)
+        to_torch = lambda a: torch.tensor(a, dtype=torch.float32)
+        self.register_buffer("betas", to_torch(betas))
+        self.register_buffer("alphas_cumprod", to_torch(alphas_cumprod))
+        self.register_buffer("alphas_cumprod_prev", to_torch(np.append(1.0, alphas_cumprod[:-1])))
+        self.first_stage_model = IdentityFirstStage()
+        self.scale_factor = scale_factor
+
+    @property
+    def device(self):
+        return self.betas.device
+
+    def ema_scope(self, context=None):
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            if self.use_ema:
+                self.model_ema.store(self.model.parameters())
+                self.model_ema.copy_to(self.model)
+            try:
+                yield None
+            finally:
+                if self.use_ema:
+                    self.model_ema.restore(self.model.parameters())
+        return scope()
+
+    def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
+        return self.first_stage_model.decode(1.0 / self.scale_factor * z)
+
+
+class AttrDict(dict):
+    """Stand-in for an OmegaConf node: `cfg.params.context_dim` and `cfg["target"]` both work."""
+    def __getattr__(self, k):
+        try:
+            v = self[k]
+        except KeyError:
+            raise AttributeError(k)
+        return AttrDict(v) if isinstance(v, dict) and not isinstance(v, AttrDict) else v
+
+
 def install(reference_root="/root/reference"):
     """Registers the stand-ins in sys.modules and puts the reference checkout first on sys.path."""
     me = sys.modules[__name__]
@@ -217,6 +312,19 @@ def install(reference_root="/root/reference"):
                                                     "timestep_embedding", "make_ddim_timesteps", "make_ddim_sampling_parameters",
                                                     "noise_like", "make_beta_schedule"))
     mod("ldm.modules.diffusionmodules.openaimodel", **pick("TimestepBlock", "ResBlock", "Downsample", "Upsample", "AttentionBlock"))
+    mod("ldm.modules.ema", **pick("LitEma"))
+    mod("ldm.models")
+    mod("ldm.models.autoencoder", AutoencoderKL=type("AutoencoderKL", (nn.Module,), {}), VQModelInterface=type("VQModelInterface", (nn.Module,), {}),
+        VQModel=type("VQModel", (nn.Module,), {}), **pick("IdentityFirstStage"))
+    cls = lambda n: type(n, (nn.Module,), {})                    # imported by rdm/modules/encoders/nn_encoders.py:6-9, never instantiated here
+    mod("ldm.modules.x_transformer", AbsolutePositionalEmbedding=cls("AbsolutePositionalEmbedding"), Encoder=cls("Encoder"), always=None, **pick("exists"))
+    mod("ldm.models.diffusion")
+    mod("ldm.models.diffusion.ddpm", **pick("LatentDiffusion"))
+    sys.modules["ldm.util"].get_obj_from_str = lambda s, reload=False: getattr(importlib.import_module(s.rsplit(".", 1)[0]), s.rsplit(".", 1)[1])
+    sys.modules["ldm.util"].isimage = lambda x: isinstance(x, torch.Tensor) and x.ndim == 4 and x.shape[1] in (1, 3)
+    mod("pytorch_lightning", LightningModule=nn.Module, seed_everything=lambda s: None)
+    mod("pytorch_lightning.utilities")
+    mod("pytorch_lightning.utilities.distributed", rank_zero_only=lambda f: f)
     mod("main", **pick("instantiate_from_config"))
     mod("kornia")
     mod("omegaconf")

@@ -32,3 +32,12 @@ def fill_(module, seed):
     sd = state_dict_for(((k, v.shape) for k, v in module.state_dict().items()), seed)
     module.load_state_dict(sd)
     return module
+
+
+def make_db(n=600):
+    """The synthetic retrieval database of ref_pipeline_tiny.npz: RAW (un-normalised) fp16 CLIP-like rows with very different norms,
+    plus a neighbour-frequency memory in the reference's pickle layout {'nn_memory', 'id_count'} (ddpm.py:166-176)."""
+    scale = 0.5 + 60.0 * np.abs(tensor_for("db.scale", (n,), 41))[:, None]
+    db = (tensor_for("db.embedding", (n, 512), 41) * np.float32(22.0) * scale).astype(np.float16)
+    mem = np.random.RandomState(42).permutation(n)[:200].astype(np.int64)
+    return db, mem, {int(i): int(1 + (7 * i) % 13) for i in mem}
