@@ -6,23 +6,31 @@ only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 CPU baseline.  The product path (``retrieval-augmented-diffusion-models_b200/``)
 never imports this package and fails loudly when its CUDA library is missing.
 
-PARITY UNPINNED by the reference: the reference ships no tests, fixtures or
-golden vectors, its own modules cannot be imported here (``ldm``,
-``scann``, ``clip``, ``omegaconf``, ``pytorch_lightning``, ``kornia`` are absent
-and un-vendored), and its kNN backend (ScaNN 1.2.4) is an
-*approximate* CPU searcher.  The oracle is therefore a restatement of
+PINNING.  The reference ships no tests, fixtures or golden vectors
+and its modules do not import as they are (``ldm``, ``scann``, ``clip``,
+``omegaconf``, ``pytorch_lightning``, ``kornia`` are absent and un-vendored,
+SURVEY.md §8c).  The restatements here follow
 
 * ``rdm/modules/diffusionmodules/openaimodel.py:17-33,66-317,335-371`` (U-Net),
-* ``rdm/modules/attention.py:16-17,20-74,77-96,122-196`` (SpatialTransformer),
+* ``rdm/modules/attention.py:16-17,20-74,77-96,122-196`` (SpatialTransformer), ``:199-272`` (RARM decoder),
 * ``rdm/models/diffusion/ddim.py:27-56,143-215,218-268`` (DDIM sampler),
+* ``rdm/models/autoregression/transformer.py:224-270`` (RARM sampling loop),
 * ``rdm/data/retrieval_dataset/dsetbuilder.py:478-518,574`` + ``rdm/models/diffusion/ddpm.py:897-921`` (kNN),
 * the public ``latent-diffusion@main`` pieces those files import,
 
-pinned only by the known answers the reference repo does contain: the printed
-U-Net size (400.92 M parameters, ``scripts/demo_rdm.ipynb:128``; exact count
-400,920,579 in 688 tensors), the per-level head counts 12/18/30 at d_head 32
-(``scripts/demo_rdm.ipynb:112-127``), the DDIM-100 timestep grid 1,11,…,991 and
-the conditioning shape ``[8, 4, 512]``.  ``tests/test_oracle.py`` asserts them.
-The vendored CLIP (``rdm/modules/custom_clip/model.py``) does import on CPU and
-is used by ``tests/golden/make_golden.py`` to pin the CLIP restatement.
+and are PINNED to outputs of the reference's own code: ``tests/golden/make_golden_ref.py``
+runs the reference's UNetModel / SpatialTransformer / DDIMSampler /
+MinimalRETRODiffusion.sample_from_rdata / sample_with_query / RetrievalPatchTransformer
+unmodified from /root/reference on CPU (over small stand-ins for the un-vendored
+``ldm`` functions, ``tests/golden/ref_stubs.py``) and commits the outputs
+(``tests/golden/ref_*.npz``); ``tests/golden/make_golden.py`` does the same for the
+vendored CLIP.  ``tests/test_oracle_ref_golden.py``, ``test_oracle_rarm.py`` and
+``test_oracle_clip.py`` check the oracle against them; ``tests/test_oracle.py`` adds the
+known answers printed in the repository (400,920,579 U-Net parameters in 688 tensors,
+``scripts/demo_rdm.ipynb:128``; head counts 12/18/30; the DDIM-100 grid 1,11,…,991).
+
+PARITY UNPINNED remains for two pieces: the kNN result (ScaNN 1.2.4 is an approximate CPU
+searcher that is not installed; ``oracle/knn_ref.c`` defines the exact semantics it
+approximates) and the first-stage decoder (``oracle/vqdecoder.py`` restates ldm's
+un-vendored ``Decoder``).
 """
