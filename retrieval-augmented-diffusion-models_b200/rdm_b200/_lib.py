@@ -91,12 +91,16 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(the product has no CPU or PyTorch fallback)")
-        L = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(L, name)
-            fn.restype, fn.argtypes = res, args
-        _lib = L
+        _lib = bind(ctypes.CDLL(LIB_PATH))
     return _lib
+
+
+def bind(L, names=None):
+    """Applies the SIGNATURES table to a loaded library (all entry points, or the given subset)."""
+    for name in (SIGNATURES if names is None else names):
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = SIGNATURES[name]
+    return L
 
 
 def check(rc, what=""):

@@ -41,15 +41,13 @@ class B200Rarm:
     """Owns one `rdm_rarm_t` handle."""
 
     def __init__(self, device, **cfg):
-        L = _lib.lib()
-        self.device = torch.device(device)
-        if self.device.index is None:
-            self.device = torch.device("cuda", torch.cuda.current_device())
+        L = self._library()
+        self.device, index = self._resolve_device(device)
         self.cfg = {k: int(cfg[k]) for k, _ in RarmCfg._fields_}
         self.shapes = rarm_param_shapes(**self.cfg)
         c = RarmCfg(**self.cfg)
         self._h = ctypes.c_void_p()
-        _lib.check(L.rdm_rarm_create(ctypes.byref(self._h), ctypes.byref(c), self.device.index), "rdm_rarm_create")
+        self._check(L.rdm_rarm_create(ctypes.byref(self._h), ctypes.byref(c), index), "rdm_rarm_create")
         names = [L.rdm_rarm_param_name(self._h, i).decode() for i in range(L.rdm_rarm_num_params(self._h))]
         assert names == list(self.shapes), "parameter inventory of csrc/rarm.cu and rarm_param_shapes() differ"
         self._B2 = 0
@@ -58,16 +56,34 @@ class B200Rarm:
         h, self._h = getattr(self, "_h", None), None
         if h:
             try:
-                _lib.lib().rdm_rarm_destroy(h)
+                self._library().rdm_rarm_destroy(h)
             except Exception:
                 pass
 
+    # The three hooks below are the only places that touch the CUDA device; tests/test_rarm_emulated.py overrides them to drive the SAME
+    # C ABI compiled against a host emulation of CUDA.  The product has no other implementation: _library() raises without the .so.
+    def _library(self):
+        return _lib.lib()
+
+    def _resolve_device(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("the RARM decoder (B200 build) has no CPU path: pass a CUDA device")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        return device, device.index
+
     def _run(self, fn, *args):
         with torch.cuda.device(self.device):
-            _lib.check(getattr(_lib.lib(), fn)(self._h, *args, _lib.stream_ptr(self.device)), fn)
+            self._check(getattr(self._library(), fn)(self._h, *args, _lib.stream_ptr(self.device)), fn)
+
+    def _check(self, rc, what=""):
+        if rc != 0:
+            msg = self._library().rdm_last_error()
+            raise RuntimeError(f"librdm_b200 {what} failed ({rc}): {msg.decode() if msg else ''}")
 
     def load_state_dict(self, sd, strict=True):
-        L = _lib.lib()
+        L = self._library()
         missing = [k for k in self.shapes if k not in sd]
         if strict and missing:
             raise RuntimeError(f"missing RARM parameters: {missing[:5]}{'...' if len(missing) > 5 else ''}")
@@ -78,17 +94,17 @@ class B200Rarm:
             if tuple(t.shape) != tuple(shp):
                 raise RuntimeError(f"size mismatch for {k}: {tuple(t.shape)} vs {tuple(shp)}")
             t = t.to("cpu", torch.float32).contiguous()
-            _lib.check(L.rdm_rarm_load(self._h, k.encode(), ctypes.c_void_p(t.data_ptr()), t.numel()), f"rdm_rarm_load({k})")
+            self._check(L.rdm_rarm_load(self._h, k.encode(), ctypes.c_void_p(t.data_ptr()), t.numel()), f"rdm_rarm_load({k})")
         return missing
 
     def missing(self):
-        return int(_lib.lib().rdm_rarm_missing(self._h))
+        return int(self._library().rdm_rarm_missing(self._h))
 
     def set_mode(self, mode):
-        _lib.check(_lib.lib().rdm_rarm_set_mode(self._h, int(mode)), "rdm_rarm_set_mode")
+        self._check(self._library().rdm_rarm_set_mode(self._h, int(mode)), "rdm_rarm_set_mode")
 
     def set_graph(self, on):
-        _lib.check(_lib.lib().rdm_rarm_set_graph(self._h, int(bool(on))), "rdm_rarm_set_graph")
+        self._check(self._library().rdm_rarm_set_graph(self._h, int(bool(on))), "rdm_rarm_set_graph")
 
     def set_context(self, context):
         """context: float32 [B2, k, context_dim]; restarts the sequences."""

@@ -1,0 +1,56 @@
+"""Builds tests/emu/_build/librdm_emu.so: csrc/rarm.cu + csrc/common.cu compiled by g++ against the host emulation of CUDA in
+tests/emu/include (see cuda_runtime.h there).  The sources are used as written except for two mechanical rewrites:
+  kernel<<<grid, block, smem, stream>>>(args);   ->  emu::launch(kernel, grid, block, smem, stream, args);
+  extern __shared__ T name[];                    ->  T* name = (T*)emu::dyn_smem;
+TEST INFRASTRUCTURE (tests/test_rarm_emulated.py)."""
+import hashlib
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "retrieval-augmented-diffusion-models_b200", "csrc")
+OUT = os.path.join(HERE, "_build")
+UNITS = ("rarm.cu", "common.cu")
+
+
+def rewrite(src):
+    n_launch = len(re.findall(r"<<<", src))
+    src, k = re.subn(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)\s*<<<([^;]*?)>>>\s*\(([^;]*?)\);", lambda m: f"emu::launch({m.group(1)}, {m.group(2)}, {m.group(3)});", src)
+    assert k == n_launch, f"rewrote {k} of {n_launch} kernel launches"
+    src = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1* \2 = (\1*)emu::dyn_smem;", src)
+    assert "extern __shared__" not in src
+    return src
+
+
+def build(verbose=False):
+    os.makedirs(OUT, exist_ok=True)
+    inputs = [os.path.join(CSRC, u) for u in UNITS] + [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "rdm_b200.h"), os.path.join(HERE, "emu_core.cpp"),
+                                                       __file__] + [os.path.join(HERE, "include", f) for f in sorted(os.listdir(os.path.join(HERE, "include")))]
+    h = hashlib.sha1()
+    for p in inputs:
+        h.update(open(p, "rb").read())
+    lib, stamp = os.path.join(OUT, "librdm_emu.so"), os.path.join(OUT, "stamp")
+    if os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
+        return lib
+    cpps = [os.path.join(HERE, "emu_core.cpp")]
+    for u in UNITS:
+        text = rewrite(open(os.path.join(CSRC, u)).read())
+        text = text.replace('#include "common.cuh"', f'#include "{os.path.join(CSRC, "common.cuh")}"').replace('#include "../../include/rdm_b200.h"', f'#include "{os.path.join(ROOT, "include", "rdm_b200.h")}"')
+        dst = os.path.join(OUT, u.replace(".cu", "_emu.cpp"))
+        open(dst, "w").write(text)
+        cpps.append(dst)
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-attributes",
+           "-I", os.path.join(HERE, "include"), "-o", lib] + cpps
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-6000:], r.stderr[-6000:])
+    if r.returncode != 0:
+        raise RuntimeError("building the emulated library failed")
+    open(stamp, "w").write(h.hexdigest())
+    return lib
+
+
+if __name__ == "__main__":
+    print(build(verbose=True))

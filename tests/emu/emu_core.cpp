@@ -1,0 +1,168 @@
+// Scheduler and runtime of the host emulation declared in include/cuda_runtime.h (test infrastructure).
+#include "cuda_runtime.h"
+#include <mutex>
+
+thread_local uint3 threadIdx, blockIdx;
+thread_local dim3 blockDim(1), gridDim(1);
+
+namespace emu {
+
+thread_local void* dyn_smem = nullptr;
+
+namespace {
+constexpr size_t STACK_BYTES = 64 * 1024;
+enum State { READY, WAIT_BLOCK, WAIT_WARP, DONE };
+struct Fiber {
+    ucontext_t ctx;
+    State state = READY;
+    uint3 tid{0, 0, 0};
+    int linear = 0;
+};
+struct Warp { uint64_t slot[2][32]; int parity = 0; int arrived = 0; int live = 0; };
+struct BlockRun {
+    std::vector<Fiber> fibers;
+    std::vector<Warp> warps;
+    ucontext_t main;
+    int cur = -1, live = 0, block_arrived = 0;
+    const std::function<void()>* body = nullptr;
+};
+thread_local BlockRun* t_run = nullptr;
+thread_local std::vector<char*>* t_stacks = nullptr;
+
+void fiber_entry() {
+    BlockRun* r = t_run;
+    (*r->body)();
+    Fiber& f = r->fibers[r->cur];
+    f.state = DONE;
+    r->live--;
+    r->warps[f.linear / 32].live--;
+    // a thread that exits releases barriers the remaining threads are waiting on (CUDA: exited threads do not participate)
+    if (r->live > 0 && r->block_arrived == r->live) { for (auto& g : r->fibers) if (g.state == WAIT_BLOCK) g.state = READY; r->block_arrived = 0; }
+    Warp& w = r->warps[f.linear / 32];
+    if (w.live > 0 && w.arrived == w.live) { for (int l = 0; l < 32; l++) { int i = (f.linear / 32) * 32 + l; if (i < (int)r->fibers.size() && r->fibers[i].state == WAIT_WARP) r->fibers[i].state = READY; } w.arrived = 0; w.parity ^= 1; }
+    swapcontext(&f.ctx, &r->main);
+}
+void yield_to_scheduler() {
+    BlockRun* r = t_run;
+    swapcontext(&r->fibers[r->cur].ctx, &r->main);
+}
+
+void run_block(const std::function<void()>& body, dim3 grid, dim3 block, uint3 bidx, size_t smem) {
+    const int n = (int)(block.x * block.y * block.z);
+    if (!t_stacks) t_stacks = new std::vector<char*>();
+    while ((int)t_stacks->size() < n) t_stacks->push_back((char*)aligned_alloc(64, STACK_BYTES));
+    std::vector<char> shared(smem + 64);
+    dyn_smem = (void*)(((uintptr_t)shared.data() + 63) & ~(uintptr_t)63);
+    BlockRun run;
+    run.fibers.resize(n); run.warps.resize((n + 31) / 32); run.live = n; run.body = &body;
+    for (int i = 0; i < n; i++) {
+        Fiber& f = run.fibers[i];
+        f.linear = i; f.tid = uint3{(unsigned)(i % block.x), (unsigned)((i / block.x) % block.y), (unsigned)(i / (block.x * block.y))};
+        run.warps[i / 32].live++;
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = (*t_stacks)[i]; f.ctx.uc_stack.ss_size = STACK_BYTES; f.ctx.uc_link = nullptr;
+        makecontext(&f.ctx, fiber_entry, 0);
+    }
+    t_run = &run;
+    blockIdx = bidx; blockDim = block; gridDim = grid;
+    int idle_rounds = 0;
+    while (run.live > 0) {
+        bool progressed = false;
+        for (int i = 0; i < n && run.live > 0; i++) {
+            Fiber& f = run.fibers[i];
+            if (f.state != READY) continue;
+            run.cur = i; threadIdx = f.tid;
+            swapcontext(&run.main, &f.ctx);
+            progressed = true;
+        }
+        if (!progressed && ++idle_rounds > 2) { fprintf(stderr, "emu: deadlock in block (%u,%u,%u): %d live threads, none runnable (divergent barrier?)\n", bidx.x, bidx.y, bidx.z, run.live); abort(); }
+        if (progressed) idle_rounds = 0;
+    }
+    t_run = nullptr; dyn_smem = nullptr;
+}
+
+struct Capture { bool on = false; EmuGraph* graph = nullptr; };
+thread_local Capture t_capture;
+std::atomic<int> g_workers{0};
+}  // namespace
+
+void sync_block() {
+    BlockRun* r = t_run;
+    Fiber& f = r->fibers[r->cur];
+    if (++r->block_arrived == r->live) {
+        for (auto& g : r->fibers) if (g.state == WAIT_BLOCK) g.state = READY;
+        r->block_arrived = 0;
+        return;                                       // the last arriver continues without parking
+    }
+    f.state = WAIT_BLOCK;
+    yield_to_scheduler();
+}
+int lane_id() { return t_run->fibers[t_run->cur].linear & 31; }
+uint64_t warp_exchange(uint64_t mine, int src_lane) {
+    BlockRun* r = t_run;
+    Fiber& f = r->fibers[r->cur];
+    const int wi = f.linear / 32, lane = f.linear & 31;
+    Warp& w = r->warps[wi];
+    const int par = w.parity;
+    w.slot[par][lane] = mine;
+    if (++w.arrived == w.live) {
+        for (int l = 0; l < 32; l++) { int i = wi * 32 + l; if (i < (int)r->fibers.size() && r->fibers[i].state == WAIT_WARP) r->fibers[i].state = READY; }
+        w.arrived = 0; w.parity ^= 1;
+    } else {
+        f.state = WAIT_WARP;
+        yield_to_scheduler();
+    }
+    return w.slot[par][src_lane];                     // double-buffered: the next exchange of this warp writes the other parity
+}
+
+void run_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, std::function<void()> body) {
+    if (t_capture.on) {                               // stream capture: record, do not execute
+        t_capture.graph->nodes.push_back([=]() { Capture saved = t_capture; t_capture.on = false; run_launch(grid, block, smem, nullptr, body); t_capture = saved; });
+        return;
+    }
+    const long nblocks = (long)grid.x * grid.y * grid.z;
+    static const int maxw = [] { const char* e = getenv("EMU_WORKERS"); int n = e ? atoi(e) : (int)std::thread::hardware_concurrency(); return n < 1 ? 1 : (n > 16 ? 16 : n); }();
+    const int nw = (int)std::min<long>(maxw, nblocks);
+    std::atomic<long> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            long b = next.fetch_add(1);
+            if (b >= nblocks) break;
+            uint3 bidx{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((long)grid.x * grid.y))};
+            run_block(body, grid, block, bidx, smem);
+        }
+    };
+    if (nw <= 1) { worker(); return; }
+    std::vector<std::thread> ts;
+    for (int i = 0; i < nw; i++) ts.emplace_back(worker);
+    for (auto& t : ts) t.join();
+}
+
+}  // namespace emu
+
+// ---- runtime API -------------------------------------------------------------------------------------------------------
+struct EmuStream { int id; };
+cudaError_t cudaMalloc(void** p, size_t bytes) { *p = aligned_alloc(256, (bytes + 255) & ~(size_t)255); if (*p) memset(*p, 0xCD, bytes); return *p ? cudaSuccess : cudaErrorEmu; }   // poisoned like fresh device memory is arbitrary
+cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemset(void* p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t bytes, cudaMemcpyKind) { memmove(d, s, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(d, s, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpy2D(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind) {
+    for (size_t r = 0; r < height; r++) memmove((char*)d + r * dpitch, (const char*)s + r * spitch, width);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy2D(d, dpitch, s, spitch, width, height, k); }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* st, unsigned) { *st = new EmuStream{1}; return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t st) { delete st; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { emu::t_capture.on = true; emu::t_capture.graph = new EmuGraph(); return cudaSuccess; }
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = emu::t_capture.graph; emu::t_capture.on = false; emu::t_capture.graph = nullptr; return cudaSuccess; }
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long) { *e = new EmuGraph(*g); return cudaSuccess; }
+cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t) { for (auto& n : e->nodes) n(); return cudaSuccess; }
+cudaError_t cudaGetLastError() { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulation error"; }
+cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 148; return cudaSuccess; }

@@ -1,0 +1,126 @@
+// HOST EMULATION of the slice of CUDA that csrc/rarm.cu uses -- TEST INFRASTRUCTURE (tests/test_rarm_emulated.py), never shipped.
+//
+// Purpose: run the UNMODIFIED kernel and host source of a translation unit on the CPU so that indexing, barrier placement, shuffle
+// networks, shared-memory reuse, graph-replay argument baking and the C-ABI host logic are checked in a container without a GPU.
+// tests/emu/build_emu.py rewrites only the launch syntax (`k<<<g, b, s, st>>>(args)` -> `emu::launch(k, g, b, s, st, args)`) and the
+// `extern __shared__ T name[];` declarations; everything else compiles as written against this header.
+//
+// Execution model: blocks are distributed over a few OS threads; the threads of ONE block are cooperative fibers (ucontext) on one OS
+// thread.  `__syncthreads()` and the `__shfl_*_sync` exchanges are yield points: a fiber parks until all live fibers of its block / all 32
+// lanes of its warp have arrived.  `__shared__` becomes `static thread_local` (one block per OS thread at a time), dynamic shared memory
+// is a per-block buffer, device memory is host memory.  A stream capture records launches (with their by-value arguments, exactly what a
+// CUDA graph bakes) and `cudaGraphLaunch` replays them.  What this does NOT check: alignment faults, shared-memory / register limits,
+// launch-configuration limits, memory-model races between warps of different blocks, performance.
+#pragma once
+#include <ucontext.h>
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static thread_local
+
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+
+extern thread_local uint3 threadIdx, blockIdx;
+extern thread_local dim3 blockDim, gridDim;
+
+// ---- runtime API subset ---------------------------------------------------------------------------------------------
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorEmu = 1 };
+typedef struct EmuStream* cudaStream_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+enum { cudaStreamNonBlocking = 1 };
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal, cudaStreamCaptureModeThreadLocal, cudaStreamCaptureModeRelaxed };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+struct EmuGraph { std::vector<std::function<void()>> nodes; };
+typedef EmuGraph* cudaGraph_t;
+typedef EmuGraph* cudaGraphExec_t;
+enum cudaLaunchAttributeID { cudaLaunchAttributeProgrammaticStreamSerialization = 1, cudaLaunchAttributeClusterDimension = 2 };
+struct cudaLaunchAttribute { cudaLaunchAttributeID id; struct { int programmaticStreamSerializationAllowed; struct { unsigned x, y, z; } clusterDim; } val; };
+struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes; cudaStream_t stream; cudaLaunchAttribute* attrs; unsigned numAttrs; };
+
+cudaError_t cudaMalloc(void** p, size_t bytes);
+cudaError_t cudaFree(void* p);
+cudaError_t cudaMemset(void* p, int v, size_t bytes);
+cudaError_t cudaMemcpy(void* d, const void* s, size_t bytes, cudaMemcpyKind k);
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t bytes, cudaMemcpyKind k, cudaStream_t st = nullptr);
+cudaError_t cudaMemcpy2D(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind k);
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind k, cudaStream_t st = nullptr);
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* st, unsigned flags);
+cudaError_t cudaStreamDestroy(cudaStream_t st);
+cudaError_t cudaStreamSynchronize(cudaStream_t st);
+cudaError_t cudaStreamBeginCapture(cudaStream_t st, cudaStreamCaptureMode mode);
+cudaError_t cudaStreamEndCapture(cudaStream_t st, cudaGraph_t* g);
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long flags);
+cudaError_t cudaGraphDestroy(cudaGraph_t g);
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e);
+cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t st);
+cudaError_t cudaGetLastError();
+const char* cudaGetErrorString(cudaError_t e);
+cudaError_t cudaGetDevice(int* d);
+cudaError_t cudaSetDevice(int d);
+cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int dev);
+template <typename F> cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <typename... KArgs, typename... Args> cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t*, void (*)(KArgs...), Args&&...) { return cudaErrorEmu; }
+
+// ---- device-side intrinsics -------------------------------------------------------------------------------------------
+namespace emu {
+void sync_block();
+uint64_t warp_exchange(uint64_t mine, int src_lane);       // returns the value posted by lane `src_lane` of the caller's warp (all 32 lanes call)
+int lane_id();
+extern thread_local void* dyn_smem;
+void run_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, std::function<void()> thread_body);
+template <typename... KArgs, typename... Args>
+void launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    auto body = [=]() { kern(static_cast<KArgs>(args)...); };          // arguments captured BY VALUE at launch time
+    run_launch(grid, block, smem, st, body);
+}
+template <typename T> inline uint64_t to_bits(T v) { uint64_t b = 0; static_assert(sizeof(T) <= 8, "shuffle of > 8 bytes"); memcpy(&b, &v, sizeof(T)); return b; }
+template <typename T> inline T from_bits(uint64_t b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
+}  // namespace emu
+
+inline void __syncthreads() { emu::sync_block(); }
+template <typename T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return emu::from_bits<T>(emu::warp_exchange(emu::to_bits(v), emu::lane_id() ^ lane_mask)); }
+template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return emu::from_bits<T>(emu::warp_exchange(emu::to_bits(v), src & 31)); }
+template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned d) { int l = emu::lane_id(); return emu::from_bits<T>(emu::warp_exchange(emu::to_bits(v), l >= (int)d ? l - (int)d : l)); }
+template <typename T> inline T __shfl_down_sync(unsigned, T v, unsigned d) { int l = emu::lane_id(); return emu::from_bits<T>(emu::warp_exchange(emu::to_bits(v), l + (int)d < 32 ? l + (int)d : l)); }
+
+template <typename T> inline T __ldg(const T* p) { return *p; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }            // fibers of a block never run concurrently
+inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
+inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; if (v > o) *p = v; return o; }
