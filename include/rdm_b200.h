@@ -173,7 +173,9 @@ RDM_API int rdm_ddim_step(const float* x_dev, const float* eps_dev, int64_t n_pe
  * "quantize.embedding.weight", "post_quant_conv.weight", ...).
  * ------------------------------------------------------------------------------------------------ */
 typedef struct rdm_vqdec_cfg {
-    int32_t embed_dim, n_embed;            /* codebook [n_embed, embed_dim], embed_dim <= 4 */
+    int32_t embed_dim, n_embed;            /* codebook [n_embed, embed_dim]; embed_dim and z_channels both <= 4 (ldm VQ-f4/f8), or both
+                                              multiples of 64 (taming VQGAN-f16 of the RARM models, models/rarm/imagenet/dogs/config.yaml:28-51:
+                                              decoded from codebook entries, i.e. quantize = 0 only) */
     int32_t z_channels, resolution, out_ch, ch, num_res_blocks;
     int32_t n_ch_mult; int32_t ch_mult[8];
     int32_t n_attn_resolutions; int32_t attn_resolutions[8];

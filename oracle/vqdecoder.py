@@ -132,3 +132,19 @@ def randomize_(m, seed):
             else:
                 p.copy_(0.05 * torch.randn(p.shape, generator=g))
     return m
+
+
+TAMING_VQ_F16 = dict(embed_dim=256, n_embed=16384, ddconfig=dict(double_z=False, z_channels=256, resolution=256, in_channels=3, out_ch=3, ch=128,
+                                                                  ch_mult=[1, 1, 2, 2, 4], num_res_blocks=2, attn_resolutions=[16], dropout=0.0))
+"""models/rarm/imagenet/dogs/config.yaml:28-51 (taming VQGAN-f16 of the RARM models: 16x16 codes of width 256 -> 256x256x3 image; same Decoder
+architecture as above, AttnBlocks after every ResnetBlock of the 16x16 level)."""
+TINY_VQ_WIDE = dict(embed_dim=64, n_embed=96, ddconfig=dict(double_z=False, z_channels=64, resolution=32, in_channels=3, out_ch=3, ch=64,
+                                                             ch_mult=[1, 2], num_res_blocks=1, attn_resolutions=[16], dropout=0.0))
+
+
+def decode_indices(model, indices, zshape):
+    """taming `Net2NetTransformer.decode_to_img` (called from rdm/models/autoregression/transformer.py:291-292) with the identity permuter:
+    codebook entries of the sampled ids, reshaped (b, h, w, c) -> NCHW, then post_quant_conv -> Decoder (no re-quantisation)."""
+    b, c, h, w = zshape
+    quant = model.quantize.embedding(indices.reshape(-1)).view(b, h, w, c).permute(0, 3, 1, 2).contiguous()
+    return model.decode(quant, force_not_quantize=True)

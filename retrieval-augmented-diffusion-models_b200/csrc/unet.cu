@@ -658,10 +658,25 @@ int dec_forward_impl(Net* n, const float* z_nchw, int B, int h, int w, int quant
       } }
     float* buf[2] = {A.allocf(big), A.allocf(big)};
     int H = h, W = w, cur = 0;
-    View z0 = fresh(cx, B * H * W, 4); z0.C = c.z_channels;
-    RUN(k_vq_quantize(z_nchw, B, c.embed_dim, H * W, n->codebook, c.n_embed, n->pq_w, n->pq_b, c.z_channels, quantize, z0, st));
     Act x{View(buf[cur], n->dec_conv_in.cout, n->dec_conv_in.cout), B, H, W};
-    gemm_any(cx, from_view(z0), B, H, W, c.z_channels, 3, 1, 0, n->dec_conv_in.w, n->dec_conv_in.b, n->dec_conv_in.cout, GemmEpi(), from_view(x.v));
+    if (c.embed_dim <= 4) {
+        View z0 = fresh(cx, B * H * W, 4); z0.C = c.z_channels;
+        RUN(k_vq_quantize(z_nchw, B, c.embed_dim, H * W, n->codebook, c.n_embed, n->pq_w, n->pq_b, c.z_channels, quantize, z0, st));
+        gemm_any(cx, from_view(z0), B, H, W, c.z_channels, 3, 1, 0, n->dec_conv_in.w, n->dec_conv_in.b, n->dec_conv_in.cout, GemmEpi(), from_view(x.v));
+    } else {
+        // wide latents (taming VQGAN-f16 of the RARM models: embed_dim = z_channels = 256): z already holds the codebook entries
+        // (`quantize.get_codebook_entry`, taming cond_transformer.decode_to_img), so post_quant_conv (1x1) and conv_in (3x3) are real GEMMs
+        const int M = B * H * W;
+        size_t mk = A.mark();
+        View zf = fresh(cx, M, c.embed_dim);
+        RUN(k_nchw_to_nhwc(z_nchw, B, B, c.embed_dim, H, W, zf, st));
+        Opnd za = fresh_opnd(cx, M, c.embed_dim, true);
+        RUN(k_split_planes(zf, M, za.out4(), st));
+        Opnd zq = fresh_opnd(cx, M, c.z_channels, true);
+        gemm_any(cx, za, B, H, W, c.embed_dim, 1, 1, 0, n->pq_w, n->pq_b, c.z_channels, GemmEpi(), zq);
+        gemm_any(cx, zq, B, H, W, c.z_channels, 3, 1, 0, n->dec_conv_in.w, n->dec_conv_in.b, n->dec_conv_in.cout, GemmEpi(), from_view(x.v));
+        A.release(mk);
+    }
     for (const DecLayer& L : n->dec_layers) {
         const int nxt = cur ^ 1;
         if (L.kind == D_RES) {
@@ -979,8 +994,10 @@ int rdm_vqdec_create(rdm_unet_t** out, const rdm_vqdec_cfg* cfg, int32_t device)
     RDM_REQUIRE(out && cfg, RDM_ERR_ARG, "rdm_vqdec_create: null argument");
     RDM_REQUIRE(cfg->n_ch_mult >= 1 && cfg->n_ch_mult <= 8 && cfg->n_attn_resolutions >= 0 && cfg->n_attn_resolutions <= 8, RDM_ERR_ARG, "rdm_vqdec_create: bad list sizes");
     RDM_REQUIRE(cfg->ch % 64 == 0, RDM_ERR_UNSUPPORTED, "rdm_vqdec_create: ch must be a multiple of 64 (GroupNorm32 + 64-wide K blocks), got %d", cfg->ch);
-    RDM_REQUIRE(cfg->embed_dim >= 1 && cfg->embed_dim <= 4 && cfg->z_channels >= 1 && cfg->z_channels <= 4 && cfg->out_ch >= 1 && cfg->out_ch <= 4,
-                RDM_ERR_UNSUPPORTED, "rdm_vqdec_create: embed_dim / z_channels / out_ch must be 1..4");
+    const bool narrow = cfg->embed_dim >= 1 && cfg->embed_dim <= 4 && cfg->z_channels >= 1 && cfg->z_channels <= 4;
+    const bool wide = cfg->embed_dim >= 64 && cfg->embed_dim % 64 == 0 && cfg->z_channels >= 64 && cfg->z_channels % 64 == 0;      // taming VQGAN (RARM): decode without quantisation only
+    RDM_REQUIRE((narrow || wide) && cfg->out_ch >= 1 && cfg->out_ch <= 4, RDM_ERR_UNSUPPORTED,
+                "rdm_vqdec_create: embed_dim / z_channels must both be 1..4 or both multiples of 64, out_ch 1..4 (got %d / %d / %d)", cfg->embed_dim, cfg->z_channels, cfg->out_ch);
     RDM_REQUIRE(cfg->n_embed >= 1 && cfg->num_res_blocks >= 1, RDM_ERR_ARG, "rdm_vqdec_create: n_embed / num_res_blocks");
     DeviceGuard guard(device);
     RDM_REQUIRE(guard.ok, RDM_ERR_CUDA, "rdm_vqdec_create: cannot select device %d", device);
@@ -1000,6 +1017,7 @@ int rdm_vqdec_decode(rdm_unet_t* n, const float* z, int32_t B, int32_t h, int32_
     RDM_REQUIRE(n->kind == 1, RDM_ERR_ARG, "rdm_vqdec_decode: this handle is not a VQ decoder");
     RDM_REQUIRE(mode_f16(n->mode), RDM_ERR_UNSUPPORTED, "rdm_vqdec_decode: the decoder runs in the fp16 tensor-core modes only (fp16x2 / fp16), mode is %d", n->mode);
     RDM_REQUIRE(B >= 1 && h >= 1 && w >= 1, RDM_ERR_ARG, "rdm_vqdec_decode: B=%d h=%d w=%d", B, h, w);
+    RDM_REQUIRE(n->dcfg.embed_dim <= 4 || quantize == 0, RDM_ERR_UNSUPPORTED, "rdm_vqdec_decode: wide codebooks (embed_dim %d) are decoded from codebook entries only (quantize = 0)", n->dcfg.embed_dim);
     for (auto& kv : n->params) RDM_REQUIRE(kv.second.loaded, RDM_ERR_STATE, "rdm_vqdec_decode: parameter '%s' was never loaded", kv.first.c_str());
     DeviceGuard guard(n->device);
     cudaStream_t st = (cudaStream_t)stream;

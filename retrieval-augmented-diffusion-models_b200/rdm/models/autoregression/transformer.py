@@ -1,7 +1,8 @@
 """`rdm.models.autoregression.transformer.LatentImageRETRO` -- the sampling side of the reference's RARM model
 (`rdm/models/autoregression/transformer.py:122-391`; base classes `LatentCrossTransformer` :24-119 and taming's
 `Net2NetTransformer`, which is not vendored: the pieces used when sampling -- the SOS conditioning of `__is_unconditional__` models,
-`top_k_logits`, `decode_to_img` -- are restated from the published taming-transformers source).
+`top_k_logits`, `decode_to_img` -- are restated from the published taming-transformers source; the VQGAN-f16 first stage is
+`shims/taming/models/vqgan.py` over the device decoder when taming itself is not installed).
 
 `sample` (:224-270) runs on the device decoder of librdm_b200 (csrc/rarm.cu): key/value caches instead of re-evaluating the growing
 prefix, guidance on the logits, top-k filter and the draw fused into one kernel, one CUDA-graph replay per position.  The draw uses
@@ -135,7 +136,7 @@ class LatentImageRETRO(nn.Module):
     @torch.no_grad()
     def decode_to_img(self, index, zshape):
         if self.first_stage_model is None:
-            raise NotImplementedError("the taming VQGAN first stage is not available here (next: SURVEY.md section 8f-2, VQGAN-f16 decode)")
+            raise NotImplementedError("this model was built without a first stage (first_stage_config missing or not importable)")
         bhwc = (zshape[0], zshape[2], zshape[3], zshape[1])
         quant_z = self.first_stage_model.quantize.get_codebook_entry(index.reshape(-1), shape=bhwc)
         return self.first_stage_model.decode(quant_z)

@@ -7,7 +7,7 @@ SHIMS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def install_shims():
-    missing = [m for m in ("ldm", "omegaconf", "pytorch_lightning", "clip") if importlib.util.find_spec(m) is None]
+    missing = [m for m in ("ldm", "omegaconf", "pytorch_lightning", "clip", "taming") if importlib.util.find_spec(m) is None]
     if missing and SHIMS not in sys.path:
         sys.path.append(SHIMS)          # appended: a real installation always wins
     return missing

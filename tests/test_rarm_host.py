@@ -120,3 +120,30 @@ def test_get_qids_follows_numpy_global_rng():
     f = np.asarray([m.id_count[int(i)] for i in mem])
     np.random.seed(4)
     assert np.array_equal(got, np.random.choice(mem, size=6, p=f / f.sum(keepdims=True)))
+
+
+def test_first_stage_in_the_taming_layout_decodes_the_sampled_ids():
+    """models/rarm/imagenet/*/config.yaml:28-51 at reduced widths: `first_stage_config.target: taming.models.vqgan.VQModel` resolves (to the
+    stand-in when taming is not installed), loads a checkpoint in the taming key layout, and `decode_to_img` == the oracle's restatement of
+    taming's `decode_to_img` (codebook entries -> post_quant_conv -> Decoder).  CPU tensors: eager parameter containers."""
+    from oracle import vqdecoder as ovq
+    vq = ovq.TINY_VQ_WIDE
+    dd = dict(vq["ddconfig"], resolution=8)
+    cfg = model_cfg(dict(SMALL, sequence_length=16))
+    cfg["first_stage_config"] = {"target": "taming.models.vqgan.VQModel",
+                                 "params": dict(embed_dim=vq["embed_dim"], n_embed=vq["n_embed"], ddconfig=dd, lossconfig={"target": "torch.nn.Identity"})}
+    m = LatentImageRETRO(**cfg).eval()
+    fs = ovq.randomize_(ovq.VQModelInterface(embed_dim=vq["embed_dim"], n_embed=vq["n_embed"], ddconfig=dd), 34).eval()
+    sd = {"first_stage_model." + k: v for k, v in fs.state_dict().items()}
+    sd.update({k: v for k, v in m.state_dict().items() if not k.startswith("first_stage_model.")})
+    missing, unexpected = m.load_state_dict(sd, strict=True)                  # the notebook loads strictly (demo_rarm.ipynb cell 5)
+    assert not missing and not unexpected
+    tsd = {k: v for k, v in m.transformer.state_dict().items()}
+    m.transformer.engine = lambda device: OracleEngine(tsd, SMALL["n_heads"])
+    torch.manual_seed(1)
+    r = torch.randn(2, 4, SMALL["context_dim"])
+    out = m.sample_from_rdata(2, nn_embeddings=r, k_nn=4, top_k=12, guidance_scale=2.0, code_side_len=4, z_dimensionality=vq["embed_dim"])
+    ids, img = out["sampled_indices"], out["samples_with_sampled_nns"]
+    assert ids.shape == (2, 16) and img.shape == (2, 3, 8, 8)
+    with torch.no_grad():
+        assert torch.equal(img, ovq.decode_indices(fs, ids, (2, vq["embed_dim"], 4, 4)))

@@ -139,3 +139,74 @@ def test_imagenet_size_decoder_against_oracle(cuda):
     net.set_context(r)
     b = net.sample(tok[:, :1], 256, temperature=1.0, top_k=256, guidance_scale=2.0, uniforms=u)
     assert a.shape == (2, 257) and torch.equal(a, b) and 0 <= int(a[:, 1:].min()) and int(a[:, 1:].max()) < 16384
+
+
+# ---- first stage of the RARM models: taming VQGAN-f16 decode of the sampled ids (wide-latent path of the device decoder) -------------
+@pytest.mark.parametrize("mode,tol", [(3, 3e-3), (4, 6e-3)])
+def test_wide_latent_decoder_small(cuda, mode, tol):
+    """embed_dim = z_channels = 64, AttnBlocks inside the lowest up level (attn_resolutions = [16]) as in the taming VQGAN-f16."""
+    from oracle import vqdecoder as ovq
+    from rdm_b200.vqdecoder import B200VQDecoder
+    cfg = ovq.TINY_VQ_WIDE
+    ref = ovq.randomize_(ovq.VQModelInterface(**cfg), 7).eval()
+    dec = B200VQDecoder(cuda, cfg["embed_dim"], cfg["n_embed"], cfg["ddconfig"])
+    assert sorted(dec.names) == sorted(ref.state_dict().keys())
+    dec.load_state_dict(ref.state_dict())
+    dec.set_mode(mode)
+    idx = torch.randint(0, cfg["n_embed"], (2, 16 * 16), generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        want = ovq.decode_indices(ref, idx, (2, 64, 16, 16))
+    quant = ref.quantize.embedding.weight.detach()[idx].view(2, 16, 16, 64).permute(0, 3, 1, 2).contiguous()
+    got = dec.decode(quant.to(cuda), force_not_quantize=True)
+    again = dec.decode(quant.to(cuda), force_not_quantize=True)               # CUDA-graph replay
+    assert got.shape == want.shape == (2, 3, 32, 32)
+    assert rel(got, want) < tol and rel(again, want) < tol
+    with pytest.raises(RuntimeError, match="quantize"):
+        dec.decode(quant.to(cuda))                                             # nearest-codebook search is not part of the sampling path
+
+
+def test_latent_image_retro_samples_and_decodes_on_the_device(cuda):
+    """scripts/rarm_sample.py end to end at reduced widths: YAML-style config -> LatentImageRETRO -> sample_from_rdata (given neighbour
+    embeddings) -> 64 sampled ids per image (8 x 8 codes) -> taming-layout first stage -> images; the ids are checked token by token against the oracle."""
+    import rdm  # noqa: F401
+    from ldm.util import instantiate_from_config
+    from omegaconf import OmegaConf
+    from oracle import vqdecoder as ovq
+    tcfg = dict(in_channels=98, n_heads=2, d_head=64, depth=2, context_dim=128, positional_encodings=True, sequence_length=64, out_channels=96,
+                cross_attend=True, causal=True, continuous=False)
+    vq = ovq.TINY_VQ_WIDE
+    cfg = {"target": "rdm.models.autoregression.transformer.LatentImageRETRO",
+           "params": dict(mask_token=96, sos_token=97, p_mask_max=0.0, nn_key="nn_embeddings",
+                          nn_reshaper_cfg={"target": "rdm.modules.encoders.nn_encoders.CLIPEmbeddingReshaper"},
+                          nn_encoder_cfg={"target": "rdm.modules.encoders.nn_encoders.IdentityEncoder"},
+                          transformer_config={"target": "rdm.modules.attention.RetrievalPatchTransformer", "params": tcfg},
+                          first_stage_config={"target": "taming.models.vqgan.VQModel",
+                                              "params": dict(embed_dim=vq["embed_dim"], n_embed=vq["n_embed"], ddconfig=dict(vq["ddconfig"], resolution=16),
+                                                             lossconfig={"target": "torch.nn.Identity"})},
+                          retrieval_cfg=None, cond_stage_config="__is_unconditional__")}
+    model = instantiate_from_config(OmegaConf.create(cfg)).eval()
+    sd = ref_weights.state_dict_for(((k, v.shape) for k, v in model.transformer.state_dict().items()), 33)
+    model.transformer.load_state_dict(sd)
+    model.transformer.engine_mode = "fp32"
+    fs = ovq.randomize_(ovq.VQModelInterface(embed_dim=vq["embed_dim"], n_embed=vq["n_embed"], ddconfig=dict(vq["ddconfig"], resolution=16)), 34).eval()
+    model.first_stage_model.load_state_dict(fs.state_dict())
+    model = model.to(cuda)
+    g = torch.Generator().manual_seed(35)
+    r = torch.randn(2, 4, 128, generator=g)
+    torch.manual_seed(36)
+    out = model.sample_from_rdata(2, nn_embeddings=r.to(cuda), k_nn=4, top_k=12, temperature=1.0, guidance_scale=2.0, code_side_len=8, z_dimensionality=64)
+    ids, img = out["sampled_indices"].cpu(), out["samples_with_sampled_nns"]
+    assert ids.shape == (2, 64) and img.shape == (2, 3, 16, 16) and int(ids.max()) < 96
+    torch.manual_seed(36)
+    u = torch.rand((64, 2), device=cuda).cpu()                                # the uniforms LatentImageRETRO.sample drew
+    c = torch.full((2, 1), 97)
+    full = torch.cat([c, ids], 1)
+    lc = orarm.forward(sd, full[:, :-1], r, 2)
+    lu = orarm.forward(sd, full[:, :-1], torch.zeros_like(r), 2)
+    for t in range(64):
+        p = orarm.step_probs(lc[:, t], lu[:, t], 2.0, 1.0, 12)
+        for b in range(2):
+            assert consistent_with_uniform(p[b], int(ids[b, t]), float(u[t, b]), 1e-4), (t, b)
+    with torch.no_grad():
+        want = ovq.decode_indices(fs, ids, (2, 64, 8, 8))
+    assert rel(img, want) < 5e-3
