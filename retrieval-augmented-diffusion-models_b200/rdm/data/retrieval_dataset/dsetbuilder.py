@@ -138,8 +138,6 @@ class DatasetBuilder(object):
             return
         emb = self.data_pool['embedding']
         assert len(emb) > 0, "no embeddings loaded"
-        if device is None:
-            device = torch.device("cuda", torch.cuda.current_device())
         n, base = emb.shape[0], 0
         dist_on = self._dist_world() > 1
         if dist_on and self._row_base is not None:
@@ -150,7 +148,7 @@ class DatasetBuilder(object):
             emb = emb[base:end]
         local = B200Searcher(emb, device=device, idx_base=base)
         self.searcher = ShardedSearcher(local) if dist_on else local
-        print(f'Finish training searcher: {emb.shape[0]:,} rows resident on {device} (exact cosine top-k)')
+        print(f'Finish training searcher: {emb.shape[0]:,} rows resident on {local.device} (exact cosine top-k)')
 
     def search_k_nearest(self, queries, k=None, is_caption=False, visualize=None, query_embedded=False):
         assert self.searcher is not None, 'Cannot search with uninitialized searcher'

@@ -20,6 +20,7 @@ import torch.nn as nn
 from ldm.util import instantiate_from_config
 
 from rdm.modules.encoders.nn_encoders import IdentityEncoder
+from rdm.util import SampleLogs
 
 
 def disabled_train(self, mode=True):
@@ -171,7 +172,7 @@ class LatentImageRETRO(nn.Module):
             raise NotImplementedError("neighbour image patches / VQ neighbour encoders need the patch dataset, which is outside the sampling hot path")
         if k_nn is None:
             k_nn = self.k_nn
-        out = {}
+        out = SampleLogs()
         if nn_embeddings is None:
             searcher = self._searcher()
             if query_embeddings is None:
@@ -183,7 +184,7 @@ class LatentImageRETRO(nn.Module):
             qh = (q / q.norm(dim=1, keepdim=True)).contiguous()                                                           # :328
             nns, _ = searcher.search_device(qh, k_nn)                                                                      # :327-329
             retro_cond = searcher.gather_device(nns)                                                                       # :342
-            out["nns"] = nns
+            out.extras["nns"] = nns
         else:
             retro_cond = nn_embeddings.to(self.device, torch.float32)
         _, c = self.encode_to_c(torch.zeros((N, 0)))                            # SOSProvider conditioning (:377-379)
@@ -192,7 +193,7 @@ class LatentImageRETRO(nn.Module):
         steps = code_side_len ** 2
         z_start = torch.zeros((N, 0), device=retro_cond.device, dtype=torch.long)
         out["samples_with_sampled_nns"] = self.sampling_util(steps, z_start, retro_cond, c, temperature, top_k, z_shape, **kwargs)
-        out["sampled_indices"] = self.last_index_sample
+        out.extras["sampled_indices"] = self.last_index_sample
         return out
 
     def get_qids(self, memsize, N, qids=None, use_weights=False, verbose=False):

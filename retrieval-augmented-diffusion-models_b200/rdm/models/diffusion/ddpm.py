@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from ldm.util import instantiate_from_config
 from rdm.models.diffusion.ddim import DDIMSampler
-from rdm.util import ischannellastimage, isimage
+from rdm.util import SampleLogs, ischannellastimage, isimage
 from rdm_b200 import sampler as _tables
 
 
@@ -288,14 +288,14 @@ class MinimalRETRODiffusion(nn.Module):
         searcher = self._searcher()
         k_nn = self.k_nn if k_nn is None else k_nn
         qids = self.get_qids(memsize, N, qids=qids, use_weights=use_weights, verbose=verbose)
-        out = {}
+        out = SampleLogs()
         qd = torch.as_tensor(np.asarray(qids), dtype=torch.int64, device=self.device)
         if nn_embeddings is None:
             q = searcher.gather_device(qd)                                     # data_pool['embedding'][qids]      ddpm.py:897
             qh = q / q.norm(dim=1, keepdim=True)                               # q / ||q||                          ddpm.py:907
             nns, _ = searcher.search_device(qh, k_nn)                          # searcher.search_batched(...)       ddpm.py:906-908
             retro_cond = searcher.gather_device(nns)                           # data_pool['embedding'][nns] fp32   ddpm.py:921
-            out['nns'] = nns
+            out.extras['nns'] = nns
         else:
             retro_cond = nn_embeddings.to(self.device, torch.float32)
         if return_nns:
@@ -306,7 +306,7 @@ class MinimalRETRODiffusion(nn.Module):
             samples, _ = self.sample_log(cond=c, batch_size=N, unconditional_guidance_scale=unconditional_guidance_scale,
                                          unconditional_conditioning=uc.to(self.device), **kwargs)
         out["samples_with_sampled_nns"] = self.decode_first_stage(samples)
-        out["latents"] = samples
+        out.extras["latents"] = samples
         return out
 
     @torch.no_grad()
@@ -344,7 +344,8 @@ class MinimalRETRODiffusion(nn.Module):
             retro_cond = torch.cat([q_emb[:, None], r_emb[:, :k_nn - 1]], dim=1)            # ddpm.py:775
         if n_reps is not None:
             retro_cond = torch.cat([retro_cond] * n_reps, dim=1)
-        out = {'nns': nns}
+        out = SampleLogs()
+        out.extras['nns'] = nns
         if return_nns:
             raise NotImplementedError("return_nns needs the image patch dataset, which is outside the sampling hot path")
         c = self.retrieval_encoder(retro_cond.float())
@@ -356,7 +357,7 @@ class MinimalRETRODiffusion(nn.Module):
             samples, _ = self.sample_log(cond=c, batch_size=c.shape[0], unconditional_guidance_scale=unconditional_guidance_scale,
                                          unconditional_conditioning=uc.to(self.device), **kwargs)
         out["query_samples"] = self.decode_first_stage(samples)
-        out["latents"] = samples
+        out.extras["latents"] = samples
         return out
 
     @torch.no_grad()
