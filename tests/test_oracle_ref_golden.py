@@ -1,7 +1,7 @@
 """The oracle against outputs of the REFERENCE's own code (tests/golden/ref_*.npz, written by tests/golden/make_golden_ref.py from
 /root/reference in the build container): U-Net forward (openaimodel.py + attention.py), the DDIM loop with classifier-free guidance
 (ddim.py) and the state-dict key layout.  This is what pins oracle/unet.py and oracle/ddim.py; the GPU tests then hold
-the CUDA path to the same files (tests/test_ref_golden_gpu.py)."""
+the CUDA path to the same files (tests/test_zy_ref_golden_gpu.py)."""
 import ast
 import os
 import sys
