@@ -71,3 +71,22 @@ def test_knn_sharding_is_result_invariant():
         parts.append((i, sc))
     mi, ms = knn.merge_shards(parts, 4)
     assert (mi == full[0]).all() and (ms == full[2]).all()
+
+
+def test_knn_oracle_agrees_with_an_independent_exact_searcher():
+    """ScaNN (the reference's searcher, scann==1.2.4) is not installable here, so the exact semantics it approximates are checked against an
+    independent third-party implementation instead: scikit-learn's brute-force cosine NearestNeighbors on the raw rows.  On tie-free data
+    the neighbour lists must be identical and the reported dot products equal 1 - cosine distance."""
+    import pytest
+    sklearn_neighbors = pytest.importorskip("sklearn.neighbors")
+    rng = np.random.default_rng(12)
+    db = (rng.standard_normal((20_000, 512)) * rng.uniform(0.3, 9.0, (20_000, 1))).astype(np.float16)      # raw rows with very different norms
+    q = rng.standard_normal((37, 512)).astype(np.float32)
+    q[:5] = db[[3, 777, 4096, 19_999, 12_345]].astype(np.float32)                                         # DB rows as queries (ddpm.py:897)
+    qh = knn.normalize_queries(q)
+    idx, dist = knn.search(db, qh, 20)
+    nn = sklearn_neighbors.NearestNeighbors(n_neighbors=20, algorithm="brute", metric="cosine").fit(db.astype(np.float64))
+    d_sk, i_sk = nn.kneighbors(q.astype(np.float64))
+    assert np.array_equal(idx, i_sk)
+    assert np.allclose(dist, 1.0 - d_sk, atol=2e-6)
+    assert list(idx[:5, 0]) == [3, 777, 4096, 19_999, 12_345] and np.allclose(dist[:5, 0], 1.0, atol=1e-6)
