@@ -41,3 +41,11 @@ def make_db(n=600):
     db = (tensor_for("db.embedding", (n, 512), 41) * np.float32(22.0) * scale).astype(np.float16)
     mem = np.random.RandomState(42).permutation(n)[:200].astype(np.int64)
     return db, mem, {int(i): int(1 + (7 * i) % 13) for i in mem}
+
+
+def round_dense_weights_to_fp16(sd):
+    """The RARM executor's fp16 mode keeps every dense-layer weight matrix in fp16 (embedding table, positional encoding, biases and norms
+    stay fp32, accumulation is fp32): the same state dict with exactly those tensors rounded, for a tight comparison of that mode."""
+    import torch
+    dense = (".to_q.weight", ".to_k.weight", ".to_v.weight", ".to_out.0.weight", ".ff.net.0.proj.weight", ".ff.net.2.weight")
+    return {k: (v.to(torch.float16).to(torch.float32) if (k.endswith(dense) or k == "proj_out.weight") else v) for k, v in sd.items()}
