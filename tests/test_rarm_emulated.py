@@ -161,3 +161,14 @@ def test_errors_are_reported(emu_cls):
     fresh = emu_cls("cpu", **cfg)
     with pytest.raises(RuntimeError, match="not loaded"):
         fresh.set_context(torch.zeros(2, 3, cfg["context_dim"]))
+
+
+def test_gpu_test_bodies_run_under_emulation(emu_cls, monkeypatch):
+    """The GPU parity tests of tests/test_zz_rarm_gpu.py, executed as they are against the emulated library (device "cpu"): keeps the
+    GPU test file itself honest -- its helpers, shapes, tolerances and oracle calls -- in a container that cannot run it on hardware."""
+    import rdm_b200.rarm as rr
+    import test_zz_rarm_gpu as gpu_tests
+    monkeypatch.setattr(rr, "B200Rarm", emu_cls)
+    gpu_tests.test_cached_logits_match_reference_code("cpu", 4, 5e-3)
+    gpu_tests.test_guided_topk_draw_kernel_matches_oracle("cpu", 16384, 256, True)
+    gpu_tests.test_sampling_loop_token_by_token("cpu", 4, 2.0)
