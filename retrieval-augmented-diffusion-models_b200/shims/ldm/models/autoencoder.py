@@ -1,7 +1,7 @@
 """`ldm.models.autoencoder.VQModelInterface` stand-in: the DECODE side only (quantise -> post_quant_conv -> Decoder), as
 described in SURVEY.md Appendix A, so `decode_first_stage` (ddpm.py:840,981) returns images for the unchanged sampling scripts.
-The nn.Modules below are the parameter containers (checkpoint key layout); on a CUDA tensor `decode` runs the hand-written
-decoder of librdm_b200 (`rdm_b200.vqdecoder.B200VQDecoder`) -- the eager PyTorch forward only serves CPU tensors.  Module names follow the latent-diffusion checkpoint layout (`first_stage_model.decoder.*`,
+The nn.Modules below are parameter containers only (checkpoint key layout, no forward); `decode` runs the hand-written
+decoder of librdm_b200 (`rdm_b200.vqdecoder.B200VQDecoder`) and raises for tensors that are not on a CUDA device.  Module names follow the latent-diffusion checkpoint layout (`first_stage_model.decoder.*`,
 `first_stage_model.quantize.embedding.weight`, `first_stage_model.post_quant_conv.*`)."""
 import torch
 import torch.nn as nn
@@ -21,10 +21,6 @@ class ResnetBlock(nn.Module):
             self.nin_shortcut = nn.Conv2d(cin, cout, 1)
         self.cin, self.cout = cin, cout
 
-    def forward(self, x):
-        h = self.conv1(F.silu(self.norm1(x)))
-        h = self.conv2(F.silu(self.norm2(h)))
-        return (self.nin_shortcut(x) if self.cin != self.cout else x) + h
 
 
 class AttnBlock(nn.Module):
@@ -33,12 +29,6 @@ class AttnBlock(nn.Module):
         self.norm = _norm(c)
         self.q, self.k, self.v, self.proj_out = (nn.Conv2d(c, c, 1) for _ in range(4))
 
-    def forward(self, x):
-        b, c, h, w = x.shape
-        n = self.norm(x)
-        q, k, v = self.q(n).reshape(b, c, h * w), self.k(n).reshape(b, c, h * w), self.v(n).reshape(b, c, h * w)
-        o = F.scaled_dot_product_attention(q.transpose(1, 2)[:, None], k.transpose(1, 2)[:, None], v.transpose(1, 2)[:, None])[:, 0]
-        return x + self.proj_out(o.transpose(1, 2).reshape(b, c, h, w))
 
 
 class Upsample(nn.Module):
@@ -46,8 +36,6 @@ class Upsample(nn.Module):
         super().__init__()
         self.conv = nn.Conv2d(c, c, 3, padding=1)
 
-    def forward(self, x):
-        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
 
 
 class Decoder(nn.Module):
@@ -71,16 +59,6 @@ class Decoder(nn.Module):
             self.up.insert(0, up)
         self.norm_out, self.conv_out = _norm(block_in), nn.Conv2d(block_in, out_ch, 3, padding=1)
 
-    def forward(self, z):
-        h = self.mid.block_2(self.mid.attn_1(self.mid.block_1(self.conv_in(z))))
-        for i_level in reversed(range(self.num_resolutions)):
-            for i_block in range(self.num_res_blocks + 1):
-                h = self.up[i_level].block[i_block](h)
-                if len(self.up[i_level].attn) > 0:
-                    h = self.up[i_level].attn[i_block](h)
-            if i_level != 0:
-                h = self.up[i_level].upsample(h)
-        return self.conv_out(F.silu(self.norm_out(h)))
 
 
 class VectorQuantizer(nn.Module):
@@ -119,7 +97,6 @@ class VQModelInterface(nn.Module):
         return self._b200_dec
 
     def decode(self, h, force_not_quantize=False):
-        if h.is_cuda:
-            return self._b200(h.device).decode(h, force_not_quantize)
-        quant = h if force_not_quantize else self.quantize(h)[0]
-        return self.decoder(self.post_quant_conv(quant))
+        if not h.is_cuda:
+            raise RuntimeError("the first-stage decoder (B200 build) has no CPU path: move the model and the latents to a CUDA device")
+        return self._b200(h.device).decode(h, force_not_quantize)

@@ -4,8 +4,8 @@
 `post_quant_conv` -> `Decoder`.  taming-transformers is not vendored by the reference; the decoder architecture is the one
 latent-diffusion inherited from it, so the parameter containers of the `ldm` stand-in are reused (same checkpoint key layout:
 `first_stage_model.decoder.*`, `first_stage_model.quantize.embedding.weight`, `first_stage_model.post_quant_conv.*`).
-On a CUDA tensor `decode` runs the hand-written decoder of librdm_b200 (wide-latent path of csrc/unet.cu); the eager PyTorch
-forward only serves CPU tensors.  Appended to sys.path only when the real package is missing (rdm_b200/compat.py)."""
+`decode` runs the hand-written decoder of librdm_b200 (wide-latent path of csrc/unet.cu) and raises for tensors that are not on a
+CUDA device.  Appended to sys.path only when the real package is missing (rdm_b200/compat.py)."""
 import torch.nn as nn
 
 from ldm.models.autoencoder import Decoder, VQModelInterface

@@ -122,10 +122,10 @@ def test_get_qids_follows_numpy_global_rng():
     assert np.array_equal(got, np.random.choice(mem, size=6, p=f / f.sum(keepdims=True)))
 
 
-def test_first_stage_in_the_taming_layout_decodes_the_sampled_ids():
+def test_first_stage_in_the_taming_layout_decodes_the_sampled_ids(monkeypatch):
     """models/rarm/imagenet/*/config.yaml:28-51 at reduced widths: `first_stage_config.target: taming.models.vqgan.VQModel` resolves (to the
     stand-in when taming is not installed), loads a checkpoint in the taming key layout, and `decode_to_img` == the oracle's restatement of
-    taming's `decode_to_img` (codebook entries -> post_quant_conv -> Decoder).  CPU tensors: eager parameter containers."""
+    taming's `decode_to_img` (codebook entries -> post_quant_conv -> Decoder); the device decoder is replaced by the oracle's (no GPU here)."""
     from oracle import vqdecoder as ovq
     vq = ovq.TINY_VQ_WIDE
     dd = dict(vq["ddconfig"], resolution=8)
@@ -133,6 +133,16 @@ def test_first_stage_in_the_taming_layout_decodes_the_sampled_ids():
     cfg["first_stage_config"] = {"target": "taming.models.vqgan.VQModel",
                                  "params": dict(embed_dim=vq["embed_dim"], n_embed=vq["n_embed"], ddconfig=dd, lossconfig={"target": "torch.nn.Identity"})}
     m = LatentImageRETRO(**cfg).eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):                    # the product's first stage only runs on the device
+        m.decode_to_img(torch.zeros(1, 16, dtype=torch.long), (1, vq["embed_dim"], 4, 4))
+    from ldm.models.autoencoder import VQModelInterface
+
+    def first_stage_decode(self, h, force_not_quantize=False):                 # stand-in for the device decoder: the oracle's
+        ref = ovq.VQModelInterface(self.embed_dim, self.quantize.embedding.num_embeddings, self._ddconfig).eval()
+        ref.load_state_dict(self.state_dict())
+        with torch.no_grad():
+            return ref.decode(h, force_not_quantize)
+    monkeypatch.setattr(VQModelInterface, "decode", first_stage_decode)
     fs = ovq.randomize_(ovq.VQModelInterface(embed_dim=vq["embed_dim"], n_embed=vq["n_embed"], ddconfig=dd), 34).eval()
     sd = {"first_stage_model." + k: v for k, v in fs.state_dict().items()}
     sd.update({k: v for k, v in m.state_dict().items() if not k.startswith("first_stage_model.")})

@@ -1,7 +1,7 @@
 """CPU: the reference's OWN sampling scripts, unchanged (`/root/reference/scripts/rdm_sample.py`, `scripts/rarm_sample.py`), run against the
 drop-in packages of this repository: `parse_args` -> `load_model` (the SHIPPED `models/**/config.yaml` with sizes reduced, a synthetic
 Lightning checkpoint in the reference's key layout, `load_state_dict(strict=False)`, `.eval()`) -> `sample_unconditional` /
-`sample_conditional` / `sample` -> PNG files.  The three device executors (searcher, U-Net engine, RARM decoder) are replaced by
+`sample_conditional` / `sample` -> PNG files.  The device executors (searcher, U-Net engine, RARM decoder, first-stage decoder) are replaced by
 oracle-backed stand-ins with the same call surface, because this container has no GPU; everything else -- configuration handling,
 class resolution through the YAML `target:` strings, checkpoint loading, conditioning assembly, the sampler, the first-stage
 containers, the returned dictionaries the scripts iterate -- is the product's host code.  Skipped where /root/reference is absent
@@ -111,6 +111,14 @@ def cpu_executors(monkeypatch):
         return eng
     monkeypatch.setattr(UNetModel, "set_context", unet_set_context)
     monkeypatch.setattr(RetrievalPatchTransformer, "engine", lambda self, device: CpuRarmEngine(self.state_dict(), self._cfg["n_heads"]))
+    from ldm.models.autoencoder import VQModelInterface
+
+    def first_stage_decode(self, h, force_not_quantize=False):                 # rdm_b200.vqdecoder.B200VQDecoder's role, by the oracle decoder
+        ref = ovq.VQModelInterface(self.embed_dim, self.quantize.embedding.num_embeddings, self._ddconfig).eval()
+        ref.load_state_dict(self.state_dict())
+        with torch.no_grad():
+            return ref.decode(h, force_not_quantize)
+    monkeypatch.setattr(VQModelInterface, "decode", first_stage_decode)
 
 
 def make_db(tmp_path, n=400):
