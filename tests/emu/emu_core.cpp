@@ -7,6 +7,7 @@ thread_local dim3 blockDim(1), gridDim(1);
 
 namespace emu {
 
+void check_device_guards(const char* when);
 thread_local void* dyn_smem = nullptr;
 
 namespace {
@@ -51,7 +52,7 @@ void run_block(const std::function<void()>& body, dim3 grid, dim3 block, uint3 b
     const int n = (int)(block.x * block.y * block.z);
     if (!t_stacks) t_stacks = new std::vector<char*>();
     while ((int)t_stacks->size() < n) t_stacks->push_back((char*)aligned_alloc(64, STACK_BYTES));
-    std::vector<char> shared(smem + 64);
+    std::vector<char> shared(smem + 64 + 64, (char)0x5A);                      // 64-byte guard after the dynamic shared memory of the block
     dyn_smem = (void*)(((uintptr_t)shared.data() + 63) & ~(uintptr_t)63);
     BlockRun run;
     run.fibers.resize(n); run.warps.resize((n + 31) / 32); run.live = n; run.body = &body;
@@ -78,6 +79,8 @@ void run_block(const std::function<void()>& body, dim3 grid, dim3 block, uint3 b
         if (!progressed && ++idle_rounds > 2) { fprintf(stderr, "emu: deadlock in block (%u,%u,%u): %d live threads, none runnable (divergent barrier?)\n", bidx.x, bidx.y, bidx.z, run.live); abort(); }
         if (progressed) idle_rounds = 0;
     }
+    for (int i = 0; i < 64; i++)
+        if (((const char*)dyn_smem)[smem + i] != (char)0x5A) { fprintf(stderr, "emu: write past the %zu bytes of dynamic shared memory in block (%u,%u,%u)\n", smem, bidx.x, bidx.y, bidx.z); abort(); }
     t_run = nullptr; dyn_smem = nullptr;
 }
 
@@ -132,18 +135,55 @@ void run_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, std::function<
             run_block(body, grid, block, bidx, smem);
         }
     };
-    if (nw <= 1) { worker(); return; }
-    std::vector<std::thread> ts;
-    for (int i = 0; i < nw; i++) ts.emplace_back(worker);
-    for (auto& t : ts) t.join();
+    if (nw <= 1) worker();
+    else {
+        std::vector<std::thread> ts;
+        for (int i = 0; i < nw; i++) ts.emplace_back(worker);
+        for (auto& t : ts) t.join();
+    }
+    check_device_guards("after a kernel launch");
 }
 
 }  // namespace emu
 
 // ---- runtime API -------------------------------------------------------------------------------------------------------
 struct EmuStream { int id; };
-cudaError_t cudaMalloc(void** p, size_t bytes) { *p = aligned_alloc(256, (bytes + 255) & ~(size_t)255); if (*p) memset(*p, 0xCD, bytes); return *p ? cudaSuccess : cudaErrorEmu; }   // poisoned like fresh device memory is arbitrary
-cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+// "Device" allocations carry a 256-byte guard zone on both sides; every launch ends with a check that no kernel wrote into one
+// (an out-of-bounds WRITE aborts with the allocation size; out-of-bounds reads are not detected).
+namespace {
+constexpr size_t GUARD = 256;
+constexpr unsigned char GUARD_BYTE = 0xA5;
+struct Alloc { char* raw; size_t bytes; };
+std::mutex g_alloc_mu;
+std::vector<Alloc> g_allocs;
+void check_guards(const char* when) {
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    for (const Alloc& a : g_allocs) {
+        for (size_t i = 0; i < GUARD; i++) {
+            if ((unsigned char)a.raw[i] != GUARD_BYTE || (unsigned char)a.raw[GUARD + a.bytes + i] != GUARD_BYTE) {
+                fprintf(stderr, "emu: out-of-bounds write %s a %zu-byte device allocation (detected %s)\n", (unsigned char)a.raw[i] != GUARD_BYTE ? "before" : "after", a.bytes, when);
+                abort();
+            }
+        }
+    }
+}
+}  // namespace
+namespace emu { void check_device_guards(const char* when) { check_guards(when); } }
+cudaError_t cudaMalloc(void** p, size_t bytes) {
+    char* raw = (char*)aligned_alloc(256, ((bytes + 255) & ~(size_t)255) + 2 * GUARD);
+    if (!raw) return cudaErrorEmu;
+    memset(raw, GUARD_BYTE, GUARD); memset(raw + GUARD, 0xCD, bytes); memset(raw + GUARD + bytes, GUARD_BYTE, GUARD);      // payload poisoned: fresh device memory is arbitrary
+    { std::lock_guard<std::mutex> lk(g_alloc_mu); g_allocs.push_back({raw, bytes}); }
+    *p = raw + GUARD;
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void* p) {
+    if (!p) return cudaSuccess;
+    check_guards("at cudaFree");
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    for (size_t i = 0; i < g_allocs.size(); i++) if (g_allocs[i].raw + GUARD == (char*)p) { free(g_allocs[i].raw); g_allocs.erase(g_allocs.begin() + i); return cudaSuccess; }
+    fprintf(stderr, "emu: cudaFree of an unknown pointer\n"); abort();
+}
 cudaError_t cudaMemset(void* p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t bytes, cudaMemcpyKind) { memmove(d, s, bytes); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(d, s, bytes); return cudaSuccess; }
