@@ -84,3 +84,53 @@ def test_shard_ranges_cover_the_database():
         for w in (1, 2, 4, 8):
             r = [shard_range(n, i, w) for i in range(w)]
             assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+
+
+def _builder_worker(rank, world, port, q, dbdir):
+    """DatasetBuilder(shard=True) under a real process group: each rank reads only its rows of the multi-part database, the sharded
+    searcher exchanges (idx, score) lists, search_k_nearest returns the same dictionary as an unsharded search on every rank."""
+    import sys
+    sys.path[:0] = [ROOT, PKG]
+    import torch.distributed as dist
+    from oracle import knn as oknn
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import rdm  # noqa: F401
+    import rdm.data.retrieval_dataset.dsetbuilder as dsb
+    import rdm_b200.knn as bknn
+    dsb.B200Searcher = lambda emb, device=None, idx_base=0: OracleLocalSearcher(np.ascontiguousarray(emb), idx_base)      # stand-in for the device scan
+    bknn.merge_device = cpu_merge                                                                                        # stand-in for rdm_knn_merge
+    full = np.concatenate([np.load(os.path.join(dbdir, f))["embedding"] for f in sorted(os.listdir(dbdir))])
+    b = dsb.DatasetBuilder(retriever_config=None, saved_embeddings=dbdir, load_patch_dataset=False, gpu=False, shard=True, k=5)
+    lo, hi = bknn.shard_range(len(full), rank, world)
+    ok = b.data_pool["embedding"].shape[0] == hi - lo and b._row_base == lo
+    b.train_searcher()
+    rng = np.random.default_rng(3)
+    queries = np.concatenate([full[[7, 2600]].astype(np.float32), rng.standard_normal((2, 512)).astype(np.float32)])
+    out = b.search_k_nearest(queries, k=5, query_embedded=True)
+    want_i, want_d = oknn.search(full, oknn.normalize_queries(queries), 5)
+    ok = ok and np.array_equal(out["nns"], want_i) and np.array_equal(out["distances"], want_d)
+    ok = ok and np.array_equal(out["embeddings"], full[want_i].astype(np.float32)) and np.array_equal(out["img_ids"], want_i)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_dataset_builder_world2_gloo(tmp_path):
+    rng = np.random.default_rng(1)
+    start = 0
+    for i, n in enumerate((1200, 900, 1501)):                  # parts that do not align with the shard boundary
+        np.savez(tmp_path / f"part_{i}.npz", embedding=rng.standard_normal((n, 512)).astype(np.float16), img_id=np.arange(start, start + n),
+                 patch_coords=np.zeros((n, 4), np.int32))
+        start += n
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_builder_worker, args=(r, 2, port, q, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
