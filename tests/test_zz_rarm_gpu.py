@@ -216,4 +216,4 @@ def test_latent_image_retro_samples_and_decodes_on_the_device(cuda):
             assert consistent_with_uniform(p[b], int(ids[b, t]), float(u[t, b]), 1e-4), (t, b)
     with torch.no_grad():
         want = ovq.decode_indices(fs, ids, (2, 64, 8, 8))
-    assert rel(img, want) < 5e-3
+    assert rel(img, want) < 1e-2                                              # fp16x2 decoder (default mode) vs the fp32 oracle
