@@ -149,7 +149,7 @@ def test_imagenet_size_decoder_against_oracle(cuda):
 
 
 # ---- first stage of the RARM models: taming VQGAN-f16 decode of the sampled ids (wide-latent path of the device decoder) -------------
-@pytest.mark.parametrize("mode,tol", [(3, 3e-3), (4, 6e-3)])
+@pytest.mark.parametrize("mode,tol", [(3, 5e-3), (4, 1e-2)])
 def test_wide_latent_decoder_small(cuda, mode, tol):
     """embed_dim = z_channels = 64, AttnBlocks inside the lowest up level (attn_resolutions = [16]) as in the taming VQGAN-f16."""
     from oracle import vqdecoder as ovq
