@@ -248,11 +248,15 @@ class DDIMRetroSampler(DDIMSampler):
         b = shape[0]
         k_nn = model.k_nn if k_nn is None else k_nn
         img = torch.randn(shape, device=device) if x_T is None else x_T.to(device)
-        if retro_cond is None:                                      # ddim.py:296-316: noise as the first conditioning, its shape from r_shape
-            assert r_shape is not None, "r_shape = (b, n*k, d) is needed when no initial retrieval conditioning is given"
-            r_enc = torch.randn(r_shape, device=device)
+        if r_shape is None:
+            r_shape = shape                                         # ddim.py:293-294
+        if retro_cond is None:                                      # ddim.py:296-316 (pre_noise False): two draws, like the reference --
+            rc = torch.randn(r_shape, device=device)                # one that only gives the encoder something to shape the conditioning from,
+            r_enc = torch.randn_like(model.retrieval_encoder(rc))   # and the noise that IS the first conditioning
         else:
-            r_enc = model.retrieval_encoder(retro_cond.to(device, torch.float32))
+            retro_cond = retro_cond.to(device, torch.float32)
+            model.retrieval_encoder(retro_cond)                     # evaluated and discarded by the reference (:309-316):
+            r_enc = retro_cond                                      # the first step is conditioned on the RAW retro_cond
         if timesteps is None:
             timesteps = self.ddpm_num_timesteps if ddim_use_original_steps else self.ddim_timesteps
         elif not ddim_use_original_steps:
@@ -282,7 +286,7 @@ class DDIMRetroSampler(DDIMSampler):
                 if rc.ndim == 4:
                     rc = rc.reshape(rc.shape[0], rc.shape[1] * rc.shape[2], rc.shape[3])    # 'b n k d -> b (n k) d'   ddim.py:374
             else:
-                rc = retro_cond.to(device, torch.float32)
+                rc = retro_cond
             r_enc = model.retrieval_encoder(rc)                                             # ddim.py:396
             r_enc = adjust_support(r_enc)                                                   # ddim.py:398-400
             if not ignore_noising:

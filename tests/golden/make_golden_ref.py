@@ -13,6 +13,9 @@ stand-ins of tests/golden/ref_stubs.py (see its header for what that covers).  W
   ref_pipeline_tiny.npz  rdm/models/diffusion/ddpm.py MinimalRETRODiffusion.sample_from_rdata / sample_with_query / get_qids /
                       get_unconditional_conditioning / apply_model / sample_log (:445-458, :647-686, :689-844, :847-875, :878-1011) with
                       EMA weights, over an exact brute-force searcher (what the reference builds for pools < 2e4 rows)   -> the mirror
+  ref_retro_sampler.npz  rdm/models/diffusion/ddim.py DDIMRetroSampler.ddim_sampling (:270-415: per-step re-retrieval, BASELINE cfg4) over a
+                      closed-form model: every tensor routed between eps-model / first stage / retrieval / q_sample and every draw from
+                      the global torch generator                                                          -> the product's DDIMRetroSampler
   ref_rarm_small.npz  rdm/modules/attention.py RetrievalPatchTransformer (:199-272; discrete tokens, positional encodings, causal
                       self-attention, cross-attention to the retrieved vectors) and the sampling arithmetic of
                       rdm/models/autoregression/transformer.py LatentImageRETRO.sample (:224-270)         -> oracle/rarm.py
@@ -219,8 +222,47 @@ def pipeline():
     save("ref_pipeline_tiny.npz", out)
 
 
+def retro_sampler():
+    """DDIMRetroSampler.ddim_sampling (ddim.py:270-415: per-step re-retrieval) over the closed-form model of tests/golden/retro_stub.py.
+    `sample()` cannot be used: the base class passes keyword arguments this subclass does not accept (dead upstream).  The class
+    asserts a `PreNoiserRetroDiffusion` model from ldm that the repository does not define: the stand-in below is that marker type."""
+    import ldm.models.diffusion.ddpm as ldm_ddpm
+    import retro_stub
+    from rdm.models.diffusion.ddim import DDIMRetroSampler
+
+    class PreNoiserRetroDiffusion(object):
+        pass
+    ldm_ddpm.PreNoiserRetroDiffusion = PreNoiserRetroDiffusion
+
+    class Model(PreNoiserRetroDiffusion, retro_stub.RetroStub):
+        pass
+
+    class CpuRetroSampler(DDIMRetroSampler):
+        def register_buffer(self, name, attr):
+            setattr(self, name, attr)
+
+    out = {}
+    for tag, kw in (("retrieve", dict(retro_cond=None, ignore_noising=False, eta=0.3, seed=3)),
+                    ("retrieve_quiet", dict(retro_cond=None, ignore_noising=True, eta=0.0, seed=4)),
+                    ("fixed", dict(retro_cond=torch.randn(2, 2, 4, generator=torch.Generator().manual_seed(9)), ignore_noising=True, eta=0.0, seed=5))):
+        m = Model().setup()
+        s = CpuRetroSampler(m)
+        s.make_schedule(ddim_num_steps=4, ddim_eta=kw["eta"], verbose=False)
+        torch.manual_seed(kw["seed"])
+        img, inter = s.ddim_sampling(None, kw["retro_cond"], (2, 3, 4, 4), r_shape=(2, 2, 4), x_T=None, log_every_t=1, k_nn=2, ignore_noising=kw["ignore_noising"])
+        out[f"{tag}:img"] = img.numpy()
+        out[f"{tag}:pred_x0"] = torch.stack(inter["pred_x0"]).numpy()
+        out[f"{tag}:contexts"] = torch.stack(m.contexts).numpy()
+        out[f"{tag}:queries"] = torch.stack(m.queries).numpy() if m.queries else np.zeros((0,))
+        out[f"{tag}:eta"], out[f"{tag}:seed"], out[f"{tag}:ignore_noising"] = np.float32(kw["eta"]), np.int64(kw["seed"]), np.bool_(kw["ignore_noising"])
+        if kw["retro_cond"] is not None:
+            out[f"{tag}:retro_cond"] = kw["retro_cond"].numpy()
+    save("ref_retro_sampler.npz", out)
+
+
 if __name__ == "__main__":
     ref_stubs.install()
     unet_and_ddim()
     rarm()
     pipeline()
+    retro_sampler()

@@ -202,7 +202,7 @@ def test_per_step_re_retrieval_sampler(tmp_path, cuda):
     S, k, scale = 5, 4, 2.0
     x_T = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(3))
     torch.manual_seed(77)
-    r0 = torch.randn((2, k, 512), device=cuda)                                                  # the sampler's first draw (ddim.py:299)
+    r0 = torch.randn_like(torch.randn((2, k, 512), device=cuda))                                # the sampler's two draws (ddim.py:297,316): the second is the first conditioning
     uc = torch.zeros(2, k, 512, device=cuda)
     torch.manual_seed(77)
     with model.ema_scope():

@@ -41,7 +41,8 @@ def test_each_step_uses_the_previous_steps_retrieval():
     m = StubModel()
     S, x_T = 4, torch.randn(2, 3, 4, 4, generator=torch.Generator().manual_seed(0))
     torch.manual_seed(5)
-    r0 = torch.randn(2, 2, 4)
+    torch.randn(2, 2, 4)                                                                       # ddim.py:297: drawn, used for its shape only
+    r0 = torch.randn(2, 2, 4)                                                                  # ddim.py:316: the noise that is the first conditioning
     torch.manual_seed(5)
     img, inter = DDIMRetroSampler(m).sample(S, 2, (3, 4, 4), r_shape=(2, 2, 4), x_T=x_T, log_every_t=1, k_nn=2, ignore_noising=True, verbose=False)
     assert len(m.contexts) == S and len(m.queries) == S and len(inter["nns"]) == S
@@ -63,3 +64,31 @@ def test_fixed_retro_cond_never_retrieves():
     rc = torch.randn(2, 2, 4, generator=torch.Generator().manual_seed(1))
     DDIMRetroSampler(m).sample(4, 2, (3, 4, 4), retro_cond=rc, x_T=torch.zeros(2, 3, 4, 4), ignore_noising=True, verbose=False)
     assert not m.queries and all(torch.equal(c, rc) for c in m.contexts)
+
+
+def test_matches_the_reference_retro_sampler_including_rng_consumption():
+    """tests/golden/ref_retro_sampler.npz: the REFERENCE's DDIMRetroSampler.ddim_sampling (ddim.py:270-415) over the closed-form model of
+    tests/golden/retro_stub.py.  Same model, same seed of the global torch generator -> the product's sampler must route the same tensors
+    (contexts seen by the eps-model, queries handed to retrieval, x0 predictions, final sample) and draw the same random numbers in the
+    same order (x_T, the two draws of the first conditioning, one noise tensor per step, q_sample of the new conditioning)."""
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import retro_stub
+    from rdm.models.diffusion.ddim import DDIMRetroSampler
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_retro_sampler.npz"))
+    for tag in ("retrieve", "retrieve_quiet", "fixed"):
+        m = retro_stub.RetroStub().setup()
+        s = DDIMRetroSampler(m)
+        s.make_schedule(ddim_num_steps=4, ddim_eta=float(g[f"{tag}:eta"]), verbose=False)
+        rc = torch.from_numpy(g[f"{tag}:retro_cond"]) if f"{tag}:retro_cond" in g.files else None
+        torch.manual_seed(int(g[f"{tag}:seed"]))
+        img, inter = s.ddim_sampling(None, rc, (2, 3, 4, 4), r_shape=(2, 2, 4), x_T=None, log_every_t=1, k_nn=2, ignore_noising=bool(g[f"{tag}:ignore_noising"]))
+        close = lambda a, b: torch.allclose(a, torch.from_numpy(b), rtol=1e-5, atol=1e-6)
+        assert close(torch.stack(m.contexts), g[f"{tag}:contexts"]), tag
+        if rc is None:
+            assert close(torch.stack(m.queries), g[f"{tag}:queries"]), tag
+        else:
+            assert not m.queries
+        assert close(torch.stack(inter["pred_x0"]), g[f"{tag}:pred_x0"]) and close(img, g[f"{tag}:img"]), tag
