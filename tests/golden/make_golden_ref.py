@@ -13,6 +13,8 @@ stand-ins of tests/golden/ref_stubs.py (see its header for what that covers).  W
   ref_pipeline_tiny.npz  rdm/models/diffusion/ddpm.py MinimalRETRODiffusion.sample_from_rdata / sample_with_query / get_qids /
                       get_unconditional_conditioning / apply_model / sample_log (:445-458, :647-686, :689-844, :847-875, :878-1011) with
                       EMA weights, over an exact brute-force searcher (what the reference builds for pools < 2e4 rows)   -> the mirror
+  ref_sampler_options.npz  rdm/models/diffusion/ddim.py DDIMSampler.sample with inpainting mask / eta + temperature / noise dropout / style-content
+                      switching / callbacks / sampler-drawn x_T / log_every_t, over the closed-form model                 -> the product's DDIMSampler (generic path)
   ref_retro_sampler.npz  rdm/models/diffusion/ddim.py DDIMRetroSampler.ddim_sampling (:270-415: per-step re-retrieval, BASELINE cfg4) over a
                       closed-form model: every tensor routed between eps-model / first stage / retrieval / q_sample and every draw from
                       the global torch generator                                                          -> the product's DDIMRetroSampler
@@ -260,9 +262,61 @@ def retro_sampler():
     save("ref_retro_sampler.npz", out)
 
 
+SAMPLER_CASES = {       # keyword arguments of DDIMSampler.sample (ddim.py:59-91) beyond the plain guided loop
+    "mask_eta": dict(S=5, eta=0.5, mask=True, temperature=0.8, log_every_t=2, seed=11),
+    "noise_dropout": dict(S=4, eta=1.0, noise_dropout=0.25, log_every_t=100, seed=12),
+    "style_content": dict(S=10, eta=0.0, style=True, log_every_t=3, seed=13, guidance=1.0),
+    "callbacks_xT_drawn": dict(S=4, eta=0.2, callbacks=True, draw_xT=True, log_every_t=1, seed=14),
+}
+
+
+def run_sampler_case(sampler_cls, model, kw, retro_stub):
+    """One DDIMSampler.sample call described by a SAMPLER_CASES entry -> dict of results (shared by the generator and the test)."""
+    g = torch.Generator().manual_seed(kw["seed"] + 100)
+    shape = (3, 4, 4)
+    c, uc = torch.randn(2, 2, 4, generator=g), torch.zeros(2, 2, 4)
+    xT = None if kw.get("draw_xT") else torch.randn(2, *shape, generator=g)
+    extra, seen = {}, []
+    if kw.get("mask"):
+        extra["mask"] = (torch.rand(2, 1, 4, 4, generator=g) > 0.5).float()
+        extra["x0"] = torch.randn(2, *shape, generator=g)
+    if kw.get("style"):
+        extra["style_cond"], extra["content_cond"] = torch.randn(2, 2, 4, generator=g), torch.randn(2, 2, 4, generator=g)
+    if kw.get("callbacks"):
+        extra["callback"] = lambda i: seen.append(("cb", int(i)))
+        extra["img_callback"] = lambda p0, i: seen.append(("img", int(i), float(p0.sum())))
+    scale = kw.get("guidance", 2.0)
+    torch.manual_seed(kw["seed"])
+    s = sampler_cls(model)
+    samples, inter = s.sample(kw["S"], 2, shape, conditioning=c, eta=kw["eta"], x_T=xT, verbose=False, log_every_t=kw["log_every_t"],
+                              temperature=kw.get("temperature", 1.0), noise_dropout=kw.get("noise_dropout", 0.0), unconditional_guidance_scale=scale,
+                              unconditional_conditioning=uc if scale > 1.0 else None, **extra)
+    return {"samples": samples.numpy(), "x_inter": torch.stack([t for t in inter["x_inter"]]).numpy(), "pred_x0": torch.stack([t for t in inter["pred_x0"]]).numpy(),
+            "contexts": torch.stack(model.contexts).numpy(), "after": torch.rand(3).numpy(),       # `after`: the generator state the call leaves behind
+            "seen": np.array([list(map(float, e[1:])) + [0.0] * (3 - len(e)) for e in seen]) if seen else np.zeros((0, 2))}
+
+
+def sampler_options():
+    """DDIMSampler.sample / ddim_sampling / p_sample_ddim (ddim.py:59-268) with the options outside the plain guided loop -- inpainting mask,
+    eta > 0 with temperature, noise dropout, style / content conditioning by SNR, callbacks, x_T drawn by the sampler, intermediates every
+    log_every_t -- over the closed-form model of tests/golden/retro_stub.py; includes what the call leaves in the global torch generator."""
+    import retro_stub
+    from rdm.models.diffusion.ddim import DDIMSampler
+
+    class CpuDDIMSampler(DDIMSampler):
+        def register_buffer(self, name, attr):
+            setattr(self, name, attr)
+    out = {}
+    for tag, kw in SAMPLER_CASES.items():
+        for k, v in run_sampler_case(CpuDDIMSampler, retro_stub.RetroStub().setup(), kw, retro_stub).items():
+            out[f"{tag}:{k}"] = v
+    save("ref_sampler_options.npz", out)
+
+
 if __name__ == "__main__":
     ref_stubs.install()
     unet_and_ddim()
     rarm()
     pipeline()
     retro_sampler()
+    sampler_options()
