@@ -213,8 +213,11 @@ def pipeline():
     out["qids_weighted"] = model.get_qids(0.4, 5, use_weights=True)
     # (2) scripts/rdm_sample.py:272-299: an embedded (text) query, prepended as neighbour 0; and omit_query
     q = torch.from_numpy(ref_weights.tensor_for("query", (2, 512), 46) * 22.0)
-    for tag, omit in (("query", False), ("query_omit", True)):
-        logs = model.sample_with_query(query=q, query_embedded=True, k_nn=K_NN, visualize_nns=False, omit_query=omit, x_T=xT[:2].clone(), **common)
+    for tag, extra in (("query", dict(omit_query=False)), ("query_omit", dict(omit_query=True)), ("query_normalize", dict(normalize=True)),
+                       ("query_reps", dict(n_reps=2)), ("query_single", dict(bs=2, single=True))):
+        extra = dict(extra)
+        qq = q[:1] if extra.pop("single", False) else q                       # one embedded query repeated over the batch (ddpm.py:717-718)
+        logs = model.sample_with_query(query=qq, query_embedded=True, k_nn=K_NN, visualize_nns=False, x_T=xT[:2].clone(), **common, **extra)
         out[f"{tag}:samples"] = logs["query_samples"].numpy()
     out["query:q"] = q.numpy()
     # (3) unconditional conditioning for a non-zero label (ddpm.py:663-686): vex / |vex| * label, stacked [bs, k, d]
