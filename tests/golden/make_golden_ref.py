@@ -220,6 +220,14 @@ def pipeline():
         logs = model.sample_with_query(query=qq, query_embedded=True, k_nn=K_NN, visualize_nns=False, x_T=xT[:2].clone(), **common, **extra)
         out[f"{tag}:samples"] = logs["query_samples"].numpy()
     out["query:q"] = q.numpy()
+    # (2b) get_nn_and_encoding (ddpm.py:263-316): image -> n x n patches -> retriever -> q / |q| -> kNN -> RAW rows [b, n*n, k, d]
+    import retro_stub
+    model.retriever.retriever = retro_stub.PatchEmbedStub()
+    imgs = torch.from_numpy(ref_weights.tensor_for("nn_enc_images", (2, 3, 16, 16), 48) * 8.0)
+    for tag, x, n in (("nnenc_2x2", imgs, 2), ("nnenc_1x1_channels_last", imgs.permute(0, 2, 3, 1).contiguous(), 1)):
+        r = model.get_nn_and_encoding(x, k_nn=3, n_patches_per_side=n)
+        out[f"{tag}:nn_embeddings"] = r[model.nn_key].numpy()
+    out["nnenc:images"] = imgs.numpy()
     # (3) unconditional conditioning for a non-zero label (ddpm.py:663-686): vex / |vex| * label, stacked [bs, k, d]
     model.unconditional_guidance_vex.copy_(torch.from_numpy(ref_weights.tensor_for("vex", (512,), 47)))
     out["uncond_label_1.5"] = model.get_unconditional_conditioning((2, K_NN, 512), unconditional_guidance_label=1.5, k_nn=K_NN).numpy()

@@ -45,3 +45,17 @@ class RetroStub:
         noise = torch.randn_like(x_start) if noise is None else noise
         shp = (-1,) + (1,) * (x_start.ndim - 1)
         return self.sqrt_alphas_cumprod[t].reshape(shp) * x_start + self.sqrt_one_minus_alphas_cumprod[t].reshape(shp) * noise
+
+
+class PatchEmbedStub(torch.nn.Module):
+    """Stand-in for the image retriever (`retriever.retriever`, CLIP in the reference): 4x4 average pooling of every channel, then a fixed
+    linear map to 512 dimensions.  Shared by the golden generator and the tests of `get_nn_and_encoding`."""
+
+    def __init__(self):
+        super().__init__()
+        import ref_weights
+        self.register_buffer("w", torch.from_numpy(ref_weights.tensor_for("patch_embed_stub", (48, 512), 51)) * 30.0)
+
+    def forward(self, x):
+        pooled = torch.nn.functional.adaptive_avg_pool2d(x.float(), 4).reshape(x.shape[0], -1)
+        return pooled @ self.w.to(pooled.device)

@@ -73,3 +73,17 @@ def test_sample_with_query_options_match_reference_code(model_and_golden, tag, e
     logs = model.sample_with_query(query=q, query_embedded=True, k_nn=4, visualize_nns=False, x_T=xT.clone(), **COMMON, **extra)
     assert list(logs.keys()) == ["query_samples"]
     assert rel(logs["query_samples"], p[f"{tag}:samples"]) < 1e-5, tag
+
+
+def test_get_nn_and_encoding_matches_reference_code(model_and_golden):
+    """ddpm.py:263-316: image -> n x n patches -> retriever -> q / |q| -> exact kNN -> RAW neighbour rows [b, n*n, k, d] (the per-step
+    re-retrieval of BASELINE cfg4); channel-first and channel-last inputs."""
+    import retro_stub
+    model, p = model_and_golden
+    model.retriever._retriever = retro_stub.PatchEmbedStub()
+    imgs = torch.from_numpy(p["nnenc:images"])
+    for tag, x, n in (("nnenc_2x2", imgs, 2), ("nnenc_1x1_channels_last", imgs.permute(0, 2, 3, 1).contiguous(), 1)):
+        r = model.get_nn_and_encoding(x, k_nn=3, n_patches_per_side=n)
+        want = p[f"{tag}:nn_embeddings"]
+        assert tuple(r[model.nn_key].shape) == want.shape == (2, n * n, 3, 512)
+        assert np.array_equal(r[model.nn_key].numpy(), want), tag
