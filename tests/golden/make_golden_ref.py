@@ -18,6 +18,8 @@ stand-ins of tests/golden/ref_stubs.py (see its header for what that covers).  W
   ref_retro_sampler.npz  rdm/models/diffusion/ddim.py DDIMRetroSampler.ddim_sampling (:270-415: per-step re-retrieval, BASELINE cfg4) over a
                       closed-form model: every tensor routed between eps-model / first stage / retrieval / q_sample and every draw from
                       the global torch generator                                                          -> the product's DDIMRetroSampler
+  ref_search_nns.p    scripts/search_neighbors.py search_nns / save_pkl (:355-450): file names, per-example pickle layout, merging of patch
+                      grids, corrupt-file policy, neighbour histogram                                     -> rdm_b200/nn_precompute.py
   ref_rarm_small.npz  rdm/modules/attention.py RetrievalPatchTransformer (:199-272; discrete tokens, positional encodings, causal
                       self-attention, cross-attention to the retrieved vectors) and the sampling arithmetic of
                       rdm/models/autoregression/transformer.py LatentImageRETRO.sample (:224-270)         -> oracle/rarm.py
@@ -324,6 +326,32 @@ def sampler_options():
     save("ref_sampler_options.npz", out)
 
 
+def neighbour_precompute():
+    """scripts/search_neighbors.py `search_nns` / `save_pkl` (:355-450) -- the writer of the per-example neighbour pickles that
+    QueryDataset.load_nns reads -- over the stand-in builder of tests/golden/retro_stub.py.  The script's module-level imports of the
+    database builder (scann, streamlit, image datasets) and kornia are satisfied by empty stand-ins; the two functions run unmodified."""
+    import importlib.util
+    import pickle
+    import tempfile
+    import types
+    import retro_stub
+    m = types.ModuleType("rdm.data.retrieval_dataset.dsetbuilder"); m.DatasetBuilder = object
+    sys.modules["rdm.data.retrieval_dataset.dsetbuilder"] = m
+    for name, attrs in (("kornia.geometry", {}), ("kornia.geometry.transform", {"crop_by_boxes": None})):
+        k = types.ModuleType(name); k.__dict__.update(attrs); sys.modules[name] = k
+    sys.modules["ldm.util"].parallel_data_prefetch = None
+    sys.modules["omegaconf"].OmegaConf = object
+    spec = importlib.util.spec_from_file_location("ref_search_neighbors", "/root/reference/scripts/search_neighbors.py")
+    script = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(script)
+    with tempfile.TemporaryDirectory() as td:
+        res = retro_stub.precompute_scenario(script.search_nns, td)
+    path = os.path.join(HERE, "ref_search_nns.p")
+    with open(path, "wb") as f:
+        pickle.dump(res, f, protocol=4)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     ref_stubs.install()
     unet_and_ddim()
@@ -331,3 +359,4 @@ if __name__ == "__main__":
     pipeline()
     retro_sampler()
     sampler_options()
+    neighbour_precompute()

@@ -59,3 +59,43 @@ class PatchEmbedStub(torch.nn.Module):
     def forward(self, x):
         pooled = torch.nn.functional.adaptive_avg_pool2d(x.float(), 4).reshape(x.shape[0], -1)
         return pooled @ self.w.to(pooled.device)
+
+
+class FakeBuilder:
+    """Stand-in DatasetBuilder for the offline neighbour precompute (scripts/search_neighbors.py:380-450): `search_k_nearest` with the
+    reference's result keys; the neighbours of query i are rows i, i+1, ... shifted per call (deterministic)."""
+    k, searcher = 3, object()
+
+    def __init__(self):
+        self.pool = np.arange(50 * 4, dtype=np.float32).reshape(50, 4)
+        self.calls = 0
+
+    def search_k_nearest(self, queries, visualize=False, is_caption=False):
+        n = len(queries)
+        nns = (np.arange(n)[:, None] + np.arange(self.k)[None] + 7 * self.calls) % 50
+        self.calls += 1
+        return {"embeddings": self.pool[nns], "nns": nns, "img_ids": nns * 10, "patch_coords": np.zeros((n, self.k, 4), np.int32), "queries": queries}
+
+
+class Loader(list):
+    batch_size = 2
+
+
+def precompute_scenario(search_nns, base):
+    """The call sequence both implementations are put through; returns everything observable: return values and every file written."""
+    import os
+    import pickle
+    os.makedirs(os.path.join(base, "embeddings"), exist_ok=True)
+    b = FakeBuilder()
+    grid2 = Loader({"patches": torch.zeros(2, 4, 8, 8, 3)} for _ in range(3))
+    paths = search_nns(b, grid2, device="cpu", save=True, npatches_perside=2, base_savedir=base, start_id=10)
+    with open(os.path.join(base, paths[12]), "wb") as f:               # a truncated file: the 1 x 1 pass must replace it
+        f.write(b"garbage")
+    grid1 = Loader({"patches": torch.zeros(2, 1, 16, 16, 3)} for _ in range(3))
+    paths1 = search_nns(b, grid1, device="cpu", save=True, npatches_perside=1, base_savedir=base, start_id=10, nn_paths=dict(paths))
+    counts = search_nns(b, Loader({"caption": ["a", "b"]} for _ in range(5)), device="cpu", mode="text", save=False, max_its=2)
+    files = {}
+    for name in sorted(os.listdir(os.path.join(base, "embeddings"))):
+        with open(os.path.join(base, "embeddings", name), "rb") as f:
+            files[name] = pickle.load(f)
+    return {"paths": dict(paths), "paths_after_second_pass": dict(paths1), "counts": {int(k): int(v) for k, v in counts.items()}, "files": files}

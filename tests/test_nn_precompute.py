@@ -68,3 +68,26 @@ def test_histogram_and_nn_memory():
     mem = build_nn_memory(hist)
     counts = [hist[int(i)] for i in mem["nn_memory"]]
     assert counts == sorted(counts, reverse=True) and mem["id_count"] == hist
+
+
+def test_files_and_return_values_equal_the_reference_writer(tmp_path):
+    """tests/golden/ref_search_nns.p: everything the REFERENCE's `search_nns` / `save_pkl` (scripts/search_neighbors.py:355-450) returned
+    and wrote for the scenario of tests/golden/retro_stub.py (2 x 2 grid pass, a truncated file, 1 x 1 pass into the same files, caption
+    counting with max_its).  The product's implementation must produce the same names, the same pickle contents and the same returns."""
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import retro_stub
+    with open(os.path.join(ROOT, "tests", "golden", "ref_search_nns.p"), "rb") as f:
+        want = pickle.load(f)
+    got = retro_stub.precompute_scenario(search_nns, str(tmp_path))
+    assert got["paths"] == want["paths"] and got["paths_after_second_pass"] == want["paths_after_second_pass"] and got["counts"] == want["counts"]
+    assert sorted(got["files"]) == sorted(want["files"])
+    for name, entry in want["files"].items():
+        assert sorted(got["files"][name]) == sorted(entry), name                      # patch grids present (the truncated file holds grid 1 only)
+        for grid, fields in entry.items():
+            assert sorted(got["files"][name][grid]) == sorted(fields)
+            for key, arr in fields.items():
+                g = got["files"][name][grid][key]
+                assert g.dtype == arr.dtype and np.array_equal(g, arr), (name, grid, key)
