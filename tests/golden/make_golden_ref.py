@@ -352,6 +352,65 @@ def neighbour_precompute():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+RARM_MODEL_CFG = dict(mask_token=48, sos_token=49, p_mask_max=0.0, nn_key="nn_embeddings", nn_memory=None, retrieval_cfg=None,
+                      cond_stage_config="__is_unconditional__")
+RARM_SAMPLING_CASES = {"guided": dict(guidance_scale=2.5, temperature=0.9, top_k=8, seed=71), "plain": dict(guidance_scale=1.0, temperature=1.3, top_k=20, seed=72)}
+
+
+def rarm_model_cfg(A=dict):
+    return dict(RARM_MODEL_CFG, nn_reshaper_cfg=A(target="rdm.modules.encoders.nn_encoders.CLIPEmbeddingReshaper"),
+                nn_encoder_cfg=A(target="rdm.modules.encoders.nn_encoders.IdentityEncoder"),
+                transformer_config=A(target="rdm.modules.attention.RetrievalPatchTransformer", params=dict(RARM_CFG)),
+                first_stage_config=A(target="retro_stub.StubFirstStage", params=dict(n_embed=48, embed_dim=8)))
+
+
+def rarm_sampling():
+    """LatentImageRETRO.sample / sampling_util / sample_from_rdata (rdm/models/autoregression/transformer.py:224-391) run end to end over the
+    reference's own RetrievalPatchTransformer: guidance on the logits, temperature, top-k filter, softmax, prefix handling, SOS conditioning,
+    decode_to_img.  The one replaced call is `torch.multinomial` (its draws cannot be reproduced by a device kernel): it is swapped for the
+    inverse-CDF draw on recorded uniforms -- the definition the oracle and the CUDA sampler use -- and the probabilities it is handed are
+    recorded, so the fixture holds, per step, exactly what the reference computed."""
+    import retro_stub  # noqa: F401
+    from rdm.models.autoregression.transformer import LatentImageRETRO           # the reference's
+    A = ref_stubs.AttrDict
+    model = LatentImageRETRO(**rarm_model_cfg(A)).eval()
+    ref_weights.fill_(model.transformer, 21)
+    db, _, _ = ref_weights.make_db(N_DB)
+    db128 = db[:, :128].copy()                                                   # context_dim of the small decoder
+    model.retriever = Retriever(db128)
+    out = {"n_db": np.int64(N_DB), "sd_keys": np.array([k for k in model.state_dict().keys()])}
+    real_multinomial = torch.multinomial
+    for tag, kw in RARM_SAMPLING_CASES.items():
+        torch.manual_seed(kw["seed"])
+        u = torch.rand((9, 2))                                                   # what the product's sampler draws (torch.rand((steps, B)))
+        rec = {"probs": [], "step": 0}
+
+        def fake_multinomial(probs, num_samples=1, **k):
+            rec["probs"].append(probs.clone())
+            cdf = probs.double().cumsum(-1)
+            ix = (cdf > (u[rec["step"]].double() * cdf[:, -1])[:, None]).float().argmax(-1)
+            rec["step"] += 1
+            return ix[:, None]
+        torch.multinomial = fake_multinomial
+        try:
+            np.random.seed(kw["seed"])
+            logs = model.sample_from_rdata(2, qids=None, k_nn=4, memsize=100, top_k=kw["top_k"], temperature=kw["temperature"], code_side_len=3,
+                                           z_dimensionality=8, guidance_scale=kw["guidance_scale"])
+        finally:
+            torch.multinomial = real_multinomial
+        out[f"{tag}:qids"], out[f"{tag}:uniforms"] = np.asarray(logs["qids"]), u.numpy()
+        out[f"{tag}:probs"] = torch.stack(rec["probs"]).numpy()
+        out[f"{tag}:images"] = logs["samples_with_sampled_nns"].numpy()
+    # greedy decoding of a given start prefix through `sample` itself (sample=False, transformer.py:265-266)
+    g = torch.Generator().manual_seed(73)
+    r = torch.randn(2, 4, 128, generator=g)
+    _, c = model.encode_to_c(torch.zeros((2, 0)))
+    start = torch.randint(0, 48, (2, 3), generator=g)
+    out["greedy:r"], out["greedy:start"] = r.numpy(), start.numpy()
+    out["greedy:tokens"] = model.sample(start, r, c, steps=6, sample=False, top_k=None, guidance_scale=3.0).numpy()
+    save("ref_rarm_sampling.npz", out)
+
+
 if __name__ == "__main__":
     ref_stubs.install()
     unet_and_ddim()
@@ -360,3 +419,4 @@ if __name__ == "__main__":
     retro_sampler()
     sampler_options()
     neighbour_precompute()
+    rarm_sampling()

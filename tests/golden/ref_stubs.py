@@ -281,6 +281,70 @@ class LatentDiffusion(nn.Module):
         return self.first_stage_model.decode(1.0 / self.scale_factor * z)
 
 
+# ---- taming.models.cond_transformer (what LatentImageRETRO's sampling methods use of Net2NetTransformer) ---------------------------
+class SOSProvider(nn.Module):
+    def __init__(self, sos_token, quantize_interface=True):
+        super().__init__()
+        self.sos_token, self.quantize_interface = sos_token, quantize_interface
+
+    def encode(self, x):
+        c = torch.ones(x.shape[0], 1) * self.sos_token
+        c = c.long().to(x.device)
+        if self.quantize_interface:
+            return c, None, [None, None, c]
+        return c
+
+
+class Net2NetTransformer(nn.Module):
+    """The slice of taming's Net2NetTransformer that sampling touches (published taming-transformers source): first stage, SOS
+    conditioning for `__is_unconditional__`, identity permuter, the transformer built from its config, `top_k_logits`, `encode_to_c`,
+    `decode_to_img`."""
+
+    def __init__(self, transformer_config, first_stage_config, cond_stage_config, permuter_config=None, ckpt_path=None, ignore_keys=[],
+                 first_stage_key="image", cond_stage_key="depth", downsample_cond_size=-1, pkeep=1.0, sos_token=0, unconditional=False):
+        super().__init__()
+        self.be_unconditional, self.sos_token = unconditional, sos_token
+        self.first_stage_key, self.cond_stage_key = first_stage_key, cond_stage_key
+        self.first_stage_model = instantiate_from_config(first_stage_config).eval()
+        if cond_stage_config == "__is_unconditional__" or self.be_unconditional:
+            print(f"Using no cond stage. Assuming the training is intended to be unconditional. Prepending {self.sos_token} as a sos token.")
+            self.be_unconditional, self.cond_stage_key = True, self.first_stage_key
+            self.cond_stage_model = SOSProvider(self.sos_token)
+        else:
+            raise NotImplementedError
+        assert permuter_config is None
+        self.permuter = lambda x, reverse=False: x
+        self.transformer = instantiate_from_config(transformer_config)
+        self.downsample_cond_size, self.pkeep = downsample_cond_size, pkeep
+
+    @property
+    def device(self):                                            # pl.LightningModule.device
+        return next(self.parameters()).device
+
+    def top_k_logits(self, logits, k):
+        v, ix = torch.topk(logits, k)
+        out = logits.clone()
+        out[out < v[..., [-1]]] = -float("Inf")
+        return out
+
+    @torch.no_grad()
+    def encode_to_c(self, c):
+        if self.downsample_cond_size > -1:
+            c = F.interpolate(c, size=(self.downsample_cond_size, self.downsample_cond_size))
+        quant_c, _, [_, _, indices] = self.cond_stage_model.encode(c)
+        if len(indices.shape) > 2:
+            indices = indices.view(c.shape[0], -1)
+        return quant_c, indices
+
+    @torch.no_grad()
+    def decode_to_img(self, index, zshape):
+        index = self.permuter(index, reverse=True)
+        bhwc = (zshape[0], zshape[2], zshape[3], zshape[1])
+        quant_z = self.first_stage_model.quantize.get_codebook_entry(index.reshape(-1), shape=bhwc)
+        x = self.first_stage_model.decode(quant_z)
+        return x
+
+
 class AttrDict(dict):
     """Stand-in for an OmegaConf node: `cfg.params.context_dim` and `cfg["target"]` both work."""
     def __getattr__(self, k):
@@ -325,6 +389,10 @@ def install(reference_root="/root/reference"):
     mod("pytorch_lightning", LightningModule=nn.Module, seed_everything=lambda s: None)
     mod("pytorch_lightning.utilities")
     mod("pytorch_lightning.utilities.distributed", rank_zero_only=lambda f: f)
+    mod("taming")
+    mod("taming.models")
+    mod("taming.models.cond_transformer", **pick("Net2NetTransformer", "SOSProvider"))
+    sys.modules["ldm.util"].log_txt_as_img = None
     mod("main", **pick("instantiate_from_config"))
     mod("kornia")
     mod("omegaconf")

@@ -99,3 +99,29 @@ def precompute_scenario(search_nns, base):
         with open(os.path.join(base, "embeddings", name), "rb") as f:
             files[name] = pickle.load(f)
     return {"paths": dict(paths), "paths_after_second_pass": dict(paths1), "counts": {int(k): int(v) for k, v in counts.items()}, "files": files}
+
+
+class StubFirstStage(torch.nn.Module):
+    """Stand-in VQGAN for the RARM flow: `quantize.get_codebook_entry(indices, shape)` (taming VectorQuantizer2, lookup side) over a fixed
+    codebook and a closed-form `decode` (first three channels of the code image), so decoded "images" depend on every sampled id."""
+
+    class _Quantize(torch.nn.Module):
+        def __init__(self, n_e, e_dim):
+            super().__init__()
+            import ref_weights
+            self.embedding = torch.nn.Embedding(n_e, e_dim)
+            with torch.no_grad():
+                self.embedding.weight.copy_(torch.from_numpy(ref_weights.tensor_for("stub_codebook", (n_e, e_dim), 61)) * float(e_dim) ** 0.5)
+
+        def get_codebook_entry(self, indices, shape):
+            z_q = self.embedding(indices)
+            if shape is not None:
+                z_q = z_q.view(shape).permute(0, 3, 1, 2).contiguous()
+            return z_q
+
+    def __init__(self, n_embed=48, embed_dim=8, **ignored):
+        super().__init__()
+        self.quantize = StubFirstStage._Quantize(n_embed, embed_dim)
+
+    def decode(self, quant, *a, **k):
+        return torch.tanh(quant[:, :3])

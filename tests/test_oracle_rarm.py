@@ -96,3 +96,30 @@ def test_sample_loop_shapes_and_prefix_consistency():
     assert torch.equal(toks2, toks)
     greedy, gp = orarm.sample(sd, cfg["n_heads"], c, x0, ctx, 4, top_k=None, guidance_scale=1.0)
     assert torch.equal(greedy, gp.argmax(-1).t())
+
+
+def test_sampling_loop_matches_reference_code():
+    """tests/golden/ref_rarm_sampling.npz: the REFERENCE's LatentImageRETRO.sample_from_rdata / sample run end to end (retrieval, SOS
+    conditioning, guidance on the logits, temperature, top-k, softmax, decode) with `torch.multinomial` swapped for the inverse-CDF draw
+    on recorded uniforms.  The oracle loop must hand the draw the same probabilities at every step and end in the same images."""
+    from oracle import knn as oknn
+    import make_golden_ref as gen
+    import retro_stub
+    g = np.load(os.path.join(GOLD, "ref_rarm_sampling.npz"))
+    cfg = gen.RARM_CFG
+    sd = ref_weights.state_dict_for(orarm.param_shapes(**cfg).items(), 21)
+    db = ref_weights.make_db(int(g["n_db"]))[0][:, :128].copy()
+    fs = retro_stub.StubFirstStage(n_embed=48, embed_dim=8)
+    c, x0 = torch.full((2, 1), 49), torch.zeros((2, 0), dtype=torch.long)
+    for tag, kw in gen.RARM_SAMPLING_CASES.items():
+        q = db[g[f"{tag}:qids"]].astype(np.float32)
+        nns, _ = oknn.search(db, oknn.normalize_queries(q), 4)
+        r = torch.from_numpy(db[nns].astype(np.float32))
+        toks, probs = orarm.sample(sd, cfg["n_heads"], c, x0, r, 9, kw["temperature"], kw["top_k"], kw["guidance_scale"], torch.from_numpy(g[f"{tag}:uniforms"]))
+        assert float((probs - torch.from_numpy(g[f"{tag}:probs"])).abs().max()) < 5e-6, tag      # fp32 rounding, amplified by the guidance scale
+        with torch.no_grad():
+            img = fs.decode(fs.quantize.get_codebook_entry(toks.reshape(-1), shape=(2, 3, 3, 8)))
+        assert torch.equal(img, torch.from_numpy(g[f"{tag}:images"])), tag
+    r, start = torch.from_numpy(g["greedy:r"]), torch.from_numpy(g["greedy:start"])
+    toks, _ = orarm.sample(sd, cfg["n_heads"], c, start, r, 6, guidance_scale=3.0)
+    assert torch.equal(toks, torch.from_numpy(g["greedy:tokens"]))

@@ -172,3 +172,46 @@ def test_gpu_test_bodies_run_under_emulation(emu_cls, monkeypatch):
     gpu_tests.test_cached_logits_match_reference_code("cpu", 4, 5e-3)
     gpu_tests.test_guided_topk_draw_kernel_matches_oracle("cpu", 16384, 256, True)
     gpu_tests.test_sampling_loop_token_by_token("cpu", 4, 2.0)
+
+
+def test_product_sampling_flow_matches_reference_code(emu_cls):
+    """The product end to end on the CPU -- `LatentImageRETRO.sample_from_rdata` / `sample` of this repository driving csrc/rarm.cu through
+    the C ABI (under emulation) -- against tests/golden/ref_rarm_sampling.npz, the REFERENCE's own LatentImageRETRO run over its own
+    RetrievalPatchTransformer (tests/golden/make_golden_ref.py): same NumPy / torch seeds, same database, same weights ->
+    same query ids, same sampled token ids, same decoded images; greedy continuation of a given prefix likewise."""
+    import types
+    import make_golden_ref as gen
+    import rdm  # noqa: F401
+    from oracle import knn as oknn
+    from rdm.models.autoregression.transformer import LatentImageRETRO
+    from rdm_b200.rarm import MODE_FP32
+    g = np.load(os.path.join(GOLD, "ref_rarm_sampling.npz"))
+    model = LatentImageRETRO(**gen.rarm_model_cfg()).eval()
+    assert sorted(model.state_dict().keys()) == sorted(str(k) for k in g["sd_keys"])          # the reference model's checkpoint keys
+    tsd = ref_weights.state_dict_for(((k, v.shape) for k, v in model.transformer.state_dict().items()), 21)
+    model.transformer.load_state_dict(tsd)
+    eng = emu_cls("cpu", **model.transformer._cfg)
+    eng.load_state_dict(tsd)
+    eng.set_mode(MODE_FP32)
+    model.transformer.engine = lambda device: eng
+    db = ref_weights.make_db(int(g["n_db"]))[0][:, :128].copy()
+
+    class Searcher:                                                            # stand-in for the device searcher (exact kNN by the oracle)
+        def search_device(self, q_hat, k):
+            i, d = oknn.search(db, q_hat.numpy(), k)
+            return torch.from_numpy(i), torch.from_numpy(d)
+
+        def gather_device(self, idx):
+            return torch.from_numpy(db[idx.numpy()].astype(np.float32))
+    model.retriever = types.SimpleNamespace(searcher=Searcher(), data_pool={"embedding": db})
+    for tag, kw in gen.RARM_SAMPLING_CASES.items():
+        np.random.seed(kw["seed"])
+        torch.manual_seed(kw["seed"])
+        logs = model.sample_from_rdata(2, qids=None, k_nn=4, memsize=100, top_k=kw["top_k"], temperature=kw["temperature"], code_side_len=3,
+                                       z_dimensionality=8, guidance_scale=kw["guidance_scale"])
+        assert sorted(logs.keys()) == ["qids", "samples_with_sampled_nns"]     # the reference's keys
+        assert np.array_equal(np.asarray(logs["qids"]), g[f"{tag}:qids"])
+        assert torch.equal(logs["samples_with_sampled_nns"], torch.from_numpy(g[f"{tag}:images"])), tag
+    _, c = model.encode_to_c(torch.zeros((2, 0)))
+    got = model.sample(torch.from_numpy(g["greedy:start"]), torch.from_numpy(g["greedy:r"]), c, steps=6, sample=False, top_k=None, guidance_scale=3.0)
+    assert torch.equal(got, torch.from_numpy(g["greedy:tokens"]))
