@@ -217,3 +217,47 @@ def test_latent_image_retro_samples_and_decodes_on_the_device(cuda):
     with torch.no_grad():
         want = ovq.decode_indices(fs, ids, (2, 64, 8, 8))
     assert rel(img, want) < 1e-2                                              # fp16x2 decoder (default mode) vs the fp32 oracle
+
+
+def test_product_sampling_flow_matches_reference_code(cuda):
+    """tests/golden/ref_rarm_sampling.npz -- the REFERENCE's own LatentImageRETRO.sample_from_rdata / sample over its own
+    RetrievalPatchTransformer -- against this repository's LatentImageRETRO on the device decoder (fp32 weights): same seeds, database and
+    weights -> same query ids, token ids and decoded images.  (The 128-wide toy database is searched by the oracle: the device searcher
+    takes d in {256, 512, 768, 1024}.)"""
+    import types
+    import make_golden_ref as gen
+    import rdm  # noqa: F401
+    from oracle import knn as oknn
+    from rdm.models.autoregression.transformer import LatentImageRETRO
+    g = np.load(os.path.join(GOLD, "ref_rarm_sampling.npz"))
+    model = LatentImageRETRO(**gen.rarm_model_cfg()).eval()
+    tsd = ref_weights.state_dict_for(((k, v.shape) for k, v in model.transformer.state_dict().items()), 21)
+    model.transformer.load_state_dict(tsd)
+    model.transformer.engine_mode = "fp32"
+    model = model.to(cuda)
+    db = ref_weights.make_db(int(g["n_db"]))[0][:, :128].copy()
+
+    class Searcher:
+        def search_device(self, q_hat, k):
+            i, d = oknn.search(db, q_hat.cpu().numpy(), k)
+            return torch.from_numpy(i).to(cuda), torch.from_numpy(d).to(cuda)
+
+        def gather_device(self, idx):
+            return torch.from_numpy(db[idx.cpu().numpy()].astype(np.float32)).to(cuda)
+    model.retriever = types.SimpleNamespace(searcher=Searcher(), data_pool={"embedding": db})
+    real_rand = torch.rand
+    for tag, kw in gen.RARM_SAMPLING_CASES.items():
+        u = torch.from_numpy(g[f"{tag}:uniforms"])
+        torch.rand = lambda *a, **k: u.to(k.get("device", "cpu"))              # the CPU generator's uniforms of the fixture (CUDA draws differ)
+        try:
+            np.random.seed(kw["seed"])
+            logs = model.sample_from_rdata(2, qids=None, k_nn=4, memsize=100, top_k=kw["top_k"], temperature=kw["temperature"], code_side_len=3,
+                                           z_dimensionality=8, guidance_scale=kw["guidance_scale"])
+        finally:
+            torch.rand = real_rand
+        assert np.array_equal(np.asarray(logs["qids"]), g[f"{tag}:qids"])
+        assert torch.equal(logs["samples_with_sampled_nns"].cpu(), torch.from_numpy(g[f"{tag}:images"])), tag
+    _, c = model.encode_to_c(torch.zeros((2, 0)))
+    got = model.sample(torch.from_numpy(g["greedy:start"]).to(cuda), torch.from_numpy(g["greedy:r"]).to(cuda), c.to(cuda), steps=6, sample=False, top_k=None,
+                       guidance_scale=3.0)
+    assert torch.equal(got.cpu(), torch.from_numpy(g["greedy:tokens"]))
