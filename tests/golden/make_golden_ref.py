@@ -18,6 +18,8 @@ stand-ins of tests/golden/ref_stubs.py (see its header for what that covers).  W
   ref_retro_sampler.npz  rdm/models/diffusion/ddim.py DDIMRetroSampler.ddim_sampling (:270-415: per-step re-retrieval, BASELINE cfg4) over a
                       closed-form model: every tensor routed between eps-model / first stage / retrieval / q_sample and every draw from
                       the global torch generator                                                          -> the product's DDIMRetroSampler
+  ref_dsetbuilder.npz rdm/data/retrieval_dataset/dsetbuilder.py DatasetBuilder.load_embeddings / train_searcher / embed / search_k_nearest over an
+                      exact stand-in for scann's brute-force scorer                                       -> the product's DatasetBuilder
   ref_search_nns.p    scripts/search_neighbors.py search_nns / save_pkl (:355-450): file names, per-example pickle layout, merging of patch
                       grids, corrupt-file policy, neighbour histogram                                     -> rdm_b200/nn_precompute.py
   ref_rarm_small.npz  rdm/modules/attention.py RetrievalPatchTransformer (:199-272; discrete tokens, positional encodings, causal
@@ -411,6 +413,69 @@ def rarm_sampling():
     save("ref_rarm_sampling.npz", out)
 
 
+def dataset_builder():
+    """rdm/data/retrieval_dataset/dsetbuilder.py DatasetBuilder.load_embeddings / train_searcher / embed / search_k_nearest (:181-236,
+    :461-518, :534-619), unmodified.  The module's imports of scann, streamlit and the image datasets are satisfied by stand-ins; the scann
+    stand-in implements what the reference asks of it for pools below 2e4 rows -- `builder(db_normalised, k, "dot_product")
+    .score_brute_force().build()` = exact top-k by dot product over the rows AS THE REFERENCE NORMALISED THEM (:574).  The constructor
+    (datasets, CLIP download) is bypassed; the methods run on an instance carrying the attributes they read."""
+    import tempfile
+    import types
+    import retro_stub
+
+    class ExactScann:
+        def __init__(self, db, k, metric):
+            assert metric == "dot_product"
+            self.db = np.asarray(db, dtype=np.float32)               # ScaNN holds float32 copies of the rows it is given
+
+        def score_brute_force(self):
+            return self
+
+        def build(self):
+            return self
+
+        def search_batched(self, q, final_num_neighbors=None):
+            s = np.asarray(q, dtype=np.float32).astype(np.float64) @ self.db.astype(np.float64).T
+            idx = np.argsort(-s, axis=1, kind="stable")[:, :final_num_neighbors]
+            return idx.astype(np.uint32), np.take_along_axis(s, idx, 1).astype(np.float32)
+    ops = types.ModuleType("scann.scann_ops_pybind"); ops.builder = ExactScann
+    sc = types.ModuleType("scann"); sc.scann_ops_pybind = ops
+    sys.modules.update({"scann": sc, "scann.scann_ops_pybind": ops, "streamlit": types.ModuleType("streamlit")})
+    base = types.ModuleType("rdm.data.base"); base.PatcherDataset = object
+    sys.modules["rdm.data.base"] = base
+    sys.modules["ldm.util"].parallel_data_prefetch = None
+    sys.modules["omegaconf"].OmegaConf = object
+    sys.modules["pytorch_lightning"].seed_everything = lambda s: None
+    sys.modules.pop("rdm.data.retrieval_dataset.dsetbuilder", None)                # (neighbour_precompute() registered an empty stand-in)
+    import importlib
+    dsb = importlib.import_module("rdm.data.retrieval_dataset.dsetbuilder")       # the reference's
+    assert "/root/reference" in dsb.__file__
+    db, _, _ = ref_weights.make_db(N_DB)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "2022-01-01T00-00-00-db.npz")
+        np.savez(path, embedding=db, img_id=np.arange(N_DB) * 3, patch_coords=np.stack([np.arange(N_DB)] * 4, 1).astype(np.int32))
+        b = object.__new__(dsb.DatasetBuilder)
+        b.data_pool = {"embedding": [], "img_id": [], "patch_coords": []}
+        b.saved_embeddings, b.max_pool_size, b.k, b.distance_metric = path, 1000, 5, "dot_product"
+        b.searcher, b.searcher_savedir, b.save_searcher, b.visualize, b.gpu = None, None, False, False, False
+        b.retriever = retro_stub.PatchEmbedStub()
+        b.load_embeddings()
+        b.train_searcher()
+    out = {"n_db": np.int64(N_DB)}
+    q = ref_weights.tensor_for("dsb_queries", (3, 512), 81) * 22.0
+    q[0] = db[17].astype(np.float32)                                               # a database row as query
+    r = b.search_k_nearest(q, k=5, query_embedded=True)
+    out["embedded:queries"] = q
+    for key in ("embeddings", "img_ids", "patch_coords", "nns", "q_embeddings"):
+        out[f"embedded:{key}"] = np.asarray(r[key])
+    imgs = ref_weights.tensor_for("dsb_images", (2, 2, 8, 8, 3), 82)               # [b, n, h, w, c] patches in channel-last layout (:464-467)
+    r = b.search_k_nearest(torch.from_numpy(imgs), k=4, is_caption=False)
+    out["images:queries"] = imgs
+    for key in ("embeddings", "img_ids", "patch_coords", "nns", "q_embeddings"):
+        out[f"images:{key}"] = np.asarray(r[key])
+    save("ref_dsetbuilder.npz", out)
+
+
 if __name__ == "__main__":
     ref_stubs.install()
     unet_and_ddim()
@@ -420,3 +485,4 @@ if __name__ == "__main__":
     sampler_options()
     neighbour_precompute()
     rarm_sampling()
+    dataset_builder()

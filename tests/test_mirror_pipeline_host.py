@@ -87,3 +87,28 @@ def test_get_nn_and_encoding_matches_reference_code(model_and_golden):
         want = p[f"{tag}:nn_embeddings"]
         assert tuple(r[model.nn_key].shape) == want.shape == (2, n * n, 3, 512)
         assert np.array_equal(r[model.nn_key].numpy(), want), tag
+
+
+def test_dataset_builder_search_matches_reference_code(tmp_path, cpu_executors):  # noqa: F811
+    """tests/golden/ref_dsetbuilder.npz: the REFERENCE's DatasetBuilder.load_embeddings / train_searcher / embed / search_k_nearest over
+    an exact stand-in for scann's brute-force scorer (the reference normalises the fp16 rows itself, dsetbuilder.py:574).  The product's
+    DatasetBuilder must return the same neighbours and the same result arrays -- for embedded queries and for channel-last image patches."""
+    import retro_stub
+    import rdm  # noqa: F401
+    from rdm.data.retrieval_dataset.dsetbuilder import DatasetBuilder
+    g = np.load(os.path.join(GOLD, "ref_dsetbuilder.npz"))
+    n = int(g["n_db"])
+    db, _, _ = ref_weights.make_db(n)
+    np.savez(tmp_path / "db.npz", embedding=db, img_id=np.arange(n) * 3, patch_coords=np.stack([np.arange(n)] * 4, 1).astype(np.int32))
+    b = DatasetBuilder(retriever_config=None, saved_embeddings=str(tmp_path / "db.npz"), load_patch_dataset=False, gpu=False, k=5, max_pool_size=1000)
+    b._retriever = retro_stub.PatchEmbedStub()
+    b.train_searcher()
+    r = b.search_k_nearest(g["embedded:queries"], k=5, query_embedded=True)
+    assert np.array_equal(r["nns"], g["embedded:nns"]) and r["nns"][0, 0] == 17
+    for key in ("embeddings", "img_ids", "patch_coords", "q_embeddings"):
+        assert np.array_equal(np.asarray(r[key]), g[f"embedded:{key}"]), key
+    r = b.search_k_nearest(torch.from_numpy(g["images:queries"]), k=4, is_caption=False)
+    assert np.array_equal(r["nns"], g["images:nns"])
+    for key in ("embeddings", "img_ids", "patch_coords"):
+        assert np.array_equal(np.asarray(r[key]), g[f"images:{key}"]), key
+    assert np.allclose(np.asarray(r["q_embeddings"]), g["images:q_embeddings"], rtol=1e-6, atol=1e-6)
