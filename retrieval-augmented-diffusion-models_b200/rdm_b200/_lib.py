@@ -114,6 +114,21 @@ def stream_ptr(device=None):
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def resolve_device(device):
+    """torch.device with an explicit CUDA index; anything else is an error (the library has no CPU path)."""
+    import torch
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"librdm_b200 needs a CUDA device, got '{device}' (there is no CPU path)")
+    return device if device.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+
+def device_ctx(device):
+    """Context manager that makes `device` current for the duration of a library call."""
+    import torch
+    return torch.cuda.device(device)
+
+
 def ptr(t):
     """Device/host pointer of a contiguous tensor (or None)."""
     if t is None:

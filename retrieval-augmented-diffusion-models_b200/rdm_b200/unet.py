@@ -113,16 +113,14 @@ class B200UNet:
 
     def __init__(self, device, **cfg):
         L = _lib.lib()
-        self.device = torch.device(device)
-        if self.device.index is None:
-            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.device = _lib.resolve_device(device)
         self.cfg = dict(cfg)
         self.shapes = unet_param_shapes(**cfg)
         c = make_cfg(cfg["in_channels"], cfg["model_channels"], cfg["out_channels"], cfg["num_res_blocks"],
                      cfg["attention_resolutions"], cfg["channel_mult"], cfg.get("num_head_channels", 32),
                      cfg.get("num_heads", -1), cfg.get("transformer_depth", 1), cfg.get("context_dim", 512))
         self._h = ctypes.c_void_p()
-        _lib.check(L.rdm_unet_create(ctypes.byref(self._h), ctypes.byref(c), self.device.index), "rdm_unet_create")
+        _lib.check(L.rdm_unet_create(ctypes.byref(self._h), ctypes.byref(c), int(self.device.index or 0)), "rdm_unet_create")
         names = [L.rdm_unet_param_name(self._h, i).decode() for i in range(L.rdm_unet_num_params(self._h))]
         assert sorted(names) == sorted(self.shapes), "parameter inventory of csrc/unet.cu and unet_param_shapes() differ"
         for k, shp in self.shapes.items():
@@ -170,7 +168,7 @@ class B200UNet:
             context = context[0]
         context = context.to(self.device, torch.float32).contiguous()
         B2, k, d = context.shape
-        with torch.cuda.device(self.device):
+        with _lib.device_ctx(self.device):
             _lib.check(_lib.lib().rdm_unet_set_context(self._h, _lib.ptr(context), B2, k, _lib.stream_ptr(self.device)), "rdm_unet_set_context")
         self._ctx_B2 = B2
 
@@ -181,7 +179,7 @@ class B200UNet:
         B2, (Bx, _, H, W) = t.shape[0], x.shape
         if out is None:
             out = torch.empty((B2, self.cfg["out_channels"], H, W), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with _lib.device_ctx(self.device):
             _lib.check(_lib.lib().rdm_unet_forward(self._h, _lib.ptr(x), Bx, _lib.ptr(t), B2, H, W, _lib.ptr(out), _lib.stream_ptr(self.device)),
                        "rdm_unet_forward")
         return out
@@ -201,7 +199,7 @@ class B200UNet:
         B2, (Bx, _, H, W) = t.shape[0], x.shape
         out = torch.empty((B2, self.cfg["out_channels"], H, W), dtype=torch.float32, device=self.device)
         o8 = (ctypes.c_double * 8)()
-        with torch.cuda.device(self.device):
+        with _lib.device_ctx(self.device):
             _lib.check(_lib.lib().rdm_unet_profile_forward(self._h, _lib.ptr(x), Bx, _lib.ptr(t), B2, H, W, _lib.ptr(out), o8, _lib.stream_ptr(self.device)),
                        "rdm_unet_profile_forward")
         return dict(tc_ms=o8[0], tc_flop=o8[1], simt_ms=o8[2], simt_flop=o8[3], total_ms=o8[4], n_tc=int(o8[5]), n_simt=int(o8[6]))
@@ -214,7 +212,7 @@ class B200UNet:
         S = timesteps.shape[0]
         num_steps = S - first_step if num_steps is None else num_steps
         p0 = torch.empty_like(x) if want_pred_x0 else None
-        with torch.cuda.device(self.device):
+        with _lib.device_ctx(self.device):
             _lib.check(_lib.lib().rdm_ddim_sample(self._h, _lib.ptr(x), B, H, W, _lib.ptr(timesteps), _lib.ptr(coef), int(first_step), int(num_steps),
                                                   float(cfg_scale), _lib.ptr(noise), _lib.ptr(p0), _lib.stream_ptr(self.device)), "rdm_ddim_sample")
         return (x, p0) if want_pred_x0 else x
@@ -226,9 +224,9 @@ def ddim_step(x, eps, coef_row, cfg_scale=None, noise=None, want_pred_x0=True):
     x, eps = x.contiguous(), eps.contiguous()
     xp = torch.empty_like(x)
     p0 = torch.empty_like(x) if want_pred_x0 else None
-    with torch.cuda.device(x.device):
+    with _lib.device_ctx(x.device):
         _lib.check(_lib.lib().rdm_ddim_step(_lib.ptr(x), _lib.ptr(eps), x.numel(), 1 if cfg_scale is not None else 0,
                                             float(cfg_scale if cfg_scale is not None else 1.0), _lib.ptr(coef_row),
                                             _lib.ptr(noise.contiguous() if noise is not None else None), _lib.ptr(xp), _lib.ptr(p0),
-                                            x.device.index, _lib.stream_ptr(x.device)), "rdm_ddim_step")
+                                            int(x.device.index or 0), _lib.stream_ptr(x.device)), "rdm_ddim_step")
     return xp, p0

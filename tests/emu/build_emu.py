@@ -1,4 +1,4 @@
-"""Builds tests/emu/_build/librdm_emu.so: csrc/rarm.cu + csrc/common.cu compiled by g++ against the host emulation of CUDA in
+"""Builds tests/emu/_build/librdm_emu.so: the SIMT translation units of csrc/ (rarm.cu, unet.cu, kernels.cu, gemm_simt.cu, common.cu) compiled by g++ against the host emulation of CUDA in
 tests/emu/include (see cuda_runtime.h there).  The sources are used as written except for two mechanical rewrites:
   kernel<<<grid, block, smem, stream>>>(args);   ->  emu::launch(kernel, grid, block, smem, stream, args);
   extern __shared__ T name[];                    ->  T* name = (T*)emu::dyn_smem;
@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "retrieval-augmented-diffusion-models_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-UNITS = ("rarm.cu", "common.cu")
+UNITS = ("rarm.cu", "common.cu", "unet.cu", "kernels.cu", "gemm_simt.cu")
 
 
 def rewrite(src):
@@ -26,18 +26,22 @@ def rewrite(src):
 
 def build(verbose=False):
     os.makedirs(OUT, exist_ok=True)
-    inputs = [os.path.join(CSRC, u) for u in UNITS] + [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "rdm_b200.h"), os.path.join(HERE, "emu_core.cpp"),
-                                                       __file__] + [os.path.join(HERE, "include", f) for f in sorted(os.listdir(os.path.join(HERE, "include")))]
+    inputs = [os.path.join(CSRC, u) for u in UNITS] + [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "rdm_b200.h"), os.path.join(HERE, "emu_core.cpp"), os.path.join(HERE, "tc_stubs.cpp"),
+                                                       os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "gemm_tc.cuh"), __file__] + [os.path.join(HERE, "include", f) for f in sorted(os.listdir(os.path.join(HERE, "include")))]
     h = hashlib.sha1()
     for p in inputs:
         h.update(open(p, "rb").read())
     lib, stamp = os.path.join(OUT, "librdm_emu.so"), os.path.join(OUT, "stamp")
     if os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
         return lib
-    cpps = [os.path.join(HERE, "emu_core.cpp")]
+    stubs = os.path.join(OUT, "tc_stubs_emu.cpp")
+    open(stubs, "w").write(open(os.path.join(HERE, "tc_stubs.cpp")).read().replace('#include "gemm_tc.cuh"', f'#include "{os.path.join(CSRC, "gemm_tc.cuh")}"'))
+    cpps = [os.path.join(HERE, "emu_core.cpp"), stubs]
     for u in UNITS:
         text = rewrite(open(os.path.join(CSRC, u)).read())
-        text = text.replace('#include "common.cuh"', f'#include "{os.path.join(CSRC, "common.cuh")}"').replace('#include "../../include/rdm_b200.h"', f'#include "{os.path.join(ROOT, "include", "rdm_b200.h")}"')
+        for hdr in ("common.cuh", "kernels.cuh", "gemm_tc.cuh"):               # headers of csrc/ by absolute path ("ptx.cuh" resolves to the emulation's)
+            text = text.replace(f'#include "{hdr}"', f'#include "{os.path.join(CSRC, hdr)}"')
+        text = text.replace('#include "../../include/rdm_b200.h"', f'#include "{os.path.join(ROOT, "include", "rdm_b200.h")}"')
         dst = os.path.join(OUT, u.replace(".cu", "_emu.cpp"))
         open(dst, "w").write(text)
         cpps.append(dst)

@@ -185,8 +185,23 @@ cudaError_t cudaFree(void* p) {
     fprintf(stderr, "emu: cudaFree of an unknown pointer\n"); abort();
 }
 cudaError_t cudaMemset(void* p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t) {
+    if (emu::t_capture.on) { emu::t_capture.graph->nodes.push_back([=]() { memset(p, v, bytes); }); return cudaSuccess; }      // a memset node of the captured graph
+    memset(p, v, bytes); return cudaSuccess;
+}
+struct EmuEvent { int id; };
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new EmuEvent{0}; return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventRecordWithFlags(cudaEvent_t, cudaStream_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t bytes, cudaMemcpyKind) { memmove(d, s, bytes); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(d, s, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t bytes, cudaMemcpyKind, cudaStream_t) {
+    if (emu::t_capture.on) { emu::t_capture.graph->nodes.push_back([=]() { memmove(d, s, bytes); }); return cudaSuccess; }     // a memcpy node: pointers baked, data read at replay
+    memmove(d, s, bytes); return cudaSuccess;
+}
 cudaError_t cudaMemcpy2D(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind) {
     for (size_t r = 0; r < height; r++) memmove((char*)d + r * dpitch, (const char*)s + r * spitch, width);
     return cudaSuccess;

@@ -35,3 +35,8 @@ inline float __half2float(__half hh) {
     float f; memcpy(&f, &u, 4); return f;
 }
 inline float2 __half22float2(__half2 h) { return make_float2(__half2float(h.x), __half2float(h.y)); }
+inline unsigned short __half_as_ushort(__half h) { return h.x; }
+inline __half __ushort_as_half(unsigned short u) { __half h; h.x = u; return h; }
+inline __half2 __floats2half2_rn(float a, float b) { __half2 r; r.x = __float2half_rn(a); r.y = __float2half_rn(b); return r; }
+inline float __low2float(__half2 h) { return __half2float(h.x); }
+inline float __high2float(__half2 h) { return __half2float(h.y); }

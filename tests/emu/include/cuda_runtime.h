@@ -68,6 +68,16 @@ struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes; cud
 cudaError_t cudaMalloc(void** p, size_t bytes);
 cudaError_t cudaFree(void* p);
 cudaError_t cudaMemset(void* p, int v, size_t bytes);
+cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t st = nullptr);
+typedef struct EmuEvent* cudaEvent_t;
+enum { cudaEventRecordDefault = 0, cudaEventRecordExternal = 1 };
+cudaError_t cudaEventCreate(cudaEvent_t* e);
+cudaError_t cudaEventDestroy(cudaEvent_t e);
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = nullptr);
+cudaError_t cudaEventRecordWithFlags(cudaEvent_t e, cudaStream_t st, unsigned flags);
+cudaError_t cudaEventSynchronize(cudaEvent_t e);
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
+cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaMemcpy(void* d, const void* s, size_t bytes, cudaMemcpyKind k);
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t bytes, cudaMemcpyKind k, cudaStream_t st = nullptr);
 cudaError_t cudaMemcpy2D(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind k);
@@ -87,7 +97,6 @@ cudaError_t cudaGetDevice(int* d);
 cudaError_t cudaSetDevice(int d);
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int dev);
 template <typename F> cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
-template <typename... KArgs, typename... Args> cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t*, void (*)(KArgs...), Args&&...) { return cudaErrorEmu; }
 
 // ---- device-side intrinsics -------------------------------------------------------------------------------------------
 namespace emu {
@@ -101,6 +110,12 @@ void launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStre
     auto body = [=]() { kern(static_cast<KArgs>(args)...); };          // arguments captured BY VALUE at launch time
     run_launch(grid, block, smem, st, body);
 }
+}  // namespace emu
+template <typename... KArgs, typename... Args> cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kern)(KArgs...), Args&&... args) {
+    emu::launch(kern, cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, cfg->stream, static_cast<KArgs>(args)...);       // launch attributes (PDL) have no functional effect
+    return cudaSuccess;
+}
+namespace emu {
 template <typename T> inline uint64_t to_bits(T v) { uint64_t b = 0; static_assert(sizeof(T) <= 8, "shuffle of > 8 bytes"); memcpy(&b, &v, sizeof(T)); return b; }
 template <typename T> inline T from_bits(uint64_t b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
 }  // namespace emu
@@ -121,6 +136,22 @@ inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
-inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }            // fibers of a block never run concurrently
+// atomics: shared-memory targets are only touched by the fibers of one block (never concurrent); GLOBAL targets can be hit by blocks on
+// other OS threads, so the read-modify-write is a real atomic either way
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+template <typename F, typename U> inline F emu_atomic_add_fp(F* p, F v) {
+    U* q = reinterpret_cast<U*>(p); U old = __atomic_load_n(q, __ATOMIC_RELAXED), neu; F f;
+    do { memcpy(&f, &old, sizeof(F)); F r = f + v; memcpy(&neu, &r, sizeof(F)); } while (!__atomic_compare_exchange_n(q, &old, neu, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    return f;
+}
+inline float atomicAdd(float* p, float v) { return emu_atomic_add_fp<float, uint32_t>(p, v); }
+inline double atomicAdd(double* p, double v) { return emu_atomic_add_fp<double, uint64_t>(p, v); }
+inline float __frcp_rn(float x) { volatile float r = 1.0f / x; return r; }
+inline float __expf(float x) { return expf(x); }
+inline void __syncwarp(unsigned = 0xffffffffu) {}                     // the lanes of a warp only interleave at emulated exchange points
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+#define __align__(n) __attribute__((aligned(n)))
 inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; if (v > o) *p = v; return o; }

@@ -1,0 +1,13 @@
+// The tensor-core engine (gemm_tc.cu, attention_mma.cu: tcgen05 / TMA / mma.sync PTX) cannot be emulated on the host.  These stand-ins make
+// the SIMT translation units link; the strict fp32 mode of the executors never calls them, every other mode fails loudly.
+#include "gemm_tc.cuh"
+bool gemm_tc_supported(const TcA&) { return true; }     // shape support is a property of the engine, not of the emulation: the call itself reports the error
+int gemm_tc(const TcA&, const TcW&, const GemmEpi&, __nv_bfloat16*, __nv_bfloat16*, int, int, int, cudaStream_t) {
+    rdm_set_error("emulation: the tcgen05 GEMM engine is not available on the host (use RDM_UNET_MODE_FP32)");
+    return RDM_ERR_UNSUPPORTED;
+}
+bool k_attention_mma_supported(int, int) { return false; }
+int k_attention_mma(const __half*, const __half*, const __half*, int, int, int, int, int, float, Out4, cudaStream_t) {
+    rdm_set_error("emulation: the warp-MMA attention kernel is not available on the host");
+    return RDM_ERR_UNSUPPORTED;
+}
