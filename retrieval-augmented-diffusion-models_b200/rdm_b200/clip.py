@@ -31,13 +31,11 @@ def cfg_from_state_dict(sd):
 class B200Clip:
     def __init__(self, device, **cfg):
         L = _lib.lib()
-        self.device = torch.device(device)
-        if self.device.index is None:
-            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.device = _lib.resolve_device(device)
         self.cfg = dict(cfg)
         c = ClipCfg(**{k: int(cfg[k]) for k, _ in ClipCfg._fields_})
         self._h = ctypes.c_void_p()
-        _lib.check(L.rdm_clip_create(ctypes.byref(self._h), ctypes.byref(c), self.device.index), "rdm_clip_create")
+        _lib.check(L.rdm_clip_create(ctypes.byref(self._h), ctypes.byref(c), int(self.device.index or 0)), "rdm_clip_create")
         self.names = [L.rdm_clip_param_name(self._h, i).decode() for i in range(L.rdm_clip_num_params(self._h))]
 
     def __del__(self):
@@ -69,7 +67,7 @@ class B200Clip:
         tokens = tokens.to(self.device, torch.int64).contiguous()
         assert tokens.ndim == 2 and tokens.shape[1] == self.cfg["context_length"]
         out = torch.empty((tokens.shape[0], self.cfg["embed_dim"]), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with _lib.device_ctx(self.device):
             _lib.check(_lib.lib().rdm_clip_encode_text(self._h, _lib.ptr(tokens), tokens.shape[0], _lib.ptr(out), _lib.stream_ptr(self.device)), "rdm_clip_encode_text")
         return out
 
@@ -78,7 +76,7 @@ class B200Clip:
         R = self.cfg["image_resolution"]
         assert tuple(image.shape[1:]) == (3, R, R), f"encode_image expects [B,3,{R},{R}] (preprocessed)"
         out = torch.empty((image.shape[0], self.cfg["embed_dim"]), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with _lib.device_ctx(self.device):
             _lib.check(_lib.lib().rdm_clip_encode_image(self._h, _lib.ptr(image), image.shape[0], _lib.ptr(out), _lib.stream_ptr(self.device)), "rdm_clip_encode_image")
         return out
 
@@ -86,7 +84,7 @@ class B200Clip:
         x = x.to(self.device, torch.float32).contiguous()
         size = size or self.cfg["image_resolution"]
         out = torch.empty((x.shape[0], 3, size, size), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().rdm_clip_preprocess(_lib.ptr(x), x.shape[0], x.shape[2], x.shape[3], size, _lib.ptr(out), self.device.index,
+        with _lib.device_ctx(self.device):
+            _lib.check(_lib.lib().rdm_clip_preprocess(_lib.ptr(x), x.shape[0], x.shape[2], x.shape[3], size, _lib.ptr(out), int(self.device.index or 0),
                                                       _lib.stream_ptr(self.device)), "rdm_clip_preprocess")
         return out

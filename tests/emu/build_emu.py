@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "retrieval-augmented-diffusion-models_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-UNITS = ("rarm.cu", "common.cu", "unet.cu", "kernels.cu", "gemm_simt.cu")
+UNITS = ("rarm.cu", "common.cu", "unet.cu", "kernels.cu", "gemm_simt.cu", "clip.cu")
 
 
 def rewrite(src):
