@@ -65,7 +65,11 @@ def unet_and_ddim():
     ctx = torch.randn(4, 3, 512, generator=g)
     with torch.no_grad():
         y = net(x, t, context=[ctx])                                         # the list form RETRODiffusionWrapper passes (ddpm.py:128-131)
+    xs, ts_, cs = torch.randn(2, 4, 8, 8, generator=g), torch.tensor([991, 42]), torch.randn(2, 2, 512, generator=g)       # a small case for the emulated CUDA path
+    with torch.no_grad():
+        ys = net(xs, ts_, context=[cs])
     out = {"cfg_json": np.array(repr(UNET_CFG)), "x": x.numpy(), "t": t.numpy(), "context": ctx.numpy(), "out": y.numpy(), "weight_seed": np.int64(11),
+           "small:x": xs.numpy(), "small:t": ts_.numpy(), "small:context": cs.numpy(), "small:out": ys.numpy(),
            "sd_keys": np.array(list(net.state_dict().keys())), "n_params": np.int64(sum(p.numel() for p in net.parameters()))}
     save("ref_unet_tiny.npz", out)
 

@@ -93,3 +93,20 @@ def test_fused_guided_ddim_loop_matches_the_pinned_oracle(emulated):
     sch = oddim.Schedule(S)
     wx, wp = oddim.ddim_update(x_T, e, *sch.coeffs(S - 2))
     assert torch.equal(xp, wx) and torch.equal(pp, wp)
+
+
+def test_strict_forward_matches_reference_code(emulated):
+    """The product's CUDA source (strict mode, emulated) against the output of the REFERENCE's own UNetModel.forward
+    (tests/golden/ref_unet_tiny.npz, small case): no oracle in between."""
+    import ast
+    from rdm_b200.unet import B200UNet
+    d = np.load(os.path.join(ROOT, "tests", "golden", "ref_unet_tiny.npz"))
+    cfg = ast.literal_eval(str(d["cfg_json"]))
+    cfg.pop("use_spatial_transformer")
+    net = B200UNet("cpu", **cfg)
+    assert list(net.shapes) == [str(k) for k in d["sd_keys"]]
+    net.load_state_dict(ref_weights.state_dict_for(net.shapes.items(), int(d["weight_seed"])))
+    net.set_mode(0)
+    net.set_context(torch.from_numpy(d["small:context"]))
+    got = net.forward(torch.from_numpy(d["small:x"]), torch.from_numpy(d["small:t"]))
+    assert rel(got, torch.from_numpy(d["small:out"])) < 1e-5
