@@ -28,7 +28,8 @@ struct BlockRun {
     const std::function<void()>* body = nullptr;
 };
 thread_local BlockRun* t_run = nullptr;
-thread_local std::vector<char*>* t_stacks = nullptr;
+struct StackPool { std::vector<char*> v; ~StackPool() { for (char* p : v) free(p); } };      // freed when the worker thread of a launch exits
+thread_local StackPool t_stacks;
 
 void fiber_entry() {
     BlockRun* r = t_run;
@@ -50,8 +51,7 @@ void yield_to_scheduler() {
 
 void run_block(const std::function<void()>& body, dim3 grid, dim3 block, uint3 bidx, size_t smem) {
     const int n = (int)(block.x * block.y * block.z);
-    if (!t_stacks) t_stacks = new std::vector<char*>();
-    while ((int)t_stacks->size() < n) t_stacks->push_back((char*)aligned_alloc(64, STACK_BYTES));
+    while ((int)t_stacks.v.size() < n) t_stacks.v.push_back((char*)aligned_alloc(64, STACK_BYTES));
     std::vector<char> shared(smem + 64 + 64, (char)0x5A);                      // 64-byte guard after the dynamic shared memory of the block
     dyn_smem = (void*)(((uintptr_t)shared.data() + 63) & ~(uintptr_t)63);
     BlockRun run;
@@ -61,7 +61,7 @@ void run_block(const std::function<void()>& body, dim3 grid, dim3 block, uint3 b
         f.linear = i; f.tid = uint3{(unsigned)(i % block.x), (unsigned)((i / block.x) % block.y), (unsigned)(i / (block.x * block.y))};
         run.warps[i / 32].live++;
         getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = (*t_stacks)[i]; f.ctx.uc_stack.ss_size = STACK_BYTES; f.ctx.uc_link = nullptr;
+        f.ctx.uc_stack.ss_sp = t_stacks.v[i]; f.ctx.uc_stack.ss_size = STACK_BYTES; f.ctx.uc_link = nullptr;
         makecontext(&f.ctx, fiber_entry, 0);
     }
     t_run = &run;
