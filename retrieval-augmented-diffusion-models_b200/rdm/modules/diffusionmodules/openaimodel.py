@@ -9,6 +9,7 @@ import os
 import torch
 import torch.nn as nn
 
+from rdm_b200 import _lib as _binding
 from rdm_b200.unet import B200UNet, unet_param_shapes
 
 _MODES = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp16x2": 3, "fp16": 4}
@@ -76,9 +77,7 @@ class UNetModel(nn.Module):
         return ("params",) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def engine(self, device):
-        device = torch.device(device)
-        if device.type != "cuda":
-            raise RuntimeError("rdm UNetModel (B200 build) has no CPU path: move the model to a CUDA device")
+        device = _binding.resolve_device(device)          # raises for anything but a CUDA device: there is no CPU path
         if self._engine is None or self._engine.device != device:
             self._engine, self._loaded_key, self._ctx_key = B200UNet(device, **self._cfg), None, None
         key = self._weights_key() + (self.engine_mode,)

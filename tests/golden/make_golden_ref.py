@@ -219,6 +219,11 @@ def pipeline():
     out["rdata:qids"], out["rdata:x_T"], out["rdata:samples"] = qids, xT.numpy(), logs["samples_with_sampled_nns"].numpy()
     np.random.seed(45)
     out["qids_weighted"] = model.get_qids(0.4, 5, use_weights=True)
+    # (1b) a small case for the product's emulated CUDA path: one image, two steps, an 8 x 8 latent through `custom_shape` (ddpm.py:994-1001)
+    xs = torch.randn(1, 4, 8, 8, generator=g)
+    logs = model.sample_from_rdata(1, qids=np.array([123]), k_nn=K_NN, x_T=xs.clone(), custom_shape=(4, 8, 8), unconditional_guidance_scale=2.0,
+                                   ddim_steps=2, ddim=True, unconditional_retro_guidance_label=0.)
+    out["rdata_small:x_T"], out["rdata_small:samples"] = xs.numpy(), logs["samples_with_sampled_nns"].numpy()
     # (2) scripts/rdm_sample.py:272-299: an embedded (text) query, prepended as neighbour 0; and omit_query
     q = torch.from_numpy(ref_weights.tensor_for("query", (2, 512), 46) * 22.0)
     for tag, extra in (("query", dict(omit_query=False)), ("query_omit", dict(omit_query=True)), ("query_normalize", dict(normalize=True)),

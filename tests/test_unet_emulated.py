@@ -110,3 +110,35 @@ def test_strict_forward_matches_reference_code(emulated):
     net.set_context(torch.from_numpy(d["small:context"]))
     got = net.forward(torch.from_numpy(d["small:x"]), torch.from_numpy(d["small:t"]))
     assert rel(got, torch.from_numpy(d["small:out"])) < 1e-5
+
+
+def test_product_pipeline_on_the_emulated_engine_matches_reference_code(emulated, monkeypatch, tmp_path):
+    """`MinimalRETRODiffusion.sample_from_rdata` of this repository end to end -- host orchestration, EMA weights handed to the engine,
+    DDIMSampler's fused loop, and the product's U-Net / DDIM kernels (strict mode, emulated) -- against the latents the REFERENCE's own
+    MinimalRETRODiffusion produced for the same checkpoint, database, query id and x_T (tests/golden/ref_pipeline_tiny.npz, small case:
+    one image, two guided steps, an 8 x 8 latent via `custom_shape`).  Only the kNN scan (TMA kernels) is played by the oracle."""
+    import copy
+    import rdm  # noqa: F401
+    import rdm.data.retrieval_dataset.dsetbuilder as dsb
+    from ldm.util import instantiate_from_config
+    from omegaconf import OmegaConf
+    from rdm_b200.unet import unet_param_shapes
+    from test_mirror_host import TINY_CFG
+    from test_reference_scripts import CpuSearcher
+    monkeypatch.setattr(dsb, "B200Searcher", CpuSearcher)
+    p = np.load(os.path.join(ROOT, "tests", "golden", "ref_pipeline_tiny.npz"))
+    db, _, _ = ref_weights.make_db(int(p["n_db"]))
+    np.savez(tmp_path / "db.npz", embedding=db, img_id=np.arange(len(db)), patch_coords=np.zeros((len(db), 4), np.int32))
+    cfg = copy.deepcopy(TINY_CFG)
+    cfg["params"]["retrieval_cfg"]["params"]["saved_embeddings"] = str(tmp_path / "db.npz")
+    model = instantiate_from_config(OmegaConf.create(cfg))
+    shapes = unet_param_shapes(**ounet.TINY_UNET)
+    live, ema = (ref_weights.state_dict_for(shapes.items(), int(p[s])) for s in ("live_seed", "ema_seed"))
+    ck = {"model.diffusion_model." + k: v for k, v in live.items()}
+    ck.update({"model_ema." + ("diffusion_model." + k).replace(".", ""): v for k, v in ema.items()})
+    model.load_state_dict(ck, strict=False)
+    model = model.eval()
+    model.model.diffusion_model.engine_mode = "fp32"
+    logs = model.sample_from_rdata(1, qids=np.array([123]), k_nn=4, x_T=torch.from_numpy(p["rdata_small:x_T"]), custom_shape=(4, 8, 8),
+                                   unconditional_guidance_scale=2.0, ddim_steps=2, ddim=True, unconditional_retro_guidance_label=0.)
+    assert rel(logs["samples_with_sampled_nns"], torch.from_numpy(p["rdata_small:samples"])) < 1e-5
