@@ -27,10 +27,8 @@ class B200Searcher:
     def __init__(self, embedding, device=None, idx_base=0):
         L = _lib.lib()
         if device is None:
-            device = embedding.device if isinstance(embedding, torch.Tensor) and embedding.is_cuda else torch.device("cuda", torch.cuda.current_device())
-        self.device = torch.device(device)
-        if self.device.index is None:
-            self.device = torch.device("cuda", torch.cuda.current_device())
+            device = embedding.device if isinstance(embedding, torch.Tensor) and embedding.is_cuda else "cuda"
+        self.device = _lib.resolve_device(device)
         if isinstance(embedding, np.ndarray):
             if embedding.dtype not in (np.float16, np.float32):
                 embedding = embedding.astype(np.float32)
@@ -43,7 +41,7 @@ class B200Searcher:
         self.idx_base = int(idx_base)
         self._h = ctypes.c_void_p()
         _lib.check(L.rdm_knn_create(ctypes.byref(self._h), _lib.ptr(self._db), self.n, self.d, _DT[self._db.dtype], 1,
-                                    self.idx_base, self.device.index), "rdm_knn_create")
+                                    self.idx_base, int(self.device.index or 0)), "rdm_knn_create")
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -56,13 +54,13 @@ class B200Searcher:
     # ---- device-level API (no host round trip) -------------------------------------------------------
     def search_device(self, q_hat, k, return_scores=False):
         """q_hat: CUDA float32 [nq, d], already L2-normalised -> (idx int64 [nq,k], dist float32 [nq,k][, score float64])."""
-        assert q_hat.is_cuda and q_hat.dtype == torch.float32 and q_hat.shape[1] == self.d
+        assert q_hat.device == self.device and q_hat.dtype == torch.float32 and q_hat.shape[1] == self.d, "queries must be float32 [nq, d] on the searcher's device"
         q_hat = q_hat.contiguous()
         nq = q_hat.shape[0]
         idx = torch.empty((nq, k), dtype=torch.int64, device=self.device)
         dist = torch.empty((nq, k), dtype=torch.float32, device=self.device)
         sc = torch.empty((nq, k), dtype=torch.float64, device=self.device) if return_scores else None
-        with torch.cuda.device(self.device):
+        with _lib.device_ctx(self.device):
             _lib.check(_lib.lib().rdm_knn_search(self._h, _lib.ptr(q_hat), nq, k, _lib.ptr(idx), _lib.ptr(dist), _lib.ptr(sc),
                                                   _lib.stream_ptr(self.device)), "rdm_knn_search")
         return (idx, dist, sc) if return_scores else (idx, dist)
@@ -71,14 +69,14 @@ class B200Searcher:
         """``data_pool['embedding'][nns]`` as float32 on the device (ddpm.py:921): idx int64 [...] -> [..., d]."""
         flat = idx.reshape(-1).to(self.device, torch.int64).contiguous()
         out = torch.empty((flat.numel(), self.d), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with _lib.device_ctx(self.device):
             _lib.check(_lib.lib().rdm_knn_gather(self._h, _lib.ptr(flat), flat.numel(), _lib.ptr(out), _lib.stream_ptr(self.device)),
                        "rdm_knn_gather")
         return out.reshape(*idx.shape, self.d)
 
     def inv_norms(self):
         out = torch.empty(self.n, dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with _lib.device_ctx(self.device):
             _lib.check(_lib.lib().rdm_knn_get_inv_norms(self._h, _lib.ptr(out), _lib.stream_ptr(self.device)), "rdm_knn_get_inv_norms")
         return out
 
@@ -103,9 +101,9 @@ def merge_device(idx_parts, score_parts, k):
     idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
     dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
     sc = torch.empty((nq, k), dtype=torch.float64, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_ctx(dev):
         _lib.check(_lib.lib().rdm_knn_merge(_lib.ptr(idx_parts.contiguous()), _lib.ptr(score_parts.contiguous()), parts, nq, k,
-                                             _lib.ptr(idx), _lib.ptr(dist), _lib.ptr(sc), dev.index, _lib.stream_ptr(dev)), "rdm_knn_merge")
+                                             _lib.ptr(idx), _lib.ptr(dist), _lib.ptr(sc), int(dev.index or 0), _lib.stream_ptr(dev)), "rdm_knn_merge")
     return idx, dist, sc
 
 

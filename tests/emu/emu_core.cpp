@@ -118,6 +118,24 @@ uint64_t warp_exchange(uint64_t mine, int src_lane) {
     return w.slot[par][src_lane];                     // double-buffered: the next exchange of this warp writes the other parity
 }
 
+const uint64_t* warp_all(uint64_t mine) {
+    BlockRun* r = t_run;
+    Fiber& f = r->fibers[r->cur];
+    const int wi = f.linear / 32, lane = f.linear & 31;
+    Warp& w = r->warps[wi];
+    const int par = w.parity;
+    w.slot[par][lane] = mine;
+    if (++w.arrived == w.live) {
+        for (int l = 0; l < 32; l++) { int i = wi * 32 + l; if (i < (int)r->fibers.size() && r->fibers[i].state == WAIT_WARP) r->fibers[i].state = READY; }
+        w.arrived = 0; w.parity ^= 1;
+    } else {
+        f.state = WAIT_WARP;
+        yield_to_scheduler();
+    }
+    return w.slot[par];
+}
+void yield() { yield_to_scheduler(); }                 // stays READY: resumed on the scheduler's next round
+
 void run_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, std::function<void()> body) {
     if (t_capture.on) {                               // stream capture: record, do not execute
         t_capture.graph->nodes.push_back([=]() { Capture saved = t_capture; t_capture.on = false; run_launch(grid, block, smem, nullptr, body); t_capture = saved; });

@@ -66,6 +66,7 @@ struct cudaLaunchAttribute { cudaLaunchAttributeID id; struct { int programmatic
 struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes; cudaStream_t stream; cudaLaunchAttribute* attrs; unsigned numAttrs; };
 
 cudaError_t cudaMalloc(void** p, size_t bytes);
+template <typename T> cudaError_t cudaMalloc(T** p, size_t bytes) { return cudaMalloc((void**)p, bytes); }      // the runtime's C++ overload
 cudaError_t cudaFree(void* p);
 cudaError_t cudaMemset(void* p, int v, size_t bytes);
 cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t st = nullptr);
@@ -102,6 +103,8 @@ template <typename F> cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int
 namespace emu {
 void sync_block();
 uint64_t warp_exchange(uint64_t mine, int src_lane);       // returns the value posted by lane `src_lane` of the caller's warp (all 32 lanes call)
+const uint64_t* warp_all(uint64_t mine);                   // posts `mine`, waits for the warp, returns the 32 posted values (valid until the warp's next exchange)
+void yield();                                              // lets the other threads of the block run (spin loops on memory another thread will write)
 int lane_id();
 extern thread_local void* dyn_smem;
 void run_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, std::function<void()> thread_body);
@@ -150,7 +153,32 @@ inline float atomicAdd(float* p, float v) { return emu_atomic_add_fp<float, uint
 inline double atomicAdd(double* p, double v) { return emu_atomic_add_fp<double, uint64_t>(p, v); }
 inline float __frcp_rn(float x) { volatile float r = 1.0f / x; return r; }
 inline float __expf(float x) { return expf(x); }
-inline void __syncwarp(unsigned = 0xffffffffu) {}                     // the lanes of a warp only interleave at emulated exchange points
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_exchange(0, 0); }      // a real rendezvous: lanes run one after the other between yield points
+inline unsigned __ballot_sync(unsigned, int pred) { const uint64_t* v = emu::warp_all(pred ? 1 : 0); unsigned m = 0; for (int l = 0; l < 32; l++) m |= (unsigned)(v[l] & 1u) << l; return m; }
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+// a failed compare-and-swap is a yield point, so spin locks make progress under cooperative scheduling
+template <typename T> inline T emu_atomic_cas(T* p, T cmp, T val) {
+    T expected = cmp;
+    if (__atomic_compare_exchange_n(p, &expected, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) return cmp;
+    emu::yield();
+    return expected;
+}
+inline int atomicCAS(int* p, int c, int v) { return emu_atomic_cas(p, c, v); }
+inline unsigned atomicCAS(unsigned* p, unsigned c, unsigned v) { return emu_atomic_cas(p, c, v); }
+inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long c, unsigned long long v) { return emu_atomic_cas(p, c, v); }
+inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+template <typename T> inline T __ldcs(const T* p) { return *p; }
+template <typename T> inline T __ldcg(const T* p) { return *(const volatile T*)p; }
+inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+inline long long clock64() { return 0; }
+inline void __trap() { fprintf(stderr, "emu: __trap()\n"); abort(); }
+template <typename F> cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return cudaSuccess; }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 #define __align__(n) __attribute__((aligned(n)))
 inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }

@@ -11,3 +11,14 @@ int k_attention_mma(const __half*, const __half*, const __half*, int, int, int, 
     rdm_set_error("emulation: the warp-MMA attention kernel is not available on the host");
     return RDM_ERR_UNSUPPORTED;
 }
+
+// tensor-core kNN scans (knn_tc.cu): the searcher is driven with RDM_KNN_NO_TC=1 under emulation
+#include "knn_tc.cuh"
+int knn_tc_queries_bytes() { return 256; }
+int knn_tc_pass_queries(int) { return 16; }
+long long knn_tc_sample_rows(long long, int) { return 0; }
+int knn_scan_tc(const void*, const float*, long long, int, const float*, int, void*, int, int, unsigned long long*, long long, const unsigned long long*, unsigned long long*,
+                unsigned*, cudaStream_t) {
+    rdm_set_error("emulation: the tcgen05 kNN scan is not available on the host (set RDM_KNN_NO_TC=1)");
+    return RDM_ERR_UNSUPPORTED;
+}

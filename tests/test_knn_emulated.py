@@ -1,0 +1,75 @@
+"""CPU: the SIMT path of the exact cosine searcher -- csrc/knn.cu as written (row scan with per-warp bulk-copy rings and mbarriers,
+sample / threshold / main / select kernels, locked fallback lists, shard merge, raw-row gather) -- under the host emulation of CUDA
+(tests/emu/), through the C ABI and the product's Python wrapper, bit-exact against the oracle (indices AND fp64 scores).  The
+tensor-core scan of knn_tc.cu needs hardware: RDM_KNN_NO_TC=1 routes every batch through the SIMT kernels, as tests/test_knn_gpu.py
+does for its comparison of the two."""
+import contextlib
+import ctypes
+import os
+import shutil
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import knn as oknn
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ to build the emulated library")
+
+
+@pytest.fixture()
+def emulated(monkeypatch):
+    os.environ["RDM_KNN_NO_TC"] = "1"                      # read once by the library, before the first fp16 / d = 512 search
+    import build_emu
+    from rdm_b200 import _lib
+    L = _lib.bind(ctypes.CDLL(build_emu.build()), [n for n in _lib.SIGNATURES if n.startswith("rdm_knn_")] + ["rdm_last_error", "rdm_launch_count"])
+    monkeypatch.setattr(_lib, "_lib", L)
+    monkeypatch.setattr(_lib, "resolve_device", lambda d: torch.device("cpu"))
+    monkeypatch.setattr(_lib, "device_ctx", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(_lib, "stream_ptr", lambda d=None: None)
+    return L
+
+
+def check(db, q, k, idx_base=0):
+    from rdm_b200.knn import B200Searcher
+    s = B200Searcher(db, device="cpu", idx_base=idx_base)
+    qh = oknn.normalize_queries(q)
+    idx, dist, sc = s.search_device(torch.from_numpy(qh), k, return_scores=True)
+    wi, wd, ws = oknn.search(db, qh, k, idx_base=idx_base, return_scores=True)
+    assert np.array_equal(idx.numpy(), wi), "neighbour indices"
+    assert np.array_equal(sc.numpy().view(np.int64), ws.view(np.int64)), "fp64 scores, bit patterns"
+    assert np.array_equal(dist.numpy(), wd)
+    return s, wi
+
+
+@pytest.mark.parametrize("dtype", [np.float16, np.float32])
+@pytest.mark.parametrize("n,nq,k", [(3001, 1, 4), (2500, 5, 8), (999, 16, 24), (40, 2, 4)])
+def test_search_is_bit_exact(emulated, dtype, n, nq, k):
+    rng = np.random.default_rng(n + nq)
+    db = (rng.standard_normal((n, 512)) * rng.uniform(0.5, 8, (n, 1))).astype(dtype)
+    q = rng.standard_normal((nq, 512)).astype(np.float32)
+    q[0] = db[n // 2].astype(np.float32)                  # a database row as query: retrieves itself first
+    s, wi = check(db, q, k)
+    assert wi[0, 0] == n // 2
+    rows = s.gather_device(torch.from_numpy(wi))
+    assert np.array_equal(rows.numpy(), db[wi].astype(np.float32))
+
+
+def test_duplicates_break_ties_by_lowest_index_and_shards_merge(emulated):
+    from rdm_b200.knn import B200Searcher, merge_device
+    rng = np.random.default_rng(7)
+    db = rng.standard_normal((1200, 256)).astype(np.float16)
+    db[700] = db[3]; db[1100] = db[3]                    # exact duplicates: equal scores -> ascending index
+    q = np.concatenate([db[[3]].astype(np.float32), rng.standard_normal((2, 256)).astype(np.float32)])
+    _, wi = check(db, q, 6)
+    assert list(wi[0, :3]) == [3, 700, 1100]
+    qh = torch.from_numpy(oknn.normalize_queries(q))
+    parts = [B200Searcher(db[lo:hi], device="cpu", idx_base=lo).search_device(qh, 6, return_scores=True) for lo, hi in ((0, 500), (500, 1200))]
+    idx, dist, sc = merge_device(torch.stack([p[0] for p in parts]), torch.stack([p[2] for p in parts]), 6)
+    assert np.array_equal(idx.numpy(), wi)
+    rows = sum(B200Searcher(db[lo:hi], device="cpu", idx_base=lo).gather_device(idx) for lo, hi in ((0, 500), (500, 1200)))      # out-of-shard rows are zeros
+    assert np.array_equal(rows.numpy(), db[wi].astype(np.float32))
