@@ -9,6 +9,7 @@ import os
 import torch
 import torch.nn as nn
 
+from rdm_b200 import _lib as _binding
 from rdm_b200.rarm import MODE_FP16, MODE_FP32, B200Rarm, rarm_param_shapes
 
 
@@ -55,9 +56,7 @@ class RetrievalPatchTransformer(nn.Module):
         self._engine, self._loaded_key = None, None
 
     def engine(self, device):
-        device = torch.device(device)
-        if device.type != "cuda":
-            raise RuntimeError("rdm RetrievalPatchTransformer (B200 build) has no CPU path: move the model to a CUDA device")
+        device = _binding.resolve_device(device)          # raises for anything but a CUDA device: there is no CPU path
         if self._engine is None or self._engine.device != device:
             self._engine, self._loaded_key = B200Rarm(device, **self._cfg), None
         key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.engine_mode,)

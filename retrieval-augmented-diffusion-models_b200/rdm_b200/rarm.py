@@ -60,21 +60,18 @@ class B200Rarm:
             except Exception:
                 pass
 
-    # The three hooks below are the only places that touch the CUDA device; tests/test_rarm_emulated.py overrides them to drive the SAME
-    # C ABI compiled against a host emulation of CUDA.  The product has no other implementation: _library() raises without the .so.
+    # The three hooks below are the only places that touch the CUDA device; they go through the same `_lib` indirections as the other
+    # wrappers (tests/emu drives the SAME C ABI compiled against a host emulation of CUDA by patching those).  The product has no other
+    # implementation: _library() raises without the .so, resolve_device() raises for anything but a CUDA device.
     def _library(self):
         return _lib.lib()
 
     def _resolve_device(self, device):
-        device = torch.device(device)
-        if device.type != "cuda":
-            raise RuntimeError("the RARM decoder (B200 build) has no CPU path: pass a CUDA device")
-        if device.index is None:
-            device = torch.device("cuda", torch.cuda.current_device())
-        return device, device.index
+        device = _lib.resolve_device(device)
+        return device, int(device.index or 0)
 
     def _run(self, fn, *args):
-        with torch.cuda.device(self.device):
+        with _lib.device_ctx(self.device):
             self._check(getattr(self._library(), fn)(self._h, *args, _lib.stream_ptr(self.device)), fn)
 
     def _check(self, rc, what=""):

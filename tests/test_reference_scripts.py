@@ -2,8 +2,8 @@
 drop-in packages of this repository: `parse_args` -> `load_model` (the SHIPPED `models/**/config.yaml` with sizes reduced, a synthetic
 Lightning checkpoint in the reference's key layout, `load_state_dict(strict=False)`, `.eval()`) -> `sample_unconditional` /
 `sample_conditional` / `sample` -> PNG files.  Because this container has no GPU the device executors are either oracle-backed stand-ins with the same call
-surface (searcher, U-Net engine, RARM decoder, first-stage decoder) or -- second parametrisation of the rdm_sample.py test -- the
-product's OWN kNN / U-Net / DDIM source executed under the host emulation of CUDA (tests/emu/); everything else -- configuration handling,
+surface (searcher, U-Net engine, RARM decoder, first-stage decoder) or -- second parametrisation of both tests -- the
+product's OWN kNN / U-Net / DDIM / RARM source executed under the host emulation of CUDA (tests/emu/); everything else -- configuration handling,
 class resolution through the YAML `target:` strings, checkpoint loading, conditioning assembly, the sampler, the first-stage
 containers, the returned dictionaries the scripts iterate -- is the product's host code.  Skipped where /root/reference is absent
 (the GPU box)."""
@@ -98,7 +98,7 @@ class CpuRarmEngine:
 
 @pytest.fixture()
 def emulated_executors(monkeypatch):
-    """The product's own kNN / U-Net / DDIM source (csrc/knn.cu, unet.cu, kernels.cu, gemm_simt.cu) under the host emulation of CUDA
+    """The product's own kNN / U-Net / DDIM / RARM source (csrc/knn.cu, unet.cu, kernels.cu, gemm_simt.cu, rarm.cu) under the host emulation of CUDA
     (tests/emu/) instead of oracle stand-ins; only the tensor-core-only first-stage decoder keeps an oracle stand-in."""
     import contextlib
     import ctypes
@@ -111,12 +111,13 @@ def emulated_executors(monkeypatch):
     from ldm.models.autoencoder import VQModelInterface
     from rdm_b200 import _lib
     os.environ["RDM_KNN_NO_TC"] = "1"
-    names = [n for n in _lib.SIGNATURES if n.startswith(("rdm_unet_", "rdm_ddim_", "rdm_knn_"))] + ["rdm_last_error", "rdm_launch_count"]
+    names = [n for n in _lib.SIGNATURES if n.startswith(("rdm_unet_", "rdm_ddim_", "rdm_knn_", "rdm_rarm_"))] + ["rdm_last_error", "rdm_launch_count"]
     monkeypatch.setattr(_lib, "_lib", _lib.bind(ctypes.CDLL(build_emu.build()), names))
     monkeypatch.setattr(_lib, "resolve_device", lambda d: torch.device("cpu"))
     monkeypatch.setattr(_lib, "device_ctx", lambda d: contextlib.nullcontext())
     monkeypatch.setattr(_lib, "stream_ptr", lambda d=None: None)
     monkeypatch.setenv("RDM_B200_MODE", "fp32")                                # strict mode: the tensor-core modes need hardware
+    monkeypatch.setenv("RDM_B200_RARM_MODE", "fp32")
 
     def first_stage_decode(self, h, force_not_quantize=False):
         ref = ovq.VQModelInterface(self.embed_dim, self.quantize.embedding.num_embeddings, self._ddconfig).eval()
@@ -233,7 +234,9 @@ def test_rdm_sample_script_runs_unchanged(tmp_path, monkeypatch, request, execut
     assert len(pngs) == 2 and all("query_samples" in f for f in pngs)
 
 
-def test_rarm_sample_script_runs_unchanged(tmp_path, monkeypatch, cpu_executors):
+@pytest.mark.parametrize("executors", ["cpu_executors", "emulated_executors"])
+def test_rarm_sample_script_runs_unchanged(tmp_path, monkeypatch, request, executors):
+    request.getfixturevalue(executors)
     from omegaconf import OmegaConf
     script = load_script("rarm_sample")
     make_db(tmp_path)
