@@ -78,14 +78,14 @@ def test_fused_guided_ddim_loop_matches_the_pinned_oracle(emulated):
     g = torch.Generator().manual_seed(4)
     x_T = torch.randn(1, 4, 8, 8, generator=g)
     c, uc = torch.randn(1, 2, 512, generator=g), torch.zeros(1, 2, 512)
-    S = 4
+    S = 2
     want, traj = oddim.ddim_sample(ref, x_T, c, uc, S=S, scale=2.0, return_all=True)
     tb = sampler.make_ddim_tables(sampler.alphas_cumprod_linear(), S, 0.0)
     net.set_context(torch.cat([c, uc]))
-    got, p0 = net.ddim_sample(x_T, tb["timesteps"], tb["coef"], cfg_scale=2.0, want_pred_x0=True)      # step 1 eager, steps 2..4 from the captured graph
+    got, p0 = net.ddim_sample(x_T, tb["timesteps"], tb["coef"], cfg_scale=2.0, want_pred_x0=True)      # step 1 eager, step 2 from the captured graph
     assert rel(got, want) < 1e-5 and rel(p0, traj[-1][1]) < 1e-5
     a = net.ddim_sample(x_T, tb["timesteps"], tb["coef"], cfg_scale=2.0, first_step=0, num_steps=1)
-    b = net.ddim_sample(a, tb["timesteps"], tb["coef"], cfg_scale=2.0, first_step=1, num_steps=3)
+    b = net.ddim_sample(a, tb["timesteps"], tb["coef"], cfg_scale=2.0, first_step=1, num_steps=1)
     assert rel(b, want) < 1e-5
     # the stand-alone update kernel is bit-exact against the reference's float32 tensor expressions
     eps = torch.randn(2, 4, 8, 8, generator=g)
