@@ -66,10 +66,19 @@ void run_block(const std::function<void()>& body, dim3 grid, dim3 block, uint3 b
     }
     t_run = &run;
     blockIdx = bidx; blockDim = block; gridDim = grid;
+    // Order in which runnable threads are resumed within a scheduling round (EMU_SCHEDULE = forward | reverse | random:<seed>): results must
+    // not depend on it -- a missing barrier (read-after-write or write-after-read across threads) shows up as a result that changes with the order.
+    const char* sched = getenv("EMU_SCHEDULE");
+    const int mode = !sched || !strncmp(sched, "forward", 7) ? 0 : !strncmp(sched, "reverse", 7) ? 1 : 2;
+    uint64_t rng = mode == 2 ? (uint64_t)strtoull(strchr(sched, ':') ? strchr(sched, ':') + 1 : "1", nullptr, 10) * 0x9E3779B97F4A7C15ull + bidx.x * 1315423911u + bidx.y * 2654435761u + 1 : 0;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = mode == 1 ? n - 1 - i : i;
     int idle_rounds = 0;
     while (run.live > 0) {
         bool progressed = false;
-        for (int i = 0; i < n && run.live > 0; i++) {
+        if (mode == 2) for (int i = n - 1; i > 0; i--) { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; std::swap(order[i], order[(int)(rng % (uint64_t)(i + 1))]); }
+        for (int oi = 0; oi < n && run.live > 0; oi++) {
+            const int i = order[oi];
             Fiber& f = run.fibers[i];
             if (f.state != READY) continue;
             run.cur = i; threadIdx = f.tid;

@@ -215,3 +215,24 @@ def test_product_sampling_flow_matches_reference_code(emu_cls):
     _, c = model.encode_to_c(torch.zeros((2, 0)))
     got = model.sample(torch.from_numpy(g["greedy:start"]), torch.from_numpy(g["greedy:r"]), c, steps=6, sample=False, top_k=None, guidance_scale=3.0)
     assert torch.equal(got, torch.from_numpy(g["greedy:tokens"]))
+
+
+@pytest.mark.parametrize("schedule", ["reverse", "random:5"])
+def test_results_do_not_depend_on_the_thread_scheduling_order(emu_cls, monkeypatch, schedule):
+    """The emulator resumes the runnable threads of a block in index order by default; a missing barrier (a read-after-write or
+    write-after-read hazard between threads) would make results depend on that order.  Same checks with the order reversed / shuffled."""
+    monkeypatch.setenv("EMU_SCHEDULE", schedule)
+    d, cfg, sd, net = small(emu_cls, 0)
+    tok, ctx = torch.from_numpy(d["tokens"])[:, :4], torch.from_numpy(d["context"])
+    assert rel(net.forward(tok, ctx), d["logits"][:, :4]) < 2e-6
+    g = torch.Generator().manual_seed(1)
+    lc, lu, u = torch.randn(2, 16384, generator=g) * 3, torch.randn(2, 16384, generator=g) * 3, torch.rand(2, generator=g)
+    tokn, probs = net.sample_step(torch.cat([lc, lu]), guidance_scale=2.0, temperature=0.9, top_k=256, uniforms=u, want_probs=True)
+    want = orarm.step_probs(lc, lu, 2.0, 0.9, 256)
+    assert torch.equal(probs > 0, want > 0) and float((probs - want).abs().max()) < 1e-6 and torch.equal(tokn, orarm.draw(want, u))
+    c = torch.full((2, 1), cfg["in_channels"] - 1)
+    uu = torch.rand(4, 2, generator=g)
+    net.set_context(torch.cat([ctx[:2], torch.zeros_like(ctx[:2])]))
+    toks = net.sample(c, 4, temperature=0.9, top_k=6, guidance_scale=2.0, uniforms=uu)
+    want_t, _ = orarm.sample(sd, cfg["n_heads"], c, torch.zeros((2, 0), dtype=torch.long), ctx[:2], 4, 0.9, 6, 2.0, uu)
+    assert torch.equal(toks[:, 1:], want_t)
