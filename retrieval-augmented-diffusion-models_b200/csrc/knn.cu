@@ -45,6 +45,15 @@ __device__ __forceinline__ float unorder_f32(uint32_t u) {
 }
 // larger key = better candidate: higher score first, then LOWER row index
 __device__ __forceinline__ u64 make_key(float s, uint32_t idx) { return ((u64)order_f32(s) << 32) | (u64)(0xffffffffu - idx); }
+// The scans rank rows by an fp32 (or tensor-core) score whose distance to the exact fp64 score of the result definition is bounded by
+// e ~ 4e-6 for unit queries and normalised rows.  Wherever an fp32 score decides whether a row can still be one of the exact top-k, the
+// comparison is relaxed by 2e: with f_k the k-th largest fp32 score seen, every row of the exact top-k has an fp32 score >= f_k - 2e.
+// (Without the slack, a cluster of near-duplicate rows -- scores closer than the fp32 rounding -- could push true neighbours out.)
+constexpr float SCORE_SLACK = 8e-6f;
+__device__ __forceinline__ u64 relax_key(u64 key) {         // key of (score - slack) with the row part cleared; 0 stays "keep everything"
+    if (key == 0ull) return 0ull;
+    return (u64)order_f32(unorder_f32((uint32_t)(key >> 32)) - SCORE_SLACK) << 32;
+}
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     uint4 r;
@@ -373,16 +382,20 @@ knn_threshold_kernel(const u64* __restrict__ maxima, size_t per_q, u64* __restri
     cur = warp < P ? __ldcg(part + ((size_t)qi * P + warp) * LIST + lane) : 0ull;
     cur = cta_tree_merge(cur, s_keys, warp, lane, P);
     if (warp == 0) {
-        if (lane == KSEL - 1) thr_key[qi] = cur;       // descending: lane 31 holds the 32nd largest
+        if (lane == KSEL - 1) thr_key[qi] = relax_key(cur);       // descending: lane 31 holds the 32nd largest (relaxed by the score slack)
         if (lane == 0) { cand_cnt[qi] = 0u; done[qi] = 0u; if (qi == 0) *overflow = 0u; }
     }
 }
 
 __device__ __forceinline__ bool better_pair(double sa, long long ia, double sb, long long ib) { return sa > sb || (sa == sb && ia < ib); }
 
-// grid = queries of this pass, block = 1024.  Merge per-CTA lists -> 32 candidates -> exact fp64 re-rank -> top-k.
-// FROM_LISTS = false: candidates of query qi are cand[qi*CAND_CAP .. + min(cnt, CAP)); sets *overflow when cnt > CAP.
-// FROM_LISTS = true : fallback, per-CTA lists [nblk][QP][LIST]; runs only when *overflow != 0.
+// grid = queries of this pass, block = 1024.  Merge the survivors to the 32 best fp32 keys, take f_k = the k-th of them, then re-rank
+// EXACTLY (fp64, definition: oracle/knn_ref.c) every survivor whose fp32 score is within the slack of f_k -- at most one per thread -- and
+// emit the top-k by (score desc, row asc).
+// FROM_LISTS = false: candidates of query qi are cand[qi*CAND_CAP .. + min(cnt, CAP)); sets *overflow when cnt > CAP or when more than
+//                     1024 survivors lie within the slack (a pathological cluster of near-identical rows: the fallback pass answers).
+// FROM_LISTS = true : fallback, per-CTA lists [nblk][QP][LIST]; runs only when *overflow != 0; re-ranks the 32 best fp32 keys.
+constexpr int SEL_MAX = 1024;
 template <typename T, int D, bool FROM_LISTS>
 __global__ void __launch_bounds__(1024)
 knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const unsigned* __restrict__ cand_cnt, unsigned* __restrict__ overflow,
@@ -391,28 +404,51 @@ knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const unsigne
                   long long* __restrict__ idx_out, float* __restrict__ dist_out, double* __restrict__ score_out) {
     __shared__ u64 s_keys[32][LIST];
     __shared__ float s_q[D];
+    __shared__ u64 s_cand[SEL_MAX];
+    __shared__ u64 s_cut;
+    __shared__ unsigned s_ncand;
+    __shared__ double s_bs[32];
+    __shared__ long long s_bi[32];
+    __shared__ long long s_win;
     const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (FROM_LISTS) { if (*overflow == 0u) return; }
     for (int i = tid; i < D; i += blockDim.x) s_q[i] = q[(size_t)qi * D + i];
+    if (tid == 0) s_ncand = 0u;
     u64 cur = 0ull;
+    unsigned cnt = 0u;
     if (FROM_LISTS) {
         for (int b = warp; b < nblk; b += 32) {
             u64 batch = lists[((size_t)b * QP + qi) * LIST + lane];
             if (__any_sync(FULL, batch != 0ull)) cur = warp_merge_top32(cur, batch, lane);
         }
     } else {
-        const unsigned cnt = cand_cnt[qi];
+        cnt = cand_cnt[qi];
         if (cnt > (unsigned)CAND_CAP) { if (tid == 0) atomicExch(overflow, 1u); return; }     // the fallback pass redoes this batch
         for (unsigned b = warp * 32; b < cnt; b += 32 * 32) {
             u64 batch = b + lane < cnt ? lists[(size_t)qi * CAND_CAP + b + lane] : 0ull;
             cur = warp_merge_top32(cur, batch, lane);
         }
     }
-    cur = cta_tree_merge(cur, s_keys, warp, lane, 32);
-    if (warp != 0) return;
-    // exact re-rank (definition: oracle/knn_ref.c)
-    const bool have = cur != 0ull;
-    long long row = have ? (long long)(0xffffffffu - (uint32_t)cur) : 0x7fffffffffffffffLL;
+    cur = cta_tree_merge(cur, s_keys, warp, lane, 32);          // warp 0: lane i holds the i-th largest fp32 key
+    if (warp == 0) {
+        const u64 kth = __shfl_sync(FULL, cur, k - 1);           // 0 when fewer than k survivors exist: keep everything
+        if (lane == 0) s_cut = relax_key(kth);
+        if (FROM_LISTS) { s_cand[lane] = cur; if (lane == 0) s_ncand = 32u; }
+    }
+    __syncthreads();
+    if (!FROM_LISTS) {
+        const u64 cut = s_cut;
+        for (unsigned i = tid; i < cnt; i += blockDim.x) {
+            const u64 key = lists[(size_t)qi * CAND_CAP + i];
+            if (key != 0ull && key >= cut) { const unsigned pos = atomicAdd(&s_ncand, 1u); if (pos < (unsigned)SEL_MAX) s_cand[pos] = key; }
+        }
+        __syncthreads();
+        if (s_ncand > (unsigned)SEL_MAX) { if (tid == 0) atomicExch(overflow, 1u); return; }
+    }
+    // exact re-rank: one candidate per thread
+    const u64 mykey = tid < (int)s_ncand ? s_cand[tid] : 0ull;
+    const bool have = mykey != 0ull;
+    long long row = have ? (long long)(0xffffffffu - (uint32_t)mykey) : 0x7fffffffffffffffLL;
     double s = -CUDART_INF;
     if (have && row < n) {
         const uint4* r = reinterpret_cast<const uint4*>(db + (size_t)row * D);      // 16-byte pieces: the loads run ahead of the fp64 chain
@@ -427,25 +463,39 @@ knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const unsigne
         }
         acc = __dmul_rn(acc, (double)inv[row]);
         s = (acc == acc) ? acc : -CUDART_INF;
-    }
-    // bitonic sort of (score, row) pairs, best first
+    } else if (have) { row = 0x7fffffffffffffffLL; }
+    // top-k by (score desc, row asc): k rounds of a block-wide arg-best over the candidates not emitted yet
+    bool taken = row == 0x7fffffffffffffffLL;
+    for (int r = 0; r < k; r++) {
+        double bs = taken ? -CUDART_INF : s;
+        long long bi = taken ? 0x7fffffffffffffffLL : row;
 #pragma unroll
-    for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            double os = __shfl_xor_sync(FULL, s, j);
-            long long orow = __shfl_xor_sync(FULL, row, j);
-            bool desc = (lane & kk) == 0, lower = (lane & j) == 0;
-            bool keep_best = (desc == lower);
-            bool other_better = better_pair(os, orow, s, row);
-            if (keep_best == other_better) { s = os; row = orow; }
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double os = __shfl_xor_sync(FULL, bs, m);
+            const long long oi = __shfl_xor_sync(FULL, bi, m);
+            if (oi != 0x7fffffffffffffffLL && (bi == 0x7fffffffffffffffLL || better_pair(os, oi, bs, bi))) { bs = os; bi = oi; }
         }
-    }
-    if (lane < k) {
-        bool ok = row != 0x7fffffffffffffffLL;
-        idx_out[(size_t)qi * k + lane] = ok ? row + idx_base : -1;
-        dist_out[(size_t)qi * k + lane] = ok ? (float)s : -CUDART_INF_F;
-        if (score_out) score_out[(size_t)qi * k + lane] = ok ? s : -CUDART_INF;
+        if (lane == 0) { s_bs[warp] = bs; s_bi[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            bs = s_bs[lane]; bi = s_bi[lane];
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                const double os = __shfl_xor_sync(FULL, bs, m);
+                const long long oi = __shfl_xor_sync(FULL, bi, m);
+                if (oi != 0x7fffffffffffffffLL && (bi == 0x7fffffffffffffffLL || better_pair(os, oi, bs, bi))) { bs = os; bi = oi; }
+            }
+            if (lane == 0) {
+                const bool ok = bi != 0x7fffffffffffffffLL;
+                idx_out[(size_t)qi * k + r] = ok ? bi + idx_base : -1;
+                dist_out[(size_t)qi * k + r] = ok ? (float)bs : -CUDART_INF_F;
+                if (score_out) score_out[(size_t)qi * k + r] = ok ? bs : -CUDART_INF;
+                s_win = bi;
+            }
+        }
+        __syncthreads();
+        if (!taken && row == s_win) taken = true;
+        __syncthreads();                                          // s_bs / s_bi / s_win are rewritten by the next round
     }
 }
 

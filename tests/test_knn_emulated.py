@@ -73,3 +73,17 @@ def test_duplicates_break_ties_by_lowest_index_and_shards_merge(emulated):
     assert np.array_equal(idx.numpy(), wi)
     rows = sum(B200Searcher(db[lo:hi], device="cpu", idx_base=lo).gather_device(idx) for lo, hi in ((0, 500), (500, 1200)))      # out-of-shard rows are zeros
     assert np.array_equal(rows.numpy(), db[wi].astype(np.float32))
+
+
+@pytest.mark.parametrize("dtype,n,nq,k", [(np.float16, 5000, 5, 8), (np.float32, 3000, 2, 24)])
+def test_near_duplicate_cluster_is_exact(emulated, dtype, n, nq, k):
+    """400 rows that differ from the query row by less than the fp32 rounding of the scan's score: the exact fp64 top-k (and the
+    self-match at rank 0) must still come out -- the scans relax every fp32 decision by the score slack and the select kernel re-ranks
+    every survivor within the slack exactly (knn.cu: SCORE_SLACK).  (Without the slack this returned other members of the cluster.)"""
+    rng = np.random.default_rng(n)
+    db = (rng.standard_normal((n, 512)) * rng.uniform(0.5, 8, (n, 1))).astype(dtype)
+    db[1000:1400] = db[1000] + (rng.standard_normal((400, 512)) * 1e-3).astype(dtype)
+    q = rng.standard_normal((nq, 512)).astype(np.float32)
+    q[0] = db[1000].astype(np.float32)
+    _, wi = check(db, q, k)
+    assert set(wi[0]) <= set(range(1000, 1400))         # (which member ranks first is decided by the last bits of the exact scores: the oracle's call)
