@@ -194,7 +194,8 @@ def test_rdm_sample_script_runs_unchanged(tmp_path, monkeypatch, request, execut
 
     out = tmp_path / "out"
     bs = 2 if executors == "cpu_executors" else 1                              # (the emulated kernels are slow: one image is enough there)
-    argv = ["rdm_sample.py", "-s", str(out), "--model_path", str(model_dir), "-bs", str(bs), "--gpu", "-1", "--n_runs", "1", "--steps", "4", "--k_nn", "4",
+    steps = 4 if executors == "cpu_executors" else 2
+    argv = ["rdm_sample.py", "-s", str(out), "--model_path", str(model_dir), "-bs", str(bs), "--gpu", "-1", "--n_runs", "1", "--steps", str(steps), "--k_nn", "4",
             "--guidance_scale", "2.0", "--top_m", "0.5"]
     monkeypatch.setattr(sys, "argv", argv)
     opt = script.parse_args()
@@ -211,7 +212,7 @@ def test_rdm_sample_script_runs_unchanged(tmp_path, monkeypatch, request, execut
     # what was saved is the EMA-weight, retrieval-conditioned sample: recompute sample 0 with the oracle pipeline
     np.random.seed(0)
     torch.manual_seed(0)
-    logs = model.sample_from_rdata(bs, qids=None, k_nn=4, use_weights=False, memsize=0.5, unconditional_guidance_scale=2.0, ddim_steps=4, ddim=True,
+    logs = model.sample_from_rdata(bs, qids=None, k_nn=4, use_weights=False, memsize=0.5, unconditional_guidance_scale=2.0, ddim_steps=steps, ddim=True,
                                    unconditional_retro_guidance_label=0.)
     assert list(logs.keys()) == ["samples_with_sampled_nns"]                   # the reference's keys only (extras: logs.extras)
     nns = logs.extras["nns"].numpy()
