@@ -83,7 +83,7 @@ struct rdm_unet {
     // CUDA-graph replay: fixed staging buffers + one captured graph per (Bx, B2, H, W, mode)
     int use_graph = 1;
     float* x_in = nullptr; long long* t_in = nullptr; float* eps_buf = nullptr; float* x_state = nullptr; float* p0_buf = nullptr; int* step_dev = nullptr;
-    size_t io_cap = 0;
+    size_t io_cap = 0, tin_cap = 0;         // capacities of the staging buffers: elements of x_in / eps_buf / ..., entries of t_in
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t fwd_exec = nullptr; int fwd_key[6] = {0, 0, 0, 0, -1, 0};
     int skip = getenv("RDM_SKIP") ? atoi(getenv("RDM_SKIP")) : 0;      // ablation mask (see RUN_UNLESS)
@@ -744,15 +744,21 @@ int ensure_io(Net* n, int B2, int H, int W) {
     const size_t need = (size_t)B2 * C * H * W;
     if (!n->cap_stream) RDM_CHECK_CUDA(cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking));
     if (!n->step_dev) RDM_CHECK_CUDA(cudaMalloc((void**)&n->step_dev, sizeof(int)));
+    if ((size_t)B2 > n->tin_cap) {          // the timestep vector has its own capacity: a larger batch of SMALLER images must not reuse a short one
+        if (n->t_in) cudaFree(n->t_in);
+        n->t_in = nullptr; n->tin_cap = 0;
+        if (n->fwd_exec) { cudaGraphExecDestroy(n->fwd_exec); n->fwd_exec = nullptr; }       // the captured graphs hold the old pointer
+        if (n->step_exec) { cudaGraphExecDestroy(n->step_exec); n->step_exec = nullptr; }
+        RDM_CHECK_CUDA(cudaMalloc((void**)&n->t_in, (size_t)B2 * 8));
+        n->tin_cap = (size_t)B2;
+    }
     if (need <= n->io_cap) return RDM_OK;
     for (float** p : {&n->x_in, &n->eps_buf, &n->x_state, &n->p0_buf}) { if (*p) cudaFree(*p); *p = nullptr; }
-    if (n->t_in) cudaFree(n->t_in); n->t_in = nullptr;
     n->io_cap = 0;
     if (n->fwd_exec) { cudaGraphExecDestroy(n->fwd_exec); n->fwd_exec = nullptr; }
     if (n->step_exec) { cudaGraphExecDestroy(n->step_exec); n->step_exec = nullptr; }
     RDM_CHECK_CUDA(cudaMalloc((void**)&n->x_in, need * 4)); RDM_CHECK_CUDA(cudaMalloc((void**)&n->eps_buf, need * 4));
     RDM_CHECK_CUDA(cudaMalloc((void**)&n->x_state, need * 4)); RDM_CHECK_CUDA(cudaMalloc((void**)&n->p0_buf, need * 4));
-    RDM_CHECK_CUDA(cudaMalloc((void**)&n->t_in, (size_t)B2 * 8));
     n->io_cap = need;
     return RDM_OK;
 }

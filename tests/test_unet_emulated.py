@@ -142,3 +142,16 @@ def test_product_pipeline_on_the_emulated_engine_matches_reference_code(emulated
     logs = model.sample_from_rdata(1, qids=np.array([123]), k_nn=4, x_T=torch.from_numpy(p["rdata_small:x_T"]), custom_shape=(4, 8, 8),
                                    unconditional_guidance_scale=2.0, ddim_steps=2, ddim=True, unconditional_retro_guidance_label=0.)
     assert rel(logs["samples_with_sampled_nns"], torch.from_numpy(p["rdata_small:samples"])) < 1e-5
+
+
+def test_batch_growth_with_smaller_images_does_not_overrun_the_timestep_buffer(emulated):
+    """Regression (found by the emulator's guard zones): the staging buffers were sized by B2*C*H*W only, so a larger batch of smaller
+    images reused a timestep vector allocated for fewer samples and wrote past it.  Shapes in that order, results checked as well."""
+    ref, net = _pair(7)
+    g = torch.Generator().manual_seed(0)
+    for B2, H, W, k in [(3, 12, 12, 1), (7, 8, 4, 2)]:
+        x, t, c = torch.randn(B2, 4, H, W, generator=g), torch.randint(0, 1000, (B2,), generator=g), torch.randn(B2, k, 512, generator=g) * 2
+        with torch.no_grad():
+            want = ref(x, t, c)
+        net.set_context(c)
+        assert rel(net.forward(x, t), want) < 1e-5
