@@ -46,10 +46,10 @@ __device__ __forceinline__ float unorder_f32(uint32_t u) {
 // larger key = better candidate: higher score first, then LOWER row index
 __device__ __forceinline__ u64 make_key(float s, uint32_t idx) { return ((u64)order_f32(s) << 32) | (u64)(0xffffffffu - idx); }
 // The scans rank rows by an fp32 (or tensor-core) score whose distance to the exact fp64 score of the result definition is bounded by
-// e ~ 4e-6 for unit queries and normalised rows.  Wherever an fp32 score decides whether a row can still be one of the exact top-k, the
-// comparison is relaxed by 2e: with f_k the k-th largest fp32 score seen, every row of the exact top-k has an fp32 score >= f_k - 2e.
+// e (a few 1e-6 for unit queries and normalised 512-d rows; the slack below allows e = 1.5e-5).  Wherever an fp32 score decides whether a
+// row can still be one of the exact top-k, the comparison is relaxed by 2e: with f_k the k-th largest fp32 score seen, every row of the exact top-k has an fp32 score >= f_k - 2e.
 // (Without the slack, a cluster of near-duplicate rows -- scores closer than the fp32 rounding -- could push true neighbours out.)
-constexpr float SCORE_SLACK = 8e-6f;
+constexpr float SCORE_SLACK = 3e-5f;
 __device__ __forceinline__ u64 relax_key(u64 key) {         // key of (score - slack) with the row part cleared; 0 stays "keep everything"
     if (key == 0ull) return 0ull;
     return (u64)order_f32(unorder_f32((uint32_t)(key >> 32)) - SCORE_SLACK) << 32;
