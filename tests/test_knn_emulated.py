@@ -87,3 +87,19 @@ def test_near_duplicate_cluster_is_exact(emulated, dtype, n, nq, k):
     q[0] = db[1000].astype(np.float32)
     _, wi = check(db, q, k)
     assert set(wi[0]) <= set(range(1000, 1400))         # (which member ranks first is decided by the last bits of the exact scores: the oracle's call)
+
+
+@pytest.mark.parametrize("ndup", [1500, 2600])
+def test_candidate_overflow_takes_the_fallback_pass(emulated, ndup):
+    """More exact duplicates of the query row than the select kernel re-ranks in one pass (1500 > SEL_MAX = 1024 survivors within the
+    slack) or than the main scan keeps per query (2600 > CAND_CAP = 2048): the overflow flag routes the batch through the locked
+    per-CTA lists and the FROM_LISTS select, which must still return the lowest-index duplicates, bit-exact; the second query of the
+    same batch (no cluster) is answered by the same fallback pass."""
+    rng = np.random.default_rng(ndup)
+    n = 4000
+    db = (rng.standard_normal((n, 512)) * rng.uniform(0.5, 8, (n, 1))).astype(np.float16)
+    dup = rng.choice(n, ndup, replace=False)
+    db[dup] = db[dup[0]]
+    q = np.concatenate([db[[dup[0]]].astype(np.float32), rng.standard_normal((1, 512)).astype(np.float32)])
+    _, wi = check(db, q, 8)
+    assert list(wi[0]) == sorted(dup)[:8]
