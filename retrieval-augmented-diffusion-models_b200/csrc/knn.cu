@@ -10,10 +10,11 @@
 //                           reduction, ONE compare per (row, query) against the threshold; the rare survivors
 //                           are appended to a small global candidate buffer.  HBM-bound for few queries:
 //                           algorithmic bytes = n * d * sizeof(elem) (+4 B/row inverse norm).
-//   3. knn_select_kernel -- top-32 of the survivors (warp bitonic networks), then RE-RANK with the exact definition
-//                           of oracle/knn_ref.c (sequential fp64, separately rounded products) and emit the top-k
-//                           by (score desc, index asc).  The fp32 scan only has to put the true top-k among its 32
-//                           candidates (margin >= 8 for k <= 24; fp32 dot error ~1e-7).
+//   3. knn_select_kernel -- the k-th best fp32 key of the survivors (warp bitonic networks) minus SCORE_SLACK is the cut; every
+//                           survivor above the cut (<= 1024, usually ~k) is RE-RANKED with the exact definition of
+//                           oracle/knn_ref.c (sequential fp64, separately rounded products) and the top-k is emitted
+//                           by (score desc, index asc).  The fp32 / tensor-core scores only decide, with the slack as
+//                           margin over their error (~1e-6), which rows reach the exact re-rank.
 //   4. fallback (device-side conditional, normally two empty launches): if a candidate buffer overflowed (sample
 //      unrepresentative of the DB), knn_scan_kernel<LOCKED> redoes the pass with per-CTA top-32 lists under a lock.
 // Replaces ScaNN behind `searcher.search_batched` (dsetbuilder.py:490, ddpm.py:906-908).
@@ -391,7 +392,8 @@ __device__ __forceinline__ bool better_pair(double sa, long long ia, double sb, 
 
 // grid = queries of this pass, block = 1024.  Merge the survivors to the 32 best fp32 keys, take f_k = the k-th of them, then re-rank
 // EXACTLY (fp64, definition: oracle/knn_ref.c) every survivor whose fp32 score is within the slack of f_k -- at most one per thread -- and
-// emit the top-k by (score desc, row asc).
+// emit the top-k by (score desc, row asc): one warp-level bitonic sort when at most 32 survivors remain (the usual case), k rounds of a
+// block-wide arg-best otherwise.
 // FROM_LISTS = false: candidates of query qi are cand[qi*CAND_CAP .. + min(cnt, CAP)); sets *overflow when cnt > CAP or when more than
 //                     1024 survivors lie within the slack (a pathological cluster of near-identical rows: the fallback pass answers).
 // FROM_LISTS = true : fallback, per-CTA lists [nblk][QP][LIST]; runs only when *overflow != 0; re-ranks the 32 best fp32 keys.
@@ -464,7 +466,30 @@ knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const unsigne
         acc = __dmul_rn(acc, (double)inv[row]);
         s = (acc == acc) ? acc : -CUDART_INF;
     } else if (have) { row = 0x7fffffffffffffffLL; }
-    // top-k by (score desc, row asc): k rounds of a block-wide arg-best over the candidates not emitted yet
+    if (s_ncand <= 32u) {
+        // the usual case (and always the fallback pass): all candidates sit in warp 0 -- one bitonic sort of (score, row) pairs, best first
+        if (warp != 0) return;
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                const double os = __shfl_xor_sync(FULL, s, j);
+                const long long orow = __shfl_xor_sync(FULL, row, j);
+                const bool desc = (lane & kk) == 0, lower = (lane & j) == 0;
+                const bool keep_best = (desc == lower);
+                const bool other_better = better_pair(os, orow, s, row);
+                if (keep_best == other_better) { s = os; row = orow; }
+            }
+        }
+        if (lane < k) {
+            const bool ok = row != 0x7fffffffffffffffLL;
+            idx_out[(size_t)qi * k + lane] = ok ? row + idx_base : -1;
+            dist_out[(size_t)qi * k + lane] = ok ? (float)s : -CUDART_INF_F;
+            if (score_out) score_out[(size_t)qi * k + lane] = ok ? s : -CUDART_INF;
+        }
+        return;
+    }
+    // more than 32 survivors within the slack: k rounds of a block-wide arg-best over the candidates not emitted yet
     bool taken = row == 0x7fffffffffffffffLL;
     for (int r = 0; r < k; r++) {
         double bs = taken ? -CUDART_INF : s;
