@@ -67,6 +67,15 @@ RDM_API int rdm_knn_get_inv_norms(rdm_knn_t* h, float* out_dev, void* stream);
 RDM_API int rdm_knn_search(rdm_knn_t* h, const float* q_hat_dev, int32_t nq, int32_t k,
                    int64_t* idx_out_dev, float* dist_out_dev, double* score_out_dev, void* stream);
 
+/* The caller-side query normalisation of the reference, `q / np.linalg.norm(q, axis=1)[:, np.newaxis]` (ddpm.py:297,907;
+ * dsetbuilder.py:487; base.py:82), for float32 rows [nq, d] on the device: bit-identical to NumPy's fp32 result (separately rounded
+ * squares, NumPy's pairwise summation order, IEEE sqrt and division; restated in oracle/knn.py pairwise_sum_f32). */
+RDM_API int rdm_knn_normalize(const float* q_dev, int32_t nq, int32_t d, float* q_hat_out_dev, int32_t device, void* stream);
+/* rdm_knn_normalize + rdm_knn_search in one call: q_raw_dev float32 [nq, d] are RAW query embeddings (DB rows or CLIP outputs), i.e.
+ * exactly what the reference holds before ddpm.py:907 -- no eager arithmetic is left between get_qids and the scan. */
+RDM_API int rdm_knn_search_raw(rdm_knn_t* h, const float* q_raw_dev, int32_t nq, int32_t k,
+                   int64_t* idx_out_dev, float* dist_out_dev, double* score_out_dev, void* stream);
+
 /* Merge `parts` per-shard results (e.g. the all_gather of every rank's rdm_knn_search output):
  * idx_in int64 [parts, nq, k], score_in float64 [parts, nq, k] -> global top-k by (score desc, idx asc). */
 RDM_API int rdm_knn_merge(const int64_t* idx_in_dev, const double* score_in_dev, int32_t parts, int32_t nq, int32_t k,

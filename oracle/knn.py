@@ -43,9 +43,53 @@ def _dt(db):
 
 
 def normalize_queries(q):
-    """The caller-side query normalisation of the reference (numpy fp32): ``ddpm.py:907``, ``dsetbuilder.py:487``."""
+    """The caller-side query normalisation of the reference (numpy fp32): ``ddpm.py:907``, ``dsetbuilder.py:487``.  Queries are taken as
+    float32 (fp16 database rows are widened first, as the product's gather does, ``ddpm.py:921``): the reference's fp16-arithmetic norm of
+    an fp16 row differs from this by a positive per-query factor (1 + O(1e-3)), which cannot change a ranking."""
     q = np.asarray(q, dtype=np.float32)
     return q / np.linalg.norm(q, axis=1)[:, np.newaxis]
+
+
+def pairwise_sum_f32(a):
+    """NumPy's float32 `add.reduce` over a contiguous row, spelled out (numpy/core/src/umath/loops_utils.h.src `FLOAT_pairwise_sum`,
+    PW_BLOCKSIZE = 128): fewer than 8 elements -> sequential; up to 128 -> eight strided accumulators r[j] += a[8 i + j] combined as
+    ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the n % 8 tail sequentially; longer -> split at n2 = n/2 rounded down to a multiple of 8 and
+    add the two halves.  This is the summation order the CUDA normalisation kernel (csrc/knn.cu knn_normalize_kernel) reproduces; the test
+    suite pins this restatement against numpy itself."""
+    a = np.asarray(a, dtype=np.float32)
+    n = a.shape[0]
+    f = np.float32
+    if n < 8:
+        res = f(0.0)
+        for v in a:
+            res = f(res + v)
+        return res
+    if n <= 128:
+        r = [f(a[j]) for j in range(8)]
+        i = 8
+        while i < n - (n % 8):
+            for j in range(8):
+                r[j] = f(r[j] + a[i + j])
+            i += 8
+        res = f(f(f(r[0] + r[1]) + f(r[2] + r[3])) + f(f(r[4] + r[5]) + f(r[6] + r[7])))
+        while i < n:
+            res = f(res + a[i])
+            i += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return f(pairwise_sum_f32(a[:n2]) + pairwise_sum_f32(a[n2:]))
+
+
+def normalize_queries_restated(q):
+    """`normalize_queries` without calling np.linalg.norm: separately rounded fp32 squares, `pairwise_sum_f32`, IEEE sqrt and division."""
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    out = np.empty_like(q)
+    for i in range(q.shape[0]):
+        sq = (q[i] * q[i]).astype(np.float32)
+        nrm = np.sqrt(np.float32(np.float32(0.0) + pairwise_sum_f32(sq)), dtype=np.float32)
+        out[i] = q[i] / nrm
+    return out
 
 
 def inv_norms(db):

@@ -34,6 +34,7 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 constexpr int MAX_QP = 16;        // queries per CUDA-core scan pass
 constexpr int MAX_TCQ = 64;       // queries per tensor-core pass (fp16 databases)
+constexpr int QHAT_ROWS = 1024;   // rdm_knn_search_raw normalises (and searches) this many raw queries at a time
 constexpr unsigned FULL = 0xffffffffu;
 typedef unsigned long long u64;
 
@@ -562,6 +563,40 @@ __global__ void knn_gather_kernel(const T* __restrict__ db, long long n, long lo
     }
 }
 
+
+// q_hat = q / ||q||_2 row-wise in fp32, bit-identical to the reference's NumPy statement `q / np.linalg.norm(q, axis=1)[:, np.newaxis]`
+// (ddpm.py:297,907; dsetbuilder.py:487; base.py:82) for float32 rows: the squares are rounded separately, summed in NumPy's pairwise order
+// (oracle/knn.py: pairwise_sum_f32 -- leaves of L = 128 (96 for d = 768) elements with 8 strided accumulators combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), leaves combined by a balanced binary tree), then an IEEE square root and an IEEE division.
+// One CTA of 64 threads per query: thread t owns accumulator t % 8 of leaf t / 8; fp32 addition is commutative, so the xor-shuffle tree
+// reproduces the association above exactly.
+template <int D>
+__global__ void __launch_bounds__(64) knn_normalize_kernel(const float* __restrict__ q, int nq, float* __restrict__ out) {
+    constexpr int NLEAF = D == 768 ? 8 : D / 128, L = D / NLEAF;
+    static_assert(NLEAF == 2 || NLEAF == 4 || NLEAF == 8, "leaf tree");
+    __shared__ float s_w[2];
+    const int qi = blockIdx.x, t = threadIdx.x, leaf = t >> 3, j = t & 7;
+    const float* x = q + (size_t)qi * D;
+    float r = 0.f;
+    if (leaf < NLEAF) {
+        const float* a = x + leaf * L + j;
+        r = __fmul_rn(a[0], a[0]);
+#pragma unroll 4
+        for (int i = 8; i < L; i += 8) r = __fadd_rn(r, __fmul_rn(a[i], a[i]));
+    }
+    r = __fadd_rn(r, __shfl_xor_sync(FULL, r, 1));
+    r = __fadd_rn(r, __shfl_xor_sync(FULL, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(FULL, r, 4));                  // leaf sums
+    if (NLEAF >= 2) r = __fadd_rn(r, __shfl_xor_sync(FULL, r, 8));
+    if (NLEAF >= 4) r = __fadd_rn(r, __shfl_xor_sync(FULL, r, 16));
+    if ((t & 31) == 0) s_w[t >> 5] = r;                             // thread 0 holds the sum of leaves 0..3, thread 32 that of leaves 4..7
+    __syncthreads();
+    r = NLEAF == 8 ? __fadd_rn(s_w[0], s_w[1]) : s_w[0];
+    r = __fadd_rn(0.f, r);                                          // add.reduce starts from the identity 0
+    const float nrm = __fsqrt_rn(r);
+    for (int i = t; i < D; i += 64) out[(size_t)qi * D + i] = __fdiv_rn(x[i], nrm);
+}
+
 // one warp per query: k rounds of arg-best over parts*k candidates
 __global__ void knn_merge_kernel(const long long* __restrict__ idx_in, const double* __restrict__ sc_in, int parts, int nq, int k,
                                  long long* __restrict__ idx_out, float* __restrict__ dist_out, double* __restrict__ sc_out) {
@@ -613,6 +648,7 @@ struct rdm_knn {
     u64* thr_part = nullptr;        // threshold kernel: [MAX_TCQ][THR_P][LIST] partial top-32 lists
     unsigned* thr_done = nullptr;   // [MAX_TCQ] arrival counters (zero between searches)
     void* qsplit = nullptr;         // fp16 hi/lo query rows for the tensor-core scan
+    float* qhat = nullptr;          // rdm_knn_search_raw: normalised queries [QHAT_ROWS][d]
     int max_grid = 0;
 };
 
@@ -780,6 +816,20 @@ int do_gather(rdm_knn* h, const long long* idx, long long count, float* out, cud
     KNN_DISPATCH(h, gather_typed, h, idx, count, out, st);
 }
 
+int normalize_rows(const float* q, int nq, int d, float* out, cudaStream_t st) {
+    if (nq == 0) return RDM_OK;
+    switch (d) {
+        case 256: knn_normalize_kernel<256><<<nq, 64, 0, st>>>(q, nq, out); break;
+        case 512: knn_normalize_kernel<512><<<nq, 64, 0, st>>>(q, nq, out); break;
+        case 768: knn_normalize_kernel<768><<<nq, 64, 0, st>>>(q, nq, out); break;
+        case 1024: knn_normalize_kernel<1024><<<nq, 64, 0, st>>>(q, nq, out); break;
+        default: rdm_set_error("knn normalize: unsupported d=%d", d); return RDM_ERR_UNSUPPORTED;
+    }
+    RDM_COUNT_LAUNCH();
+    RDM_CHECK_CUDA(cudaGetLastError());
+    return RDM_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -818,7 +868,8 @@ int rdm_knn_create(rdm_knn_t** out, const void* db, int64_t n, int32_t d, int32_
             cudaMalloc(&h->thr_part, (size_t)MAX_TCQ * THR_P * LIST * sizeof(u64)) != cudaSuccess ||
             cudaMalloc(&h->thr_done, (size_t)MAX_TCQ * sizeof(unsigned)) != cudaSuccess ||
             cudaMemset(h->thr_done, 0, (size_t)MAX_TCQ * sizeof(unsigned)) != cudaSuccess ||
-            cudaMalloc(&h->qsplit, (size_t)knn_tc_queries_bytes()) != cudaSuccess) {
+            cudaMalloc(&h->qsplit, (size_t)knn_tc_queries_bytes()) != cudaSuccess ||
+            cudaMalloc(&h->qhat, (size_t)QHAT_ROWS * d * sizeof(float)) != cudaSuccess) {
             rdm_set_error("rdm_knn_create: workspace cudaMalloc failed"); rc = RDM_ERR_CUDA; break;
         }
         rc = do_create(h);
@@ -839,6 +890,7 @@ void rdm_knn_destroy(rdm_knn_t* h) {
     if (h->thr_key) cudaFree(h->thr_key);
     if (h->cand_cnt) cudaFree(h->cand_cnt);
     if (h->qsplit) cudaFree(h->qsplit);
+    if (h->qhat) cudaFree(h->qhat);
     if (h->thr_part) cudaFree(h->thr_part);
     if (h->thr_done) cudaFree(h->thr_done);
     delete h;
@@ -859,6 +911,27 @@ int rdm_knn_search(rdm_knn_t* h, const float* q, int32_t nq, int32_t k, int64_t*
     if (nq == 0) return RDM_OK;
     DeviceGuard guard(h->device);
     return do_search(h, q, nq, k, (long long*)idx_out, dist_out, score_out, (cudaStream_t)stream);
+}
+
+int rdm_knn_normalize(const float* q, int32_t nq, int32_t d, float* q_hat_out, int32_t device, void* stream) {
+    RDM_REQUIRE(q && q_hat_out, RDM_ERR_ARG, "rdm_knn_normalize: null argument");
+    RDM_REQUIRE(nq >= 0, RDM_ERR_ARG, "rdm_knn_normalize: nq=%d", nq);
+    DeviceGuard guard(device);
+    return normalize_rows(q, nq, d, q_hat_out, (cudaStream_t)stream);
+}
+
+int rdm_knn_search_raw(rdm_knn_t* h, const float* q_raw, int32_t nq, int32_t k, int64_t* idx_out, float* dist_out, double* score_out, void* stream) {
+    RDM_REQUIRE(h && q_raw && idx_out && dist_out, RDM_ERR_ARG, "rdm_knn_search_raw: null argument");
+    RDM_REQUIRE(k >= 1 && k <= RDM_KNN_MAX_K, RDM_ERR_ARG, "rdm_knn_search_raw: k=%d outside 1..%d", k, RDM_KNN_MAX_K);
+    RDM_REQUIRE(nq >= 0, RDM_ERR_ARG, "rdm_knn_search_raw: nq=%d", nq);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int q0 = 0; q0 < nq; q0 += QHAT_ROWS) {
+        const int cnt = nq - q0 < QHAT_ROWS ? nq - q0 : QHAT_ROWS;
+        RDM_TRY(normalize_rows(q_raw + (size_t)q0 * h->d, cnt, h->d, h->qhat, st));
+        RDM_TRY(do_search(h, h->qhat, cnt, k, (long long*)idx_out + (size_t)q0 * k, dist_out + (size_t)q0 * k, score_out ? score_out + (size_t)q0 * k : nullptr, st));
+    }
+    return RDM_OK;
 }
 
 int rdm_knn_merge(const int64_t* idx_in, const double* score_in, int32_t parts, int32_t nq, int32_t k,

@@ -52,6 +52,12 @@ class DatasetBuilder(object):
         self.searcher = None
         self.searcher_savedir = searcher_savepath
 
+    @property
+    def num_rows(self):
+        """GLOBAL number of database rows: `len(data_pool['embedding'])` of the reference (ddpm.py:867), also when this rank holds only
+        its row range of a sharded database (`get_qids` must draw pseudo-queries from the whole database on every rank)."""
+        return int(self._n_total) if self._n_total is not None else len(self.data_pool['embedding'])
+
     # ---- retriever (CLIP) ------------------------------------------------------------------------------------
     @property
     def retriever(self):

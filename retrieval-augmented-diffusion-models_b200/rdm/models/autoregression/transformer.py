@@ -21,6 +21,7 @@ from ldm.util import instantiate_from_config
 
 from rdm.modules.encoders.nn_encoders import IdentityEncoder
 from rdm.util import SampleLogs
+from rdm_b200.knn import search_raw
 
 
 def disabled_train(self, mode=True):
@@ -181,8 +182,7 @@ class LatentImageRETRO(nn.Module):
                 q = searcher.gather_device(torch.as_tensor(np.asarray(qids), dtype=torch.int64, device=self.device))      # :320
             else:
                 q = torch.as_tensor(np.asarray(query_embeddings), dtype=torch.float32).to(self.device)
-            qh = (q / q.norm(dim=1, keepdim=True)).contiguous()                                                           # :328
-            nns, _ = searcher.search_device(qh, k_nn)                                                                      # :327-329
+            nns, _ = search_raw(searcher, q, k_nn)                                                                         # :327-329
             retro_cond = searcher.gather_device(nns)                                                                       # :342
             out.extras["nns"] = nns
         else:
@@ -213,7 +213,7 @@ class LatentImageRETRO(nn.Module):
                 qids = np.random.choice(nn_mem, size=N, p=ps)
             else:
                 print('Randomly sampling retrieval database entries')
-                qids = np.random.choice(len(self.retriever.data_pool['embedding']), size=N)
+                qids = np.random.choice(getattr(self.retriever, 'num_rows', None) or len(self.retriever.data_pool['embedding']), size=N)   # global row count, also when row-sharded
         else:
             assert qids.shape[0] == N
         if verbose:

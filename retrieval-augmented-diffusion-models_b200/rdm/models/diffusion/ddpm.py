@@ -20,6 +20,7 @@ from ldm.util import instantiate_from_config
 from rdm.models.diffusion.ddim import DDIMSampler
 from rdm.util import SampleLogs, ischannellastimage, isimage
 from rdm_b200 import sampler as _tables
+from rdm_b200.knn import search_raw
 
 
 def disabled_train(self, mode=True):
@@ -247,8 +248,7 @@ class MinimalRETRODiffusion(nn.Module):
             output['query_patches'] = queries[:, :, None]                                   # [b, n, 1, c, h, w] (not resized: no first-stage encoder here)
         queries = queries.reshape(-1, *queries.shape[2:]).contiguous().float()               # '(b n) c h w'           ddpm.py:292
         q_emb = self.retriever.retriever(queries).float()                                    # CLIP image encode       ddpm.py:294
-        qh = q_emb / q_emb.norm(dim=1, keepdim=True)                                         # ddpm.py:297
-        nns, _ = searcher.search_device(qh.contiguous(), k_nn)                               # ddpm.py:298
+        nns, _ = search_raw(searcher, q_emb, k_nn)                                           # q / ||q|| + search_batched   ddpm.py:297-298
         out = searcher.gather_device(nns)                                                    # data_pool['embedding'][nns]   ddpm.py:301
         output[self.nn_key] = out.reshape(query.shape[0], n_ptch ** 2, k_nn, out.shape[-1])  # '(b n) k d -> b n k d'
         output['nns'] = nns
@@ -272,7 +272,7 @@ class MinimalRETRODiffusion(nn.Module):
                 qids = np.random.choice(nn_mem, size=N, p=ps)
             else:
                 print('Randomly sampling retrieval database entries')
-                qids = np.random.choice(len(self.retriever.data_pool['embedding']), size=N)
+                qids = np.random.choice(getattr(self.retriever, 'num_rows', None) or len(self.retriever.data_pool['embedding']), size=N)   # global row count, also when row-sharded
         else:
             assert qids.shape[0] == N
         if verbose:
@@ -292,8 +292,7 @@ class MinimalRETRODiffusion(nn.Module):
         qd = torch.as_tensor(np.asarray(qids), dtype=torch.int64, device=self.device)
         if nn_embeddings is None:
             q = searcher.gather_device(qd)                                     # data_pool['embedding'][qids]      ddpm.py:897
-            qh = q / q.norm(dim=1, keepdim=True)                               # q / ||q||                          ddpm.py:907
-            nns, _ = searcher.search_device(qh, k_nn)                          # searcher.search_batched(...)       ddpm.py:906-908
+            nns, _ = search_raw(searcher, q, k_nn)                             # q / ||q|| + search_batched(...)    ddpm.py:906-908
             retro_cond = searcher.gather_device(nns)                           # data_pool['embedding'][nns] fp32   ddpm.py:921
             out.extras['nns'] = nns
         else:
@@ -324,6 +323,8 @@ class MinimalRETRODiffusion(nn.Module):
             assert query.ndim in [3, 4], 'User defined query for sampling has to be an image or of batch of images'
             if query.ndim == 3:
                 query = torch.stack([query] * bs, dim=0)
+            elif query.shape[0] == 1 and bs > 1:
+                query = query.expand(bs, *query.shape[1:]).contiguous()         # '1 h w c -> b h w c'   ddpm.py:715-716
             assert ischannellastimage(query) or isimage(query)
             q_emb = self.retriever.embed(query.to(self.device))                 # CLIP image encode (dsetbuilder.py:461-473)
         else:
@@ -332,8 +333,7 @@ class MinimalRETRODiffusion(nn.Module):
                 q_emb = q_emb.expand(bs, -1).contiguous()
         k_nn = self.k_nn if k_nn is None else k_nn
         print(f'Query shape is {tuple(q_emb.shape)}')
-        qh = q_emb / q_emb.norm(dim=1, keepdim=True)                            # dsetbuilder.py:487
-        nns, _ = searcher.search_device(qh.contiguous(), k_nn)                  # dsetbuilder.py:490
+        nns, _ = search_raw(searcher, q_emb, k_nn)                              # q / ||q|| + search_batched   dsetbuilder.py:487-490
         r_emb = searcher.gather_device(nns)                                     # dsetbuilder.py:493
         if normalize:
             q_emb = q_emb / q_emb.norm(dim=-1, keepdim=True)

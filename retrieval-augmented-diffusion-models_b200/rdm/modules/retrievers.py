@@ -90,7 +90,7 @@ class CLIPTextEmbedder(nn.Module):
         self.device, self.add_k_shape = device, add_k_shape
 
     def preprocess(self, text):
-        from clip import tokenize
+        from rdm.modules.custom_clip.clip import tokenize          # retrievers.py:9,111: the vendored tokenizer (cuts over-long captions)
         return tokenize(text)
 
     def forward(self, txt):

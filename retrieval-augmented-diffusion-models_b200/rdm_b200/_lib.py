@@ -25,6 +25,8 @@ SIGNATURES = {
     "rdm_knn_size": (c_int64, [c_void_p]),
     "rdm_knn_get_inv_norms": (c_int, [c_void_p, c_void_p, c_void_p]),
     "rdm_knn_search": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rdm_knn_normalize": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "rdm_knn_search_raw": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdm_knn_merge": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "rdm_knn_gather": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "rdm_unet_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int32]),

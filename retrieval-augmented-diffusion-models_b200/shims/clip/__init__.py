@@ -1,7 +1,8 @@
 """`clip.tokenize` stand-in (OpenAI CLIP byte-pair tokenizer; the reference vendors the same algorithm in
 `rdm/modules/custom_clip/simple_tokenizer.py` / `clip.py:127-143`).  Own implementation of the published BPE procedure; the
 merge table (`bpe_simple_vocab_16e6.txt.gz`, a data file of the CLIP release) is NOT shipped here and is looked up at
-`$CLIP_BPE_PATH`, next to an installed `clip` / the reference's `rdm/modules/custom_clip/`, or under the current directory."""
+`$CLIP_BPE_PATH`, then under every `sys.path` root as `rdm/modules/custom_clip/` (drop the file next to this package's mirror of that
+directory), `clip/` (an installed CLIP) or the root itself, then under the current directory."""
 import gzip
 import html
 import os
@@ -16,7 +17,7 @@ _PAT = re.compile(r"""<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|
 
 def _find_vocab():
     cands = [os.environ.get("CLIP_BPE_PATH")]
-    roots = [os.getcwd()] + list(sys.path) + ["/root/reference"]
+    roots = [os.getcwd()] + list(sys.path)
     for r in roots:
         if r:
             cands += [os.path.join(r, "rdm", "modules", "custom_clip", "bpe_simple_vocab_16e6.txt.gz"), os.path.join(r, "clip", "bpe_simple_vocab_16e6.txt.gz"),
@@ -82,7 +83,9 @@ def _tokenizer():
     return _Tokenizer(_find_vocab())
 
 
-def tokenize(texts, context_length=77, truncate=False):
+def tokenize(texts, context_length=77, truncate=False, cut=False):
+    """OpenAI `clip.tokenize` (raises on over-long input unless `truncate`, which re-inserts EOT).  `cut=True` is the behaviour of the
+    reference's vendored copy (`rdm/modules/custom_clip/clip.py:127-143`): warn and cut to `context_length` WITHOUT re-inserting EOT."""
     if isinstance(texts, str):
         texts = [texts]
     t = _tokenizer()
@@ -91,9 +94,13 @@ def tokenize(texts, context_length=77, truncate=False):
     for i, text in enumerate(texts):
         ids = [sot] + t.encode(text) + [eot]
         if len(ids) > context_length:
-            if not truncate:
+            if cut:
+                print(f"WARNING: Input of length {len(ids)} is too long for context length {context_length}. Cutting.")
+                ids = ids[:context_length]
+            elif not truncate:
                 raise RuntimeError(f"Input {text} is too long for context length {context_length}")
-            ids = ids[:context_length]; ids[-1] = eot
+            else:
+                ids = ids[:context_length]; ids[-1] = eot
         result[i, :len(ids)] = torch.tensor(ids)
     return result
 

@@ -52,12 +52,29 @@ def _worker(rank, world, port, q):
     db[4000] = db[3]                                            # a duplicate that lives in the OTHER shard: tie -> lowest global index
     qh = oknn.normalize_queries(np.concatenate([db[[3, 4990]].astype(np.float32), rng.standard_normal((3, 512)).astype(np.float32)]))
     lo, hi = shard_range(len(db), rank, world)
-    s = ShardedSearcher(OracleLocalSearcher(db[lo:hi], lo), merge_fn=cpu_merge)
+    full_i, full_d = oknn.search(db, qh, 6)
+    ok = list(full_i[0, :2]) == [3, 4000]
+    # (a) the same queries on every rank, declared: one packed all_gather, all_reduce of the owners' rows
+    s = ShardedSearcher(OracleLocalSearcher(db[lo:hi], lo), merge_fn=cpu_merge, same_queries=True)
     idx, dist_ = s.search_device(torch.from_numpy(qh), 6)
     ctx = s.gather_device(idx)
-    full_i, full_d = oknn.search(db, qh, 6)
-    ok = np.array_equal(idx.numpy(), full_i) and np.array_equal(dist_.numpy(), full_d) and np.array_equal(ctx.numpy(), db[full_i].astype(np.float32))
-    ok = ok and list(full_i[0, :2]) == [3, 4000]
+    ok = ok and np.array_equal(idx.numpy(), full_i) and np.array_equal(dist_.numpy(), full_d) and np.array_equal(ctx.numpy(), db[full_i].astype(np.float32))
+    # (b) the default contract: every rank brings its OWN queries (same count) -- all_gather of the queries, all_to_all of the packed
+    #     lists, reduce_scatter of the owners' rows; each rank must get exactly the unsharded answer for ITS queries
+    s2 = ShardedSearcher(OracleLocalSearcher(db[lo:hi], lo), merge_fn=cpu_merge)
+    mine = oknn.normalize_queries(np.concatenate([db[[3 + 4000 * rank, 17 + rank]].astype(np.float32),
+                                                  np.random.default_rng(100 + rank).standard_normal((3, 512)).astype(np.float32)]))
+    idx2, dist2 = s2.search_device(torch.from_numpy(mine), 6)
+    ctx2 = s2.gather_device(idx2)
+    want_i, want_d = oknn.search(db, mine, 6)
+    ok = ok and np.array_equal(idx2.numpy(), want_i) and np.array_equal(dist2.numpy(), want_d) and np.array_equal(ctx2.numpy(), db[want_i].astype(np.float32))
+    ok = ok and ctx2.shape == (5, 6, 512)
+    # (c) unequal query counts are reported, not mis-merged
+    try:
+        s2.search_device(torch.from_numpy(mine[:4 + rank]), 6)
+        ok = False
+    except RuntimeError as e:
+        ok = ok and "same number of queries" in str(e)
     q.put((rank, bool(ok), (lo, hi)))
     dist.barrier()
     dist.destroy_process_group()
@@ -111,6 +128,17 @@ def _builder_worker(rank, world, port, q, dbdir):
     want_i, want_d = oknn.search(full, oknn.normalize_queries(queries), 5)
     ok = ok and np.array_equal(out["nns"], want_i) and np.array_equal(out["distances"], want_d)
     ok = ok and np.array_equal(out["embeddings"], full[want_i].astype(np.float32)) and np.array_equal(out["img_ids"], want_i)
+    # pseudo-queries are drawn from the WHOLE database on every rank (ddpm.py:867), not from the rows this rank happens to hold
+    ok = ok and b.num_rows == len(full) and len(b.data_pool["embedding"]) < len(full)
+    from rdm.models.diffusion.ddpm import MinimalRETRODiffusion
+    from rdm.models.autoregression.transformer import LatentImageRETRO
+    import types
+    for cls in (MinimalRETRODiffusion, LatentImageRETRO):
+        host = types.SimpleNamespace(use_memory=False, retriever=b)
+        np.random.seed(5)
+        qids = cls.get_qids(host, 100, 4000)
+        np.random.seed(5)
+        ok = ok and np.array_equal(qids, np.random.choice(len(full), size=4000)) and int(qids.max()) >= hi - lo
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()

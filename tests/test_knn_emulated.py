@@ -103,3 +103,20 @@ def test_candidate_overflow_takes_the_fallback_pass(emulated, ndup):
     q = np.concatenate([db[[dup[0]]].astype(np.float32), rng.standard_normal((1, 512)).astype(np.float32)])
     _, wi = check(db, q, 8)
     assert list(wi[0]) == sorted(dup)[:8]
+
+
+@pytest.mark.parametrize("d", [256, 512, 768, 1024])
+def test_query_normalisation_is_bit_identical_to_numpy(emulated, d):
+    """rdm_knn_normalize (csrc/knn.cu knn_normalize_kernel) == `q / np.linalg.norm(q, axis=1)[:, np.newaxis]` (ddpm.py:907), bit patterns;
+    rdm_knn_search_raw == normalise + rdm_knn_search."""
+    from rdm_b200.knn import B200Searcher, normalize_device
+    rng = np.random.default_rng(d)
+    q = (rng.standard_normal((7, d)) * rng.uniform(0.01, 30.0, size=(7, 1))).astype(np.float32)
+    want = q / np.linalg.norm(q, axis=1)[:, np.newaxis]
+    got = normalize_device(torch.from_numpy(q)).numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    db = rng.standard_normal((700, d)).astype(np.float16)
+    s = B200Searcher(db, device="cpu")
+    a = s.search_raw_device(torch.from_numpy(q), 5, return_scores=True)
+    b = s.search_device(torch.from_numpy(want), 5, return_scores=True)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))

@@ -90,3 +90,16 @@ def test_knn_oracle_agrees_with_an_independent_exact_searcher():
     assert np.array_equal(idx, i_sk)
     assert np.allclose(dist, 1.0 - d_sk, atol=2e-6)
     assert list(idx[:5, 0]) == [3, 777, 4096, 19_999, 12_345] and np.allclose(dist[:5, 0], 1.0, atol=1e-6)
+
+
+def test_query_normalisation_restatement_matches_numpy_bitwise():
+    """oracle/knn.py pairwise_sum_f32 / normalize_queries_restated (the order csrc/knn.cu knn_normalize_kernel follows) against NumPy's own
+    `q / np.linalg.norm(q, axis=1)[:, np.newaxis]` (ddpm.py:907), every supported width plus ragged ones, bit patterns compared."""
+    from oracle import knn as oknn
+    rng = np.random.default_rng(12)
+    for d in (5, 8, 100, 128, 136, 256, 512, 768, 1024, 1000):
+        q = (rng.standard_normal((6, d)) * rng.uniform(0.01, 30.0, size=(6, 1))).astype(np.float32)
+        want = q / np.linalg.norm(q, axis=1)[:, np.newaxis]
+        got = oknn.normalize_queries_restated(q)
+        assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), want.view(np.uint32)), d
+        assert np.array_equal(oknn.normalize_queries(q).view(np.uint32), want.view(np.uint32))

@@ -58,3 +58,34 @@ def test_tokenizer_matches_reference_golden_ids():
     for row, (prompt, ids) in zip(toks, g["prompts"].items()):
         assert row[:len(ids)].tolist() == ids and int(row[len(ids):].abs().sum()) == 0, prompt
         assert int(row.argmax()) == len(ids) - 1                      # EOT is the largest id: encode_text gathers it (model.py:318)
+
+
+def test_vendored_tokenizer_cuts_long_captions_like_the_reference():
+    """rdm/modules/custom_clip/clip.py:127-143: over-long captions are cut to 77 ids with a warning and EOT is NOT re-inserted
+    (OpenAI's clip.tokenize raises instead); CLIPTextEmbedder.preprocess goes through it (retrievers.py:9,111)."""
+    import pytest
+    _shims()
+    import clip
+    try:
+        clip._find_vocab()
+    except FileNotFoundError:
+        pytest.skip("bpe_simple_vocab_16e6.txt.gz not available")
+    import rdm  # noqa: F401
+    from rdm.modules.custom_clip.clip import tokenize
+    long_caption = " ".join(["a photo of a very fluffy corgi wearing a tiny hat"] * 12)
+    with pytest.raises(RuntimeError):
+        clip.tokenize(long_caption)
+    toks = tokenize([long_caption, "a corgi"])
+    assert toks.shape == (2, 77) and int(toks[0, 0]) == 49406 and int((toks[0] == 49407).sum()) == 0 and int(toks[0, -1]) != 0
+    assert toks[1].tolist()[:4] == clip.tokenize("a corgi")[0].tolist()[:4] and int(toks[1].argmax()) == 3
+    ref_path = "/root/reference/rdm/modules/custom_clip"
+    if os.path.isdir(ref_path):                                            # the reference's own vendored tokenizer on the same caption
+        import importlib.util
+        import sys
+        import types
+        sys.modules.setdefault("ftfy", types.SimpleNamespace(fix_text=lambda x: x))          # absent here; an identity on ASCII captions
+        spec = importlib.util.spec_from_file_location("ref_simple_tokenizer", os.path.join(ref_path, "simple_tokenizer.py"))
+        mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+        t = mod.SimpleTokenizer()
+        want = ([t.encoder["<|startoftext|>"]] + t.encode(long_caption) + [t.encoder["<|endoftext|>"]])[:77]
+        assert toks[0].tolist() == want

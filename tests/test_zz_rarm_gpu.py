@@ -256,7 +256,15 @@ def test_product_sampling_flow_matches_reference_code(cuda):
         finally:
             torch.rand = real_rand
         assert np.array_equal(np.asarray(logs["qids"]), g[f"{tag}:qids"])
-        assert torch.equal(logs["samples_with_sampled_nns"].cpu(), torch.from_numpy(g[f"{tag}:images"])), tag
+        # token ids are compared EXACTLY; they are recovered from the fixture's images through the stub first stage (decode = tanh of the
+        # first three code channels, one pixel per token).  The images themselves are compared to 1 ulp-scale tolerance only: the stub's
+        # torch.tanh runs on the device here and on the CPU in the fixture, and the two math libraries round differently.
+        cb = torch.tanh(model.first_stage_model.quantize.embedding.weight.detach().cpu()[:, :3])            # [n_embed, 3]
+        want_img = torch.from_numpy(g[f"{tag}:images"])
+        want_ids = (want_img.permute(0, 2, 3, 1).reshape(2, -1, 1, 3) - cb[None, None]).abs().sum(-1).argmin(-1)
+        got_ids = logs["sampled_indices"].cpu().reshape(2, -1)
+        assert torch.equal(got_ids, want_ids), (tag, got_ids.tolist(), want_ids.tolist())
+        assert torch.allclose(logs["samples_with_sampled_nns"].cpu(), want_img, rtol=0, atol=2e-6), tag
     _, c = model.encode_to_c(torch.zeros((2, 0)))
     got = model.sample(torch.from_numpy(g["greedy:start"]).to(cuda), torch.from_numpy(g["greedy:r"]).to(cuda), c.to(cuda), steps=6, sample=False, top_k=None,
                        guidance_scale=3.0)
