@@ -139,6 +139,11 @@ RDM_API int rdm_unet_forward(rdm_unet_t* h, const float* x_dev, int32_t Bx, cons
  * 4 LayerNorm, 8 attention, 16 GEMMs with M >= 8192, 32 GEMMs with M < 8192, 64 un-fuse the cross-attention).  Outputs are garbage while a
  * mask is set; bench.py uses full-forward time minus GEMM-less forward time as the in-graph duration of the tcgen05 launches. */
 RDM_API int rdm_unet_set_ablation(rdm_unet_t* h, int32_t mask);
+/* Batch chains: the B2 rows of a forward / DDIM step are split into `chains` (1..8) contiguous sub-batches that run the whole layer
+ * sequence concurrently on their own streams (fork / join by events, captured as branches of the step graph).  GroupNorm, LayerNorm and
+ * attention are per-sample, so results do not depend on the split; small-resolution layers that cannot fill 148 SMs at once overlap.
+ * Takes effect at the next forward. */
+RDM_API int rdm_unet_set_chains(rdm_unet_t* h, int32_t chains);
 /* CUDA-graph replay of the forward (default on).  Off: every kernel is launched eagerly. */
 RDM_API int rdm_unet_set_graph(rdm_unet_t* h, int32_t on);
 /* rdm_unet_forward, then the same forward replayed from a CUDA graph captured with external event-record nodes around every

@@ -701,6 +701,9 @@ int dispatch_tc(int BN, int nsplit, const CUtensorMap& ta_hi, const CUtensorMap&
 
 }  // namespace
 
+static int g_tc_ws_slot = 0;
+void gemm_tc_set_workspace_slot(int slot) { g_tc_ws_slot = slot; }
+
 bool gemm_tc_supported(const TcA& a) {
     if (a.C % BK != 0 || a.ld % 8 != 0) return false;
     if (a.ksize == 1) return true;
@@ -783,17 +786,18 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     p.splits = splits; p.kb_per_split = (nkb_total + splits - 1) / splits; p.part = nullptr; p.cluster = clustered;
     if (getenv("RDM_TC_TRACE")) fprintf(stderr, "gemm_tc M=%d N=%d K=%d -> BN=%d splits=%d cluster=%d\n", M, w.N, w.K, BN, splits, clustered);
     if (splits > 1 && !p.cluster) {
-        static float* ws[16] = {nullptr}; static size_t ws_cap[16] = {0};
+        static float* ws[16][8] = {{nullptr}}; static size_t ws_cap[16][8] = {{0}};      // [device][workspace slot]: concurrent chains must not share partials
         int dev = 0; cudaGetDevice(&dev);
+        const int slot = g_tc_ws_slot & 7;
         const size_t need = (size_t)splits * M * w.N * sizeof(float);
-        if (need > ws_cap[dev & 15]) {                                   // grown during the eager warm-up pass, never inside a graph capture
-            if (ws[dev & 15]) cudaFree(ws[dev & 15]);
-            ws[dev & 15] = nullptr; ws_cap[dev & 15] = 0;
+        if (need > ws_cap[dev & 15][slot]) {                             // grown during the eager warm-up pass, never inside a graph capture
+            if (ws[dev & 15][slot]) cudaFree(ws[dev & 15][slot]);
+            ws[dev & 15][slot] = nullptr; ws_cap[dev & 15][slot] = 0;
             size_t cap = (size_t)48 << 20;
-            RDM_CHECK_CUDA(cudaMalloc((void**)&ws[dev & 15], cap));
-            ws_cap[dev & 15] = cap;
+            RDM_CHECK_CUDA(cudaMalloc((void**)&ws[dev & 15][slot], cap));
+            ws_cap[dev & 15][slot] = cap;
         }
-        p.part = ws[dev & 15];
+        p.part = ws[dev & 15][slot];
     }
     RDM_TRY(make_map_2d(&tb_hi, w.hi, w.K, w.N, w.ld, BN));
     if (nsplit >= 2) RDM_TRY(make_map_2d(&tb_lo, w.lo, w.K, w.N, w.ld, BN)); else tb_lo = tb_hi;

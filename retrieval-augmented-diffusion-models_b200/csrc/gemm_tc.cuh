@@ -17,3 +17,6 @@ bool gemm_tc_supported(const TcA& a);
 // f16: the 16-bit planes hold IEEE fp16 (11-bit significand) instead of bf16 (8-bit); kind::f16 MMA either way.
 // Output either fp32 (e.out) or 16-bit planes (out_hi[/out_lo], same format flag); e.res / e.bias / e.rowvec / e.act as for gemm_simt.
 int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_bf_ld, int nsplit, int f16, cudaStream_t st);
+// Concurrent batch chains (unet.cu) issue their GEMMs from one host thread, chain after chain: the split-K partial-sum workspace used by
+// the launches that follow is slot `slot` (0..7), so that chains running at the same time on different streams never share partials.
+void gemm_tc_set_workspace_slot(int slot);

@@ -19,13 +19,13 @@ __device__ __forceinline__ void store4(const Out4& o, size_t m, int c, float a, 
     if (o.hi) store_planes4(o.hi + m * o.ldb + c, o.lo ? o.lo + m * o.ldb + c : nullptr, o.f16, a, b, cc, d);
 }
 
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int Bsrc, int Bout, int C, int HW, float* __restrict__ out, int ld) {
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int Bsrc, int Bout, int b_off, int C, int HW, float* __restrict__ out, int ld) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over Bout*HW*C, c fastest
     long long total = (long long)Bout * HW * C;
     if (i >= total) return;
     int c = (int)(i % C);
     long long m = i / C;
-    int p = (int)(m % HW), b = (int)(m / HW) % Bsrc;
+    int p = (int)(m % HW), b = ((int)(m / HW) + b_off) % Bsrc;
     out[m * ld + c] = x[((long long)b * C + c) * HW + p];
 }
 
@@ -485,9 +485,9 @@ __global__ void __launch_bounds__(256) vq_quantize_kernel(const float* __restric
 
 #define LAUNCH_CHECK() do { RDM_COUNT_LAUNCH(); RDM_CHECK_CUDA(cudaGetLastError()); } while (0)
 
-int k_nchw_to_nhwc(const float* x, int Bsrc, int Bout, int C, int H, int W, View out, cudaStream_t st) {
+int k_nchw_to_nhwc(const float* x, int Bsrc, int Bout, int C, int H, int W, View out, cudaStream_t st, int b_off) {
     long long n = (long long)Bout * H * W * C;
-    nchw_to_nhwc_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, Bsrc, Bout, C, H * W, out.p, out.ld);
+    nchw_to_nhwc_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, Bsrc, Bout, b_off, C, H * W, out.p, out.ld);
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_nhwc_to_nchw(View in, int B, int C, int H, int W, float* out, cudaStream_t st) {

@@ -66,8 +66,9 @@ struct GemmEpi {
 int gemm_simt(const GemmA& a, const float* W, int N, const GemmEpi& e, cudaStream_t st);
 
 // ---- glue kernels -------------------------------------------------------------------------------
-// x NCHW [Bsrc,C,H,W] -> NHWC rows [Bout*H*W, C] with batch index taken modulo Bsrc (CFG doubling, ddim.py:233)
-int k_nchw_to_nhwc(const float* x, int Bsrc, int Bout, int C, int H, int W, View out, cudaStream_t st);
+// x NCHW [Bsrc,C,H,W] -> NHWC rows [Bout*H*W, C]: output image b reads source image (b + b_off) modulo Bsrc (CFG doubling, ddim.py:233;
+// b_off = first batch row of a chain)
+int k_nchw_to_nhwc(const float* x, int Bsrc, int Bout, int C, int H, int W, View out, cudaStream_t st, int b_off = 0);
 int k_nhwc_to_nchw(View in, int B, int C, int H, int W, float* out, cudaStream_t st);
 // timestep_embedding (ldm util): t int64 [B] -> [B, dim] = [cos | sin]
 int k_timestep_embedding(const long long* t, int B, int dim, float* out, cudaStream_t st);

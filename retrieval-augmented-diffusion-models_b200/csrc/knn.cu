@@ -186,7 +186,8 @@ struct ScanArgs {
     const u64* thr_key;    // MAIN: [QP] threshold keys
     u64* cand;             // MAIN: [QP][CAND_CAP]
     unsigned* cand_cnt;    // MAIN: [QP]
-    const unsigned* overflow;   // LOCKED: run only if *overflow != 0
+    const unsigned* overflow;   // LOCKED: per-query flags; a query group is re-scanned only if one of its flags is set
+    int nq_total;          // LOCKED: queries of the whole pass (blockIdx.y = group of QP queries)
     int group_stride;      // SAMPLE: take every group_stride-th row group
 };
 
@@ -197,7 +198,18 @@ template <typename T, int D, int QP, int R, int MODE, int NST>
 __global__ void __launch_bounds__(SCAN_THREADS)
 knn_scan_kernel(const T* __restrict__ db, const float* __restrict__ inv, long long n,
                 const float* __restrict__ q, int nq_valid, ScanArgs args) {
-    if (MODE == SCAN_LOCKED) { if (*args.overflow == 0u) return; }
+    if (MODE == SCAN_LOCKED) {
+        pdl_launch_dependents();                     // fallback pair: launched with programmatic serialisation behind the select kernel
+        pdl_wait();
+        // fallback pass: blockIdx.y selects a group of QP queries; it re-scans the database only if a query of the group overflowed
+        const int grp = blockIdx.y;
+        nq_valid = args.nq_total - grp * QP < QP ? args.nq_total - grp * QP : QP;
+        unsigned any = 0u;
+        for (int i = 0; i < nq_valid; i++) any |= args.overflow[grp * QP + i];
+        if (any == 0u) return;
+        q += (size_t)grp * QP * D;
+        args.lists_out += (size_t)grp * gridDim.x * QP * LIST;
+    }
     constexpr int STAGE_BYTES = R * D * (int)sizeof(T);
     constexpr int EPL = D / 32;              // elements per lane per row
     constexpr int EPV = Elem<T>::EPV;        // elements per 16-byte vector
@@ -385,7 +397,7 @@ knn_threshold_kernel(const u64* __restrict__ maxima, size_t per_q, u64* __restri
     cur = cta_tree_merge(cur, s_keys, warp, lane, P);
     if (warp == 0) {
         if (lane == KSEL - 1) thr_key[qi] = relax_key(cur);       // descending: lane 31 holds the 32nd largest (relaxed by the score slack)
-        if (lane == 0) { cand_cnt[qi] = 0u; done[qi] = 0u; if (qi == 0) *overflow = 0u; }
+        if (lane == 0) { cand_cnt[qi] = 0u; done[qi] = 0u; overflow[qi] = 0u; }
     }
 }
 
@@ -395,10 +407,18 @@ __device__ __forceinline__ bool better_pair(double sa, long long ia, double sb, 
 // EXACTLY (fp64, definition: oracle/knn_ref.c) every survivor whose fp32 score is within the slack of f_k -- at most one per thread -- and
 // emit the top-k by (score desc, row asc): one warp-level bitonic sort when at most 32 survivors remain (the usual case), k rounds of a
 // block-wide arg-best otherwise.
-// FROM_LISTS = false: candidates of query qi are cand[qi*CAND_CAP .. + min(cnt, CAP)); sets *overflow when cnt > CAP or when more than
+// FROM_LISTS = false: candidates of query qi are cand[qi*CAND_CAP .. + min(cnt, CAP)); sets overflow[qi] when cnt > CAP or when more than
 //                     1024 survivors lie within the slack (a pathological cluster of near-identical rows: the fallback pass answers).
-// FROM_LISTS = true : fallback, per-CTA lists [nblk][QP][LIST]; runs only when *overflow != 0; re-ranks the 32 best fp32 keys.
+// FROM_LISTS = true : fallback, per-CTA lists [group][nblk][QP][LIST]; runs only for queries with overflow[qi] != 0 (every other query keeps
+//                     the result of the main path); re-ranks the 32 best fp32 keys.
+// Exact re-rank: a WARP stages each candidate row in shared memory with coalesced 16-byte loads (a thread walking its own row paid ~16
+// dependent DRAM round trips), then one lane evaluates the oracle's sequential fp64 sum from shared memory.
 constexpr int SEL_MAX = 1024;
+template <typename T, int D> struct SelCfg {
+    static constexpr int ROW_BYTES = D * (int)sizeof(T);
+    static constexpr int ROWS_PAR = 32768 / ROW_BYTES > 32 ? 32 : 32768 / ROW_BYTES;      // rows staged per round (one per warp)
+    static constexpr int DYN_BYTES = ROWS_PAR * ROW_BYTES;
+};
 template <typename T, int D, bool FROM_LISTS>
 __global__ void __launch_bounds__(1024)
 knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const unsigned* __restrict__ cand_cnt, unsigned* __restrict__ overflow,
@@ -408,25 +428,30 @@ knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const unsigne
     __shared__ u64 s_keys[32][LIST];
     __shared__ float s_q[D];
     __shared__ u64 s_cand[SEL_MAX];
+    __shared__ double s_score[SEL_MAX];
+    extern __shared__ uint4 s_rows[];                      // [ROWS_PAR][ROW_BYTES / 16]
     __shared__ u64 s_cut;
     __shared__ unsigned s_ncand;
     __shared__ double s_bs[32];
     __shared__ long long s_bi[32];
     __shared__ long long s_win;
     const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (FROM_LISTS) { if (*overflow == 0u) return; }
+    pdl_launch_dependents();                         // the kernels of a search are chained with programmatic serialisation: the next one is
+    pdl_wait();                                      // staged while this one runs and waits here for its predecessor's results
+    if (FROM_LISTS) { if (overflow[qi] == 0u) return; }
     for (int i = tid; i < D; i += blockDim.x) s_q[i] = q[(size_t)qi * D + i];
     if (tid == 0) s_ncand = 0u;
     u64 cur = 0ull;
     unsigned cnt = 0u;
     if (FROM_LISTS) {
+        const int grp = qi / QP, ql = qi - grp * QP;
         for (int b = warp; b < nblk; b += 32) {
-            u64 batch = lists[((size_t)b * QP + qi) * LIST + lane];
+            u64 batch = lists[(((size_t)grp * nblk + b) * QP + ql) * LIST + lane];
             if (__any_sync(FULL, batch != 0ull)) cur = warp_merge_top32(cur, batch, lane);
         }
     } else {
         cnt = cand_cnt[qi];
-        if (cnt > (unsigned)CAND_CAP) { if (tid == 0) atomicExch(overflow, 1u); return; }     // the fallback pass redoes this batch
+        if (cnt > (unsigned)CAND_CAP) { if (tid == 0) overflow[qi] = 1u; return; }            // the fallback pass redoes this query
         for (unsigned b = warp * 32; b < cnt; b += 32 * 32) {
             u64 batch = b + lane < cnt ? lists[(size_t)qi * CAND_CAP + b + lane] : 0ull;
             cur = warp_merge_top32(cur, batch, lane);
@@ -446,27 +471,48 @@ knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const unsigne
             if (key != 0ull && key >= cut) { const unsigned pos = atomicAdd(&s_ncand, 1u); if (pos < (unsigned)SEL_MAX) s_cand[pos] = key; }
         }
         __syncthreads();
-        if (s_ncand > (unsigned)SEL_MAX) { if (tid == 0) atomicExch(overflow, 1u); return; }
+        if (s_ncand > (unsigned)SEL_MAX) { if (tid == 0) overflow[qi] = 1u; return; }
     }
-    // exact re-rank: one candidate per thread
+    // exact re-rank: warp w stages candidate base + w, lane 0 sums it in the oracle's order; afterwards thread t owns candidate t
+    {
+        constexpr int RP = SelCfg<T, D>::ROWS_PAR, V = SelCfg<T, D>::ROW_BYTES / 16, EPV = Elem<T>::EPV;
+        const int ncand = (int)s_ncand;
+        for (int base = 0; base < ncand; base += RP) {
+            const int c = base + warp;
+            if (warp < RP && c < ncand) {
+                const u64 key = s_cand[c];
+                const long long r = key != 0ull ? (long long)(0xffffffffu - (uint32_t)key) : n;
+                double acc = -CUDART_INF;
+                if (r < n) {
+                    const uint4* src = reinterpret_cast<const uint4*>(db + (size_t)r * D);
+                    uint4* dst = s_rows + (size_t)warp * V;
+                    for (int v = lane; v < V; v += 32) dst[v] = ldg_stream(src + v);
+                    __syncwarp();
+                    if (lane == 0) {
+                        acc = 0.0;
+#pragma unroll 4
+                        for (int j = 0; j < V; j++) {
+                            float f[EPV];
+                            Elem<T>::unpack(dst[j], f);
+#pragma unroll
+                            for (int e = 0; e < EPV; e++) acc = __dadd_rn(acc, __dmul_rn((double)s_q[j * EPV + e], (double)f[e]));      // same order as the oracle
+                        }
+                        acc = __dmul_rn(acc, (double)inv[r]);
+                        if (!(acc == acc)) acc = -CUDART_INF;
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) s_score[c] = acc;
+            }
+        }
+        __syncthreads();
+    }
     const u64 mykey = tid < (int)s_ncand ? s_cand[tid] : 0ull;
     const bool have = mykey != 0ull;
     long long row = have ? (long long)(0xffffffffu - (uint32_t)mykey) : 0x7fffffffffffffffLL;
     double s = -CUDART_INF;
-    if (have && row < n) {
-        const uint4* r = reinterpret_cast<const uint4*>(db + (size_t)row * D);      // 16-byte pieces: the loads run ahead of the fp64 chain
-        constexpr int EPV = Elem<T>::EPV;
-        double acc = 0.0;
-#pragma unroll 4
-        for (int j = 0; j < D / EPV; j++) {
-            float f[EPV];
-            Elem<T>::unpack(ldg_stream(r + j), f);
-#pragma unroll
-            for (int e = 0; e < EPV; e++) acc = __dadd_rn(acc, __dmul_rn((double)s_q[j * EPV + e], (double)f[e]));      // same order as the oracle
-        }
-        acc = __dmul_rn(acc, (double)inv[row]);
-        s = (acc == acc) ? acc : -CUDART_INF;
-    } else if (have) { row = 0x7fffffffffffffffLL; }
+    if (have && row < n) s = s_score[tid];
+    else if (have) row = 0x7fffffffffffffffLL;
     if (s_ncand <= 32u) {
         // the usual case (and always the fallback pass): all candidates sit in warp 0 -- one bitonic sort of (score, row) pairs, best first
         if (warp != 0) return;
@@ -571,11 +617,19 @@ __global__ void knn_gather_kernel(const T* __restrict__ db, long long n, long lo
 // One CTA of 64 threads per query: thread t owns accumulator t % 8 of leaf t / 8; fp32 addition is commutative, so the xor-shuffle tree
 // reproduces the association above exactly.
 template <int D>
-__global__ void __launch_bounds__(64) knn_normalize_kernel(const float* __restrict__ q, int nq, float* __restrict__ out) {
+__global__ void __launch_bounds__(64) knn_normalize_kernel(const float* __restrict__ q, int nq, float* __restrict__ out,
+                                                          __half* __restrict__ split, int NQ, unsigned* __restrict__ grid_bar) {
     constexpr int NLEAF = D == 768 ? 8 : D / 128, L = D / NLEAF;
     static_assert(NLEAF == 2 || NLEAF == 4 || NLEAF == 8, "leaf tree");
     __shared__ float s_w[2];
     const int qi = blockIdx.x, t = threadIdx.x, leaf = t >> 3, j = t & 7;
+    // split != null (tensor-core scan follows): also emit the fp16 hi / lo rows of q_hat (rows [0, NQ) = hi, [NQ, 2 NQ) = lo, zero beyond nq)
+    // and reset the grid-barrier counter of the fused scan -- the separate query-split launch disappears
+    if (qi == 0 && t == 0 && grid_bar) *grid_bar = 0u;
+    if (qi >= nq) {
+        for (int i = t; i < D; i += 64) { split[(size_t)qi * D + i] = __float2half_rn(0.f); split[(size_t)(NQ + qi) * D + i] = __float2half_rn(0.f); }
+        return;
+    }
     const float* x = q + (size_t)qi * D;
     float r = 0.f;
     if (leaf < NLEAF) {
@@ -594,7 +648,15 @@ __global__ void __launch_bounds__(64) knn_normalize_kernel(const float* __restri
     r = NLEAF == 8 ? __fadd_rn(s_w[0], s_w[1]) : s_w[0];
     r = __fadd_rn(0.f, r);                                          // add.reduce starts from the identity 0
     const float nrm = __fsqrt_rn(r);
-    for (int i = t; i < D; i += 64) out[(size_t)qi * D + i] = __fdiv_rn(x[i], nrm);
+    for (int i = t; i < D; i += 64) {
+        const float v = __fdiv_rn(x[i], nrm);
+        out[(size_t)qi * D + i] = v;
+        if (split) {
+            const __half hh = __float2half_rn(v);
+            split[(size_t)qi * D + i] = hh;
+            split[(size_t)(NQ + qi) * D + i] = __float2half_rn(v - __half2float(hh));
+        }
+    }
 }
 
 // one warp per query: k rounds of arg-best over parts*k candidates
@@ -644,18 +706,32 @@ struct rdm_knn {
     size_t maxima_keys = 0;
     u64* cand = nullptr;       // [MAX_QP][CAND_CAP]
     u64* thr_key = nullptr;    // [MAX_QP]
-    unsigned* cand_cnt = nullptr;   // [MAX_QP] + overflow flag at [MAX_QP]
+    unsigned* cand_cnt = nullptr;   // [MAX_TCQ] survivor counters, then [MAX_TCQ] per-query overflow flags
     u64* thr_part = nullptr;        // threshold kernel: [MAX_TCQ][THR_P][LIST] partial top-32 lists
     unsigned* thr_done = nullptr;   // [MAX_TCQ] arrival counters (zero between searches)
     void* qsplit = nullptr;         // fp16 hi/lo query rows for the tensor-core scan
     float* qhat = nullptr;          // rdm_knn_search_raw: normalised queries [QHAT_ROWS][d]
+    void* fused_ws = nullptr;       // fused tensor-core scan: group maxima + grid-barrier counter
     int max_grid = 0;
 };
 
 namespace {
 
+// launch with programmatic stream serialisation: the kernel may be staged while its predecessor in the stream still runs; it calls
+// griddepcontrol.wait before touching the predecessor's results (RDM_KNN_NO_PDL=1: ordinary stream order)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    static const int no_pdl = getenv("RDM_KNN_NO_PDL") ? 1 : 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <typename T, int D, int QP, int R, int MODE>
-int launch_scan(rdm_knn* h, const float* q, int nq_valid, ScanArgs args, cudaStream_t st, int* grid_out) {
+int launch_scan(rdm_knn* h, const float* q, int nq_valid, ScanArgs args, cudaStream_t st, int* grid_out, int groups = 1) {
     constexpr int STAGE = R * D * (int)sizeof(T);
     constexpr int QBYTES = QP * D * (int)sizeof(float);
     // 2-byte rows: TMA rings (3 stages if they fit next to the queries in 227 KB, else 2); 4-byte rows: direct loads
@@ -678,10 +754,30 @@ int launch_scan(rdm_knn* h, const float* q, int nq_valid, ScanArgs args, cudaStr
     int g = grid;
     long long need = (nsteps + SCAN_WARPS - 1) / SCAN_WARPS;
     if (need < g) g = (int)(need < 1 ? 1 : need);
-    kern<<<g, SCAN_THREADS, smem, st>>>((const T*)h->db, h->inv, h->n, q, nq_valid, args);
+    if (MODE == SCAN_LOCKED) {
+        RDM_CHECK_CUDA(launch_chained(kern, dim3(g, groups), dim3(SCAN_THREADS), smem, st, (const T*)h->db, (const float*)h->inv, (long long)h->n, q, nq_valid, args));
+    } else {
+        kern<<<dim3(g, groups), SCAN_THREADS, smem, st>>>((const T*)h->db, h->inv, h->n, q, nq_valid, args);
+    }
     RDM_COUNT_LAUNCH();
     RDM_CHECK_CUDA(cudaGetLastError());
     *grid_out = g;
+    return RDM_OK;
+}
+
+template <typename T, int D, bool FROM_LISTS>
+int launch_select(rdm_knn* h, int nq, const u64* lists, int nblk, int QP, const float* qp, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st) {
+    auto kern = knn_select_kernel<T, D, FROM_LISTS>;
+    static bool configured[16] = {false};
+    if (!configured[h->device & 15]) {
+        RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SelCfg<T, D>::DYN_BYTES));
+        configured[h->device & 15] = true;
+    }
+    unsigned* overflow = h->cand_cnt + MAX_TCQ;
+    RDM_CHECK_CUDA(launch_chained(kern, dim3(nq), dim3(1024), (size_t)SelCfg<T, D>::DYN_BYTES, st, lists, nblk, QP, (const unsigned*)h->cand_cnt, overflow, (const T*)h->db,
+                                  (const float*)h->inv, (long long)h->n, qp, k, (long long)h->idx_base, idx_out, dist_out, sc_out));
+    RDM_COUNT_LAUNCH();
+    RDM_CHECK_CUDA(cudaGetLastError());
     return RDM_OK;
 }
 
@@ -698,44 +794,40 @@ int search_pass(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_out,
     RDM_COUNT_LAUNCH();
     ScanArgs m{}; m.group_stride = 1; m.thr_key = h->thr_key; m.cand = h->cand; m.cand_cnt = h->cand_cnt;
     RDM_TRY((launch_scan<T, D, QP, R, SCAN_MAIN>(h, qp, cnt, m, st, &g1)));
-    knn_select_kernel<T, D, false><<<cnt, 1024, 0, st>>>(h->cand, 0, QP, h->cand_cnt, overflow, (const T*)h->db, h->inv, h->n, qp, k, h->idx_base,
-                                                         idx_out, dist_out, sc_out);
-    RDM_COUNT_LAUNCH();
-    // device-side conditional fallback (both kernels return immediately unless a candidate buffer overflowed)
-    ScanArgs f{}; f.group_stride = 1; f.lists_out = h->lists; f.overflow = overflow;
+    RDM_TRY((launch_select<T, D, false>(h, cnt, h->cand, 0, QP, qp, k, idx_out, dist_out, sc_out, st)));
+    // device-side conditional fallback (both kernels return immediately unless a candidate buffer of one of the queries overflowed)
+    ScanArgs f{}; f.group_stride = 1; f.lists_out = h->lists; f.overflow = overflow; f.nq_total = cnt;
     RDM_TRY((launch_scan<T, D, QP, R, SCAN_LOCKED>(h, qp, cnt, f, st, &g2)));
-    knn_select_kernel<T, D, true><<<cnt, 1024, 0, st>>>(h->lists, g2, QP, h->cand_cnt, overflow, (const T*)h->db, h->inv, h->n, qp, k, h->idx_base,
-                                                        idx_out, dist_out, sc_out);
-    RDM_COUNT_LAUNCH();
-    RDM_CHECK_CUDA(cudaGetLastError());
+    RDM_TRY((launch_select<T, D, true>(h, cnt, h->lists, g2, QP, qp, k, idx_out, dist_out, sc_out, st)));
     return RDM_OK;
 }
 
 // fp16 / d=512, >= 8 queries: sample + main scans on the tensor cores, up to 64 queries per pass.
 template <typename T, int D>
-int search_pass_tc(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st) {
+int search_pass_tc(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st, int presplit = 0) {
     constexpr int R = 8;
     unsigned* overflow = h->cand_cnt + MAX_TCQ;
-    const long long ntiles = (h->n + 127) / 128;
-    int stride = (int)(ntiles / 512); if (stride > 16) stride = 16; if (stride < 1) stride = 1;       // >= ~64K sampled rows
-    const long long per_q = knn_tc_sample_rows(h->n, stride);
-    RDM_REQUIRE((size_t)per_q * cnt <= h->maxima_keys, RDM_ERR_STATE, "knn: sample buffer too small");
-    RDM_TRY(knn_scan_tc(h->db, h->inv, h->n, h->device, qp, cnt, h->qsplit, 1, stride, h->maxima, per_q, nullptr, nullptr, nullptr, st));
-    knn_threshold_kernel<<<dim3(cnt, THR_P), 1024, 0, st>>>(h->maxima, (size_t)per_q, h->thr_key, h->cand_cnt, overflow, h->thr_part, h->thr_done);
-    RDM_COUNT_LAUNCH();
-    RDM_TRY(knn_scan_tc(h->db, h->inv, h->n, h->device, qp, cnt, h->qsplit, 0, 1, nullptr, 0, h->thr_key, h->cand, h->cand_cnt, st));
-    knn_select_kernel<T, D, false><<<cnt, 1024, 0, st>>>(h->cand, 0, 0, h->cand_cnt, overflow, (const T*)h->db, h->inv, h->n, qp, k, h->idx_base,
-                                                         idx_out, dist_out, sc_out);
-    RDM_COUNT_LAUNCH();
-    for (int g0 = 0; g0 < cnt; g0 += MAX_QP) {         // device-side conditional fallback, 16 queries per group (normally empty launches)
-        const int gc = cnt - g0 < MAX_QP ? cnt - g0 : MAX_QP; int g2 = 0;
-        ScanArgs f{}; f.group_stride = 1; f.lists_out = h->lists; f.overflow = overflow;
-        RDM_TRY((launch_scan<T, D, MAX_QP, R, SCAN_LOCKED>(h, qp + (size_t)g0 * D, gc, f, st, &g2)));
-        knn_select_kernel<T, D, true><<<gc, 1024, 0, st>>>(h->lists, g2, MAX_QP, h->cand_cnt, overflow, (const T*)h->db, h->inv, h->n, qp + (size_t)g0 * D, k,
-                                                           h->idx_base, idx_out + (size_t)g0 * k, dist_out + (size_t)g0 * k, sc_out ? sc_out + (size_t)g0 * k : nullptr);
+    // one cooperative launch (sample phase -> grid barrier -> thresholds -> main scan) where the database is large enough for it;
+    // otherwise (or with RDM_KNN_NO_FUSED) the three-kernel sequence: sample scan, threshold kernel, main scan
+    static const bool no_fused = getenv("RDM_KNN_NO_FUSED") != nullptr;
+    int fused = no_fused ? 1 : knn_scan_tc_fused(h->db, h->inv, h->n, h->device, qp, cnt, k, h->qsplit, h->cand, h->cand_cnt, overflow, h->fused_ws, presplit, st);
+    if (fused < 0) return fused;
+    if (fused != RDM_OK) {
+        const long long ntiles = (h->n + 127) / 128;
+        int stride = (int)(ntiles / 512); if (stride > 16) stride = 16; if (stride < 1) stride = 1;       // >= ~64K sampled rows
+        const long long per_q = knn_tc_sample_rows(h->n, stride);
+        RDM_REQUIRE((size_t)per_q * cnt <= h->maxima_keys, RDM_ERR_STATE, "knn: sample buffer too small");
+        RDM_TRY(knn_scan_tc(h->db, h->inv, h->n, h->device, qp, cnt, h->qsplit, 1, stride, h->maxima, per_q, nullptr, nullptr, nullptr, st));
+        knn_threshold_kernel<<<dim3(cnt, THR_P), 1024, 0, st>>>(h->maxima, (size_t)per_q, h->thr_key, h->cand_cnt, overflow, h->thr_part, h->thr_done);
         RDM_COUNT_LAUNCH();
+        RDM_TRY(knn_scan_tc(h->db, h->inv, h->n, h->device, qp, cnt, h->qsplit, 0, 1, nullptr, 0, h->thr_key, h->cand, h->cand_cnt, st));
     }
-    RDM_CHECK_CUDA(cudaGetLastError());
+    RDM_TRY((launch_select<T, D, false>(h, cnt, h->cand, 0, MAX_QP, qp, k, idx_out, dist_out, sc_out, st)));
+    // device-side conditional fallback: ONE launch pair for all groups of 16 queries (blockIdx.y = group); normally two empty launches
+    int g2 = 0;
+    ScanArgs f{}; f.group_stride = 1; f.lists_out = h->lists; f.overflow = overflow; f.nq_total = cnt;
+    RDM_TRY((launch_scan<T, D, MAX_QP, R, SCAN_LOCKED>(h, qp, cnt, f, st, &g2, (cnt + MAX_QP - 1) / MAX_QP)));
+    RDM_TRY((launch_select<T, D, true>(h, cnt, h->lists, g2, MAX_QP, qp, k, idx_out, dist_out, sc_out, st)));
     return RDM_OK;
 }
 
@@ -816,13 +908,14 @@ int do_gather(rdm_knn* h, const long long* idx, long long count, float* out, cud
     KNN_DISPATCH(h, gather_typed, h, idx, count, out, st);
 }
 
-int normalize_rows(const float* q, int nq, int d, float* out, cudaStream_t st) {
+int normalize_rows(const float* q, int nq, int d, float* out, cudaStream_t st, __half* split = nullptr, int NQ = 0, unsigned* grid_bar = nullptr) {
     if (nq == 0) return RDM_OK;
+    const int grid = split && NQ > nq ? NQ : nq;
     switch (d) {
-        case 256: knn_normalize_kernel<256><<<nq, 64, 0, st>>>(q, nq, out); break;
-        case 512: knn_normalize_kernel<512><<<nq, 64, 0, st>>>(q, nq, out); break;
-        case 768: knn_normalize_kernel<768><<<nq, 64, 0, st>>>(q, nq, out); break;
-        case 1024: knn_normalize_kernel<1024><<<nq, 64, 0, st>>>(q, nq, out); break;
+        case 256: knn_normalize_kernel<256><<<grid, 64, 0, st>>>(q, nq, out, split, NQ, grid_bar); break;
+        case 512: knn_normalize_kernel<512><<<grid, 64, 0, st>>>(q, nq, out, split, NQ, grid_bar); break;
+        case 768: knn_normalize_kernel<768><<<grid, 64, 0, st>>>(q, nq, out, split, NQ, grid_bar); break;
+        case 1024: knn_normalize_kernel<1024><<<grid, 64, 0, st>>>(q, nq, out, split, NQ, grid_bar); break;
         default: rdm_set_error("knn normalize: unsupported d=%d", d); return RDM_ERR_UNSUPPORTED;
     }
     RDM_COUNT_LAUNCH();
@@ -860,16 +953,17 @@ int rdm_knn_create(rdm_knn_t** out, const void* db, int64_t n, int32_t d, int32_
         int tc_stride = (int)(tc_tiles / 512); if (tc_stride > 16) tc_stride = 16; if (tc_stride < 1) tc_stride = 1;
         const long long tc_per_q = (dtype == RDM_DTYPE_F16 && d == 512) ? knn_tc_sample_rows(n, tc_stride) : 0;
         if (cudaMalloc(&h->inv, (size_t)n * sizeof(float)) != cudaSuccess ||
-            cudaMalloc(&h->lists, (size_t)h->max_grid * MAX_QP * LIST * sizeof(u64)) != cudaSuccess ||
+            cudaMalloc(&h->lists, (size_t)(MAX_TCQ / MAX_QP) * h->max_grid * MAX_QP * LIST * sizeof(u64)) != cudaSuccess ||
             cudaMalloc(&h->maxima, (h->maxima_keys = std::max((size_t)h->max_grid * SCAN_THREADS * MAX_QP, (size_t)tc_per_q * MAX_TCQ)) * sizeof(u64)) != cudaSuccess ||
             cudaMalloc(&h->cand, (size_t)MAX_TCQ * CAND_CAP * sizeof(u64)) != cudaSuccess ||
             cudaMalloc(&h->thr_key, (size_t)MAX_TCQ * sizeof(u64)) != cudaSuccess ||
-            cudaMalloc(&h->cand_cnt, (size_t)(MAX_TCQ + 1) * sizeof(unsigned)) != cudaSuccess ||
+            cudaMalloc(&h->cand_cnt, (size_t)(2 * MAX_TCQ) * sizeof(unsigned)) != cudaSuccess ||
             cudaMalloc(&h->thr_part, (size_t)MAX_TCQ * THR_P * LIST * sizeof(u64)) != cudaSuccess ||
             cudaMalloc(&h->thr_done, (size_t)MAX_TCQ * sizeof(unsigned)) != cudaSuccess ||
             cudaMemset(h->thr_done, 0, (size_t)MAX_TCQ * sizeof(unsigned)) != cudaSuccess ||
             cudaMalloc(&h->qsplit, (size_t)knn_tc_queries_bytes()) != cudaSuccess ||
-            cudaMalloc(&h->qhat, (size_t)QHAT_ROWS * d * sizeof(float)) != cudaSuccess) {
+            cudaMalloc(&h->qhat, (size_t)QHAT_ROWS * d * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&h->fused_ws, knn_tc_fused_ws_bytes(device)) != cudaSuccess) {
             rdm_set_error("rdm_knn_create: workspace cudaMalloc failed"); rc = RDM_ERR_CUDA; break;
         }
         rc = do_create(h);
@@ -891,6 +985,7 @@ void rdm_knn_destroy(rdm_knn_t* h) {
     if (h->cand_cnt) cudaFree(h->cand_cnt);
     if (h->qsplit) cudaFree(h->qsplit);
     if (h->qhat) cudaFree(h->qhat);
+    if (h->fused_ws) cudaFree(h->fused_ws);
     if (h->thr_part) cudaFree(h->thr_part);
     if (h->thr_done) cudaFree(h->thr_done);
     delete h;
@@ -926,6 +1021,16 @@ int rdm_knn_search_raw(rdm_knn_t* h, const float* q_raw, int32_t nq, int32_t k, 
     RDM_REQUIRE(nq >= 0, RDM_ERR_ARG, "rdm_knn_search_raw: nq=%d", nq);
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool no_tc = getenv("RDM_KNN_NO_TC") != nullptr;
+    if (h->dtype == RDM_DTYPE_F16 && h->d == 512 && nq >= 3 && !no_tc) {
+        // tensor-core passes of <= 64 queries: ONE launch normalises the pass, writes its fp16 hi / lo rows and resets the scan's barrier
+        for (int q0 = 0; q0 < nq; q0 += MAX_TCQ) {
+            const int cnt = nq - q0 < MAX_TCQ ? nq - q0 : MAX_TCQ;
+            RDM_TRY(normalize_rows(q_raw + (size_t)q0 * 512, cnt, 512, h->qhat, st, (__half*)h->qsplit, knn_tc_pass_queries(cnt), knn_tc_fused_grid_bar(h->fused_ws, h->device)));
+            RDM_TRY((search_pass_tc<__half, 512>(h, h->qhat, cnt, k, (long long*)idx_out + (size_t)q0 * k, dist_out + (size_t)q0 * k, score_out ? score_out + (size_t)q0 * k : nullptr, st, 1)));
+        }
+        return RDM_OK;
+    }
     for (int q0 = 0; q0 < nq; q0 += QHAT_ROWS) {
         const int cnt = nq - q0 < QHAT_ROWS ? nq - q0 : QHAT_ROWS;
         RDM_TRY(normalize_rows(q_raw + (size_t)q0 * h->d, cnt, h->d, h->qhat, st));

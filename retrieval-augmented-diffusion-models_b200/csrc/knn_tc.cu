@@ -34,8 +34,9 @@ __device__ __forceinline__ float unorder_f32(uint32_t u) { return __uint_as_floa
 __device__ __forceinline__ u64 make_key(float s, uint32_t idx) { return ((u64)order_f32(s) << 32) | (u64)(0xffffffffu - idx); }
 
 // q fp32 [nq, 512] -> fp16 rows [0, NQ) = hi, [NQ, 2 NQ) = lo (zero rows beyond nq)
-__global__ void split_queries_kernel(const float* __restrict__ q, int nq, int NQ, __half* __restrict__ out) {
+__global__ void split_queries_kernel(const float* __restrict__ q, int nq, int NQ, __half* __restrict__ out, unsigned* __restrict__ grid_bar) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && grid_bar) *grid_bar = 0u;              // arrival counter of the fused scan's grid barrier (that kernel follows in stream order)
     if (i >= NQ * D) return;
     int qi = i / D, c = i % D;
     float v = qi < nq ? q[(size_t)qi * D + c] : 0.f;
@@ -190,6 +191,218 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
+
+// ---- ONE launch per search: sample phase -> grid barrier -> thresholds -> main scan ---------------------------------------------------------
+// The three-kernel sequence above (sample scan, threshold kernel, main scan) costs two extra launches, a second prologue and a 19 us
+// selection kernel around a 187 us scan of 1.28 M rows.  Here the persistent CTAs (one per SM, cooperative launch: all co-resident) first
+// run their own first `t_sample` tiles and keep, per TMEM lane quarter and query, the MAXIMUM score (an ordered u32) of the 32 * t_sample
+// rows that quarter saw: 4 * grid group maxima per query, each the score of a distinct real row.  After a grid-wide barrier every CTA
+// derives the thresholds redundantly: the k_eff-th largest group maximum per query (a warp-wide bisection over <= 19 values per lane with
+// redux.sync counts) is a VALID lower bound of the k_eff-th best score of the whole database (k_eff distinct rows reach it), relaxed by the
+// score slack like before.  The main phase then scans every tile (the sample tiles again: they are L2 hits) and appends the survivors.
+// Expected survivors per query ~ k_eff * n / (32 * t_sample * 4 * grid); the host sizes t_sample for ~512.
+constexpr int FUSED_MAXV = 20;                       // group maxima per lane in the threshold bisection: 4 * grid <= 32 * FUSED_MAXV
+constexpr float FUSED_SLACK = 3e-5f;                 // = SCORE_SLACK of knn.cu
+
+template <int NQ>
+__global__ void __launch_bounds__(THREADS, 1)
+knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ inv, long long n,
+                      int nq_valid, int k_eff, int t_sample, u64* __restrict__ cand, unsigned* __restrict__ cand_cnt, unsigned* __restrict__ overflow,
+                      uint32_t* __restrict__ gmax, unsigned* __restrict__ grid_bar) {
+    constexpr int NCOL = Cfg<NQ>::NCOL, B_KB_BYTES = Cfg<NQ>::B_KB_BYTES, B_BYTES = Cfg<NQ>::B_BYTES, STAGES = Cfg<NQ>::STAGES;
+    constexpr int NGRP = (NQ / 16 + EPI_PER_Q - 1) / EPI_PER_Q;          // 16-query groups per epilogue warp
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + B_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint64_t* b_full = tmem_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+    float* s_thr = reinterpret_cast<float*>(tmem_slot + 1);           // [NQ]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();                            // the select kernel (launched with programmatic serialisation) may be staged behind this grid
+    const long long ntiles = (n + TM - 1) / TM;
+    const long long my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;      // >= 1: grid <= ntiles
+    const long long ts = t_sample < my_tiles ? t_sample : my_tiles;                    // sample tiles of this CTA (its own first tiles)
+    const long long nseq = ts + my_tiles;                                              // tile sequence: sample tiles, then all tiles
+    auto tile_at = [&](long long p) { return (long long)blockIdx.x + (p < ts ? p : p - ts) * gridDim.x; };
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
+        mbar_init(b_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg<NQ>::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(b_full, B_BYTES);                          // the queries: loaded once, resident for the whole kernel
+            for (int kb = 0; kb < KB; kb++) tma_load_2d(sB + kb * B_KB_BYTES, &tmB, b_full, kb * TK, 0);
+            long long it = 0;
+            for (long long p = 0; p < nseq; p++) {
+                const long long tile = tile_at(p);
+                for (int kb = 0; kb < KB; kb++, it++) {
+                    const int s = (int)(it % STAGES); const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], A_BYTES);
+                    tma_load_2d(smem + s * A_BYTES, &tmA, &full[s], kb * TK, (int)(tile * TM));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(NCOL, /*f16=*/1);
+            mbar_wait(b_full, 0);
+            long long it = 0;
+            for (long long p = 0; p < nseq; p++) {
+                const int buf = (int)(p & 1);
+                mbar_wait(&tmem_empty[buf], (uint32_t)(((p >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * NCOL);
+                for (int kb = 0; kb < KB; kb++, it++) {
+                    const int s = (int)(it % STAGES); const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a = smem_u32(smem + s * A_BYTES), b = smem_u32(sB + kb * B_KB_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TK / 16; k++) umma_bf16(tmem_d, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc, (kb | k) != 0);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        const int q4 = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;   // the EPI_PER_Q warps of a lane quarter take the 16-query groups round-robin
+        uint32_t mx[NGRP][16];                                            // sample phase: running maximum (ordered score) per query of this lane's rows
+#pragma unroll
+        for (int g = 0; g < NGRP; g++)
+#pragma unroll
+            for (int j = 0; j < 16; j++) mx[g][j] = 0u;
+        for (long long p = 0; p < nseq; p++) {
+            if (p == ts) {
+                // ---- end of the sample phase: publish the group maxima, grid barrier, thresholds ------------------------------------------
+                const unsigned G4 = gridDim.x * 4u;
+#pragma unroll
+                for (int g = 0; g < NGRP; g++) {
+                    const int q0 = (half + g * EPI_PER_Q) * 16;
+                    if (q0 < NQ) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const uint32_t w = __reduce_max_sync(0xffffffffu, mx[g][j]);
+                            if (lane == 0 && q0 + j < nq_valid) gmax[(size_t)(q0 + j) * G4 + blockIdx.x * 4u + q4] = w;
+                        }
+                    }
+                }
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+                if (ew == 0 && lane == 0) {
+                    if (blockIdx.x == 0) {                                  // survivor counters of this search: zero before any CTA leaves the barrier
+                        for (int i = 0; i < NQ; i++) cand_cnt[i] = 0u;
+                        for (int i = 0; i < NQ; i++) overflow[i] = 0u;
+                        __threadfence();
+                    }
+                    atomicAdd(grid_bar, 1u);
+                    while (*(volatile unsigned*)grid_bar < gridDim.x) __nanosleep(32);
+                    __threadfence();
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+                // thresholds: CTA c answers queries c, c + grid, ... (one warp each): the k_eff-th largest of the 4 * grid group maxima by a
+                // warp-wide bisection over the ordered scores; a second grid barrier publishes them to every CTA
+                float* thr_out = reinterpret_cast<float*>(gmax + (size_t)64 * G4);
+                for (int qi = blockIdx.x + ew * gridDim.x; qi < nq_valid; qi += EPI_WARPS * gridDim.x) {
+                    uint32_t v[FUSED_MAXV];
+#pragma unroll
+                    for (int i = 0; i < FUSED_MAXV; i++) { const unsigned e = lane + 32u * i; v[i] = e < G4 ? __ldcg(gmax + (size_t)qi * G4 + e) : 0u; }
+                    uint32_t res = 0u;
+#pragma unroll 1
+                    for (int bit = 31; bit >= 0; bit--) {
+                        const uint32_t c = res | (1u << bit);
+                        unsigned cnt = 0;
+#pragma unroll
+                        for (int i = 0; i < FUSED_MAXV; i++) cnt += v[i] >= c ? 1u : 0u;
+                        cnt = __reduce_add_sync(0xffffffffu, cnt);
+                        if (cnt >= (unsigned)k_eff) res = c;
+                    }
+                    if (lane == 0) thr_out[qi] = res == 0u ? -CUDART_INF_F : unorder_f32(res) - FUSED_SLACK;      // fewer than k_eff sampled rows: keep everything
+                }
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+                if (ew == 0 && lane == 0) {
+                    atomicAdd(grid_bar, 1u);
+                    while (*(volatile unsigned*)grid_bar < 2u * gridDim.x) __nanosleep(32);
+                    __threadfence();
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+                for (int qi = ew * 32 + lane; qi < nq_valid; qi += EPI_WARPS * 32) s_thr[qi] = __ldcg(thr_out + qi);
+                asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+            }
+            const bool sample = p < ts;
+            const int buf = (int)(p & 1);
+            const long long row = tile_at(p) * TM + q4 * 32 + lane;
+            mbar_wait(&tmem_full[buf], (uint32_t)((p >> 1) & 1));
+            tc_fence_after();
+            const float iv = row < n ? __ldg(inv + row) : 0.f;
+            if (half * 16 >= NQ) {                                           // fewer groups than warps (16 queries): nothing to read, release at once
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+            }
+#pragma unroll
+            for (int g = 0; g < NGRP; g++) {
+                const int q0 = (half + g * EPI_PER_Q) * 16;
+                if (q0 >= NQ) continue;
+                uint32_t r[32];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                             : "r"(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NCOL + q0)));
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                             : "r"(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NCOL + NQ + q0)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (q0 + 16 * EPI_PER_Q >= NQ) {                                // this warp's last read of the accumulator: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+                }
+                if (row < n) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int qi = q0 + j;
+                        float s = (__uint_as_float(r[j]) + __uint_as_float(r[16 + j])) * iv;
+                        if (!(s == s)) s = -CUDART_INF_F;
+                        if (sample) {
+                            const uint32_t o = order_f32(s);
+                            mx[g][j] = o > mx[g][j] ? o : mx[g][j];
+                        } else if (qi < nq_valid && s >= s_thr[qi]) {
+                            const unsigned pos = atomicAdd(&cand_cnt[qi], 1u);
+                            if (pos < (unsigned)CAND_CAP) cand[(size_t)qi * CAND_CAP + pos] = make_key(s, (uint32_t)row);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg<NQ>::TMEM_COLS) : "memory");
+    }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -229,6 +442,29 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const float* inv, long 
     return RDM_OK;
 }
 
+
+template <int NQ>
+int launch_fused(const CUtensorMap& ta, const CUtensorMap& tb, const float* inv, long long n, int device, int nq_valid, int k_eff, int t_sample,
+                 u64* cand, unsigned* cand_cnt, unsigned* overflow, uint32_t* gmax, unsigned* grid_bar, int grid, cudaStream_t st) {
+    auto kern = knn_scan_fused_kernel<NQ>;
+    static int ok[16] = {0};                          // 0 unknown, 1 usable, -1 not (no cooperative launch / grid does not fit)
+    if (ok[device & 15] == 0) {
+        RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NQ>::SMEM_TOTAL));
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, Cfg<NQ>::SMEM_TOTAL);
+        ok[device & 15] = (coop && per_sm >= 1) ? 1 : -1;
+    }
+    if (ok[device & 15] < 0) return 1;                // caller falls back to the three-kernel path
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = Cfg<NQ>::SMEM_TOTAL; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;      // every CTA resident at once: the in-kernel grid barrier cannot deadlock
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    RDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, inv, n, nq_valid, k_eff, t_sample, cand, cand_cnt, overflow, gmax, grid_bar));
+    RDM_COUNT_LAUNCH();
+    return RDM_OK;
+}
 }  // namespace
 
 int knn_tc_queries_bytes() { return 2 * 64 * D * (int)sizeof(__half); }
@@ -240,7 +476,7 @@ int knn_scan_tc(const void* db_f16, const float* inv, long long n, int device, c
     RDM_REQUIRE(nq_valid >= 1 && nq_valid <= 64, RDM_ERR_ARG, "knn_scan_tc: %d queries", nq_valid);
     const int NQ = knn_tc_pass_queries(nq_valid);
     if (sample) {                                     // the sample pass runs first: it also prepares the fp16 hi/lo query rows
-        split_queries_kernel<<<(NQ * D + 255) / 256, 256, 0, st>>>(q, nq_valid, NQ, (__half*)qsplit_ws);
+        split_queries_kernel<<<(NQ * D + 255) / 256, 256, 0, st>>>(q, nq_valid, NQ, (__half*)qsplit_ws, nullptr);
         RDM_COUNT_LAUNCH();
     }
     CUtensorMap ta, tb;
@@ -252,4 +488,38 @@ int knn_scan_tc(const void* db_f16, const float* inv, long long n, int device, c
     if (NQ == 32) return KNN_TC_GO(32);
     return KNN_TC_GO(64);
 #undef KNN_TC_GO
+}
+
+// [64 queries][4 * grid] group maxima | [64] thresholds | grid-barrier counter
+size_t knn_tc_fused_ws_bytes(int device) { return (size_t)64 * 4 * rdm_num_sms(device) * sizeof(uint32_t) + 64 * sizeof(float) + 256; }
+unsigned* knn_tc_fused_grid_bar(void* fused_ws, int device) {
+    return reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(fused_ws) + (size_t)64 * 4 * rdm_num_sms(device) * sizeof(uint32_t) + 64 * sizeof(float));
+}
+
+// Returns RDM_OK, an error code, or 1 when the fused path is not usable here (database too small for a sample, no cooperative launch).
+int knn_scan_tc_fused(const void* db_f16, const float* inv, long long n, int device, const float* q, int nq_valid, int k, void* qsplit_ws,
+                      unsigned long long* cand, unsigned* cand_cnt, unsigned* overflow, void* fused_ws, int presplit, cudaStream_t st) {
+    RDM_REQUIRE(nq_valid >= 1 && nq_valid <= 64, RDM_ERR_ARG, "knn_scan_tc_fused: %d queries", nq_valid);
+    const int sms = rdm_num_sms(device);
+    const long long ntiles = (n + TM - 1) / TM;
+    if (ntiles < 4LL * sms || 4 * sms > 32 * FUSED_MAXV) return 1;          // a sample tile per CTA next to >= 3 more; the group maxima must fit the bisection registers
+    const int grid = sms;
+    const int NQ = knn_tc_pass_queries(nq_valid);
+    const int k_eff = k < 8 ? 8 : k;
+    // survivors per query ~ k_eff * n / (32 * t_sample * 4 * grid): aim at <= ~700, between 1 tile and 1/8 of a CTA's share
+    long long t_sample = (long long)((double)k_eff * (double)n / (32.0 * 4.0 * grid * 700.0)) + 1;
+    const long long cap = ntiles / grid / 8 > 1 ? ntiles / grid / 8 : 1;
+    if (t_sample > cap) t_sample = cap;
+    uint32_t* gmax = reinterpret_cast<uint32_t*>(fused_ws);
+    unsigned* grid_bar = knn_tc_fused_grid_bar(fused_ws, device);
+    if (!presplit) {                                   // (rdm_knn_search_raw: the normalisation kernel already wrote the fp16 hi / lo rows and reset the barrier)
+        split_queries_kernel<<<(NQ * D + 255) / 256, 256, 0, st>>>(q, nq_valid, NQ, (__half*)qsplit_ws, grid_bar);
+        RDM_COUNT_LAUNCH();
+    }
+    CUtensorMap ta, tb;
+    RDM_TRY(make_map(&ta, db_f16, n, TM));
+    RDM_TRY(make_map(&tb, qsplit_ws, 2 * NQ, 2 * NQ));
+    if (NQ == 16) return launch_fused<16>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, st);
+    if (NQ == 32) return launch_fused<32>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, st);
+    return launch_fused<64>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, st);
 }

@@ -8,3 +8,11 @@ long long knn_tc_sample_rows(long long n, int tile_stride);       // keys per qu
 // sample == 0: the main scan; survivors of thr_key go to cand / cand_cnt.  q: fp32 [nq_valid, 512] normalised queries (device).
 int knn_scan_tc(const void* db_f16, const float* inv, long long n, int device, const float* q, int nq_valid, void* qsplit_ws, int sample, int tile_stride,
                 unsigned long long* maxima, long long per_q, const unsigned long long* thr_key, unsigned long long* cand, unsigned* cand_cnt, cudaStream_t st);
+// ONE launch per search (plus the query split): sample phase, grid barrier, thresholds and main scan in a persistent cooperative kernel.
+// Resets cand_cnt / *overflow itself.  fused_ws: knn_tc_fused_ws_bytes(device) bytes of device memory owned by the searcher.
+// Returns RDM_OK, a negative error code, or 1 if this path cannot run here (small database / no cooperative launch): use knn_scan_tc then.
+size_t knn_tc_fused_ws_bytes(int device);
+// presplit != 0: qsplit_ws already holds the fp16 hi / lo rows of the queries and the barrier counter was reset (fused normalisation kernel).
+int knn_scan_tc_fused(const void* db_f16, const float* inv, long long n, int device, const float* q, int nq_valid, int k, void* qsplit_ws,
+                      unsigned long long* cand, unsigned* cand_cnt, unsigned* overflow, void* fused_ws, int presplit, cudaStream_t st);
+unsigned* knn_tc_fused_grid_bar(void* fused_ws, int device);

@@ -75,6 +75,11 @@ struct rdm_unet {
     cudaGraphExec_t dec_exec = nullptr; int dec_key[5] = {0, 0, 0, 0, -1}; unsigned long long dec_kernels = 0; float* dec_in = nullptr; float* dec_out = nullptr; size_t dec_io_cap = 0;
     // runtime
     Arena arena; double* stats = nullptr; size_t stats_cap = 0, stats_off = 0;
+    // batch chains: the B2 rows of a forward are split into `chains` sub-batches that run the whole layer sequence concurrently on their own
+    // streams (fork / join by events, also inside the captured graphs); every chain owns a slice of the arena and of the statistics buffer
+    int chains = getenv("RDM_CHAINS") ? atoi(getenv("RDM_CHAINS")) : 1; int plan_chains = 0;
+    size_t shared_bytes = 0, chain_bytes = 0, chain_stats = 0;
+    cudaStream_t side[8] = {nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[8] = {nullptr};
     float* ctx_kv = nullptr; size_t ctx_kv_floats = 0; std::vector<size_t> ctx_off; int ctx_B = 0, ctx_k = 0;
     long long* t_dev = nullptr; int t_cap = 0;
     int plan_B = 0, plan_H = 0, plan_W = 0;
@@ -256,7 +261,7 @@ void build_net(Net* n) {
 }
 
 // ---- forward ------------------------------------------------------------------------------------------
-struct Ctx { Net* n; cudaStream_t st; bool dry; int rc = RDM_OK; };
+struct Ctx { Net* n; cudaStream_t st; bool dry; int rc = RDM_OK; Arena* A = nullptr; size_t stats_off = 0; int b0 = 0; };     // A / stats_off / b0: this chain's arena, statistics slice and first batch row
 #define RUN(expr) do { if (!cx.dry && cx.rc == RDM_OK) cx.rc = (expr); } while (0)
 // Timing ablation (rdm_unet_set_ablation, tools/ablate_forward.py; env RDM_SKIP sets the initial value): a bit mask of kernel classes that are NOT launched (results are garbage; only the
 // change of the graph-replayed forward time is meaningful).  1 gn_stats, 2 gn_apply, 4 layernorm, 8 attention, 16 GEMM M>=8192, 32 GEMM M<8192.
@@ -278,15 +283,15 @@ inline int mode_f16(int m) { return (m == RDM_UNET_MODE_TC_FP16X2 || m == RDM_UN
 
 double* stats_alloc(Ctx& cx, int B, int groups) {
     Net* n = cx.n; size_t need = (size_t)B * groups * 2;
-    size_t o = n->stats_off; n->stats_off += need;
+    size_t o = cx.stats_off; cx.stats_off += need;
     return cx.dry ? (double*)nullptr + o : n->stats + o;
 }
-View fresh(Ctx& cx, int M, int C) { return View(cx.n->arena.allocf((size_t)M * C), C, C); }
+View fresh(Ctx& cx, int M, int C) { return View(cx.A->allocf((size_t)M * C), C, C); }
 Opnd fresh_opnd(Ctx& cx, int M, int C, bool tc) {
     Opnd o;
     if (!tc) { o.f = fresh(cx, M, C); return o; }
-    o.hi = (__nv_bfloat16*)cx.n->arena.alloc((size_t)M * C * 2);
-    if (mode_a_split(cx.n->mode)) o.lo = (__nv_bfloat16*)cx.n->arena.alloc((size_t)M * C * 2);
+    o.hi = (__nv_bfloat16*)cx.A->alloc((size_t)M * C * 2);
+    if (mode_a_split(cx.n->mode)) o.lo = (__nv_bfloat16*)cx.A->alloc((size_t)M * C * 2);
     o.ldb = C; o.f.C = C; o.f16 = mode_f16(cx.n->mode);
     return o;
 }
@@ -330,12 +335,12 @@ void gemm_any(Ctx& cx, const Opnd& a, int B, int H, int W, int C, int ks, int st
     }
     GemmA ga; ga.x = a.f.p; ga.ld = a.f.ld; ga.B = B; ga.Hs = H; ga.Ws = W; ga.Cin = C; ga.ksize = ks; ga.stride = stride; ga.ups = ups; ga.Ho = Ho; ga.Wo = Wo;
     if (out.tc()) {      // CUDA-core producer feeding a tensor-core consumer: fp32 temporary, then split
-        size_t mk = n->arena.mark();
+        size_t mk = cx.A->mark();
         View tmp = fresh(cx, M, Nout);
         e.out = tmp.p; e.out_ld = tmp.ld;
         RUN(gemm_simt(ga, w, N, e, cx.st));
         RUN(k_split_planes(tmp, M, out.out4(), cx.st));
-        n->arena.release(mk);
+        cx.A->release(mk);
     } else {
         e.out = out.f.p; e.out_ld = out.f.ld;
         RUN(gemm_simt(ga, w, N, e, cx.st));
@@ -355,7 +360,7 @@ void gn(Ctx& cx, const Act& x, const Norm& nm, float eps, int silu, const Opnd& 
 }
 
 void run_res(Ctx& cx, const ResW& r, const Act& x, const float* emb_all, View out) {
-    Arena& A = cx.n->arena; size_t mk = A.mark();
+    Arena& A = *cx.A; size_t mk = A.mark();
     const int M = x.M();
     const bool tc1 = tc_ok(cx, x.B, x.H, x.W, r.cin, 3), tc2 = tc_ok(cx, x.B, x.H, x.W, r.cout, 3);
     const bool tcs = r.has_skip && tc_ok(cx, x.B, x.H, x.W, r.cin, 1);
@@ -374,7 +379,7 @@ void run_res(Ctx& cx, const ResW& r, const Act& x, const float* emb_all, View ou
 }
 
 void run_st(Ctx& cx, const STW& s, const Act& x, View out) {
-    Net* n = cx.n; Arena& A = n->arena; size_t mk = A.mark();
+    Net* n = cx.n; Arena& A = *cx.A; size_t mk = A.mark();
     const int M = x.M(), C = s.C, N = x.H * x.W;
     const float scale = 0.17677669529663687f;                      // d_head ** -0.5 for d_head = 32 (attention.py:27)
     const bool tcp = tc_ok(cx, M, 1, 1, C, 1), tcf = tc_ok(cx, M, 1, 1, 4 * C, 1);
@@ -403,7 +408,7 @@ void run_st(Ctx& cx, const STW& s, const Act& x, View out) {
     { GemmEpi e; e.res = t0.p; e.res_ld = t0.ld; lin_any(cx, att, M, s.o1, e, from_view(t1)); }
     // cross-attention to the retrieved neighbours (attention.py:94); K/V were projected once in set_context
     RUN_UNLESS(4, k_layernorm(t1, M, s.ln2.g, s.ln2.b, 1e-5f, nrm.out4(), cx.st));
-    View kv(cx.dry ? nullptr : n->ctx_kv + n->ctx_off[s.id], 2 * C, 2 * C);
+    View kv(cx.dry ? nullptr : n->ctx_kv + n->ctx_off[s.id] + (size_t)cx.b0 * n->ctx_k * 2 * C, 2 * C, 2 * C);     // this chain's rows of the projected context
     if (tcp && n->ctx_k <= 8 && N >= 16 && !(n->skip & 64)) {
         // tensor-core engine: softmax(q k^T) v over the k retrieved neighbours runs in the epilogue of the to_q GEMM (one 32-column
         // accumulator chunk = one head's query), so neither q nor a separate attention launch exists
@@ -427,7 +432,7 @@ void run_st(Ctx& cx, const STW& s, const Act& x, View out) {
 }
 
 void run_down(Ctx& cx, const Conv& c, const Act& x, View out) {
-    Arena& A = cx.n->arena; size_t mk = A.mark();
+    Arena& A = *cx.A; size_t mk = A.mark();
     const int Ho = (x.H + 1) / 2, Wo = (x.W + 1) / 2, Mo = x.B * Ho * Wo;
     if (tc_ok(cx, Mo, 1, 1, 9 * c.cin, 1)) {
         Opnd col = fresh_opnd(cx, Mo, 9 * c.cin, true);
@@ -439,7 +444,7 @@ void run_down(Ctx& cx, const Conv& c, const Act& x, View out) {
     A.release(mk);
 }
 void run_up(Ctx& cx, const Conv& c, const Act& x, View out) {
-    Arena& A = cx.n->arena; size_t mk = A.mark();
+    Arena& A = *cx.A; size_t mk = A.mark();
     if (tc_ok(cx, x.B, 2 * x.H, 2 * x.W, c.cin, 3)) {
         Opnd up = fresh_opnd(cx, x.B * 4 * x.H * x.W, c.cin, true);
         RUN(k_upsample2x(x.v, x.B, x.H, x.W, up.out4(), cx.st));
@@ -491,13 +496,13 @@ Act run_block(Ctx& cx, const Block& b, Act x, const float* emb_all, View dst) {
     return x;
 }
 
-// x_nchw: [Bx, C, H, W] with Bx == B2 or B2/2 (then duplicated, ddim.py:233); t: int64 [B2] device; out NCHW [B2,...]
-int forward_impl(Net* n, const float* x_nchw, int Bx, const long long* t, int B2, int H, int W, float* out_nchw, cudaStream_t st, bool dry) {
-    Ctx cx{n, st, dry};
-    n->debug_block = 0; if (!dry) n->debug_log.clear();
-    Arena& A = n->arena; A.off = 0; A.dry = dry; n->stats_off = 0;
+// One chain: the whole layer sequence for batch rows [cx.b0, cx.b0 + nb) of the forward.  x_nchw / t / emb_all / out_nchw are the FULL-batch
+// buffers; this chain reads and writes only its rows.
+int chain_impl(Ctx& cx, const float* x_nchw, int Bx, const long long* t, int nb, int H, int W, View emb_all, float* out_nchw) {
+    Net* n = cx.n; Arena& A = *cx.A; cudaStream_t st = cx.st; const bool dry = cx.dry;
     const rdm_unet_cfg& c = n->cfg;
     const int nin = (int)n->in_blocks.size(), nout = (int)n->out_blocks.size();
+    const float* emb = dry ? emb_all.p : emb_all.p + (size_t)cx.b0 * emb_all.ld;
     std::vector<int> hH(nin), hW(nin);
     { int h = H, w = W; for (int i = 0; i < nin; i++) { if (n->in_blocks[i].layers[0].kind == L_DOWN) { h = (h + 1) / 2; w = (w + 1) / 2; } hH[i] = h; hW[i] = w; } }
     // concat buffers: output block j reads cat([h (ch_j), hs[nin-1-j] (ich_j)])
@@ -507,14 +512,55 @@ int forward_impl(Net* n, const float* x_nchw, int Bx, const long long* t, int B2
         for (int j = 0; j < nout; j++) {
             int i = nin - 1 - j, ich = n->skip_ch[i];
             cat_ch[j] = ch;
-            cat[j] = View(A.allocf((size_t)B2 * hH[i] * hW[i] * (ch + ich)), ch + ich, ch + ich);
+            cat[j] = View(A.allocf((size_t)nb * hH[i] * hW[i] * (ch + ich)), ch + ich, ch + ich);
             ch = n->out_blocks[j].cout;
         }
     }
+    View x0 = fresh(cx, nb * H * W, c.in_channels < 4 ? 4 : c.in_channels); x0.C = c.in_channels;
+    RUN(k_nchw_to_nhwc(x_nchw, Bx, nb, c.in_channels, H, W, x0, st, cx.b0));
+    Act h{x0, nb, H, W};
+    for (int i = 0; i < nin; i++) {
+        int j = nout - 1 - i;
+        h = run_block(cx, n->in_blocks[i], h, emb, cat[j].cols(cat_ch[j], n->skip_ch[i]));
+    }
+    h = run_block(cx, n->mid, h, emb, cat[0].cols(0, cat_ch[0]));
+    View last;
+    for (int j = 0; j < nout; j++) {
+        int i = nin - 1 - j;
+        Act in{cat[j], nb, hH[i], hW[i]};
+        View dst;
+        if (j + 1 < nout) dst = cat[j + 1].cols(0, cat_ch[j + 1]);
+        else { last = fresh(cx, nb * H * W, n->out_blocks[j].cout); dst = last; }
+        h = run_block(cx, n->out_blocks[j], in, emb, dst);
+    }
+    // out = conv3x3(SiLU(GN(h)))  (openaimodel.py:312-316,371)
+    Opnd a = fresh_opnd(cx, h.M(), h.v.C, tc_ok(cx, h.B, h.H, h.W, h.v.C, 3));
+    gn(cx, h, n->out_norm, 1e-5f, 1, a);
+    View o = fresh(cx, h.M(), 4); o.C = c.out_channels;
+    conv_any(cx, a, h, n->out_conv, GemmEpi(), from_view(o));
+    debug_view(cx, "out", 0, 0, o, h.M());
+    RUN(k_nhwc_to_nchw(o, nb, c.out_channels, H, W, dry ? out_nchw : out_nchw + (size_t)cx.b0 * c.out_channels * H * W, st));
+    return cx.rc;
+}
+
+int effective_chains(const Net* n, int B2) {
+    int g = n->chains < 1 ? 1 : n->chains > 8 ? 8 : n->chains;
+    if (n->debug || n->profile) g = 1;                  // per-layer dumps / per-GEMM event brackets follow ONE stream
+    return g < B2 ? g : B2;
+}
+
+// x_nchw: [Bx, C, H, W] with Bx == B2 or B2/2 (then duplicated, ddim.py:233); t: int64 [B2] device; out NCHW [B2,...]
+int forward_impl(Net* n, const float* x_nchw, int Bx, const long long* t, int B2, int H, int W, float* out_nchw, cudaStream_t st, bool dry) {
+    const int G = dry ? (n->plan_chains > 0 ? n->plan_chains : 1) : n->plan_chains;
+    Ctx cx{n, st, dry};
+    n->debug_block = 0; if (!dry) n->debug_log.clear();
+    Arena& A = n->arena; A.off = 0; A.dry = dry; n->stats_off = 0;
+    cx.A = &A;
+    const rdm_unet_cfg& c = n->cfg;
     if (!dry) RDM_CHECK_CUDA(cudaMemsetAsync(n->stats, 0, n->stats_cap * sizeof(double), st));
     // time embedding (openaimodel.py:352-353); only SiLU(emb) is ever consumed (ResBlock emb_layers = [SiLU, Linear]).
     // M = B2 rows: pure weight streaming (38 MB for the 25 concatenated emb_layers) -- on the tensor-core engine the weights arrive by
-    // TMA and split-K spreads them over all SMs; in fp32 mode the CUDA-core engine is used.
+    // TMA and split-K spreads them over all SMs; in fp32 mode the CUDA-core engine is used.  Shared by all chains (runs before the fork).
     View temb = fresh(cx, B2, c.model_channels), semb = fresh(cx, B2, n->ted), emb_all = fresh(cx, B2, n->emb_total);
     RUN(k_timestep_embedding(t, B2, c.model_channels, temb.p, st));
     {
@@ -528,31 +574,40 @@ int forward_impl(Net* n, const float* x_nchw, int Bx, const long long* t, int B2
         if (cx.n->debug && !dry) { if (se.tc()) { /* planes only: no fp32 copy to show */ } else semb = se.f; }
     }
     debug_view(cx, "temb", 0, 0, temb, B2); debug_view(cx, "emb_all", 0, 0, emb_all, B2);
-    View x0 = fresh(cx, B2 * H * W, c.in_channels < 4 ? 4 : c.in_channels); x0.C = c.in_channels;
-    RUN(k_nchw_to_nhwc(x_nchw, Bx, B2, c.in_channels, H, W, x0, st));
-    Act h{x0, B2, H, W};
-    for (int i = 0; i < nin; i++) {
-        int j = nout - 1 - i;
-        h = run_block(cx, n->in_blocks[i], h, emb_all.p, cat[j].cols(cat_ch[j], n->skip_ch[i]));
+    if (cx.rc != RDM_OK) return cx.rc;
+    if (dry) {
+        // plan: shared prologue, then the LARGEST chain (the first B2 % G chains carry one more row); every chain gets a slice of that size
+        n->shared_bytes = A.off;
+        const int nbmax = (B2 + G - 1) / G;
+        Arena ca; ca.dry = true;
+        Ctx cc{n, st, true}; cc.A = &ca;
+        RDM_TRY(chain_impl(cc, x_nchw, Bx, t, nbmax, H, W, emb_all, out_nchw));
+        n->chain_bytes = ca.peak; n->chain_stats = cc.stats_off;
+        A.peak = n->shared_bytes + (size_t)G * n->chain_bytes;
+        n->stats_off = (size_t)G * n->chain_stats;
+        return RDM_OK;
     }
-    h = run_block(cx, n->mid, h, emb_all.p, cat[0].cols(0, cat_ch[0]));
-    View last;
-    for (int j = 0; j < nout; j++) {
-        int i = nin - 1 - j;
-        Act in{cat[j], B2, hH[i], hW[i]};
-        View dst;
-        if (j + 1 < nout) dst = cat[j + 1].cols(0, cat_ch[j + 1]);
-        else { last = fresh(cx, B2 * H * W, n->out_blocks[j].cout); dst = last; }
-        h = run_block(cx, n->out_blocks[j], in, emb_all.p, dst);
+    // fork: chain 0 continues on `st`, chains 1.. run on their own streams behind an event (captured as graph branches)
+    if (G > 1) {
+        RDM_CHECK_CUDA(cudaEventRecord(n->ev_fork, st));
+        for (int g = 1; g < G; g++) RDM_CHECK_CUDA(cudaStreamWaitEvent(n->side[g], n->ev_fork, 0));
     }
-    // out = conv3x3(SiLU(GN(h)))  (openaimodel.py:312-316,371)
-    Opnd a = fresh_opnd(cx, h.M(), h.v.C, tc_ok(cx, h.B, h.H, h.W, h.v.C, 3));
-    gn(cx, h, n->out_norm, 1e-5f, 1, a);
-    View o = fresh(cx, h.M(), 4); o.C = c.out_channels;
-    conv_any(cx, a, h, n->out_conv, GemmEpi(), from_view(o));
-    debug_view(cx, "out", 0, 0, o, h.M());
-    RUN(k_nhwc_to_nchw(o, B2, c.out_channels, H, W, out_nchw, st));
-    return cx.rc;
+    int rc = RDM_OK;
+    for (int g = 0, b0 = 0; g < G; g++) {
+        const int nb = B2 / G + (g < B2 % G ? 1 : 0);
+        Arena ca; ca.dry = false; ca.base = A.base + n->shared_bytes + (size_t)g * n->chain_bytes; ca.cap = n->chain_bytes;
+        Ctx cc{n, g == 0 ? st : n->side[g], false}; cc.A = &ca; cc.stats_off = (size_t)g * n->chain_stats; cc.b0 = b0;
+        gemm_tc_set_workspace_slot(g);
+        const int r = chain_impl(cc, x_nchw, Bx, t, nb, H, W, emb_all, out_nchw);
+        if (r != RDM_OK && rc == RDM_OK) rc = r;          // keep issuing: the join below must still happen (an open capture has to be closed cleanly)
+        b0 += nb;
+    }
+    gemm_tc_set_workspace_slot(0);
+    for (int g = 1; g < G; g++) {
+        RDM_CHECK_CUDA(cudaEventRecord(n->ev_join[g], n->side[g]));
+        RDM_CHECK_CUDA(cudaStreamWaitEvent(st, n->ev_join[g], 0));
+    }
+    return rc;
 }
 
 // ---- first-stage VQ decoder -----------------------------------------------------------------------------------
@@ -615,7 +670,7 @@ void build_decoder(Net* n) {
 // One head of width C (512): both contractions are real GEMMs (4096 x 4096 x 512 per image at 64 x 64), so they run on the tcgen05 engine
 // per image with the K / V^T planes of that image as the "weight" operand; softmax and the V transpose are row / tile kernels in between.
 void run_dec_attn(Ctx& cx, const AttnW& a, const Act& x, View out) {
-    Net* n = cx.n; Arena& A = n->arena; size_t mk = A.mark();
+    Net* n = cx.n; Arena& A = *cx.A; size_t mk = A.mark();
     const int M = x.M(), C = a.C, HW = x.H * x.W;
     Opnd g = fresh_opnd(cx, M, C, true);
     gn(cx, x, a.norm, 1e-6f, 0, g);
@@ -645,6 +700,7 @@ void run_dec_attn(Ctx& cx, const AttnW& a, const Act& x, View out) {
 int dec_forward_impl(Net* n, const float* z_nchw, int B, int h, int w, int quantize, float* out_nchw, cudaStream_t st, bool dry) {
     Ctx cx{n, st, dry};
     Arena& A = n->arena; A.off = 0; A.dry = dry; n->stats_off = 0;
+    cx.A = &A;
     const rdm_vqdec_cfg& c = n->dcfg;
     if (!dry) RDM_CHECK_CUDA(cudaMemsetAsync(n->stats, 0, n->stats_cap * sizeof(double), st));
     // two ping-pong activation buffers sized for the largest layer output
@@ -702,6 +758,7 @@ int dec_forward_impl(Net* n, const float* z_nchw, int B, int h, int w, int quant
     View o = fresh(cx, x.M(), 4); o.C = c.out_ch;
     conv_any(cx, a, x, n->dec_conv_out, GemmEpi(), from_view(o));
     RUN(k_nhwc_to_nchw(o, B, c.out_ch, H, W, out_nchw, st));
+    n->stats_off = cx.stats_off;
     return cx.rc;
 }
 
@@ -716,7 +773,16 @@ int ensure_weight_planes(Net* n, cudaStream_t st) {
 }
 
 int ensure_plan(Net* n, int B2, int H, int W) {
-    if (n->plan_B == B2 && n->plan_H == H && n->plan_W == W && n->arena.base) return RDM_OK;
+    const int G = effective_chains(n, B2);
+    if (n->plan_B == B2 && n->plan_H == H && n->plan_W == W && n->plan_chains == G && n->arena.base) return RDM_OK;
+    if (G > 1 && !n->ev_fork) {
+        RDM_CHECK_CUDA(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming));
+        for (int g = 1; g < 8; g++) {
+            RDM_CHECK_CUDA(cudaStreamCreateWithFlags(&n->side[g], cudaStreamNonBlocking));
+            RDM_CHECK_CUDA(cudaEventCreateWithFlags(&n->ev_join[g], cudaEventDisableTiming));
+        }
+    }
+    n->plan_chains = G;
     n->arena.dry = true; n->arena.off = 0; n->arena.peak = 0; n->stats_off = 0;
     RDM_TRY(forward_impl(n, nullptr, B2, nullptr, B2, H, W, nullptr, 0, true));
     size_t need = n->arena.peak, sneed = n->stats_off;
@@ -840,6 +906,8 @@ void rdm_unet_destroy(rdm_unet_t* n) {
     if (n->t_in) cudaFree(n->t_in);
     if (n->step_dev) cudaFree(n->step_dev);
     if (n->cap_stream) cudaStreamDestroy(n->cap_stream);
+    if (n->ev_fork) cudaEventDestroy(n->ev_fork);
+    for (int g = 1; g < 8; g++) { if (n->side[g]) cudaStreamDestroy(n->side[g]); if (n->ev_join[g]) cudaEventDestroy(n->ev_join[g]); }
     if (n->dec_exec) cudaGraphExecDestroy(n->dec_exec);
     if (n->dec_in) cudaFree(n->dec_in);
     if (n->dec_out) cudaFree(n->dec_out);
@@ -913,7 +981,7 @@ int rdm_unet_set_context(rdm_unet_t* n, const float* ctx, int32_t B2, int32_t k,
         if (n->step_exec) { cudaGraphExecDestroy(n->step_exec); n->step_exec = nullptr; }
     }
     size_t off = 0;
-    Ctx cx{n, st, false};
+    Ctx cx{n, st, false}; cx.A = &n->arena;
     for (auto& s : n->sts) {
         n->ctx_off[s.id] = off;
         View dst(n->ctx_kv + off, 2 * s.C, 2 * s.C);
@@ -946,6 +1014,12 @@ int rdm_unet_forward(rdm_unet_t* n, const float* x, int32_t Bx, const int64_t* t
 }
 
 int rdm_unet_set_ablation(rdm_unet_t* n, int32_t mask) { RDM_REQUIRE(n, RDM_ERR_ARG, "rdm_unet_set_ablation: null handle"); n->skip = mask; return RDM_OK; }
+int rdm_unet_set_chains(rdm_unet_t* n, int32_t chains) {
+    RDM_REQUIRE(n, RDM_ERR_ARG, "rdm_unet_set_chains: null handle");
+    RDM_REQUIRE(chains >= 1 && chains <= 8, RDM_ERR_ARG, "rdm_unet_set_chains: %d outside 1..8", chains);
+    n->chains = chains;                 // takes effect at the next forward (ensure_plan re-plans and drops the captured graphs)
+    return RDM_OK;
+}
 int rdm_unet_set_graph(rdm_unet_t* n, int32_t on) { RDM_REQUIRE(n, RDM_ERR_ARG, "rdm_unet_set_graph: null handle"); n->use_graph = on; return RDM_OK; }
 
 int rdm_unet_profile_forward(rdm_unet_t* n, const float* x, int32_t Bx, const int64_t* t, int32_t B2, int32_t H, int32_t W, float* eps_out,
@@ -958,7 +1032,8 @@ int rdm_unet_profile_forward(rdm_unet_t* n, const float* x, int32_t Bx, const in
     DeviceGuard guard(n->device);
     // 2. the same forward captured into a graph with external event-record nodes around every GEMM: durations are those of the
     //    graph-replayed kernels (no host launch gaps inside the brackets).  Replayed twice; the second replay is the one measured.
-    n->profile = 2; n->prof_ev.clear(); n->prof_flops.clear(); n->prof_kind.clear(); n->prof_desc.clear(); n->prof_text.clear();
+    n->profile = 2; n->prof_ev.clear();
+    RDM_TRY(ensure_plan(n, B2, H, W));                 // per-GEMM brackets follow one stream: re-plan with a single chain (the next ordinary forward re-plans back) n->prof_flops.clear(); n->prof_kind.clear(); n->prof_desc.clear(); n->prof_text.clear();
     cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
     cudaGraphExec_t pexec = nullptr; unsigned long long nk = 0;
     int rc = capture_graph(n, &pexec, &nk, [&](cudaStream_t cs) {

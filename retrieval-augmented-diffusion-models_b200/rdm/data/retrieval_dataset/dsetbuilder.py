@@ -28,7 +28,7 @@ class DatasetBuilder(object):
                  patch_sampling='random', k=10, img_size=None, num_workers=None, max_pool_size=None, visualize=False, save=True,
                  saved_embeddings=None, trainset_size_partitioning=None, chunk_size=None, gpu=True, load_patch_dataset=True,
                  patch_dset_kwargs=None, searcher_savepath=None, timestamp_searcher_savepath=False, savepath_postfix=None,
-                 save_searcher=False, shard=False):
+                 save_searcher=False, shard=False, direct_to_hbm=False):
         assert metric == 'dot_product', "the reference configs search by dot product on normalised vectors"
         self.retriever_config = retriever_config
         self.retriever_name = retriever_config["target"].split('.')[-1] if retriever_config else "none"
@@ -46,11 +46,16 @@ class DatasetBuilder(object):
         self.data_pool = {'embedding': [], 'img_id': [], 'patch_coords': []}
         self.saved_embeddings = saved_embeddings
         self.shard = shard
+        # direct_to_hbm (not a reference key): the embedding rows go from the .npz parts straight into the searcher's device buffer through
+        # pinned staging chunks (rdm_b200.db_loader.load_rows_to_device) -- no host concatenation, no host copy of the rows at all;
+        # data_pool['embedding'] is then a DeviceRows view (len / shape / fancy indexing by device gather)
+        self.direct_to_hbm = bool(direct_to_hbm)
+        self.load_stats = None
         self._row_base, self._n_total = None, None   # set when only this rank's rows of a sharded database were read
-        if self.saved_embeddings:
-            self.load_embeddings()
         self.searcher = None
         self.searcher_savedir = searcher_savepath
+        if self.saved_embeddings:
+            self.load_embeddings()
 
     @property
     def num_rows(self):
@@ -102,6 +107,8 @@ class DatasetBuilder(object):
         if len(self.data_pool['embedding']) > 0:
             return
         print(f'Load saved patch embedding from "{self.saved_embeddings}"')
+        if self.direct_to_hbm and (os.path.isfile(self.saved_embeddings) or os.path.isdir(self.saved_embeddings)):
+            return self._load_direct()
         if self._dist_world() > 1 and (os.path.isfile(self.saved_embeddings) or os.path.isdir(self.saved_embeddings)):
             # row-sharded database: this rank reads only the parts that overlap the rows it will own; the small
             # id / coordinate arrays stay complete on every rank because search results index them globally (dsetbuilder.py:494-495)
@@ -129,6 +136,25 @@ class DatasetBuilder(object):
         else:
             raise ValueError(f'Embeddings string "{self.saved_embeddings}" nor directory neither file --> check this.')
         print(f'Finished loading of retrieval database of length {self.data_pool["embedding"].shape[0]}.')
+
+    def _load_direct(self):
+        """f-3: this rank's rows (all rows without sharding) from disk to HBM in pinned-staged chunks; the searcher is ready afterwards."""
+        n_total = sum(db_loader.part_row_counts(db_loader.list_parts(self.saved_embeddings)))
+        w = self._dist_world()
+        r = torch.distributed.get_rank() if w > 1 else 0
+        lo, hi = shard_range(n_total, r, w)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        rows, self.load_stats = db_loader.load_rows_to_device(self.saved_embeddings, lo, hi, dev)
+        local = B200Searcher(rows, device=dev, idx_base=lo)
+        self.searcher = ShardedSearcher(local) if w > 1 else local
+        meta = db_loader.load_rows(self.saved_embeddings, 0, n_total, keys=('img_id', 'patch_coords'))
+        self.data_pool = {'embedding': db_loader.DeviceRows(self.searcher, n_total, rows.shape[1], str(rows.dtype).split('.')[-1])}
+        self.data_pool.update({k: meta[k] for k in ('img_id', 'patch_coords') if k in meta})
+        self._row_base, self._n_total = (lo if w > 1 else None), n_total
+        if self.max_pool_size is None or n_total >= self.max_pool_size:
+            self.max_pool_size = n_total
+        s = self.load_stats
+        print(f'Rows [{lo}, {hi}) of {n_total} straight to {dev}: {s["bytes"] / 1e9:.2f} GB in {s["seconds"]:.2f} s ({s["gb_per_s"]:.2f} GB/s)')
 
     def _dist_world(self):
         """World size when the database is to be row-sharded (`shard=True` under an initialised torch.distributed), else 1."""

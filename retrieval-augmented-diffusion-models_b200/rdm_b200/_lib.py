@@ -42,6 +42,7 @@ SIGNATURES = {
     "rdm_unet_set_context": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "rdm_unet_forward": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "rdm_unet_set_graph": (c_int, [c_void_p, c_int32]),
+    "rdm_unet_set_chains": (c_int, [c_void_p, c_int32]),
     "rdm_unet_set_ablation": (c_int, [c_void_p, c_int32]),
     "rdm_unet_profile_forward": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "rdm_unet_profile_text": (c_char_p, [c_void_p]),

@@ -188,6 +188,10 @@ class B200UNet:
     def set_graph(self, on):
         _lib.check(_lib.lib().rdm_unet_set_graph(self._h, 1 if on else 0), "rdm_unet_set_graph")
 
+    def set_chains(self, chains):
+        """Concurrent batch chains (rdm_unet_set_chains): 1..8 sub-batches of a forward run the layer sequence on their own streams."""
+        _lib.check(_lib.lib().rdm_unet_set_chains(self._h, int(chains)), "rdm_unet_set_chains")
+
     def set_ablation(self, mask):
         """Measurement aid (rdm_unet_set_ablation): bit mask of kernel classes that the following forwards do NOT launch."""
         _lib.check(_lib.lib().rdm_unet_set_ablation(self._h, int(mask)), "rdm_unet_set_ablation")

@@ -73,6 +73,11 @@ cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t st = null
 typedef struct EmuEvent* cudaEvent_t;
 enum { cudaEventRecordDefault = 0, cudaEventRecordExternal = 1 };
 cudaError_t cudaEventCreate(cudaEvent_t* e);
+enum { cudaEventDefault = 0, cudaEventDisableTiming = 2 };
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned flags);
+// launches execute synchronously in issue order under emulation (and a capture records them in that order), which satisfies every
+// cross-stream dependency an event wait can express
+cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t e, unsigned flags = 0);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = nullptr);
 cudaError_t cudaEventRecordWithFlags(cudaEvent_t e, cudaStream_t st, unsigned flags);

@@ -6,6 +6,7 @@ int gemm_tc(const TcA&, const TcW&, const GemmEpi&, __nv_bfloat16*, __nv_bfloat1
     rdm_set_error("emulation: the tcgen05 GEMM engine is not available on the host (use RDM_UNET_MODE_FP32)");
     return RDM_ERR_UNSUPPORTED;
 }
+void gemm_tc_set_workspace_slot(int) {}
 bool k_attention_mma_supported(int, int) { return false; }
 int k_attention_mma(const __half*, const __half*, const __half*, int, int, int, int, int, float, Out4, cudaStream_t) {
     rdm_set_error("emulation: the warp-MMA attention kernel is not available on the host");
@@ -19,6 +20,12 @@ int knn_tc_pass_queries(int) { return 16; }
 long long knn_tc_sample_rows(long long, int) { return 0; }
 int knn_scan_tc(const void*, const float*, long long, int, const float*, int, void*, int, int, unsigned long long*, long long, const unsigned long long*, unsigned long long*,
                 unsigned*, cudaStream_t) {
+    rdm_set_error("emulation: the tcgen05 kNN scan is not available on the host (set RDM_KNN_NO_TC=1)");
+    return RDM_ERR_UNSUPPORTED;
+}
+size_t knn_tc_fused_ws_bytes(int) { return 256; }
+unsigned* knn_tc_fused_grid_bar(void*, int) { return nullptr; }
+int knn_scan_tc_fused(const void*, const float*, long long, int, const float*, int, int, void*, unsigned long long*, unsigned*, unsigned*, void*, int, cudaStream_t) {
     rdm_set_error("emulation: the tcgen05 kNN scan is not available on the host (set RDM_KNN_NO_TC=1)");
     return RDM_ERR_UNSUPPORTED;
 }

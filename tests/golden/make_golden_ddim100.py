@@ -7,6 +7,7 @@ ref_unet_tiny.npz / ref_ddim_tiny.npz):
                      batch 16 (= bench.BATCH), seeds 0..NSEEDS-1: final latents [NSEEDS, 16, 4, 32, 32]
   rshape_imagenet.npz  R: models/rdm/imagenet/config.yaml:14-59 (64x64x3 latent, in_channels 3), weights randomize_(seed 3):
                      one forward at B2 = 2 and DDIM-20 (CFG 2.0) of one image
+  rshape_imagenet_ddim100.npz  the same model, DDIM-100 (CFG 2.0) of two images
 
 Inputs are regenerated from seeds by `inputs_cfg2` / `inputs_rshape` below (the GPU tests import them), only the oracle's outputs are stored.
     python tests/golden/make_golden_ddim100.py [cfg2|rshape|all] [nseeds]
@@ -42,6 +43,13 @@ def inputs_rshape():
     return x, t, c, x_T, cond, torch.zeros_like(cond)
 
 
+def inputs_rshape100():
+    g = torch.Generator().manual_seed(78)
+    x_T = torch.randn(2, 3, 64, 64, generator=g)
+    cond = torch.randn(2, 4, 512, generator=g) * 3
+    return x_T, cond, torch.zeros_like(cond)
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     nseeds = int(sys.argv[2]) if len(sys.argv) > 2 else NSEEDS
@@ -57,6 +65,14 @@ def main():
         lat = oddim.ddim_sample(ref, x_T, cond, unc, S=20, scale=SCALE)
         np.savez(os.path.join(HERE, "rshape_imagenet.npz"), forward=fwd.numpy(), ddim20=lat.numpy())
         print(f"rshape: {time.time() - t0:.1f}s", flush=True)
+    if what in ("rshape100", "all"):
+        # the shipped shape at the headline step count: DDIM-100, CFG 2.0, two images (inputs_rshape100)
+        ref = ounet.randomize_(ounet.UNetModel(**ounet.IMAGENET_UNET), 3).eval()
+        x_T, cond, unc = inputs_rshape100()
+        t0 = time.time()
+        lat = oddim.ddim_sample(ref, x_T, cond, unc, S=S_DDIM, scale=SCALE)
+        np.savez(os.path.join(HERE, "rshape_imagenet_ddim100.npz"), ddim100=lat.numpy())
+        print(f"rshape100: {time.time() - t0:.1f}s", flush=True)
     if what in ("cfg2", "all"):
         ref = ounet.UNetModel(**bench.UNET).eval()
         ref.load_state_dict(bench.make_weights())

@@ -75,3 +75,34 @@ def test_dataset_builder_reads_only_its_shard(tmp_path, monkeypatch, rank):
     # without shard=True every rank keeps the reference behaviour: the whole database
     b = DatasetBuilder(retriever_config=None, saved_embeddings=str(tmp_path), load_patch_dataset=False, gpu=False, shard=False)
     assert b._row_base is None and np.array_equal(b.data_pool["embedding"], full["embedding"])
+
+
+@pytest.mark.parametrize("compressed", [False, True])
+def test_members_are_memory_mapped_when_stored(tmp_path, compressed):
+    """open_member: np.savez parts (stored) come back as read-only memmaps over the payload inside the zip -- no copy until rows are sliced --
+    and compressed parts as ordinary arrays; both equal the saved data."""
+    rng = np.random.default_rng(3)
+    emb = rng.standard_normal((37, 8)).astype(np.float16)
+    ids = np.arange(37)
+    (np.savez_compressed if compressed else np.savez)(tmp_path / "p.npz", embedding=emb, img_id=ids)
+    got = db_loader.open_member(str(tmp_path / "p.npz"), "embedding")
+    assert isinstance(got, np.memmap) != compressed
+    assert got.dtype == np.float16 and np.array_equal(np.asarray(got), emb)
+    assert np.array_equal(np.asarray(db_loader.open_member(str(tmp_path / "p.npz"), "img_id")), ids)
+
+
+def test_device_rows_view_indexes_like_the_host_array():
+    class FakeSearcher:
+        device = "cpu"
+
+        def __init__(self, rows):
+            self.rows = rows
+
+        def gather_device(self, idx):
+            import torch
+            return torch.from_numpy(self.rows[idx.numpy()].astype(np.float32))
+    rows = np.random.default_rng(0).standard_normal((20, 8)).astype(np.float16)
+    v = db_loader.DeviceRows(FakeSearcher(rows), 20, 8, "float16")
+    assert len(v) == 20 and v.shape == (20, 8) and v.dtype == np.float16
+    nns = np.array([[3, 4], [19, 0]])
+    assert np.array_equal(v[nns], rows[nns].astype(np.float32)) and v[nns].shape == (2, 2, 8)

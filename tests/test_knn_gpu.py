@@ -116,3 +116,22 @@ def test_bad_arguments_fail_loudly(cuda):
         s.search_device(torch.zeros(1, 512, device=cuda), 25)          # k > RDM_KNN_MAX_K
     with pytest.raises(RuntimeError):
         B200Searcher(np.zeros((10, 100), np.float32), device=cuda)     # unsupported row width
+
+
+@pytest.mark.parametrize("d", [256, 512, 768, 1024])
+def test_query_normalisation_inside_the_library_is_bit_identical_to_numpy(cuda, d):
+    """rdm_knn_normalize / rdm_knn_search_raw: the reference's `q / np.linalg.norm(q, axis=1)[:, np.newaxis]` (ddpm.py:907) on the device."""
+    from rdm_b200.knn import B200Searcher, normalize_device
+    rng = np.random.default_rng(d)
+    q = (rng.standard_normal((19, d)) * rng.uniform(0.01, 30.0, size=(19, 1))).astype(np.float32)
+    want = q / np.linalg.norm(q, axis=1)[:, np.newaxis]
+    got = normalize_device(torch.from_numpy(q).to(cuda)).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(oknn.normalize_queries_restated(q).view(np.uint32), want.view(np.uint32))
+    db = _db(20_000, d, np.float16, seed=d + 1)
+    s = B200Searcher(db, device=cuda)
+    a = s.search_raw_device(torch.from_numpy(q).to(cuda), 6, return_scores=True)
+    b = s.search_device(torch.from_numpy(want).to(cuda), 6, return_scores=True)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    ri, _, rs = oknn.search(db, want, 6, return_scores=True)
+    assert np.array_equal(a[0].cpu().numpy(), ri) and np.array_equal(a[2].cpu().numpy().view(np.uint64), rs.view(np.uint64))

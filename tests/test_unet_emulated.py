@@ -155,3 +155,28 @@ def test_batch_growth_with_smaller_images_does_not_overrun_the_timestep_buffer(e
             want = ref(x, t, c)
         net.set_context(c)
         assert rel(net.forward(x, t), want) < 1e-5
+
+
+@pytest.mark.parametrize("chains", [2, 3])
+def test_batch_chains_partition_is_invisible(emulated, chains):
+    """rdm_unet_set_chains under emulation: the host-side partition (arena slices with guard zones, statistics slices, context / time-embedding /
+    input / output row offsets, CFG doubling across the chain boundary) gives the single-chain result; the streams run in issue order here,
+    the concurrency itself is covered by tests/test_unet_gpu.py::test_batch_chains_do_not_change_the_result."""
+    from rdm_b200 import sampler
+    ref, net = _pair(5)
+    g = torch.Generator().manual_seed(9)
+    B = 3
+    x_T = torch.randn(B, 4, 8, 8, generator=g)
+    c, uc = torch.randn(B, 2, 512, generator=g) * 2, torch.zeros(B, 2, 512)
+    t = torch.tensor([501, 12, 700, 3, 999, 250])
+    with torch.no_grad():
+        want_f = ref(torch.cat([x_T] * 2), t, torch.cat([c, uc]))
+    want = oddim.ddim_sample(ref, x_T, c, uc, S=4, scale=2.0)
+    tb = sampler.make_ddim_tables(sampler.alphas_cumprod_linear(), 4, 0.0, device="cpu")
+    net.set_chains(chains)
+    net.set_context(torch.cat([c, uc]))
+    assert rel(net.forward(x_T, t), want_f) < 1e-5            # eager + capture
+    assert rel(net.forward(x_T, t), want_f) < 1e-5            # replay
+    assert rel(net.ddim_sample(x_T, tb["timesteps"], tb["coef"], cfg_scale=2.0), want) < 1e-5
+    net.set_chains(1)
+    assert rel(net.forward(x_T, t), want_f) < 1e-5

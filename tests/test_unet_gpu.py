@@ -195,3 +195,34 @@ def test_full_arch_ddim20_tensor_core(cuda, mode, tol):
     err = rel_l2(got, want)
     print(f"full-arch DDIM-20 mode {mode}: rel-L2 {err:.3e}")
     assert err < tol
+
+
+@pytest.mark.parametrize("mode,tol", [(0, 1e-5), (3, 3e-3)])
+@pytest.mark.parametrize("chains", [2, 3, 8])
+def test_batch_chains_do_not_change_the_result(cuda, mode, tol, chains):
+    """rdm_unet_set_chains: sub-batches of a forward run concurrently on their own streams (graph branches).  GroupNorm / LayerNorm /
+    attention are per sample, so the split is invisible: forward and the fused DDIM loop agree with the single-chain run (to the
+    summation-order noise of atomics / split-K) and with the oracle, for batch sizes that do not divide evenly and for CFG doubling."""
+    ref, net = _pair(ounet.TINY_UNET, 5, cuda)
+    net.set_mode(mode)
+    g = torch.Generator().manual_seed(77)
+    B = 5
+    x_T = torch.randn(B, 4, 16, 16, generator=g)
+    cond, unc = torch.randn(B, 4, 512, generator=g) * 3, torch.zeros(B, 4, 512)
+    t = torch.randint(0, 1000, (2 * B,), generator=g)
+    with torch.no_grad():
+        want_f = ref(torch.cat([x_T] * 2), t, torch.cat([cond, unc]))
+    want = oddim.ddim_sample(ref, x_T, cond, unc, S=5, scale=2.0)
+    tb = _tables(5, cuda)
+    outs = []
+    for ch in (1, chains):
+        net.set_chains(ch)
+        net.set_context(torch.cat([cond, unc]).to(cuda))
+        f = net.forward(x_T.to(cuda), t.to(cuda))              # Bx = B2 / 2: chains cross the cond / uncond boundary
+        f2 = net.forward(x_T.to(cuda), t.to(cuda))             # graph replay
+        d = net.ddim_sample(x_T.to(cuda), tb["timesteps"], tb["coef"], cfg_scale=2.0)
+        assert rel_l2(f, want_f) < tol and rel_l2(f2, f) < 1e-5 and rel_l2(d, want) < max(tol, 1e-3)
+        outs.append((f, d))
+    assert rel_l2(outs[1][0], outs[0][0]) < (1e-5 if mode == 0 else 1e-3)
+    assert rel_l2(outs[1][1], outs[0][1]) < (1e-5 if mode == 0 else 2e-3)
+    net.set_chains(1)

@@ -95,6 +95,23 @@ def test_reference_shape_ddim20(cuda, rshape, mode, tol):
     assert err < tol
 
 
+@pytest.mark.parametrize("mode,tol", [(4, 1e-3), (3, 1e-3)])
+def test_reference_shape_ddim100(cuda, rshape, mode, tol):
+    """The shipped shape at the headline step count (DDIM-100, CFG 2.0, two images) in the default single-MMA fp16 mode and in fp16x2."""
+    import make_golden_ddim100 as gen
+    from rdm_b200 import sampler
+    net, _ = rshape
+    want = torch.from_numpy(np.load(os.path.join(GOLD, "rshape_imagenet_ddim100.npz"))["ddim100"])
+    x_T, cond, unc = gen.inputs_rshape100()
+    net.set_mode(mode)
+    tb = sampler.make_ddim_tables(sampler.alphas_cumprod_linear(), gen.S_DDIM, 0.0, device=cuda)
+    net.set_context(torch.cat([cond, unc]).to(cuda))
+    got = net.ddim_sample(x_T.to(cuda), tb["timesteps"], tb["coef"], cfg_scale=gen.SCALE)
+    err = rel_l2(got, want)
+    print(f"R-shape DDIM-100 mode {mode}: rel-L2 {err:.2e}")
+    assert err < tol
+
+
 # ---------------------------------------------------------------------------------------------------------------- kNN at BASELINE sizes
 def _bits(a):
     return np.ascontiguousarray(a).view(np.int64)

@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """Stage-by-stage measurements of BASELINE.json configs 3 and 4 -- the configurations next to the headline cfg2 that
-bench.py reports.  Synthetic data, random-init weights of the named architectures.  One JSON line (rank 0).  NOT YET RUN: written after the
-round's GPU budget was spent; every call goes through wrappers that the GPU tests already exercise.
+bench.py reports.  Synthetic data, random-init weights of the named architectures.  One JSON line (rank 0); results under profiles/.
 
   cfg 3  text2img:  synthetic prompts -> CLIP ViT-B/32 text tower -> exact kNN (k=4) over a 20,927,907 x 512 fp16 database row-sharded over
          the ranks (all_gather + merge) -> context = [query | 3 neighbours] -> DDIM-250 with guidance 2.0, batch 64 sharded by image.
@@ -72,7 +71,7 @@ def main():
     ap.add_argument("--rows", type=int, default=20_927_907)
     ap.add_argument("--batch", type=int, default=None, help="GLOBAL batch (default 64 for cfg 3, 32 for cfg 4)")
     ap.add_argument("--steps", type=int, default=None, help="DDIM steps (default 250 / 100)")
-    ap.add_argument("--mode", default="fp16x2")
+    ap.add_argument("--mode", default=bench.DEFAULT_MODE)
     a = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local)
@@ -95,7 +94,7 @@ def main():
     lo, hi = shard_range(a.rows, rank, world)
     db = synthetic_db(a.rows, lo, hi, dev)
     local_s = B200Searcher(db, device=dev, idx_base=lo)
-    searcher = ShardedSearcher(local_s) if world > 1 else local_s
+    searcher = ShardedSearcher(local_s, validate=False) if world > 1 else local_s
     net = B200UNet(dev, **bench.UNET)
     net.load_state_dict(bench.make_weights())
     net.set_mode(modes[a.mode])
@@ -110,13 +109,11 @@ def main():
         dist.barrier()
     t0 = time.time()
     if a.cfg == 3:
-        tok_all = synthetic_prompts(B_glob).to(dev)                              # every rank encodes all prompts: the sharded search needs the same queries everywhere
-        q = T.run("clip_text", lambda: clip.encode_text(tok_all).float())
-        qh = (q / q.norm(dim=1, keepdim=True)).contiguous()
-        nns, _ = T.run("knn", lambda: searcher.search_device(qh, k))
-        rows = T.run("gather", lambda: searcher.gather_device(nns))
-        mine = slice(rank * B, (rank + 1) * B)
-        cond = torch.cat([q[mine, None], rows[mine, :k - 1]], dim=1)            # the query itself is neighbour 0 (ddpm.py:775)
+        tok = synthetic_prompts(B_glob)[rank * B:(rank + 1) * B].to(dev)          # every rank encodes ITS prompts; the sharded searcher exchanges the query rows
+        q = T.run("clip_text", lambda: clip.encode_text(tok).float())
+        nns, _ = T.run("knn", lambda: searcher.search_raw_device(q, k))          # q / ||q|| inside the library (ddpm.py:907), all_gather / all_to_all when sharded
+        rows = T.run("gather", lambda: searcher.gather_device(nns))              # neighbour rows from their owner ranks
+        cond = torch.cat([q[:, None], rows[:, :k - 1]], dim=1)                   # the query itself is neighbour 0 (ddpm.py:775)
         T.run("kv_projection", lambda: net.set_context(torch.cat([cond, torch.zeros_like(cond)])))
         x = T.run("ddim", lambda: net.ddim_sample(x_T, tb["timesteps"], tb["coef"], cfg_scale=2.0))
     else:
@@ -131,16 +128,8 @@ def main():
             x, p0 = T.run("unet_step", lambda: net.ddim_sample(x, tb["timesteps"], tb["coef"], cfg_scale=2.0, first_step=i, num_steps=1, want_pred_x0=True))
             img = T.run("vq_decode", lambda: dec.decode(p0, force_not_quantize=True))
             q = T.run("clip_image", lambda: clip.encode_image(clip.preprocess(img)).float())
-            qh = (q / q.norm(dim=1, keepdim=True)).contiguous()
-            if world > 1:                                                        # the sharded search needs the same queries on every rank
-                allq = [torch.empty_like(qh) for _ in range(world)]
-                T.run("query_all_gather", lambda: dist.all_gather(allq, qh))
-                qh_all = torch.cat(allq)
-            else:
-                qh_all = qh
-            nns, _ = T.run("knn", lambda: searcher.search_device(qh_all, k))
-            rows = T.run("gather", lambda: searcher.gather_device(nns))
-            cond = rows[rank * B:(rank + 1) * B]
+            nns, _ = T.run("knn", lambda: searcher.search_raw_device(q, k))      # per-rank queries; exchange inside the sharded searcher
+            cond = T.run("gather", lambda: searcher.gather_device(nns))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -151,7 +140,7 @@ def main():
     if rank == 0:
         pk = bench.peaks()
         knn_calls = 1 if a.cfg == 3 else S
-        nq = B_glob
+        nq = B_glob                                                             # queries every shard scans per search (the union of all ranks' queries)
         knn_ms = T.ms["knn"] / knn_calls
         print(json.dumps({"config": f"BASELINE cfg{a.cfg}", "n_gpus": world, "global_batch": B_glob, "ddim_steps": S, "k_nn": k, "db_rows": a.rows,
                           "unet_mode": a.mode, "images_per_s": B_glob / float(t), "wall_s": float(t), "setup_s": setup_s,
