@@ -36,8 +36,20 @@ __shared__ long long g_ts[24];
 constexpr int BM = 128, BK = 64, EPI_WARPS = 8, EPI_WARP0 = 4, TC_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // warpgroup 0: warp 0 TMA, warp 1 MMA, warps 2-3 idle; warpgroups 1-2: epilogue
 
 // ---- PTX wrappers (mbarrier / TMA helpers live in ptx.cuh) -----------------------------------------------
-// exact-erf GELU (F.gelu default, ldm FeedForward GEGLU).  (A two-MUFU Abramowitz-Stegun erf was measured SLOWER than erff's FMA-only polynomial here.)
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// erf-form GELU (F.gelu default, ldm FeedForward GEGLU): GELU(x) = x * Phi(x) = max(x, 0) - a * Q(a), a = |x|, with the normal tail
+// Q(a) = erfc(a / sqrt 2) / 2 evaluated as 2^-(a p(a) + 1): p is a degree-5 fit of -log2(erfc(a / sqrt 2)) / a on [0, 6] (tools/fit_gelu.py,
+// weighted for the absolute error of a Q(a); Q(6) = 1e-9, so a is clamped there).  Branch-free, ONE MUFU.EX2 + 9 FMA-class instructions
+// against ~35 for erff with its two divergent ranges -- ncu's source view had erff and the fp16 conversions at half of the GEGLU kernel's
+// issue slots.  Max |error| vs the fp64 erf form: 1.2e-7 absolute (1.2e-6 relative above 0.01), i.e. the rounding level of erff itself.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float a = fminf(fabsf(x), 6.f);
+    float q = -2.992859299411066e-05f;
+    q = fmaf(q, a, 0.0007399106398224831f); q = fmaf(q, a, -0.00797757226973772f); q = fmaf(q, a, 0.053238335996866226f);
+    q = fmaf(q, a, 0.4589155912399292f); q = fmaf(q, a, 1.1511471271514893f);
+    float h;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(fmaf(-a, q, -1.f)));
+    return fmaf(-a, h, fmaxf(x, 0.f));
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
 
 struct TcKernelParams {
@@ -159,15 +171,32 @@ __device__ __forceinline__ void epilogue_ragged(const TcKernelParams& p, const u
 // of this sample.  The K/V rows of this head (1-2 images per warp) are staged once per chunk in the warp's transpose tile and read back as
 // shared-memory broadcasts.  Online softmax in a deliberately ROLLED key loop: a chunk executes this once, and straight-line code of that
 // size would be fetched from L2 every time (instruction-cache misses cost more than the arithmetic).
-__device__ __forceinline__ void epilogue_xattn(const TcKernelParams& p, float (&v)[32], float* stage, int lane, int m_warp0, int nb) {
+// The K/V rows of one chunk (one head; the 32 rows of a warp lie in at most TWO images: rows_per_batch is a multiple of 16, checked on the
+// host): [image][K | V][xk][32 floats] = at most 2 * 2 * 8 * 8 float4, i.e. 8 per lane.  They do not depend on the accumulator, so they are
+// requested a whole chunk ahead (before the accumulator is waited for / while the previous head is processed) and parked in registers.
+struct XPre { float4 v[8]; };
+__device__ __forceinline__ void xattn_prefetch(const TcKernelParams& p, int lane, int m_warp0, int nb, XPre& xp) {
+    const int hw = p.rows_per_batch;
+    const int b0 = (m_warp0 < p.M ? m_warp0 : p.M - 1) / hw, b1 = (m_warp0 + 31 < p.M ? m_warp0 + 31 : p.M - 1) / hw;
+    const int half_img = p.xk * 8, per_img = 2 * half_img, tot = (b1 - b0 + 1) * per_img;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int i = lane + 32 * j;
+        if (i < tot) {
+            const int img = i >= per_img ? 1 : 0, r = i - img * per_img, kvsel = r >= half_img ? 1 : 0, r2 = r - kvsel * half_img;
+            xp.v[j] = __ldg(reinterpret_cast<const float4*>(p.xkv + ((size_t)(b0 + img) * p.xk + (r2 >> 3)) * p.xkv_ld + nb + kvsel * p.xv_off) + (r2 & 7));
+        }
+    }
+}
+__device__ __forceinline__ void epilogue_xattn(const TcKernelParams& p, float (&v)[32], float* stage, int lane, int m_warp0, int nb, const XPre& xp) {
     const int m = m_warp0 + lane, mm = m < p.M ? m : p.M - 1, hw = p.rows_per_batch;
     const int b0 = (m_warp0 < p.M ? m_warp0 : p.M - 1) / hw, b1 = (m_warp0 + 31 < p.M ? m_warp0 + 31 : p.M - 1) / hw;
     const int per_img = 2 * p.xk * 8;                              // float4 pieces per image: [K | V][xk][32 floats]
     __syncwarp();
-    for (int i = lane; i < (b1 - b0 + 1) * per_img; i += 32) {
-        const int img = i / per_img, r = i - img * per_img, kvsel = r / (p.xk * 8), r2 = r - kvsel * p.xk * 8;
-        const float4 t = __ldg(reinterpret_cast<const float4*>(p.xkv + ((size_t)(b0 + img) * p.xk + (r2 >> 3)) * p.xkv_ld + nb + kvsel * p.xv_off) + (r2 & 7));
-        *reinterpret_cast<float4*>(stage + (size_t)i * 4) = t;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int i = lane + 32 * j;
+        if (i < (b1 - b0 + 1) * per_img) *reinterpret_cast<float4*>(stage + (size_t)i * 4) = xp.v[j];
     }
     __syncwarp();
     const float* kb = stage + (size_t)(mm / hw - b0) * per_img * 4;
@@ -199,17 +228,18 @@ __device__ __forceinline__ void epilogue_xattn(const TcKernelParams& p, float (&
     for (int i = 0; i < 32; i++) v[i] = o[i] * il;
 }
 
-// r: this lane's 32 accumulators (row m_warp0 + lane, columns nb..nb+31, nb + 32 <= N); stage: this warp's smem tile; pre: operands of THIS
-// chunk (epi_prefetch).  nb_next >= 0: prefetch the operands of that chunk (same rows) into `pre` once this chunk has consumed them.
+// r: this lane's 32 accumulators (row m_warp0 + lane, columns nb..nb+31, nb + 32 <= N); stage: this warp's smem tile; pre / xp: operands of
+// THIS chunk (epi_prefetch / xattn_prefetch), requested by the caller one whole chunk earlier.
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const uint32_t (&r)[32], float* stage, int lane, int m_warp0, int nb, EpiPre& pre, int nb_next, float* part) {
+__device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const uint32_t (&r)[32], float* stage, int lane, int m_warp0, int nb, const EpiPre& pre, XPre& xp, float* part) {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
     TSTAMP_EPI(8);
     const int cg = (lane & 7) * 4, r0 = lane >> 3, n = nb + cg;
     if (epi_is_xattn<EPI>(p) && !part) {           // no bias / residual operands on this path (checked on the host): `pre` is dead here
-        epilogue_xattn(p, v, stage, lane, m_warp0, nb);
+        if (EPI == EPI_ANY) xattn_prefetch(p, lane, m_warp0, nb, xp);       // the all-in-one kernel loads just in time (register budget)
+        epilogue_xattn(p, v, stage, lane, m_warp0, nb, xp);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(epi_at(stage, lane, j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -252,10 +282,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
                 const float4 bb = pre.b[it >> 2];
                 const float o0 = (t[it].x + bb.x) * gelu_erf(t[it].y + bb.y) + pre.r[it].x, o1 = (t[it].z + bb.z) * gelu_erf(t[it].w + bb.w) + pre.r[it].y;
                 if (p.out) *reinterpret_cast<float2*>(p.out + (size_t)mo * p.out_ld + no) = make_float2(o0, o1);
+                else if (!p.out_lo) *reinterpret_cast<uint32_t*>(p.out_hi + (size_t)mo * p.out_bf_ld + no) = pack16x2(o0, o1, p.f16);
                 else {
                     unsigned short h0, l0, h1, l1; split16(o0, p.f16, h0, l0); split16(o1, p.f16, h1, l1);
                     *reinterpret_cast<uint32_t*>(p.out_hi + (size_t)mo * p.out_bf_ld + no) = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                    if (p.out_lo) *reinterpret_cast<uint32_t*>(p.out_lo + (size_t)mo * p.out_bf_ld + no) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                    *reinterpret_cast<uint32_t*>(p.out_lo + (size_t)mo * p.out_bf_ld + no) = (uint32_t)l0 | ((uint32_t)l1 << 16);
                 }
             }
         }
@@ -309,8 +340,6 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
         }
     }
     TSTAMP_EPI(10);
-    if (nb_next >= 0) epi_prefetch<EPI>(p, lane, m_warp0, nb_next, pre);
-    TSTAMP_EPI(11);
 }
 
 // epilogue of 4 consecutive accumulator columns n..n+3 of row m (bias, time-embedding row vector, activation, residual, store)
@@ -516,8 +545,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const int buf = lt & 1;
             const int mt = tile / ntn, n0 = (tile % ntn) * BN;
             const int m_warp0 = mt * BM + q * 32;
-            EpiPre pre;
-            if (!part && m_warp0 < p.M && n0 + half * 32 + 32 <= p.N) epi_prefetch<EPI>(p, lane, m_warp0, n0 + half * 32, pre);      // overlaps the mainloop
+            // Epilogue operands (bias / time-embedding row / residual, or the K/V rows of the fused cross-attention) are requested ONE WHOLE
+            // CHUNK ahead: the first chunk's before the accumulator is waited for (overlaps the mainloop), chunk c + 1's before chunk c is
+            // read from TMEM -- an L2 round trip (~700 cycles; ncu: long-scoreboard stalls on the residual adds and the stores) is then
+            // covered by the TMEM load, the transpose and the stores of a full chunk instead of being paid per chunk.
+            EpiPre pre, pre_nx; XPre xp, xp_nx;
+            const bool xat = EPI == EPI_XATTN && !part;
+            if (!part && m_warp0 < p.M && n0 + half * 32 + 32 <= p.N) {
+                if (xat) xattn_prefetch(p, lane, m_warp0, n0 + half * 32, xp);
+                else epi_prefetch<EPI>(p, lane, m_warp0, n0 + half * 32, pre);
+            }
             mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
             tc_fence_after();
 #ifdef RDM_AB_TIMING
@@ -528,12 +565,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const int nb = n0 + c * 32;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32);
                 if (m_warp0 >= p.M || nb >= p.N) continue;
+                const int nbn = nb + 64;                           // this warp's next chunk of the tile
+                const bool has_next = !part && c + 2 < BN / 32 && nbn + 32 <= p.N;
+                if (has_next) {
+                    if (xat) xattn_prefetch(p, lane, m_warp0, nbn, xp_nx);
+                    else epi_prefetch<EPI>(p, lane, m_warp0, nbn, pre_nx);
+                }
                 uint32_t r[32];
                 tmem_ld32(taddr, r);
-                if (nb + 32 <= p.N) {
-                    const int nbn = nb + 64;                       // this warp's next chunk of the tile
-                    epilogue_chunk<EPI>(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb, pre, (c + 2 < BN / 32 && nbn + 32 <= p.N) ? nbn : -1, part);
-                } else if (EPI == EPI_ANY) epilogue_ragged(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0 + lane, nb);     // (split-K needs N % 4 == 0 ... never a partial tile here)
+                if (nb + 32 <= p.N) epilogue_chunk<EPI>(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb, pre, xp, part);
+                else if (EPI == EPI_ANY) epilogue_ragged(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0 + lane, nb);     // (split-K needs N % 4 == 0 ... never a partial tile here)
+                if (has_next) { if (xat) xp = xp_nx; else pre = pre_nx; }
             }
             tc_fence_before();
             __syncwarp();
@@ -740,7 +782,7 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     p.bias = e.bias; p.rowvec = e.rowvec; p.rowvec_ld = e.rowvec_ld; p.rows_per_batch = e.rows_per_batch > 0 ? e.rows_per_batch : 1;
     p.res = e.res; p.res_ld = e.res_ld; p.act = e.act; p.out = e.out; p.out_ld = e.out_ld;
     p.xkv = e.xkv; p.xkv_ld = e.xkv_ld; p.xv_off = e.xv_off; p.xk = e.xk; p.xscale_log2e = e.xscale * 1.4426950408889634f;
-    RDM_REQUIRE(e.act != ACT_XATTN || (e.xkv && e.xk >= 1 && e.xk <= 8 && p.rows_per_batch >= 16 && w.N % 32 == 0 && e.xkv_ld % 4 == 0 && !e.bias && !e.res && !e.rowvec), RDM_ERR_ARG,
+    RDM_REQUIRE(e.act != ACT_XATTN || (e.xkv && e.xk >= 1 && e.xk <= 8 && p.rows_per_batch >= 16 && p.rows_per_batch % 16 == 0 && w.N % 32 == 0 && e.xkv_ld % 4 == 0 && !e.bias && !e.res && !e.rowvec), RDM_ERR_ARG,
                 "gemm_tc: fused cross-attention needs 1..8 context rows, N %% 32 == 0 and no bias/residual (xk=%d N=%d)", e.xk, w.N);
     p.out_hi = out_hi; p.out_lo = out_lo; p.out_bf_ld = out_bf_ld; p.f16 = f16; p.pdl_off = w.dynamic;
     RDM_REQUIRE((p.out != nullptr) != (p.out_hi != nullptr), RDM_ERR_ARG, "gemm_tc: exactly one of fp32 / bf16 outputs");

@@ -33,8 +33,22 @@ __device__ __forceinline__ void split16(float x, int f16, unsigned short& hi, un
         __nv_bfloat16 h = __float2bfloat16_rn(x); hi = __bfloat16_as_ushort(h); lo = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(h)));
     }
 }
+// two values -> one packed 32-bit word of a single 16-bit plane (first value in the low half); fp16: saturating to the finite range, which is
+// what split16's clamp does.  One F2FP instruction on the device; the host emulation (no inline PTX) goes through split16.
+__device__ __forceinline__ uint32_t pack16x2(float a, float b, int f16) {
+#ifdef __CUDA_ARCH__
+    uint32_t u;
+    if (f16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(b), "f"(a));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(b), "f"(a));
+    return u;
+#else
+    unsigned short h0, l0, h1, l1; split16(a, f16, h0, l0); split16(b, f16, h1, l1);
+    return (uint32_t)h0 | ((uint32_t)h1 << 16);
+#endif
+}
 // 4 consecutive values -> packed hi (and lo) 8-byte stores
 __device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, int f16, float a, float b, float c, float d) {
+    if (!lo) { *reinterpret_cast<uint2*>(hi) = make_uint2(pack16x2(a, b, f16), pack16x2(c, d, f16)); return; }
     unsigned short h[4], l[4];
     split16(a, f16, h[0], l[0]); split16(b, f16, h[1], l[1]); split16(c, f16, h[2], l[2]); split16(d, f16, h[3], l[3]);
     *reinterpret_cast<uint2*>(hi) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
@@ -77,6 +91,12 @@ int k_gn_stats(View x, int B, int HW, int groups, double* sums, cudaStream_t st)
 // y = (x-mean)*rstd*gamma+beta, optional SiLU; y is a contiguous-or-strided fp32 view
 int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps, const float* gamma, const float* beta,
                int silu, Out4 y, Out4 raw, cudaStream_t st);      // raw (optional): the un-normalised x re-emitted (skip 1x1 conv operand)
+// One-launch GroupNorm for the tensor-core engine modes (gn_fused.cu): the CTAs of an image form a cluster and exchange their partial sums
+// through distributed shared memory; or, chan != nullptr, the group sums are folded from per-(image, channel) {sum, sumsq} pairs that the
+// producing GEMM's epilogue accumulated (image stride chan_ld channels) and x is read once.
+bool k_gn_fused_supported(int C, int HW, int groups, bool pre);
+int k_gn_fused(View x, int B, int HW, int groups, const double* chan, int chan_ld, float eps, const float* gamma, const float* beta, int silu,
+               Out4 y, Out4 raw, cudaStream_t st);
 // LayerNorm over the last dim of [M, C] (eps 1e-5), one warp per row
 int k_layernorm(View x, int M, const float* gamma, const float* beta, float eps, Out4 y, cudaStream_t st);
 // softmax(q k^T * scale) v for heads of width 32.  q: [B*Nq, heads*32] view, k/v: [B*Nk, heads*32] views.

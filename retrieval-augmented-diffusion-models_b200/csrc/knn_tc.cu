@@ -346,6 +346,14 @@ knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
                 for (int qi = ew * 32 + lane; qi < nq_valid; qi += EPI_WARPS * 32) s_thr[qi] = __ldcg(thr_out + qi);
                 asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+                // main phase: the thresholds of this warp's query groups live in the registers the sample maxima occupied (as ordered-u32
+                // bit patterns of the float: +inf for padding queries, so they never pass)
+#pragma unroll
+                for (int g = 0; g < NGRP; g++) {
+                    const int q0 = (half + g * EPI_PER_Q) * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) mx[g][j] = __float_as_uint(q0 + j < nq_valid ? s_thr[q0 + j] : CUDART_INF_F);
+                }
             }
             const bool sample = p < ts;
             const int buf = (int)(p & 1);
@@ -377,16 +385,36 @@ knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
                 }
-                if (row < n) {
+                if (sample) {
+                    if (row < n) {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int qi = q0 + j;
-                        float s = (__uint_as_float(r[j]) + __uint_as_float(r[16 + j])) * iv;
-                        if (!(s == s)) s = -CUDART_INF_F;
-                        if (sample) {
+                        for (int j = 0; j < 16; j++) {
+                            float s = (__uint_as_float(r[j]) + __uint_as_float(r[16 + j])) * iv;
+                            if (!(s == s)) s = -CUDART_INF_F;
                             const uint32_t o = order_f32(s);
                             mx[g][j] = o > mx[g][j] ? o : mx[g][j];
-                        } else if (qi < nq_valid && s >= s_thr[qi]) {
+                        }
+                    }
+                } else {
+                    // ONE compare per (row, query) folded into a 16-bit survivor mask -- no branch per element (ncu: the per-element branch and
+                    // the shared-memory threshold load were the top stall sites at 64 queries); survivors (~4e-4 of the pairs) are handled after.
+                    // A NaN score (zero row: 0 * inf) takes the slow path too, where it becomes -inf as before.
+                    unsigned pass = 0u;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const float s = (__uint_as_float(r[j]) + __uint_as_float(r[16 + j])) * iv;
+                        pass |= !(s < __uint_as_float(mx[g][j])) ? (1u << j) : 0u;
+                    }
+                    if (row >= n) pass = 0u;
+                    while (pass) {
+                        const int j = __ffs(pass) - 1; pass &= pass - 1u;
+                        uint32_t hi_v = r[0], lo_v = r[16];
+#pragma unroll
+                        for (int jj = 1; jj < 16; jj++) if (jj == j) { hi_v = r[jj]; lo_v = r[16 + jj]; }
+                        float s = (__uint_as_float(hi_v) + __uint_as_float(lo_v)) * iv;
+                        if (!(s == s)) s = -CUDART_INF_F;
+                        const int qi = q0 + j;
+                        if (qi < nq_valid && s >= s_thr[qi]) {
                             const unsigned pos = atomicAdd(&cand_cnt[qi], 1u);
                             if (pos < (unsigned)CAND_CAP) cand[(size_t)qi * CAND_CAP + pos] = make_key(s, (uint32_t)row);
                         }

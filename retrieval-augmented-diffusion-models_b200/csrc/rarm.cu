@@ -13,6 +13,7 @@
 // graph with the position in device memory and replayed 256 times without host synchronisation.
 // Algorithmic bytes per step: sum over layers of N*K*sizeof(weight) + the live part of the KV cache (2*L*B2*(pos+1)*C*4 B).
 #include "common.cuh"
+#include "ptx.cuh"
 #include "../../include/rdm_b200.h"
 #include <math_constants.h>
 #include <string.h>
@@ -64,6 +65,31 @@ __device__ __forceinline__ float4 load_w4(const __half* w) {
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// 8 consecutive weights of one row as floats: ONE 16-byte load for fp16 weights (two for fp32)
+__device__ __forceinline__ void load_w8(const float* w, float (&o)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w)), b = __ldg(reinterpret_cast<const float4*>(w) + 1);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+__device__ __forceinline__ void load_w8(const __half* w, float (&o)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(w));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
+}
+
+// The kernels of a decode step are chained with programmatic dependent launch: a kernel may be staged (and request its STATIC weights)
+// while its predecessor still runs; it executes griddepcontrol.wait before it touches anything a predecessor wrote and before its own
+// first global store.  RDM_PDL=0 switches the attribute off (plain stream order).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_rdm_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- dense layers: out[M, N'] = epi(LN?(x)[M, K] * W[N, K]^T) ------------------------------------------------
 struct GemvP {
     const float* x; int ldx;            // activations, fp32 [M, K]
@@ -75,10 +101,31 @@ struct GemvP {
 };
 // CPW weight rows (output columns) per warp pass; GEGLU: rows (2j, 2j+1) = (value_j, gate_j) -> output column j (needs CPW == 4).
 template <typename WT, int CPW, int WARPS, bool GEGLU>
-__global__ void __launch_bounds__(WARPS * 32) rarm_gemv_kernel(GemvP p, const WT* __restrict__ w) {
+__global__ void __launch_bounds__(WARPS * 32, 2) rarm_gemv_kernel(GemvP p, const WT* __restrict__ w) {
     extern __shared__ float sx[];                          // [GV_ROWS][K]
     const int K = p.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m0 = blockIdx.y * GV_ROWS, rows = min(GV_ROWS, p.M - m0);
+    constexpr int R = CPW * GV_ROWS;
+    const int n0 = (blockIdx.x * WARPS + warp) * CPW;
+    pdl_launch_dependents();
+    // Weight rows are static: the first PF 256-element blocks of this warp's rows are requested BEFORE the predecessor kernel is waited for
+    // and before the activation prologue (staging + LayerNorm), so the DRAM round trip of the weights overlaps both.  A lane owns 8
+    // consecutive elements of every block: one 16-byte load per row and block (fp16).
+    constexpr int PF = CPW >= 4 ? 2 : 4;                   // 64 registers of weights in flight per lane either way (two CTAs per SM)
+    const int nblk = K >> 8;                               // whole 256-element blocks; K % 256 == 128 leaves one 128-element tail
+    const WT* wr[CPW];
+#pragma unroll
+    for (int c = 0; c < CPW; c++) wr[c] = w + (size_t)min(n0 + c, p.N - 1) * K;      // clamped: the duplicate column is not stored
+    float wpre[PF][CPW][8];
+    if (n0 < p.N) {
+#pragma unroll
+        for (int b = 0; b < PF; b++)
+            if (b < nblk) {
+#pragma unroll
+                for (int c = 0; c < CPW; c++) load_w8(wr[c] + (b << 8) + lane * 8, wpre[b][c]);
+            }
+    }
+    pdl_wait();
     for (int i = threadIdx.x; i < GV_ROWS * (K / 4); i += WARPS * 32) {
         const int r = i / (K / 4), c = i % (K / 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -99,20 +146,43 @@ __global__ void __launch_bounds__(WARPS * 32) rarm_gemv_kernel(GemvP p, const WT
         }
         __syncthreads();
     }
-    constexpr int R = CPW * GV_ROWS;
-    const int n0 = (blockIdx.x * WARPS + warp) * CPW;
     if (n0 >= p.N) return;                                 // no block-wide barrier below this line
-    const WT* wr[CPW];
-#pragma unroll
-    for (int c = 0; c < CPW; c++) wr[c] = w + (size_t)min(n0 + c, p.N - 1) * K + lane * 4;      // clamped: the duplicate column is not stored
     float acc[R];
 #pragma unroll
     for (int i = 0; i < R; i++) acc[i] = 0.f;
-#pragma unroll 2
-    for (int kc = 0; kc < K; kc += 128) {
+    auto fma_block = [&](const float (&wv)[CPW][8], int kc) {
+#pragma unroll
+        for (int m = 0; m < GV_ROWS; m++) {
+            const float4 a0 = *reinterpret_cast<const float4*>(sx + m * K + kc + lane * 8), a1 = *reinterpret_cast<const float4*>(sx + m * K + kc + lane * 8 + 4);
+#pragma unroll
+            for (int c = 0; c < CPW; c++) {
+                float t = acc[c * GV_ROWS + m];
+                t = fmaf(a0.x, wv[c][0], t); t = fmaf(a0.y, wv[c][1], t); t = fmaf(a0.z, wv[c][2], t); t = fmaf(a0.w, wv[c][3], t);
+                t = fmaf(a1.x, wv[c][4], t); t = fmaf(a1.y, wv[c][5], t); t = fmaf(a1.z, wv[c][6], t); t = fmaf(a1.w, wv[c][7], t);
+                acc[c * GV_ROWS + m] = t;
+            }
+        }
+    };
+#pragma unroll
+    for (int b = 0; b < PF; b++)
+        if (b < nblk) fma_block(wpre[b], b << 8);
+    // rows longer than PF blocks (the 4C-wide feed-forward input): PF blocks of loads in flight per round
+    for (int b0 = PF; b0 < nblk; b0 += PF) {
+#pragma unroll
+        for (int b = 0; b < PF; b++)
+            if (b0 + b < nblk) {
+#pragma unroll
+                for (int c = 0; c < CPW; c++) load_w8(wr[c] + ((b0 + b) << 8) + lane * 8, wpre[b][c]);
+            }
+#pragma unroll
+        for (int b = 0; b < PF; b++)
+            if (b0 + b < nblk) fma_block(wpre[b], (b0 + b) << 8);
+    }
+    if (K & 128) {                                         // 128-element tail: 4 elements per lane
+        const int kc = nblk << 8;
         float4 wv[CPW];
 #pragma unroll
-        for (int c = 0; c < CPW; c++) wv[c] = load_w4(wr[c] + kc);
+        for (int c = 0; c < CPW; c++) wv[c] = load_w4(wr[c] + kc + lane * 4);
 #pragma unroll
         for (int m = 0; m < GV_ROWS; m++) {
             const float4 a = *reinterpret_cast<const float4*>(sx + m * K + kc + lane * 4);
@@ -166,6 +236,8 @@ __global__ void __launch_bounds__(256) rarm_attn_kernel(const float* __restrict_
                                                         float scale_log2e, float* __restrict__ out, int ldo) {
     extern __shared__ float sm[];                          // q[64] | p[nk] | red[4*64]
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
+    pdl_wait();                                            // q / knew / vnew come from the preceding GEMV; the cache append below is this kernel's first store
     int nk = nk_fixed;
     if (knew) {
         const int pos = *pos_dev;
@@ -412,7 +484,7 @@ int launch_gemv(const GemvP& p, const WT* w, cudaStream_t st) {
         configured = 200 * 1024;
     }
     dim3 grid((unsigned)ceil_div(p.N, CPW * WARPS), (unsigned)ceil_div(p.M, GV_ROWS));
-    rarm_gemv_kernel<WT, CPW, WARPS, GEGLU><<<grid, WARPS * 32, smem, st>>>(p, w);
+    RDM_CHECK_CUDA(launch_dep(rarm_gemv_kernel<WT, CPW, WARPS, GEGLU>, grid, dim3(WARPS * 32), smem, st, p, w));
     LAUNCH_CHECK();
     return RDM_OK;
 }
@@ -433,7 +505,7 @@ int attn(const float* q, int ldq, const float* knew, const float* vnew, int ldn,
          int nk_max, int heads, int B2, float* out, int ldo, cudaStream_t st) {
     const size_t smem = (size_t)(DH + ((nk_max + 3) & ~3) + 4 * DH) * sizeof(float);
     RDM_REQUIRE(smem <= 48 * 1024, RDM_ERR_UNSUPPORTED, "rarm attention: %d keys", nk_max);
-    rarm_attn_kernel<<<dim3(heads, B2), 256, smem, st>>>(q, ldq, knew, vnew, ldn, kc, vc, tk, ldk, pos_dev, nk_fixed, 0.125f * 1.4426950408889634f, out, ldo);
+    RDM_CHECK_CUDA(launch_dep(rarm_attn_kernel, dim3(heads, B2), dim3(256), smem, st, q, ldq, knew, vnew, ldn, kc, vc, tk, ldk, pos_dev, nk_fixed, 0.125f * 1.4426950408889634f, out, ldo));
     LAUNCH_CHECK();
     return RDM_OK;
 }

@@ -354,6 +354,15 @@ void lin_any(Ctx& cx, const Opnd& a, int M, const Lin& l, GemmEpi e, const Opnd&
 }
 
 void gn(Ctx& cx, const Act& x, const Norm& nm, float eps, int silu, const Opnd& y, const Opnd* raw = nullptr) {
+    // A/B (RDM_GN_CLUSTER=1): statistics and normalisation in ONE launch, the CTAs of an image exchanging partial sums through distributed
+    // shared memory (gn_fused.cu).  Measured on B200 (full architecture, B2 = 32, fp16 mode): 4.85 ms per forward against 4.60 ms with the
+    // two kernels below -- an 8-CTA cluster per image offers the memory system far fewer independent loads than the 148 x 16 small CTAs of
+    // gn_stats / gn_apply, and the cluster launch itself is slower than two plain launches.  Kept as the negative result it is; default off.
+    static const int use_cluster = getenv("RDM_GN_CLUSTER") ? atoi(getenv("RDM_GN_CLUSTER")) : 0;
+    if (cx.n->mode != RDM_UNET_MODE_FP32 && use_cluster && k_gn_fused_supported(x.v.C, x.H * x.W, 32, false)) {
+        RUN_UNLESS(2, k_gn_fused(x.v, x.B, x.H * x.W, 32, nullptr, 0, eps, nm.g, nm.b, silu, y.out4(), raw ? raw->out4() : Out4(), cx.st));
+        return;
+    }
     double* s = stats_alloc(cx, x.B, 32);
     RUN_UNLESS(1, k_gn_stats(x.v, x.B, x.H * x.W, 32, s, cx.st));
     RUN_UNLESS(2, k_gn_apply(x.v, x.B, x.H * x.W, 32, s, eps, nm.g, nm.b, silu, y.out4(), raw ? raw->out4() : Out4(), cx.st));
@@ -409,7 +418,7 @@ void run_st(Ctx& cx, const STW& s, const Act& x, View out) {
     // cross-attention to the retrieved neighbours (attention.py:94); K/V were projected once in set_context
     RUN_UNLESS(4, k_layernorm(t1, M, s.ln2.g, s.ln2.b, 1e-5f, nrm.out4(), cx.st));
     View kv(cx.dry ? nullptr : n->ctx_kv + n->ctx_off[s.id] + (size_t)cx.b0 * n->ctx_k * 2 * C, 2 * C, 2 * C);     // this chain's rows of the projected context
-    if (tcp && n->ctx_k <= 8 && N >= 16 && !(n->skip & 64)) {
+    if (tcp && n->ctx_k <= 8 && N >= 16 && N % 16 == 0 && !(n->skip & 64)) {
         // tensor-core engine: softmax(q k^T) v over the k retrieved neighbours runs in the epilogue of the to_q GEMM (one 32-column
         // accumulator chunk = one head's query), so neither q nor a separate attention launch exists
         GemmEpi e; e.act = ACT_XATTN; e.xkv = kv.p; e.xkv_ld = kv.ld; e.xv_off = C; e.xk = n->ctx_k; e.xscale = scale; e.rows_per_batch = N;

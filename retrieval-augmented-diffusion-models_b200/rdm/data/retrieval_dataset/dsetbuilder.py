@@ -8,7 +8,8 @@
   `shard=True`;
 * `search_k_nearest` (`:478-518`) with the same result dictionary;
 * `embed` (`:461-473`) through the retriever (CLIP).
-Database *construction* (`build_data_pool`, patch datasets, visualisation) is out of scope and raises.
+* `build_data_pool` / `save_datapool` / `reset_data_pool` (`:238-262,317-437`): bulk CLIP-image embedding of caller-supplied patch batches
+  and the chunked `.npz` pool writer (the image datasets themselves and visualisation stay out of scope).
 """
 import datetime
 import os
@@ -54,6 +55,8 @@ class DatasetBuilder(object):
         self._row_base, self._n_total = None, None   # set when only this rank's rows of a sharded database were read
         self.searcher = None
         self.searcher_savedir = searcher_savepath
+        self.savepath_postfix = savepath_postfix
+        self.dset_name = data["target"].split('.')[-1] if data is not None and "target" in data else "dataset"
         if self.saved_embeddings:
             self.load_embeddings()
 
@@ -210,7 +213,103 @@ class DatasetBuilder(object):
     def get_nn_patches(self, batched_nns):
         raise NotImplementedError("neighbour image patches need the patch dataset, which is outside the sampling hot path")
 
-    def build_data_pool(self, *a, **k):
-        raise NotImplementedError("database construction is outside the sampling hot path (SURVEY.md section 2)")
+    # ---- database construction (reference dsetbuilder.py:238-262,317-437) ---------------------------------------
+    def reset_data_pool(self):
+        self.data_pool = {key: [] for key in self.data_pool}
 
-    save_datapool = build_data_pool
+    def save_datapool(self, postfix: str = None):
+        """`np.savez_compressed` of the collected pool into `<base>/<dir_identifier>/<rows>x<dim>[-postfix].npz` -- the layout
+        `load_embeddings` / `db_loader` read back.  `<base>` is the reference's hard-coded directory (dsetbuilder.py:248) unless
+        `RDM_RETRIEVAL_DATASETS_DIR` (or the `pool_dir` attribute) names another one."""
+        print('Save embeddings...')
+        shape = list(self.data_pool['embedding'][0].shape)
+        shape[0] *= len(self.data_pool['embedding'])                  # the reference's file name: rows of the first batch x number of batches
+        identifier = 'x'.join(str(s) for s in shape)
+        if postfix:
+            print(f'Adding postfix "{postfix}" to identifier')
+            identifier = identifier + '-' + postfix
+        base = getattr(self, 'pool_dir', None) or os.environ.get('RDM_RETRIEVAL_DATASETS_DIR') or '/export/compvis-nfs/group/datasets/retrieval_datasets'
+        img_dir = os.path.join(base, self.dir_identifier)
+        os.makedirs(img_dir, exist_ok=True)
+        self.saved_embeddings = img_dir
+        saved_embeddings = f'{img_dir}/{identifier}.npz'
+        self.data_pool = {key: np.concatenate(self.data_pool[key]) for key in self.data_pool}
+        np.savez_compressed(saved_embeddings, **self.data_pool)
+        return saved_embeddings
+
+    @property
+    def dir_identifier(self):
+        ident = '-'.join([self.timestamp, getattr(self, 'dset_name', 'dataset'), self.retriever_name, str(self.patch_size)])
+        return ident + (f"-{self.savepath_postfix}" if getattr(self, 'savepath_postfix', None) else '')
+
+    def build_data_pool(self, loader=None, save=True, pool_dtype=np.float16):
+        """Bulk embedding of image patches into a retrieval database (reference `build_data_pool`, dsetbuilder.py:317-437): every batch
+        of `loader` -- dictionaries with `patch` ([b, h, w, 3] or [b, n, h, w, 3] in [-1, 1]), `img_id`, `patch_coords` and optionally
+        `class_id`, i.e. what the reference's `PatcherDataset` + `custom_collate` deliver -- goes through `embed` (CLIP image tower on the
+        device, one launch sequence per batch) and is appended to the pool; the pool is written as `part_<i>` files every `chunk_size`
+        rows (or as one file at the end) and extraction stops at `max_pool_size` rows.  The image datasets themselves (ImageNet /
+        OpenImages readers, patch sampling) stay with the caller: `loader` is any iterable, e.g. a `DataLoader` over the caller's patch
+        dataset.  Rows are stored as float16 like the published databases (the reference's CLIP runs in half precision on the GPU).
+        A pool that was loaded from `saved_embeddings` and is shorter than `max_pool_size` is continued: the batches whose rows are
+        already present are skipped (the loader must replay the same order), new parts are numbered after the existing ones."""
+        if loader is None:
+            raise NotImplementedError("build_data_pool needs a loader of patch batches: the image patch datasets are outside this build (SURVEY.md section 2)")
+        assert self.max_pool_size is not None, 'Max pool size still None --> check implementation'
+        if self.chunk_size is not None:
+            assert self.chunk_size % self.retriever_bs == 0, '"batch_size" has to evenly divide "chunk_size", if the latter is specified'
+        n_examples = skip_rows = 0
+        if self.saved_embeddings and len(self.data_pool['embedding']) > 0:
+            current_len = self.data_pool['embedding'].shape[0]
+            if current_len >= self.max_pool_size:
+                print('embeddings are already saved, not recomputing....')
+                return
+            print(f'Restarting extraction as only {current_len} of overall {self.max_pool_size} examples are in data_pool.')
+            n_examples = skip_rows = current_len
+            self.data_pool = {key: [] for key in self.data_pool}
+        self.data_pool = {key: ([] if not isinstance(v, list) else v) for key, v in self.data_pool.items()}
+        part = int(n_examples / self.chunk_size) + 1 if self.chunk_size is not None else 1
+        deltas, overall_start, seen, written = [], time.time(), 0, []
+
+        def flush(postfix):
+            if save and len(self.data_pool['embedding']) > 0:
+                written.append(self.save_datapool(postfix=postfix))
+                self.reset_data_pool()
+
+        for batch in loader:
+            if 'patch' not in batch:
+                break
+            patches = batch['patch']
+            rows = int(np.prod(patches.shape[:-3]))
+            if seen + rows <= skip_rows:                               # already in the saved pool
+                seen += rows
+                continue
+            seen += rows
+            start = time.time()
+            embeddings = self.embed(patches)
+            embeddings = (embeddings.detach().cpu().numpy() if isinstance(embeddings, torch.Tensor) else np.asarray(embeddings)).astype(pool_dtype, copy=False)
+            deltas.append(time.time() - start)
+            as_np = lambda v: v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+            self.data_pool['patch_coords'].append(as_np(batch['patch_coords']))
+            self.data_pool['img_id'].append(as_np(batch['img_id']))
+            self.data_pool['embedding'].append(embeddings)
+            if 'class_id' in batch:
+                self.data_pool.setdefault('class_id', []).append(as_np(batch['class_id']))
+            n_examples += embeddings.shape[0]
+            if self.chunk_size is not None and n_examples / self.chunk_size >= part:
+                flush(f'part_{part}')                                   # save in different chunks to avoid exceeding RAM
+                part += 1
+                if n_examples >= self.max_pool_size:
+                    break
+            elif self.chunk_size is None and n_examples >= self.max_pool_size:
+                break
+        if self.chunk_size is not None:
+            flush(f'part_{part}')                                       # a last part smaller than chunk_size (nothing left after a complete chunk)
+        elif save and len(self.data_pool['embedding']) > 0:             # only save a single file, when chunk size not defined
+            written.append(self.save_datapool())
+            self.reset_data_pool()
+        overall, extract = time.time() - overall_start, float(np.sum(deltas))
+        print(f'Finish extraction of {n_examples} feature embeddings')
+        print('=' * 25, ' Time results ', '=' * 25)
+        print(f'Extraction alone took {extract} secs; with loading {overall} secs; {extract / max(1, n_examples - skip_rows)} secs per sample')
+        self.build_stats = {'rows': n_examples, 'new_rows': n_examples - skip_rows, 'embed_seconds': extract, 'seconds': overall, 'files': written}
+        return written

@@ -12,6 +12,12 @@ int k_attention_mma(const __half*, const __half*, const __half*, int, int, int, 
     rdm_set_error("emulation: the warp-MMA attention kernel is not available on the host");
     return RDM_ERR_UNSUPPORTED;
 }
+// one-launch GroupNorm of the tensor-core modes (gn_fused.cu: thread-block clusters + distributed shared memory); the strict mode never asks for it
+bool k_gn_fused_supported(int, int, int, bool) { return false; }
+int k_gn_fused(View, int, int, int, const double*, int, float, const float*, const float*, int, Out4, Out4, cudaStream_t) {
+    rdm_set_error("emulation: the cluster GroupNorm kernel is not available on the host (use RDM_UNET_MODE_FP32)");
+    return RDM_ERR_UNSUPPORTED;
+}
 
 // tensor-core kNN scans (knn_tc.cu): the searcher is driven with RDM_KNN_NO_TC=1 under emulation
 #include "knn_tc.cuh"
