@@ -71,6 +71,7 @@ struct TcKernelParams {
     float* out; int out_ld;                                // fp32 output (or null)
     __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_bf_ld;   // 16-bit-plane output (or null)
     int f16;                                                       // planes are IEEE fp16 instead of bf16
+    double* stats; int stats_ld, stats_hw;                         // GroupNorm statistics of the result (GemmEpi::stats), or null
 };
 
 template <int BN, int NSPLIT, int STAGES>
@@ -78,7 +79,8 @@ struct TcSmem {
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * A_BYTES + (NSPLIT >= 2 ? 2 : 1) * B_BYTES;   // [A_hi][B_hi][B_lo?][A_lo?]
     static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;      // per-epilogue-warp transpose tiles
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+    static constexpr int STAT_BYTES = 2 * BN * 4;                  // GroupNorm column sums of a tile: [sum | sumsq][BN] fp32
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES + STAT_BYTES;
     static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
     static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
     static_assert(TOTAL <= 232448, "shared memory budget");
@@ -228,10 +230,50 @@ __device__ __forceinline__ void epilogue_xattn(const TcKernelParams& p, float (&
     for (int i = 0; i < 32; i++) v[i] = o[i] * il;
 }
 
+// GroupNorm statistics of the finished values (the consumer of this GEMM's output is a GroupNorm: ResBlock in/out_layers, the
+// SpatialTransformer norm, the output head): per-(image, column) sum and sum of squares.  The lane holds 4 columns x 8 rows
+// (r0 + 4 it): fp32 partial sums over the warp's 32 rows, two xor-shuffles across the row groups, then SHARED-memory fp32 atomics from the
+// 8 lanes of row group 0 into the tile's column sums (a 128-row tile lies in one image: stats_hw is a multiple of 128).  At the end of
+// the tile the epilogue warps flush the 2 * BN sums with fp64 global atomics (epi_stats_flush) -- one atomic per column and tile instead
+// of one per column, warp and chunk (the first version: 393 K fp64 atomics per level-0 GEMM cost more than the statistics pass saved).
+__device__ __forceinline__ void epi_stats(const TcKernelParams& p, const float4 (&t)[8], int lane, int m_warp0, int col, float* s_stat, int BN) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    const int r0 = lane >> 3;
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        if (m_warp0 + r0 + 4 * it < p.M) {
+            s[0] += t[it].x; q[0] = fmaf(t[it].x, t[it].x, q[0]); s[1] += t[it].y; q[1] = fmaf(t[it].y, t[it].y, q[1]);
+            s[2] += t[it].z; q[2] = fmaf(t[it].z, t[it].z, q[2]); s[3] += t[it].w; q[3] = fmaf(t[it].w, t[it].w, q[3]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        s[j] += __shfl_xor_sync(0xffffffffu, s[j], 8); s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
+        q[j] += __shfl_xor_sync(0xffffffffu, q[j], 8); q[j] += __shfl_xor_sync(0xffffffffu, q[j], 16);
+    }
+    if (r0 == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) { atomicAdd(s_stat + col + j, s[j]); atomicAdd(s_stat + BN + col + j, q[j]); }
+    }
+}
+// all EPI_WARPS * 32 epilogue threads, once per tile: column sums of the tile -> fp64 global accumulators of image m_tile0 / stats_hw; the
+// array is zeroed for the next tile (second named barrier)
+__device__ __forceinline__ void epi_stats_flush(const TcKernelParams& p, float* s_stat, int BN, int m_tile0, int n0, int tid_epi) {
+    asm volatile("bar.sync 2, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+    double* d = p.stats + ((size_t)(m_tile0 / p.stats_hw) * p.stats_ld + n0) * 2;
+    for (int i = tid_epi; i < 2 * BN; i += EPI_WARPS * 32) {
+        const int which = i >= BN ? 1 : 0, c = i - which * BN;
+        if (n0 + c < p.N) atomicAdd(d + 2 * c + which, (double)s_stat[i]);
+        s_stat[i] = 0.f;
+    }
+    asm volatile("bar.sync 2, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+}
+
 // r: this lane's 32 accumulators (row m_warp0 + lane, columns nb..nb+31, nb + 32 <= N); stage: this warp's smem tile; pre / xp: operands of
 // THIS chunk (epi_prefetch / xattn_prefetch), requested by the caller one whole chunk earlier.
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const uint32_t (&r)[32], float* stage, int lane, int m_warp0, int nb, const EpiPre& pre, XPre& xp, float* part) {
+__device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const uint32_t (&r)[32], float* stage, int lane, int m_warp0, int nb, const EpiPre& pre, XPre& xp, float* part,
+                                               float* s_stat, int stat_col, int BN) {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
@@ -325,6 +367,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
             const float4 bb = pre.b[it >> 2];
             t[it] = make_float4(t[it].x + bb.x + pre.r[it].x, t[it].y + bb.y + pre.r[it].y, t[it].z + bb.z + pre.r[it].z, t[it].w + bb.w + pre.r[it].w);
         }
+        if (p.stats) epi_stats(p, t, lane, m_warp0, stat_col + cg, s_stat, BN);
         if (p.out) {
 #pragma unroll
             for (int it = 0; it < 8; it++) {
@@ -406,6 +449,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* epi_stage = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);
+    float* stat_base = epi_stage + EPI_WARPS * EPI_WARP_FLOATS;          // [2 * BN]
+    for (int i = threadIdx.x; i < 2 * BN; i += TC_THREADS) stat_base[i] = 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.taps * p.kb_per_tap;
@@ -573,13 +618,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 }
                 uint32_t r[32];
                 tmem_ld32(taddr, r);
-                if (nb + 32 <= p.N) epilogue_chunk<EPI>(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb, pre, xp, part);
+                if (nb + 32 <= p.N) epilogue_chunk<EPI>(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb, pre, xp, part, stat_base, c * 32, BN);
                 else if (EPI == EPI_ANY) epilogue_ragged(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0 + lane, nb);     // (split-K needs N % 4 == 0 ... never a partial tile here)
                 if (has_next) { if (xat) xp = xp_nx; else pre = pre_nx; }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+            if (p.stats && !part) epi_stats_flush(p, stat_base, BN, mt * BM, n0, (int)threadIdx.x - EPI_WARP0 * 32);
 #ifdef RDM_AB_TIMING
             if (warp == EPI_WARP0 && lane == 0) TSTAMP(6);
 #endif
@@ -792,11 +838,16 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     const int mtiles = (M + BM - 1) / BM, sms = 148, nkb_total = p.taps * p.kb_per_tap;
     static const int forced = getenv("RDM_TC_BN") ? atoi(getenv("RDM_TC_BN")) : 0;
     static const int no_split = getenv("RDM_TC_NOSPLIT") ? 1 : 0;
-    static const int use_cluster = getenv("RDM_TC_CLUSTER") ? atoi(getenv("RDM_TC_CLUSTER")) : 1;
+    static const int use_cluster = getenv("RDM_TC_CLUSTER") ? atoi(getenv("RDM_TC_CLUSTER")) : 0;
+    static const int c_fix = getenv("RDM_TC_FIX") ? atoi(getenv("RDM_TC_FIX")) : 6, c_red = getenv("RDM_TC_RED") ? atoi(getenv("RDM_TC_RED")) : 5,
+                     c_minkb = getenv("RDM_TC_MINKB") ? atoi(getenv("RDM_TC_MINKB")) : 4;       // cost-model constants (developer sweeps)
     // Split-K has two implementations: (a) persistent CTAs write fp32 partials, a dependent kernel reduces them; (b) the splits of a tile
     // form a thread-block cluster (CTA rank = split) and reduce through distributed shared memory -- no partials in HBM/L2 and no second
     // kernel, but splits <= 8 (portable cluster size), one CTA per item, and only `cap` clusters are co-resident (GPC granularity).
-    // Both are candidates of the cost model below; RDM_TC_CLUSTER=0 / 2 forces the reduce-kernel / the cluster variant.
+    // RDM_TC_CLUSTER = 0 (default since round 2): reduce kernel only; 1: both are candidates of the cost model below; 2: cluster variant only.
+    // Measured on B200 (full architecture, B2 = 32, fp16 mode, graph replay): 4.46 ms per forward with 0, 4.64 ms with 1, 4.80 ms with 2 --
+    // the cluster variant pays two cluster barriers, the DSMEM pass and the gang-scheduled launch on the critical path of every small GEMM
+    // (in-kernel stamps: 5 us from the last MMA to the end of the kernel against ~2 us for the straight epilogue).
     CUtensorMap tdummy = ta_hi;
     int BN = 32, splits = 1, clustered = 0;
     const int cand[4] = {192, 128, 64, 32};
@@ -808,7 +859,7 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
         for (int cl = 0; cl <= 1; cl++) {
             if (cl == 1 && use_cluster == 0) continue;
             for (int sp = cl ? 2 : 1; sp <= (cl ? 8 : 16); sp++) {
-                if (sp > 1 && (no_split || e.act == ACT_XATTN || nkb_total / sp < 4 || (w.N & 31) || (!cl && (size_t)sp * M * w.N * 4 > ((size_t)48 << 20)))) break;
+                if (sp > 1 && (no_split || e.act == ACT_XATTN || nkb_total / sp < c_minkb || (w.N & 31) || (!cl && (size_t)sp * M * w.N * 4 > ((size_t)48 << 20)))) break;
                 if (sp > 1 && !cl && use_cluster == 2) break;
                 const int kbps = (nkb_total + sp - 1) / sp;
                 if ((sp - 1) * kbps >= nkb_total) continue;                  // an empty split
@@ -820,12 +871,18 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
                     waves = ((long)mtiles * nt + cap - 1) / cap;
                 }
                 // fixed cost of the reduction in k-block units: a dependent reduce kernel over partials in L2 vs an in-kernel DSMEM pass
-                const long cost = waves * (kbps + 6) * (128 + c) + (sp > 1 ? (cl ? 2 : 5) * (128 + c) : 0);
+                const long cost = waves * (kbps + c_fix) * (128 + c) + (sp > 1 ? (cl ? 2 : c_red) * (128 + c) : 0);
                 if (best < 0 || cost < best) { best = cost; BN = c; splits = sp; clustered = cl; }
             }
         }
     }
     p.splits = splits; p.kb_per_split = (nkb_total + splits - 1) / splits; p.part = nullptr; p.cluster = clustered;
+    // GroupNorm statistics in the epilogue: only on the straight path (no split-K: those tiles are finished by epi_store4), plain epilogue,
+    // fp32 result, whole 32-column chunks, images of a multiple of 128 rows (a tile then lies in one image: the 32x32 and 16x16 levels)
+    const bool stats_ok = e.stats && splits == 1 && e.act == ACT_NONE && p.out && (w.N & 31) == 0 && !(e.rowvec && p.rows_per_batch < 16) &&
+                          e.stats_hw >= BM && e.stats_hw % BM == 0 && M % e.stats_hw == 0;
+    p.stats = stats_ok ? e.stats : nullptr; p.stats_ld = e.stats_ld; p.stats_hw = e.stats_hw;
+    if (e.stats_fused) *e.stats_fused = stats_ok ? 1 : 0;
     if (getenv("RDM_TC_TRACE")) fprintf(stderr, "gemm_tc M=%d N=%d K=%d -> BN=%d splits=%d cluster=%d\n", M, w.N, w.K, BN, splits, clustered);
     if (splits > 1 && !p.cluster) {
         static float* ws[16][8] = {{nullptr}}; static size_t ws_cap[16][8] = {{0}};      // [device][workspace slot]: concurrent chains must not share partials

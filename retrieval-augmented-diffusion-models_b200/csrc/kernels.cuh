@@ -8,9 +8,12 @@ struct View {            // [M, C] fp32 matrix view
     float* p = nullptr;
     int ld = 0;          // row stride in floats (multiple of 4)
     int C = 0;
+    // optional GroupNorm statistics slab that travels with the buffer: {sum, sum of squares} (fp64) per (image, column), entry (b, c) at
+    // st[(b * st_ld + c) * 2]; accumulated by the epilogue of the tcgen05 GEMM that writes the view (zeroed once per forward)
+    double* st = nullptr; int st_ld = 0;
     View() {}
     View(float* p_, int ld_, int C_) : p(p_), ld(ld_), C(C_) {}
-    View cols(int c0, int n) const { return View(p + c0, ld, n); }
+    View cols(int c0, int n) const { View v(p + c0, ld, n); if (st) { v.st = st + 2 * (size_t)c0; v.st_ld = st_ld; } return v; }
 };
 
 // Destination of an element-wise producer: fp32 view and/or bf16 hi(/lo) planes (x ~= hi + lo) for the tcgen05 engine.
@@ -75,6 +78,9 @@ struct GemmEpi {
     // values at + xv_off, b = m / rows_per_batch; out[m, head*32 + i] = sum_j softmax_j(q . k_j * xscale) v_j[i]
     const float* xkv = nullptr; int xkv_ld = 0, xv_off = 0, xk = 0; float xscale = 1.f;
     float* out = nullptr; int out_ld = 0;
+    // tensor-core engine only: accumulate per-(image, column) {sum, sumsq} of the fp32 result into stats (see View::st); images are
+    // stats_hw consecutive rows.  *stats_fused is set to 1 by gemm_tc when the launch does it (not with split-K or odd shapes).
+    double* stats = nullptr; int stats_ld = 0, stats_hw = 0; int* stats_fused = nullptr;
 };
 // fp32 CUDA-core engine (strict mode / fallback).  W: [N, K] row-major, K ordered (tap, cin).
 int gemm_simt(const GemmA& a, const float* W, int N, const GemmEpi& e, cudaStream_t st);

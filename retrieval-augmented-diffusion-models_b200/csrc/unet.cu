@@ -261,7 +261,22 @@ void build_net(Net* n) {
 }
 
 // ---- forward ------------------------------------------------------------------------------------------
-struct Ctx { Net* n; cudaStream_t st; bool dry; int rc = RDM_OK; Arena* A = nullptr; size_t stats_off = 0; int b0 = 0; };     // A / stats_off / b0: this chain's arena, statistics slice and first batch row
+struct Ctx {
+    Net* n; cudaStream_t st; bool dry; int rc = RDM_OK; Arena* A = nullptr; size_t stats_off = 0; int b0 = 0;     // A / stats_off / b0: this chain's arena, statistics slice and first batch row
+    // column ranges of statistics slabs (View::st) that a GEMM epilogue of THIS forward has filled: (first entry, columns)
+    std::vector<std::pair<const double*, int>> st_done;
+    void mark_stats(const View& v) { if (v.st) st_done.push_back({v.st, v.C}); }
+    bool has_stats(const View& v) const {                 // every column of the view is covered (a concat buffer has two producers)
+        if (!v.st) return false;
+        const double* cur = v.st; const double* end = v.st + 2 * (size_t)v.C;
+        while (cur < end) {
+            bool found = false;
+            for (const auto& r : st_done) if (r.first == cur) { cur += 2 * (size_t)r.second; found = true; break; }
+            if (!found) return false;
+        }
+        return cur == end;
+    }
+};
 #define RUN(expr) do { if (!cx.dry && cx.rc == RDM_OK) cx.rc = (expr); } while (0)
 // Timing ablation (rdm_unet_set_ablation, tools/ablate_forward.py; env RDM_SKIP sets the initial value): a bit mask of kernel classes that are NOT launched (results are garbage; only the
 // change of the graph-replayed forward time is meaningful).  1 gn_stats, 2 gn_apply, 4 layernorm, 8 attention, 16 GEMM M>=8192, 32 GEMM M<8192.
@@ -287,6 +302,20 @@ double* stats_alloc(Ctx& cx, int B, int groups) {
     return cx.dry ? (double*)nullptr + o : n->stats + o;
 }
 View fresh(Ctx& cx, int M, int C) { return View(cx.A->allocf((size_t)M * C), C, C); }
+// statistics slab [B][C] x {sum, sumsq} for a buffer whose consumer is a GroupNorm (tensor-core modes; zeroed with the rest of n->stats)
+void attach_stats(Ctx& cx, View& v, int B) {
+    if (cx.n->mode == RDM_UNET_MODE_FP32 || cx.n->kind != 0) return;
+    // A/B (RDM_GN_EPI_STATS=1): per-(image, channel) sums accumulated by the epilogue of the producing tcgen05 GEMM (gemm_tc.cu: epi_stats)
+    // and folded by the one-read form of gn_fused.cu.  Measured on B200 (full architecture, B2 = 32, fp16): it applies to 12 of the 67
+    // GroupNorms of a forward (non-split-K producers at the 32x32 / 16x16 levels whose every input half has such a producer) and is a
+    // wash -- 4.645 ms with, 4.635 ms without: the epilogue's shuffles + shared atomics + two named barriers per tile and the larger
+    // statistics memset cost what the 12 saved statistics launches gain.  Default off.
+    static const int on = getenv("RDM_GN_EPI_STATS") ? atoi(getenv("RDM_GN_EPI_STATS")) : 0;
+    if (!on) return;
+    const size_t need = (size_t)B * v.C * 2, o = cx.stats_off; cx.stats_off += need;
+    v.st = cx.dry ? (double*)nullptr + o : cx.n->stats + o; v.st_ld = v.C;
+}
+View fresh_st(Ctx& cx, int B, int M, int C) { View v = fresh(cx, M, C); attach_stats(cx, v, B); return v; }
 Opnd fresh_opnd(Ctx& cx, int M, int C, bool tc) {
     Opnd o;
     if (!tc) { o.f = fresh(cx, M, C); return o; }
@@ -330,7 +359,12 @@ void gemm_any(Ctx& cx, const Opnd& a, int B, int H, int W, int C, int ks, int st
         const int nsplit = mode_nsplit(n->mode), f16 = mode_f16(n->mode);
         const int skip_bit = M >= 8192 ? 16 : 32;
         if (out.tc()) { e.out = nullptr; RUN_UNLESS(skip_bit, gemm_tc(ta, tw, e, out.hi, out.lo, out.ldb, nsplit, f16, cx.st)); }
-        else { e.out = out.f.p; e.out_ld = out.f.ld; RUN_UNLESS(skip_bit, gemm_tc(ta, tw, e, nullptr, nullptr, 0, nsplit, f16, cx.st)); }
+        else {
+            int fused = 0;
+            if (out.f.st && B > 0 && M % B == 0) { e.stats = out.f.st; e.stats_ld = out.f.st_ld; e.stats_hw = M / B; e.stats_fused = &fused; }
+            e.out = out.f.p; e.out_ld = out.f.ld; RUN_UNLESS(skip_bit, gemm_tc(ta, tw, e, nullptr, nullptr, 0, nsplit, f16, cx.st));
+            if (fused && cx.rc == RDM_OK) { View done = out.f; done.C = Nout; cx.mark_stats(done); }
+        }
         return;
     }
     GemmA ga; ga.x = a.f.p; ga.ld = a.f.ld; ga.B = B; ga.Hs = H; ga.Ws = W; ga.Cin = C; ga.ksize = ks; ga.stride = stride; ga.ups = ups; ga.Ho = Ho; ga.Wo = Wo;
@@ -363,6 +397,11 @@ void gn(Ctx& cx, const Act& x, const Norm& nm, float eps, int silu, const Opnd& 
         RUN_UNLESS(2, k_gn_fused(x.v, x.B, x.H * x.W, 32, nullptr, 0, eps, nm.g, nm.b, silu, y.out4(), raw ? raw->out4() : Out4(), cx.st));
         return;
     }
+    if (!cx.dry && cx.has_stats(x.v) && k_gn_fused_supported(x.v.C, x.H * x.W, 32, true)) {
+        // the producing GEMMs left per-(image, channel) sums behind (gemm_tc.cu: epi_stats): no statistics pass, x is read once
+        RUN_UNLESS(2, k_gn_fused(x.v, x.B, x.H * x.W, 32, x.v.st, x.v.st_ld, eps, nm.g, nm.b, silu, y.out4(), raw ? raw->out4() : Out4(), cx.st));
+        return;
+    }
     double* s = stats_alloc(cx, x.B, 32);
     RUN_UNLESS(1, k_gn_stats(x.v, x.B, x.H * x.W, 32, s, cx.st));
     RUN_UNLESS(2, k_gn_apply(x.v, x.B, x.H * x.W, 32, s, eps, nm.g, nm.b, silu, y.out4(), raw ? raw->out4() : Out4(), cx.st));
@@ -376,7 +415,7 @@ void run_res(Ctx& cx, const ResW& r, const Act& x, const float* emb_all, View ou
     Opnd a1 = fresh_opnd(cx, M, r.cin, tc1), xraw;
     if (tcs) xraw = fresh_opnd(cx, M, r.cin, true);
     gn(cx, x, r.n1, r.eps, 1, a1, tcs ? &xraw : nullptr);
-    View h1 = fresh(cx, M, r.cout);
+    View h1 = fresh_st(cx, x.B, M, r.cout);                      // consumed by out_layers' GroupNorm only: conv1's epilogue leaves its statistics
     { GemmEpi e; if (r.emb_off >= 0) { e.rowvec = emb_all + r.emb_off; e.rowvec_ld = cx.n->emb_total; e.rows_per_batch = x.H * x.W; }
       conv_any(cx, a1, x, r.c1, e, from_view(h1)); }
     Opnd a2 = fresh_opnd(cx, M, r.cout, tc2);
@@ -490,7 +529,8 @@ Act run_block(Ctx& cx, const Block& b, Act x, const float* emb_all, View dst) {
             case L_DOWN: Co = n->convs[L.idx].cout; Ho = (x.H + 1) / 2; Wo = (x.W + 1) / 2; break;
             case L_UP: Co = n->convs[L.idx].cout; Ho = x.H * 2; Wo = x.W * 2; break;
         }
-        View o = last ? dst : fresh(cx, x.B * Ho * Wo, Co);
+        const bool feeds_gn = !last && (b.layers[i + 1].kind == L_RES || b.layers[i + 1].kind == L_ST);
+        View o = last ? dst : feeds_gn ? fresh_st(cx, x.B, x.B * Ho * Wo, Co) : fresh(cx, x.B * Ho * Wo, Co);
         switch (L.kind) {
             case L_CONV_IN: { const Conv& c = n->convs[L.idx]; gemm_any(cx, from_view(x.v), x.B, x.H, x.W, c.cin, 3, 1, 0, c.w, c.b, c.cout, GemmEpi(), from_view(o)); break; }
             case L_RES: run_res(cx, n->res[L.idx], x, emb_all, o); break;
@@ -522,6 +562,7 @@ int chain_impl(Ctx& cx, const float* x_nchw, int Bx, const long long* t, int nb,
             int i = nin - 1 - j, ich = n->skip_ch[i];
             cat_ch[j] = ch;
             cat[j] = View(A.allocf((size_t)nb * hH[i] * hW[i] * (ch + ich)), ch + ich, ch + ich);
+            attach_stats(cx, cat[j], nb);                        // both halves are GroupNorm inputs (the skip half also of the next input block)
             ch = n->out_blocks[j].cout;
         }
     }
@@ -539,7 +580,7 @@ int chain_impl(Ctx& cx, const float* x_nchw, int Bx, const long long* t, int nb,
         Act in{cat[j], nb, hH[i], hW[i]};
         View dst;
         if (j + 1 < nout) dst = cat[j + 1].cols(0, cat_ch[j + 1]);
-        else { last = fresh(cx, nb * H * W, n->out_blocks[j].cout); dst = last; }
+        else { last = fresh_st(cx, nb, nb * H * W, n->out_blocks[j].cout); dst = last; }
         h = run_block(cx, n->out_blocks[j], in, emb, dst);
     }
     // out = conv3x3(SiLU(GN(h)))  (openaimodel.py:312-316,371)

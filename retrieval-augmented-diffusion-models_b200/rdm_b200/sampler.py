@@ -35,6 +35,7 @@ def make_ddim_tables(alphas_cumprod, S, eta=0.0, device="cpu"):
     s1m = np.sqrt(1.0 - alphas)
     f32 = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), dtype=torch.float32)
     a_t, a_prev, sg, s1 = f32(alphas), f32(alphas_prev), f32(sigmas), f32(s1m)
+    S = len(ts)                                           # range(0, T, T // S) has MORE than S entries when S does not divide T (e.g. 6 -> 7, 30 -> 31): the reference runs them all (ddim.py:164)
     coef = torch.zeros(S, 8, dtype=torch.float32)
     coef[:, 0], coef[:, 1], coef[:, 2] = s1, a_t.sqrt(), a_prev.sqrt()
     coef[:, 3], coef[:, 4] = (1.0 - a_prev - sg ** 2).sqrt(), sg

@@ -116,3 +116,15 @@ def test_ddim_sampler_schedule_buffers_match_the_oracle():
     ref = oddim.Schedule(100)
     assert np.array_equal(s.ddim_timesteps, ref.timesteps) and np.array_equal(np.asarray(s.ddim_alphas), ref.alphas)
     assert np.array_equal(np.asarray(s.ddim_alphas_prev), ref.alphas_prev) and np.array_equal(np.asarray(s.ddim_sqrt_one_minus_alphas), ref.sqrt_one_minus_alphas)
+
+
+def test_ddim_tables_for_step_counts_that_do_not_divide_the_schedule():
+    """`make_ddim_timesteps` is `range(0, T, T // S)` (ldm util): 6 requested steps give 7, 30 give 31 -- the reference runs them all
+    (ddim.py:164, `total_steps = timesteps.shape[0]`).  Found by tests/test_script_flow_gpu.py (`--steps 6`)."""
+    from oracle import ddim as oddim
+    from rdm_b200 import sampler
+    for S, n in ((6, 7), (30, 31), (100, 100), (250, 250)):
+        tb = sampler.make_ddim_tables(sampler.alphas_cumprod_linear(), S, 0.0)
+        sch = oddim.Schedule(S, 0.0)
+        assert tb["timesteps"].shape == (n,) and tb["coef"].shape == (n, 8)
+        assert np.array_equal(tb["timesteps"].numpy(), np.flip(sch.timesteps).astype(np.int64))

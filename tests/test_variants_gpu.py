@@ -13,8 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = {"0": 1e-4, "1": 1e-4, "3": 3e-3, "4": 4e-3}          # same per-forward tolerances as tests/test_unet_gpu.py
 
 
-@pytest.mark.parametrize("env", [{"RDM_TC_CLUSTER": "0"}, {"RDM_TC_CLUSTER": "2"}, {"RDM_SKIP": "64"}, {"RDM_PDL": "0"}, {"RDM_TC_NOSPLIT": "1"}],
-                         ids=["splitk-reduce-kernel", "splitk-cluster-dsmem", "unfused-cross-attention", "no-pdl", "no-splitk"])
+@pytest.mark.parametrize("env", [{"RDM_TC_CLUSTER": "1"}, {"RDM_TC_CLUSTER": "2"}, {"RDM_SKIP": "64"}, {"RDM_PDL": "0"}, {"RDM_TC_NOSPLIT": "1"}, {"RDM_GN_EPI_STATS": "1"}, {"RDM_GN_CLUSTER": "1"}],
+                         ids=["splitk-cost-model-with-clusters", "splitk-cluster-dsmem", "unfused-cross-attention", "no-pdl", "no-splitk", "gn-epilogue-statistics", "gn-cluster-kernel"])
 def test_engine_variant_matches_oracle(cuda, env):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "variant_check.py"), "1,3"], env=dict(os.environ, **env),
                        capture_output=True, text=True, timeout=600)

@@ -1,0 +1,102 @@
+"""Turns the ncu / sanitizer outputs of tools/evidence.sh (gpurun_out/, scratch) into the tracked summaries under profiles/.
+python tools/evidence_summarise.py r2"""
+import collections
+import csv
+import io
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1, "us": 1e3, "ms": 1e6}
+METRICS = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread", "gpu__time_duration.sum",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
+           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+           "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum"]
+
+
+def short(name):
+    return re.sub(r"void |<unnamed>::|\(anonymous namespace\)::", "", name).split("(")[0][:64]
+
+
+def gemm_traffic():
+    src = os.path.join(G, f"gemm_tc_dram_{tag}.csv")
+    rows = list(csv.DictReader([l for l in open(src) if not l.startswith("==")]))
+    tot, ids = collections.Counter(), set()
+    for x in rows:
+        tot[x["Metric Name"]] += float(x["Metric Value"].replace(",", "")) * SCALE.get(x["Metric Unit"], 1)
+        ids.add(x["ID"])
+    n = len(ids)
+    per_fwd = (tot["dram__bytes_read.sum"] + tot["dram__bytes_write.sum"]) * 197 / n
+    shutil.copy(src, os.path.join(P, f"gemm_tc_dram_{tag}.csv"))
+    out = {"bytes_per_forward": per_fwd, "launches_captured": n, "dram_read_bytes": tot["dram__bytes_read.sum"], "dram_write_bytes": tot["dram__bytes_write.sum"],
+           "sum_gpu_time_ms": tot["gpu__time_duration.sum"] / 1e6,
+           "how": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:gemm_tc_kernel over {n} of the 197 tcgen05 GEMM launches of one full-architecture forward "
+                  f"(B2 = 32, fp16 mode), scaled by 197/{n}; profiles/gemm_tc_dram_{tag}.csv; every launch is replayed with a flushed L2, so activations that are L2 hits in "
+                  "the running step count as DRAM reads here (an upper bound of the in-step traffic)"}
+    json.dump(out, open(os.path.join(P, f"gemm_tc_dram_{tag}.json"), "w"), indent=1)
+    print("traffic", out["bytes_per_forward"] / 1e9, "GB per forward from", n, "launches")
+
+
+def launches(name, title, skip):
+    src = os.path.join(G, f"launches_{name}_{tag}.csv")
+    shutil.copy(src, os.path.join(P, f"launches_{name}_{tag}.csv"))
+    rows = list(csv.DictReader([l for l in open(src) if not l.startswith("==")]))
+    rows = rows[int(len(rows) * skip):]
+    agg = collections.OrderedDict()
+    for r in rows:
+        a = agg.setdefault(short(r["Kernel Name"]), [0, 0.0]); a[0] += 1; a[1] += float(r["Metric Value"].replace(",", ""))
+    tot = sum(v[1] for v in agg.values())
+    with open(os.path.join(P, f"launches_{name}_{tag}.md"), "w") as f:
+        f.write(f"# {title}\n\n{len(rows)} launches, {tot / 1e6:.3f} ms total (cold-cache, serialised under ncu: compare SHARES)\n\n| kernel | launches | us | share | us / launch |\n|---|---|---|---|---|\n")
+        for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k}` | {c} | {t / 1e3:.1f} | {100 * t / tot:.1f}% | {t / 1e3 / c:.2f} |\n")
+
+
+def raw_table(rep, title, how, f, pick=None, stalls=True):
+    out = subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    if pick:
+        data = [data[i] for i in pick if i < len(data)]
+    ki = hdr.index("Kernel Name")
+    f.write(f"\n## {title}\n\n`{how}`\n\n| metric | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |\n|---|" + "---|" * len(data) + "\n")
+    f.write("| kernel | " + " | ".join(f"`{short(d[ki])}`" for d in data) + " |\n")
+    for m in METRICS:
+        if m in hdr:
+            i = hdr.index(m)
+            f.write(f"| `{m}` [{units[i]}] | " + " | ".join(d[i] for d in data) + " |\n")
+    if stalls:
+        st = [i for i, h in enumerate(hdr) if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
+        top = sorted(st, key=lambda i: -max(float(d[i] or 0) for d in data))[:6]
+        for i in top:
+            f.write(f"| stall `{hdr[i][len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]}` [warps / issue] | " + " | ".join(f"{float(d[i] or 0):.2f}" for d in data) + " |\n")
+
+
+gemm_traffic()
+launches("bench", "ncu launch list: `ncu --metrics gpu__time_duration.sum --clock-control none -c 3000` over `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-r-shape` "
+         "(database build, kNN, context K/V, the first DDIM steps of the fp16 engine; last 80 % of the list)", 0.2)
+launches("rarm", "ncu launch list of the RARM decode loop: `ncu --metrics gpu__time_duration.sum -k regex:rarm_ --launch-skip 600 -c 300` over `python tools/rarm_bench.py` "
+         "(two decode steps of the ImageNet-size model, batch 4, fp16 weights)", 0.0)
+with open(os.path.join(P, f"ncu_summary_{tag}.md"), "w") as f:
+    f.write(f"# ncu `--set full --clock-control none --import-source on` captures, round 2 (B200, sm_100a)\n\nRaw reports stay in `gpurun_out/` (scratch); the tables are "
+            "`ncu -i <rep> --page raw --csv` of those files (tools/evidence.sh, tools/evidence_summarise.py).  Durations are cold-cache, serialised ncu replays.\n")
+    if os.path.exists(os.path.join(G, "gemm_tc_r2g.ncu-rep")):
+        raw_table("gemm_tc_r2g.ncu-rep", "gemm_tc_kernel (fp16 mode, one MMA per product): 12 consecutive launches of a graph-replayed full-architecture forward (B2 = 32)",
+                  "ncu --set full -k regex:gemm_tc_kernel --launch-skip 203 --launch-count 12 python tools/profile_forward.py 4 1  [before the epilogue rework of this round: "
+                  "launch 0 = level-0 3x3 conv M = 32768; 1-9 level-1 layers incl. the fused cross-attention (8) ; 10 = GEGLU feed-forward]", f)
+    raw_table(f"glue_{tag}.ncu-rep", "glue kernels of the forward: GroupNorm statistics / apply, LayerNorm, warp-MMA self-attention",
+              "ncu --set full -k regex:'gn_stats|gn_apply|layernorm_kernel|attention_mma' --launch-skip 300 --launch-count 8 python tools/profile_forward.py 4 1", f)
+    raw_table(f"rarm_{tag}.ncu-rep", "RARM decode step: weight-streaming GEMV (`rarm_gemv_kernel`) and cached attention (`rarm_attn_kernel`)",
+              "ncu --set full -k regex:'rarm_gemv|rarm_attn' --launch-skip 600 --launch-count 9 python tools/rarm_bench.py", f)
+    raw_table(f"knn_{tag}.ncu-rep", "one exact kNN search, fp16 database 1,281,167 x 512, 16 queries, k = 4 (normalise + fused tensor-core scan + select + conditional fallback pair)",
+              "ncu --set full -k regex:knn_ --launch-skip 12 --launch-count 6 python tools/knn_sweep.py --n 1281167 --q 16 --dtypes float16", f)
+shutil.copy(os.path.join(G, f"sanitize_{tag}.log"), os.path.join(P, f"sanitize_{tag}.log"))
+with open(os.path.join(P, f"sass_histogram_{tag}.md"), "w") as f:
+    f.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_histogram.py")], capture_output=True, text=True).stdout)
+print("done")
