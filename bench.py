@@ -168,7 +168,7 @@ def cpu_reference_images_per_sec(ddim_steps, reps=1, threads=None):
     return 1.0 / t_img, dict(sec_per_image=t_img, sec_per_ddim_step=t_step, knn_sec_extrapolated=t_knn)
 
 
-def run_reference(args):
+def run_reference(args, out=sys.stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -185,13 +185,13 @@ def run_reference(args):
     ms = (time.time() - t0) * 1e3 / max(1, args.steps)
     v = float(np.median(vals))
     sample = "per step: 2 DDIM steps (CFG, B2=2) of 1 image on the torch-CPU oracle + C kNN oracle over 100K rows, EXTRAPOLATED to DDIM-100 / 1.28M rows"
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    print(file=out, flush=True, *[json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": "cfg2 RDM ImageNet-arch 32x32x4, DDIM-100, CFG 2.0, k=4 over 1,281,167x512 fp16 DB (CPU oracle port; reference not installable)",
                                  "extrapolated": True, "extrapolation": "value = 1 / (100 x measured seconds per guided DDIM step of one image + C kNN oracle seconds over 100K rows x 12.8); "
                                                                         "the reference cannot run this path on a CUDA-less host at all (DDIMSampler.register_buffer forces cuda, SURVEY F6)"},
                       "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
-                      "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                      "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})])
 
 
 # ------------------------------------------------------------------------------------------------ the drop-in model (reference API)
@@ -228,6 +228,15 @@ def build_dropin(unet_cfg, sd, searcher, mode, chains, dev):
     return model
 
 
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: whatever else is printed there by libraries during the run (NCCL's version banner at
+    communicator creation, progress lines of the reference-facing API) is routed to stderr; returns the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -243,8 +252,9 @@ def main():
     ap.add_argument("--no-r-shape", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
+    out = claim_stdout()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import torch.distributed as dist
     from rdm_b200 import _lib, sampler
@@ -481,7 +491,8 @@ def main():
                              "same graph without the GEMM launches, CUDA events); whole_step_* = algorithmic FLOPs of the timed step over its wall time, "
                              "everything included (glue kernels, kNN, chains overlap)"},
         "knn": {"ms": knn_ms, "qps": BATCH / knn_ms * 1e3, "gbs": knn_gbs, "frac_hbm": knn_gbs / pk["hbm_gbs"], "peak_gbs": pk["hbm_gbs"], "rows": hi - lo,
-                "what": "rdm_knn_search_raw: 16 raw queries, k = 4, normalisation + scans + exact re-rank, this GPU's rows"},
+                "what": "rdm_knn_search_raw: 16 raw queries, k = 4, normalisation + scans + exact re-rank, this GPU's rows; peak = the measured COPY bandwidth "
+                        "(read + write), so a read-only scan of a large shard can exceed 1.0"},
     }
     if r_shape is not None:
         line["r_shape"] = r_shape
@@ -495,7 +506,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": "4 DDIM steps (CFG, B2=2) of 1 image on the torch-CPU fp32 oracle + C kNN oracle over 100K rows, extrapolated to DDIM-100 / 1.28M rows",
                                 **info}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -52,6 +52,41 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B
     if ((dim & 1) && j == 0) out[(size_t)b * dim + dim - 1] = 0.f;
 }
 
+// First convolution of the U-Net (openaimodel.py:141-145: conv_nd(dims, in_channels, model_channels, 3, padding=1) with 3 or 4 input
+// channels): K = 9 * Cin <= 36 is far too short for either GEMM engine (the generic CUDA-core engine took 65 us for 0.45 GFLOP at 32x32,
+// B2 = 32 -- 1.4 % of the forward).  Direct form: the weights [Cout][tap][Cin] are re-laid as [tap * Cin][Cout] in shared memory once per
+// CTA; a thread owns one pixel x 4 output channels (consecutive threads -> consecutive channel groups: coalesced 16-byte stores, the 9
+// input taps are broadcast loads); the CTA walks PIX pixels per round.
+template <int PIX>
+__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, int ld, int Cin, int B, int H, int W, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, int Cout, float* __restrict__ out, int out_ld) {
+    extern __shared__ float s_w[];                       // [9 * Cin][Cout]
+    const int K = 9 * Cin, G = Cout / 4;
+    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) { const int o = i / K, k = i - o * K; s_w[k * Cout + o] = w[i]; }
+    __syncthreads();
+    const long long M = (long long)B * H * W;
+    const long long p0 = (long long)blockIdx.x * PIX;
+    for (int it = threadIdx.x; it < PIX * G; it += blockDim.x) {
+        const long long m = p0 + it / G;
+        if (m >= M) break;
+        const int cg = (it % G) * 4;
+        const int px = (int)(m % W), py = (int)((m / W) % H);
+        float4 acc = bias ? *reinterpret_cast<const float4*>(bias + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int tap = 0; tap < 9; tap++) {
+            const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+            if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+            const float* xi = x + (m + (long long)(tap / 3 - 1) * W + (tap % 3 - 1)) * ld;
+            for (int c = 0; c < Cin; c++) {
+                const float v = xi[c];
+                const float4 ww = *reinterpret_cast<const float4*>(s_w + (tap * Cin + c) * Cout + cg);
+                acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y); acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
+            }
+        }
+        *reinterpret_cast<float4*>(out + m * out_ld + cg) = acc;
+    }
+}
+
 // grid (row_chunks, B).  Thread t owns the float4 column v = t % V for the whole kernel and walks rows slot, slot+nslots, ...
 // (consecutive threads -> consecutive 16-byte pieces of a row: coalesced), keeping its 4 channel sums in fp64 registers; one
 // shared-memory atomic per touched group per thread at the end, then fp64 atomics to the global accumulators.
@@ -497,6 +532,14 @@ int k_nhwc_to_nchw(View in, int B, int C, int H, int W, float* out, cudaStream_t
 }
 int k_timestep_embedding(const long long* t, int B, int dim, float* out, cudaStream_t st) {
     timestep_embedding_kernel<<<blocks_for((long long)B * (dim / 2), 128), 128, 0, st>>>(t, B, dim, out);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+bool k_conv_first_supported(int Cin, int Cout) { return Cin >= 1 && Cin <= 4 && Cout % 4 == 0 && (size_t)9 * Cin * Cout * 4 <= 48 * 1024; }
+int k_conv_first(View x, int B, int H, int W, const float* w, const float* bias, int Cout, View out, cudaStream_t st) {
+    RDM_REQUIRE(k_conv_first_supported(x.C, Cout) && out.ld % 4 == 0, RDM_ERR_UNSUPPORTED, "conv_first: Cin=%d Cout=%d", x.C, Cout);
+    constexpr int PIX = 64;
+    const long long M = (long long)B * H * W;
+    conv_first_kernel<PIX><<<(unsigned)((M + PIX - 1) / PIX), 256, (size_t)9 * x.C * Cout * sizeof(float), st>>>(x.p, x.ld, x.C, B, H, W, w, bias, Cout, out.p, out.ld);
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_gn_stats(View x, int B, int HW, int groups, double* sums, cudaStream_t st) {

@@ -92,6 +92,9 @@ int k_nchw_to_nhwc(const float* x, int Bsrc, int Bout, int C, int H, int W, View
 int k_nhwc_to_nchw(View in, int B, int C, int H, int W, float* out, cudaStream_t st);
 // timestep_embedding (ldm util): t int64 [B] -> [B, dim] = [cos | sin]
 int k_timestep_embedding(const long long* t, int B, int dim, float* out, cudaStream_t st);
+// first convolution (3x3, pad 1, stride 1, Cin <= 4): direct CUDA-core form, out = conv(x) + bias in fp32.  w: [Cout][9][Cin] (tap-major K)
+bool k_conv_first_supported(int Cin, int Cout);
+int k_conv_first(View x, int B, int H, int W, const float* w, const float* bias, int Cout, View out, cudaStream_t st);
 // GroupNorm statistics: sums[b][g] = (sum, sumsq) in fp64 (buffer must be zeroed), over x [B*HW, C]
 int k_gn_stats(View x, int B, int HW, int groups, double* sums, cudaStream_t st);
 // y = (x-mean)*rstd*gamma+beta, optional SiLU; y is a contiguous-or-strided fp32 view

@@ -33,7 +33,7 @@ constexpr int LIST = 32;          // candidates kept per query (one per lane)
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 constexpr int MAX_QP = 16;        // queries per CUDA-core scan pass
-constexpr int MAX_TCQ = 64;       // queries per tensor-core pass (fp16 databases)
+constexpr int MAX_TCQ = 128;      // queries per tensor-core pass (fp16 databases): 128 with the fused hi-only scan, 64 on the three-kernel path
 constexpr int QHAT_ROWS = 1024;   // rdm_knn_search_raw normalises (and searches) this many raw queries at a time
 constexpr unsigned FULL = 0xffffffffu;
 typedef unsigned long long u64;
@@ -52,9 +52,9 @@ __device__ __forceinline__ u64 make_key(float s, uint32_t idx) { return ((u64)or
 // row can still be one of the exact top-k, the comparison is relaxed by 2e: with f_k the k-th largest fp32 score seen, every row of the exact top-k has an fp32 score >= f_k - 2e.
 // (Without the slack, a cluster of near-duplicate rows -- scores closer than the fp32 rounding -- could push true neighbours out.)
 constexpr float SCORE_SLACK = 3e-5f;
-__device__ __forceinline__ u64 relax_key(u64 key) {         // key of (score - slack) with the row part cleared; 0 stays "keep everything"
+__device__ __forceinline__ u64 relax_key(u64 key, float slack = SCORE_SLACK) {         // key of (score - slack) with the row part cleared; 0 stays "keep everything"
     if (key == 0ull) return 0ull;
-    return (u64)order_f32(unorder_f32((uint32_t)(key >> 32)) - SCORE_SLACK) << 32;
+    return (u64)order_f32(unorder_f32((uint32_t)(key >> 32)) - slack) << 32;
 }
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(1024)
 knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const unsigned* __restrict__ cand_cnt, unsigned* __restrict__ overflow,
                   const T* __restrict__ db, const float* __restrict__ inv,
                   long long n, const float* __restrict__ q, int k, long long idx_base,
-                  long long* __restrict__ idx_out, float* __restrict__ dist_out, double* __restrict__ score_out) {
+                  long long* __restrict__ idx_out, float* __restrict__ dist_out, double* __restrict__ score_out, float slack) {
     __shared__ u64 s_keys[32][LIST];
     __shared__ float s_q[D];
     __shared__ u64 s_cand[SEL_MAX];
@@ -460,7 +460,7 @@ knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const unsigne
     cur = cta_tree_merge(cur, s_keys, warp, lane, 32);          // warp 0: lane i holds the i-th largest fp32 key
     if (warp == 0) {
         const u64 kth = __shfl_sync(FULL, cur, k - 1);           // 0 when fewer than k survivors exist: keep everything
-        if (lane == 0) s_cut = relax_key(kth);
+        if (lane == 0) s_cut = relax_key(kth, slack);            // slack of the scan that produced the candidates (hi-only tensor-core passes: 1.05e-3)
         if (FROM_LISTS) { s_cand[lane] = cur; if (lane == 0) s_ncand = 32u; }
     }
     __syncthreads();
@@ -766,7 +766,7 @@ int launch_scan(rdm_knn* h, const float* q, int nq_valid, ScanArgs args, cudaStr
 }
 
 template <typename T, int D, bool FROM_LISTS>
-int launch_select(rdm_knn* h, int nq, const u64* lists, int nblk, int QP, const float* qp, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st) {
+int launch_select(rdm_knn* h, int nq, const u64* lists, int nblk, int QP, const float* qp, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st, float slack = SCORE_SLACK) {
     auto kern = knn_select_kernel<T, D, FROM_LISTS>;
     static bool configured[16] = {false};
     if (!configured[h->device & 15]) {
@@ -775,7 +775,7 @@ int launch_select(rdm_knn* h, int nq, const u64* lists, int nblk, int QP, const 
     }
     unsigned* overflow = h->cand_cnt + MAX_TCQ;
     RDM_CHECK_CUDA(launch_chained(kern, dim3(nq), dim3(1024), (size_t)SelCfg<T, D>::DYN_BYTES, st, lists, nblk, QP, (const unsigned*)h->cand_cnt, overflow, (const T*)h->db,
-                                  (const float*)h->inv, (long long)h->n, qp, k, (long long)h->idx_base, idx_out, dist_out, sc_out));
+                                  (const float*)h->inv, (long long)h->n, qp, k, (long long)h->idx_base, idx_out, dist_out, sc_out, slack));
     RDM_COUNT_LAUNCH();
     RDM_CHECK_CUDA(cudaGetLastError());
     return RDM_OK;
@@ -810,9 +810,16 @@ int search_pass_tc(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_o
     // one cooperative launch (sample phase -> grid barrier -> thresholds -> main scan) where the database is large enough for it;
     // otherwise (or with RDM_KNN_NO_FUSED) the three-kernel sequence: sample scan, threshold kernel, main scan
     static const bool no_fused = getenv("RDM_KNN_NO_FUSED") != nullptr;
-    int fused = no_fused ? 1 : knn_scan_tc_fused(h->db, h->inv, h->n, h->device, qp, cnt, k, h->qsplit, h->cand, h->cand_cnt, overflow, h->fused_ws, presplit, st);
+    float slack = SCORE_SLACK;
+    int fused = no_fused ? 1 : knn_scan_tc_fused(h->db, h->inv, h->n, h->device, qp, cnt, k, h->qsplit, h->cand, h->cand_cnt, overflow, h->fused_ws, presplit, &slack, st);
     if (fused < 0) return fused;
+    if (fused != RDM_OK && cnt > 64) {                    // the three-kernel path takes at most 64 queries: two half passes (they split the queries themselves)
+        const int half = 64;
+        RDM_TRY((search_pass_tc<T, D>(h, qp, half, k, idx_out, dist_out, sc_out, st, 0)));
+        return search_pass_tc<T, D>(h, qp + (size_t)half * D, cnt - half, k, idx_out + (size_t)half * k, dist_out + (size_t)half * k, sc_out ? sc_out + (size_t)half * k : nullptr, st, 0);
+    }
     if (fused != RDM_OK) {
+        slack = SCORE_SLACK;
         const long long ntiles = (h->n + 127) / 128;
         int stride = (int)(ntiles / 512); if (stride > 16) stride = 16; if (stride < 1) stride = 1;       // >= ~64K sampled rows
         const long long per_q = knn_tc_sample_rows(h->n, stride);
@@ -822,7 +829,7 @@ int search_pass_tc(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_o
         RDM_COUNT_LAUNCH();
         RDM_TRY(knn_scan_tc(h->db, h->inv, h->n, h->device, qp, cnt, h->qsplit, 0, 1, nullptr, 0, h->thr_key, h->cand, h->cand_cnt, st));
     }
-    RDM_TRY((launch_select<T, D, false>(h, cnt, h->cand, 0, MAX_QP, qp, k, idx_out, dist_out, sc_out, st)));
+    RDM_TRY((launch_select<T, D, false>(h, cnt, h->cand, 0, MAX_QP, qp, k, idx_out, dist_out, sc_out, st, slack)));
     // device-side conditional fallback: ONE launch pair for all groups of 16 queries (blockIdx.y = group); normally two empty launches
     int g2 = 0;
     ScanArgs f{}; f.group_stride = 1; f.lists_out = h->lists; f.overflow = overflow; f.nq_total = cnt;

@@ -21,12 +21,21 @@ typedef unsigned long long u64;
 constexpr int TM = 128, TK = 64, D = 512, KB = D / TK, EPI_WARPS = 8, EPI_PER_Q = EPI_WARPS / 4, THREADS = 64 + EPI_WARPS * 32;      // warp 0 TMA, warp 1 MMA, two epilogue warps per TMEM lane quarter (4 -> 8 warps: 20 M rows x 64 queries 54 % -> 72 % of HBM peak; 16 warps measured no better)
 constexpr int A_BYTES = TM * TK * 2;
 constexpr int CAND_CAP = 2048;
-template <int NQ> struct Cfg {
-    static constexpr int NCOL = 2 * NQ, B_KB_BYTES = NCOL * TK * 2, B_BYTES = KB * B_KB_BYTES;
-    static constexpr int STAGES = NQ <= 16 ? 8 : NQ <= 32 ? 6 : 4;      // (6 stages fit for 64 queries too, but measured no faster: that case is bound by the epilogue / MMA, not by bytes in flight)
+constexpr int MAX_FUSED_Q = 128;                    // queries per fused pass (= MAX_TCQ of knn.cu)
+// HILO: the queries are resident as fp16 hi + lo rows (q = hi + lo + O(2^-22): scan scores within ~1e-6 of the exact ones, score slack 3e-5);
+// !HILO (round 2, passes of more than 16 queries): hi rows only -- half the MMA work, half the TMEM columns and half the epilogue, and up to
+// 128 queries per pass.  The scan score then differs from the exact one by at most u * |q_hat| * |d_i| * inv_i = u = 2^-11 = 4.9e-4
+// (fp16 unit roundoff, Cauchy-Schwarz; plus ~1e-6 of accumulation), so the decisions of such a pass are relaxed by HI_SLACK >= 2 * that
+// bound: thresholds and the select cut admit a few more survivors, the exact fp64 re-rank of every survivor keeps the result bit-exact.
+constexpr float HILO_SLACK = 3e-5f;                  // = SCORE_SLACK of knn.cu
+constexpr float HI_SLACK = 1.05e-3f;
+template <int NQ, bool HILO> struct Cfg {
+    static constexpr int NCOL = (HILO ? 2 : 1) * NQ, B_KB_BYTES = NCOL * TK * 2, B_BYTES = KB * B_KB_BYTES;
+    static constexpr int STAGES = NCOL <= 32 ? 8 : NCOL <= 64 ? 6 : 4;      // (6 stages fit for 128 columns too, but measured no faster: that case is bound by the epilogue / MMA, not by bytes in flight)
     static constexpr int SMEM_TOTAL = STAGES * A_BYTES + B_BYTES + 1024 + 1024;
     static_assert(SMEM_TOTAL <= 232448, "kNN tensor-core scan: shared-memory budget");
     static constexpr int TMEM_COLS = 2 * NCOL <= 64 ? 64 : 2 * NCOL <= 128 ? 128 : 256;
+    static_assert(2 * NCOL <= 256, "two accumulator buffers");
 };
 
 __device__ __forceinline__ uint32_t order_f32(float f) { uint32_t b = __float_as_uint(f); return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
@@ -52,7 +61,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 knn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ inv, long long n,
                    int nq_valid, const u64* __restrict__ thr_key, u64* __restrict__ cand, unsigned* __restrict__ cand_cnt,
                    int tile_stride, u64* __restrict__ maxima, long long per_q) {
-    constexpr int NCOL = Cfg<NQ>::NCOL, B_KB_BYTES = Cfg<NQ>::B_KB_BYTES, B_BYTES = Cfg<NQ>::B_BYTES, STAGES = Cfg<NQ>::STAGES;
+    constexpr int NCOL = Cfg<NQ, true>::NCOL, B_KB_BYTES = Cfg<NQ, true>::B_KB_BYTES, B_BYTES = Cfg<NQ, true>::B_BYTES, STAGES = Cfg<NQ, true>::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sB = smem + STAGES * A_BYTES;
@@ -77,7 +86,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     if (!SAMPLE && threadIdx.x < NQ) { u64 k = thr_key[threadIdx.x]; s_thr[threadIdx.x] = k == 0ull ? -CUDART_INF_F : unorder_f32((uint32_t)(k >> 32)); }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg<NQ>::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg<NQ, true>::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -187,7 +196,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg<NQ>::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg<NQ, true>::TMEM_COLS) : "memory");
     }
 }
 
@@ -202,14 +211,13 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // score slack like before.  The main phase then scans every tile (the sample tiles again: they are L2 hits) and appends the survivors.
 // Expected survivors per query ~ k_eff * n / (32 * t_sample * 4 * grid); the host sizes t_sample for ~512.
 constexpr int FUSED_MAXV = 20;                       // group maxima per lane in the threshold bisection: 4 * grid <= 32 * FUSED_MAXV
-constexpr float FUSED_SLACK = 3e-5f;                 // = SCORE_SLACK of knn.cu
 
-template <int NQ>
+template <int NQ, bool HILO>
 __global__ void __launch_bounds__(THREADS, 1)
 knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ inv, long long n,
                       int nq_valid, int k_eff, int t_sample, u64* __restrict__ cand, unsigned* __restrict__ cand_cnt, unsigned* __restrict__ overflow,
-                      uint32_t* __restrict__ gmax, unsigned* __restrict__ grid_bar) {
-    constexpr int NCOL = Cfg<NQ>::NCOL, B_KB_BYTES = Cfg<NQ>::B_KB_BYTES, B_BYTES = Cfg<NQ>::B_BYTES, STAGES = Cfg<NQ>::STAGES;
+                      uint32_t* __restrict__ gmax, unsigned* __restrict__ grid_bar, float slack) {
+    constexpr int NCOL = Cfg<NQ, HILO>::NCOL, B_KB_BYTES = Cfg<NQ, HILO>::B_KB_BYTES, B_BYTES = Cfg<NQ, HILO>::B_BYTES, STAGES = Cfg<NQ, HILO>::STAGES;
     constexpr int NGRP = (NQ / 16 + EPI_PER_Q - 1) / EPI_PER_Q;          // 16-query groups per epilogue warp
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -237,7 +245,7 @@ knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg<NQ>::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg<NQ, HILO>::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -319,7 +327,7 @@ knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
                 // thresholds: CTA c answers queries c, c + grid, ... (one warp each): the k_eff-th largest of the 4 * grid group maxima by a
                 // warp-wide bisection over the ordered scores; a second grid barrier publishes them to every CTA
-                float* thr_out = reinterpret_cast<float*>(gmax + (size_t)64 * G4);
+                float* thr_out = reinterpret_cast<float*>(gmax + (size_t)MAX_FUSED_Q * G4);
                 for (int qi = blockIdx.x + ew * gridDim.x; qi < nq_valid; qi += EPI_WARPS * gridDim.x) {
                     uint32_t v[FUSED_MAXV];
 #pragma unroll
@@ -334,7 +342,7 @@ knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         cnt = __reduce_add_sync(0xffffffffu, cnt);
                         if (cnt >= (unsigned)k_eff) res = c;
                     }
-                    if (lane == 0) thr_out[qi] = res == 0u ? -CUDART_INF_F : unorder_f32(res) - FUSED_SLACK;      // fewer than k_eff sampled rows: keep everything
+                    if (lane == 0) thr_out[qi] = res == 0u ? -CUDART_INF_F : unorder_f32(res) - slack;      // fewer than k_eff sampled rows: keep everything
                 }
                 __threadfence();
                 asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
@@ -375,10 +383,15 @@ knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                              : "r"(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NCOL + q0)));
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                             : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                             : "r"(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NCOL + NQ + q0)));
+                if (HILO) {
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                                 : "r"(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * NCOL + NQ + q0)));
+                } else {
+#pragma unroll
+                    for (int j = 16; j < 32; j++) r[j] = 0u;             // +0.0f: the lo products of a hi-only pass
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (q0 + 16 * EPI_PER_Q >= NQ) {                                // this warp's last read of the accumulator: hand it back to the MMA warp
                     tc_fence_before();
@@ -427,7 +440,7 @@ knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg<NQ>::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg<NQ, HILO>::TMEM_COLS) : "memory");
     }
 }
 
@@ -459,44 +472,44 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const float* inv, long 
     auto kern = knn_scan_tc_kernel<NQ, SAMPLE>;
     static bool configured[16] = {false};
     if (!configured[device & 15]) {
-        RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NQ>::SMEM_TOTAL));
+        RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NQ, true>::SMEM_TOTAL));
         configured[device & 15] = true;
     }
     const long long ntiles_all = (n + TM - 1) / TM, items = SAMPLE ? (ntiles_all + tile_stride - 1) / tile_stride : ntiles_all;
     const int sms = rdm_num_sms(device);
-    kern<<<(int)(items < sms ? items : sms), THREADS, Cfg<NQ>::SMEM_TOTAL, st>>>(ta, tb, inv, n, nq_valid, thr_key, cand, cand_cnt, tile_stride, maxima, per_q);
+    kern<<<(int)(items < sms ? items : sms), THREADS, Cfg<NQ, true>::SMEM_TOTAL, st>>>(ta, tb, inv, n, nq_valid, thr_key, cand, cand_cnt, tile_stride, maxima, per_q);
     RDM_COUNT_LAUNCH();
     RDM_CHECK_CUDA(cudaGetLastError());
     return RDM_OK;
 }
 
 
-template <int NQ>
+template <int NQ, bool HILO>
 int launch_fused(const CUtensorMap& ta, const CUtensorMap& tb, const float* inv, long long n, int device, int nq_valid, int k_eff, int t_sample,
-                 u64* cand, unsigned* cand_cnt, unsigned* overflow, uint32_t* gmax, unsigned* grid_bar, int grid, cudaStream_t st) {
-    auto kern = knn_scan_fused_kernel<NQ>;
+                 u64* cand, unsigned* cand_cnt, unsigned* overflow, uint32_t* gmax, unsigned* grid_bar, int grid, float slack, cudaStream_t st) {
+    auto kern = knn_scan_fused_kernel<NQ, HILO>;
     static int ok[16] = {0};                          // 0 unknown, 1 usable, -1 not (no cooperative launch / grid does not fit)
     if (ok[device & 15] == 0) {
-        RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NQ>::SMEM_TOTAL));
+        RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NQ, HILO>::SMEM_TOTAL));
         int coop = 0, per_sm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, Cfg<NQ>::SMEM_TOTAL);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, Cfg<NQ, HILO>::SMEM_TOTAL);
         ok[device & 15] = (coop && per_sm >= 1) ? 1 : -1;
     }
     if (ok[device & 15] < 0) return 1;                // caller falls back to the three-kernel path
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = Cfg<NQ>::SMEM_TOTAL; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = Cfg<NQ, HILO>::SMEM_TOTAL; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;      // every CTA resident at once: the in-kernel grid barrier cannot deadlock
     cfg.attrs = attr; cfg.numAttrs = 1;
-    RDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, inv, n, nq_valid, k_eff, t_sample, cand, cand_cnt, overflow, gmax, grid_bar));
+    RDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, inv, n, nq_valid, k_eff, t_sample, cand, cand_cnt, overflow, gmax, grid_bar, slack));
     RDM_COUNT_LAUNCH();
     return RDM_OK;
 }
 }  // namespace
 
-int knn_tc_queries_bytes() { return 2 * 64 * D * (int)sizeof(__half); }
-int knn_tc_pass_queries(int nq) { return nq <= 16 ? 16 : nq <= 32 ? 32 : 64; }
+int knn_tc_queries_bytes() { return 2 * MAX_FUSED_Q * D * (int)sizeof(__half); }      // hi rows [0, NQ), lo rows [NQ, 2 NQ), NQ <= 128
+int knn_tc_pass_queries(int nq) { return nq <= 16 ? 16 : nq <= 32 ? 32 : nq <= 64 ? 64 : 128; }
 long long knn_tc_sample_rows(long long n, int tile_stride) { long long t = (n + TM - 1) / TM; return ((t + tile_stride - 1) / tile_stride) * TM; }
 
 int knn_scan_tc(const void* db_f16, const float* inv, long long n, int device, const float* q, int nq_valid, void* qsplit_ws, int sample, int tile_stride,
@@ -518,16 +531,16 @@ int knn_scan_tc(const void* db_f16, const float* inv, long long n, int device, c
 #undef KNN_TC_GO
 }
 
-// [64 queries][4 * grid] group maxima | [64] thresholds | grid-barrier counter
-size_t knn_tc_fused_ws_bytes(int device) { return (size_t)64 * 4 * rdm_num_sms(device) * sizeof(uint32_t) + 64 * sizeof(float) + 256; }
+// [128 queries][4 * grid] group maxima | [128] thresholds | grid-barrier counter
+size_t knn_tc_fused_ws_bytes(int device) { return (size_t)MAX_FUSED_Q * 4 * rdm_num_sms(device) * sizeof(uint32_t) + MAX_FUSED_Q * sizeof(float) + 256; }
 unsigned* knn_tc_fused_grid_bar(void* fused_ws, int device) {
-    return reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(fused_ws) + (size_t)64 * 4 * rdm_num_sms(device) * sizeof(uint32_t) + 64 * sizeof(float));
+    return reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(fused_ws) + (size_t)MAX_FUSED_Q * 4 * rdm_num_sms(device) * sizeof(uint32_t) + MAX_FUSED_Q * sizeof(float));
 }
 
 // Returns RDM_OK, an error code, or 1 when the fused path is not usable here (database too small for a sample, no cooperative launch).
 int knn_scan_tc_fused(const void* db_f16, const float* inv, long long n, int device, const float* q, int nq_valid, int k, void* qsplit_ws,
-                      unsigned long long* cand, unsigned* cand_cnt, unsigned* overflow, void* fused_ws, int presplit, cudaStream_t st) {
-    RDM_REQUIRE(nq_valid >= 1 && nq_valid <= 64, RDM_ERR_ARG, "knn_scan_tc_fused: %d queries", nq_valid);
+                      unsigned long long* cand, unsigned* cand_cnt, unsigned* overflow, void* fused_ws, int presplit, float* slack_used, cudaStream_t st) {
+    RDM_REQUIRE(nq_valid >= 1 && nq_valid <= MAX_FUSED_Q, RDM_ERR_ARG, "knn_scan_tc_fused: %d queries", nq_valid);
     const int sms = rdm_num_sms(device);
     const long long ntiles = (n + TM - 1) / TM;
     if (ntiles < 4LL * sms || 4 * sms > 32 * FUSED_MAXV) return 1;          // a sample tile per CTA next to >= 3 more; the group maxima must fit the bisection registers
@@ -546,8 +559,18 @@ int knn_scan_tc_fused(const void* db_f16, const float* inv, long long n, int dev
     }
     CUtensorMap ta, tb;
     RDM_TRY(make_map(&ta, db_f16, n, TM));
-    RDM_TRY(make_map(&tb, qsplit_ws, 2 * NQ, 2 * NQ));
-    if (NQ == 16) return launch_fused<16>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, st);
-    if (NQ == 32) return launch_fused<32>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, st);
-    return launch_fused<64>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, st);
+    // passes of up to 16 queries keep the hi + lo query rows (HBM-bound already, tight slack); wider passes use the hi rows only
+    static const int force_hilo = getenv("RDM_KNN_HILO") ? 1 : 0;       // A/B: hi + lo rows for every pass (then <= 64 queries per pass)
+    const bool hilo = NQ == 16 || (force_hilo && NQ <= 64);
+    if (force_hilo && NQ > 64) return 1;
+    *slack_used = hilo ? HILO_SLACK : HI_SLACK;
+    RDM_TRY(make_map(&tb, qsplit_ws, hilo ? 2 * NQ : NQ, hilo ? 2 * NQ : NQ));
+    if (hilo) {
+        if (NQ == 16) return launch_fused<16, true>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, HILO_SLACK, st);
+        if (NQ == 32) return launch_fused<32, true>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, HILO_SLACK, st);
+        return launch_fused<64, true>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, HILO_SLACK, st);
+    }
+    if (NQ == 32) return launch_fused<32, false>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, HI_SLACK, st);
+    if (NQ == 64) return launch_fused<64, false>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, HI_SLACK, st);
+    return launch_fused<128, false>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, HI_SLACK, st);
 }

@@ -2,7 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 int knn_tc_queries_bytes();
-int knn_tc_pass_queries(int nq);                                  // 16, 32 or 64 query columns for a pass of nq <= 64 queries
+int knn_tc_pass_queries(int nq);                                  // 16, 32, 64 or 128 query columns for a pass of nq <= 128 queries
 long long knn_tc_sample_rows(long long n, int tile_stride);       // keys per query written by the sample pass
 // sample != 0: every tile_stride-th 128-row tile, writes maxima[q][per_q] (and prepares qsplit_ws from q).
 // sample == 0: the main scan; survivors of thr_key go to cand / cand_cnt.  q: fp32 [nq_valid, 512] normalised queries (device).
@@ -14,5 +14,7 @@ int knn_scan_tc(const void* db_f16, const float* inv, long long n, int device, c
 size_t knn_tc_fused_ws_bytes(int device);
 // presplit != 0: qsplit_ws already holds the fp16 hi / lo rows of the queries and the barrier counter was reset (fused normalisation kernel).
 int knn_scan_tc_fused(const void* db_f16, const float* inv, long long n, int device, const float* q, int nq_valid, int k, void* qsplit_ws,
-                      unsigned long long* cand, unsigned* cand_cnt, unsigned* overflow, void* fused_ws, int presplit, cudaStream_t st);
+                      unsigned long long* cand, unsigned* cand_cnt, unsigned* overflow, void* fused_ws, int presplit, float* slack_used, cudaStream_t st);
+// *slack_used: the score slack the pass decided with (hi + lo query rows: 3e-5; hi rows only, more than 16 queries: 1.05e-3) -- the select
+// kernel's cut must use the same value.  Up to 128 queries per fused pass; knn_scan_tc (the three-kernel path) takes at most 64.
 unsigned* knn_tc_fused_grid_bar(void* fused_ws, int device);

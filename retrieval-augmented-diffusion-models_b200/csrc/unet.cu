@@ -532,7 +532,12 @@ Act run_block(Ctx& cx, const Block& b, Act x, const float* emb_all, View dst) {
         const bool feeds_gn = !last && (b.layers[i + 1].kind == L_RES || b.layers[i + 1].kind == L_ST);
         View o = last ? dst : feeds_gn ? fresh_st(cx, x.B, x.B * Ho * Wo, Co) : fresh(cx, x.B * Ho * Wo, Co);
         switch (L.kind) {
-            case L_CONV_IN: { const Conv& c = n->convs[L.idx]; gemm_any(cx, from_view(x.v), x.B, x.H, x.W, c.cin, 3, 1, 0, c.w, c.b, c.cout, GemmEpi(), from_view(o)); break; }
+            case L_CONV_IN: {
+                const Conv& c = n->convs[L.idx];
+                if (k_conv_first_supported(c.cin, c.cout)) RUN(k_conv_first(x.v, x.B, x.H, x.W, c.w, c.b, c.cout, o, cx.st));
+                else gemm_any(cx, from_view(x.v), x.B, x.H, x.W, c.cin, 3, 1, 0, c.w, c.b, c.cout, GemmEpi(), from_view(o));
+                break;
+            }
             case L_RES: run_res(cx, n->res[L.idx], x, emb_all, o); break;
             case L_ST: run_st(cx, n->sts[L.idx], x, o); break;
             case L_DOWN: run_down(cx, n->convs[L.idx], x, o); break;

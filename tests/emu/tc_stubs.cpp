@@ -31,7 +31,7 @@ int knn_scan_tc(const void*, const float*, long long, int, const float*, int, vo
 }
 size_t knn_tc_fused_ws_bytes(int) { return 256; }
 unsigned* knn_tc_fused_grid_bar(void*, int) { return nullptr; }
-int knn_scan_tc_fused(const void*, const float*, long long, int, const float*, int, int, void*, unsigned long long*, unsigned*, unsigned*, void*, int, cudaStream_t) {
+int knn_scan_tc_fused(const void*, const float*, long long, int, const float*, int, int, void*, unsigned long long*, unsigned*, unsigned*, void*, int, float*, cudaStream_t) {
     rdm_set_error("emulation: the tcgen05 kNN scan is not available on the host (set RDM_KNN_NO_TC=1)");
     return RDM_ERR_UNSUPPORTED;
 }

@@ -135,3 +135,26 @@ def test_query_normalisation_inside_the_library_is_bit_identical_to_numpy(cuda, 
     assert all(torch.equal(x, y) for x, y in zip(a, b))
     ri, _, rs = oknn.search(db, want, 6, return_scores=True)
     assert np.array_equal(a[0].cpu().numpy(), ri) and np.array_equal(a[2].cpu().numpy().view(np.uint64), rs.view(np.uint64))
+
+
+@pytest.mark.parametrize("nq,k", [(37, 20), (64, 8), (100, 20), (130, 4)])
+def test_wide_hi_only_passes_stay_exact_on_near_duplicate_clusters(cuda, nq, k):
+    """Passes of more than 16 queries over a database large enough for the fused scan keep only the fp16 hi rows of the queries (up to 128
+    queries per pass): the scan score is then off by up to 2^-11, far more than the spacing inside a cluster of near-duplicate rows.  The
+    wider score slack of such a pass (thresholds and the select cut, knn_tc.cu: HI_SLACK) must keep every true neighbour among the rows
+    that are re-ranked exactly: indices and fp64 scores bit-identical to the oracle, on clustered and on plain queries."""
+    from oracle import knn as oknn
+    from rdm_b200.knn import B200Searcher
+    n = 200_000
+    rng = np.random.default_rng(1000 + nq)
+    db = (rng.standard_normal((n, 512)) * rng.uniform(0.5, 8, (n, 1))).astype(np.float16)
+    db[5000:5600] = db[5000] + (rng.standard_normal((600, 512)) * 2e-3).astype(np.float16)           # 600 rows within ~1e-6 of each other in cosine
+    db[90_000:90_050] = db[90_000]                                                                      # exact duplicates: ties broken by index
+    q = rng.standard_normal((nq, 512)).astype(np.float32)
+    q[0], q[nq // 2], q[nq - 1] = db[5000].astype(np.float32), db[5300].astype(np.float32) * 3.0, db[90_010].astype(np.float32)
+    qh = oknn.normalize_queries(q)
+    idx, dist, sc = B200Searcher(db, device=cuda).search_device(torch.from_numpy(qh).to(cuda), k, return_scores=True)
+    wi, wd, ws = oknn.search(db, qh, k, return_scores=True)
+    assert set(wi[0]) <= set(range(5000, 5600)) and list(wi[nq - 1][:k]) == list(range(90_000, 90_000 + k))
+    assert np.array_equal(idx.cpu().numpy(), wi)
+    assert np.array_equal(sc.cpu().numpy().view(np.int64), ws.view(np.int64))
