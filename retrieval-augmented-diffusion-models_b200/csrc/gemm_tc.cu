@@ -72,6 +72,7 @@ struct TcKernelParams {
     __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_bf_ld;   // 16-bit-plane output (or null)
     int f16;                                                       // planes are IEEE fp16 instead of bf16
     double* stats; int stats_ld, stats_hw;                         // GroupNorm statistics of the result (GemmEpi::stats), or null
+    int geglu_rows;                                                // GEGLU in row form (no residual / row vector, aligned outputs): see geglu_row_form
 };
 
 template <int BN, int NSPLIT, int STAGES>
@@ -107,8 +108,19 @@ template <int EPI> __device__ __forceinline__ bool epi_is_xattn(const TcKernelPa
 
 struct EpiPre { float4 b[2]; float4 r[8]; };        // bias (+ row vector) for rows 0..15 / 16..31 of the warp; residual per row
 
+// GEGLU without residual / row vector (the feed-forward of every SpatialTransformer): the "row form" of the epilogue -- a thread keeps its
+// accumulator ROW (32 columns = 16 (value, gate) pairs -> 16 outputs = 32 contiguous bytes of the fp16 plane), so there is no transpose
+// through shared memory at all and the 16 GELUs of a thread are independent (the transposed form left the two epilogue warps of a
+// scheduler waiting on shared-memory round trips between short dependent chains).  Its only operand is the chunk's bias: 32 floats, the
+// same for every lane (broadcast loads), parked in the registers of EpiPre::r.
+__device__ __forceinline__ bool geglu_row_form(const TcKernelParams& p) { return p.geglu_rows != 0; }
 template <int EPI>
 __device__ __forceinline__ void epi_prefetch(const TcKernelParams& p, int lane, int m_warp0, int nb, EpiPre& pre) {
+    if (epi_is_geglu<EPI>(p) && geglu_row_form(p)) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) pre.r[i] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
     const int cg = (lane & 7) * 4, r0 = lane >> 3, n = nb + cg;
     float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias) bz = __ldg(reinterpret_cast<const float4*>(p.bias + n));
@@ -293,6 +305,32 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
             if (mo < p.M) {
                 if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)mo * p.out_ld + n) = o;
                 else store_planes4(p.out_hi + (size_t)mo * p.out_bf_ld + n, p.out_lo ? p.out_lo + (size_t)mo * p.out_bf_ld + n : nullptr, p.f16, o.x, o.y, o.z, o.w);
+            }
+        }
+        return;
+    }
+    if (epi_is_geglu<EPI>(p) && geglu_row_form(p) && !part) {
+        const int m = m_warp0 + lane, no = nb >> 1;
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 bb = pre.r[i];
+            o[2 * i] = (v[4 * i] + bb.x) * gelu_erf(v[4 * i + 1] + bb.y);
+            o[2 * i + 1] = (v[4 * i + 2] + bb.z) * gelu_erf(v[4 * i + 3] + bb.w);
+        }
+        if (m < p.M) {
+            if (p.out) {
+                float4* d = reinterpret_cast<float4*>(p.out + (size_t)m * p.out_ld + no);
+#pragma unroll
+                for (int i = 0; i < 4; i++) d[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            } else if (!p.out_lo) {
+                uint4* d = reinterpret_cast<uint4*>(p.out_hi + (size_t)m * p.out_bf_ld + no);
+                d[0] = make_uint4(pack16x2(o[0], o[1], p.f16), pack16x2(o[2], o[3], p.f16), pack16x2(o[4], o[5], p.f16), pack16x2(o[6], o[7], p.f16));
+                d[1] = make_uint4(pack16x2(o[8], o[9], p.f16), pack16x2(o[10], o[11], p.f16), pack16x2(o[12], o[13], p.f16), pack16x2(o[14], o[15], p.f16));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    store_planes4(p.out_hi + (size_t)m * p.out_bf_ld + no + 4 * i, p.out_lo + (size_t)m * p.out_bf_ld + no + 4 * i, p.f16, o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
             }
         }
         return;
@@ -831,6 +869,9 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     RDM_REQUIRE(e.act != ACT_XATTN || (e.xkv && e.xk >= 1 && e.xk <= 8 && p.rows_per_batch >= 16 && p.rows_per_batch % 16 == 0 && w.N % 32 == 0 && e.xkv_ld % 4 == 0 && !e.bias && !e.res && !e.rowvec), RDM_ERR_ARG,
                 "gemm_tc: fused cross-attention needs 1..8 context rows, N %% 32 == 0 and no bias/residual (xk=%d N=%d)", e.xk, w.N);
     p.out_hi = out_hi; p.out_lo = out_lo; p.out_bf_ld = out_bf_ld; p.f16 = f16; p.pdl_off = w.dynamic;
+    static const int no_geglu_rows = getenv("RDM_TC_GEGLU_TRANSPOSED") ? 1 : 0;       // A/B: the transposed GEGLU epilogue
+    p.geglu_rows = e.act == ACT_GEGLU && !e.res && !e.rowvec && !no_geglu_rows && (w.N & 63) == 0 &&
+                   (e.out ? e.out_ld % 4 == 0 && ((uintptr_t)e.out & 15) == 0 : out_bf_ld % 8 == 0 && ((uintptr_t)out_hi & 15) == 0 && (!out_lo || ((uintptr_t)out_lo & 15) == 0));
     RDM_REQUIRE((p.out != nullptr) != (p.out_hi != nullptr), RDM_ERR_ARG, "gemm_tc: exactly one of fp32 / bf16 outputs");
     // Tile width and split-K.  The mainloop is operand-feed bound (TMA/L2 -> smem): one k-block of a work item costs ~(128 + BN)
     // (the 128-row A tile is re-loaded for every N tile); every item pays a fixed prologue/epilogue worth ~6 k-blocks.  Small-M layers
