@@ -73,37 +73,18 @@ struct TcKernelParams {
     int f16;                                                       // planes are IEEE fp16 instead of bf16
     double* stats; int stats_ld, stats_hw;                         // GroupNorm statistics of the result (GemmEpi::stats), or null
     int geglu_rows;                                                // GEGLU in row form (no residual / row vector, aligned outputs): see geglu_row_form
-    int l2_ahead;                                                  // static weights: pull the B tiles of later k-blocks into L2 ahead of the ring (tma_prefetch_l2_2d)
-    int halo_bst;                                                  // HALO pipeline: stages of the B ring
-    int halo_bytes, halo_dy_bytes;                                 // HALO pipeline: bytes of one A box ((bh + 2) * bw rows of 128 B), bytes between dy taps (bw rows)
 };
 
-// HALO pipeline (STAGES == 0; 3x3 convolutions whose 128-row tile is bh whole image rows, one MMA per product): the nine taps of a 3x3
-// convolution read nearly the same pixels, but the tap-by-tap pipeline fetched the 16 KB A tile nine times per 64-channel block -- and the
-// big convolutions are bound by exactly that L2 -> SM operand traffic.  Here ONE box per (channel block, dx) brings
-// the tile with a halo row above and below ((bh + 2) x bw pixels); the three dy taps are views of it: the start address of the A
-// descriptor moves by dy * bw rows = a multiple of the 1024-byte swizzle atom (bw is a multiple of 8 pixels), so the 128B-swizzled layout
-// TMA wrote is read back consistently.  A traffic per channel block: 3 x (bh + 2) / bh x 16 KB instead of 9 x 16 KB (2x less at 32x32,
-// 2.4x at 16x16).  A and B travel in separate rings (the B tile of every tap is still its own 64-column block of the weight matrix):
-// warp 0 feeds A, warp 2 (idle otherwise) feeds B.
-constexpr int HALO_A_MAX = 32768, HALO_AST = 3, HALO_BST_MAX = 10, HALO_PIPE_BYTES = 196608;
-// three A slots of exactly one box ((bh + 2) * bw * 128 B <= HALO_A_MAX, a multiple of 1 KB); the rest of the pipeline memory is the B
-// ring: 5 stages of a 192-column tile at 32x32 / 16x16 (4 in the classic pipeline, 4 at 64x64)
 template <int BN, int NSPLIT, int STAGES>
 struct TcSmem {
-    static constexpr bool HALO = STAGES == 0;
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * A_BYTES + (NSPLIT >= 2 ? 2 : 1) * B_BYTES;   // [A_hi][B_hi][B_lo?][A_lo?]
-    static constexpr int PIPE_BYTES = HALO ? HALO_PIPE_BYTES : STAGES * STAGE_BYTES;
-    static constexpr int NFULL = HALO ? HALO_AST + HALO_BST_MAX : STAGES;                                   // full (and empty) barriers
     static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;      // per-epilogue-warp transpose tiles
     static constexpr int STAT_BYTES = 2 * BN * 4;                  // GroupNorm column sums of a tile: [sum | sumsq][BN] fp32
-    static constexpr int TOTAL = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES + STAT_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES + STAT_BYTES;
     static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
     static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
     static_assert(TOTAL <= 232448, "shared memory budget");
-    static_assert(!HALO || NSPLIT == 1, "the HALO pipeline carries one A and one B plane");
-    static_assert((2 * NFULL + 4) * 8 + 8 <= 256, "barrier region");
 };
 
 // ---- epilogue ------------------------------------------------------------------------------------------
@@ -493,21 +474,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcKernelParams p) {
     using S = TcSmem<BN, NSPLIT, STAGES>;
     constexpr int RED_LD = BN + 4;                 // row stride (floats) of the split-K staging tile: conflict-free float4 rows
-    static_assert(BM * RED_LD * 4 <= S::PIPE_BYTES, "split-K staging tile must fit the pipeline stages");
-    constexpr bool HALO = S::HALO;
-    constexpr int NFULL = S::NFULL;
+    static_assert(BM * RED_LD * 4 <= STAGES * S::STAGE_BYTES, "split-K staging tile must fit the pipeline stages");
     extern __shared__ uint8_t smem_raw[];
 #ifdef RDM_AB_GENERIC_SMEM
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 #else
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // 1 KB aligned; pointer arithmetic keeps the shared address space
 #endif
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::PIPE_BYTES);         // HALO: [0, HALO_AST) = A ring, [HALO_AST, NFULL) = B ring
-    uint64_t* empty = full + NFULL;
-    uint64_t* tmem_full = empty + NFULL;           // [2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;          // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* epi_stage = reinterpret_cast<float*>(smem + S::PIPE_BYTES + 256);
+    float* epi_stage = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);
     float* stat_base = epi_stage + EPI_WARPS * EPI_WARP_FLOATS;          // [2 * BN]
     for (int i = threadIdx.x; i < 2 * BN; i += TC_THREADS) stat_base[i] = 0.f;
 
@@ -525,7 +504,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmB_hi);
         if (NSPLIT >= 2) prefetch_tmap(&tmB_lo);
         if (NSPLIT == 3) prefetch_tmap(&tmA_lo);
-        for (int s = 0; s < NFULL; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
         fence_barrier_init();
     }
@@ -544,74 +523,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // (operand prefetch + 32 accumulators + transpose tiles) take them: 4 x 32 x 56 + 8 x 32 x 224 = 64512 = 384 x 168.
     if (warp < EPI_WARP0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if constexpr (HALO) {
-        // ---- HALO pipeline (see TcSmem): warp 0 = A boxes, warp 2 = B tiles, warp 1 = MMA issue; no split-K here (host) ----
-        const int A_SLOT = p.halo_bytes, BST = p.halo_bst;              // (host: halo_bytes is a multiple of 1024; BST = what fits behind the three A slots)
-        uint8_t* slotB0 = smem + HALO_AST * A_SLOT;
-        if (warp == 0 && lane == 0) {
-            pdl_wait();                                                  // the activation plane comes from the previous kernel
-            int ga = 0;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const int mt = item / ntn;
-                const int tiles_per_img = (p.H * p.W) / BM, b0 = mt / tiles_per_img, y0 = (mt % tiles_per_img) * p.bh;
-                for (int cb = 0; cb < p.kb_per_tap; cb++)
-                    for (int dx = -1; dx <= 1; dx++, ga++) {
-                        const int sa = ga % HALO_AST; const uint32_t ph = (ga / HALO_AST) & 1;
-                        mbar_wait(&empty[sa], ph ^ 1);
-                        mbar_expect_tx(&full[sa], (uint32_t)p.halo_bytes);
-                        tma_load_4d(smem + sa * A_SLOT, &tmA_hi, &full[sa], cb * BK, dx, y0 - 1, b0);      // rows y0-1 .. y0+bh: out-of-image rows / columns are zero = the padding
-                    }
-            }
-        } else if (warp == 2 && lane == 0) {
-            if (!p.pdl) pdl_wait();                                      // static weights may be requested ahead of the dependency wait; an activation as B may not
-            int gb = 0;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const int n0 = (item % ntn) * BN;
-                // the weight tiles of the next channel block are pulled into L2 while this one is being consumed (a ring of 4-8 stages alone
-                // leaves every tile a full HBM round trip away)
-                if (p.l2_ahead)
-                    for (int t = 0; t < 9; t++) tma_prefetch_l2_2d(&tmB_hi, t * p.kb_per_tap * BK, n0);
-                for (int cb = 0; cb < p.kb_per_tap; cb++) {
-                    if (p.l2_ahead && cb + 1 < p.kb_per_tap)
-                        for (int t = 0; t < 9; t++) tma_prefetch_l2_2d(&tmB_hi, (t * p.kb_per_tap + cb + 1) * BK, n0);
-                    for (int dx = 0; dx < 3; dx++)
-                        for (int dy = 0; dy < 3; dy++, gb++) {
-                            const int sb = gb % BST; const uint32_t ph = (gb / BST) & 1;
-                            mbar_wait(&empty[HALO_AST + sb], ph ^ 1);
-                            mbar_expect_tx(&full[HALO_AST + sb], S::B_BYTES);
-                            tma_load_2d(slotB0 + sb * S::B_BYTES, &tmB_hi, &full[HALO_AST + sb], ((dy * 3 + dx) * p.kb_per_tap + cb) * BK, n0);
-                        }
-                }
-            }
-        } else if (warp == 1 && lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(BN, p.f16);
-            int ga = 0, gb = 0, lt = 0;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x, lt++) {
-                const int buf = lt & 1;
-                mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-                uint32_t acc = 0;
-                for (int g = 0; g < 3 * p.kb_per_tap; g++, ga++) {
-                    const int sa = ga % HALO_AST;
-                    mbar_wait(&full[sa], (ga / HALO_AST) & 1);
-                    tc_fence_after();
-                    const uint32_t a_base = smem_u32(smem + sa * A_SLOT);
-                    for (int dy = 0; dy < 3; dy++, gb++) {
-                        const int sb = gb % BST;
-                        mbar_wait(&full[HALO_AST + sb], (gb / BST) & 1);
-                        tc_fence_after();
-                        const uint32_t a_tap = a_base + (uint32_t)(dy * p.halo_dy_bytes), b_tile = smem_u32(slotB0 + sb * S::B_BYTES);
-#pragma unroll
-                        for (int k = 0; k < BK / 16; k++) { umma_bf16(tmem_d, umma_desc_sw128(a_tap + k * 32), umma_desc_sw128(b_tile + k * 32), idesc, acc); acc = 1; }
-                        umma_commit(&empty[HALO_AST + sb]);
-                    }
-                    umma_commit(&empty[sa]);                             // the three taps of this box have been issued
-                }
-                umma_commit(&tmem_full[buf]);
-            }
-        }
-    } else
     if (warp == 0) {
         if (lane == 0) {
             // PDL prologue: the WEIGHT tiles of the first stages do not depend on the previous kernel -> request them before waiting
@@ -627,16 +538,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         tma_load_2d(st + S::A_BYTES, &tmB_hi, &full[pre], kb * BK, n0);
                         if (NSPLIT >= 2) tma_load_2d(st + S::A_BYTES + S::B_BYTES, &tmB_lo, &full[pre], kb * BK, n0);
                     }
-                }
-            }
-            // ... and the weight tiles behind them are pulled into L2 (no shared memory needed): L2_AHEAD k-blocks ahead of the ring
-            constexpr int L2_AHEAD = 12;
-            if (p.l2_ahead && (int)blockIdx.x < nitems) {
-                const int tile = blockIdx.x / p.splits, sp = blockIdx.x - tile * p.splits;
-                const int kb0 = sp * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split), n0 = (tile % ntn) * BN;
-                for (int kb = kb0 + pre; kb < kb1 && kb < kb0 + pre + L2_AHEAD; kb++) {
-                    tma_prefetch_l2_2d(&tmB_hi, kb * BK, n0);
-                    if (NSPLIT >= 2) tma_prefetch_l2_2d(&tmB_lo, kb * BK, n0);
                 }
             }
             pdl_wait();                                                  // activations / residuals of the previous kernels are now visible
@@ -655,10 +556,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
                     uint8_t* st = smem + s * S::STAGE_BYTES;
                     const bool prefetched = it < pre;                    // weights already requested (and the barrier armed) before pdl_wait
-                    if (p.l2_ahead && kb + STAGES + L2_AHEAD - 1 < kb1) {
-                        tma_prefetch_l2_2d(&tmB_hi, (kb + STAGES + L2_AHEAD - 1) * BK, n0);
-                        if (NSPLIT >= 2) tma_prefetch_l2_2d(&tmB_lo, (kb + STAGES + L2_AHEAD - 1) * BK, n0);
-                    }
                     if (!prefetched) { mbar_wait(&empty[s], ph ^ 1); mbar_expect_tx(&full[s], S::STAGE_BYTES); }
                     const int tap = kb / p.kb_per_tap, kc = (kb - tap * p.kb_per_tap) * BK;
                     const int dy = p.ksize == 3 ? tap / 3 - 1 : 0, dx = p.ksize == 3 ? tap % 3 - 1 : 0;
@@ -879,11 +776,7 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     const int nitems = ((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * p.splits;
     const int sms = rdm_num_sms(dev);
     const int use_pdl = g_rdm_use_pdl;
-    // RDM_TC_L2_AHEAD=1: pull the weight tiles of later k-blocks into L2 ahead of the ring (cp.async.bulk.prefetch.tensor).  Measured on
-    // B200: 4.56 ms per forward with it against 4.44 ms without -- every CTA of a layer prefetches the same tiles, and the extra L2 requests
-    // cost more than the shorter HBM round trips save.  Off by default.
-    static const int l2_ahead = getenv("RDM_TC_L2_AHEAD") ? atoi(getenv("RDM_TC_L2_AHEAD")) : 0;
-    TcKernelParams pl = p; pl.pdl = use_pdl && !p.pdl_off; pl.l2_ahead = !p.pdl_off && l2_ahead;
+    TcKernelParams pl = p; pl.pdl = use_pdl && !p.pdl_off;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(p.cluster ? nitems : (nitems < sms ? nitems : sms)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -919,11 +812,6 @@ int dispatch_tc_epi(int BN, int nsplit, const CUtensorMap& ta_hi, const CUtensor
 }
 int dispatch_tc(int BN, int nsplit, const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
                 const TcKernelParams& p, cudaStream_t st, int* cluster_cap) {
-    if (p.halo_bytes > 0) {                          // HALO pipeline (STAGES = 0): plain epilogue family, nsplit == 1, BN >= 64 (checked by the caller)
-        if (BN == 192) return launch_tc<192, 1, 0, EPI_PLAIN>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
-        if (BN == 128) return launch_tc<128, 1, 0, EPI_PLAIN>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
-        return launch_tc<64, 1, 0, EPI_PLAIN>(ta_hi, ta_lo, tb_hi, tb_lo, p, st, cluster_cap);
-    }
     static const int one_family = getenv("RDM_TC_ONE_EPI") ? 1 : 0;              // A/B: always the all-in-one kernel
     int epi = EPI_ANY;
     if (!one_family) {
@@ -1050,17 +938,6 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
             ws_cap[dev & 15][slot] = cap;
         }
         p.part = ws[dev & 15][slot];
-    }
-    // HALO pipeline for 3x3 convolutions whose tile is bh whole image rows of one image (the 32x32 / 16x16 / 64x64 levels)
-    static const int use_halo = getenv("RDM_TC_HALO") ? atoi(getenv("RDM_TC_HALO")) : 0;       // measured slower (see the commit message / DESIGN.md section 8): off
-    const bool halo = use_halo && a.ksize == 3 && nsplit == 1 && splits == 1 && BN >= 64 && a.W <= BM && p.bb == 1 && p.bh * p.bw == BM && p.bw == a.W && (p.bw & 7) == 0 &&
-                      (p.bh + 2) * p.bw * BK * 2 <= HALO_A_MAX && ((p.bh + 2) * p.bw * BK * 2) % 1024 == 0 && e.act == ACT_NONE && (w.N & 31) == 0 && !(e.rowvec && p.rows_per_batch < 16);
-    if (halo) {
-        p.halo_bytes = (p.bh + 2) * p.bw * BK * 2; p.halo_dy_bytes = p.bw * BK * 2;
-        p.halo_bst = (HALO_PIPE_BYTES - HALO_AST * p.halo_bytes) / (BN * BK * 2);
-        if (p.halo_bst > HALO_BST_MAX) p.halo_bst = HALO_BST_MAX;
-        RDM_TRY(make_map_4d(&ta_hi, a.hi, a.C, a.W, a.H, a.B, a.ld, p.bw, p.bh + 2, 1));
-        ta_lo = ta_hi;
     }
     RDM_TRY(make_map_2d(&tb_hi, w.hi, w.K, w.N, w.ld, BN));
     if (nsplit >= 2) RDM_TRY(make_map_2d(&tb_lo, w.lo, w.K, w.N, w.ld, BN)); else tb_lo = tb_hi;
