@@ -710,6 +710,148 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
 }
 
+// ---- CTA-pair variant (cta_group::2) for the large layers ------------------------------------------------------------------------------------
+// The mainloop of the one-CTA kernel is bound by SHARED-MEMORY bandwidth, not by L2 or HBM: a 128 x 192 x 64 k-block writes 40 KB of
+// operands into shared memory (TMA) and the tensor core reads the same 40 KB back -- 80 KB through a 128 B/clk port = 640 cycles against
+// 384 cycles of math (in-kernel stamps: 587 cycles per k-block; halving the A traffic with halo boxes or prefetching the weights into L2
+// changed nothing, commit 9400ff7).  Here the two CTAs of a cluster work on ONE 256-row tile: each CTA holds its 128 rows of A and HALF
+// of the B tile (rows [rank * BN / 2, +BN / 2) of the weight block), one `tcgen05.mma.cta_group::2` (M = 256) issued by the even CTA
+// drives both tensor cores, each accumulating its 128 rows in its own TMEM.  Per SM and k-block: 28 KB written + 28 KB read instead of
+// 40 + 40, and the 28 KB stages leave room for 6 of them.  Protocol (CUTLASS sm100 2-SM pipelines):
+//   full[s]       lives in the even CTA: armed by its producer with the bytes of BOTH CTAs; both producers' TMA loads (.cta_group::2)
+//                 count on it (peer bit of the barrier address cleared)
+//   empty[s]      one per CTA (each producer waits for its own stage); the MMA completion arrives on both (commit ... multicast)
+//   tmem_full[b]  one per CTA, same multicast commit; tmem_empty[b] lives in the even CTA and collects the epilogue warps of both
+// Epilogue: unchanged (each CTA drains its own 128 TMEM lanes = its own 128 output rows).  No split-K, plain epilogue family only.
+constexpr int TC2_STAGES_192 = 6;
+template <int BN, int STAGES>
+struct Tc2Smem {
+    static constexpr int A_BYTES = BM * BK * 2, BH_BYTES = (BN / 2) * BK * 2, STAGE_BYTES = A_BYTES + BH_BYTES;
+    static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+    static_assert(TOTAL <= 232448, "shared memory budget");
+    static_assert((BN / 2) % 8 == 0 && BN % 32 == 0, "the B half tile is whole 8-row swizzle groups");
+};
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcKernelParams p) {
+    using S = Tc2Smem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;          // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2] (used in the even CTA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* epi_stage = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int nkb = p.taps * p.kb_per_tap;
+    const int ntn = (p.N + BN - 1) / BN, npair = ((p.M + 2 * BM - 1) / (2 * BM)) * ntn;        // work items of a PAIR: (256-row tile, N tile), N fastest
+    const int pair0 = blockIdx.x >> 1, pairs = gridDim.x >> 1;
+    pdl_launch_dependents();
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 2 * EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {                                  // the same warp of BOTH CTAs allocates (and frees) the pair's tensor memory
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)S::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                               // the peer's barriers exist before anything is signalled across the pair
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < EPI_WARP0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 0 && lane == 0) {
+            pdl_wait();
+            int it = 0;
+            for (int item = pair0; item < npair; item += pairs) {
+                const int mt = 2 * (item / ntn) + (int)rank, n0 = (item % ntn) * BN + (int)rank * (BN / 2);
+                int x0 = 0, y0 = 0, b0 = 0;
+                if (p.plain) x0 = mt * BM;
+                else if (p.W > BM) { const int tpr = p.W / BM; x0 = (mt % tpr) * BM; y0 = (mt / tpr) % p.H; b0 = mt / (tpr * p.H); }
+                else if (p.bb > 1 || p.bh * p.bw == p.H * p.W) b0 = mt * p.bb;
+                else { const int tiles_per_img = (p.H * p.W) / BM; b0 = mt / tiles_per_img; y0 = (mt % tiles_per_img) * p.bh; }
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
+                    uint8_t* st = smem + s * S::STAGE_BYTES;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (rank == 0) mbar_expect_tx(&full[s], 2 * S::STAGE_BYTES);
+                    const int tap = kb / p.kb_per_tap, kc = (kb - tap * p.kb_per_tap) * BK;
+                    const int dy = p.ksize == 3 ? tap / 3 - 1 : 0, dx = p.ksize == 3 ? tap % 3 - 1 : 0;
+                    tma_load_4d_2sm(st, &tmA, &full[s], kc, x0 + dx, y0 + dy, b0);           // rows beyond M: out-of-bounds boxes are zero-filled (and still counted)
+                    tma_load_2d_2sm(st + S::A_BYTES, &tmB, &full[s], kb * BK, n0);
+                }
+            }
+        } else if (warp == 1 && lane == 0 && rank == 0) {
+            const uint32_t idesc = umma_idesc_bf16_2sm(BN, p.f16);
+            int it = 0, lt = 0;
+            for (int item = pair0; item < npair; item += pairs, lt++) {
+                const int buf = lt & 1;
+                mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);        // the epilogues of both CTAs have drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a = smem_u32(smem + s * S::STAGE_BYTES), b = a + S::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++) umma_bf16_2sm(tmem_d, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc, (kb | k) != 0);
+                    umma_commit_2sm(&empty[s]);
+                }
+                umma_commit_2sm(&tmem_full[buf]);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        pdl_wait();
+        const int q = warp & 3, half = (warp - EPI_WARP0) >> 2, ew = warp - EPI_WARP0;
+        int lt = 0;
+        for (int item = pair0; item < npair; item += pairs, lt++) {
+            const int buf = lt & 1;
+            const int mt = 2 * (item / ntn) + (int)rank, n0 = (item % ntn) * BN;
+            const int m_warp0 = mt * BM + q * 32;
+            EpiPre pre, pre_nx; XPre xp;
+            if (m_warp0 < p.M && n0 + half * 32 + 32 <= p.N) epi_prefetch<EPI_PLAIN>(p, lane, m_warp0, n0 + half * 32, pre);
+            mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = half; c < BN / 32; c += 2) {
+                const int nb = n0 + c * 32;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32);
+                if (m_warp0 >= p.M || nb + 32 > p.N) continue;
+                const int nbn = nb + 64;
+                const bool has_next = c + 2 < BN / 32 && nbn + 32 <= p.N;
+                if (has_next) epi_prefetch<EPI_PLAIN>(p, lane, m_warp0, nbn, pre_nx);
+                uint32_t r[32];
+                tmem_ld32(taddr, r);
+                epilogue_chunk<EPI_PLAIN>(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb, pre, xp, nullptr, nullptr, 0, BN);
+                if (has_next) pre = pre_nx;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[buf]), 0));      // on the even CTA's barrier
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                               // no CTA of the pair leaves (or frees tensor memory) while the other may still signal it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -785,6 +927,32 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     if (p.cluster) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = p.splits; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; na++; }
     cfg.attrs = attr; cfg.numAttrs = na;
     RDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, b_hi, b_lo, pl));
+    RDM_COUNT_LAUNCH();
+    RDM_CHECK_CUDA(cudaGetLastError());
+    return RDM_OK;
+}
+
+template <int BN, int STAGES>
+int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const TcKernelParams& p, cudaStream_t st) {
+    auto kern = gemm_tc2_kernel<BN, STAGES>;
+    constexpr int smem = Tc2Smem<BN, STAGES>::TOTAL;
+    static bool configured[16] = {false};
+    int dev = 0; cudaGetDevice(&dev);
+    if (!configured[dev & 15]) {
+        RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured[dev & 15] = true;
+    }
+    const int npair = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN), max_pairs = rdm_num_sms(dev) / 2;
+    const int pairs = npair < max_pairs ? npair : max_pairs;
+    TcKernelParams pl = p; pl.pdl = 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (g_rdm_use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+    attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; na++;
+    cfg.attrs = attr; cfg.numAttrs = na;
+    RDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, pl));
     RDM_COUNT_LAUNCH();
     RDM_CHECK_CUDA(cudaGetLastError());
     return RDM_OK;
@@ -873,6 +1041,26 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     p.geglu_rows = e.act == ACT_GEGLU && !e.res && !e.rowvec && !no_geglu_rows && (w.N & 63) == 0 &&
                    (e.out ? e.out_ld % 4 == 0 && ((uintptr_t)e.out & 15) == 0 : out_bf_ld % 8 == 0 && ((uintptr_t)out_hi & 15) == 0 && (!out_lo || ((uintptr_t)out_lo & 15) == 0));
     RDM_REQUIRE((p.out != nullptr) != (p.out_hi != nullptr), RDM_ERR_ARG, "gemm_tc: exactly one of fp32 / bf16 outputs");
+    // CTA pairs (gemm_tc2_kernel) for the large plain layers: 256-row tiles, no split-K.  RDM_TC_2SM=0 switches them off.
+    {
+        static const int use_2sm = getenv("RDM_TC_2SM") ? atoi(getenv("RDM_TC_2SM")) : 1;
+        static const int min_m = getenv("RDM_TC_2SM_MIN_M") ? atoi(getenv("RDM_TC_2SM_MIN_M")) : 8192;
+        const int bn2 = w.N % 192 == 0 ? 192 : w.N % 128 == 0 ? 128 : 0;
+        // Measured per layer (B200, fp16): the pair kernel wins where the one-CTA kernel needs more than one wave of tiles AND several N
+        // tiles (M = 32768, N = 384: 964 vs 598 TFLOP/s; M = 8192, N = 576: 713 vs 612) and loses a little on single-wave layers and on
+        // short K (cluster launch + two cluster barriers around a 2 us mainloop: M = 8192, N = 384, K = 384: 150 vs 172).  The mainloop itself
+        // gains nothing -- it already runs at the chip's burst tensor rate in both kernels (587 cycles per 128 x 192 x 64 k-block =
+        // 1560 TFLOP/s over 148 SMs); RDM_TC_2SM=2 forces the pair kernel wherever it is legal.
+        const int tiles1 = ((M + BM - 1) / BM) * ((w.N + 191) / 192);
+        const bool wins = use_2sm >= 2 || (tiles1 > 148 && w.N > 192 && p.taps * p.kb_per_tap >= 16);
+        if (use_2sm && wins && nsplit == 1 && bn2 && M >= min_m && M % (2 * BM) == 0 && e.act == ACT_NONE && !e.stats && !(e.rowvec && p.rows_per_batch < 16)) {
+            p.splits = 1; p.kb_per_split = p.taps * p.kb_per_tap; p.part = nullptr; p.cluster = 0; p.stats = nullptr; p.geglu_rows = 0;
+            RDM_TRY(make_map_2d(&tb_hi, w.hi, w.K, w.N, w.ld, bn2 / 2));
+            if (e.stats_fused) *e.stats_fused = 0;
+            if (getenv("RDM_TC_TRACE")) fprintf(stderr, "gemm_tc M=%d N=%d K=%d -> CTA pairs, BN=%d\n", M, w.N, w.K, bn2);
+            return bn2 == 192 ? launch_tc2<192, 6>(ta_hi, tb_hi, p, st) : launch_tc2<128, 7>(ta_hi, tb_hi, p, st);
+        }
+    }
     // Tile width and split-K.  The mainloop is operand-feed bound (TMA/L2 -> smem): one k-block of a work item costs ~(128 + BN)
     // (the 128-row A tile is re-loaded for every N tile); every item pays a fixed prologue/epilogue worth ~6 k-blocks.  Small-M layers
     // (4x4 / 8x8 latents) split K so that all SMs stream a slice of the weights.  cost = waves * (kb_per_item + 6) * (128 + BN).
