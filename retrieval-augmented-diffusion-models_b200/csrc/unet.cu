@@ -388,12 +388,13 @@ void lin_any(Ctx& cx, const Opnd& a, int M, const Lin& l, GemmEpi e, const Opnd&
 }
 
 void gn(Ctx& cx, const Act& x, const Norm& nm, float eps, int silu, const Opnd& y, const Opnd* raw = nullptr) {
-    // A/B (RDM_GN_CLUSTER=1): statistics and normalisation in ONE launch, the CTAs of an image exchanging partial sums through distributed
-    // shared memory (gn_fused.cu).  Measured on B200 (full architecture, B2 = 32, fp16 mode): 4.85 ms per forward against 4.60 ms with the
-    // two kernels below -- an 8-CTA cluster per image offers the memory system far fewer independent loads than the 148 x 16 small CTAs of
-    // gn_stats / gn_apply, and the cluster launch itself is slower than two plain launches.  Kept as the negative result it is; default off.
-    static const int use_cluster = getenv("RDM_GN_CLUSTER") ? atoi(getenv("RDM_GN_CLUSTER")) : 0;
-    if (cx.n->mode != RDM_UNET_MODE_FP32 && use_cluster && k_gn_fused_supported(x.v.C, x.H * x.W, 32, false)) {
+    // Statistics and normalisation in ONE launch (gn_fused.cu: the CTAs of an image exchange partial sums through distributed shared
+    // memory) for SMALL images -- at the 8x8 / 4x4 levels the two kernels below are pure launch latency (4.32 vs 4.38 ms per forward on
+    // B200).  For the large images the one-launch form loses (4.85 vs 4.60 ms when used everywhere: an 8-CTA cluster per image offers
+    // the memory system far fewer independent loads than the 148 x 16 small CTAs of gn_stats / gn_apply), so they keep the two kernels.
+    // RDM_GN_FUSED_MAX_HW: largest image (pixels) that takes the one-launch form (0: never).
+    static const int fused_max_hw = getenv("RDM_GN_FUSED_MAX_HW") ? atoi(getenv("RDM_GN_FUSED_MAX_HW")) : 64;
+    if (cx.n->mode != RDM_UNET_MODE_FP32 && x.H * x.W <= fused_max_hw && k_gn_fused_supported(x.v.C, x.H * x.W, 32, false)) {
         RUN_UNLESS(2, k_gn_fused(x.v, x.B, x.H * x.W, 32, nullptr, 0, eps, nm.g, nm.b, silu, y.out4(), raw ? raw->out4() : Out4(), cx.st));
         return;
     }
