@@ -100,12 +100,14 @@ struct GemvP {
     float* out; int ldo;
 };
 // CPW weight rows (output columns) per warp pass; GEGLU: rows (2j, 2j+1) = (value_j, gate_j) -> output column j (needs CPW == 4).
-template <typename WT, int CPW, int WARPS, bool GEGLU>
+// MR: activation rows per CTA (4 for batches of <= 4 rows -- an unguided batch of 4 --, else 8 = GV_ROWS): the FMA loop, the staged tile and the
+// accumulators scale with it
+template <typename WT, int CPW, int WARPS, bool GEGLU, int MR>
 __global__ void __launch_bounds__(WARPS * 32, 2) rarm_gemv_kernel(GemvP p, const WT* __restrict__ w) {
-    extern __shared__ float sx[];                          // [GV_ROWS][K]
+    extern __shared__ float sx[];                          // [MR][K]
     const int K = p.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int m0 = blockIdx.y * GV_ROWS, rows = min(GV_ROWS, p.M - m0);
-    constexpr int R = CPW * GV_ROWS;
+    const int m0 = blockIdx.y * MR, rows = min(MR, p.M - m0);
+    constexpr int R = CPW * MR, LPR = 32 / R;               // LPR: lanes that hold the same (column, row) sum after the reduction
     const int n0 = (blockIdx.x * WARPS + warp) * CPW;
     pdl_launch_dependents();
     // Weight rows are static: the first PF 256-element blocks of this warp's rows are requested BEFORE the predecessor kernel is waited for
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) rarm_gemv_kernel(GemvP p, const
             }
     }
     pdl_wait();
-    for (int i = threadIdx.x; i < GV_ROWS * (K / 4); i += WARPS * 32) {
+    for (int i = threadIdx.x; i < MR * (K / 4); i += WARPS * 32) {
         const int r = i / (K / 4), c = i % (K / 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < rows) v = *reinterpret_cast<const float4*>(p.x + (size_t)(m0 + r) * p.ldx + c * 4);
@@ -152,14 +154,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2) rarm_gemv_kernel(GemvP p, const
     for (int i = 0; i < R; i++) acc[i] = 0.f;
     auto fma_block = [&](const float (&wv)[CPW][8], int kc) {
 #pragma unroll
-        for (int m = 0; m < GV_ROWS; m++) {
+        for (int m = 0; m < MR; m++) {
             const float4 a0 = *reinterpret_cast<const float4*>(sx + m * K + kc + lane * 8), a1 = *reinterpret_cast<const float4*>(sx + m * K + kc + lane * 8 + 4);
 #pragma unroll
             for (int c = 0; c < CPW; c++) {
-                float t = acc[c * GV_ROWS + m];
+                float t = acc[c * MR + m];
                 t = fmaf(a0.x, wv[c][0], t); t = fmaf(a0.y, wv[c][1], t); t = fmaf(a0.z, wv[c][2], t); t = fmaf(a0.w, wv[c][3], t);
                 t = fmaf(a1.x, wv[c][4], t); t = fmaf(a1.y, wv[c][5], t); t = fmaf(a1.z, wv[c][6], t); t = fmaf(a1.w, wv[c][7], t);
-                acc[c * GV_ROWS + m] = t;
+                acc[c * MR + m] = t;
             }
         }
     };
@@ -184,32 +186,32 @@ __global__ void __launch_bounds__(WARPS * 32, 2) rarm_gemv_kernel(GemvP p, const
 #pragma unroll
         for (int c = 0; c < CPW; c++) wv[c] = load_w4(wr[c] + kc + lane * 4);
 #pragma unroll
-        for (int m = 0; m < GV_ROWS; m++) {
+        for (int m = 0; m < MR; m++) {
             const float4 a = *reinterpret_cast<const float4*>(sx + m * K + kc + lane * 4);
 #pragma unroll
             for (int c = 0; c < CPW; c++) {
-                float t = acc[c * GV_ROWS + m];
+                float t = acc[c * MR + m];
                 t = fmaf(a.x, wv[c].x, t); t = fmaf(a.y, wv[c].y, t); t = fmaf(a.z, wv[c].z, t); t = fmaf(a.w, wv[c].w, t);
-                acc[c * GV_ROWS + m] = t;
+                acc[c * MR + m] = t;
             }
         }
     }
     float tot = reduce_rows<R>(acc, lane);
-    const int r = R == 32 ? lane : lane >> 1;              // row_of_lane<R>
-    const int c = r / GV_ROWS, m = r % GV_ROWS, n = n0 + c;
+    const int r = lane / LPR;                              // row_of_lane<R>
+    const int c = r / MR, m = r % MR, n = n0 + c;
     const bool col_ok = n < p.N;
     if (p.bias && col_ok) tot += p.bias[n];
     if (GEGLU) {
         static_assert(!GEGLU || CPW == 4, "GEGLU pairs need 4 columns per warp");
-        const float gate = __shfl_sync(FULL, tot, (lane + GV_ROWS) & 31);       // same row m of column c + 1
-        if ((c & 1) == 0 && n + 1 < p.N && m < rows) {
+        const float gate = __shfl_sync(FULL, tot, (lane + MR * LPR) & 31);       // same row m of column c + 1
+        if ((c & 1) == 0 && (lane % LPR) == 0 && n + 1 < p.N && m < rows) {
             const int no = n >> 1;
             float t = tot * gelu_erf(gate);
             if (p.res) t += p.res[(size_t)(m0 + m) * p.ldres + no];
             p.out[(size_t)(m0 + m) * p.ldo + no] = t;
         }
     } else {
-        const bool writer = R == 32 || (lane & 1) == 0;
+        const bool writer = (lane % LPR) == 0;
         if (writer && col_ok && m < rows) {
             float t = tot;
             if (p.res) t += p.res[(size_t)(m0 + m) * p.ldres + n];
@@ -475,18 +477,22 @@ int ensure_half(Rarm* n, cudaStream_t st) {
     return RDM_OK;
 }
 
-template <typename WT, int CPW, int WARPS, bool GEGLU>
-int launch_gemv(const GemvP& p, const WT* w, cudaStream_t st) {
-    const size_t smem = (size_t)GV_ROWS * p.K * sizeof(float);
+template <typename WT, int CPW, int WARPS, bool GEGLU, int MR>
+int launch_gemv_mr(const GemvP& p, const WT* w, cudaStream_t st) {
+    const size_t smem = (size_t)MR * p.K * sizeof(float);
     static size_t configured = 0;                          // per instantiation; all handles of the process share the device function
     if (smem > 48 * 1024 && smem > configured) {
-        RDM_CHECK_CUDA(cudaFuncSetAttribute(rarm_gemv_kernel<WT, CPW, WARPS, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        RDM_CHECK_CUDA(cudaFuncSetAttribute(rarm_gemv_kernel<WT, CPW, WARPS, GEGLU, MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = 200 * 1024;
     }
-    dim3 grid((unsigned)ceil_div(p.N, CPW * WARPS), (unsigned)ceil_div(p.M, GV_ROWS));
-    RDM_CHECK_CUDA(launch_dep(rarm_gemv_kernel<WT, CPW, WARPS, GEGLU>, grid, dim3(WARPS * 32), smem, st, p, w));
+    dim3 grid((unsigned)ceil_div(p.N, CPW * WARPS), (unsigned)ceil_div(p.M, MR));
+    RDM_CHECK_CUDA(launch_dep(rarm_gemv_kernel<WT, CPW, WARPS, GEGLU, MR>, grid, dim3(WARPS * 32), smem, st, p, w));
     LAUNCH_CHECK();
     return RDM_OK;
+}
+template <typename WT, int CPW, int WARPS, bool GEGLU>
+int launch_gemv(const GemvP& p, const WT* w, cudaStream_t st) {
+    return p.M <= 4 ? launch_gemv_mr<WT, CPW, WARPS, GEGLU, 4>(p, w, st) : launch_gemv_mr<WT, CPW, WARPS, GEGLU, GV_ROWS>(p, w, st);
 }
 // out[M, N or N/2] = epi(LN?(x) * W^T): W is an fp32 pointer into the weight arena; the fp16 modes read the same offset of the half plane
 int gemv(Rarm* n, const float* x, int ldx, int M, int K, const float* w, int N, const float* bias, const float* ln_g, const float* ln_b,

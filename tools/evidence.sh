@@ -10,7 +10,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm_tc_kernel --launch-skip 203 --launch-count 197 \
     --csv --log-file gpurun_out/gemm_tc_dram_$tag.csv python tools/profile_forward.py 4 1 > /dev/null 2>&1
 # (3) --set full of the glue kernel classes inside the replayed forward
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:'gn_stats|gn_apply|layernorm_kernel|attention_mma' --launch-skip 300 --launch-count 8 \
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:'gn_stats|gn_apply|layernorm_kernel|attention_mma' --launch-skip 150 --launch-count 8 \
     -o gpurun_out/glue_$tag python tools/profile_forward.py 4 1 > gpurun_out/ncu_glue_$tag.log 2>&1
 # (4) RARM decode step: launch list + --set full of the weight-streaming GEMV and the cached attention
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:rarm_ --launch-skip 600 -c 300 --csv --log-file gpurun_out/launches_rarm_$tag.csv \

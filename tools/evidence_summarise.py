@@ -59,6 +59,9 @@ def launches(name, title, skip):
 
 
 def raw_table(rep, title, how, f, pick=None, stalls=True):
+    if not os.path.exists(os.path.join(G, rep)):
+        f.write(f"\n## {title}\n\n(no capture in this run: `{rep}` missing)\n")
+        return
     out = subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -90,8 +93,8 @@ with open(os.path.join(P, f"ncu_summary_{tag}.md"), "w") as f:
         raw_table("gemm_tc_r2g.ncu-rep", "gemm_tc_kernel (fp16 mode, one MMA per product): 12 consecutive launches of a graph-replayed full-architecture forward (B2 = 32)",
                   "ncu --set full -k regex:gemm_tc_kernel --launch-skip 203 --launch-count 12 python tools/profile_forward.py 4 1  [before the epilogue rework of this round: "
                   "launch 0 = level-0 3x3 conv M = 32768; 1-9 level-1 layers incl. the fused cross-attention (8) ; 10 = GEGLU feed-forward]", f)
-    raw_table(f"glue_{tag}.ncu-rep", "glue kernels of the forward: GroupNorm statistics / apply, LayerNorm, warp-MMA self-attention",
-              "ncu --set full -k regex:'gn_stats|gn_apply|layernorm_kernel|attention_mma' --launch-skip 300 --launch-count 8 python tools/profile_forward.py 4 1", f)
+    raw_table(f"glue_{tag}.ncu-rep", "glue kernels of the forward: GroupNorm statistics / apply (large images), one-launch cluster GroupNorm (small images), LayerNorm, warp-MMA self-attention",
+              "ncu --set full -k regex:'gn_stats|gn_apply|gn_fused|layernorm_kernel|attention_mma' --launch-skip 150 --launch-count 10 python tools/profile_forward.py 4 1", f)
     raw_table(f"rarm_{tag}.ncu-rep", "RARM decode step: weight-streaming GEMV (`rarm_gemv_kernel`) and cached attention (`rarm_attn_kernel`)",
               "ncu --set full -k regex:'rarm_gemv|rarm_attn' --launch-skip 600 --launch-count 9 python tools/rarm_bench.py", f)
     raw_table(f"knn_{tag}.ncu-rep", "one exact kNN search, fp16 database 1,281,167 x 512, 16 queries, k = 4 (normalise + fused tensor-core scan + select + conditional fallback pair)",
