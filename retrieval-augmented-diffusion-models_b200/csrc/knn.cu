@@ -838,8 +838,38 @@ int search_pass_tc(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_o
     return RDM_OK;
 }
 
+// fp32 / d=512 databases, >= 3 queries: the fused scan on kind::tf32 MMAs (knn_tc.cu), up to 64 queries per pass.  Returns 1 (nothing
+// launched) when the database is too small for the fused scan: the caller then takes the CUDA-core passes.
+template <typename T, int D>
+int search_pass_tf32(rdm_knn* h, const float* qp, int cnt, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st) {
+    constexpr int R = 8;
+    unsigned* overflow = h->cand_cnt + MAX_TCQ;
+    float slack = SCORE_SLACK;
+    const int fused = knn_scan_tc_fused_f32(h->db, h->inv, h->n, h->device, qp, cnt, k, h->qsplit, h->cand, h->cand_cnt, overflow, h->fused_ws, &slack, st);
+    if (fused != RDM_OK) return fused;
+    RDM_TRY((launch_select<T, D, false>(h, cnt, h->cand, 0, MAX_QP, qp, k, idx_out, dist_out, sc_out, st, slack)));
+    int g2 = 0;
+    ScanArgs f{}; f.group_stride = 1; f.lists_out = h->lists; f.overflow = overflow; f.nq_total = cnt;
+    RDM_TRY((launch_scan<T, D, MAX_QP, R, SCAN_LOCKED>(h, qp, cnt, f, st, &g2, (cnt + MAX_QP - 1) / MAX_QP)));
+    RDM_TRY((launch_select<T, D, true>(h, cnt, h->lists, g2, MAX_QP, qp, k, idx_out, dist_out, sc_out, st)));
+    return RDM_OK;
+}
+
 template <typename T, int D>
 int search_typed(rdm_knn* h, const float* q, int nq, int k, long long* idx_out, float* dist_out, double* sc_out, cudaStream_t st) {
+    if constexpr (std::is_same<T, float>::value && D == 512) {
+        static const bool no_tc = getenv("RDM_KNN_NO_TC") != nullptr;
+        if (!no_tc && nq >= 3) {
+            bool done = true;
+            for (int q0 = 0; q0 < nq && done; q0 += 64) {
+                const int cnt = nq - q0 < 64 ? nq - q0 : 64;
+                const int rc = search_pass_tf32<T, D>(h, q + (size_t)q0 * D, cnt, k, idx_out + (size_t)q0 * k, dist_out + (size_t)q0 * k, sc_out ? sc_out + (size_t)q0 * k : nullptr, st);
+                if (rc < 0) return rc;
+                if (rc != RDM_OK) done = false;          // (only the first pass can say "not usable here": nothing was launched)
+            }
+            if (done) return RDM_OK;
+        }
+    }
     if constexpr (std::is_same<T, __half>::value && D == 512) {
         static const bool no_tc = getenv("RDM_KNN_NO_TC") != nullptr;
         if (!no_tc && nq >= 3) {          // measured: from 3 queries on, the (padded) tensor-core pass beats the FMA scan (0.28 vs 0.35 ms at 4 queries, 1.28 M rows)

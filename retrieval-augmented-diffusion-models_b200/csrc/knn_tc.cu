@@ -1,4 +1,5 @@
-// Tensor-core scans (sample + main) of the exact kNN for fp16 databases (d = 512), 16 / 32 / 64 query columns per pass.
+// Tensor-core scans (sample + main) of the exact kNN for fp16 databases (d = 512), 16 / 32 / 64 / 128 query columns per pass, and (fused scan only)
+// for fp32 databases on kind::tf32 MMAs, 16 / 32 / 64 query columns per pass.
 //
 // With >= 8 queries the CUDA-core scan (knn.cu) is FMA-bound; here the 128-row database tile is the A operand of tcgen05.mma
 // straight from TMA (the stored fp16 rows are used as they are -- no conversion pass), the queries are the B operand, resident in
@@ -29,9 +30,16 @@ constexpr int MAX_FUSED_Q = 128;                    // queries per fused pass (=
 // bound: thresholds and the select cut admit a few more survivors, the exact fp64 re-rank of every survivor keeps the result bit-exact.
 constexpr float HILO_SLACK = 3e-5f;                  // = SCORE_SLACK of knn.cu
 constexpr float HI_SLACK = 1.05e-3f;
-template <int NQ, bool HILO> struct Cfg {
-    static constexpr int NCOL = (HILO ? 2 : 1) * NQ, B_KB_BYTES = NCOL * TK * 2, B_BYTES = KB * B_KB_BYTES;
-    static constexpr int STAGES = NCOL <= 32 ? 8 : NCOL <= 64 ? 6 : 4;      // (6 stages fit for 128 columns too, but measured no faster: that case is bound by the epilogue / MMA, not by bytes in flight)
+// F32 (round 2): fp32 databases on the tensor cores -- rows and queries stay fp32 in shared memory and are read as tf32 by kind::tf32 MMAs
+// (32 floats = 128 bytes per k-block, 16 k-blocks per 512-d row tile, hi-only queries).  Both operands lose their low 13 mantissa bits:
+// |scan score - exact score| <= 2 * 2^-10, decisions relaxed by F32_SLACK >= 2 * that bound.  Replaces the CUDA-core scan in passes of 16
+// queries (0.42 of the HBM peak at 16 queries, 0.10 at 64) for fp32 databases large enough for the fused scan.
+constexpr float F32_SLACK = 4.2e-3f;
+template <int NQ, bool HILO, bool F32 = false> struct Cfg {
+    static constexpr int KBN = F32 ? 16 : KB, TKN = F32 ? 32 : TK;             // k-blocks per row tile, elements per k-block (always 128 bytes)
+    static constexpr int NCOL = (HILO ? 2 : 1) * NQ, B_KB_BYTES = NCOL * 128, B_BYTES = KBN * B_KB_BYTES;
+    static_assert(!(F32 && HILO), "fp32 databases: hi-only (fp32 query rows read as tf32)");
+    static constexpr int STAGES = F32 ? 4 : NCOL <= 32 ? 8 : NCOL <= 64 ? 6 : 4;      // (6 stages fit for 128 columns too, but measured no faster: that case is bound by the epilogue / MMA, not by bytes in flight)
     static constexpr int SMEM_TOTAL = STAGES * A_BYTES + B_BYTES + 1024 + 1024;
     static_assert(SMEM_TOTAL <= 232448, "kNN tensor-core scan: shared-memory budget");
     static constexpr int TMEM_COLS = 2 * NCOL <= 64 ? 64 : 2 * NCOL <= 128 ? 128 : 256;
@@ -52,6 +60,14 @@ __global__ void split_queries_kernel(const float* __restrict__ q, int nq, int NQ
     __half h = __float2half_rn(v);
     out[(size_t)qi * D + c] = h;
     out[(size_t)(NQ + qi) * D + c] = __float2half_rn(v - __half2float(h));
+}
+
+// fp32 databases: q fp32 [nq, 512] -> NQ fp32 rows (zero rows beyond nq) for the kind::tf32 scan
+__global__ void pad_queries_f32_kernel(const float* __restrict__ q, int nq, int NQ, float* __restrict__ out, unsigned* __restrict__ grid_bar) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && grid_bar) *grid_bar = 0u;
+    if (i >= NQ * D) return;
+    out[i] = i / D < nq ? q[i] : 0.f;
 }
 
 // SAMPLE: visits every `tile_stride`-th row tile and writes the key of EVERY (row, query) to maxima[q][sample_row] (per_q keys per
@@ -212,13 +228,14 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // Expected survivors per query ~ k_eff * n / (32 * t_sample * 4 * grid); the host sizes t_sample for ~512.
 constexpr int FUSED_MAXV = 20;                       // group maxima per lane in the threshold bisection: 4 * grid <= 32 * FUSED_MAXV
 
-template <int NQ, bool HILO>
+template <int NQ, bool HILO, bool F32>
 __global__ void __launch_bounds__(THREADS, 1)
 knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ inv, long long n,
                       int nq_valid, int k_eff, int t_sample, u64* __restrict__ cand, unsigned* __restrict__ cand_cnt, unsigned* __restrict__ overflow,
                       uint32_t* __restrict__ gmax, unsigned* __restrict__ grid_bar, float slack) {
-    constexpr int NCOL = Cfg<NQ, HILO>::NCOL, B_KB_BYTES = Cfg<NQ, HILO>::B_KB_BYTES, B_BYTES = Cfg<NQ, HILO>::B_BYTES, STAGES = Cfg<NQ, HILO>::STAGES;
+    constexpr int NCOL = Cfg<NQ, HILO, F32>::NCOL, B_KB_BYTES = Cfg<NQ, HILO, F32>::B_KB_BYTES, B_BYTES = Cfg<NQ, HILO, F32>::B_BYTES, STAGES = Cfg<NQ, HILO, F32>::STAGES;
     constexpr int NGRP = (NQ / 16 + EPI_PER_Q - 1) / EPI_PER_Q;          // 16-query groups per epilogue warp
+    constexpr int KBN = Cfg<NQ, HILO, F32>::KBN, TKN = Cfg<NQ, HILO, F32>::TKN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sB = smem + STAGES * A_BYTES;
@@ -245,7 +262,7 @@ knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg<NQ, HILO>::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg<NQ, HILO, F32>::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -256,21 +273,21 @@ knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 0) {
         if (lane == 0) {
             mbar_expect_tx(b_full, B_BYTES);                          // the queries: loaded once, resident for the whole kernel
-            for (int kb = 0; kb < KB; kb++) tma_load_2d(sB + kb * B_KB_BYTES, &tmB, b_full, kb * TK, 0);
+            for (int kb = 0; kb < KBN; kb++) tma_load_2d(sB + kb * B_KB_BYTES, &tmB, b_full, kb * TKN, 0);
             long long it = 0;
             for (long long p = 0; p < nseq; p++) {
                 const long long tile = tile_at(p);
-                for (int kb = 0; kb < KB; kb++, it++) {
+                for (int kb = 0; kb < KBN; kb++, it++) {
                     const int s = (int)(it % STAGES); const uint32_t ph = (uint32_t)((it / STAGES) & 1);
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], A_BYTES);
-                    tma_load_2d(smem + s * A_BYTES, &tmA, &full[s], kb * TK, (int)(tile * TM));
+                    tma_load_2d(smem + s * A_BYTES, &tmA, &full[s], kb * TKN, (int)(tile * TM));
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(NCOL, /*f16=*/1);
+            const uint32_t idesc = F32 ? umma_idesc_tf32(NCOL) : umma_idesc_bf16(NCOL, /*f16=*/1);
             mbar_wait(b_full, 0);
             long long it = 0;
             for (long long p = 0; p < nseq; p++) {
@@ -278,13 +295,16 @@ knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_wait(&tmem_empty[buf], (uint32_t)(((p >> 1) & 1) ^ 1));
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(buf * NCOL);
-                for (int kb = 0; kb < KB; kb++, it++) {
+                for (int kb = 0; kb < KBN; kb++, it++) {
                     const int s = (int)(it % STAGES); const uint32_t ph = (uint32_t)((it / STAGES) & 1);
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t a = smem_u32(smem + s * A_BYTES), b = smem_u32(sB + kb * B_KB_BYTES);
 #pragma unroll
-                    for (int k = 0; k < TK / 16; k++) umma_bf16(tmem_d, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc, (kb | k) != 0);
+                    for (int k = 0; k < 4; k++) {                      // four 32-byte K slices per 128-byte k-block (16 halves or 8 floats each)
+                        if (F32) umma_tf32(tmem_d, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc, (kb | k) != 0);
+                        else umma_bf16(tmem_d, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc, (kb | k) != 0);
+                    }
                     umma_commit(&empty[s]);
                 }
                 umma_commit(&tmem_full[buf]);
@@ -440,7 +460,7 @@ knn_scan_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg<NQ, HILO>::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg<NQ, HILO, F32>::TMEM_COLS) : "memory");
     }
 }
 
@@ -453,15 +473,16 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     }
     return fn;
 }
-int make_map(CUtensorMap* tm, const void* base, long long rows, int box_rows) {
+int make_map(CUtensorMap* tm, const void* base, long long rows, int box_rows, bool f32 = false) {
     auto enc = get_encode();
     RDM_REQUIRE(enc, RDM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const int esz = f32 ? 4 : 2;
     cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)D * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)box_rows}, estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t strides[1] = {(cuuint64_t)D * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows}, estr[2] = {1, 1};
+    CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    RDM_REQUIRE(r == CUDA_SUCCESS, RDM_ERR_CUDA, "cuTensorMapEncodeTiled(knn rows=%lld) failed: %d", rows, (int)r);
+    RDM_REQUIRE(r == CUDA_SUCCESS, RDM_ERR_CUDA, "cuTensorMapEncodeTiled(kNN, %lld rows, box %d, %s) failed: %d", rows, box_rows, f32 ? "fp32" : "fp16", (int)r);
     return RDM_OK;
 }
 
@@ -484,21 +505,21 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const float* inv, long 
 }
 
 
-template <int NQ, bool HILO>
+template <int NQ, bool HILO, bool F32 = false>
 int launch_fused(const CUtensorMap& ta, const CUtensorMap& tb, const float* inv, long long n, int device, int nq_valid, int k_eff, int t_sample,
                  u64* cand, unsigned* cand_cnt, unsigned* overflow, uint32_t* gmax, unsigned* grid_bar, int grid, float slack, cudaStream_t st) {
-    auto kern = knn_scan_fused_kernel<NQ, HILO>;
+    auto kern = knn_scan_fused_kernel<NQ, HILO, F32>;
     static int ok[16] = {0};                          // 0 unknown, 1 usable, -1 not (no cooperative launch / grid does not fit)
     if (ok[device & 15] == 0) {
-        RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NQ, HILO>::SMEM_TOTAL));
+        RDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NQ, HILO, F32>::SMEM_TOTAL));
         int coop = 0, per_sm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, Cfg<NQ, HILO>::SMEM_TOTAL);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, Cfg<NQ, HILO, F32>::SMEM_TOTAL);
         ok[device & 15] = (coop && per_sm >= 1) ? 1 : -1;
     }
     if (ok[device & 15] < 0) return 1;                // caller falls back to the three-kernel path
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = Cfg<NQ, HILO>::SMEM_TOTAL; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = Cfg<NQ, HILO, F32>::SMEM_TOTAL; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;      // every CTA resident at once: the in-kernel grid barrier cannot deadlock
     cfg.attrs = attr; cfg.numAttrs = 1;
@@ -573,4 +594,31 @@ int knn_scan_tc_fused(const void* db_f16, const float* inv, long long n, int dev
     if (NQ == 32) return launch_fused<32, false>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, HI_SLACK, st);
     if (NQ == 64) return launch_fused<64, false>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, HI_SLACK, st);
     return launch_fused<128, false>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, HI_SLACK, st);
+}
+
+// fp32 database (d = 512): the same fused scan on kind::tf32 MMAs, passes of up to 64 queries.  Same return convention as knn_scan_tc_fused.
+int knn_scan_tc_fused_f32(const void* db_f32, const float* inv, long long n, int device, const float* q, int nq_valid, int k, void* qpad_ws,
+                          unsigned long long* cand, unsigned* cand_cnt, unsigned* overflow, void* fused_ws, float* slack_used, cudaStream_t st) {
+    RDM_REQUIRE(nq_valid >= 1 && nq_valid <= 64, RDM_ERR_ARG, "knn_scan_tc_fused_f32: %d queries", nq_valid);
+    static const int off = getenv("RDM_KNN_NO_TF32") ? 1 : 0;
+    const int sms = rdm_num_sms(device);
+    const long long ntiles = (n + TM - 1) / TM;
+    if (off || ntiles < 4LL * sms || 4 * sms > 32 * FUSED_MAXV) return 1;
+    const int grid = sms;
+    const int NQ = nq_valid <= 16 ? 16 : nq_valid <= 32 ? 32 : 64;
+    const int k_eff = k < 8 ? 8 : k;
+    long long t_sample = (long long)((double)k_eff * (double)n / (32.0 * 4.0 * grid * 700.0)) + 1;
+    const long long cap = ntiles / grid / 8 > 1 ? ntiles / grid / 8 : 1;
+    if (t_sample > cap) t_sample = cap;
+    uint32_t* gmax = reinterpret_cast<uint32_t*>(fused_ws);
+    unsigned* grid_bar = knn_tc_fused_grid_bar(fused_ws, device);
+    pad_queries_f32_kernel<<<(NQ * D + 255) / 256, 256, 0, st>>>(q, nq_valid, NQ, (float*)qpad_ws, grid_bar);
+    RDM_COUNT_LAUNCH();
+    CUtensorMap ta, tb;
+    RDM_TRY(make_map(&ta, db_f32, n, TM, true));
+    RDM_TRY(make_map(&tb, qpad_ws, NQ, NQ, true));
+    *slack_used = F32_SLACK;
+    if (NQ == 16) return launch_fused<16, false, true>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, F32_SLACK, st);
+    if (NQ == 32) return launch_fused<32, false, true>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, F32_SLACK, st);
+    return launch_fused<64, false, true>(ta, tb, inv, n, device, nq_valid, k_eff, (int)t_sample, cand, cand_cnt, overflow, gmax, grid_bar, grid, F32_SLACK, st);
 }

@@ -18,3 +18,7 @@ int knn_scan_tc_fused(const void* db_f16, const float* inv, long long n, int dev
 // *slack_used: the score slack the pass decided with (hi + lo query rows: 3e-5; hi rows only, more than 16 queries: 1.05e-3) -- the select
 // kernel's cut must use the same value.  Up to 128 queries per fused pass; knn_scan_tc (the three-kernel path) takes at most 64.
 unsigned* knn_tc_fused_grid_bar(void* fused_ws, int device);
+// fp32 databases (d = 512): the fused scan on kind::tf32 MMAs (rows and queries read as tf32, slack 4.2e-3), at most 64 queries per pass;
+// qpad_ws: knn_tc_queries_bytes() bytes.  Returns like knn_scan_tc_fused (1: not usable here -> CUDA-core scan).
+int knn_scan_tc_fused_f32(const void* db_f32, const float* inv, long long n, int device, const float* q, int nq_valid, int k, void* qpad_ws,
+                          unsigned long long* cand, unsigned* cand_cnt, unsigned* overflow, void* fused_ws, float* slack_used, cudaStream_t st);

@@ -35,3 +35,6 @@ int knn_scan_tc_fused(const void*, const float*, long long, int, const float*, i
     rdm_set_error("emulation: the tcgen05 kNN scan is not available on the host (set RDM_KNN_NO_TC=1)");
     return RDM_ERR_UNSUPPORTED;
 }
+int knn_scan_tc_fused_f32(const void*, const float*, long long, int, const float*, int, int, void*, unsigned long long*, unsigned*, unsigned*, void*, float*, cudaStream_t) {
+    return 1;       // not usable under emulation: the caller takes the CUDA-core scan
+}

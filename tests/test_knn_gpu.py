@@ -137,18 +137,20 @@ def test_query_normalisation_inside_the_library_is_bit_identical_to_numpy(cuda, 
     assert np.array_equal(a[0].cpu().numpy(), ri) and np.array_equal(a[2].cpu().numpy().view(np.uint64), rs.view(np.uint64))
 
 
-@pytest.mark.parametrize("nq,k", [(37, 20), (64, 8), (100, 20), (130, 4)])
-def test_wide_hi_only_passes_stay_exact_on_near_duplicate_clusters(cuda, nq, k):
+@pytest.mark.parametrize("nq,k,dtype", [(37, 20, np.float16), (64, 8, np.float16), (100, 20, np.float16), (130, 4, np.float16),
+                                        (5, 8, np.float32), (37, 20, np.float32), (100, 4, np.float32)])
+def test_wide_hi_only_passes_stay_exact_on_near_duplicate_clusters(cuda, nq, k, dtype):
     """Passes of more than 16 queries over a database large enough for the fused scan keep only the fp16 hi rows of the queries (up to 128
     queries per pass): the scan score is then off by up to 2^-11, far more than the spacing inside a cluster of near-duplicate rows.  The
     wider score slack of such a pass (thresholds and the select cut, knn_tc.cu: HI_SLACK) must keep every true neighbour among the rows
-    that are re-ranked exactly: indices and fp64 scores bit-identical to the oracle, on clustered and on plain queries."""
+    that are re-ranked exactly: indices and fp64 scores bit-identical to the oracle, on clustered and on plain queries.  fp32 databases take
+    the same fused scan on kind::tf32 MMAs (rows AND queries cut to 10 mantissa bits, slack 4.2e-3, passes of 64)."""
     from oracle import knn as oknn
     from rdm_b200.knn import B200Searcher
     n = 200_000
     rng = np.random.default_rng(1000 + nq)
-    db = (rng.standard_normal((n, 512)) * rng.uniform(0.5, 8, (n, 1))).astype(np.float16)
-    db[5000:5600] = db[5000] + (rng.standard_normal((600, 512)) * 2e-3).astype(np.float16)           # 600 rows within ~1e-6 of each other in cosine
+    db = (rng.standard_normal((n, 512)) * rng.uniform(0.5, 8, (n, 1))).astype(dtype)
+    db[5000:5600] = db[5000] + (rng.standard_normal((600, 512)) * 2e-3).astype(dtype)                # 600 rows within ~1e-6 of each other in cosine
     db[90_000:90_050] = db[90_000]                                                                      # exact duplicates: ties broken by index
     q = rng.standard_normal((nq, 512)).astype(np.float32)
     q[0], q[nq // 2], q[nq - 1] = db[5000].astype(np.float32), db[5300].astype(np.float32) * 3.0, db[90_010].astype(np.float32)
@@ -158,3 +160,22 @@ def test_wide_hi_only_passes_stay_exact_on_near_duplicate_clusters(cuda, nq, k):
     assert set(wi[0]) <= set(range(5000, 5600)) and list(wi[nq - 1][:k]) == list(range(90_000, 90_000 + k))
     assert np.array_equal(idx.cpu().numpy(), wi)
     assert np.array_equal(sc.cpu().numpy().view(np.int64), ws.view(np.int64))
+
+
+@pytest.mark.parametrize("n,nq", [(30_000, 100), (30_000, 129), (90_000, 70)])
+def test_more_than_64_queries_on_databases_with_and_without_the_fused_scan(cuda, n, nq):
+    """Passes of up to 128 queries exist only on the fused scan; a database too small for it (fewer than 4 tiles per SM) takes the
+    three-kernel path, which splits a pass of more than 64 queries in two.  Both entry points (normalised and raw queries) against the
+    oracle, bit-exact."""
+    from oracle import knn as oknn
+    from rdm_b200.knn import B200Searcher
+    rng = np.random.default_rng(n + nq)
+    db = (rng.standard_normal((n, 512)) * rng.uniform(0.5, 8, (n, 1))).astype(np.float16)
+    q = rng.standard_normal((nq, 512)).astype(np.float32) * 5.0
+    q[3] = db[777].astype(np.float32)
+    qh = oknn.normalize_queries(q)
+    s = B200Searcher(db, device=cuda)
+    wi, wd, ws = oknn.search(db, qh, 5, return_scores=True)
+    for idx, dist, sc in (s.search_device(torch.from_numpy(qh).to(cuda), 5, return_scores=True), s.search_raw_device(torch.from_numpy(q).to(cuda), 5, return_scores=True)):
+        assert np.array_equal(idx.cpu().numpy(), wi) and wi[3, 0] == 777
+        assert np.array_equal(sc.cpu().numpy().view(np.int64), ws.view(np.int64))
