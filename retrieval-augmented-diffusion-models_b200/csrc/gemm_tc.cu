@@ -55,7 +55,12 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); 
 struct TcKernelParams {
     int M, N;                  // valid rows / columns of the output
     int taps, kb_per_tap;      // K blocks: taps * kb_per_tap, each BK=64 wide
-    int ksize;                 // 1 or 3 (tap -> (dy,dx))
+    int kb2;                   // K extension (TcA::hi2): kb2 more k-blocks whose A tile comes from the SECOND activation (same pixels, no shift) and whose
+                               // weights come from the second weight matrix -- both through the otherwise unused `lo` tensor maps (NSPLIT = 1 only)
+    int ksize;                 // 1 or 3 (tap -> (dy,dx)); 2: the 2x2 taps of one output parity of an upsample-folded conv (ups)
+    int ups;                   // 1: 3x3 conv over the 2x nearest-upsampled image, folded (TcA::ups): 4 x the work items, one quarter per output
+                               // parity (py, px); taps (ty, tx) read source pixel (y + ty + py - 1, x + tx + px - 1); weights of parity q are rows
+                               // [q * N, (q + 1) * N) of the [4 N, 4 C] matrix; GEMM row (b, y, x) is stored to output row (b, 2 y + py, 2 x + px)
     int plain;                 // 1: A is a plain [M, C] matrix encoded as (c, m, 1, 1): tile -> x0 = mt*128
     int bw, bh, bb;            // box extents (x, y, batch): bw*bh*bb == 128
     int H, W;                  // logical output grid per image (for tile -> (b,y,x))
@@ -285,7 +290,7 @@ __device__ __forceinline__ void epi_stats_flush(const TcKernelParams& p, float* 
 // THIS chunk (epi_prefetch / xattn_prefetch), requested by the caller one whole chunk earlier.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const uint32_t (&r)[32], float* stage, int lane, int m_warp0, int nb, const EpiPre& pre, XPre& xp, float* part,
-                                               float* s_stat, int stat_col, int BN) {
+                                               float* s_stat, int stat_col, int BN, int par) {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
@@ -406,7 +411,17 @@ __device__ __forceinline__ void epilogue_chunk(const TcKernelParams& p, const ui
             t[it] = make_float4(t[it].x + bb.x + pre.r[it].x, t[it].y + bb.y + pre.r[it].y, t[it].z + bb.z + pre.r[it].z, t[it].w + bb.w + pre.r[it].w);
         }
         if (p.stats) epi_stats(p, t, lane, m_warp0, stat_col + cg, s_stat, BN);
-        if (p.out) {
+        if (p.ups) {                               // upsample-folded conv: GEMM row (b, y, x) of parity (py, px) is output pixel (b, 2 y + py, 2 x + px)
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int mo = m_warp0 + r0 + 4 * it;
+                if (mo >= p.M) continue;
+                const int x = mo % p.W, yb = mo / p.W, y = yb % p.H, b = yb / p.H;
+                const size_t row = ((size_t)(b * 2 * p.H + 2 * y + (par >> 1)) * (2 * p.W) + 2 * x + (par & 1));
+                if (p.out) *reinterpret_cast<float4*>(p.out + row * p.out_ld + n) = t[it];
+                else store_planes4(p.out_hi + row * p.out_bf_ld + n, p.out_lo ? p.out_lo + row * p.out_bf_ld + n : nullptr, p.f16, t[it].x, t[it].y, t[it].z, t[it].w);
+            }
+        } else if (p.out) {
 #pragma unroll
             for (int it = 0; it < 8; it++) {
                 const int mo = m_warp0 + r0 + 4 * it;
@@ -491,8 +506,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     for (int i = threadIdx.x; i < 2 * BN; i += TC_THREADS) stat_base[i] = 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = p.taps * p.kb_per_tap;
-    const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + BM - 1) / BM, nitems = ntn * ntm * p.splits;
+    const int nkb_main = p.taps * p.kb_per_tap, nkb = nkb_main + (NSPLIT == 1 ? p.kb2 : 0);
+    const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + BM - 1) / BM, nitems_q = ntn * ntm * p.splits, nitems = nitems_q * (p.ups ? 4 : 1);
 #ifdef RDM_AB_TIMING
     unsigned long long gt0 = 0;
     if (threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0)); for (int i = 0; i < 24; i++) g_ts[i] = 0; TSTAMP(0); }
@@ -503,7 +518,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmB_hi);
         if (NSPLIT >= 2) prefetch_tmap(&tmB_lo);
-        if (NSPLIT == 3) prefetch_tmap(&tmA_lo);
+        if (NSPLIT == 3 || (NSPLIT == 1 && p.kb2)) prefetch_tmap(&tmA_lo);
+        if (NSPLIT == 1 && p.kb2) prefetch_tmap(&tmB_lo);
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
         fence_barrier_init();
@@ -528,14 +544,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             // PDL prologue: the WEIGHT tiles of the first stages do not depend on the previous kernel -> request them before waiting
             int pre = 0;
             {
-                const int item = blockIdx.x;
-                if (p.pdl && item < nitems) {
+                const int item0 = blockIdx.x;
+                if (p.pdl && item0 < nitems) {
+                    const int par = p.ups ? item0 / nitems_q : 0, item = item0 - par * nitems_q;
                     const int tile = item / p.splits, sp = item - tile * p.splits;
-                    const int kb0 = sp * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split), n0 = (tile % ntn) * BN;
+                    const int kb0 = sp * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split), n0 = (tile % ntn) * BN + par * p.N;
                     for (int kb = kb0; kb < kb1 && pre < STAGES; kb++, pre++) {
                         uint8_t* st = smem + pre * S::STAGE_BYTES;
                         mbar_expect_tx(&full[pre], S::STAGE_BYTES);
-                        tma_load_2d(st + S::A_BYTES, &tmB_hi, &full[pre], kb * BK, n0);
+                        if (NSPLIT == 1 && kb >= nkb_main) tma_load_2d(st + S::A_BYTES, &tmB_lo, &full[pre], (kb - nkb_main) * BK, n0);
+                        else tma_load_2d(st + S::A_BYTES, &tmB_hi, &full[pre], kb * BK, n0);
                         if (NSPLIT >= 2) tma_load_2d(st + S::A_BYTES + S::B_BYTES, &tmB_lo, &full[pre], kb * BK, n0);
                     }
                 }
@@ -543,10 +561,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             pdl_wait();                                                  // activations / residuals of the previous kernels are now visible
             TSTAMP(2);
             int it = 0;                                                  // global k-block counter (ring position)
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            for (int item0 = blockIdx.x; item0 < nitems; item0 += gridDim.x) {
+                const int par = p.ups ? item0 / nitems_q : 0, item = item0 - par * nitems_q;
                 const int tile = item / p.splits, sp = item - tile * p.splits;
                 const int kb0 = sp * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
-                const int mt = tile / ntn, n0 = (tile % ntn) * BN;
+                const int mt = tile / ntn, n0 = (tile % ntn) * BN + par * p.N;     // (ups: row block of this parity's weights)
                 int x0 = 0, y0 = 0, b0 = 0;                              // tile origin in (x, y, b) of the NHWC plane
                 if (p.plain) x0 = mt * BM;
                 else if (p.W > BM) { const int tpr = p.W / BM; x0 = (mt % tpr) * BM; y0 = (mt / tpr) % p.H; b0 = mt / (tpr * p.H); }   // wide images: a tile is a 128-pixel piece of one row
@@ -557,8 +576,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     uint8_t* st = smem + s * S::STAGE_BYTES;
                     const bool prefetched = it < pre;                    // weights already requested (and the barrier armed) before pdl_wait
                     if (!prefetched) { mbar_wait(&empty[s], ph ^ 1); mbar_expect_tx(&full[s], S::STAGE_BYTES); }
+                    if (NSPLIT == 1 && kb >= nkb_main) {                // K extension: the second activation / weight pair (ResBlock skip_connection)
+                        const int kc2 = (kb - nkb_main) * BK;
+                        tma_load_4d(st, &tmA_lo, &full[s], kc2, x0, y0, b0);
+                        if (!prefetched) tma_load_2d(st + S::A_BYTES, &tmB_lo, &full[s], kc2, n0);
+                        continue;
+                    }
                     const int tap = kb / p.kb_per_tap, kc = (kb - tap * p.kb_per_tap) * BK;
-                    const int dy = p.ksize == 3 ? tap / 3 - 1 : 0, dx = p.ksize == 3 ? tap % 3 - 1 : 0;
+                    const int dy = p.ksize == 3 ? tap / 3 - 1 : p.ksize == 2 ? (tap >> 1) + (par >> 1) - 1 : 0;
+                    const int dx = p.ksize == 3 ? tap % 3 - 1 : p.ksize == 2 ? (tap & 1) + (par & 1) - 1 : 0;
                     tma_load_4d(st, &tmA_hi, &full[s], kc, x0 + dx, y0 + dy, b0);
                     if (!prefetched) {
                         tma_load_2d(st + S::A_BYTES, &tmB_hi, &full[s], kb * BK, n0);
@@ -622,7 +648,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     *reinterpret_cast<float4*>(red + c * 32 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
             }
         } else
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x, lt++) {
+        for (int item0 = blockIdx.x; item0 < nitems; item0 += gridDim.x, lt++) {
+            const int par = p.ups ? item0 / nitems_q : 0, item = item0 - par * nitems_q;
             const int tile = item / p.splits, sp = item - tile * p.splits;
             float* part = p.splits > 1 ? p.part + (size_t)sp * p.M * p.N : nullptr;    // raw partial sums; the reduce kernel applies the epilogue
             const int buf = lt & 1;
@@ -656,7 +683,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 }
                 uint32_t r[32];
                 tmem_ld32(taddr, r);
-                if (nb + 32 <= p.N) epilogue_chunk<EPI>(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb, pre, xp, part, stat_base, c * 32, BN);
+                if (nb + 32 <= p.N) epilogue_chunk<EPI>(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb, pre, xp, part, stat_base, c * 32, BN, par);
                 else if (EPI == EPI_ANY) epilogue_ragged(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0 + lane, nb);     // (split-K needs N % 4 == 0 ... never a partial tile here)
                 if (has_next) { if (xat) xp = xp_nx; else pre = pre_nx; }
             }
@@ -733,7 +760,7 @@ struct Tc2Smem {
     static_assert(TOTAL <= 232448, "shared memory budget");
     static_assert((BN / 2) % 8 == 0 && BN % 32 == 0, "the B half tile is whole 8-row swizzle groups");
 };
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcKernelParams p) {
     using S = Tc2Smem<BN, STAGES>;
@@ -822,7 +849,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int mt = 2 * (item / ntn) + (int)rank, n0 = (item % ntn) * BN;
             const int m_warp0 = mt * BM + q * 32;
             EpiPre pre, pre_nx; XPre xp;
-            if (m_warp0 < p.M && n0 + half * 32 + 32 <= p.N) epi_prefetch<EPI_PLAIN>(p, lane, m_warp0, n0 + half * 32, pre);
+            if (m_warp0 < p.M && n0 + half * 32 + 32 <= p.N) epi_prefetch<EPI>(p, lane, m_warp0, n0 + half * 32, pre);
             mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -832,10 +859,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (m_warp0 >= p.M || nb + 32 > p.N) continue;
                 const int nbn = nb + 64;
                 const bool has_next = c + 2 < BN / 32 && nbn + 32 <= p.N;
-                if (has_next) epi_prefetch<EPI_PLAIN>(p, lane, m_warp0, nbn, pre_nx);
+                if (has_next) epi_prefetch<EPI>(p, lane, m_warp0, nbn, pre_nx);
                 uint32_t r[32];
                 tmem_ld32(taddr, r);
-                epilogue_chunk<EPI_PLAIN>(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb, pre, xp, nullptr, nullptr, 0, BN);
+                epilogue_chunk<EPI>(p, r, epi_stage + ew * EPI_WARP_FLOATS, lane, m_warp0, nb, pre, xp, nullptr, nullptr, 0, BN, 0);
                 if (has_next) pre = pre_nx;
             }
             tc_fence_before();
@@ -915,7 +942,7 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
         *cluster_cap = c > 0 ? c : 0;
         return RDM_OK;
     }
-    const int nitems = ((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * p.splits;
+    const int nitems = ((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * p.splits * (p.ups ? 4 : 1);
     const int sms = rdm_num_sms(dev);
     const int use_pdl = g_rdm_use_pdl;
     TcKernelParams pl = p; pl.pdl = use_pdl && !p.pdl_off;
@@ -932,9 +959,9 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     return RDM_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const TcKernelParams& p, cudaStream_t st) {
-    auto kern = gemm_tc2_kernel<BN, STAGES>;
+    auto kern = gemm_tc2_kernel<BN, STAGES, EPI>;
     constexpr int smem = Tc2Smem<BN, STAGES>::TOTAL;
     static bool configured[16] = {false};
     int dev = 0; cudaGetDevice(&dev);
@@ -1013,23 +1040,32 @@ bool gemm_tc_supported(const TcA& a) {
 int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_bf_ld, int nsplit, int f16, cudaStream_t st) {
     RDM_REQUIRE(gemm_tc_supported(a), RDM_ERR_UNSUPPORTED, "gemm_tc: shape not supported (C=%d W=%d H=%d ks=%d)", a.C, a.W, a.H, a.ksize);
     RDM_REQUIRE(nsplit >= 1 && nsplit <= 3 && a.hi && w.hi && (nsplit < 2 || w.lo) && (nsplit < 3 || a.lo), RDM_ERR_ARG, "gemm_tc: missing operand plane (nsplit %d)", nsplit);
-    RDM_REQUIRE(w.K == a.ksize * a.ksize * a.C && w.ld % 8 == 0, RDM_ERR_ARG, "gemm_tc: weight K=%d vs %d", w.K, a.ksize * a.ksize * a.C);
+    const int ntaps = a.ups ? 4 : a.ksize * a.ksize;
+    RDM_REQUIRE(w.K == ntaps * a.C && w.ld % 8 == 0, RDM_ERR_ARG, "gemm_tc: weight K=%d vs %d", w.K, ntaps * a.C);
+    const bool ext = a.hi2 != nullptr;
+    RDM_REQUIRE(!a.ups || (a.ksize == 3 && a.W <= BM && !ext && e.act == ACT_NONE && !e.res && !e.rowvec && (w.N & 31) == 0), RDM_ERR_ARG,
+                "gemm_tc: upsample-folded conv needs a plain epilogue and N %% 32 == 0 (N=%d W=%d)", w.N, a.W);
+    RDM_REQUIRE(!ext || (nsplit == 1 && w.hi2 && a.C2 > 0 && a.C2 % BK == 0 && a.ld2 % 8 == 0 && w.ld2 % 8 == 0), RDM_ERR_ARG, "gemm_tc: K extension needs one-plane operands and C2 %% 64 == 0 (C2=%d nsplit=%d)", a.C2, nsplit);
     TcKernelParams p{};
     const int M = a.B * a.H * a.W;
-    p.M = M; p.N = w.N; p.taps = a.ksize * a.ksize; p.kb_per_tap = a.C / BK; p.ksize = a.ksize; p.H = a.H; p.W = a.W;
+    p.M = M; p.N = w.N; p.taps = ntaps; p.kb_per_tap = a.C / BK; p.ksize = a.ups ? 2 : a.ksize; p.ups = a.ups ? 1 : 0; p.H = a.H; p.W = a.W;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     if (a.ksize == 1) {
         // plain [M, C] matrix: box = 128 rows
         p.plain = 1; p.bw = BM; p.bh = 1; p.bb = 1;
         // encode as (c, m, 1, 1): x = m
         RDM_TRY(make_map_4d(&ta_hi, a.hi, a.C, M, 1, 1, a.ld, BM, 1, 1));
-        if (nsplit == 3) RDM_TRY(make_map_4d(&ta_lo, a.lo, a.C, M, 1, 1, a.ld, BM, 1, 1)); else ta_lo = ta_hi;
+        if (nsplit == 3) RDM_TRY(make_map_4d(&ta_lo, a.lo, a.C, M, 1, 1, a.ld, BM, 1, 1));
+        else if (ext) RDM_TRY(make_map_4d(&ta_lo, a.hi2, a.C2, M, 1, 1, a.ld2, BM, 1, 1));
+        else ta_lo = ta_hi;
     } else {
         const int W = a.W, H = a.H;
         if (W > BM) { p.bw = BM; p.bh = 1; p.bb = 1; }
         else { p.bw = W; p.bh = (BM / W) < H ? (BM / W) : H; p.bb = BM / (p.bw * p.bh); }
         RDM_TRY(make_map_4d(&ta_hi, a.hi, a.C, W, H, a.B, a.ld, p.bw, p.bh, p.bb));
-        if (nsplit == 3) RDM_TRY(make_map_4d(&ta_lo, a.lo, a.C, W, H, a.B, a.ld, p.bw, p.bh, p.bb)); else ta_lo = ta_hi;
+        if (nsplit == 3) RDM_TRY(make_map_4d(&ta_lo, a.lo, a.C, W, H, a.B, a.ld, p.bw, p.bh, p.bb));
+        else if (ext) RDM_TRY(make_map_4d(&ta_lo, a.hi2, a.C2, W, H, a.B, a.ld2, p.bw, p.bh, p.bb));      // same boxes, centre tap only
+        else ta_lo = ta_hi;
     }
     p.bias = e.bias; p.rowvec = e.rowvec; p.rowvec_ld = e.rowvec_ld; p.rows_per_batch = e.rows_per_batch > 0 ? e.rows_per_batch : 1;
     p.res = e.res; p.res_ld = e.res_ld; p.act = e.act; p.out = e.out; p.out_ld = e.out_ld;
@@ -1052,19 +1088,28 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
         // gains nothing -- it already runs at the chip's burst tensor rate in both kernels (587 cycles per 128 x 192 x 64 k-block =
         // 1560 TFLOP/s over 148 SMs); RDM_TC_2SM=2 forces the pair kernel wherever it is legal.
         const int tiles1 = ((M + BM - 1) / BM) * ((w.N + 191) / 192);
-        const bool wins = use_2sm >= 2 || (tiles1 > 148 && w.N > 192 && p.taps * p.kb_per_tap >= 16);
-        if (use_2sm && wins && nsplit == 1 && bn2 && M >= min_m && M % (2 * BM) == 0 && e.act == ACT_NONE && !e.stats && !(e.rowvec && p.rows_per_batch < 16)) {
-            p.splits = 1; p.kb_per_split = p.taps * p.kb_per_tap; p.part = nullptr; p.cluster = 0; p.stats = nullptr; p.geglu_rows = 0;
+        // Short-K layers with MANY waves of tiles (the GEGLU projection: M = 8192, N = 3072, K = 384 -- 1024 tiles of 6 k-blocks, 415 TFLOP/s)
+        // looked bound by the operand traffic per tile ((128 + 192) x K x 2 bytes from L2 per 128 x 192 outputs; a pair shares the weight
+        // tile: 1.43x fewer bytes).  Measured: 4.176 ms per forward with pairs for them, 4.156 without -- they are bound by the GEGLU
+        // EPILOGUE (TMEM -> GELU -> fp16 stores of a tile take longer than its 6 k-blocks), which a pair does not shorten.  Opt-in:
+        // RDM_TC_2SM_WAVES = waves of one-CTA tiles from which short K qualifies (0, the default: never).
+        static const int short_k_waves = getenv("RDM_TC_2SM_WAVES") ? atoi(getenv("RDM_TC_2SM_WAVES")) : 0;
+        const bool geglu = e.act == ACT_GEGLU && p.geglu_rows;
+        const bool wins = use_2sm >= 2 || (tiles1 > 148 && w.N > 192 && (p.taps * p.kb_per_tap >= 16 || (short_k_waves > 0 && tiles1 >= short_k_waves * 148)));
+        if (use_2sm && wins && !ext && !a.ups && nsplit == 1 && bn2 && M >= min_m && M % (2 * BM) == 0 && (e.act == ACT_NONE || geglu) && !e.stats && !(e.rowvec && p.rows_per_batch < 16)) {
+            p.splits = 1; p.kb_per_split = p.taps * p.kb_per_tap; p.part = nullptr; p.cluster = 0; p.stats = nullptr; if (!geglu) p.geglu_rows = 0;
             RDM_TRY(make_map_2d(&tb_hi, w.hi, w.K, w.N, w.ld, bn2 / 2));
             if (e.stats_fused) *e.stats_fused = 0;
             if (getenv("RDM_TC_TRACE")) fprintf(stderr, "gemm_tc M=%d N=%d K=%d -> CTA pairs, BN=%d\n", M, w.N, w.K, bn2);
-            return bn2 == 192 ? launch_tc2<192, 6>(ta_hi, tb_hi, p, st) : launch_tc2<128, 7>(ta_hi, tb_hi, p, st);
+            if (geglu) return bn2 == 192 ? launch_tc2<192, 6, EPI_GEGLU>(ta_hi, tb_hi, p, st) : launch_tc2<128, 7, EPI_GEGLU>(ta_hi, tb_hi, p, st);
+            return bn2 == 192 ? launch_tc2<192, 6, EPI_PLAIN>(ta_hi, tb_hi, p, st) : launch_tc2<128, 7, EPI_PLAIN>(ta_hi, tb_hi, p, st);
         }
     }
     // Tile width and split-K.  The mainloop is operand-feed bound (TMA/L2 -> smem): one k-block of a work item costs ~(128 + BN)
     // (the 128-row A tile is re-loaded for every N tile); every item pays a fixed prologue/epilogue worth ~6 k-blocks.  Small-M layers
     // (4x4 / 8x8 latents) split K so that all SMs stream a slice of the weights.  cost = waves * (kb_per_item + 6) * (128 + BN).
-    const int mtiles = (M + BM - 1) / BM, sms = 148, nkb_total = p.taps * p.kb_per_tap;
+    p.kb2 = ext ? a.C2 / BK : 0;
+    const int mtiles = (M + BM - 1) / BM, sms = 148, nkb_total = p.taps * p.kb_per_tap + p.kb2;
     static const int forced = getenv("RDM_TC_BN") ? atoi(getenv("RDM_TC_BN")) : 0;
     static const int no_split = getenv("RDM_TC_NOSPLIT") ? 1 : 0;
     static const int use_cluster = getenv("RDM_TC_CLUSTER") ? atoi(getenv("RDM_TC_CLUSTER")) : 0;
@@ -1088,11 +1133,11 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
         for (int cl = 0; cl <= 1; cl++) {
             if (cl == 1 && use_cluster == 0) continue;
             for (int sp = cl ? 2 : 1; sp <= (cl ? 8 : 16); sp++) {
-                if (sp > 1 && (no_split || e.act == ACT_XATTN || nkb_total / sp < c_minkb || (w.N & 31) || (!cl && (size_t)sp * M * w.N * 4 > ((size_t)48 << 20)))) break;
+                if (sp > 1 && (no_split || a.ups || e.act == ACT_XATTN || nkb_total / sp < c_minkb || (w.N & 31) || (!cl && (size_t)sp * M * w.N * 4 > ((size_t)48 << 20)))) break;
                 if (sp > 1 && !cl && use_cluster == 2) break;
                 const int kbps = (nkb_total + sp - 1) / sp;
                 if ((sp - 1) * kbps >= nkb_total) continue;                  // an empty split
-                long items = (long)mtiles * nt * sp, waves = (items + sms - 1) / sms;
+                long items = (long)mtiles * nt * sp * (a.ups ? 4 : 1), waves = (items + sms - 1) / sms;
                 if (cl) {
                     TcKernelParams q = p; q.splits = sp; int cap = 0;
                     RDM_TRY(dispatch_tc(c, nsplit, tdummy, tdummy, tdummy, tdummy, q, st, &cap));
@@ -1108,7 +1153,7 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
     p.splits = splits; p.kb_per_split = (nkb_total + splits - 1) / splits; p.part = nullptr; p.cluster = clustered;
     // GroupNorm statistics in the epilogue: only on the straight path (no split-K: those tiles are finished by epi_store4), plain epilogue,
     // fp32 result, whole 32-column chunks, images of a multiple of 128 rows (a tile then lies in one image: the 32x32 and 16x16 levels)
-    const bool stats_ok = e.stats && splits == 1 && e.act == ACT_NONE && p.out && (w.N & 31) == 0 && !(e.rowvec && p.rows_per_batch < 16) &&
+    const bool stats_ok = e.stats && !a.ups && splits == 1 && e.act == ACT_NONE && p.out && (w.N & 31) == 0 && !(e.rowvec && p.rows_per_batch < 16) &&
                           e.stats_hw >= BM && e.stats_hw % BM == 0 && M % e.stats_hw == 0;
     p.stats = stats_ok ? e.stats : nullptr; p.stats_ld = e.stats_ld; p.stats_hw = e.stats_hw;
     if (e.stats_fused) *e.stats_fused = stats_ok ? 1 : 0;
@@ -1127,8 +1172,11 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
         }
         p.part = ws[dev & 15][slot];
     }
-    RDM_TRY(make_map_2d(&tb_hi, w.hi, w.K, w.N, w.ld, BN));
-    if (nsplit >= 2) RDM_TRY(make_map_2d(&tb_lo, w.lo, w.K, w.N, w.ld, BN)); else tb_lo = tb_hi;
+    const int w_rows = a.ups ? 4 * w.N : w.N;
+    RDM_TRY(make_map_2d(&tb_hi, w.hi, w.K, w_rows, w.ld, BN));
+    if (nsplit >= 2) RDM_TRY(make_map_2d(&tb_lo, w.lo, w.K, w_rows, w.ld, BN));
+    else if (ext) RDM_TRY(make_map_2d(&tb_lo, w.hi2, a.C2, w.N, w.ld2, BN));
+    else tb_lo = tb_hi;
     RDM_TRY(dispatch_tc(BN, nsplit, ta_hi, ta_lo, tb_hi, tb_lo, p, st, nullptr));
     if (splits > 1 && !p.cluster) {
         const long long n4 = (long long)M * (w.N >> 2);

@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace {
 
@@ -54,36 +55,58 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B
 
 // First convolution of the U-Net (openaimodel.py:141-145: conv_nd(dims, in_channels, model_channels, 3, padding=1) with 3 or 4 input
 // channels): K = 9 * Cin <= 36 is far too short for either GEMM engine (the generic CUDA-core engine took 65 us for 0.45 GFLOP at 32x32,
-// B2 = 32 -- 1.4 % of the forward).  Direct form: the weights [Cout][tap][Cin] are re-laid as [tap * Cin][Cout] in shared memory once per
-// CTA; a thread owns one pixel x 4 output channels (consecutive threads -> consecutive channel groups: coalesced 16-byte stores, the 9
-// input taps are broadcast loads); the CTA walks PIX pixels per round.
-template <int PIX>
+// B2 = 32 -- 1.4 % of the forward).  Direct form, register-tiled: a CTA owns TP = PG * 16 consecutive pixels and every output channel.
+// Shared memory holds the weights re-laid as [k = tap * Cin + c][Cout (+4 pad)] and the im2col patch of the CTA's pixels [TP][K] (zeros
+// for the padding ring); a thread owns 4 output channels x 16 pixels = 16 float4 accumulators, and per 4 k it reads 4 weight float4 and
+// 16 patch float4 (broadcast within the lanes of a pixel group) for 256 FMAs -- FMA-bound instead of shared-memory-bound (the first
+// version, one pixel x 4 channels per thread, re-read its weights for every pixel: 36 LDS.128 per 144 FMAs, 65 us under ncu).
+// Summation order per output: bias, then k ascending -- the order of the previous form and of the reference's fp32 convolution loop nest.
+constexpr int CF_PPT = 16;
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, int ld, int Cin, int B, int H, int W, const float* __restrict__ w,
                                                          const float* __restrict__ bias, int Cout, float* __restrict__ out, int out_ld) {
-    extern __shared__ float s_w[];                       // [9 * Cin][Cout]
-    const int K = 9 * Cin, G = Cout / 4;
-    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) { const int o = i / K, k = i - o * K; s_w[k * Cout + o] = w[i]; }
-    __syncthreads();
-    const long long M = (long long)B * H * W;
-    const long long p0 = (long long)blockIdx.x * PIX;
-    for (int it = threadIdx.x; it < PIX * G; it += blockDim.x) {
-        const long long m = p0 + it / G;
-        if (m >= M) break;
-        const int cg = (it % G) * 4;
-        const int px = (int)(m % W), py = (int)((m / W) % H);
-        float4 acc = bias ? *reinterpret_cast<const float4*>(bias + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int tap = 0; tap < 9; tap++) {
-            const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
-            if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-            const float* xi = x + (m + (long long)(tap / 3 - 1) * W + (tap % 3 - 1)) * ld;
-            for (int c = 0; c < Cin; c++) {
-                const float v = xi[c];
-                const float4 ww = *reinterpret_cast<const float4*>(s_w + (tap * Cin + c) * Cout + cg);
-                acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y); acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
-            }
+    extern __shared__ float s_cf[];
+    const int K = 9 * Cin, Kp = (K + 3) & ~3, LDW = Cout + 4, G = Cout / 4, PG = blockDim.x / G, TP = PG * CF_PPT;
+    float* s_w = s_cf;                                   // [Kp][LDW]
+    float* s_x = s_cf + Kp * LDW;                        // [TP][Kp]
+    for (int i = threadIdx.x; i < Kp * Cout; i += blockDim.x) { const int o = i / Kp, k = i - o * Kp; s_w[k * LDW + o] = k < K ? w[o * K + k] : 0.f; }
+    const long long M = (long long)B * H * W, p0 = (long long)blockIdx.x * TP;
+    for (int i = threadIdx.x; i < TP * Kp; i += blockDim.x) {
+        const int p = i / Kp, k = i - p * Kp;
+        const long long m = p0 + p;
+        float v = 0.f;
+        if (k < K && m < M) {
+            const int tap = k / Cin, c = k - tap * Cin, dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const int iy = (int)((m / W) % H) + dy, ix = (int)(m % W) + dx;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(m + (long long)dy * W + dx) * ld + c];
         }
-        *reinterpret_cast<float4*>(out + m * out_ld + cg) = acc;
+        s_x[i] = v;
+    }
+    __syncthreads();
+    const int cg = (threadIdx.x % G) * 4, pg = threadIdx.x / G;
+    if (pg >= PG) return;
+    float4 acc[CF_PPT];
+    const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < CF_PPT; p++) acc[p] = b4;
+    const float* xp = s_x + pg * CF_PPT * Kp;
+    for (int k4 = 0; k4 < Kp; k4 += 4) {
+        const float4 w0 = *reinterpret_cast<const float4*>(s_w + (k4 + 0) * LDW + cg), w1 = *reinterpret_cast<const float4*>(s_w + (k4 + 1) * LDW + cg);
+        const float4 w2 = *reinterpret_cast<const float4*>(s_w + (k4 + 2) * LDW + cg), w3 = *reinterpret_cast<const float4*>(s_w + (k4 + 3) * LDW + cg);
+#pragma unroll
+        for (int p = 0; p < CF_PPT; p++) {
+            const float4 v = *reinterpret_cast<const float4*>(xp + p * Kp + k4);
+            float4 a = acc[p];
+            a.x = fmaf(v.x, w0.x, a.x); a.y = fmaf(v.x, w0.y, a.y); a.z = fmaf(v.x, w0.z, a.z); a.w = fmaf(v.x, w0.w, a.w);
+            a.x = fmaf(v.y, w1.x, a.x); a.y = fmaf(v.y, w1.y, a.y); a.z = fmaf(v.y, w1.z, a.z); a.w = fmaf(v.y, w1.w, a.w);
+            a.x = fmaf(v.z, w2.x, a.x); a.y = fmaf(v.z, w2.y, a.y); a.z = fmaf(v.z, w2.z, a.z); a.w = fmaf(v.z, w2.w, a.w);
+            a.x = fmaf(v.w, w3.x, a.x); a.y = fmaf(v.w, w3.y, a.y); a.z = fmaf(v.w, w3.z, a.z); a.w = fmaf(v.w, w3.w, a.w);
+            acc[p] = a;
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < CF_PPT; p++) {
+        const long long m = p0 + pg * CF_PPT + p;
+        if (m < M) *reinterpret_cast<float4*>(out + m * out_ld + cg) = acc[p];
     }
 }
 
@@ -106,6 +129,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int ld, int C, int 
     if (slot < nslots) {
         const float* base = x + ((long long)b * HW) * ld + v * 4;
         double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
         for (int r = r0 + slot; r < r1; r += nslots) {
             const float4 q = *reinterpret_cast<const float4*>(base + (long long)r * ld);
             const double q0 = q.x, q1 = q.y, q2 = q.z, q3 = q.w;
@@ -157,6 +181,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int ld, int C, int 
     const size_t m0 = (size_t)b * HW;
     const bool want_raw = raw.any();
     const bool fast = y.f == nullptr && y.lo == nullptr;   // single 16-bit plane output (2^-11 / 2^-8 rounding follows): MUFU exp + reciprocal are exact enough
+#pragma unroll 4
     for (int r = r0 + slot; r < r1; r += nslots) {
         const float4 q = *reinterpret_cast<const float4*>(x + (m0 + r) * ld + v * 4);
         float o0 = fmaf(q.x, sc[0], sh[0]), o1 = fmaf(q.y, sc[1], sh[1]), o2 = fmaf(q.z, sc[2], sh[2]), o3 = fmaf(q.w, sc[3], sh[3]);
@@ -534,12 +559,15 @@ int k_timestep_embedding(const long long* t, int B, int dim, float* out, cudaStr
     timestep_embedding_kernel<<<blocks_for((long long)B * (dim / 2), 128), 128, 0, st>>>(t, B, dim, out);
     LAUNCH_CHECK(); return RDM_OK;
 }
-bool k_conv_first_supported(int Cin, int Cout) { return Cin >= 1 && Cin <= 4 && Cout % 4 == 0 && (size_t)9 * Cin * Cout * 4 <= 48 * 1024; }
+// block = G * PG threads (G = Cout / 4 channel groups, PG pixel groups of 16 pixels); shared memory: weights + patch
+static int conv_first_pg(int Cout) { const int G = Cout / 4; int pg = 256 / G; return pg > 4 ? 4 : pg; }
+static size_t conv_first_smem(int Cin, int Cout) { const int Kp = (9 * Cin + 3) & ~3; return ((size_t)Kp * (Cout + 4) + (size_t)conv_first_pg(Cout) * CF_PPT * Kp) * sizeof(float); }
+bool k_conv_first_supported(int Cin, int Cout) { return Cin >= 1 && Cin <= 4 && Cout % 4 == 0 && Cout >= 4 && Cout / 4 <= 256 && conv_first_smem(Cin, Cout) <= 48 * 1024; }
 int k_conv_first(View x, int B, int H, int W, const float* w, const float* bias, int Cout, View out, cudaStream_t st) {
     RDM_REQUIRE(k_conv_first_supported(x.C, Cout) && out.ld % 4 == 0, RDM_ERR_UNSUPPORTED, "conv_first: Cin=%d Cout=%d", x.C, Cout);
-    constexpr int PIX = 64;
+    const int PG = conv_first_pg(Cout), TP = PG * CF_PPT;
     const long long M = (long long)B * H * W;
-    conv_first_kernel<PIX><<<(unsigned)((M + PIX - 1) / PIX), 256, (size_t)9 * x.C * Cout * sizeof(float), st>>>(x.p, x.ld, x.C, B, H, W, w, bias, Cout, out.p, out.ld);
+    conv_first_kernel<<<(unsigned)((M + TP - 1) / TP), (Cout / 4) * PG, conv_first_smem(x.C, Cout), st>>>(x.p, x.ld, x.C, B, H, W, w, bias, Cout, out.p, out.ld);
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_gn_stats(View x, int B, int HW, int groups, double* sums, cudaStream_t st) {
@@ -551,9 +579,10 @@ int k_gn_stats(View x, int B, int HW, int groups, double* sums, cudaStream_t st)
     RDM_REQUIRE(V <= 1024, RDM_ERR_UNSUPPORTED, "gn_stats: C=%d too wide", x.C);
     // enough CTAs to fill the machine, at least ~8 rows per thread slot
     int nslots = threads / V; if (nslots < 1) nslots = 1;
-    int rows_per_cta = nslots * 8;
+    static const int rows_pt = getenv("RDM_GN_ROWS_STATS") ? atoi(getenv("RDM_GN_ROWS_STATS")) : 8, cta_cap = getenv("RDM_GN_CTAS") ? atoi(getenv("RDM_GN_CTAS")) : 8;
+    int rows_per_cta = nslots * rows_pt;
     int chunks = (HW + rows_per_cta - 1) / rows_per_cta;
-    while (chunks * B > 148 * 8 && rows_per_cta < HW) { rows_per_cta *= 2; chunks = (HW + rows_per_cta - 1) / rows_per_cta; }
+    while (chunks * B > 148 * cta_cap && rows_per_cta < HW) { rows_per_cta *= 2; chunks = (HW + rows_per_cta - 1) / rows_per_cta; }
     RDM_CHECK_CUDA(launch_pdl(gn_stats_kernel, dim3(chunks, B), dim3(threads), 2 * groups * sizeof(double), st, (const float*)x.p, x.ld, x.C, HW, groups, rows_per_cta, sums));
     LAUNCH_CHECK(); return RDM_OK;
 }
@@ -564,9 +593,10 @@ int k_gn_apply(View x, int B, int HW, int groups, const double* sums, float eps,
     int threads = V >= 256 ? ((V + 31) / 32) * 32 : (256 / V) * V;
     if (threads < groups) threads = ((groups + 31) / 32) * 32;
     int nslots = threads / V; if (nslots < 1) nslots = 1;
-    int rows_per_cta = nslots * 4;
+    static const int rows_pt = getenv("RDM_GN_ROWS_APPLY") ? atoi(getenv("RDM_GN_ROWS_APPLY")) : 4, cta_cap = getenv("RDM_GN_CTAS_APPLY") ? atoi(getenv("RDM_GN_CTAS_APPLY")) : 16;
+    int rows_per_cta = nslots * rows_pt;
     int chunks = (HW + rows_per_cta - 1) / rows_per_cta;
-    while (chunks * B > 148 * 16 && rows_per_cta < HW) { rows_per_cta *= 2; chunks = (HW + rows_per_cta - 1) / rows_per_cta; }
+    while (chunks * B > 148 * cta_cap && rows_per_cta < HW) { rows_per_cta *= 2; chunks = (HW + rows_per_cta - 1) / rows_per_cta; }
     RDM_CHECK_CUDA(launch_pdl(gn_apply_kernel, dim3(chunks, B), dim3(threads), 0, st, (const float*)x.p, x.ld, x.C, HW, groups, sums, eps, gamma, beta, silu, y, raw, rows_per_cta));
     LAUNCH_CHECK(); return RDM_OK;
 }
@@ -609,6 +639,35 @@ int k_vq_quantize(const float* z, int B, int E, int HW, const float* codebook, i
     RDM_REQUIRE(E >= 1 && E <= 4 && Z >= 1 && Z <= out.ld, RDM_ERR_UNSUPPORTED, "vq_quantize: embed_dim=%d z_channels=%d", E, Z);
     const long long total = (long long)B * HW;
     vq_quantize_kernel<<<blocks_for(total, 256), 256, 0, st>>>(z, B, E, HW, codebook, n_e, pq_w, pq_b, Z, quantize, out.p, out.ld);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+// out = a + b (weight-load time: the summed bias of a ResBlock whose skip_connection rides on its second conv, unet.cu)
+int k_add_vec(const float* a, const float* b, float* out, int n, cudaStream_t st) {
+    add_vec_kernel<<<blocks_for(n, 256), 256, 0, st>>>(a, b, out, n);
+    LAUNCH_CHECK(); return RDM_OK;
+}
+// w [N][9][C] (3x3 taps, row-major) -> out [4][N][4][C]: parity q = (py, px) of the output pixel, 2x2 taps (ty, tx) over the source image.
+// Kernel rows that land on source row y + ty + py - 1:  py = 0: ty 0 <- {0}, ty 1 <- {1, 2};   py = 1: ty 0 <- {0, 1}, ty 1 <- {2}  (same for columns).
+__global__ void fold_up_weights_kernel(const float* __restrict__ w, int N, int C, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, total = (long long)16 * N * C;
+    if (i >= total) return;
+    const int c = (int)(i % C); long long t = i / C;
+    const int tap = (int)(t % 4); t /= 4;
+    const int n = (int)(t % N), q = (int)(t / N);
+    const int py = q >> 1, px = q & 1, ty = tap >> 1, tx = tap & 1;
+    const int ky0 = py == 0 ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), ky1 = py == 0 ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+    const int kx0 = px == 0 ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), kx1 = px == 0 ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+    float s = 0.f;
+    for (int ky = ky0; ky <= ky1; ky++)
+        for (int kx = kx0; kx <= kx1; kx++) s += w[((size_t)n * 9 + ky * 3 + kx) * C + c];
+    out[i] = s;
+}
+int k_fold_up_weights(const float* w, int N, int C, float* out, cudaStream_t st) {
+    fold_up_weights_kernel<<<blocks_for((long long)16 * N * C, 256), 256, 0, st>>>(w, N, C, out);
     LAUNCH_CHECK(); return RDM_OK;
 }
 int k_split_planes(View x, long long M, Out4 y, cudaStream_t st) {

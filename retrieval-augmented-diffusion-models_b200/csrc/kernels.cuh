@@ -123,6 +123,8 @@ int k_vq_quantize(const float* z, int B, int E, int HW, const float* codebook, i
                   View out, cudaStream_t st);
 // fp32 [M, C] -> bf16 planes
 int k_split_planes(View x, long long M, Out4 y, cudaStream_t st);
+int k_add_vec(const float* a, const float* b, float* out, int n, cudaStream_t st);
+int k_fold_up_weights(const float* w, int N, int C, float* out, cudaStream_t st);
 // im2col of a 3x3 / stride 2 / pad 1 conv (ldm Downsample): x NHWC [B,H,W,C] -> [B*Ho*Wo, 9*C] (tap-major), Ho=(H+1)/2
 int k_im2col_s2(View x, int B, int H, int W, Out4 y, cudaStream_t st);
 // nearest-neighbour 2x upsample (ldm Upsample): x NHWC [B,H,W,C] -> [B,2H,2W,C]

@@ -38,10 +38,10 @@ struct ParamSlot { size_t numel = 0; bool loaded = false; std::function<void(con
                    int rows = 0, row_len = 0, dst_row0 = 0, dst_row_step = 1; };
 
 struct Norm { int C = 0; float* g = nullptr; float* b = nullptr; };
-struct Conv { int cin = 0, cout = 0, ks = 1; float* w = nullptr; float* b = nullptr; };     // w: [cout][ks*ks*cin] (tap-major K)
+struct Conv { int cin = 0, cout = 0, ks = 1; float* w = nullptr; float* b = nullptr; float* wfold = nullptr; };     // w: [cout][ks*ks*cin] (tap-major K); wfold: [4][cout][2*2*cin], conv after Upsample only (fold_up_weights)
 struct Lin { int in = 0, out = 0; float* w = nullptr; float* b = nullptr; };                // w: [out][in]
 
-struct ResW { int cin, cout; Norm n1; Conv c1; int emb_off; Norm n2; Conv c2; bool has_skip; Conv skip; float eps = 1e-5f; };   // emb_off < 0: no time embedding (VQ decoder ResnetBlock)
+struct ResW { int cin, cout; Norm n1; Conv c1; int emb_off; Norm n2; Conv c2; bool has_skip; Conv skip; float eps = 1e-5f; float* b2s = nullptr; };   // b2s: c2.b + skip.b (ensure_weight_planes)   // emb_off < 0: no time embedding (VQ decoder ResnetBlock)
 struct AttnW { int C; Norm norm; Lin qkv; Conv proj_out; };     // taming/ldm AttnBlock: single head over all pixels, q/k/v 1x1 convs concatenated [3C, C]
 enum DecKind { D_RES, D_ATTN, D_UP };
 struct DecLayer { DecKind kind; int idx; };
@@ -156,6 +156,12 @@ Conv make_conv(Net* n, const std::string& p, int cin, int cout, int ks) {
     reg_conv_w(n, p + ".weight", c.w, cout, cin, ks); reg_plain(n, p + ".bias", c.b, cout);
     return c;
 }
+// the 3x3 conv that follows a 2x nearest Upsample: also reserves the parity-folded weights (filled by ensure_weight_planes)
+Conv make_up_conv(Net* n, const std::string& p, int cin, int cout) {
+    Conv c = make_conv(n, p, cin, cout, 3);
+    c.wfold = walloc(n, (size_t)16 * cout * cin);
+    return c;
+}
 Lin make_lin(Net* n, const std::string& p, int in, int out, bool bias) {
     Lin l; l.in = in; l.out = out; l.w = walloc(n, (size_t)in * out); reg_plain(n, p + ".weight", l.w, (size_t)in * out);
     if (bias) { l.b = walloc(n, out); reg_plain(n, p + ".bias", l.b, out); }
@@ -170,7 +176,7 @@ int add_res(Net* n, const std::string& p, int cin, int cout) {
     r.n2 = make_norm(n, p + ".out_layers.0", cout);
     r.c2 = make_conv(n, p + ".out_layers.3", cout, cout, 3);
     r.has_skip = cin != cout;
-    if (r.has_skip) r.skip = make_conv(n, p + ".skip_connection", cin, cout, 1);
+    if (r.has_skip) { r.skip = make_conv(n, p + ".skip_connection", cin, cout, 1); r.b2s = walloc(n, cout); }
     n->res.push_back(r);
     n->host_scratch.push_back(nullptr);
     return (int)n->res.size() - 1;
@@ -243,7 +249,7 @@ void build_net(Net* n) {
             push_res(b, p + "." + std::to_string(li++), ch + ich, mc * mult); ch = mc * mult;
             if (in_list(c.attention_resolutions, c.n_attention_resolutions, ds)) b.layers.push_back({L_ST, add_st(n, p + "." + std::to_string(li++), ch, heads_of(ch), c.context_dim)});
             if (level && i == c.num_res_blocks) {
-                n->convs.push_back(make_conv(n, p + "." + std::to_string(li++) + ".conv", ch, ch, 3)); b.layers.push_back({L_UP, (int)n->convs.size() - 1});
+                n->convs.push_back(make_up_conv(n, p + "." + std::to_string(li++) + ".conv", ch, ch)); b.layers.push_back({L_UP, (int)n->convs.size() - 1});
                 ds /= 2;
             }
             b.cout = ch; b.ds_after = ds; n->out_blocks.push_back(b);
@@ -334,8 +340,10 @@ const __nv_bfloat16* w_lo(Net* n, const float* w) { return mode_w_split(n->mode)
 
 // out = epi(conv/linear(a)).  a: [B*H*W, C] operand; ks 1|3 (stride 1, pad ks/2) on the tensor-core engine;
 // stride / ups only exist on the CUDA-core engine (the TC path materialises im2col / upsampled planes instead).
+// K extension of a tensor-core GEMM (gemm_tc.cuh: TcA::hi2): a second [M, C] operand with its own [N, C] weights in the same accumulator
+struct KExt { const Opnd* a = nullptr; const float* w = nullptr; int C = 0; };
 void gemm_any(Ctx& cx, const Opnd& a, int B, int H, int W, int C, int ks, int stride, int ups, const float* w, const float* bias, int N,
-              GemmEpi e, const Opnd& out) {
+              GemmEpi e, const Opnd& out, KExt x2 = KExt()) {
     Net* n = cx.n;
     if (!e.bias) e.bias = bias;
     const int Ho = ups ? H * 2 : (stride == 2 ? (H + 1) / 2 : H), Wo = ups ? W * 2 : (stride == 2 ? (W + 1) / 2 : W);
@@ -351,11 +359,12 @@ void gemm_any(Ctx& cx, const Opnd& a, int B, int H, int W, int C, int ks, int st
         // profile == 2: the forward is being captured into a CUDA graph; external event-record nodes time the kernels inside the replay
         void rec(cudaEvent_t e) { if (cx.n->profile == 2) cudaEventRecordWithFlags(e, cx.st, cudaEventRecordExternal); else cudaEventRecord(e, cx.st); }
         ~ProfScope() { if (on) rec(cx.n->prof_ev.back()); }
-    } prof(cx, 2.0 * M * (double)N * ks * ks * C, a.tc() ? 1 : 0);
+    } prof(cx, 2.0 * M * (double)N * ((a.tc() && ups ? 4 : ks * ks) * C + x2.C), a.tc() ? 1 : 0);
     if (prof.on) { char d[128]; snprintf(d, sizeof(d), "%s M=%d N=%d K=%d ks=%d HxW=%dx%d act=%d", a.tc() ? "tc" : "simt", M, N, ks * ks * C, ks, H, W, e.act); n->prof_desc.push_back(d); }
     if (a.tc()) {
-        TcA ta; ta.hi = a.hi; ta.lo = a.lo; ta.ld = a.ldb; ta.B = B; ta.H = H; ta.W = W; ta.C = C; ta.ksize = ks;
-        TcW tw; tw.hi = w_hi(n, w); tw.lo = w_lo(n, w); tw.N = N; tw.K = ks * ks * C; tw.ld = tw.K;
+        TcA ta; ta.hi = a.hi; ta.lo = a.lo; ta.ld = a.ldb; ta.B = B; ta.H = H; ta.W = W; ta.C = C; ta.ksize = ks; ta.ups = ups;
+        TcW tw; tw.hi = w_hi(n, w); tw.lo = w_lo(n, w); tw.N = N; tw.K = (ups ? 4 : ks * ks) * C; tw.ld = tw.K;      // (ups: `w` = the folded weights)
+        if (x2.a) { ta.hi2 = x2.a->hi; ta.ld2 = x2.a->ldb; ta.C2 = x2.C; tw.hi2 = w_hi(n, x2.w); tw.ld2 = x2.C; }
         const int nsplit = mode_nsplit(n->mode), f16 = mode_f16(n->mode);
         const int skip_bit = M >= 8192 ? 16 : 32;
         if (out.tc()) { e.out = nullptr; RUN_UNLESS(skip_bit, gemm_tc(ta, tw, e, out.hi, out.lo, out.ldb, nsplit, f16, cx.st)); }
@@ -380,8 +389,8 @@ void gemm_any(Ctx& cx, const Opnd& a, int B, int H, int W, int C, int ks, int st
         RUN(gemm_simt(ga, w, N, e, cx.st));
     }
 }
-void conv_any(Ctx& cx, const Opnd& a, const Act& g, const Conv& c, GemmEpi e, const Opnd& out) {
-    gemm_any(cx, a, g.B, g.H, g.W, c.cin, c.ks, 1, 0, c.w, c.b, c.cout, e, out);
+void conv_any(Ctx& cx, const Opnd& a, const Act& g, const Conv& c, GemmEpi e, const Opnd& out, KExt x2 = KExt()) {
+    gemm_any(cx, a, g.B, g.H, g.W, c.cin, c.ks, 1, 0, c.w, c.b, c.cout, e, out, x2);
 }
 void lin_any(Ctx& cx, const Opnd& a, int M, const Lin& l, GemmEpi e, const Opnd& out) {
     gemm_any(cx, a, M, 1, 1, l.in, 1, 1, 0, l.w, l.b, l.out, e, out);
@@ -421,6 +430,17 @@ void run_res(Ctx& cx, const ResW& r, const Act& x, const float* emb_all, View ou
       conv_any(cx, a1, x, r.c1, e, from_view(h1)); }
     Opnd a2 = fresh_opnd(cx, M, r.cout, tc2);
     gn(cx, Act{h1, x.B, x.H, x.W}, r.n2, r.eps, 1, a2);
+    // One-plane tensor-core modes: the 1x1 skip_connection is a K extension of the second conv -- its k-blocks (raw fp16 x, skip weights)
+    // follow the nine taps into the same TMEM accumulator, the summed bias replaces both biases; no second GEMM, no fp32 residual buffer
+    // written and read back.  RDM_RES_SKIP_FUSED=0: the separate GEMM (also what the split-plane and fp32 modes run).
+    static const int fuse_on = getenv("RDM_RES_SKIP_FUSED") ? atoi(getenv("RDM_RES_SKIP_FUSED")) : 1;
+    if (fuse_on && tcs && tc2 && r.b2s && mode_nsplit(cx.n->mode) == 1) {
+        GemmEpi e; e.bias = r.b2s;
+        KExt x2; x2.a = &xraw; x2.w = r.skip.w; x2.C = r.cin;
+        conv_any(cx, a2, x, r.c2, e, from_view(out), x2);
+        A.release(mk);
+        return;
+    }
     View resv = x.v;
     if (r.has_skip) { resv = fresh(cx, M, r.cout); conv_any(cx, tcs ? xraw : from_view(x.v), x, r.skip, GemmEpi(), from_view(resv)); }
     { GemmEpi e; e.res = resv.p; e.res_ld = resv.ld; conv_any(cx, a2, x, r.c2, e, from_view(out)); }
@@ -494,6 +514,18 @@ void run_down(Ctx& cx, const Conv& c, const Act& x, View out) {
 }
 void run_up(Ctx& cx, const Conv& c, const Act& x, View out) {
     Arena& A = *cx.A; size_t mk = A.mark();
+    // Tensor-core modes: the upsampled plane is never built -- each output parity is a 2x2-tap conv of the SOURCE image with pre-summed
+    // weights (gemm_tc.cuh: TcA::ups): 4/9 of the MMA work, and a same-size fp16 copy of x instead of a 4x larger one.  The folded weights
+    // are rounded to the operand format after the fp32 sums (so a product differs from the reference's by rounding only).
+    // RDM_UP_FOLD=0: upsample2x + plain 3x3 conv.
+    static const int fold_on = getenv("RDM_UP_FOLD") ? atoi(getenv("RDM_UP_FOLD")) : 1;
+    if (fold_on && c.wfold && c.cout % 32 == 0 && x.W <= 128 && tc_ok(cx, x.B, x.H, x.W, c.cin, 3)) {
+        Opnd src = fresh_opnd(cx, x.M(), c.cin, true);
+        RUN(k_split_planes(x.v, x.M(), src.out4(), cx.st));
+        gemm_any(cx, src, x.B, x.H, x.W, c.cin, 3, 1, 1, c.wfold, c.b, c.cout, GemmEpi(), from_view(out));
+        A.release(mk);
+        return;
+    }
     if (tc_ok(cx, x.B, 2 * x.H, 2 * x.W, c.cin, 3)) {
         Opnd up = fresh_opnd(cx, x.B * 4 * x.H * x.W, c.cin, true);
         RUN(k_upsample2x(x.v, x.B, x.H, x.W, up.out4(), cx.st));
@@ -674,7 +706,7 @@ int add_dec_res(Net* n, const std::string& p, int cin, int cout) {
     r.n1 = make_norm(n, p + ".norm1", cin); r.c1 = make_conv(n, p + ".conv1", cin, cout, 3);
     r.n2 = make_norm(n, p + ".norm2", cout); r.c2 = make_conv(n, p + ".conv2", cout, cout, 3);
     r.has_skip = cin != cout;
-    if (r.has_skip) r.skip = make_conv(n, p + ".nin_shortcut", cin, cout, 1);
+    if (r.has_skip) { r.skip = make_conv(n, p + ".nin_shortcut", cin, cout, 1); r.b2s = walloc(n, cout); }
     n->res.push_back(r);
     return (int)n->res.size() - 1;
 }
@@ -710,7 +742,7 @@ void build_decoder(Net* n) {
                 n->dec_layers.push_back({D_ATTN, add_dec_attn(n, up + ".attn." + std::to_string(i), block_in)});
         }
         if (lvl != 0) {
-            n->convs.push_back(make_conv(n, up + ".upsample.conv", block_in, block_in, 3));
+            n->convs.push_back(make_up_conv(n, up + ".upsample.conv", block_in, block_in));
             n->dec_layers.push_back({D_UP, (int)n->convs.size() - 1});
             curr_res *= 2;
         }
@@ -823,6 +855,8 @@ int ensure_weight_planes(Net* n, cudaStream_t st) {
     if (n->mode == RDM_UNET_MODE_FP32 || !n->planes_dirty) return RDM_OK;
     if (!n->wb_hi) RDM_CHECK_CUDA(cudaMalloc((void**)&n->wb_hi, n->wfloats * 2));
     if (!n->wb_lo) RDM_CHECK_CUDA(cudaMalloc((void**)&n->wb_lo, n->wfloats * 2));
+    for (const ResW& r : n->res) if (r.b2s) RDM_TRY(k_add_vec(r.c2.b, r.skip.b, r.b2s, r.cout, st));       // bias of the K-extended second conv (run_res)
+    for (const Conv& c : n->convs) if (c.wfold) RDM_TRY(k_fold_up_weights(c.w, c.cout, c.cin, c.wfold, st));    // Upsample + conv as four 2x2-tap convs (run_up)
     RDM_TRY(k_split_planes(View(n->wbase, 64, 64), (long long)(n->wfloats / 64), Out4(n->wb_hi, n->wb_lo, 64, mode_f16(n->mode)), st));
     n->planes_dirty = false;
     return RDM_OK;

@@ -13,8 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = {"0": 1e-4, "1": 1e-4, "2": 3e-2, "3": 3e-3, "4": 4e-3}          # ("2" = plain bf16: 8-bit significands)          # same per-forward tolerances as tests/test_unet_gpu.py
 
 
-@pytest.mark.parametrize("env", [{"RDM_TC_CLUSTER": "1"}, {"RDM_TC_CLUSTER": "2"}, {"RDM_SKIP": "64"}, {"RDM_PDL": "0"}, {"RDM_TC_NOSPLIT": "1"}, {"RDM_GN_EPI_STATS": "1"}, {"RDM_GN_FUSED_MAX_HW": "4096"}, {"RDM_TC_2SM": "2", "RDM_TC_2SM_MIN_M": "256", "MODES": "4,2"}, {"RDM_TC_2SM": "0", "MODES": "4"}],
-                         ids=["splitk-cost-model-with-clusters", "splitk-cluster-dsmem", "unfused-cross-attention", "no-pdl", "no-splitk", "gn-epilogue-statistics", "gn-one-launch-everywhere", "cta-pairs-everywhere", "no-cta-pairs"])
+@pytest.mark.parametrize("env", [{"RDM_TC_CLUSTER": "1"}, {"RDM_TC_CLUSTER": "2"}, {"RDM_SKIP": "64"}, {"RDM_PDL": "0"}, {"RDM_TC_NOSPLIT": "1"}, {"RDM_GN_EPI_STATS": "1"}, {"RDM_GN_FUSED_MAX_HW": "4096"}, {"RDM_TC_2SM": "2", "RDM_TC_2SM_MIN_M": "256", "MODES": "4,2"}, {"RDM_TC_2SM": "0", "MODES": "4"}, {"RDM_RES_SKIP_FUSED": "0", "MODES": "4,2"}, {"RDM_UP_FOLD": "0", "MODES": "4,3"}, {"RDM_TC_2SM_WAVES": "3", "MODES": "4"}],
+                         ids=["splitk-cost-model-with-clusters", "splitk-cluster-dsmem", "unfused-cross-attention", "no-pdl", "no-splitk", "gn-epilogue-statistics", "gn-one-launch-everywhere", "cta-pairs-everywhere", "no-cta-pairs", "skip-connection-as-its-own-gemm", "upsample-materialised", "cta-pairs-for-geglu"])
 def test_engine_variant_matches_oracle(cuda, env):
     env = dict(env)
     modes = env.pop("MODES", "1,3")                                # engine modes to check (the CTA-pair kernel exists for the one-MMA modes only)
