@@ -63,10 +63,13 @@ def peaks():
 
 def traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum over the tcgen05 GEMM launches of one forward, from the committed ncu pass of this round."""
-    path = os.path.join(ROOT, "profiles", "gemm_tc_dram_r2z.json")
+    for name in ("gemm_tc_dram_r2zb.json", "gemm_tc_dram_r2z.json"):          # newest capture of this round's kernels first
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            break
     try:
         j = json.load(open(path))
-        return j["bytes_per_forward"], f"profiles/gemm_tc_dram_r2z.json ({j['how']})"
+        return j["bytes_per_forward"], f"profiles/{name} ({j['how']})"
     except Exception:
         return None, "no ncu capture of this round's kernels committed"
 

@@ -129,7 +129,6 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int ld, int C, int 
     if (slot < nslots) {
         const float* base = x + ((long long)b * HW) * ld + v * 4;
         double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
         for (int r = r0 + slot; r < r1; r += nslots) {
             const float4 q = *reinterpret_cast<const float4*>(base + (long long)r * ld);
             const double q0 = q.x, q1 = q.y, q2 = q.z, q3 = q.w;
@@ -181,7 +180,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int ld, int C, int 
     const size_t m0 = (size_t)b * HW;
     const bool want_raw = raw.any();
     const bool fast = y.f == nullptr && y.lo == nullptr;   // single 16-bit plane output (2^-11 / 2^-8 rounding follows): MUFU exp + reciprocal are exact enough
-#pragma unroll 4
+    // (no unroll pragma: a thread walks only 4-8 rows; `#pragma unroll 4` here and in gn_stats_kernel measured 4.23 vs 4.16 ms per forward)
     for (int r = r0 + slot; r < r1; r += nslots) {
         const float4 q = *reinterpret_cast<const float4*>(x + (m0 + r) * ld + v * 4);
         float o0 = fmaf(q.x, sc[0], sh[0]), o1 = fmaf(q.y, sc[1], sh[1]), o2 = fmaf(q.z, sc[2], sh[2]), o3 = fmaf(q.w, sc[3], sh[3]);

@@ -6,8 +6,8 @@ tag=${1:-r2}
 # (1) every launch of the first DDIM steps of the benchmark with its device time (cold-cache, serialised: compare shares)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_bench_$tag.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-r-shape > /dev/null 2>&1
-# (2) DRAM traffic of every tcgen05 GEMM launch of one graph-replayed forward (197 launches; the eager pass + capture come first)
-timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm_tc_kernel --launch-skip 203 --launch-count 197 \
+# (2) DRAM traffic of every tcgen05 GEMM launch of one graph-replayed forward (182 launches since the skip_connection fusion; the eager pass + capture come first)
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm_tc_kernel --launch-skip 188 --launch-count 182 \
     --csv --log-file gpurun_out/gemm_tc_dram_$tag.csv python tools/profile_forward.py 4 1 > /dev/null 2>&1
 # (3) --set full of the glue kernel classes inside the replayed forward
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:'gn_stats|gn_apply|layernorm_kernel|attention_mma' --launch-skip 150 --launch-count 8 \

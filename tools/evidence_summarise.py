@@ -24,6 +24,9 @@ def short(name):
     return re.sub(r"void |<unnamed>::|\(anonymous namespace\)::", "", name).split("(")[0][:64]
 
 
+GEMMS_PER_FWD = 182      # tcgen05 GEMM launches of one full-architecture forward (197 before the skip_connection K extension)
+
+
 def gemm_traffic():
     src = os.path.join(G, f"gemm_tc_dram_{tag}.csv")
     rows = list(csv.DictReader([l for l in open(src) if not l.startswith("==")]))
@@ -32,12 +35,12 @@ def gemm_traffic():
         tot[x["Metric Name"]] += float(x["Metric Value"].replace(",", "")) * SCALE.get(x["Metric Unit"], 1)
         ids.add(x["ID"])
     n = len(ids)
-    per_fwd = (tot["dram__bytes_read.sum"] + tot["dram__bytes_write.sum"]) * 197 / n
+    per_fwd = (tot["dram__bytes_read.sum"] + tot["dram__bytes_write.sum"]) * GEMMS_PER_FWD / n
     shutil.copy(src, os.path.join(P, f"gemm_tc_dram_{tag}.csv"))
     out = {"bytes_per_forward": per_fwd, "launches_captured": n, "dram_read_bytes": tot["dram__bytes_read.sum"], "dram_write_bytes": tot["dram__bytes_write.sum"],
            "sum_gpu_time_ms": tot["gpu__time_duration.sum"] / 1e6,
-           "how": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:gemm_tc_kernel over {n} of the 197 tcgen05 GEMM launches of one full-architecture forward "
-                  f"(B2 = 32, fp16 mode), scaled by 197/{n}; profiles/gemm_tc_dram_{tag}.csv; every launch is replayed with a flushed L2, so activations that are L2 hits in "
+           "how": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:gemm_tc_kernel over {n} of the {GEMMS_PER_FWD} tcgen05 GEMM launches of one full-architecture forward "
+                  f"(B2 = 32, fp16 mode), scaled by {GEMMS_PER_FWD}/{n}; profiles/gemm_tc_dram_{tag}.csv; every launch is replayed with a flushed L2, so activations that are L2 hits in "
                   "the running step count as DRAM reads here (an upper bound of the in-step traffic)"}
     json.dump(out, open(os.path.join(P, f"gemm_tc_dram_{tag}.json"), "w"), indent=1)
     print("traffic", out["bytes_per_forward"] / 1e9, "GB per forward from", n, "launches")
