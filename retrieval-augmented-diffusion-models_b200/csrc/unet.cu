@@ -359,8 +359,8 @@ void gemm_any(Ctx& cx, const Opnd& a, int B, int H, int W, int C, int ks, int st
         // profile == 2: the forward is being captured into a CUDA graph; external event-record nodes time the kernels inside the replay
         void rec(cudaEvent_t e) { if (cx.n->profile == 2) cudaEventRecordWithFlags(e, cx.st, cudaEventRecordExternal); else cudaEventRecord(e, cx.st); }
         ~ProfScope() { if (on) rec(cx.n->prof_ev.back()); }
-    } prof(cx, 2.0 * M * (double)N * ((a.tc() && ups ? 4 : ks * ks) * C + x2.C), a.tc() ? 1 : 0);
-    if (prof.on) { char d[128]; snprintf(d, sizeof(d), "%s M=%d N=%d K=%d ks=%d HxW=%dx%d act=%d", a.tc() ? "tc" : "simt", M, N, ks * ks * C, ks, H, W, e.act); n->prof_desc.push_back(d); }
+    } prof(cx, 2.0 * M * (double)N * (ks * ks * C + x2.C), a.tc() ? 1 : 0);       // ALGORITHMIC flops (the reference's conv); an upsample-folded conv executes 4/9 of them
+    if (prof.on) { char d[128]; snprintf(d, sizeof(d), "%s M=%d N=%d K=%d ks=%d HxW=%dx%d act=%d%s%s", a.tc() ? "tc" : "simt", M, N, ks * ks * C + x2.C, ks, H, W, e.act, a.tc() && ups ? " upfold" : "", x2.a ? " kext" : ""); n->prof_desc.push_back(d); }
     if (a.tc()) {
         TcA ta; ta.hi = a.hi; ta.lo = a.lo; ta.ld = a.ldb; ta.B = B; ta.H = H; ta.W = W; ta.C = C; ta.ksize = ks; ta.ups = ups;
         TcW tw; tw.hi = w_hi(n, w); tw.lo = w_lo(n, w); tw.N = N; tw.K = (ups ? 4 : ks * ks) * C; tw.ld = tw.K;      // (ups: `w` = the folded weights)

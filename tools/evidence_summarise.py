@@ -87,8 +87,9 @@ def raw_table(rep, title, how, f, pick=None, stalls=True):
 gemm_traffic()
 launches("bench", "ncu launch list: `ncu --metrics gpu__time_duration.sum --clock-control none -c 3000` over `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-r-shape` "
          "(database build, kNN, context K/V, the first DDIM steps of the fp16 engine; last 80 % of the list)", 0.2)
-launches("rarm", "ncu launch list of the RARM decode loop: `ncu --metrics gpu__time_duration.sum -k regex:rarm_ --launch-skip 600 -c 300` over `python tools/rarm_bench.py` "
-         "(two decode steps of the ImageNet-size model, batch 4, fp16 weights)", 0.0)
+if os.path.exists(os.path.join(G, f"launches_rarm_{tag}.csv")):
+    launches("rarm", "ncu launch list of the RARM decode loop: `ncu --metrics gpu__time_duration.sum -k regex:rarm_ --launch-skip 600 -c 300` over `python tools/rarm_bench.py` "
+             "(two decode steps of the ImageNet-size model, batch 4, fp16 weights)", 0.0)
 with open(os.path.join(P, f"ncu_summary_{tag}.md"), "w") as f:
     f.write(f"# ncu `--set full --clock-control none --import-source on` captures, round 2 (B200, sm_100a)\n\nRaw reports stay in `gpurun_out/` (scratch); the tables are "
             "`ncu -i <rep> --page raw --csv` of those files (tools/evidence.sh, tools/evidence_summarise.py).  Durations are cold-cache, serialised ncu replays.\n")
@@ -102,7 +103,22 @@ with open(os.path.join(P, f"ncu_summary_{tag}.md"), "w") as f:
               "ncu --set full -k regex:'rarm_gemv|rarm_attn' --launch-skip 600 --launch-count 9 python tools/rarm_bench.py", f)
     raw_table(f"knn_{tag}.ncu-rep", "one exact kNN search, fp16 database 1,281,167 x 512, 16 queries, k = 4 (normalise + fused tensor-core scan + select + conditional fallback pair)",
               "ncu --set full -k regex:knn_ --launch-skip 12 --launch-count 6 python tools/knn_sweep.py --n 1281167 --q 16 --dtypes float16", f)
-shutil.copy(os.path.join(G, f"sanitize_{tag}.log"), os.path.join(P, f"sanitize_{tag}.log"))
+    # later captures of the round (present only for some tags)
+    if os.path.exists(os.path.join(G, f"gemm_{tag}.ncu-rep")):
+        raw_table(f"gemm_{tag}.ncu-rep", "gemm_tc_kernel, final state of the round (skip_connection K extension, upsample fold): 12 consecutive launches of a graph-replayed forward",
+                  "ncu --set full -k regex:gemm_tc_kernel --launch-skip 188 --launch-count 12 python tools/profile_forward.py 4 1", f)
+    if os.path.exists(os.path.join(G, f"convfirst_{tag}.ncu-rep")):
+        raw_table(f"convfirst_{tag}.ncu-rep", "weight-load kernels and the register-tiled first convolution (`fold_up_weights_kernel`, `split_planes_kernel`, `conv_first_kernel`)",
+                  "ncu --set full -k regex:'conv_first|split_planes|fold_up' --launch-count 3 python tools/profile_forward.py 4 1", f)
+    if os.path.exists(os.path.join(G, f"knn64_{tag}.ncu-rep")):
+        raw_table(f"knn64_{tag}.ncu-rep", "fused tensor-core kNN scan at 64 queries (hi-only pass), 1,281,167 x 512 fp16: 1.317 GB in 226.6 us = 5.81 TB/s = 0.90 of the measured copy peak",
+                  "ncu --set full -k regex:knn_scan_fused --launch-skip 4 --launch-count 1 python tools/knn_sweep.py --n 1281167 --q 64 --k 4 --dtypes float16", f)
+    if os.path.exists(os.path.join(G, f"knnsel_{tag}.ncu-rep")):
+        raw_table(f"knnsel_{tag}.ncu-rep", "knn_select_kernel (16 queries): 21.7 us; 44 % of the stall samples sit at the barrier behind the exact re-rank (one lane per candidate "
+                  "evaluates the oracle's SEQUENTIAL 512-term fp64 sum: ~35 cycles per dependent DADD)",
+                  "ncu --set full -k regex:knn_select --launch-skip 8 --launch-count 1 python tools/knn_sweep.py --n 1281167 --q 16 --k 4 --dtypes float16", f)
+if os.path.exists(os.path.join(G, f"sanitize_{tag}.log")):
+    shutil.copy(os.path.join(G, f"sanitize_{tag}.log"), os.path.join(P, f"sanitize_{tag}.log"))
 with open(os.path.join(P, f"sass_histogram_{tag}.md"), "w") as f:
     f.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_histogram.py")], capture_output=True, text=True).stdout)
 print("done")
