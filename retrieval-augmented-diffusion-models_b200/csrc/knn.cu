@@ -411,13 +411,16 @@ __device__ __forceinline__ bool better_pair(double sa, long long ia, double sb, 
 //                     1024 survivors lie within the slack (a pathological cluster of near-identical rows: the fallback pass answers).
 // FROM_LISTS = true : fallback, per-CTA lists [group][nblk][QP][LIST]; runs only for queries with overflow[qi] != 0 (every other query keeps
 //                     the result of the main path); re-ranks the 32 best fp32 keys.
-// Exact re-rank: a WARP stages each candidate row in shared memory with coalesced 16-byte loads (a thread walking its own row paid ~16
-// dependent DRAM round trips), then one lane evaluates the oracle's sequential fp64 sum from shared memory.
+// Exact re-rank: a WARP fetches each candidate row with coalesced 16-byte loads (a thread walking its own row paid ~16 dependent DRAM round
+// trips) and its 32 lanes leave the fp64 PRODUCTS q_j * d_j in shared memory -- every product is exact in fp64 (24 x 11 or 24 x 24
+// significand bits), so computing them in parallel changes nothing; then one lane evaluates the oracle's SEQUENTIAL sum over them: 512
+// dependent DADDs fed by plain shared-memory loads.  (Round 2, measured with ncu: with the unpacking, the two F2F conversions and the DMUL
+// inside that one lane's loop the sum cost ~35 cycles per term and 44 % of the kernel's stall samples sat at the barrier behind it.)
 constexpr int SEL_MAX = 1024;
 template <typename T, int D> struct SelCfg {
     static constexpr int ROW_BYTES = D * (int)sizeof(T);
-    static constexpr int ROWS_PAR = 32768 / ROW_BYTES > 32 ? 32 : 32768 / ROW_BYTES;      // rows staged per round (one per warp)
-    static constexpr int DYN_BYTES = ROWS_PAR * ROW_BYTES;
+    static constexpr int ROWS_PAR = 16;                                                    // candidates re-ranked per round (one per warp)
+    static constexpr int DYN_BYTES = ROWS_PAR * D * (int)sizeof(double);                   // their fp64 product rows
 };
 template <typename T, int D, bool FROM_LISTS>
 __global__ void __launch_bounds__(1024)
@@ -429,7 +432,7 @@ knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const unsigne
     __shared__ float s_q[D];
     __shared__ u64 s_cand[SEL_MAX];
     __shared__ double s_score[SEL_MAX];
-    extern __shared__ uint4 s_rows[];                      // [ROWS_PAR][ROW_BYTES / 16]
+    extern __shared__ double s_prod[];                     // [ROWS_PAR][D]
     __shared__ u64 s_cut;
     __shared__ unsigned s_ncand;
     __shared__ double s_bs[32];
@@ -485,18 +488,18 @@ knn_select_kernel(const u64* __restrict__ lists, int nblk, int QP, const unsigne
                 double acc = -CUDART_INF;
                 if (r < n) {
                     const uint4* src = reinterpret_cast<const uint4*>(db + (size_t)r * D);
-                    uint4* dst = s_rows + (size_t)warp * V;
-                    for (int v = lane; v < V; v += 32) dst[v] = ldg_stream(src + v);
+                    double* prod = s_prod + (size_t)warp * D;
+                    for (int v = lane; v < V; v += 32) {
+                        float f[EPV];
+                        Elem<T>::unpack(ldg_stream(src + v), f);
+#pragma unroll
+                        for (int e = 0; e < EPV; e++) prod[v * EPV + e] = __dmul_rn((double)s_q[v * EPV + e], (double)f[e]);      // exact
+                    }
                     __syncwarp();
                     if (lane == 0) {
                         acc = 0.0;
-#pragma unroll 4
-                        for (int j = 0; j < V; j++) {
-                            float f[EPV];
-                            Elem<T>::unpack(dst[j], f);
-#pragma unroll
-                            for (int e = 0; e < EPV; e++) acc = __dadd_rn(acc, __dmul_rn((double)s_q[j * EPV + e], (double)f[e]));      // same order as the oracle
-                        }
+#pragma unroll 8
+                        for (int j = 0; j < D; j++) acc = __dadd_rn(acc, prod[j]);                                                 // same order as the oracle
                         acc = __dmul_rn(acc, (double)inv[r]);
                         if (!(acc == acc)) acc = -CUDART_INF;
                     }
