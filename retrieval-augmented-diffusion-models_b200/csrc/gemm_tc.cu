@@ -5,15 +5,20 @@
 //   NSPLIT = 3:  acc += A_hi*W_hi + A_lo*W_hi + A_hi*W_lo   (fp32-grade contraction on the bf16 tensor pipe)
 //   NSPLIT = 1:  acc += A_hi*W_hi                            (plain bf16)
 //
-// One 128 x BN output tile per CTA, K swept in 64-element blocks:
+// One 128 x BN output tile per work item (persistent CTAs, one per SM), K swept in 64-element blocks; 12 warps:
 //   warp 0   : TMA producer -- cp.async.bulk.tensor.4d into 128B-swizzled shared-memory stages; a 3x3 conv is
 //              9 shifted box loads of the NHWC plane (TMA out-of-bounds zero fill *is* the conv padding), so no
-//              im2col buffer exists; 1x1 convs / Linear layers use the same path with a degenerate box
+//              im2col buffer exists; 1x1 convs / Linear layers use the same path with a degenerate box.  Two
+//              extensions of the k-block sequence (round 2): a second activation / weight pair appended behind the
+//              taps (TcA::hi2: the ResBlock skip_connection), and the 2x2-tap parity form of Upsample + conv (TcA::ups)
 //   warp 1   : allocates TMEM, one elected lane issues tcgen05.mma (kind::f16, M=128, N=BN, K=16) with the
-//              fp32 accumulator in TMEM, tcgen05.commit releases stages / signals the epilogue
-//   warps 2-5: epilogue -- tcgen05.ld 32 lanes x 32 columns, bias / per-sample row vector (time embedding) /
-//              SiLU / GEGLU / residual, fp32 or bf16-plane stores
-// full/empty mbarrier ring between producer and MMA issuer; tmem_full mbarrier between issuer and epilogue.
+//              fp32 accumulator double-buffered in TMEM, tcgen05.commit releases stages / signals the epilogue
+//   warps 2-3: idle (setmaxnreg works on whole warpgroups: warpgroup 0 hands its registers to the epilogue)
+//   warps 4-11: epilogue, two warps per TMEM lane quarter -- tcgen05.ld 32 lanes x 32 columns, bias / per-sample
+//              row vector (time embedding) / SiLU / GEGLU / fused cross-attention / residual, fp32 or 16-bit-plane
+//              stores; operands prefetched one chunk ahead
+// full/empty mbarrier ring between producer and MMA issuer; tmem_full / tmem_empty mbarriers between issuer and epilogue.
+// gemm_tc2_kernel below is the same pipeline on a CTA pair (tcgen05.mma.cta_group::2, M = 256).
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
@@ -1105,9 +1110,10 @@ int gemm_tc(const TcA& a, const TcW& w, const GemmEpi& e, __nv_bfloat16* out_hi,
             return bn2 == 192 ? launch_tc2<192, 6, EPI_PLAIN>(ta_hi, tb_hi, p, st) : launch_tc2<128, 7, EPI_PLAIN>(ta_hi, tb_hi, p, st);
         }
     }
-    // Tile width and split-K.  The mainloop is operand-feed bound (TMA/L2 -> smem): one k-block of a work item costs ~(128 + BN)
-    // (the 128-row A tile is re-loaded for every N tile); every item pays a fixed prologue/epilogue worth ~6 k-blocks.  Small-M layers
-    // (4x4 / 8x8 latents) split K so that all SMs stream a slice of the weights.  cost = waves * (kb_per_item + 6) * (128 + BN).
+    // Tile width and split-K by a cost model fitted to measured layer times: one k-block of a work item costs ~(128 + BN) (MMA time
+    // grows with BN, the 128-row A tile is re-loaded for every N tile); every item pays a fixed prologue/epilogue worth ~6 k-blocks.
+    // Small-M layers (4x4 / 8x8 latents) split K so that all SMs stream a slice of the weights.
+    // cost = waves * (kb_per_item + 6) * (128 + BN) (+ the reduction).
     p.kb2 = ext ? a.C2 / BK : 0;
     const int mtiles = (M + BM - 1) / BM, sms = 148, nkb_total = p.taps * p.kb_per_tap + p.kb2;
     static const int forced = getenv("RDM_TC_BN") ? atoi(getenv("RDM_TC_BN")) : 0;
