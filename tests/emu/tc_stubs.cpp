@@ -38,3 +38,12 @@ int knn_scan_tc_fused(const void*, const float*, long long, int, const float*, i
 int knn_scan_tc_fused_f32(const void*, const float*, long long, int, const float*, int, int, void*, unsigned long long*, unsigned*, unsigned*, void*, float*, cudaStream_t) {
     return 1;       // not usable under emulation: the caller takes the CUDA-core scan
 }
+
+// ---- test-only entry points (tests/test_engine_identities_host.py): weight-load / first-conv kernels of kernels.cu that no strict-mode
+// forward reaches through the C ABI in isolation.  Pointers are plain host memory (the emulation runs kernels on the host).
+extern "C" int emu_fold_up_weights(const float* w, int N, int C, float* out) { return k_fold_up_weights(w, N, C, out, nullptr); }
+extern "C" int emu_add_vec(const float* a, const float* b, float* out, int n) { return k_add_vec(a, b, out, n, nullptr); }
+extern "C" int emu_conv_first(const float* x, int B, int H, int W, int Cin, const float* w, const float* bias, int Cout, float* out) {
+    if (!k_conv_first_supported(Cin, Cout)) return RDM_ERR_UNSUPPORTED;
+    return k_conv_first(View(const_cast<float*>(x), Cin, Cin), B, H, W, w, bias, Cout, View(out, Cout, Cout), nullptr);
+}

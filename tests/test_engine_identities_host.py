@@ -7,7 +7,11 @@ tests/test_variants_gpu.py, which run both forms of each layer; these tests pin 
   source pixel (y + ty + py - 1, x + tx + px - 1) (zero outside), and GEMM row (b, y, x) is output pixel (b, 2y + py, 2x + px).
   Reference op: ldm Upsample.forward (interpolate nearest x2, then conv) as used by openaimodel.py's output blocks.
 * K extension (csrc/gemm_tc.cuh TcA::hi2): conv2(h) + skip_connection(x) of a ResBlock is ONE contraction over the concatenated K axis
-  [9 * Cout taps of h | Cin channels of x] with the summed bias."""
+  [9 * Cout taps of h | Cin channels of x] with the summed bias.
+
+The last section runs the CUDA kernels of csrc/kernels.cu that prepare those operands (fold_up_weights_kernel, add_vec_kernel) and the
+register-tiled first convolution (conv_first_kernel) AS WRITTEN under the host emulation of tests/emu, through test-only entry points
+(tests/emu/tc_stubs.cpp)."""
 import numpy as np
 import pytest
 import torch
@@ -81,3 +85,52 @@ def test_resblock_tail_is_one_contraction_over_taps_plus_skip_channels(Cin, Cout
     Wm = torch.cat([w2.permute(0, 2, 3, 1).reshape(Cout, 9 * Cout), ws.reshape(Cout, Cin)], dim=1)
     got = (A @ Wm.T + (b2 + bs)).reshape(2, H, H, Cout).permute(0, 3, 1, 2)
     torch.testing.assert_close(got, want, rtol=1e-12, atol=1e-12)
+
+
+# ---- the CUDA kernels themselves (csrc/kernels.cu as written) under the host emulation of tests/emu --------------------------------------
+@pytest.fixture(scope="module")
+def emu():
+    import ctypes, os, shutil, sys
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++ to build the emulated library")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+    import build_emu
+    return ctypes.CDLL(build_emu.build())
+
+
+def _p(a):
+    import ctypes
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+@pytest.mark.parametrize("N,C", [(4, 8), (7, 3), (32, 64)])
+def test_fold_up_weights_kernel_is_the_restated_rule_bit_for_bit(emu, N, C):
+    """fold_up_weights_kernel: input [N][9][C] (the packed conv layout of unet.cu), output [4][N][2*2][C]; fp32 sums in (ky, kx) order."""
+    rng = np.random.default_rng(N * 100 + C)
+    w = rng.standard_normal((N, C, 3, 3)).astype(np.float32)                                      # torch layout
+    packed = np.ascontiguousarray(w.transpose(0, 2, 3, 1).reshape(N, 9, C))                      # reg_conv_w: [cout][tap][cin]
+    out = np.full((4, N, 4, C), np.nan, np.float32)
+    assert emu.emu_fold_up_weights(_p(packed), N, C, _p(out)) == 0
+    want = fold_up_weights(w).reshape(4, N, 4, C)
+    assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
+
+
+def test_add_vec_kernel(emu):
+    a = np.arange(1000, dtype=np.float32) * 0.37; b = np.arange(1000, dtype=np.float32)[::-1].copy() * 1e-3
+    out = np.empty(1000, np.float32)
+    assert emu.emu_add_vec(_p(a), _p(b), _p(out), 1000) == 0
+    assert np.array_equal(out, a + b)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 8, 8, 4, 32), (1, 5, 7, 3, 16), (3, 4, 4, 4, 192), (1, 9, 3, 1, 8), (2, 16, 16, 3, 64)])
+def test_first_convolution_kernel_matches_torch(emu, B, H, W, Cin, Cout):
+    """conv_first_kernel (register-tiled direct 3x3 conv over 1-4 input channels, openaimodel.py:141-145 input_blocks.0.0): ragged pixel
+    counts (the last CTA is partial), K = 27 padded to 28 for three input channels, bias, the zero padding ring."""
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + Cin)
+    x = torch.randn(B, Cin, H, W, generator=g); w = torch.randn(Cout, Cin, 3, 3, generator=g) * 0.3; b = torch.randn(Cout, generator=g)
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1).reshape(B * H * W, Cout).numpy()
+    xn = np.ascontiguousarray(x.permute(0, 2, 3, 1).reshape(B * H * W, Cin).numpy())
+    packed = np.ascontiguousarray(w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).numpy())
+    out = np.full((B * H * W, Cout), np.nan, np.float32)
+    assert emu.emu_conv_first(_p(xn), B, H, W, Cin, _p(packed), _p(b.numpy()), Cout, _p(out)) == 0
+    np.testing.assert_allclose(out, want, rtol=2e-5, atol=2e-5)
